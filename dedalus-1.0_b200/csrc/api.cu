@@ -1,0 +1,542 @@
+// C ABI (include/ddl.h): plan, transforms, fused RHS pipelines, stage updates.
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+
+#include "../../include/ddl.h"
+#include "pointwise.cuh"
+#include "tile_kernel.cuh"
+
+namespace ddl {
+
+// ---------------------------------------------------------------- errors / memory
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void* dev_alloc(size_t bytes) {
+#if DDL_DEVICE_BUILD
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+    return p;
+#else
+    return malloc(bytes ? bytes : 16);
+#endif
+}
+void dev_free(void* p) {
+    if (!p) return;
+#if DDL_DEVICE_BUILD
+    cudaFree(p);
+#else
+    free(p);
+#endif
+}
+int dev_upload(void* dst, const void* src, size_t bytes) {
+#if DDL_DEVICE_BUILD
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -2;
+#else
+    memcpy(dst, src, bytes);
+    return 0;
+#endif
+}
+
+// ---------------------------------------------------------------- per-length kernels
+#define DDL_DECL(N) int run_tile_##N(int, int, int, const TileParams&, int, ddl_stream_t);
+DDL_DECL(8) DDL_DECL(16) DDL_DECL(32) DDL_DECL(64) DDL_DECL(128) DDL_DECL(256) DDL_DECL(512) DDL_DECL(1024)
+DDL_DECL(2048)
+
+static int run_tile(int N, int mode, int dir, int phys, const TileParams& p, int nthreads, ddl_stream_t s) {
+    switch (N) {
+#define DDL_CASE(N) case N: return run_tile_##N(mode, dir, phys, p, nthreads, s);
+        DDL_CASE(8) DDL_CASE(16) DDL_CASE(32) DDL_CASE(64) DDL_CASE(128) DDL_CASE(256) DDL_CASE(512)
+        DDL_CASE(1024) DDL_CASE(2048)
+    }
+    set_error("unsupported transform length %d (powers of two 8..2048)", N);
+    return -1;
+}
+
+template <class T>
+static T* upload_vec(const std::vector<T>& v) {
+    T* d = (T*)dev_alloc(v.size() * sizeof(T));
+    if (d && !v.empty()) dev_upload(d, v.data(), v.size() * sizeof(T));
+    return d;
+}
+
+}  // namespace ddl
+
+using namespace ddl;
+
+// one periodic axis: wavenumbers, mask, compaction tables, twiddles
+struct Axis {
+    int n = 1;          // x-space length
+    int nk = 1;         // stored spectral length (n, or n/2+1 for the half-complex axis)
+    int m = 0;          // retained modes: |index| <= m
+    int cnt = 1;        // retained count: 2m+1 (full axis) or m+1 (half axis)
+    bool half = false;
+    double* kv = nullptr;           // [nk] wavenumber per stored index
+    unsigned char* keep = nullptr;  // [nk]
+    double* kvc = nullptr;          // [cnt] wavenumber per compact index
+    int* c2f = nullptr;             // [cnt] compact -> stored index
+    int* f2c = nullptr;             // [nk] stored -> compact or -1
+    int* f2f = nullptr;             // [nk] stored -> stored or -1
+    cplx* tw = nullptr;             // [n] exp(-2 pi i m / n)
+};
+
+struct ddl_plan {
+    int ndim = 0;
+    Axis ax, ay, az;
+    long long ntot = 1;
+    KGeom geom;          // full k-array geometry
+    long long nmodes = 0;
+    std::vector<void*> owned;
+};
+
+static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv, const uint8_t* keep) {
+    a.n = n; a.half = half; a.nk = half ? n / 2 + 1 : n;
+    if (n < 8 || n > 2048 || (n & (n - 1))) { set_error("axis length %d unsupported (power of two in 8..2048)", n); return -1; }
+    int m = -1;
+    for (int j = 0; j < a.nk; ++j) {
+        int mi = (j <= n / 2) ? j : n - j;
+        if (keep[j] && mi > m) m = mi;
+    }
+    if (m < 0) { set_error("dealias mask removes every mode"); return -1; }
+    if (m >= n / 2) { set_error("dealias mask keeps the Nyquist mode; unsupported"); return -1; }
+    for (int j = 0; j < a.nk; ++j) {
+        int mi = (j <= n / 2) ? j : n - j;
+        if ((keep[j] != 0) != (mi <= m)) { set_error("dealias mask is not of the form |k index| <= m"); return -1; }
+    }
+    a.m = m; a.cnt = half ? m + 1 : 2 * m + 1;
+    std::vector<double> kvh(kv, kv + a.nk), kvc(a.cnt);
+    std::vector<unsigned char> kp(keep, keep + a.nk);
+    std::vector<int> c2f(a.cnt), f2c(a.nk, -1), f2f(a.nk, -1);
+    for (int j = 0; j < a.cnt; ++j) {
+        int f = (j <= m) ? j : j + (a.nk - a.cnt);
+        c2f[j] = f; f2c[f] = j; f2f[f] = f; kvc[j] = kv[f];
+    }
+    std::vector<cplx> tw(n);
+    const long double PI = acosl(-1.0L);
+    for (int q = 0; q < n; ++q) { tw[q].x = (double)cosl(-2 * PI * q / n); tw[q].y = (double)sinl(-2 * PI * q / n); }
+    a.kv = upload_vec(kvh); a.keep = upload_vec(kp); a.kvc = upload_vec(kvc);
+    a.c2f = upload_vec(c2f); a.f2c = upload_vec(f2c); a.f2f = upload_vec(f2f); a.tw = upload_vec(tw);
+    void* all[] = {a.kv, a.keep, a.kvc, a.c2f, a.f2c, a.f2f, a.tw};
+    for (void* p : all) { if (!p) { set_error("device allocation failed"); return -2; } pl->owned.push_back(p); }
+    return 0;
+}
+
+extern "C" int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x, const double* kx, const double* ky,
+                               const double* kz, const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz) {
+    if (!out || (ndim != 2 && ndim != 3)) { set_error("Must use either 2 or 3 dimensions."); return -1; }
+    ddl_plan* pl = new ddl_plan();
+    pl->ndim = ndim;
+    int rc = 0;
+    if (ndim == 3) {
+        rc = build_axis(pl, pl->az, (int)shape_x[0], false, kz, keepz);
+        if (!rc) rc = build_axis(pl, pl->ay, (int)shape_x[1], false, ky, keepy);
+        if (!rc) rc = build_axis(pl, pl->ax, (int)shape_x[2], true, kx, keepx);
+    } else {
+        rc = build_axis(pl, pl->ay, (int)shape_x[0], false, ky, keepy);
+        if (!rc) rc = build_axis(pl, pl->ax, (int)shape_x[1], true, kx, keepx);
+    }
+    if (rc) { ddl_plan_destroy(pl); return rc; }
+    KGeom& g = pl->geom;
+    if (ndim == 3) {
+        pl->ntot = (long long)pl->ax.n * pl->ay.n * pl->az.n;
+        const Axis* lv[3] = {&pl->ay, &pl->az, &pl->ax};
+        const int axid[3] = {1, 2, 0};
+        for (int l = 0; l < 3; ++l) { g.dim[l] = lv[l]->nk; g.kv[l] = lv[l]->kv; g.keep[l] = lv[l]->keep; g.ax[l] = axid[l]; }
+        g.twod = 0;
+    } else {
+        pl->ntot = (long long)pl->ax.n * pl->ay.n;
+        g.dim[0] = 1; g.kv[0] = nullptr; g.keep[0] = nullptr; g.ax[0] = -1;
+        g.dim[1] = pl->ax.nk; g.kv[1] = pl->ax.kv; g.keep[1] = pl->ax.keep; g.ax[1] = 0;
+        g.dim[2] = pl->ay.nk; g.kv[2] = pl->ay.kv; g.keep[2] = pl->ay.keep; g.ax[2] = 1;
+        g.twod = 1;
+    }
+    pl->nmodes = (long long)g.dim[0] * g.dim[1] * g.dim[2];
+    *out = pl;
+    return 0;
+}
+
+extern "C" int ddl_plan_destroy(ddl_plan* pl) {
+    if (!pl) return 0;
+    for (void* p : pl->owned) dev_free(p);
+    delete pl;
+    return 0;
+}
+
+// ---------------------------------------------------------------- workspace layout
+struct WsLayout {
+    long long r0, r1, r2;   // region sizes in cplx elements
+};
+static WsLayout ws_layout(const ddl_plan* pl, int ni, int no) {
+    WsLayout w;
+    const long long CX = pl->ax.cnt, CY = pl->ay.cnt;
+    if (pl->ndim == 3) {
+        const long long CZ = pl->az.cnt, ny = pl->ay.n, nz = pl->az.n;
+        const int nmax = ni > no ? ni : no;
+        w.r0 = nmax * CY * nz * CX;                               // A (inverse) / D (forward): [f][ky_c][z][kx_c]
+        long long b = (long long)ni * nz * ny * CX, e = (long long)no * CY * CZ * CX;
+        w.r1 = b > e ? b : e;                                     // B [f][z][y][kx_c], later E [f][ky_c][kz_c][kx_c]
+        w.r2 = (long long)no * nz * ny * CX;                      // C [f][z][y][kx_c]
+    } else {
+        const long long ny = pl->ay.n;
+        w.r0 = (long long)ni * CX * ny;                           // A [f][kx_c][y]
+        w.r1 = (long long)no * CX * ny;                           // C [f][kx_c][y]
+        w.r2 = (long long)no * CX * CY;                           // E [f][kx_c][ky_c]
+    }
+    return w;
+}
+
+extern "C" size_t ddl_workspace_bytes(const ddl_plan* pl, int n_in, int n_out) {
+    WsLayout w = ws_layout(pl, n_in, n_out);
+    return (size_t)(w.r0 + w.r1 + w.r2) * sizeof(cplx);
+}
+
+static void phys_counts(int ndim, int physics, int& ni, int& no, int& code) {
+    if (ndim == 3) {
+        if (physics == DDL_HYDRO) { ni = 3; no = 6; code = 3; }
+        else if (physics == DDL_BOUSSINESQ) { ni = 4; no = 9; code = 4; }
+        else { ni = 6; no = 9; code = 5; }
+    } else {
+        if (physics == DDL_HYDRO) { ni = 2; no = 3; code = 0; }
+        else if (physics == DDL_BOUSSINESQ) { ni = 3; no = 5; code = 1; }
+        else { ni = 4; no = 4; code = 2; }
+    }
+}
+
+extern "C" size_t ddl_rhs_workspace_bytes(const ddl_plan* pl, int physics) {
+    int ni, no, code;
+    phys_counts(pl->ndim, physics, ni, no, code);
+    return ddl_workspace_bytes(pl, ni, no);
+}
+
+// ---------------------------------------------------------------- pass builders
+static int pick_c2c_group(int N, long long inner_len) {
+    int g = 4096 / N;
+    if (g < 1) g = 1;
+    if (g > 32) g = 32;
+    if (g > inner_len) g = (int)inner_len;
+    return g;
+}
+static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 1024 ? 1024 : t); }
+
+// complex pass of nf fields along an axis of length N
+static int pass_c2c(int N, int dir, int nf, const void* const* in, void* const* out, const TileSide& si,
+                    const TileSide& so, int inner_len, int n_outer, double scale, const cplx* tw, ddl_stream_t st) {
+    TileParams p;
+    memset(&p, 0, sizeof(p));
+    for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
+    p.si = si; p.so = so; p.nf_in = p.nf_out = nf; p.nft = 1;
+    p.G = pick_c2c_group(N, inner_len);
+    p.inner_len = inner_len; p.n_outer = n_outer; p.kn = 0;
+    p.ld = (si.s_n == 1 || so.s_n == 1) ? (p.G | 1) : p.G;
+    p.scale = scale; p.tw = tw;
+    const int rmax = N >= 8 ? 8 : 4;
+    return run_tile(N, TM_C2C, dir, 0, p, round32(p.G * (N / rmax)), st);
+}
+
+// pair-mode pass (C2R / R2C / FUSED) over real lines
+static int pass_pair(int N, int mode, int phys, int ni, int no, const void* const* in, void* const* out,
+                     const TileSide& si, const TileSide& so, int n_lines, int n_outer, int kn, double scale,
+                     const cplx* tw, const PhysConst& pc, ddl_stream_t st) {
+    TileParams p;
+    memset(&p, 0, sizeof(p));
+    for (int f = 0; f < ni; ++f) p.in[f] = in[f];
+    for (int f = 0; f < no; ++f) p.out[f] = out[f];
+    p.si = si; p.so = so; p.nf_in = ni; p.nf_out = no;
+    p.nft = ni > no ? ni : no;
+    int g = 6144 / (N * p.nft);
+    if (g < 1) g = 1;
+    if (g > 16) g = 16;
+    const int pairs = (n_lines + 1) / 2;
+    if (g > pairs) g = pairs;
+    p.G = g;
+    p.inner_len = n_lines; p.n_outer = n_outer; p.kn = kn;
+    p.ld = (g * p.nft) | 1;
+    p.scale = scale; p.tw = tw; p.pc = pc;
+    const int rmax = N >= 8 ? 8 : 4;
+    return run_tile(N, mode, 0, phys, p, round32(g * p.nft * (N / rmax)), st);
+}
+
+static TileSide side(long long s_n, long long s_inner, long long s_outer, const int* n_tab, const int* outer_tab) {
+    TileSide s; s.s_n = s_n; s.s_inner = s_inner; s.s_outer = s_outer; s.n_tab = n_tab; s.outer_tab = outer_tab;
+    return s;
+}
+
+#define DDL_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+// inverse passes up to (not including) the pair pass: state (full k layout) -> half-transformed
+// arrays ready for the pair pass.  3-D: k -> A -> B ; 2-D: k -> A.
+static int inverse_head(ddl_plan* pl, int nf, const void* const* kin, cplx* r0, cplx* r1, void** heads, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+    const long long CX = X.cnt;
+    std::vector<void*> A(nf), B(nf);
+    if (pl->ndim == 3) {
+        const long long KP = X.nk, ny = Y.n, nz = Z.n, CY = Y.cnt;
+        for (int f = 0; f < nf; ++f) { A[f] = r0 + f * CY * nz * CX; B[f] = r1 + f * nz * ny * CX; }
+        // z pass: k[ky][kz][kx] -> A[ky_c][z][kx_c]
+        DDL_TRY(pass_c2c(Z.n, +1, nf, kin, A.data(), side(KP, 1, nz * KP, Z.f2f, Y.c2f), side(CX, 1, nz * CX, nullptr, nullptr),
+                         (int)CX, (int)CY, 1.0, Z.tw, st));
+        // y pass: A[ky_c][z][kx_c] -> B[z][y][kx_c]
+        DDL_TRY(pass_c2c(Y.n, +1, nf, A.data(), B.data(), side(nz * CX, 1, CX, Y.f2c, nullptr), side(CX, 1, ny * CX, nullptr, nullptr),
+                         (int)CX, (int)nz, 1.0, Y.tw, st));
+        for (int f = 0; f < nf; ++f) heads[f] = B[f];
+    } else {
+        const long long ny = Y.n;
+        for (int f = 0; f < nf; ++f) A[f] = r0 + f * CX * ny;
+        // ky pass along contiguous lines: k[kx][ky] -> A[kx_c][y]
+        DDL_TRY(pass_c2c(Y.n, +1, nf, kin, A.data(), side(1, ny, 0, Y.f2f, nullptr), side(1, ny, 0, nullptr, nullptr),
+                         (int)CX, 1, 1.0, Y.tw, st));
+        for (int f = 0; f < nf; ++f) heads[f] = A[f];
+    }
+    return 0;
+}
+
+// forward passes after the pair pass: C -> (D ->) destination.  `full_out`: write straight into
+// full-layout k arrays (transform API) instead of the compact product arrays E.
+static int forward_tail(ddl_plan* pl, int nf, void* const* Cin, cplx* r0, void* const* dst, bool full_out, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+    const long long CX = X.cnt;
+    if (pl->ndim == 3) {
+        const long long KP = X.nk, ny = Y.n, nz = Z.n, CY = Y.cnt, CZ = Z.cnt;
+        std::vector<void*> D(nf);
+        for (int f = 0; f < nf; ++f) D[f] = r0 + f * CY * nz * CX;
+        // y pass: C[z][y][kx_c] -> D[ky_c][z][kx_c]
+        DDL_TRY(pass_c2c(Y.n, -1, nf, Cin, D.data(), side(CX, 1, ny * CX, nullptr, nullptr), side(nz * CX, 1, CX, Y.f2c, nullptr),
+                         (int)CX, (int)nz, 1.0, Y.tw, st));
+        // z pass: D[ky_c][z][kx_c] -> E[ky_c][kz_c][kx_c]  or  k[ky][kz][kx]
+        TileSide so = full_out ? side(KP, 1, nz * KP, Z.f2f, Y.c2f) : side(CX, 1, CZ * CX, Z.f2c, nullptr);
+        DDL_TRY(pass_c2c(Z.n, -1, nf, D.data(), dst, side(CX, 1, nz * CX, nullptr, nullptr), so, (int)CX, (int)CY, 1.0, Z.tw, st));
+    } else {
+        const long long ny = Y.n, CY = Y.cnt;
+        TileSide so = full_out ? side(1, ny, 0, Y.f2f, nullptr) : side(1, CY, 0, Y.f2c, nullptr);
+        DDL_TRY(pass_c2c(Y.n, -1, nf, Cin, dst, side(1, ny, 0, nullptr, nullptr), so, (int)CX, 1, 1.0, Y.tw, st));
+    }
+    return 0;
+}
+
+static int mask_arrays(ddl_plan* pl, int n, void* const* arr, ddl_stream_t st) {
+    MaskF f;
+    f.g = pl->geom;
+    int done = 0;
+    while (done < n) {
+        int c = n - done < DDL_MAXF ? n - done : DDL_MAXF;
+        for (int i = 0; i < c; ++i) f.arr[i] = (cplx*)arr[done + i];
+        f.narr = c;
+        DDL_TRY(launch_items(f, pl->nmodes, st));
+        done += c;
+    }
+    return 0;
+}
+
+static int check_ws(const ddl_plan* pl, int ni, int no, void* work, size_t bytes) {
+    if (!work || bytes < ddl_workspace_bytes(pl, ni, no)) {
+        set_error("workspace too small: %zu < %zu bytes", bytes, ddl_workspace_bytes(pl, ni, no));
+        return -1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- transforms
+extern "C" int ddl_dealias(ddl_plan* pl, void* k, void* stream) {
+    void* arr[1] = {k};
+    return mask_arrays(pl, 1, arr, (ddl_stream_t)stream);
+}
+
+extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t work_bytes, void* stream) {
+    ddl_stream_t st = (ddl_stream_t)stream;
+    DDL_TRY(check_ws(pl, 1, 1, work, work_bytes));
+    DDL_TRY(ddl_dealias(pl, k, stream));
+    WsLayout w = ws_layout(pl, 1, 1);
+    cplx* r0 = (cplx*)work; cplx* r1 = r0 + w.r0;
+    const void* kin[1] = {k};
+    void* head[1];
+    DDL_TRY(inverse_head(pl, 1, kin, r0, r1, head, st));
+    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+    void* xo[1] = {x};
+    PhysConst pc = {};
+    if (pl->ndim == 3)
+        return pass_pair(X.n, TM_C2R, 0, 1, 1, head, xo, side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr),
+                         side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr), Y.n, Z.n, X.cnt, 1.0, X.tw, pc, st);
+    return pass_pair(X.n, TM_C2R, 0, 1, 1, head, xo, side(Y.n, 1, 0, nullptr, nullptr), side(1, X.n, 0, nullptr, nullptr),
+                     Y.n, 1, X.cnt, 1.0, X.tw, pc, st);
+}
+
+extern "C" int ddl_forward(ddl_plan* pl, const double* x, void* k, void* work, size_t work_bytes, void* stream) {
+    ddl_stream_t st = (ddl_stream_t)stream;
+    DDL_TRY(check_ws(pl, 1, 1, work, work_bytes));
+    WsLayout w = ws_layout(pl, 1, 1);
+    cplx* r0 = (cplx*)work; cplx* r2 = r0 + w.r0 + w.r1;
+    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+    const void* xi[1] = {x};
+    void* C[1] = {pl->ndim == 3 ? (void*)r2 : (void*)(r0 + w.r0)};
+    PhysConst pc = {};
+    const double sc = 1.0 / (double)pl->ntot;
+    if (pl->ndim == 3)
+        DDL_TRY(pass_pair(X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr),
+                          side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr), Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
+    else
+        DDL_TRY(pass_pair(X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, 0, nullptr, nullptr), side(Y.n, 1, 0, nullptr, nullptr),
+                          Y.n, 1, X.cnt, sc, X.tw, pc, st));
+    void* dst[1] = {k};
+    DDL_TRY(forward_tail(pl, 1, C, r0, dst, true, st));
+    return ddl_dealias(pl, k, stream);
+}
+
+extern "C" int ddl_deriv(ddl_plan* pl, const void* k_in, void* k_out, int axis, void* stream) {
+    DerivF f;
+    f.g = pl->geom; f.in = (const cplx*)k_in; f.out = (cplx*)k_out; f.level = -1;
+    for (int l = 0; l < 3; ++l) if (pl->geom.ax[l] == axis) f.level = l;
+    if (f.level < 0) { set_error("deriv: bad axis %d", axis); return -1; }
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+}
+
+// ---------------------------------------------------------------- fused RHS
+template <class PHYS>
+static int assemble(ddl_plan* pl, cplx* E, void* const* state, void* const* deriv, const PhysConst& pc, ddl_stream_t st) {
+    AssembleF<PHYS> f;
+    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+    const long long CX = X.cnt, CY = Y.cnt;
+    long long per;
+    if (pl->ndim == 3) {
+        const long long CZ = Z.cnt;
+        per = CY * CZ * CX;
+        f.cdim[0] = (int)CY; f.cdim[1] = (int)CZ; f.cdim[2] = (int)CX;
+        f.cstride[0] = CZ * CX; f.cstride[1] = CX; f.cstride[2] = 1;
+        f.fstride[0] = (long long)Z.n * X.nk; f.fstride[1] = X.nk; f.fstride[2] = 1;
+        f.ftab[0] = Y.c2f; f.ftab[1] = Z.c2f; f.ftab[2] = nullptr;
+        f.kvc[0] = Y.kvc; f.kvc[1] = Z.kvc; f.kvc[2] = X.kvc;
+        f.ax[0] = 1; f.ax[1] = 2; f.ax[2] = 0;
+    } else {
+        per = CX * CY;
+        f.cdim[0] = 1; f.cdim[1] = (int)CX; f.cdim[2] = (int)CY;
+        f.cstride[0] = 0; f.cstride[1] = CY; f.cstride[2] = 1;
+        f.fstride[0] = 0; f.fstride[1] = Y.n; f.fstride[2] = 1;
+        f.ftab[0] = nullptr; f.ftab[1] = nullptr; f.ftab[2] = Y.c2f;
+        f.kvc[0] = nullptr; f.kvc[1] = X.kvc; f.kvc[2] = Y.kvc;
+        f.ax[0] = -1; f.ax[1] = 0; f.ax[2] = 1;
+    }
+    for (int i = 0; i < PHYS::NO; ++i) f.P[i] = E + i * per;
+    for (int i = 0; i < PHYS::NS; ++i) f.S[i] = (const cplx*)state[i];
+    for (int i = 0; i < PHYS::NC; ++i) f.D[i] = (cplx*)deriv[i];
+    f.pc = pc;
+    return launch_items(f, per, st);
+}
+
+extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
+                       void* work, size_t work_bytes, int flags, void* stream) {
+    ddl_stream_t st = (ddl_stream_t)stream;
+    int ni, no, code;
+    if (physics < 0 || physics > 2) { set_error("unknown physics id %d", physics); return -1; }
+    phys_counts(pl->ndim, physics, ni, no, code);
+    DDL_TRY(check_ws(pl, ni, no, work, work_bytes));
+    PhysConst pc;
+    pc.inv_fpr = 1.0 / (4.0 * 3.14159265358979323846 * prm->rho0);
+    pc.g_alpha = prm->g * prm->alpha_t;
+    pc.beta = prm->beta;
+    pc.bdir = prm->boussinesq_dir;
+    if (physics == DDL_BOUSSINESQ && (pc.bdir < 0 || pc.bdir >= pl->ndim)) {
+        set_error("boussinesq_direction component %d not present in %d-D", pc.bdir, pl->ndim);
+        return -1;
+    }
+    const int ncomp = ni;   // state components == inverse transforms in the conservative forms
+    if (flags & DDL_RHS_DEALIAS_STATE) DDL_TRY(mask_arrays(pl, ncomp, state, st));
+    if (flags & DDL_RHS_ZERO_FILL) DDL_TRY(mask_arrays(pl, ncomp, deriv, st));
+
+    WsLayout w = ws_layout(pl, ni, no);
+    cplx* r0 = (cplx*)work; cplx* r1 = r0 + w.r0; cplx* r2 = r1 + w.r1;
+    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+    std::vector<void*> head(ni), C(no), E(no);
+    DDL_TRY(inverse_head(pl, ni, (const void* const*)state, r0, r1, head.data(), st));
+    const double sc = 1.0 / (double)pl->ntot;
+    cplx* Ebase;
+    if (pl->ndim == 3) {
+        const long long per = (long long)Z.n * Y.n * X.cnt, pere = (long long)Y.cnt * Z.cnt * X.cnt;
+        for (int f = 0; f < no; ++f) { C[f] = r2 + f * per; E[f] = r1 + f * pere; }
+        Ebase = r1;
+        TileSide s = side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr);
+        DDL_TRY(pass_pair(X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
+    } else {
+        const long long per = (long long)X.cnt * Y.n, pere = (long long)X.cnt * Y.cnt;
+        for (int f = 0; f < no; ++f) { C[f] = r1 + f * per; E[f] = r2 + f * pere; }
+        Ebase = r2;
+        TileSide s = side(Y.n, 1, 0, nullptr, nullptr);
+        DDL_TRY(pass_pair(X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st));
+    }
+    DDL_TRY(forward_tail(pl, no, C.data(), r0, E.data(), false, st));
+    switch (code) {
+        case 0: return assemble<Hydro2C>(pl, Ebase, state, deriv, pc, st);
+        case 1: return assemble<Bouss2C>(pl, Ebase, state, deriv, pc, st);
+        case 2: return assemble<MHD2C>(pl, Ebase, state, deriv, pc, st);
+        case 3: return assemble<Hydro3C>(pl, Ebase, state, deriv, pc, st);
+        case 4: return assemble<Bouss3C>(pl, Ebase, state, deriv, pc, st);
+        default: return assemble<MHD3C>(pl, Ebase, state, deriv, pc, st);
+    }
+}
+
+// ---------------------------------------------------------------- stage updates
+static int fill_stage(ddl_plan* pl, StageArgs& a, int ncomp, const double* coeff, int vo) {
+    if (ncomp < 1 || ncomp > DDL_MAXC) { set_error("ncomp %d out of range 1..%d", ncomp, DDL_MAXC); return -1; }
+    memset(&a, 0, sizeof(a));
+    a.g = pl->geom; a.ncomp = ncomp; a.vo = vo;
+    for (int c = 0; c < ncomp; ++c) a.coeff[c] = coeff ? coeff[c] : 0.0;
+    return 0;
+}
+
+extern "C" int ddl_stage(ddl_plan* pl, int kind, int ncomp, void* const* start, void* const* out, void* const* d1,
+                         void* const* d2, const double* coeff, int visc_order, double dt, void* stream) {
+    StageF f;
+    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order));
+    if (kind < DDL_EULER || kind > DDL_ETD2RK2) { set_error("bad stage kind %d", kind); return -1; }
+    if ((kind == DDL_ETD2RK1 || kind == DDL_ETD2RK2) && !d2) { set_error("stage kind %d needs deriv2", kind); return -1; }
+    f.a.kind = kind; f.a.dt = dt;
+    for (int c = 0; c < ncomp; ++c) {
+        f.a.start[c] = (const cplx*)start[c]; f.a.out[c] = (cplx*)out[c]; f.a.d1[c] = (const cplx*)d1[c];
+        f.a.d2[c] = d2 ? (const cplx*)d2[c] : nullptr;
+    }
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+}
+
+extern "C" int ddl_rk4_stage(ddl_plan* pl, int ncomp, void* const* y, void* const* k, void* const* total, void* const* out,
+                             const double* coeff, int visc_order, double wdiv, double dt_step, int first, int last,
+                             void* stream) {
+    StageF f;
+    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order));
+    f.a.kind = SK_RK4; f.a.dt = dt_step; f.a.wdiv = wdiv; f.a.first = first; f.a.last = last;
+    for (int c = 0; c < ncomp; ++c) {
+        f.a.start[c] = (const cplx*)y[c]; f.a.out[c] = (cplx*)out[c]; f.a.d1[c] = (const cplx*)k[c];
+        f.a.total[c] = (cplx*)total[c];
+    }
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+}
+
+extern "C" int ddl_cn_step(ddl_plan* pl, int ncomp, void* const* y, void* const* k, const double* coeff, int visc_order,
+                           double dt, void* stream) {
+    StageF f;
+    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order));
+    f.a.kind = SK_CN; f.a.dt = dt;
+    for (int c = 0; c < ncomp; ++c) { f.a.start[c] = (const cplx*)y[c]; f.a.out[c] = (cplx*)y[c]; f.a.d1[c] = (const cplx*)k[c]; }
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+}
+
+extern "C" int ddl_sync(void* stream) {
+#if DDL_DEVICE_BUILD
+    DDL_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+#else
+    (void)stream;
+#endif
+    return 0;
+}
+
+extern "C" const char* ddl_last_error(void) { return g_err; }
+extern "C" const char* ddl_version(void) {
+#if DDL_DEVICE_BUILD
+    return "ddl-b200 0.1 (sm_100a)";
+#else
+    return "ddl-b200 0.1 (host emulation, tests only)";
+#endif
+}

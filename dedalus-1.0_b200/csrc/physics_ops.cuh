@@ -1,0 +1,164 @@
+// Real-space products and spectral assembly for the three physics classes.
+//
+// Conservative ("flux") formulations, algebraically identical to the reference's advective
+// forms on the dealiased, solenoidal subspace (F_min table):
+//   hydro      : inverse u (ndim)          -> forward u_i u_j (sym.)                 physics.py:527-599
+//   Boussinesq : inverse u, T              -> forward u_i u_j, u_j T                 physics.py:664-712
+//   MHD        : inverse u, B              -> forward u_i u_j - B_i B_j/(4 pi rho0), u x B   physics.py:770-819
+// Assembly in k-space:  du/dt = P[-i k_j T_ij (+ g alpha T e_dir)],  P = I - k k/k^2  (k^2(0) := 1,
+// physics.py:588-599, 407-416);  dT/dt = -i k_j (u_j T) - beta u_dir;  dB/dt = i k x E (curlX, :374-405).
+#pragma once
+#include "fft_core.cuh"
+
+namespace ddl {
+
+struct PhysConst {
+    double inv_fpr;    // 1 / (4 pi rho0)                      (physics.py:791)
+    double g_alpha;    // g * alpha_t                           (physics.py:691-694)
+    double beta;       // stratification                        (physics.py:706-708)
+    int bdir;          // buoyancy direction as component index (x=0, y=1, z=2)
+};
+
+enum PhysicsId { PH_HYDRO = 0, PH_BOUSSINESQ = 1, PH_MHD = 2 };
+
+DDL_HD cplx mul_mi(cplx a) { return mk(a.y, -a.x); }   // * (-i)
+DDL_HD cplx mul_pi(cplx a) { return mk(-a.y, a.x); }   // * (+i)
+DDL_HD cplx lin3(double a, cplx x, double b, cplx y, double c, cplx z) {
+    return mk(a * x.x + b * y.x + c * z.x, a * x.y + b * y.y + c * z.y);
+}
+DDL_HD cplx lin2(double a, cplx x, double b, cplx y) { return mk(a * x.x + b * y.x, a * x.y + b * y.y); }
+
+// solenoidal projection of (Nx,Ny,Nz) given real k; k2 already has the k=0 -> 1 substitution
+DDL_HD void project3(cplx& nx, cplx& ny, cplx& nz, double kx, double ky, double kz, double k2) {
+    cplx kn = lin3(kx, nx, ky, ny, kz, nz);
+    double s = 1.0 / k2;
+    kn = scal(kn, s);
+    nx = nx - scal(kn, kx); ny = ny - scal(kn, ky); nz = nz - scal(kn, kz);
+}
+DDL_HD void project2(cplx& nx, cplx& ny, double kx, double ky, double k2) {
+    cplx kn = scal(lin2(kx, nx, ky, ny), 1.0 / k2);
+    nx = nx - scal(kn, kx); ny = ny - scal(kn, ky);
+}
+DDL_HD double k2nz3(double kx, double ky, double kz) {
+    double k2 = ky * ky + kz * kz + kx * kx;     // reference summation order y, z, x
+    return k2 == 0.0 ? 1.0 : k2;
+}
+DDL_HD double k2nz2(double kx, double ky) {
+    double k2 = kx * kx + ky * ky;               // 2-D dict order x, y
+    return k2 == 0.0 ? 1.0 : k2;
+}
+
+// ------------------------------------------------------------------ 3-D hydro
+struct Hydro3C {
+    static constexpr int NI = 3, NO = 6, NS = 0, NC = 3, NDIM = 3;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
+        const double u = in[0], v = in[1], w = in[2];
+        o[0] = u * u; o[1] = u * v; o[2] = u * w; o[3] = v * v; o[4] = v * w; o[5] = w * w;
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx*, cplx* D, double kx, double ky, double kz, const PhysConst&) {
+        cplx nx = mul_mi(lin3(kx, P[0], ky, P[1], kz, P[2]));
+        cplx ny = mul_mi(lin3(kx, P[1], ky, P[3], kz, P[4]));
+        cplx nz = mul_mi(lin3(kx, P[2], ky, P[4], kz, P[5]));
+        project3(nx, ny, nz, kx, ky, kz, k2nz3(kx, ky, kz));
+        D[0] = nx; D[1] = ny; D[2] = nz;
+    }
+};
+
+// ------------------------------------------------------------------ 3-D Boussinesq
+struct Bouss3C {
+    static constexpr int NI = 4, NO = 9, NS = 4, NC = 4, NDIM = 3;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
+        const double u = in[0], v = in[1], w = in[2], T = in[3];
+        o[0] = u * u; o[1] = u * v; o[2] = u * w; o[3] = v * v; o[4] = v * w; o[5] = w * w;
+        o[6] = u * T; o[7] = v * T; o[8] = w * T;
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx* S, cplx* D, double kx, double ky, double kz, const PhysConst& pc) {
+        cplx n[3];
+        n[0] = mul_mi(lin3(kx, P[0], ky, P[1], kz, P[2]));
+        n[1] = mul_mi(lin3(kx, P[1], ky, P[3], kz, P[4]));
+        n[2] = mul_mi(lin3(kx, P[2], ky, P[4], kz, P[5]));
+        n[pc.bdir] = n[pc.bdir] + scal(S[3], pc.g_alpha);
+        project3(n[0], n[1], n[2], kx, ky, kz, k2nz3(kx, ky, kz));
+        D[0] = n[0]; D[1] = n[1]; D[2] = n[2];
+        D[3] = mul_mi(lin3(kx, P[6], ky, P[7], kz, P[8])) - scal(S[pc.bdir], pc.beta);
+    }
+};
+
+// ------------------------------------------------------------------ 3-D MHD
+struct MHD3C {
+    static constexpr int NI = 6, NO = 9, NS = 0, NC = 6, NDIM = 3;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst& pc) {
+        const double u = in[0], v = in[1], w = in[2], a = in[3], b = in[4], c = in[5];
+        const double f = pc.inv_fpr;
+        o[0] = u * u - f * (a * a); o[1] = u * v - f * (a * b); o[2] = u * w - f * (a * c);
+        o[3] = v * v - f * (b * b); o[4] = v * w - f * (b * c); o[5] = w * w - f * (c * c);
+        o[6] = v * c - w * b; o[7] = w * a - u * c; o[8] = u * b - v * a;     // E = u x B
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx*, cplx* D, double kx, double ky, double kz, const PhysConst&) {
+        cplx nx = mul_mi(lin3(kx, P[0], ky, P[1], kz, P[2]));
+        cplx ny = mul_mi(lin3(kx, P[1], ky, P[3], kz, P[4]));
+        cplx nz = mul_mi(lin3(kx, P[2], ky, P[4], kz, P[5]));
+        project3(nx, ny, nz, kx, ky, kz, k2nz3(kx, ky, kz));
+        D[0] = nx; D[1] = ny; D[2] = nz;
+        D[3] = mul_pi(lin2(ky, P[8], -kz, P[7]));
+        D[4] = mul_pi(lin2(kz, P[6], -kx, P[8]));
+        D[5] = mul_pi(lin2(kx, P[7], -ky, P[6]));
+    }
+};
+
+// ------------------------------------------------------------------ 2-D
+struct Hydro2C {
+    static constexpr int NI = 2, NO = 3, NS = 0, NC = 2, NDIM = 2;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
+        o[0] = in[0] * in[0]; o[1] = in[0] * in[1]; o[2] = in[1] * in[1];
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx*, cplx* D, double kx, double ky, double, const PhysConst&) {
+        cplx nx = mul_mi(lin2(kx, P[0], ky, P[1]));
+        cplx ny = mul_mi(lin2(kx, P[1], ky, P[2]));
+        project2(nx, ny, kx, ky, k2nz2(kx, ky));
+        D[0] = nx; D[1] = ny;
+    }
+};
+
+struct Bouss2C {
+    static constexpr int NI = 3, NO = 5, NS = 3, NC = 3, NDIM = 2;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
+        const double u = in[0], v = in[1], T = in[2];
+        o[0] = u * u; o[1] = u * v; o[2] = v * v; o[3] = u * T; o[4] = v * T;
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx* S, cplx* D, double kx, double ky, double, const PhysConst& pc) {
+        cplx n[2];
+        n[0] = mul_mi(lin2(kx, P[0], ky, P[1]));
+        n[1] = mul_mi(lin2(kx, P[1], ky, P[2]));
+        n[pc.bdir] = n[pc.bdir] + scal(S[2], pc.g_alpha);
+        project2(n[0], n[1], kx, ky, k2nz2(kx, ky));
+        D[0] = n[0]; D[1] = n[1];
+        D[2] = mul_mi(lin2(kx, P[3], ky, P[4])) - scal(S[pc.bdir], pc.beta);
+    }
+};
+
+struct MHD2C {
+    static constexpr int NI = 4, NO = 4, NS = 0, NC = 4, NDIM = 2;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst& pc) {
+        const double u = in[0], v = in[1], a = in[2], b = in[3];
+        const double f = pc.inv_fpr;
+        o[0] = u * u - f * (a * a); o[1] = u * v - f * (a * b); o[2] = v * v - f * (b * b);
+        o[3] = u * b - v * a;                                                  // E_z
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx*, cplx* D, double kx, double ky, double, const PhysConst&) {
+        cplx nx = mul_mi(lin2(kx, P[0], ky, P[1]));
+        cplx ny = mul_mi(lin2(kx, P[1], ky, P[2]));
+        project2(nx, ny, kx, ky, k2nz2(kx, ky));
+        D[0] = nx; D[1] = ny;
+        D[2] = mul_pi(scal(P[3], ky));       // dBx/dt =  d_y E_z
+        D[3] = mul_mi(scal(P[3], kx));       // dBy/dt = -d_x E_z
+    }
+};
+
+// identity policy for the plain real<->complex transforms
+struct PhysNone {
+    static constexpr int NI = 1, NO = 1, NS = 0, NC = 1, NDIM = 0;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst&) { o[0] = in[0]; }
+};
+
+}  // namespace ddl

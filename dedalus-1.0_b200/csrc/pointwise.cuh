@@ -1,0 +1,234 @@
+// Pointwise spectral kernels: RK stage updates with in-register integrating factors,
+// spectral assembly (derivatives, curl, solenoidal projection), dealias mask, ik-derivative.
+//
+// Replaces dedalus/time_stepping/forward_step_cy_{2d,3d}.pyx (euler/etd1/etd2rk1/etd2rk2),
+// dedalus/data_objects/dealias_cy_{2d,3d}.pyx, representations.py:419-425 (deriv) and the
+// numpy passes of physics.py:180-195,374-416,588-599.
+#pragma once
+#include <cmath>
+
+#include "ddl_common.cuh"
+#include "physics_ops.cuh"
+
+namespace ddl {
+
+// A k-space array seen as three nested levels (level 2 fastest):
+//   3-D: [ny][nz][nx/2+1] -> levels (y, z, x);   2-D: [1][nx/2+1][ny] -> levels (-, x, y)
+struct KGeom {
+    int dim[3];                 // full extents per level
+    const double* kv[3];        // wavenumber value per full index (NULL for an absent level)
+    const unsigned char* keep[3];  // 1 = survives dealiasing
+    int ax[3];                  // level -> component index (x=0,y=1,z=2), -1 = absent
+    int twod;
+};
+
+DDL_HD void split3(long long i, const int* dim, int& a, int& b, int& c) {
+    c = (int)(i % dim[2]);
+    long long r = i / dim[2];
+    b = (int)(r % dim[1]);
+    a = (int)(r / dim[1]);
+}
+
+// sum k^2 in the reference's order (representations.py:434-436: dict order y,z,x / x,y)
+DDL_HD double ksq(const KGeom& g, int a, int b, int c) {
+    double k2 = 0.0;
+    if (g.kv[0]) { double v = g.kv[0][a]; k2 += v * v; }
+    { double v = g.kv[1][b]; k2 += v * v; }
+    { double v = g.kv[2][c]; k2 += v * v; }
+    return k2;
+}
+
+DDL_HD double ipow(double x, int n) {
+    if (n == 1) return x;
+    if (n == 2) return x * x;
+    return pow(x, (double)n);
+}
+
+// phi functions of the ETD schemes, branch structure of forward_step_cy_3d.pyx:50-59 /
+// forward_step_cy_2d.pyx:50-60 (|Z| < 0.5: Taylor to Z^14/14!; else closed forms).
+DDL_HD void phi_funcs(double Z, int twod, double& f0, double& f1, double& f2) {
+    if (Z < 0.5 && Z > -0.5) {
+        // 1/j!, j = 0..14
+        const double r[15] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                              1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0,
+                              1.0 / 87178291200.0};
+        double a1 = r[14], a2 = r[14], a0 = r[14];
+#pragma unroll
+        for (int j = 13; j >= 2; --j) { a2 = a2 * Z + r[j]; }
+#pragma unroll
+        for (int j = 13; j >= 1; --j) { a1 = a1 * Z + r[j]; }
+        f1 = a1; f2 = a2;
+        if (twod) {
+#pragma unroll
+            for (int j = 13; j >= 0; --j) { a0 = a0 * Z + r[j]; }
+            f0 = a0;
+        } else {
+            f0 = exp(Z);
+        }
+    } else {
+        f0 = exp(Z);
+        f1 = (f0 - 1.0) / Z;
+        f2 = (f1 - 1.0) / Z;
+    }
+}
+
+struct StageArgs {
+    KGeom g;
+    cplx* out[DDL_MAXC];
+    const cplx* start[DDL_MAXC];
+    const cplx* d1[DDL_MAXC];
+    const cplx* d2[DDL_MAXC];
+    cplx* total[DDL_MAXC];
+    double coeff[DDL_MAXC];
+    int ncomp, kind, vo, first, last;
+    double dt, wdiv;
+};
+
+enum { SK_EULER = 0, SK_ETD1 = 1, SK_ETD2RK1 = 2, SK_ETD2RK2 = 3, SK_RK4 = 4, SK_CN = 5 };
+
+DDL_HD cplx etd1_step(cplx s, cplx d, double Z, double f0, double f1, double dt) {
+    if (Z == 0.0) return mk(s.x + dt * d.x, s.y + dt * d.y);
+    const double a = f1 * dt;
+    return mk(s.x * f0 + d.x * a, s.y * f0 + d.y * a);
+}
+
+struct StageF {
+    StageArgs a;
+    DDL_HD void operator()(long long i) const {
+        int ia, ib, ic;
+        split3(i, a.g.dim, ia, ib, ic);
+        const double pw = ipow(ksq(a.g, ia, ib, ic), a.vo);
+        double lastc = -1.0, Z = 0.0, f0 = 1.0, f1 = 1.0, f2 = 0.5;
+        for (int c = 0; c < a.ncomp; ++c) {
+            const double co = a.coeff[c];
+            if (a.kind != SK_EULER && co != lastc) {
+                lastc = co;
+                Z = -(co * pw) * a.dt;
+                if (Z != 0.0 && a.kind != SK_CN) phi_funcs(Z, a.g.twod, f0, f1, f2);
+            }
+            const double dt = a.dt;
+            if (a.kind == SK_EULER) {
+                cplx s = a.start[c][i], d = a.d1[c][i];
+                a.out[c][i] = mk(s.x + dt * d.x, s.y + dt * d.y);
+            } else if (a.kind == SK_ETD1) {
+                a.out[c][i] = etd1_step(a.start[c][i], a.d1[c][i], Z, f0, f1, dt);
+            } else if (a.kind == SK_ETD2RK1) {
+                cplx s = a.start[c][i], p = a.d1[c][i], q = a.d2[c][i];
+                const double w = (Z == 0.0) ? dt / 2.0 : f2 * dt;
+                a.out[c][i] = mk(s.x + (q.x - p.x) * w, s.y + (q.y - p.y) * w);
+            } else if (a.kind == SK_ETD2RK2) {
+                cplx s = a.start[c][i], p = a.d1[c][i], q = a.d2[c][i];
+                if (Z == 0.0) {
+                    a.out[c][i] = mk(s.x + dt * q.x, s.y + dt * q.y);
+                } else {
+                    const double w2 = 2.0 * f2 * dt, w1 = f1 * dt;
+                    a.out[c][i] = mk(s.x * f0 + (q.x - p.x) * w2 + p.x * w1, s.y * f0 + (q.y - p.y) * w2 + p.y * w1);
+                }
+            } else if (a.kind == SK_RK4) {
+                cplx kk = a.d1[c][i];
+                cplx t = mk(kk.x / a.wdiv, kk.y / a.wdiv);
+                if (!a.first) { cplx o = a.total[c][i]; t = mk(o.x + t.x, o.y + t.y); }
+                if (!a.last) a.total[c][i] = t;
+                a.out[c][i] = etd1_step(a.start[c][i], a.last ? t : kk, Z, f0, f1, dt);
+            } else {  // SK_CN
+                const double IF = co * pw;
+                const double top = 1.0 / dt - 0.5 * IF, bottom = 1.0 / dt + 0.5 * IF;
+                const double r1 = top / bottom, r2 = 1.0 / bottom;
+                cplx s = a.start[c][i], d = a.d1[c][i];
+                a.out[c][i] = mk(r1 * s.x + r2 * d.x, r1 * s.y + r2 * d.y);
+            }
+        }
+    }
+};
+
+// zero the masked-out modes of up to DDL_MAXF arrays, touching only those entries
+struct MaskF {
+    KGeom g;
+    cplx* arr[DDL_MAXF];
+    int narr;
+    DDL_HD void operator()(long long i) const {
+        int ia, ib, ic;
+        split3(i, g.dim, ia, ib, ic);
+        bool keep = g.keep[1][ib] && g.keep[2][ic];
+        if (g.keep[0]) keep = keep && g.keep[0][ia];
+        if (!keep) {
+            for (int f = 0; f < narr; ++f) arr[f][i] = mk(0.0, 0.0);
+        }
+    }
+};
+
+struct DerivF {
+    KGeom g;
+    const cplx* in;
+    cplx* out;
+    int level;
+    DDL_HD void operator()(long long i) const {
+        int idx[3];
+        split3(i, g.dim, idx[0], idx[1], idx[2]);
+        const double k = g.kv[level][idx[level]];
+        cplx v = in[i];
+        out[i] = mk(-v.y * k, v.x * k);
+    }
+};
+
+// spectral assembly over the retained modes: compact product arrays -> full deriv arrays
+template <class PHYS>
+struct AssembleF {
+    const cplx* P[PHYS::NO];            // compact [c0][c1][pitch]
+    const cplx* S[PHYS::NS ? PHYS::NS : 1];   // state (full layout)
+    cplx* D[PHYS::NC];                  // deriv (full layout)
+    int cdim[3];                        // compact extents per level
+    long long cstride[3];               // compact strides per level
+    long long fstride[3];               // full strides per level
+    const int* ftab[3];                 // compact -> full index per level (NULL = identity)
+    const double* kvc[3];               // wavenumber per COMPACT index per level
+    int ax[3];
+    PhysConst pc;
+    DDL_HD void operator()(long long i) const {
+        int j[3];
+        split3(i, cdim, j[0], j[1], j[2]);
+        long long ci = 0, fi = 0;
+        double kk[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            ci += j[l] * cstride[l];
+            fi += (long long)(ftab[l] ? ftab[l][j[l]] : j[l]) * fstride[l];
+            if (ax[l] >= 0) kk[ax[l]] = kvc[l][j[l]];
+        }
+        cplx p[PHYS::NO], s[PHYS::NS ? PHYS::NS : 1], d[PHYS::NC];
+#pragma unroll
+        for (int f = 0; f < PHYS::NO; ++f) p[f] = P[f][ci];
+#pragma unroll
+        for (int f = 0; f < PHYS::NS; ++f) s[f] = S[f][fi];
+        PHYS::assemble(p, s, d, kk[0], kk[1], kk[2], pc);
+#pragma unroll
+        for (int f = 0; f < PHYS::NC; ++f) D[f][fi] = d[f];
+    }
+};
+
+#if DDL_DEVICE_BUILD
+template <class F>
+__global__ void items_kernel(const __grid_constant__ F f, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) f(i);
+}
+#endif
+
+template <class F>
+int launch_items(const F& f, long long count, ddl_stream_t stream) {
+    if (count <= 0) return 0;
+#if DDL_DEVICE_BUILD
+    const int threads = 256;
+    long long blocks = (count + threads - 1) / threads;
+    const long long cap = 148LL * 16;
+    if (blocks > cap) blocks = cap;
+    items_kernel<F><<<(unsigned)blocks, threads, 0, stream>>>(f, count);
+    DDL_CUDA_CHECK(cudaGetLastError());
+#else
+    (void)stream;
+    for (long long i = 0; i < count; ++i) f(i);
+#endif
+    return 0;
+}
+
+}  // namespace ddl

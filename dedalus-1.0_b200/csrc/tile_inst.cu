@@ -1,0 +1,35 @@
+// Instantiates the generic tile kernel for ONE transform length (compile with -DDDL_N=<N>);
+// one translation unit per length so the build parallelises.
+#include "tile_kernel.cuh"
+
+#ifndef DDL_N
+#error "compile with -DDDL_N=<transform length>"
+#endif
+#define DDL_CAT2(a, b) a##b
+#define DDL_CAT(a, b) DDL_CAT2(a, b)
+
+namespace ddl {
+
+int DDL_CAT(run_tile_, DDL_N)(int mode, int dir, int phys, const TileParams& p, int nthreads, ddl_stream_t s) {
+    constexpr int N = DDL_N;
+    switch (mode) {
+        case TM_C2C:
+            return dir < 0 ? launch_tile<N, TM_C2C, -1, PhysNone>(p, nthreads, s)
+                           : launch_tile<N, TM_C2C, +1, PhysNone>(p, nthreads, s);
+        case TM_C2R: return launch_tile<N, TM_C2R, +1, PhysNone>(p, nthreads, s);
+        case TM_R2C: return launch_tile<N, TM_R2C, -1, PhysNone>(p, nthreads, s);
+        case TM_FUSED:
+            switch (phys) {
+                case 0: return launch_tile<N, TM_FUSED, 0, Hydro2C>(p, nthreads, s);
+                case 1: return launch_tile<N, TM_FUSED, 0, Bouss2C>(p, nthreads, s);
+                case 2: return launch_tile<N, TM_FUSED, 0, MHD2C>(p, nthreads, s);
+                case 3: return launch_tile<N, TM_FUSED, 0, Hydro3C>(p, nthreads, s);
+                case 4: return launch_tile<N, TM_FUSED, 0, Bouss3C>(p, nthreads, s);
+                case 5: return launch_tile<N, TM_FUSED, 0, MHD3C>(p, nthreads, s);
+            }
+    }
+    set_error("run_tile: bad mode/physics %d/%d", mode, phys);
+    return -1;
+}
+
+}  // namespace ddl

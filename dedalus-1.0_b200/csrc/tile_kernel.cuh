@@ -1,0 +1,251 @@
+// Generic tiled pencil-FFT kernel (all axis passes of the 2-D / 3-D transforms and the fused
+// "inverse -> real-space products -> forward" middle pass).
+//
+// One CTA owns a tile of pencils along the transform axis, staged in shared memory as
+// tile[row*ld + c].  Four modes:
+//   TM_C2C   : complex pass along a strided or contiguous axis (pruned rows via index tables)
+//   TM_C2R   : half-complex spectra of a PAIR of adjacent real lines packed into one complex
+//              pencil (z = a + i b), inverse transform, store the two real lines
+//   TM_R2C   : the mirror (forward)
+//   TM_FUSED : Hermitian pack -> inverse (DIF) -> PHYS::apply at every grid point ->
+//              forward (DIT) -> unpack; the real-space fields never touch HBM
+// Replaces, per transform, fftw rPlan execute + "/= N" + dealias passes of the reference
+// (dedalus/data_objects/representations.py:318-357, dealias_cy_3d.pyx:13-46).
+#pragma once
+#include "ddl_common.cuh"
+#include "physics_ops.cuh"
+
+namespace ddl {
+
+enum TileMode { TM_C2C = 0, TM_C2R = 1, TM_R2C = 2, TM_FUSED = 3 };
+
+struct TileSide {
+    long long s_n, s_inner, s_outer;   // element strides: transform axis, pencil (inner) index, outer index
+    const int* n_tab;                  // spectral side: logical row -> stored row, -1 = absent (zero / skip); NULL = identity
+    const int* outer_tab;              // outer index -> stored outer index; NULL = identity
+};
+
+struct TileParams {
+    const void* in[DDL_MAXF];
+    void* out[DDL_MAXF];
+    TileSide si, so;
+    int nf_in, nf_out;    // fields read / written (TM_C2C: one field per blockIdx.z)
+    int nft;              // pencil slots per group inside the tile (>= max(nf_in, nf_out))
+    int G;                // TM_C2C: pencils per tile; pair modes: line PAIRS per tile
+    int inner_len;        // TM_C2C: number of pencils; pair modes: number of real lines
+    int n_outer;
+    int kn;               // pair modes: stored non-negative modes along the transform axis
+    int ld;               // tile leading dimension
+    double scale;
+    const cplx* tw;
+    PhysConst pc;
+};
+
+template <int N, int S_IDX, int DIR, bool DIT>
+DDL_BODY void stage_all(cplx* tile, int ld, int nfa, int nft, int G, const cplx* __restrict__ tw) {
+    constexpr int R = Fac<N>::radix(S_IDX);
+    const int items = nfa * G * (N / R);
+    DDL_FOR_ITEMS(i, items) {
+        const int f = i % nfa, t = i / nfa;
+        const int g = t % G, w = t / G;
+        stage_item<N, S_IDX, DIR, DIT>(tile, ld, g * nft + f, w, tw);
+    }
+}
+
+// natural in -> scrambled out; the caller has synchronised after filling the tile
+template <int N, int DIR, int S_IDX = 0>
+DDL_BODY void tile_fft_dif(cplx* tile, int ld, int nfa, int nft, int G, const cplx* __restrict__ tw) {
+    stage_all<N, S_IDX, DIR, false>(tile, ld, nfa, nft, G, tw);
+    DDL_SYNC();
+    if constexpr (S_IDX + 1 < Fac<N>::S) tile_fft_dif<N, DIR, S_IDX + 1>(tile, ld, nfa, nft, G, tw);
+}
+
+// scrambled in -> natural out
+template <int N, int DIR, int S_IDX = Fac<N>::S - 1>
+DDL_BODY void tile_fft_dit(cplx* tile, int ld, int nfa, int nft, int G, const cplx* __restrict__ tw) {
+    stage_all<N, S_IDX, DIR, true>(tile, ld, nfa, nft, G, tw);
+    DDL_SYNC();
+    if constexpr (S_IDX > 0) tile_fft_dit<N, DIR, S_IDX - 1>(tile, ld, nfa, nft, G, tw);
+}
+
+DDL_HD long long outer_off(const TileSide& s, int o) {
+    return (long long)(s.outer_tab ? s.outer_tab[o] : o) * s.s_outer;
+}
+
+template <int N, int MODE, int DIR, class PHYS>
+DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz) {
+    const int ld = p.ld;
+    const cplx* __restrict__ tw = p.tw;
+
+    if constexpr (MODE == TM_C2C) {
+        const cplx* __restrict__ in = (const cplx*)p.in[bz];
+        cplx* __restrict__ out = (cplx*)p.out[bz];
+        const int i0 = bx * p.G;
+        const int npc = (p.inner_len - i0) < p.G ? (p.inner_len - i0) : p.G;
+        const long long ib = outer_off(p.si, by) + (long long)i0 * p.si.s_inner;
+        const long long ob = outer_off(p.so, by) + (long long)i0 * p.so.s_inner;
+        const bool in_nfast = (p.si.s_n == 1);
+        DDL_FOR_ITEMS(i, N * npc) {
+            int n, c;
+            if (in_nfast) { n = i % N; c = i / N; } else { c = i % npc; n = i / npc; }
+            const int pn = p.si.n_tab ? p.si.n_tab[n] : n;
+            cplx v = mk(0.0, 0.0);
+            if (pn >= 0) v = in[ib + (long long)pn * p.si.s_n + (long long)c * p.si.s_inner];
+            tile[n * ld + c] = v;
+        }
+        DDL_SYNC();
+        tile_fft_dif<N, DIR>(tile, ld, 1, 1, npc, tw);
+        const bool out_nfast = (p.so.s_n == 1);
+        const double sc = p.scale;
+        DDL_FOR_ITEMS(i, N * npc) {
+            int k, c, pos;
+            if (out_nfast) { k = i % N; c = i / N; pos = pos_of_index<N>(k); }
+            else { c = i % npc; pos = i / npc; k = index_of_pos<N>(pos); }
+            const int pk = p.so.n_tab ? p.so.n_tab[k] : k;
+            if (pk >= 0) out[ob + (long long)pk * p.so.s_n + (long long)c * p.so.s_inner] = scal(tile[pos * ld + c], sc);
+        }
+    } else {
+        constexpr int NI = PHYS::NI, NO = PHYS::NO;
+        const int nft = p.nft;
+        const int line0 = bx * 2 * p.G;
+        int ng = (p.inner_len - line0 + 1) / 2;
+        if (ng > p.G) ng = p.G;
+        const long long ib = outer_off(p.si, by), ob = outer_off(p.so, by);
+
+        if constexpr (MODE == TM_C2R || MODE == TM_FUSED) {
+            // Hermitian pack of line pairs: Z[k] = A[k] + i B[k], Z[N-k] = conj(A[k]) + i conj(B[k])
+            constexpr int H = N / 2 + 1;
+            const bool nfast = (p.si.s_n == 1);
+            DDL_FOR_ITEMS(i, H * ng * NI) {
+                int k, g, f;
+                if (nfast) { k = i % H; int r = i / H; f = r % NI; g = r / NI; }
+                else { g = i % ng; int r = i / ng; k = r % H; f = r / H; }
+                const int l0 = line0 + 2 * g, l1 = l0 + 1;
+                cplx A = mk(0.0, 0.0), B = mk(0.0, 0.0);
+                if (k < p.kn) {
+                    const int pk = p.si.n_tab ? p.si.n_tab[k] : k;
+                    if (pk >= 0) {
+                        const cplx* __restrict__ src = (const cplx*)p.in[f];
+                        const long long a = ib + (long long)pk * p.si.s_n;
+                        A = src[a + (long long)l0 * p.si.s_inner];
+                        if (l1 < p.inner_len) B = src[a + (long long)l1 * p.si.s_inner];
+                    }
+                }
+                const int c = g * nft + f;
+                if (k == 0 || 2 * k == N) {
+                    tile[k * ld + c] = mk(A.x, B.x);
+                } else {
+                    tile[k * ld + c] = mk(A.x - B.y, A.y + B.x);
+                    tile[(N - k) * ld + c] = mk(A.x + B.y, B.x - A.y);
+                }
+            }
+            DDL_SYNC();
+            tile_fft_dif<N, +1>(tile, ld, NI, nft, ng, tw);
+        }
+
+        if constexpr (MODE == TM_R2C) {
+            const bool nfast = (p.si.s_n == 1);
+            DDL_FOR_ITEMS(i, N * ng * NI) {
+                int n, g, f;
+                if (nfast) { n = i % N; int r = i / N; f = r % NI; g = r / NI; }
+                else { g = i % ng; int r = i / ng; n = r % N; f = r / N; }
+                const int l0 = line0 + 2 * g, l1 = l0 + 1;
+                const double* __restrict__ src = (const double*)p.in[f];
+                const long long a = ib + (long long)n * p.si.s_n;
+                const double va = src[a + (long long)l0 * p.si.s_inner];
+                const double vb = (l1 < p.inner_len) ? src[a + (long long)l1 * p.si.s_inner] : 0.0;
+                tile[pos_of_index<N>(n) * ld + g * nft + f] = mk(va, vb);
+            }
+            DDL_SYNC();
+        }
+
+        if constexpr (MODE == TM_FUSED) {
+            // real-space products at every grid point of both lines of the pair
+            DDL_FOR_ITEMS(i, N * ng) {
+                const int g = i % ng, pos = i / ng;
+                cplx* row = tile + pos * ld + g * nft;
+                double ax[NI], ay[NI], ox[NO], oy[NO];
+#pragma unroll
+                for (int f = 0; f < NI; ++f) { cplx v = row[f]; ax[f] = v.x; ay[f] = v.y; }
+                PHYS::apply(ax, ox, p.pc);
+                PHYS::apply(ay, oy, p.pc);
+#pragma unroll
+                for (int f = 0; f < NO; ++f) row[f] = mk(ox[f], oy[f]);
+            }
+            DDL_SYNC();
+        }
+
+        if constexpr (MODE == TM_R2C || MODE == TM_FUSED) {
+            tile_fft_dit<N, -1>(tile, ld, NO, nft, ng, tw);
+            const bool nfast = (p.so.s_n == 1);
+            const double h = 0.5 * p.scale;
+            const int kn = p.kn;
+            DDL_FOR_ITEMS(i, kn * ng * NO) {
+                int k, g, f;
+                if (nfast) { k = i % kn; int r = i / kn; f = r % NO; g = r / NO; }
+                else { g = i % ng; int r = i / ng; k = r % kn; f = r / kn; }
+                const int pk = p.so.n_tab ? p.so.n_tab[k] : k;
+                if (pk < 0) continue;
+                const int c = g * nft + f;
+                const cplx Zk = tile[k * ld + c], Zm = tile[((N - k) % N) * ld + c];
+                const int l0 = line0 + 2 * g, l1 = l0 + 1;
+                cplx* __restrict__ dst = (cplx*)p.out[f];
+                const long long a = ob + (long long)pk * p.so.s_n;
+                dst[a + (long long)l0 * p.so.s_inner] = mk((Zk.x + Zm.x) * h, (Zk.y - Zm.y) * h);
+                if (l1 < p.inner_len) dst[a + (long long)l1 * p.so.s_inner] = mk((Zk.y + Zm.y) * h, (Zm.x - Zk.x) * h);
+            }
+        }
+
+        if constexpr (MODE == TM_C2R) {
+            const bool nfast = (p.so.s_n == 1);
+            const double sc = p.scale;
+            DDL_FOR_ITEMS(i, N * ng * NI) {
+                int n, g, f;
+                if (nfast) { n = i % N; int r = i / N; f = r % NI; g = r / NI; }
+                else { g = i % ng; int r = i / ng; n = r % N; f = r / N; }
+                const int l0 = line0 + 2 * g, l1 = l0 + 1;
+                const cplx z = tile[pos_of_index<N>(n) * ld + g * nft + f];
+                double* __restrict__ dst = (double*)p.out[f];
+                const long long a = ob + (long long)n * p.so.s_n;
+                dst[a + (long long)l0 * p.so.s_inner] = z.x * sc;
+                if (l1 < p.inner_len) dst[a + (long long)l1 * p.so.s_inner] = z.y * sc;
+            }
+        }
+    }
+}
+
+#if DDL_DEVICE_BUILD
+template <int N, int MODE, int DIR, class PHYS>
+__global__ void tile_kernel(const __grid_constant__ TileParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tile_block<N, MODE, DIR, PHYS>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y, blockIdx.z);
+}
+#endif
+
+// Launch geometry + dispatch.  Returns 0 or a negative error code.
+template <int N, int MODE, int DIR, class PHYS>
+int launch_tile(const TileParams& p, int nthreads, ddl_stream_t stream) {
+    const int per_tile = (MODE == TM_C2C) ? p.G : 2 * p.G;
+    const int gx = (p.inner_len + per_tile - 1) / per_tile;
+    const int gz = (MODE == TM_C2C) ? p.nf_in : 1;
+    const int np = (MODE == TM_C2C) ? p.G : p.G * p.nft;
+    if (p.ld < np) { set_error("launch_tile: ld %d < pencils %d", p.ld, np); return -1; }
+    const size_t smem = (size_t)N * p.ld * sizeof(cplx);
+#if DDL_DEVICE_BUILD
+    auto kern = tile_kernel<N, MODE, DIR, PHYS>;
+    if (smem > 48 * 1024) DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(gx, p.n_outer, gz);
+    kern<<<grid, nthreads, smem, stream>>>(p);
+    DDL_CUDA_CHECK(cudaGetLastError());
+#else
+    (void)nthreads; (void)stream;
+    cplx* tile = (cplx*)malloc(smem);
+    for (int bz = 0; bz < gz; ++bz)
+        for (int by = 0; by < p.n_outer; ++by)
+            for (int bx = 0; bx < gx; ++bx) tile_block<N, MODE, DIR, PHYS>(p, tile, bx, by, bz);
+    free(tile);
+#endif
+    return 0;
+}
+
+}  // namespace ddl

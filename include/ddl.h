@@ -1,0 +1,105 @@
+/* ddl.h -- C ABI of the B200-native pseudospectral RHS + timestep library (libddl_b200.so).
+ *
+ * Drop-in boundary for the hot path of jsoishi/dedalus-1.0 (paths below are relative to the
+ * reference tree).  Every entry point takes raw DEVICE pointers (storage is owned by the
+ * caller -- torch tensors in the Python host layer), enqueues work on the given cudaStream_t
+ * and returns immediately: 0 on success, a negative code on error with the text available
+ * from ddl_last_error().  Nothing allocates per call; nothing synchronises (ddl_sync only).
+ *
+ * Layouts (dedalus/data_objects/representations.py:84-93,174-176):
+ *   3-D  x-space double [nz][ny][nx]            k-space complex128 [ny][nz][nx/2+1]
+ *   2-D  x-space double [ny][nx]                k-space complex128 [nx/2+1][ny]
+ * Forward transforms are normalised by 1/N_total, inverse unnormalised (:321,:329,:333).
+ */
+#ifndef DDL_H
+#define DDL_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ddl_plan ddl_plan;
+
+/* physics ids (dedalus/physics/physics.py:419,612,724) */
+enum { DDL_HYDRO = 0, DDL_BOUSSINESQ = 1, DDL_MHD = 2 };
+
+/* stage-update kinds (dedalus/time_stepping/forward_step_cy_3d.pyx:17,34,63,95) */
+enum { DDL_EULER = 0, DDL_ETD1 = 1, DDL_ETD2RK1 = 2, DDL_ETD2RK2 = 3 };
+
+/* ddl_rhs flags */
+enum {
+    DDL_RHS_ZERO_FILL = 1,      /* also write zeros to the masked-out modes of deriv */
+    DDL_RHS_DEALIAS_STATE = 2   /* zero the masked-out modes of the input state in place
+                                   (what IncompressibleMHD does to it, physics.py:797-815 via
+                                   representations.py:353) */
+};
+
+typedef struct ddl_phys_params {
+    double rho0;        /* physics.py:753 */
+    double g, alpha_t, beta;  /* physics.py:643-645 */
+    int boussinesq_dir; /* component index of boussinesq_direction: x=0, y=1, z=2 (physics.py:646) */
+    int reserved;
+} ddl_phys_params;
+
+/* Plan = wavenumbers, dealias mask, twiddles, index tables.  Replaces
+ * fftw.create_data / fftw.rPlan (dedalus/utils/fftw/_fftw.pyx:81-185,246-309),
+ * FourierRepresentation._setup_k and set_dealiasing (representations.py:204-233,359-382).
+ *   shape_x  : x-space shape, (nz,ny,nx) or (ny,nx); powers of two >= 8
+ *   kx,ky,kz : the wavenumber VALUES along each axis exactly as the host computed them
+ *              (kx: nx/2+1 entries, ky: ny, kz: nz; kz NULL in 2-D)
+ *   keepx..  : 1 where the mode survives the dealias mask on that axis, 0 where it is zeroed
+ *              (must be of the form |index| <= m on every axis)                              */
+int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x,
+                    const double* kx, const double* ky, const double* kz,
+                    const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz);
+int ddl_plan_destroy(ddl_plan* plan);
+
+/* scratch requirement of ddl_rhs / ddl_forward / ddl_backward for n_in inverse and n_out
+ * forward transforms in flight (the transforms use n_in = n_out = 1) */
+size_t ddl_workspace_bytes(const ddl_plan* plan, int n_in, int n_out);
+size_t ddl_rhs_workspace_bytes(const ddl_plan* plan, int physics);
+
+/* representations.py:335-345 forward(): x -> k, normalised, transposed out, dealiased */
+int ddl_forward(ddl_plan* plan, const double* x, void* k, void* work, size_t work_bytes, void* stream);
+/* representations.py:347-357 backward(): dealias k IN PLACE, then k -> x (unnormalised) */
+int ddl_backward(ddl_plan* plan, void* k, double* x, void* work, size_t work_bytes, void* stream);
+/* dealias_cy_{2,3}d.pyx dealias_23 / representations.py:442-455 zero_nyquist, in place */
+int ddl_dealias(ddl_plan* plan, void* k, void* stream);
+/* representations.py:419-425 deriv(): out = i * k_axis * in   (axis: 0=x, 1=y, 2=z) */
+int ddl_deriv(ddl_plan* plan, const void* k_in, void* k_out, int axis, void* stream);
+
+/* physics.py:527-599 / 664-712 / 770-819: deriv = RHS(state), all pointers k-space arrays in
+ * StateData insertion order (u_x,u_y[,u_z] then T or B_x,B_y[,B_z]) */
+int ddl_rhs(ddl_plan* plan, int physics, const ddl_phys_params* params,
+            void* const* state, void* const* deriv, void* work, size_t work_bytes,
+            int flags, void* stream);
+
+/* forward_step_cy_{2d,3d}.pyx euler/etd1/etd2rk1/etd2rk2 for ncomp components at once.
+ * The integrating factor is not an array: Z = -coeff[c] * (k^2)^visc_order * dt is formed
+ * from the plan's wavenumbers (coeff = nu / kappa / eta, 0 => the reference's IF None =>
+ * Euler branch).  deriv2 may be NULL for EULER / ETD1.  out may alias start.            */
+int ddl_stage(ddl_plan* plan, int kind, int ncomp, void* const* start, void* const* out,
+              void* const* deriv1, void* const* deriv2, const double* coeff, int visc_order,
+              double dt, void* stream);
+
+/* One stage of the restated RK4 (time_step.py:395-483 + forward_step :187-221):
+ *   total = (first ? 0 : total) + k / wdiv ;  if (!last) out = S(y, k, dt_step)
+ *   else out = S(y, total, dt_step),  S = euler / etd1(-IF)                              */
+int ddl_rk4_stage(ddl_plan* plan, int ncomp, void* const* y, void* const* k, void* const* total,
+                  void* const* out, const double* coeff, int visc_order, double wdiv,
+                  double dt_step, int first, int last, void* stream);
+
+/* restated CrankNicholsonVisc (time_step.py:486-506): y = (top/bottom) y + k / bottom */
+int ddl_cn_step(ddl_plan* plan, int ncomp, void* const* y, void* const* k, const double* coeff,
+                int visc_order, double dt, void* stream);
+
+int ddl_sync(void* stream);
+const char* ddl_last_error(void);
+const char* ddl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDL_H */

@@ -1,0 +1,113 @@
+"""ctypes driver for the HOST-EMULATION build of the CUDA library (tests only).
+
+The emulation build (dedalus-1.0_b200/build.py --emul) compiles the very same kernel bodies
+with g++; one host thread walks every work item.  It exists so that the index logic of the
+kernels can be checked against the oracle in the GPU-less build container.  The product
+package never loads it.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+BUILD = os.path.join(ROOT, "tests", "host", "_build")
+
+
+class PhysParams(C.Structure):
+    _fields_ = [("rho0", C.c_double), ("g", C.c_double), ("alpha_t", C.c_double), ("beta", C.c_double),
+                ("boussinesq_dir", C.c_int), ("reserved", C.c_int)]
+
+
+def load():
+    sys.path.insert(0, os.path.join(ROOT, "dedalus-1.0_b200"))
+    import build as ddl_build
+    lib = C.CDLL(ddl_build.build_emul(BUILD))
+    lib.ddl_last_error.restype = C.c_char_p
+    lib.ddl_version.restype = C.c_char_p
+    lib.ddl_workspace_bytes.restype = C.c_size_t
+    lib.ddl_rhs_workspace_bytes.restype = C.c_size_t
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _pa(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+class EmulPlan:
+    PHYS = {"IncompressibleHydro": 0, "BoussinesqHydro": 1, "IncompressibleMHD": 2}
+
+    def __init__(self, lib, grid):
+        """grid: oracle Grid (supplies k values and the dealias mask exactly as the host layer will)."""
+        self.lib, self.g = lib, grid
+        nd = grid.ndim
+        shape = np.array(grid.shape, dtype=np.int64)
+        k = {n: np.ascontiguousarray(v.ravel(), dtype=np.float64) for n, v in grid.k.items()}
+        mask = grid.dealias_mask()
+        keep = {}
+        for name in k:
+            axis = grid.ktrans[name]
+            other = tuple(a for a in range(nd) if a != axis)
+            keep[name] = np.ascontiguousarray((~mask).any(axis=other).astype(np.uint8))
+        self._keep = keep
+        self._k = k
+        self.plan = C.c_void_p()
+        rc = lib.ddl_plan_create(C.byref(self.plan), nd, _p(shape), _p(k["x"]), _p(k["y"]),
+                                 _p(k["z"]) if nd == 3 else None, _p(keep["x"]), _p(keep["y"]),
+                                 _p(keep["z"]) if nd == 3 else None)
+        self.check(rc)
+        self.work = None
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.ddl_last_error().decode())
+
+    def _ws(self, nbytes):
+        if self.work is None or self.work.nbytes < nbytes:
+            self.work = np.zeros(nbytes // 16 + 1, dtype=np.complex128)
+        return self.work
+
+    def forward(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        k = np.full(self.g.kshape, np.nan + 0j, dtype=np.complex128)
+        w = self._ws(self.lib.ddl_workspace_bytes(self.plan, 1, 1))
+        self.check(self.lib.ddl_forward(self.plan, _p(x), _p(k), _p(w), C.c_size_t(w.nbytes), None))
+        return k
+
+    def backward(self, k):
+        k = np.ascontiguousarray(k, dtype=np.complex128).copy()
+        x = np.full(self.g.shape, np.nan, dtype=np.float64)
+        w = self._ws(self.lib.ddl_workspace_bytes(self.plan, 1, 1))
+        self.check(self.lib.ddl_backward(self.plan, _p(k), _p(x), _p(w), C.c_size_t(w.nbytes), None))
+        return x, k
+
+    def deriv(self, k, axis):
+        k = np.ascontiguousarray(k, dtype=np.complex128)
+        o = np.empty_like(k)
+        self.check(self.lib.ddl_deriv(self.plan, _p(k), _p(o), axis, None))
+        return o
+
+    def rhs(self, physics, params, state, flags=1):
+        pid = self.PHYS[physics]
+        pp = PhysParams(params.get("rho0", 1.0), params.get("g", 1.0), params.get("alpha_t", 1.0),
+                        params.get("beta", 1.0), {"x": 0, "y": 1, "z": 2}[params.get("boussinesq_direction", "z")], 0)
+        state = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in state]
+        deriv = [np.full(self.g.kshape, np.nan + 0j, dtype=np.complex128) for _ in state]
+        w = self._ws(self.lib.ddl_rhs_workspace_bytes(self.plan, pid))
+        self.check(self.lib.ddl_rhs(self.plan, pid, C.byref(pp), _pa(state), _pa(deriv), _p(w), C.c_size_t(w.nbytes),
+                                    flags, None))
+        return np.stack(deriv), np.stack(state)
+
+    def stage(self, kind, start, d1, d2, coeff, vo, dt):
+        n = len(start)
+        out = [np.empty_like(s) for s in start]
+        co = np.ascontiguousarray(coeff, dtype=np.float64)
+        self.check(self.lib.ddl_stage(self.plan, kind, n, _pa(start), _pa(out), _pa(d1), _pa(d2) if d2 is not None else None,
+                                      _p(co), vo, C.c_double(dt), None))
+        return out

@@ -1,0 +1,116 @@
+"""CPU: run the CUDA library's kernel bodies through the g++ host-emulation build
+(tests/host/emul.py) and compare with the reference goldens / the oracle.  This checks the
+index logic of every pass (pruned tables, Hermitian pair packing, scrambled FFT order,
+spectral assembly, stage updates) without a GPU; the -m gpu tests repeat it on the device."""
+import ast
+import glob
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "host"))
+import dedalus_oracle as orc
+import emul
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emul.load()
+
+
+def test_fft_core_host_emulation(tmp_path):
+    exe = str(tmp_path / "emul_fft")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "dedalus-1.0_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "host", "emul_fft.cpp"), "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stdout
+
+
+@pytest.mark.parametrize("name,shape,L,dl", [("t2d", (16, 32), (2 * np.pi, 2 * np.pi), "2/3 cython"),
+                                             ("t3d", (8, 16, 32), (2.0, 3.0, 5.0), "2/3 cython"),
+                                             ("t3dn", (16, 16, 16), (2 * np.pi,) * 3, "None")])
+def test_emulated_transforms_match_reference(lib, name, shape, L, dl):
+    z = np.load(os.path.join(GOLDEN, "transforms.npz"))
+    g = orc.Grid(shape, L, dl)
+    pl = emul.EmulPlan(lib, g)
+    k = pl.forward(z[name + "_x"])
+    assert rel(k, z[name + "_k"]) < 1e-14
+    x, kd = pl.backward(z[name + "_k"])
+    assert rel(x, z[name + "_xb"]) < 1e-14
+    assert rel(pl.deriv(z[name + "_k"], 0), z[name + "_derivx"]) < 1e-15
+    assert rel(pl.deriv(z[name + "_k"], 1), z[name + "_derivy"]) < 1e-15
+
+
+def test_emulated_backward_dealiases_source_in_place(lib):
+    g = orc.Grid((16, 16, 16))
+    pl = emul.EmulPlan(lib, g)
+    rng = np.random.default_rng(3)
+    k = rng.standard_normal(g.kshape) + 1j * rng.standard_normal(g.kshape)
+    c = orc.Comp(g)
+    c["kspace"] = k
+    xr = c["xspace"].copy()           # numpy irfftn semantics for non-Hermitian junk too
+    x, kd = pl.backward(k)
+    assert np.array_equal(kd, c.kdata)
+    assert rel(x, xr) < 1e-14
+
+
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+               if os.path.basename(p) not in ("stage_kernels.npz", "transforms.npz"))
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if "nodealias" not in c])
+def test_emulated_rhs_matches_reference(lib, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    g = orc.Grid(meta["shape"], meta["length"], meta.get("dealiasing", "2/3 cython"))
+    pl = emul.EmulPlan(lib, g)
+    params = dict(meta["params"])
+    if meta["physics"] == "BoussinesqHydro":
+        params["boussinesq_direction"] = "y" if g.ndim == 2 else "z"
+    mhd = meta["physics"] == "IncompressibleMHD"
+    d, s = pl.rhs(meta["physics"], params, list(z["y0"]), flags=1 | (2 if mhd else 0))
+    if meta["ic"] == "taylor_green":
+        # nonlinear term is a pure gradient: compare absolutely
+        assert np.abs(d - z["dy0"]).max() < 1e-15
+    else:
+        assert rel(d, z["dy0"]) < 1e-13
+    assert rel(s, z["y0_after_rhs"]) < 1e-13
+
+
+@pytest.mark.parametrize("shape", [(16, 32), (8, 16, 16)])
+def test_emulated_stage_kernels_match_oracle(lib, shape):
+    g = orc.Grid(shape, None)
+    pl = emul.EmulPlan(lib, g)
+    rng = np.random.default_rng(5)
+    mk = lambda: np.ascontiguousarray(rng.standard_normal(g.kshape) + 1j * rng.standard_normal(g.kshape))
+    n = 3
+    start, d1, d2 = [mk() for _ in range(n)], [mk() for _ in range(n)], [mk() for _ in range(n)]
+    coeff = [0.0, 0.004, 0.3]        # None-branch, Taylor branch, exp branch
+    dt = 0.05
+    for vo in (1, 2):
+        k2p = g.k2() ** vo
+        Zmax = [c * k2p.max() * dt for c in coeff]
+        if vo == 1:
+            assert Zmax[1] < 0.5 and Zmax[2] > 0.5
+        for kind, fn in ((0, orc.euler), (1, orc.etd1), (2, orc.etd2rk1), (3, orc.etd2rk2)):
+            out = pl.stage(kind, start, d1, d2, coeff, vo, dt)
+            for c in range(n):
+                ref = np.empty_like(start[c])
+                IF = -(coeff[c] * k2p)
+                if kind == 0:
+                    fn(start[c], ref, d1[c], dt)
+                elif kind == 1:
+                    fn(start[c], ref, d1[c], IF, dt)
+                else:
+                    fn(start[c], ref, d1[c], d2[c], IF, dt)
+                assert rel(out[c], ref) < 1e-15, (kind, c, vo)
