@@ -1,0 +1,70 @@
+"""ctypes binding of libddl_b200.so (C ABI: include/ddl.h).
+
+There is no fallback: if the shared library has not been built
+(``python dedalus-1.0_b200/build.py`` / ``__graft_entry__.build()``) importing this module
+raises, and every compute entry point of the package depends on it.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libddl_b200.so")
+
+EXPORTS = [
+    "ddl_plan_create", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
+    "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_deriv", "ddl_rhs", "ddl_stage",
+    "ddl_rk4_stage", "ddl_cn_step", "ddl_sync", "ddl_last_error", "ddl_version",
+]
+
+HYDRO, BOUSSINESQ, MHD = 0, 1, 2
+EULER, ETD1, ETD2RK1, ETD2RK2 = 0, 1, 2, 3
+RHS_ZERO_FILL, RHS_DEALIAS_STATE = 1, 2
+
+
+class PhysParams(C.Structure):
+    _fields_ = [("rho0", C.c_double), ("g", C.c_double), ("alpha_t", C.c_double), ("beta", C.c_double),
+                ("boussinesq_dir", C.c_int), ("reserved", C.c_int)]
+
+
+class DDLError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libddl_b200.so is missing (%s): build it with `python dedalus-1.0_b200/build.py`. "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
+    lib.ddl_plan_create.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.ddl_plan_destroy.argtypes = [vp]
+    lib.ddl_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.ddl_workspace_bytes.restype = sz
+    lib.ddl_rhs_workspace_bytes.argtypes = [vp, i32]
+    lib.ddl_rhs_workspace_bytes.restype = sz
+    lib.ddl_forward.argtypes = [vp, vp, vp, vp, sz, vp]
+    lib.ddl_backward.argtypes = [vp, vp, vp, vp, sz, vp]
+    lib.ddl_dealias.argtypes = [vp, vp, vp]
+    lib.ddl_deriv.argtypes = [vp, vp, vp, i32, vp]
+    lib.ddl_rhs.argtypes = [vp, i32, C.POINTER(PhysParams), vp, vp, vp, sz, i32, vp]
+    lib.ddl_stage.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, dbl, vp]
+    lib.ddl_rk4_stage.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, dbl, dbl, i32, i32, vp]
+    lib.ddl_cn_step.argtypes = [vp, i32, vp, vp, vp, i32, dbl, vp]
+    lib.ddl_sync.argtypes = [vp]
+    lib.ddl_last_error.restype = C.c_char_p
+    lib.ddl_version.restype = C.c_char_p
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise DDLError(lib.ddl_last_error().decode())
+
+
+def ptr_array(tensors):
+    """(void*)[n] of device pointers; keep the tensors alive while it is in use."""
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])

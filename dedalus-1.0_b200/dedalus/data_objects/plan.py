@@ -1,0 +1,127 @@
+"""Host-side plan cache: wavenumbers, dealias masks and the ddl_plan handle shared by every
+component of the same (shape, length, dealiasing).  Replaces fftw.create_data / fftw.rPlan
+(dedalus/utils/fftw/_fftw.pyx:81-185,246-309) and the per-representation k / mask setup
+(representations.py:204-233,359-417): one plan, no per-component scratch."""
+import ctypes as C
+
+import numpy as np
+import numpy.fft as npfft
+import torch
+
+from .._lib import lib, check
+from ..utils.parallelism import swap_indices
+
+_PLANS = {}
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dedalus (B200) needs a CUDA device: there is no CPU path.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def current_stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def wavenumbers(shape, length):
+    """k arrays exactly as representations.py:204-229 builds them (same float expressions):
+    returns (global kspace shape, ktrans, dk, kny, {name: 1-D float64 array})."""
+    ndim = len(shape)
+    xs = np.array(shape)
+    length = np.asarray(length, dtype=float)
+    ks = xs.copy()
+    ks[-1] = ks[-1] // 2 + 1
+    kshape = np.array(swap_indices(ks))
+    if ndim == 2:
+        ktrans = {"x": 0, 0: "x", "y": 1, 1: "y"}
+    else:
+        ktrans = {"x": 2, 2: "x", "y": 0, 0: "y", "z": 1, 1: "z"}
+    dk = swap_indices(2 * np.pi / length)
+    kny = swap_indices(np.pi * xs / length)
+    xs_sw = swap_indices(xs)
+    k = {}
+    for i, ksize in enumerate(kshape):
+        xsize = xs_sw[i]
+        if i == ktrans["x"]:
+            ki = npfft.fftfreq(xsize)[:ksize] * 2.0 * kny[i]
+            if xsize % 2 == 0:
+                ki[-1] *= -1.0
+        else:
+            ki = npfft.fftfreq(ksize) * 2.0 * kny[i]
+            if xsize % 2 == 0:
+                ki[ksize // 2] *= -1.0
+        k[ktrans[i]] = np.ascontiguousarray(ki)
+    return kshape, ktrans, dk, kny, k
+
+
+def keep_masks(dealiasing, ktrans, kny, k):
+    """Per-axis 'mode survives' masks with the reference's own comparisons
+    (dealias_cy_3d.pyx:34-36: zero if |k| >= 2/3 k_nyquist; representations.py:442-455)."""
+    keep = {}
+    for name, kv in k.items():
+        kn = kny[ktrans[name]]
+        if dealiasing in ("2/3", "2/3 cython"):
+            keep[name] = ~((kv >= 2.0 / 3.0 * kn) | (kv <= -2.0 / 3.0 * kn))
+        elif dealiasing in ("None", None, 0):
+            keep[name] = ~(np.abs(kv) == kn)
+        elif dealiasing == "2/3 spherical":
+            raise NotImplementedError("'2/3 spherical' dealiasing is not implemented in the CUDA backend.")
+        else:
+            raise NotImplementedError("Specified dealiasing method not implemented.")
+    return keep
+
+
+class Plan(object):
+    def __init__(self, shape, length, dealiasing):
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        self.length = tuple(float(x) for x in length)
+        self.dealiasing = dealiasing
+        self.kshape, self.ktrans, self.dk, self.kny, self.k_np = wavenumbers(self.shape, self.length)
+        self.keep_np = keep_masks(dealiasing, self.ktrans, self.kny, self.k_np)
+        self.device = device()
+        shp = np.array(self.shape, dtype=np.int64)
+        keep8 = {n: np.ascontiguousarray(v.astype(np.uint8)) for n, v in self.keep_np.items()}
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.handle = C.c_void_p()
+        check(lib.ddl_plan_create(C.byref(self.handle), self.ndim, vp(shp), vp(self.k_np["x"]), vp(self.k_np["y"]),
+                                  vp(self.k_np["z"]) if self.ndim == 3 else None, vp(keep8["x"]), vp(keep8["y"]),
+                                  vp(keep8["z"]) if self.ndim == 3 else None))
+        # broadcast-shaped device copies for the Python-level API (comp.k['x'] etc.)
+        self.k = {}
+        for name, kv in self.k_np.items():
+            i = self.ktrans[name]
+            shp_b = [1] * self.ndim
+            shp_b[i] = len(kv)
+            self.k[name] = torch.from_numpy(kv).to(self.device).reshape(shp_b)
+        self._work = None
+        self.nmodes = int(np.prod(self.kshape))
+
+    def workspace(self, nbytes):
+        if self._work is None or self._work.numel() < nbytes:
+            self._work = None
+            self._work = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._work
+
+    def transform_workspace(self):
+        return self.workspace(lib.ddl_workspace_bytes(self.handle, 1, 1))
+
+    def rhs_workspace(self, physics_id):
+        return self.workspace(lib.ddl_rhs_workspace_bytes(self.handle, physics_id))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.ddl_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def get_plan(shape, length, dealiasing):
+    key = (tuple(int(s) for s in shape), tuple(float(x) for x in length), str(dealiasing),
+           torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    pl = _PLANS.get(key)
+    if pl is None:
+        pl = _PLANS[key] = Plan(shape, length, dealiasing)
+    return pl

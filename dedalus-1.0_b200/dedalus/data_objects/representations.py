@@ -1,0 +1,253 @@
+"""Field-component representations (reference: dedalus/data_objects/representations.py).
+
+`FourierRepresentation` keeps the reference's interface -- ``comp['kspace']`` / ``comp['xspace']``
+lazy state machine, ``forward`` / ``backward``, ``deriv``, ``k2``, ``dealias`` and friends -- with
+torch CUDA tensors as storage and the transforms done by the hand-written CUDA kernels behind
+include/ddl.h.  k-space is transposed exactly like FFTW-MPI's output (representations.py:84-93):
+3-D x-space (z,y,x) <-> k-space (ky,kz,kx); 2-D (y,x) <-> (kx,ky).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .._lib import lib, check
+from ..config import decfg
+from ..utils.logger import mylog
+from ..utils.parallelism import com_sys
+from ..utils.timer import timer
+from ..utils.function_count import counts
+from . import plan as _plan
+
+
+class Representation(object):
+    """Base class: stores data and provides spatial derivatives (representations.py:47-55)."""
+
+    def __init__(self, sd, shape, length):
+        pass
+
+
+class FourierRepresentation(Representation):
+    """Component that is periodic (Fourier) in every direction."""
+
+    timer = timer
+    _static_k = True
+
+    def __init__(self, sd, shape, length):
+        self.sd = sd
+        self.ndim = len(shape)
+        if self.ndim not in (2, 3):
+            raise ValueError("Must use either 2 or 3 dimensions.")
+        if len(shape) != len(length):
+            raise ValueError("Shape and Length must have same dimensions.")
+        self.global_shape = {"xspace": np.array(shape)}
+        self.length = np.asarray(length, dtype=float)
+        self.dtype = {"kspace": "complex128", "xspace": "float64"}
+        self._eps = {"kspace": np.finfo(np.complex128).eps, "xspace": np.finfo(np.float64).eps}
+
+        method = decfg.get("FFT", "method")
+        dealiasing = decfg.get("FFT", "dealiasing")
+        if method not in ("cuda", "fftw", "numpy"):
+            raise NotImplementedError("Specified FFT method not implemented.")
+        if com_sys.nproc > 1:
+            raise NotImplementedError("Slab-decomposed runs go through dedalus.parallel (one plan per rank).")
+
+        if self.ndim == 2:
+            self.xtrans = {"x": 1, 1: "x", "y": 0, 0: "y"}
+        else:
+            self.xtrans = {"x": 2, 2: "x", "y": 1, 1: "y", "z": 0, 0: "z"}
+
+        self._plan = _plan.get_plan(shape, self.length, dealiasing)
+        pl = self._plan
+        self.ktrans = pl.ktrans
+        self.global_shape["kspace"] = pl.kshape.copy()
+        self.local_shape = {"kspace": pl.kshape.copy(), "xspace": self.global_shape["xspace"].copy()}
+        self.offset = {"xspace": 0, "kspace": 0}
+        self.dk, self.kny, self.k = pl.dk, pl.kny, pl.k
+        self.set_dealiasing(dealiasing)
+
+        self.kdata = torch.zeros(tuple(int(n) for n in pl.kshape), dtype=torch.complex128, device=pl.device)
+        self._xdata = None          # allocated on first use: most components never leave k-space
+        self._curr_space = "kspace"
+        self.integrating_factor = None
+        self.fwd_count = 0
+        self.rev_count = 0
+
+    # ------------------------------------------------------------------ storage
+    @property
+    def xdata(self):
+        if self._xdata is None:
+            self._xdata = torch.zeros(tuple(int(n) for n in self.global_shape["xspace"]), dtype=torch.float64,
+                                      device=self._plan.device)
+        return self._xdata
+
+    @property
+    def data(self):
+        return self.kdata if self._curr_space == "kspace" else self.xdata
+
+    def __getitem__(self, space):
+        self.require_space(space)
+        return self.data
+
+    def __setitem__(self, space, data):
+        """Copy into the fixed buffer (its identity never changes, representations.py:144-166)."""
+        if space == "xspace":
+            target = self.xdata
+        elif space == "kspace":
+            target = self.kdata
+        else:
+            raise KeyError("space must be either xspace or kspace.")
+        if isinstance(data, (float, complex, int)):
+            target.fill_(data)
+        else:
+            if not torch.is_tensor(data):
+                data = torch.as_tensor(np.asarray(data))
+            if data.is_complex() and not target.is_complex():
+                data = data.real
+            if data.dim() == target.dim():
+                data = data[tuple(slice(int(n)) for n in target.shape)]
+            target.copy_(data)
+        self._curr_space = space
+
+    def require_space(self, space):
+        if self._curr_space == space:
+            return
+        if space == "xspace":
+            self.backward()
+        elif space == "kspace":
+            self.forward()
+        else:
+            raise ValueError("space must be either xspace or kspace.")
+
+    # ------------------------------------------------------------------ transforms
+    @timer
+    def forward(self):
+        """x -> k: FFT / N_total, transposed out, then dealias (representations.py:335-345)."""
+        if self._curr_space == "kspace":
+            raise ValueError("Forward transform cannot be called from kspace.")
+        pl = self._plan
+        w = pl.transform_workspace()
+        check(lib.ddl_forward(pl.handle, self.xdata.data_ptr(), self.kdata.data_ptr(), w.data_ptr(), w.numel(),
+                              _plan.current_stream()))
+        self._curr_space = "kspace"
+        self.fwd_count += 1
+
+    @timer
+    def backward(self):
+        """k -> x: dealias the spectrum in place, then unnormalised inverse (:347-357)."""
+        if self._curr_space == "xspace":
+            raise ValueError("Backward transform cannot be called from xspace.")
+        pl = self._plan
+        w = pl.transform_workspace()
+        check(lib.ddl_backward(pl.handle, self.kdata.data_ptr(), self.xdata.data_ptr(), w.data_ptr(), w.numel(),
+                               _plan.current_stream()))
+        self._curr_space = "xspace"
+        self.rev_count += 1
+
+    fft = forward
+    ifft = backward
+
+    # ------------------------------------------------------------------ dealiasing
+    def set_dealiasing(self, dealiasing):
+        """Same option strings as representations.py:359-382; '2/3' and '2/3 cython' are one kernel."""
+        n = self.global_shape["xspace"]
+        if dealiasing in ("2/3", "2/3 cython"):
+            self.nmodes = np.prod(2 * np.ceil(n / 3.0 - 1) + 1)
+        elif dealiasing in ("None", None, 0):
+            self.nmodes = np.prod(2 * np.ceil(n / 2.0 - 1) + 1)
+        else:
+            raise NotImplementedError("Specified dealiasing method not implemented.")
+        self._dealiasing = dealiasing
+
+    def dealias(self):
+        """Zero the modes outside the plan's mask, in place (dealias_cy_{2,3}d.pyx)."""
+        self.require_space("kspace")
+        check(lib.ddl_dealias(self._plan.handle, self.kdata.data_ptr(), _plan.current_stream()))
+
+    dealias_23 = dealias
+    dealias_23_cython = dealias
+
+    def zero_nyquist(self):
+        """Zero the Nyquist planes (representations.py:442-455)."""
+        self.require_space("kspace")
+        mask = None
+        for name, kv in self.k.items():
+            m = kv.abs() == float(self.kny[self.ktrans[name]])
+            mask = m if mask is None else (mask | m)
+        self.kdata.masked_fill_(mask.expand_as(self.kdata), 0.0)
+
+    # ------------------------------------------------------------------ spectral helpers
+    def deriv(self, dim):
+        """i k_dim * data (representations.py:419-425); returns a fresh tensor."""
+        self.require_space("kspace")
+        out = torch.empty_like(self.kdata)
+        check(lib.ddl_deriv(self._plan.handle, self.kdata.data_ptr(), out.data_ptr(), {"x": 0, "y": 1, "z": 2}[dim],
+                            _plan.current_stream()))
+        return out
+
+    def k2(self, no_zero=False, set_zero=1.0):
+        """|k|^2, summed in the reference's order (representations.py:427-440)."""
+        k2 = torch.zeros(tuple(int(n) for n in self.local_shape["kspace"]), dtype=torch.float64, device=self.kdata.device)
+        for kv in self.k.values():
+            k2 += kv ** 2
+        if no_zero:
+            k2[k2 == 0] = set_zero
+        return k2
+
+    def find_mode(self, mode, exact=False):
+        """Index of the mode closest to the physical wavevector `mode`, given in k-space axis
+        order ((ky,kz,kx) / (kx,ky)); None if absent (representations.py:247-288)."""
+        idx = []
+        for i in range(self.ndim):
+            kv = self._plan.k_np[self.ktrans[i]]
+            if exact:
+                hit = np.nonzero(kv == mode[i])[0]
+            else:
+                half = self.dk[i] / 2.0
+                hit = np.nonzero((kv <= mode[i] + half) & (kv > mode[i] - half))[0]
+            if len(hit) == 0:
+                return None
+            if len(hit) > 1:
+                raise ValueError("Multiple modes tested true. This shouldn't happen.")
+            idx.append(int(hit[0]))
+        return tuple(idx)
+
+    def enforce_hermitian(self):
+        """Zero the Nyquist planes and overwrite the redundant half of the kx = 0 plane with
+        the conjugate of its Hermitian partner (representations.py:457-503)."""
+        self.require_space("kspace")
+        self.zero_nyquist()
+        d = self.kdata
+        if self.ndim == 2:
+            ny = d.shape[1] // 2
+            d[0, 0] = d[0, 0].real
+            d[0, -ny:] = d[0, 1:ny + 1].flip(0).conj()
+        else:
+            plane = d[:, :, 0]
+            nyy, nyz = plane.shape[0] // 2, plane.shape[1] // 2
+            plane[0, -nyz:] = plane[0, 1:nyz + 1].flip(0).conj()
+            plane[-nyy:, 0] = plane[1:nyy + 1, 0].flip(0).conj()
+            plane[-nyy:, 1:] = plane[1:nyy + 1, 1:].flip(0, 1).conj()
+
+    def zero_under_eps(self):
+        self.require_space("kspace")
+        self.kdata[self.kdata.abs() < self._eps["kspace"]] = 0.0
+
+    # ------------------------------------------------------------------ grids / io
+    def dx(self):
+        return self.length / self.global_shape["xspace"]
+
+    def xspace_grid(self, open=False):
+        """Coordinates of the local x-space points, [ndim, ...] (representations.py:528-548)."""
+        n = [int(v) for v in self.local_shape["xspace"]]
+        dx = self.dx()
+        axes = [torch.arange(n[i], dtype=torch.float64, device=self.kdata.device) * float(dx[i]) for i in range(self.ndim)]
+        axes[0] = axes[0] + self.offset["xspace"] * float(dx[0])
+        if open:
+            return [a.reshape([-1 if j == i else 1 for j in range(self.ndim)]) for i, a in enumerate(axes)]
+        return torch.stack(torch.meshgrid(*axes, indexing="ij"))
+
+    def save(self, dataset):
+        """Write the current data into an h5py-like dataset (representations.py:511-526)."""
+        dataset[:] = self.data.cpu().numpy()
+        dataset.attrs["space"] = self._curr_space

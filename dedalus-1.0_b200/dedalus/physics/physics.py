@@ -1,0 +1,402 @@
+"""Physics classes: IncompressibleHydro, BoussinesqHydro, IncompressibleMHD
+(reference: dedalus/physics/physics.py).
+
+Same constructor, parameters dictionary and ``RHS(data, deriv)`` contract as the reference, but
+the right-hand side is ONE fused device pipeline (include/ddl.h: ddl_rhs) instead of ~100 numpy
+passes and 15-36 separate FFTs: inverse transforms of the state, the quadratic products at
+every grid point inside the middle transform pass (the real-space fields never reach HBM),
+forward transforms of the products, then derivatives / curl / solenoidal projection in one
+spectral assembly kernel.  The conservative forms used are algebraically identical to the
+reference's advective forms for a dealiased, solenoidal state.
+
+The unfused vector-calculus helpers of the reference (XgradY, XcrossY, curlX, divX, ...) are
+kept as thin tensor-level methods for analysis scripts; the hot path does not use them.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import lib, check
+from ..config import decfg
+from ..data_objects.api import create_field_classes, AuxEquation, StateData
+from ..data_objects import plan as _plan
+from ..utils.logger import mylog
+from ..utils.timer import timer
+
+
+class IntegratingFactor(object):
+    """c * (k^2)**order, kept symbolic: the stage kernels rebuild it from integer wavenumbers in
+    registers, so no N_k-sized array exists unless somebody asks for one
+    (reference: one real array per component, physics.py:504-522)."""
+
+    def __init__(self, comp, coeff, order):
+        self.comp, self.coeff, self.order = comp, float(coeff), int(order)
+
+    def tensor(self):
+        return self.coeff * self.comp.k2() ** self.order
+
+    def __neg__(self):
+        return -self.tensor()
+
+    def __mul__(self, other):
+        return self.tensor() * other
+
+    __rmul__ = __mul__
+
+    def copy(self):
+        return IntegratingFactor(self.comp, self.coeff, self.order)
+
+
+def _reconstruct_object(cls, state):
+    obj = cls(state["shape"], state["_representation"], state["length"])
+    obj.__dict__.update(state)
+    return obj
+
+
+class Physics(object):
+    """Base class: defines fields and provides a right-hand side for the integrators."""
+
+    _physics_id = None
+
+    def __init__(self, shape, representation, length=None):
+        self.shape = shape
+        self._representation = representation
+        self.length = length if length else (2 * np.pi,) * len(shape)
+        self.ndim = len(self.shape)
+        self.dims = range(self.ndim)
+        self._field_list = []
+        self._aux_field_list = []
+        self.parameters = {}
+        self.aux_eqns = {}
+        self.forcing_functions = {}
+        self._forcing_function_names = {}
+        self._field_classes = create_field_classes(self._representation, self.shape, self.length)
+        self._is_finalized = False
+        self._tracer = decfg.getboolean("physics", "use_tracer")
+        self.k2 = None
+        self._trans = {0: "x", 1: "y", 2: "z"}
+
+    def __getitem__(self, item):
+        value = self.parameters.get(item, None)
+        if value is None:
+            raise KeyError
+        return value
+
+    def __reduce__(self):
+        self._is_finalized = False
+        keep = {k: v for k, v in self.__dict__.items() if k not in ("aux_fields", "_field_classes", "forcing_functions")}
+        return (_reconstruct_object, (self.__class__, keep))
+
+    def _finalize(self):
+        self._is_finalized = True
+
+    def create_fields(self, time, field_list=None):
+        if field_list is None:
+            field_list = self._field_list
+        return StateData(time, self.shape, self.length, self._field_classes, field_list=field_list,
+                         params=self.parameters)
+
+    @property
+    def aux_fields(self):
+        """Scratch fields of the reference (mathscalar, mathvector, ...).  The fused RHS needs
+        none of them; they are built on first access for scripts that use the helpers."""
+        if getattr(self, "_aux_fields", None) is None:
+            self._aux_fields = self.create_fields(0., self._aux_field_list)
+        return self._aux_fields
+
+    def _setup_aux_eqns(self, aux_eqns, RHS, ics, kwarglists):
+        for f, r, ic, kwargs in zip(aux_eqns, RHS, ics, kwarglists):
+            self.aux_eqns[f] = AuxEquation(r, kwargs, ic)
+
+    def compute_dt(self, data):
+        """Raw time-step limit without the CFL number (physics.py:151-158)."""
+        self.dtlist = []
+        self.set_dtlist(data)
+        return min(self.dtlist)
+
+    # ------------------------------------------------------------------ fused RHS
+    def _phys_params(self):
+        p = self.parameters
+        d = p.get("boussinesq_direction", "z")
+        return _lib.PhysParams(float(p.get("rho0", 1.0)), float(p.get("g", 1.0)), float(p.get("alpha_t", 1.0)),
+                               float(p.get("beta", 1.0)), {"x": 0, "y": 1, "z": 2}[d], 0)
+
+    def RHS(self, data, deriv):
+        """Base behaviour of the reference (physics.py:134-149): zero deriv, synchronise times."""
+        if not self._is_finalized:
+            self._finalize()
+        for _, field in deriv:
+            field.zero_all()
+        deriv.set_time(data.time)
+
+    def _fused_rhs(self, data, deriv, flags):
+        if not self._is_finalized:
+            self._finalize()
+        if decfg.get("FFT", "dealiasing") not in ("2/3", "2/3 cython"):
+            raise NotImplementedError(
+                "The fused RHS uses conservative products, which equal the reference's advective form only under "
+                "2/3 dealiasing; FFT.dealiasing=%r is not supported." % decfg.get("FFT", "dealiasing"))
+        state = []
+        for _, _, c in data.components():
+            c.require_space("kspace")
+            state.append(c.kdata)
+        out = []
+        for _, _, c in deriv.components():
+            c._curr_space = "kspace"
+            out.append(c.kdata)
+        pl = next(data.components())[2]._plan
+        w = pl.rhs_workspace(self._physics_id)
+        pp = self._phys_params()
+        check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), _lib.ptr_array(out),
+                          w.data_ptr(), w.numel(), flags, _plan.current_stream()))
+        deriv.set_time(data.time)
+
+    # ------------------------------------------------------------------ unfused helpers
+    def gradX(self, X, output):
+        """output[N*i + j] = d X_i / d x_j (physics.py:160-178)."""
+        N = self.ndim
+        for i in range(X.ncomp):
+            for j in self.dims:
+                output[N * i + j]["kspace"] = X[i].deriv(self._trans[j])
+
+    def divX(self, X, output):
+        acc = 0
+        for i in range(X.ncomp):
+            acc = acc + X[i].deriv(self._trans[i])
+        output["kspace"] = acc
+
+    def XgradY(self, X, Y, stmp, vtmp, output):
+        """(X . grad) Y evaluated in x-space, component by component (physics.py:197-228)."""
+        xs = [X[i]["kspace"].clone() for i in range(X.ncomp)]
+        for i in range(X.ncomp):
+            vtmp[i]["kspace"] = xs[i]
+        for ci in range(Y.ncomp):
+            acc = 0
+            for i in self.dims:
+                stmp["kspace"] = Y[ci].deriv(self._trans[i])
+                acc = acc + stmp["xspace"] * vtmp[i]["xspace"]
+            output[ci]["xspace"] = acc
+
+    def XconstcrossY(self, X, Y, output):
+        Yk = [Y[i]["kspace"] for i in range(Y.ncomp)]
+        if self.ndim == 2:
+            if np.isscalar(X):
+                output["x"]["kspace"] = -X * Yk[1]
+                output["y"]["kspace"] = X * Yk[0]
+            else:
+                Xy, Xx = X
+                output["kspace"] = Xx * Yk[1] - Xy * Yk[0]
+        else:
+            Xz, Xy, Xx = X
+            output["x"]["kspace"] = Xy * Yk[2] - Xz * Yk[1]
+            output["y"]["kspace"] = Xz * Yk[0] - Xx * Yk[2]
+            output["z"]["kspace"] = Xx * Yk[1] - Xy * Yk[0]
+
+    def XcrossY(self, X, Y, output):
+        """X x Y in x-space (physics.py:309-354); like the reference this leaves its inputs in x-space."""
+        Yx = [Y[i]["xspace"] for i in range(Y.ncomp)]
+        if self.ndim == 2:
+            if X.ncomp == 1:
+                Xz = X["xspace"]
+                output["x"]["xspace"] = -Xz * Yx[1]
+                output["y"]["xspace"] = Xz * Yx[0]
+            else:
+                output["xspace"] = X["x"]["xspace"] * Yx[1] - X["y"]["xspace"] * Yx[0]
+        else:
+            Xx = [X[i]["xspace"] for i in range(3)]
+            output["x"]["xspace"] = Xx[1] * Yx[2] - Xx[2] * Yx[1]
+            output["y"]["xspace"] = Xx[2] * Yx[0] - Xx[0] * Yx[2]
+            output["z"]["xspace"] = Xx[0] * Yx[1] - Xx[1] * Yx[0]
+
+    def XdotY(self, X, Y, output, space):
+        if X.ncomp != Y.ncomp:
+            raise ValueError("Vectors not the same size")
+        acc = 0
+        for i in range(X.ncomp):
+            acc = acc + X[i][space] * Y[i][space]
+        output[space] = acc
+
+    def curlX(self, X, output):
+        t = self._trans
+        if X.ncomp == 3:
+            output[0]["kspace"] = X[2].deriv(t[1]) - X[1].deriv(t[2])
+            output[1]["kspace"] = X[0].deriv(t[2]) - X[2].deriv(t[0])
+            output[2]["kspace"] = X[1].deriv(t[0]) - X[0].deriv(t[1])
+        elif X.ncomp == 2:
+            output["kspace"] = X[1].deriv(t[0]) - X[0].deriv(t[1])
+        else:
+            output[0]["kspace"] = X[0].deriv(t[1])
+            output[1]["kspace"] = -X[0].deriv(t[0])
+
+    @timer
+    def laplace_solve(self, X, output):
+        """Solve laplace(output) = X (physics.py:407-416)."""
+        if self.k2 is None:
+            self.k2 = output.k2(no_zero=True)
+        output["kspace"] = -X["kspace"] / self.k2
+
+
+class IncompressibleHydro(Physics):
+    """Homogeneous incompressible hydrodynamics (physics.py:419-610).
+
+    parameters: 'nu' (0.), 'viscosity_order' (1), 'shear_rate' (0., shearing box not
+    supported by this backend), 'Omega' (None)."""
+
+    _physics_id = _lib.HYDRO
+
+    def __init__(self, *args, **kwargs):
+        Physics.__init__(self, *args, **kwargs)
+        self._field_list.append(("u", "VectorField"))
+        self._aux_field_list.append(("mathscalar", "ScalarField"))
+        self._aux_field_list.append(("mathvector", "VectorField"))
+        self.parameters["viscosity_order"] = 1
+        self.parameters["nu"] = 0.
+        self.parameters["shear_rate"] = 0.
+        self.parameters["Omega"] = None
+        if self._tracer:
+            raise NotImplementedError("Passive tracer (physics.use_tracer) is not implemented in the CUDA backend.")
+        self._first_rhs = True
+
+    def __reduce__(self):
+        self._first_rhs = True
+        return Physics.__reduce__(self)
+
+    def _finalize(self):
+        Physics._finalize(self)
+        if self.parameters["shear_rate"] != 0.:
+            raise NotImplementedError("Linear shear needs FourierShearRepresentation, which this backend does not provide.")
+        self._shear = False
+        self._rotation = self.parameters["Omega"] is not None
+        if self._rotation and self.ndim == 2:
+            mylog.warning("Rotation is dynamically insignificant in 2D incompressible hydrodynamics.")
+
+    def _setup_integrating_factors(self, deriv):
+        nu, vo = self.parameters["nu"], self.parameters["viscosity_order"]
+        for _, comp in deriv["u"]:
+            comp.integrating_factor = None if nu == 0. else IntegratingFactor(comp, nu, vo)
+
+    def set_velocity_forcing(self, func):
+        self.forcing_functions["VelocityForcing"] = func
+
+    def _rhs_flags(self):
+        return _lib.RHS_ZERO_FILL
+
+    def RHS(self, data, deriv):
+        """deriv = RHS(data):  d_t u = P[-u.grad u (+ class terms)]  (physics.py:527-599)."""
+        if self._first_rhs:
+            self._setup_integrating_factors(deriv)
+            self._first_rhs = False
+        self._fused_rhs(data, deriv, self._rhs_flags())
+        self._extra_momentum_terms(data, deriv)
+
+    def _extra_momentum_terms(self, data, deriv):
+        """Rotation and user forcing (physics.py:563-572), added through the projector, which is
+        linear: P[N + E] = P[N] + P[E].  Off the hot path (both default to off)."""
+        extra = None
+        if self._rotation:
+            Om = self.parameters["Omega"]
+            u = [data["u"][i]["kspace"] for i in self.dims]
+            if self.ndim == 2:
+                cross = [-Om * u[1], Om * u[0]]
+            else:
+                Oz, Oy, Ox = Om
+                cross = [Oy * u[2] - Oz * u[1], Oz * u[0] - Ox * u[2], Ox * u[1] - Oy * u[0]]
+            extra = [-2 * c for c in cross]
+        if "VelocityForcing" in self.forcing_functions:
+            f = [self.forcing_functions["VelocityForcing"](data, i) for i in self.dims]
+            extra = f if extra is None else [a + b for a, b in zip(extra, f)]
+        if extra is None:
+            return
+        c0 = deriv["u"][0]
+        k = [c0.k[self._trans[i]] for i in self.dims]
+        k2 = c0.k2(no_zero=True)
+        kdot = sum(k[i] * extra[i] for i in self.dims) / k2
+        for i in self.dims:
+            deriv["u"][i]["kspace"].add_(extra[i] - k[i] * kdot)
+
+    def pressure_projection(self, data, deriv):
+        """Solenoidal projection of deriv['u'] as tensor operations (physics.py:588-599); the
+        fused RHS already contains it."""
+        c0 = deriv["u"][0]
+        k = [c0.k[self._trans[i]] for i in self.dims]
+        k2 = c0.k2(no_zero=True)
+        kdot = sum(k[i] * deriv["u"][i]["kspace"] for i in self.dims) / k2
+        for i in self.dims:
+            deriv["u"][i]["kspace"].sub_(k[i] * kdot)
+
+    def max_abs_vel(self, data):
+        return np.sqrt(data["u"].max_square())
+
+    def set_dtlist(self, data):
+        dx = data["u"]["x"].dx().min()
+        self.dtlist.append(dx / self.max_abs_vel(data))
+
+
+class BoussinesqHydro(IncompressibleHydro):
+    """Boussinesq hydrodynamics (physics.py:612-721): adds T, 'kappa', 'g', 'alpha_t', 'beta'."""
+
+    _physics_id = _lib.BOUSSINESQ
+
+    def __init__(self, *args, **kwargs):
+        IncompressibleHydro.__init__(self, *args, **kwargs)
+        self._field_list.append(("T", "ScalarField"))
+        self.parameters["kappa"] = 0.
+        self.parameters["g"] = 1.
+        self.parameters["alpha_t"] = 1.
+        self.parameters["beta"] = 1.
+        self.parameters["boussinesq_direction"] = decfg.get("physics", "boussinesq_direction")
+
+    def _setup_integrating_factors(self, deriv):
+        IncompressibleHydro._setup_integrating_factors(self, deriv)
+        kappa, vo = self.parameters["kappa"], self.parameters["viscosity_order"]
+        comp = deriv["T"][0]
+        comp.integrating_factor = None if kappa == 0. else IntegratingFactor(comp, kappa, vo)
+
+    def set_thermal_forcing(self, func):
+        self.forcing_functions["ThermalForcing"] = func
+
+    def RHS(self, data, deriv):
+        IncompressibleHydro.RHS(self, data, deriv)
+        if "ThermalForcing" in self.forcing_functions:
+            deriv["T"]["kspace"].add_(self.forcing_functions["ThermalForcing"](data))
+
+    def set_dtlist(self, data):
+        IncompressibleHydro.set_dtlist(self, data)
+        p = self.parameters
+        dx = data["u"]["x"].dx().min()
+        self.dtlist.append(dx / np.sqrt(np.abs(p["alpha_t"] * p["g"] * p["beta"])))
+
+
+class IncompressibleMHD(IncompressibleHydro):
+    """Homogeneous incompressible MHD (physics.py:724-836): adds B, 'rho0' (1.), 'eta' (0.)."""
+
+    _physics_id = _lib.MHD
+
+    def __init__(self, *args, **kwargs):
+        IncompressibleHydro.__init__(self, *args, **kwargs)
+        self._field_list.append(("B", "VectorField"))
+        self._aux_field_list.append(("mathvector2", "VectorField"))
+        self.parameters["rho0"] = 1.
+        self.parameters["eta"] = 0.
+
+    def _setup_integrating_factors(self, deriv):
+        IncompressibleHydro._setup_integrating_factors(self, deriv)
+        eta, vo = self.parameters["eta"], self.parameters["viscosity_order"]
+        for _, comp in deriv["B"]:
+            comp.integrating_factor = None if eta == 0. else IntegratingFactor(comp, eta, vo)
+
+    def _rhs_flags(self):
+        # the reference transforms the MHD state itself to x-space and back (physics.py:797-815),
+        # which zeroes its masked-out modes in place
+        return _lib.RHS_ZERO_FILL | _lib.RHS_DEALIAS_STATE
+
+    def max_alfven_speed(self, data):
+        fpr = 4 * np.pi * self.parameters["rho0"]
+        return np.sqrt(data["B"].max_square() / fpr)
+
+    def set_dtlist(self, data):
+        IncompressibleHydro.set_dtlist(self, data)
+        dx = data["u"]["x"].dx().min()
+        self.dtlist.append(dx / self.max_alfven_speed(data))

@@ -1,0 +1,284 @@
+"""Time integrators (reference: dedalus/time_stepping/time_step.py).
+
+RK2mid / RK2trap follow the reference's ETD2RK schemes exactly; the per-component Cython loops
+(forward_step_cy_{2d,3d}.pyx) are replaced by ONE multi-component device kernel per stage that
+rebuilds the integrating factor from the wavenumbers in registers (include/ddl.h: ddl_stage).
+
+RK4 and CrankNicholsonVisc cannot run in the reference as shipped (time_step.py:209,214 call
+undefined linear_step / intfac_step; :449 passes the same StateData as input and output;
+:495 uses a removed one-argument RHS API).  They are implemented here as RESTATED in
+SURVEY.md section 8(c): classical RK4 data flow of :426-483 with distinct k buffers and
+forward_step = Euler where the integrating factor is None, etd1(-IF) otherwise; CN as
+y+ = ((1/dt - IF/2) y + N(y)) / (1/dt + IF/2).
+"""
+import ctypes as C
+import os
+import pickle
+import time
+
+import numpy as np
+
+from .. import _lib
+from .._lib import lib, check
+from ..data_objects import plan as _plan
+from ..utils.logger import mylog
+from ..utils.parallelism import com_sys
+from ..utils.timer import timer
+
+hg_version = "b200-native"
+
+
+def _kspace_tensors(sd):
+    out = []
+    for _, _, c in sd.components():
+        c.require_space("kspace")
+        out.append(c.kdata)
+    return out
+
+
+def _plan_of(sd):
+    return next(sd.components())[2]._plan
+
+
+def _if_coefficients(deriv):
+    """(coeff[ncomp], order) from the integrating factors the physics attached to `deriv`."""
+    co, order = [], 1
+    for _, _, c in deriv.components():
+        IF = c.integrating_factor
+        if IF is None:
+            co.append(0.0)
+        else:
+            co.append(IF.coeff)
+            order = IF.order
+    return (C.c_double * len(co))(*co), order
+
+
+class TimeStepBase(object):
+    """Stopping controls, statistics and the snapshot trigger (time_step.py:48-179)."""
+
+    timer = timer
+
+    def __init__(self, RHS, CFL=0.1, int_factor=None):
+        self.RHS = RHS
+        self.CFL = CFL
+        self.int_factor = int_factor
+        self.sim_stop_time = 1000
+        self.wall_stop_time = 60. * 60.
+        self.stop_iteration = 1000
+        self.save_cadence = 100
+        self.max_save_period = 100.
+        self.time = 0
+        self.iteration = 0
+        self._nsnap = 0
+        self._tlastsnap = 0.
+        self.dt_old = np.finfo("d").max / 10.
+        self._start_time = time.time()
+
+    @property
+    def ok(self):
+        if self.iteration >= self.stop_iteration:
+            why = "stop iteration reached."
+        elif self.time >= self.sim_stop_time:
+            why = "simulation stop time reached."
+        elif (time.time() - self._start_time) >= self.wall_stop_time:
+            why = "wall stop time reached."
+        else:
+            return True
+        if com_sys.myproc == 0:
+            mylog.info("Timestepping complete: " + why)
+        return False
+
+    @timer
+    def advance(self, data, dt=None):
+        if (self.iteration % self.save_cadence) == 0 or (self.time - self._tlastsnap >= self.max_save_period):
+            self.snapshot(data)
+        if dt is None:
+            dt = self.cfl_dt(data)
+        self.do_advance(data, dt)
+        mylog.info("step %i" % self.iteration)
+
+    def do_advance(self, data, dt):
+        raise NotImplementedError("do_advance must be provided by subclass.")
+
+    @timer
+    def snapshot(self, data):
+        """Per-rank snapshot directory snap_%05i (time_step.py:112-151): HDF5 when h5py is
+        importable (same /time, /fields/<name>/<comp> layout), otherwise one .npy per component."""
+        rank = com_sys.myproc
+        path = "snap_%05i" % self._nsnap
+        if rank == 0 and not os.path.exists(path):
+            os.mkdir(path)
+        if com_sys.comm:
+            com_sys.comm.barrier()
+        try:
+            import h5py
+        except ImportError:
+            h5py = None
+        if h5py is not None:
+            with h5py.File(os.path.join(path, "data.cpu%04i" % rank), mode="w") as out:
+                out.create_dataset("time", data=self.time)
+                out.attrs["hg_version"] = hg_version
+                data.snapshot(out.create_group("/fields"))
+        else:
+            np.save(os.path.join(path, "time.cpu%04i.npy" % rank), np.array(self.time))
+            for name, i, c in data.components():
+                np.save(os.path.join(path, "%s_%i_%s.cpu%04i.npy" % (name, i, c._curr_space, rank)), c.data.cpu().numpy())
+        self._nsnap += 1
+        self._tlastsnap = self.time
+
+    def final_stats(self):
+        self.timer.print_stats()
+        if com_sys.myproc == 0:
+            total = self.timer.timers.get("advance", 0.0)
+            print("total advance wall time: %10.5e sec" % total)
+            print("%10.5e sec/step " % (total / max(self.iteration, 1)))
+            print()
+            print("Simulation complete. Status: awesome")
+
+    def finalize(self, data):
+        self.snapshot(data)
+        self.final_stats()
+
+    def cfl_dt(self, data):
+        dt = self.CFL * self.RHS.compute_dt(data)
+        if dt > 1.05 * self.dt_old:      # at most 5% growth per step
+            dt = 1.05 * self.dt_old
+        self.dt_old = dt
+        mylog.info("dt = %10.5e" % dt)
+        return dt
+
+    # ---- device stage launches ---------------------------------------------------------
+    def _stage(self, kind, start, out, d1, d2, if_from, dt):
+        s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
+        b = _kspace_tensors(d2) if d2 is not None else None
+        coeff, order = _if_coefficients(if_from)
+        check(lib.ddl_stage(_plan_of(start).handle, kind, len(s), _lib.ptr_array(s), _lib.ptr_array(o),
+                            _lib.ptr_array(a), _lib.ptr_array(b) if b is not None else None, coeff, order,
+                            float(dt), _plan.current_stream()))
+
+
+class RKBase(TimeStepBase):
+    """Base class for the Runge-Kutta integrators."""
+
+    @timer
+    def forward_step(self, start, deriv, output, dt):
+        """output = start advanced by dt with `deriv`: forward Euler for components without an
+        integrating factor, first-order ETD otherwise (time_step.py:187-221; the undefined
+        linear_step / intfac_step are euler / etd1(-IF))."""
+        self._stage(_lib.ETD1, start, output, deriv, None, deriv, dt)
+        output.set_time(start.time + dt)
+
+
+class RK2mid(RKBase):
+    """Second-order explicit midpoint RK with exponential time differencing (time_step.py:224-309)."""
+
+    def __init__(self, *arg, **kwargs):
+        TimeStepBase.__init__(self, *arg, **kwargs)
+        self.data2 = self.RHS.create_fields(0.)
+        self.deriv1 = self.RHS.create_fields(0.)
+        self.deriv2 = self.RHS.create_fields(0.)
+
+    def do_advance(self, data, dt):
+        data2, k1, k2 = self.data2, self.deriv1, self.deriv2
+        self.RHS.RHS(data, k1)
+        self._stage(_lib.ETD1, data, data2, k1, None, k1, dt / 2.)        # a_n (euler where IF is None)
+        data2.set_time(data.time + dt / 2.)
+        self.RHS.RHS(data2, k2)
+        self._stage(_lib.ETD2RK2, data, data, k1, k2, k1, dt)
+        data.set_time(data.time + dt)
+        self.time += dt
+        self.iteration += 1
+
+
+class RK2trap(RKBase):
+    """Second-order explicit trapezoidal RK with ETD (time_step.py:312-392)."""
+
+    def __init__(self, *arg, **kwargs):
+        TimeStepBase.__init__(self, *arg, **kwargs)
+        self.deriv1 = self.RHS.create_fields(0.)
+        self.deriv2 = self.RHS.create_fields(0.)
+
+    def do_advance(self, data, dt):
+        k1, k2 = self.deriv1, self.deriv2
+        self.RHS.RHS(data, k1)
+        self._stage(_lib.ETD1, data, data, k1, None, k1, dt)
+        data.set_time(data.time + dt)
+        self.RHS.RHS(data, k2)
+        self._stage(_lib.ETD2RK1, data, data, k1, k2, k1, dt)
+        self.time += dt
+        self.iteration += 1
+
+
+class RK4(RKBase):
+    """Classical fourth-order RK (tableau of time_step.py:399-411), restated -- see module doc."""
+
+    def __init__(self, *arg, **kwargs):
+        TimeStepBase.__init__(self, *arg, **kwargs)
+        self.temp_data = self.RHS.create_fields(0.)     # stage states
+        self.total_deriv = self.RHS.create_fields(0.)   # (k1 + 2 k2 + 2 k3 + k4) / 6
+        self.k_data = self.RHS.create_fields(0.)        # current k_i
+        self._coeff = None
+
+    def _rk4(self, y, out, wdiv, dt_step, first, last):
+        pl = _plan_of(y)
+        ys, ks = _kspace_tensors(y), _kspace_tensors(self.k_data)
+        ts, os_ = _kspace_tensors(self.total_deriv), _kspace_tensors(out)
+        coeff, order = self._coeff
+        check(lib.ddl_rk4_stage(pl.handle, len(ys), _lib.ptr_array(ys), _lib.ptr_array(ks), _lib.ptr_array(ts),
+                                _lib.ptr_array(os_), coeff, order, float(wdiv), float(dt_step), int(first), int(last),
+                                _plan.current_stream()))
+
+    def do_advance(self, data, dt):
+        R, tmp, k = self.RHS, self.temp_data, self.k_data
+        aux = list(R.aux_eqns.values())
+        a_old = [a.value for a in aux]
+        a_final = [a.RHS(a.value) / 6. for a in aux]
+        R.RHS(data, k)                                     # k1
+        if self._coeff is None:
+            self._coeff = _if_coefficients(k)
+            for (_, _, ct), (_, _, ck) in zip(self.total_deriv.components(), k.components()):
+                ct.integrating_factor = ck.integrating_factor
+        self._rk4(data, tmp, 6., dt / 2., True, False)     # total = k1/6 ; tmp = S(y, k1, dt/2)
+        tmp.set_time(data.time + dt / 2.)
+        for j, a in enumerate(aux):
+            a.value = a_old[j] + dt / 2. * a.RHS(a.value)
+            a_final[j] += a.RHS(a.value) / 3.
+        R.RHS(tmp, k)                                      # k2
+        self._rk4(data, tmp, 3., dt / 2., False, False)
+        for j, a in enumerate(aux):
+            a.value = a_old[j] + dt / 2. * a.RHS(a.value)
+            a_final[j] += a.RHS(a.value) / 3.
+        R.RHS(tmp, k)                                      # k3
+        self._rk4(data, tmp, 3., dt, False, False)
+        tmp.set_time(data.time + dt)
+        for j, a in enumerate(aux):
+            a.value = a_old[j] + dt * a.RHS(a.value)
+            a_final[j] += a.RHS(a.value) / 6.
+        R.RHS(tmp, k)                                      # k4
+        self._rk4(data, data, 6., dt, False, True)         # y+ = S(y, total + k4/6, dt)
+        data.set_time(data.time + dt)
+        for j, a in enumerate(aux):
+            a.value = a_old[j] + dt * a_final[j]
+        self.time += dt
+        self.iteration += 1
+
+
+class CrankNicholsonVisc(TimeStepBase):
+    """Crank-Nicholson on the viscous term, explicit nonlinear term (time_step.py:486-506), restated."""
+
+    def __init__(self, *arg, **kwargs):
+        TimeStepBase.__init__(self, *arg, **kwargs)
+        self.deriv = self.RHS.create_fields(0.)
+        self._coeff = None
+
+    def do_advance(self, data, dt):
+        self.RHS.RHS(data, self.deriv)
+        if self._coeff is None:
+            self._coeff = _if_coefficients(self.deriv)
+        ys, ks = _kspace_tensors(data), _kspace_tensors(self.deriv)
+        coeff, order = self._coeff
+        check(lib.ddl_cn_step(_plan_of(data).handle, len(ys), _lib.ptr_array(ys), _lib.ptr_array(ks), coeff, order,
+                              float(dt), _plan.current_stream()))
+        data.set_time(data.time + dt)
+        self.time += dt
+        self.iteration += 1

@@ -1,0 +1,3 @@
+from .function_count import counts
+from .timer import Timer, timer
+from .parallelism import com_sys, swap_indices, reduce_mean, reduce_sum, reduce_min, reduce_max

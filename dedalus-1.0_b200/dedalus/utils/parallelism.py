@@ -1,0 +1,98 @@
+"""Communication singleton and reductions (reference: dedalus/utils/parallelism.py:29-173).
+
+The reference wraps mpi4py's COMM_WORLD; here one process drives one GPU and the process group
+is torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests).  With no process
+group initialised the system degrades to a single rank exactly as the reference does without
+mpi4py (parallelism.py:33-50).
+"""
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except ImportError:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+class CommunicationSystem(object):
+    """`com_sys`: rank / size bookkeeping.  `comm` is the torch.distributed module when a
+    process group exists, else None (the reference's `comm is None` tests keep working)."""
+
+    @property
+    def comm(self):
+        return dist if (dist is not None and dist.is_available() and dist.is_initialized()) else None
+
+    @property
+    def myproc(self):
+        return dist.get_rank() if self.comm else 0
+
+    @property
+    def nproc(self):
+        return dist.get_world_size() if self.comm else 1
+
+    MPI = None
+
+
+com_sys = CommunicationSystem()
+
+
+def _as_tensor(x):
+    if torch.is_tensor(x):
+        return x
+    return torch.as_tensor(np.asarray(x))
+
+
+def _all_reduce(value, op):
+    """value: 0-d tensor on the device the process group expects."""
+    if com_sys.comm is None:
+        return value
+    t = value.clone()
+    if dist.get_backend() == "nccl" and not t.is_cuda:
+        t = t.cuda()
+    dist.all_reduce(t, op=op)
+    return t
+
+
+def _finish(t, reduce_all):
+    """The reference returns the value on every rank for reduce_all, else only on rank 0."""
+    out = t.item()
+    if com_sys.comm is None or reduce_all or com_sys.myproc == 0:
+        return out
+    return None
+
+
+def reduce_mean(data):
+    data = _as_tensor(data)
+    if com_sys.comm is None:
+        return data.mean().item()
+    total = _all_reduce(data.sum(), dist.ReduceOp.SUM)
+    count = _all_reduce(torch.tensor(float(data.numel()), dtype=total.dtype, device=total.device), dist.ReduceOp.SUM)
+    return _finish(total / count, False)
+
+
+def reduce_sum(data, reduce_all=False):
+    data = _as_tensor(data)
+    return _finish(_all_reduce(data.sum(), dist.ReduceOp.SUM if dist else None), reduce_all)
+
+
+def reduce_min(data, reduce_all=False):
+    data = _as_tensor(data)
+    return _finish(_all_reduce(data.min(), dist.ReduceOp.MIN if dist else None), reduce_all)
+
+
+def reduce_max(data, reduce_all=False):
+    data = _as_tensor(data)
+    return _finish(_all_reduce(data.max(), dist.ReduceOp.MAX if dist else None), reduce_all)
+
+
+def swap_indices(arr):
+    """Exchange entries [0] and [1] (x-space order <-> FFTW-transposed k-space order)."""
+    if isinstance(arr, np.ndarray):
+        out = arr.copy()
+    elif isinstance(arr, list):
+        out = list(arr)
+    else:
+        raise NotImplementedError("swap_indices only implemented for numpy arrays and lists.")
+    out[0], out[1] = out[1], out[0]
+    return out
