@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Headline benchmark: Fourier mode-stage updates/s of 3-D incompressible MHD, RK4
+(BASELINE.json metric).  `python bench.py --gpus N --steps K --warmup W`.
+
+  value      whole-job throughput, state resident in HBM, CUDA-event timed (max over ranks)
+  e2e        same metric through the public API with HOST buffers: every step copies the state
+             from pinned host memory to the device, advances, and copies it back
+  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event duration (measured in
+             a separate instrumented pass of the same steps) vs the measured HBM peak
+  cpu_baseline  the reference's own CPU path (oracle/_ref) on this host, bounded sample
+
+`--impl reference` times only the reference CPU path and prints its own line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dedalus-1.0_b200"))
+
+METRIC = "Fourier mode-stage updates/s (3-D incompressible MHD, RK4)"
+UNIT = "mode-stage updates/s"
+A_STAGE_MHD3D = 1920.0     # algorithmic bytes per mode-stage (SURVEY.md section 8d / BASELINE.md)
+# algorithmic bytes per N_k mode of each kernel of the MHD RHS (one launch = one RHS):
+# axis passes covered x (read + write) x 16 B;  stage sweep = 5 touches x 6 components
+ALGO_BYTES_PER_MODE = {
+    "z_inv": 6 * 32.0, "y_inv": 6 * 32.0, "x_fused": 15 * 32.0, "y_fwd": 9 * 32.0, "z_fwd": 9 * 32.0,
+    "stage": 30 * 16.0, "assemble": 0.0, "mask": 0.0,
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_state(n, seed=5):
+    """Synthetic random-phase MHD state on the device (SURVEY.md 8d recipe, torch generator):
+    per component white noise -> forward -> k^(-5/6) amplitude -> solenoidal projection -> rms 1."""
+    import numpy as np
+    import torch
+    from dedalus.mods import IncompressibleMHD, FourierRepresentation
+    P = IncompressibleMHD((n, n, n), FourierRepresentation)
+    P.parameters["nu"] = 1e-3
+    P.parameters["eta"] = 1e-3
+    data = P.create_fields(0.)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    c0 = data["u"][0]
+    kk = torch.sqrt(c0.k2())
+    shape = torch.where(kk > 0, kk.clamp(min=1e-30) ** (-5.0 / 6.0), torch.zeros_like(kk))
+    del kk
+    import dedalus.analysis.volume_average as va
+    umax2 = 0.0
+    for _, f in data:
+        for _, c in f:
+            c["xspace"] = torch.randn(n, n, n, dtype=torch.float64, device="cuda", generator=g)
+            c["kspace"].mul_(shape)
+            c._xdata = None
+        f.div_free()
+        en = sum(va.volume_average(c["kspace"].abs() ** 2, kdict=c.k) for _, c in f)
+        for _, c in f:
+            c["kspace"].mul_(1.0 / np.sqrt(en))
+    del shape
+    for _, c in data["u"]:
+        umax2 = max(umax2, float((c["xspace"] ** 2).max()))
+        c["kspace"]
+        c._xdata = None
+    torch.cuda.empty_cache()
+    dt = 0.2 * (2 * np.pi / n) / np.sqrt(umax2)
+    return P, data, dt
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import dedalus._lib as L
+    from dedalus.mods import RK4
+    import dedalus.analysis.volume_average as va
+    n = args.n
+    if world > 1:
+        # TODO(multi-GPU): slab-decomposed transforms.  Until then refuse rather than report
+        # replicas as a strong-scaling number.
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world,
+                              "unavailable": "slab-decomposed multi-GPU path not implemented yet (round 1)"}))
+        dist.destroy_process_group()
+        return
+    P, data, dt = make_state(n)
+    ti = RK4(P)
+    nk = n * n * (n // 2 + 1)
+    for _ in range(args.warmup):
+        ti.do_advance(data, dt)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        ti.do_advance(data, dt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - l0
+    clocks = sampler.stop()
+    value = args.steps * 4 * nk / (ms * 1e-3)
+    ekin, emag = va.ekin(data), va.emag(data)
+    assert np.isfinite(ekin) and np.isfinite(emag)
+
+    # ---- instrumented pass: per-kernel CUDA-event durations (not part of `value`)
+    L.profile(True)
+    for _ in range(2):
+        ti.do_advance(data, dt)
+    prof = L.profile_report()
+    L.profile(False)
+    peak, peak_src = measured_peak()
+    tot_ms = sum(v["ms"] for v in prof.values())
+    kern = {k: {"launches": v["n"], "ms_per_launch": v["ms"] / v["n"], "share": v["ms"] / tot_ms,
+                "algo_gbs": ALGO_BYTES_PER_MODE.get(k, 0.0) * nk / (v["ms"] / v["n"] * 1e-3) / 1e9}
+            for k, v in prof.items()}
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["algo_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["algo_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_MODE.get(dom, 0.0) * nk,
+                "step": {"achieved": A_STAGE_MHD3D * value / 1e9, "frac": A_STAGE_MHD3D * value / 1e9 / peak,
+                         "frac_of_8TBs": A_STAGE_MHD3D * value / 8e12, "bytes_per_mode_stage": A_STAGE_MHD3D},
+                "kernels": kern}
+
+    # ---- end to end with host buffers
+    comps = [c for _, _, c in data.components()]
+    host = [torch.empty(c.kdata.shape, dtype=c.kdata.dtype, pin_memory=True) for c in comps]
+    for h, c in zip(host, comps):
+        h.copy_(c.kdata)
+    torch.cuda.synchronize()
+    nbytes = sum(h.numel() * h.element_size() for h in host)
+    ksteps = max(1, min(args.steps, 3))
+    e0.record()
+    for _ in range(ksteps):
+        for h, c in zip(host, comps):
+            c["kspace"] = h                          # H2D through the public API (pinned, async)
+        ti.do_advance(data, dt)
+        for h, c in zip(host, comps):
+            h.copy_(c["kspace"], non_blocking=True)  # D2H of the step result
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    e2e = {"value": ksteps * 4 * nk / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
+           "d2h_bytes_per_step": nbytes, "steps": ksteps, "ms_per_step": ms_e2e / ksteps}
+
+    cpu = cpu_baseline(args)
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "3D incompressible MHD %d^3 RK4, 2/3 dealiasing, nu=eta=1e-3" % n, "n_components": 6,
+                      "N_k": nk, "stages_per_step": 4, "dt": dt, "cache": "inputs larger than L2 (state 6.5 GB)"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+           "invariants": {"ekin": ekin, "emag": emag}}
+    print(json.dumps(out))
+
+
+def cpu_baseline(args):
+    """Bounded sample of the same workload on the reference's CPU path, in a subprocess."""
+    n = args.cpu_n
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--n", str(n), "--steps",
+                            str(args.cpu_steps), "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           timeout=1200)
+        res = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": res["value"], "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "reference",
+                "sample": "reference numpy-FFT path + reference Cython stage kernels, MHD %d^3, %s, %d steps after 1 warm-up "
+                          "(single-threaded by construction; FFTW-MPI mode not reproducible here)" % (n, res["integrator"], res["steps"]),
+                "ms_per_step": res["ms_per_step"]}
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_bench
+    n = args.cpu_n
+    res = ref_bench.run(n, 3, max(1, args.steps), max(0, min(args.warmup, 1)))
+    cb = {"value": res["value"], "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "reference",
+          "sample": "MHD %d^3 %s, %d timed steps per run" % (n, res["integrator"], res["steps"])}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": res["ms_per_step"],
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "3D incompressible MHD RK4 (bounded CPU sample %d^3 of the 512^3 workload)" % n,
+                                 "N_k": res["nk"], "stages_per_step": 4},
+                      "cpu_baseline": cb,
+                      "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=512, help="grid size per axis (headline: 512)")
+    ap.add_argument("--cpu-n", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

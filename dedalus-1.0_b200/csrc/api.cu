@@ -1,6 +1,8 @@
 // C ABI (include/ddl.h): plan, transforms, fused RHS pipelines, stage updates.
 #include <cstdarg>
 #include <cmath>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ddl.h"
@@ -16,6 +18,39 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---------------------------------------------------------------- launch accounting
+struct ProfEvent {
+    const char* name;
+#if DDL_DEVICE_BUILD
+    cudaEvent_t a, b;
+#endif
+};
+static long long g_launches = 0;
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof;
+
+void prof_begin(const char* name, ddl_stream_t stream) {
+    ++g_launches;
+#if DDL_DEVICE_BUILD
+    if (!g_prof_on) return;
+    ProfEvent e;
+    e.name = name ? name : "?";
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, stream);
+    g_prof.push_back(e);
+#else
+    (void)name; (void)stream;
+#endif
+}
+void prof_end(ddl_stream_t stream) {
+#if DDL_DEVICE_BUILD
+    if (g_prof_on && !g_prof.empty()) cudaEventRecord(g_prof.back().b, stream);
+#else
+    (void)stream;
+#endif
 }
 
 void* dev_alloc(size_t bytes) {
@@ -225,7 +260,7 @@ static int pick_c2c_group(int N, long long inner_len) {
 static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 1024 ? 1024 : t); }
 
 // complex pass of nf fields along an axis of length N
-static int pass_c2c(int N, int dir, int nf, const void* const* in, void* const* out, const TileSide& si,
+static int pass_c2c(const char* name, int N, int dir, int nf, const void* const* in, void* const* out, const TileSide& si,
                     const TileSide& so, int inner_len, int n_outer, double scale, const cplx* tw, ddl_stream_t st) {
     TileParams p;
     memset(&p, 0, sizeof(p));
@@ -234,13 +269,13 @@ static int pass_c2c(int N, int dir, int nf, const void* const* in, void* const* 
     p.G = pick_c2c_group(N, inner_len);
     p.inner_len = inner_len; p.n_outer = n_outer; p.kn = 0;
     p.ld = (si.s_n == 1 || so.s_n == 1) ? (p.G | 1) : p.G;
-    p.scale = scale; p.tw = tw;
+    p.scale = scale; p.tw = tw; p.name = name;
     const int rmax = N >= 8 ? 8 : 4;
     return run_tile(N, TM_C2C, dir, 0, p, round32(p.G * (N / rmax)), st);
 }
 
 // pair-mode pass (C2R / R2C / FUSED) over real lines
-static int pass_pair(int N, int mode, int phys, int ni, int no, const void* const* in, void* const* out,
+static int pass_pair(const char* name, int N, int mode, int phys, int ni, int no, const void* const* in, void* const* out,
                      const TileSide& si, const TileSide& so, int n_lines, int n_outer, int kn, double scale,
                      const cplx* tw, const PhysConst& pc, ddl_stream_t st) {
     TileParams p;
@@ -257,7 +292,7 @@ static int pass_pair(int N, int mode, int phys, int ni, int no, const void* cons
     p.G = g;
     p.inner_len = n_lines; p.n_outer = n_outer; p.kn = kn;
     p.ld = (g * p.nft) | 1;
-    p.scale = scale; p.tw = tw; p.pc = pc;
+    p.scale = scale; p.tw = tw; p.pc = pc; p.name = name;
     const int rmax = N >= 8 ? 8 : 4;
     return run_tile(N, mode, 0, phys, p, round32(g * p.nft * (N / rmax)), st);
 }
@@ -279,17 +314,17 @@ static int inverse_head(ddl_plan* pl, int nf, const void* const* kin, cplx* r0, 
         const long long KP = X.nk, ny = Y.n, nz = Z.n, CY = Y.cnt;
         for (int f = 0; f < nf; ++f) { A[f] = r0 + f * CY * nz * CX; B[f] = r1 + f * nz * ny * CX; }
         // z pass: k[ky][kz][kx] -> A[ky_c][z][kx_c]
-        DDL_TRY(pass_c2c(Z.n, +1, nf, kin, A.data(), side(KP, 1, nz * KP, Z.f2f, Y.c2f), side(CX, 1, nz * CX, nullptr, nullptr),
+        DDL_TRY(pass_c2c("z_inv", Z.n, +1, nf, kin, A.data(), side(KP, 1, nz * KP, Z.f2f, Y.c2f), side(CX, 1, nz * CX, nullptr, nullptr),
                          (int)CX, (int)CY, 1.0, Z.tw, st));
         // y pass: A[ky_c][z][kx_c] -> B[z][y][kx_c]
-        DDL_TRY(pass_c2c(Y.n, +1, nf, A.data(), B.data(), side(nz * CX, 1, CX, Y.f2c, nullptr), side(CX, 1, ny * CX, nullptr, nullptr),
+        DDL_TRY(pass_c2c("y_inv", Y.n, +1, nf, A.data(), B.data(), side(nz * CX, 1, CX, Y.f2c, nullptr), side(CX, 1, ny * CX, nullptr, nullptr),
                          (int)CX, (int)nz, 1.0, Y.tw, st));
         for (int f = 0; f < nf; ++f) heads[f] = B[f];
     } else {
         const long long ny = Y.n;
         for (int f = 0; f < nf; ++f) A[f] = r0 + f * CX * ny;
         // ky pass along contiguous lines: k[kx][ky] -> A[kx_c][y]
-        DDL_TRY(pass_c2c(Y.n, +1, nf, kin, A.data(), side(1, ny, 0, Y.f2f, nullptr), side(1, ny, 0, nullptr, nullptr),
+        DDL_TRY(pass_c2c("y_inv", Y.n, +1, nf, kin, A.data(), side(1, ny, 0, Y.f2f, nullptr), side(1, ny, 0, nullptr, nullptr),
                          (int)CX, 1, 1.0, Y.tw, st));
         for (int f = 0; f < nf; ++f) heads[f] = A[f];
     }
@@ -306,15 +341,15 @@ static int forward_tail(ddl_plan* pl, int nf, void* const* Cin, cplx* r0, void* 
         std::vector<void*> D(nf);
         for (int f = 0; f < nf; ++f) D[f] = r0 + f * CY * nz * CX;
         // y pass: C[z][y][kx_c] -> D[ky_c][z][kx_c]
-        DDL_TRY(pass_c2c(Y.n, -1, nf, Cin, D.data(), side(CX, 1, ny * CX, nullptr, nullptr), side(nz * CX, 1, CX, Y.f2c, nullptr),
+        DDL_TRY(pass_c2c("y_fwd", Y.n, -1, nf, Cin, D.data(), side(CX, 1, ny * CX, nullptr, nullptr), side(nz * CX, 1, CX, Y.f2c, nullptr),
                          (int)CX, (int)nz, 1.0, Y.tw, st));
         // z pass: D[ky_c][z][kx_c] -> E[ky_c][kz_c][kx_c]  or  k[ky][kz][kx]
         TileSide so = full_out ? side(KP, 1, nz * KP, Z.f2f, Y.c2f) : side(CX, 1, CZ * CX, Z.f2c, nullptr);
-        DDL_TRY(pass_c2c(Z.n, -1, nf, D.data(), dst, side(CX, 1, nz * CX, nullptr, nullptr), so, (int)CX, (int)CY, 1.0, Z.tw, st));
+        DDL_TRY(pass_c2c("z_fwd", Z.n, -1, nf, D.data(), dst, side(CX, 1, nz * CX, nullptr, nullptr), so, (int)CX, (int)CY, 1.0, Z.tw, st));
     } else {
         const long long ny = Y.n, CY = Y.cnt;
         TileSide so = full_out ? side(1, ny, 0, Y.f2f, nullptr) : side(1, CY, 0, Y.f2c, nullptr);
-        DDL_TRY(pass_c2c(Y.n, -1, nf, Cin, dst, side(1, ny, 0, nullptr, nullptr), so, (int)CX, 1, 1.0, Y.tw, st));
+        DDL_TRY(pass_c2c("y_fwd", Y.n, -1, nf, Cin, dst, side(1, ny, 0, nullptr, nullptr), so, (int)CX, 1, 1.0, Y.tw, st));
     }
     return 0;
 }
@@ -327,7 +362,7 @@ static int mask_arrays(ddl_plan* pl, int n, void* const* arr, ddl_stream_t st) {
         int c = n - done < DDL_MAXF ? n - done : DDL_MAXF;
         for (int i = 0; i < c; ++i) f.arr[i] = (cplx*)arr[done + i];
         f.narr = c;
-        DDL_TRY(launch_items(f, pl->nmodes, st));
+        DDL_TRY(launch_items(f, pl->nmodes, st, "mask"));
         done += c;
     }
     return 0;
@@ -360,9 +395,9 @@ extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t
     void* xo[1] = {x};
     PhysConst pc = {};
     if (pl->ndim == 3)
-        return pass_pair(X.n, TM_C2R, 0, 1, 1, head, xo, side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr),
+        return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr),
                          side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr), Y.n, Z.n, X.cnt, 1.0, X.tw, pc, st);
-    return pass_pair(X.n, TM_C2R, 0, 1, 1, head, xo, side(Y.n, 1, 0, nullptr, nullptr), side(1, X.n, 0, nullptr, nullptr),
+    return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(Y.n, 1, 0, nullptr, nullptr), side(1, X.n, 0, nullptr, nullptr),
                      Y.n, 1, X.cnt, 1.0, X.tw, pc, st);
 }
 
@@ -377,10 +412,10 @@ extern "C" int ddl_forward(ddl_plan* pl, const double* x, void* k, void* work, s
     PhysConst pc = {};
     const double sc = 1.0 / (double)pl->ntot;
     if (pl->ndim == 3)
-        DDL_TRY(pass_pair(X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr),
+        DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr),
                           side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr), Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
     else
-        DDL_TRY(pass_pair(X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, 0, nullptr, nullptr), side(Y.n, 1, 0, nullptr, nullptr),
+        DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, 0, nullptr, nullptr), side(Y.n, 1, 0, nullptr, nullptr),
                           Y.n, 1, X.cnt, sc, X.tw, pc, st));
     void* dst[1] = {k};
     DDL_TRY(forward_tail(pl, 1, C, r0, dst, true, st));
@@ -392,7 +427,7 @@ extern "C" int ddl_deriv(ddl_plan* pl, const void* k_in, void* k_out, int axis, 
     f.g = pl->geom; f.in = (const cplx*)k_in; f.out = (cplx*)k_out; f.level = -1;
     for (int l = 0; l < 3; ++l) if (pl->geom.ax[l] == axis) f.level = l;
     if (f.level < 0) { set_error("deriv: bad axis %d", axis); return -1; }
-    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream, "deriv");
 }
 
 // ---------------------------------------------------------------- fused RHS
@@ -424,7 +459,7 @@ static int assemble(ddl_plan* pl, cplx* E, void* const* state, void* const* deri
     for (int i = 0; i < PHYS::NS; ++i) f.S[i] = (const cplx*)state[i];
     for (int i = 0; i < PHYS::NC; ++i) f.D[i] = (cplx*)deriv[i];
     f.pc = pc;
-    return launch_items(f, per, st);
+    return launch_items(f, per, st, "assemble");
 }
 
 extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
@@ -459,13 +494,13 @@ extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, vo
         for (int f = 0; f < no; ++f) { C[f] = r2 + f * per; E[f] = r1 + f * pere; }
         Ebase = r1;
         TileSide s = side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr);
-        DDL_TRY(pass_pair(X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
+        DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
     } else {
         const long long per = (long long)X.cnt * Y.n, pere = (long long)X.cnt * Y.cnt;
         for (int f = 0; f < no; ++f) { C[f] = r1 + f * per; E[f] = r2 + f * pere; }
         Ebase = r2;
         TileSide s = side(Y.n, 1, 0, nullptr, nullptr);
-        DDL_TRY(pass_pair(X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st));
+        DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st));
     }
     DDL_TRY(forward_tail(pl, no, C.data(), r0, E.data(), false, st));
     switch (code) {
@@ -498,7 +533,7 @@ extern "C" int ddl_stage(ddl_plan* pl, int kind, int ncomp, void* const* start, 
         f.a.start[c] = (const cplx*)start[c]; f.a.out[c] = (cplx*)out[c]; f.a.d1[c] = (const cplx*)d1[c];
         f.a.d2[c] = d2 ? (const cplx*)d2[c] : nullptr;
     }
-    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream, "stage");
 }
 
 extern "C" int ddl_rk4_stage(ddl_plan* pl, int ncomp, void* const* y, void* const* k, void* const* total, void* const* out,
@@ -511,7 +546,7 @@ extern "C" int ddl_rk4_stage(ddl_plan* pl, int ncomp, void* const* y, void* cons
         f.a.start[c] = (const cplx*)y[c]; f.a.out[c] = (cplx*)out[c]; f.a.d1[c] = (const cplx*)k[c];
         f.a.total[c] = (cplx*)total[c];
     }
-    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream, "stage");
 }
 
 extern "C" int ddl_cn_step(ddl_plan* pl, int ncomp, void* const* y, void* const* k, const double* coeff, int visc_order,
@@ -520,7 +555,7 @@ extern "C" int ddl_cn_step(ddl_plan* pl, int ncomp, void* const* y, void* const*
     DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order));
     f.a.kind = SK_CN; f.a.dt = dt;
     for (int c = 0; c < ncomp; ++c) { f.a.start[c] = (const cplx*)y[c]; f.a.out[c] = (cplx*)y[c]; f.a.d1[c] = (const cplx*)k[c]; }
-    return launch_items(f, pl->nmodes, (ddl_stream_t)stream);
+    return launch_items(f, pl->nmodes, (ddl_stream_t)stream, "stage");
 }
 
 extern "C" int ddl_sync(void* stream) {
@@ -529,6 +564,43 @@ extern "C" int ddl_sync(void* stream) {
 #else
     (void)stream;
 #endif
+    return 0;
+}
+
+extern "C" long long ddl_launch_count(void) { return g_launches; }
+
+extern "C" int ddl_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+
+// Aggregate the recorded launches by kernel label into `buf` as JSON
+// {"label": {"n": launches, "ms": total device ms}, ...} and clear the record.
+extern "C" int ddl_profile_report(char* buf, size_t nbuf) {
+    std::vector<std::pair<std::string, std::pair<long long, double>>> agg;
+#if DDL_DEVICE_BUILD
+    DDL_CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& e : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+        bool found = false;
+        for (auto& a : agg) if (a.first == e.name) { a.second.first++; a.second.second += ms; found = true; break; }
+        if (!found) agg.push_back({e.name, {1, (double)ms}});
+    }
+#endif
+    g_prof.clear();
+    std::string out = "{";
+    for (size_t i = 0; i < agg.size(); ++i) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"n\": %lld, \"ms\": %.6f}", i ? ", " : "", agg[i].first.c_str(),
+                 agg[i].second.first, agg[i].second.second);
+        out += tmp;
+    }
+    out += "}";
+    if (out.size() + 1 > nbuf) { set_error("profile buffer too small"); return -1; }
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 

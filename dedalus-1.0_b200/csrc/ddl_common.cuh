@@ -48,6 +48,10 @@ void set_error(const char* fmt, ...);
     } while (0)
 #endif
 
+// launch accounting + optional per-launch CUDA-event timing (ddl_profile_* in include/ddl.h)
+void prof_begin(const char* name, ddl_stream_t stream);
+void prof_end(ddl_stream_t stream);
+
 // small device buffers owned by a plan (twiddles, index tables)
 void* dev_alloc(size_t bytes);
 void dev_free(void* p);

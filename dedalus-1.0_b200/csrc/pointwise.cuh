@@ -215,17 +215,19 @@ __global__ void items_kernel(const __grid_constant__ F f, long long count) {
 #endif
 
 template <class F>
-int launch_items(const F& f, long long count, ddl_stream_t stream) {
+int launch_items(const F& f, long long count, ddl_stream_t stream, const char* name = "pointwise") {
     if (count <= 0) return 0;
 #if DDL_DEVICE_BUILD
     const int threads = 256;
     long long blocks = (count + threads - 1) / threads;
     const long long cap = 148LL * 16;
     if (blocks > cap) blocks = cap;
+    prof_begin(name, stream);
     items_kernel<F><<<(unsigned)blocks, threads, 0, stream>>>(f, count);
+    prof_end(stream);
     DDL_CUDA_CHECK(cudaGetLastError());
 #else
-    (void)stream;
+    (void)stream; (void)name;
     for (long long i = 0; i < count; ++i) f(i);
 #endif
     return 0;

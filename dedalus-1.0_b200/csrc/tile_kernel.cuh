@@ -39,6 +39,7 @@ struct TileParams {
     double scale;
     const cplx* tw;
     PhysConst pc;
+    const char* name;     // label for launch accounting / profiling (host side only)
 };
 
 template <int N, int S_IDX, int DIR, bool DIT>
@@ -235,7 +236,9 @@ int launch_tile(const TileParams& p, int nthreads, ddl_stream_t stream) {
     auto kern = tile_kernel<N, MODE, DIR, PHYS>;
     if (smem > 48 * 1024) DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(gx, p.n_outer, gz);
+    prof_begin(p.name, stream);
     kern<<<grid, nthreads, smem, stream>>>(p);
+    prof_end(stream);
     DDL_CUDA_CHECK(cudaGetLastError());
 #else
     (void)nthreads; (void)stream;

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libddl_b200.so")
 EXPORTS = [
     "ddl_plan_create", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
     "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_deriv", "ddl_rhs", "ddl_stage",
-    "ddl_rk4_stage", "ddl_cn_step", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_rk4_stage", "ddl_cn_step", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
@@ -51,6 +51,9 @@ def _load():
     lib.ddl_stage.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, dbl, vp]
     lib.ddl_rk4_stage.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, dbl, dbl, i32, i32, vp]
     lib.ddl_cn_step.argtypes = [vp, i32, vp, vp, vp, i32, dbl, vp]
+    lib.ddl_launch_count.restype = C.c_longlong
+    lib.ddl_profile_enable.argtypes = [i32]
+    lib.ddl_profile_report.argtypes = [C.c_char_p, sz]
     lib.ddl_sync.argtypes = [vp]
     lib.ddl_last_error.restype = C.c_char_p
     lib.ddl_version.restype = C.c_char_p
@@ -68,3 +71,19 @@ def check(rc):
 def ptr_array(tensors):
     """(void*)[n] of device pointers; keep the tensors alive while it is in use."""
     return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def launch_count():
+    return int(lib.ddl_launch_count())
+
+
+def profile(enable):
+    check(lib.ddl_profile_enable(1 if enable else 0))
+
+
+def profile_report():
+    """{label: {"n": launches, "ms": device ms}} for the launches recorded since profile(True)."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.ddl_profile_report(buf, len(buf)))
+    return json.loads(buf.value.decode())

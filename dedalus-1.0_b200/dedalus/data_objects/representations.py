@@ -106,7 +106,7 @@ class FourierRepresentation(Representation):
                 data = data.real
             if data.dim() == target.dim():
                 data = data[tuple(slice(int(n)) for n in target.shape)]
-            target.copy_(data)
+            target.copy_(data, non_blocking=True)
         self._curr_space = space
 
     def require_space(self, space):

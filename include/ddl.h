@@ -95,6 +95,12 @@ int ddl_rk4_stage(ddl_plan* plan, int ncomp, void* const* y, void* const* k, voi
 int ddl_cn_step(ddl_plan* plan, int ncomp, void* const* y, void* const* k, const double* coeff,
                 int visc_order, double dt, void* stream);
 
+/* launch accounting: cumulative number of kernels this library has launched in the process,
+ * and optional per-launch CUDA-event timing aggregated by kernel label (bench.py roofline) */
+long long ddl_launch_count(void);
+int ddl_profile_enable(int on);
+int ddl_profile_report(char* json_out, size_t nbytes);
+
 int ddl_sync(void* stream);
 const char* ddl_last_error(void);
 const char* ddl_version(void);
