@@ -154,11 +154,15 @@ def run_ours(args):
     l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if args.quick:
+        torch.cuda.profiler.start()          # ncu --profile-from-start off captures only this region
     e0.record()
     for _ in range(args.steps):
         ti.do_advance(data, dt)
     e1.record()
     torch.cuda.synchronize()
+    if args.quick:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = L.launch_count() - l0
     clocks = sampler.stop()
@@ -166,6 +170,10 @@ def run_ours(args):
     ekin, emag = va.ekin(data), va.emag(data)
     assert np.isfinite(ekin) and np.isfinite(emag)
 
+    if args.quick:
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "quick": True,
+                          "gpu_launches": launches}))
+        return
     # ---- instrumented pass: per-kernel CUDA-event durations (not part of `value`)
     L.profile(True)
     for _ in range(2):
@@ -261,6 +269,7 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=512, help="grid size per axis (headline: 512)")
     ap.add_argument("--cpu-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--quick", action="store_true", help="timed region only (for runs under ncu)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

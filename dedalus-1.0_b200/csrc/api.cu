@@ -514,18 +514,36 @@ extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, vo
 }
 
 // ---------------------------------------------------------------- stage updates
-static int fill_stage(ddl_plan* pl, StageArgs& a, int ncomp, const double* coeff, int vo) {
+static int fill_stage(ddl_plan* pl, StageArgs& a, int ncomp, const double* coeff, int vo, int flags, long long& count) {
     if (ncomp < 1 || ncomp > DDL_MAXC) { set_error("ncomp %d out of range 1..%d", ncomp, DDL_MAXC); return -1; }
     memset(&a, 0, sizeof(a));
     a.g = pl->geom; a.ncomp = ncomp; a.vo = vo;
     for (int c = 0; c < ncomp; ++c) a.coeff[c] = coeff ? coeff[c] : 0.0;
+    count = pl->nmodes;
+    if (flags & DDL_STAGE_RETAINED_ONLY) {
+        const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+        a.compact = 1;
+        if (pl->ndim == 3) {
+            a.cdim[0] = Y.cnt; a.cdim[1] = Z.cnt; a.cdim[2] = X.cnt;
+            a.fstride[0] = (long long)Z.n * X.nk; a.fstride[1] = X.nk; a.fstride[2] = 1;
+            a.ftab[0] = Y.c2f; a.ftab[1] = Z.c2f; a.ftab[2] = nullptr;
+            a.kvc[0] = Y.kvc; a.kvc[1] = Z.kvc; a.kvc[2] = X.kvc;
+        } else {
+            a.cdim[0] = 1; a.cdim[1] = X.cnt; a.cdim[2] = Y.cnt;
+            a.fstride[0] = 0; a.fstride[1] = Y.n; a.fstride[2] = 1;
+            a.ftab[0] = nullptr; a.ftab[1] = nullptr; a.ftab[2] = Y.c2f;
+            a.kvc[0] = nullptr; a.kvc[1] = X.kvc; a.kvc[2] = Y.kvc;
+        }
+        count = (long long)a.cdim[0] * a.cdim[1] * a.cdim[2];
+    }
     return 0;
 }
 
 extern "C" int ddl_stage(ddl_plan* pl, int kind, int ncomp, void* const* start, void* const* out, void* const* d1,
-                         void* const* d2, const double* coeff, int visc_order, double dt, void* stream) {
+                         void* const* d2, const double* coeff, int visc_order, double dt, int flags, void* stream) {
     StageF f;
-    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order));
+    long long count;
+    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order, flags, count));
     if (kind < DDL_EULER || kind > DDL_ETD2RK2) { set_error("bad stage kind %d", kind); return -1; }
     if ((kind == DDL_ETD2RK1 || kind == DDL_ETD2RK2) && !d2) { set_error("stage kind %d needs deriv2", kind); return -1; }
     f.a.kind = kind; f.a.dt = dt;
@@ -533,29 +551,31 @@ extern "C" int ddl_stage(ddl_plan* pl, int kind, int ncomp, void* const* start, 
         f.a.start[c] = (const cplx*)start[c]; f.a.out[c] = (cplx*)out[c]; f.a.d1[c] = (const cplx*)d1[c];
         f.a.d2[c] = d2 ? (const cplx*)d2[c] : nullptr;
     }
-    return launch_items(f, pl->nmodes, (ddl_stream_t)stream, "stage");
+    return launch_items(f, count, (ddl_stream_t)stream, "stage");
 }
 
 extern "C" int ddl_rk4_stage(ddl_plan* pl, int ncomp, void* const* y, void* const* k, void* const* total, void* const* out,
                              const double* coeff, int visc_order, double wdiv, double dt_step, int first, int last,
-                             void* stream) {
+                             int flags, void* stream) {
     StageF f;
-    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order));
+    long long count;
+    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order, flags, count));
     f.a.kind = SK_RK4; f.a.dt = dt_step; f.a.wdiv = wdiv; f.a.first = first; f.a.last = last;
     for (int c = 0; c < ncomp; ++c) {
         f.a.start[c] = (const cplx*)y[c]; f.a.out[c] = (cplx*)out[c]; f.a.d1[c] = (const cplx*)k[c];
         f.a.total[c] = (cplx*)total[c];
     }
-    return launch_items(f, pl->nmodes, (ddl_stream_t)stream, "stage");
+    return launch_items(f, count, (ddl_stream_t)stream, "stage");
 }
 
 extern "C" int ddl_cn_step(ddl_plan* pl, int ncomp, void* const* y, void* const* k, const double* coeff, int visc_order,
-                           double dt, void* stream) {
+                           double dt, int flags, void* stream) {
     StageF f;
-    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order));
+    long long count;
+    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order, flags, count));
     f.a.kind = SK_CN; f.a.dt = dt;
     for (int c = 0; c < ncomp; ++c) { f.a.start[c] = (const cplx*)y[c]; f.a.out[c] = (cplx*)y[c]; f.a.d1[c] = (const cplx*)k[c]; }
-    return launch_items(f, pl->nmodes, (ddl_stream_t)stream, "stage");
+    return launch_items(f, count, (ddl_stream_t)stream, "stage");
 }
 
 extern "C" int ddl_sync(void* stream) {

@@ -82,6 +82,13 @@ struct StageArgs {
     double coeff[DDL_MAXC];
     int ncomp, kind, vo, first, last;
     double dt, wdiv;
+    // compact sweep: visit only the retained modes (every operand is known to vanish outside
+    // the dealias mask, so the update there is 0 -> 0)
+    int compact;
+    int cdim[3];
+    long long fstride[3];
+    const int* ftab[3];
+    const double* kvc[3];
 };
 
 enum { SK_EULER = 0, SK_ETD1 = 1, SK_ETD2RK1 = 2, SK_ETD2RK2 = 3, SK_RK4 = 4, SK_CN = 5 };
@@ -96,8 +103,23 @@ struct StageF {
     StageArgs a;
     DDL_HD void operator()(long long i) const {
         int ia, ib, ic;
-        split3(i, a.g.dim, ia, ib, ic);
-        const double pw = ipow(ksq(a.g, ia, ib, ic), a.vo);
+        double k2;
+        if (a.compact) {
+            int j[3];
+            split3(i, a.cdim, j[0], j[1], j[2]);
+            long long fi = 0;
+            k2 = 0.0;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                fi += (long long)(a.ftab[l] ? a.ftab[l][j[l]] : j[l]) * a.fstride[l];
+                if (a.kvc[l]) { const double v = a.kvc[l][j[l]]; k2 += v * v; }
+            }
+            i = fi;
+        } else {
+            split3(i, a.g.dim, ia, ib, ic);
+            k2 = ksq(a.g, ia, ib, ic);
+        }
+        const double pw = ipow(k2, a.vo);
         double lastc = -1.0, Z = 0.0, f0 = 1.0, f1 = 1.0, f2 = 0.5;
         for (int c = 0; c < a.ncomp; ++c) {
             const double co = a.coeff[c];

@@ -19,6 +19,7 @@ EXPORTS = [
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
 EULER, ETD1, ETD2RK1, ETD2RK2 = 0, 1, 2, 3
 RHS_ZERO_FILL, RHS_DEALIAS_STATE = 1, 2
+STAGE_RETAINED_ONLY = 1
 
 
 class PhysParams(C.Structure):
@@ -48,9 +49,9 @@ def _load():
     lib.ddl_dealias.argtypes = [vp, vp, vp]
     lib.ddl_deriv.argtypes = [vp, vp, vp, i32, vp]
     lib.ddl_rhs.argtypes = [vp, i32, C.POINTER(PhysParams), vp, vp, vp, sz, i32, vp]
-    lib.ddl_stage.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, dbl, vp]
-    lib.ddl_rk4_stage.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, dbl, dbl, i32, i32, vp]
-    lib.ddl_cn_step.argtypes = [vp, i32, vp, vp, vp, i32, dbl, vp]
+    lib.ddl_stage.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, dbl, i32, vp]
+    lib.ddl_rk4_stage.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, dbl, dbl, i32, i32, i32, vp]
+    lib.ddl_cn_step.argtypes = [vp, i32, vp, vp, vp, i32, dbl, i32, vp]
     lib.ddl_launch_count.restype = C.c_longlong
     lib.ddl_profile_enable.argtypes = [i32]
     lib.ddl_profile_report.argtypes = [C.c_char_p, sz]

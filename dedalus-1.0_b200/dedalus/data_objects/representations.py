@@ -66,8 +66,12 @@ class FourierRepresentation(Representation):
         self.dk, self.kny, self.k = pl.dk, pl.kny, pl.k
         self.set_dealiasing(dealiasing)
 
-        self.kdata = torch.zeros(tuple(int(n) for n in pl.kshape), dtype=torch.complex128, device=pl.device)
+        self._k = torch.zeros(tuple(int(n) for n in pl.kshape), dtype=torch.complex128, device=pl.device)
         self._xdata = None          # allocated on first use: most components never leave k-space
+        # True while the spectrum is KNOWN to vanish outside the dealias mask (set by our own
+        # kernels, cleared whenever the buffer is handed to the caller, who may write to it);
+        # lets the RHS skip mask passes and the RK sweep visit the retained modes only
+        self._clean = True
         self._curr_space = "kspace"
         self.integrating_factor = None
         self.fwd_count = 0
@@ -82,6 +86,13 @@ class FourierRepresentation(Representation):
         return self._xdata
 
     @property
+    def kdata(self):
+        """The k-space buffer.  Handing it out means the caller may modify it: the
+        'zero outside the mask' knowledge is dropped (internal code uses _k)."""
+        self._clean = False
+        return self._k
+
+    @property
     def data(self):
         return self.kdata if self._curr_space == "kspace" else self.xdata
 
@@ -94,7 +105,8 @@ class FourierRepresentation(Representation):
         if space == "xspace":
             target = self.xdata
         elif space == "kspace":
-            target = self.kdata
+            target = self._k
+            self._clean = isinstance(data, (float, complex, int)) and data == 0
         else:
             raise KeyError("space must be either xspace or kspace.")
         if isinstance(data, (float, complex, int)):
@@ -127,9 +139,10 @@ class FourierRepresentation(Representation):
             raise ValueError("Forward transform cannot be called from kspace.")
         pl = self._plan
         w = pl.transform_workspace()
-        check(lib.ddl_forward(pl.handle, self.xdata.data_ptr(), self.kdata.data_ptr(), w.data_ptr(), w.numel(),
+        check(lib.ddl_forward(pl.handle, self.xdata.data_ptr(), self._k.data_ptr(), w.data_ptr(), w.numel(),
                               _plan.current_stream()))
         self._curr_space = "kspace"
+        self._clean = True
         self.fwd_count += 1
 
     @timer
@@ -139,9 +152,10 @@ class FourierRepresentation(Representation):
             raise ValueError("Backward transform cannot be called from xspace.")
         pl = self._plan
         w = pl.transform_workspace()
-        check(lib.ddl_backward(pl.handle, self.kdata.data_ptr(), self.xdata.data_ptr(), w.data_ptr(), w.numel(),
+        check(lib.ddl_backward(pl.handle, self._k.data_ptr(), self.xdata.data_ptr(), w.data_ptr(), w.numel(),
                                _plan.current_stream()))
         self._curr_space = "xspace"
+        self._clean = True
         self.rev_count += 1
 
     fft = forward
@@ -162,7 +176,8 @@ class FourierRepresentation(Representation):
     def dealias(self):
         """Zero the modes outside the plan's mask, in place (dealias_cy_{2,3}d.pyx)."""
         self.require_space("kspace")
-        check(lib.ddl_dealias(self._plan.handle, self.kdata.data_ptr(), _plan.current_stream()))
+        check(lib.ddl_dealias(self._plan.handle, self._k.data_ptr(), _plan.current_stream()))
+        self._clean = True
 
     dealias_23 = dealias
     dealias_23_cython = dealias
@@ -180,14 +195,14 @@ class FourierRepresentation(Representation):
     def deriv(self, dim):
         """i k_dim * data (representations.py:419-425); returns a fresh tensor."""
         self.require_space("kspace")
-        out = torch.empty_like(self.kdata)
-        check(lib.ddl_deriv(self._plan.handle, self.kdata.data_ptr(), out.data_ptr(), {"x": 0, "y": 1, "z": 2}[dim],
+        out = torch.empty_like(self._k)
+        check(lib.ddl_deriv(self._plan.handle, self._k.data_ptr(), out.data_ptr(), {"x": 0, "y": 1, "z": 2}[dim],
                             _plan.current_stream()))
         return out
 
     def k2(self, no_zero=False, set_zero=1.0):
         """|k|^2, summed in the reference's order (representations.py:427-440)."""
-        k2 = torch.zeros(tuple(int(n) for n in self.local_shape["kspace"]), dtype=torch.float64, device=self.kdata.device)
+        k2 = torch.zeros(tuple(int(n) for n in self.local_shape["kspace"]), dtype=torch.float64, device=self._k.device)
         for kv in self.k.values():
             k2 += kv ** 2
         if no_zero:
@@ -241,7 +256,7 @@ class FourierRepresentation(Representation):
         """Coordinates of the local x-space points, [ndim, ...] (representations.py:528-548)."""
         n = [int(v) for v in self.local_shape["xspace"]]
         dx = self.dx()
-        axes = [torch.arange(n[i], dtype=torch.float64, device=self.kdata.device) * float(dx[i]) for i in range(self.ndim)]
+        axes = [torch.arange(n[i], dtype=torch.float64, device=self._k.device) * float(dx[i]) for i in range(self.ndim)]
         axes[0] = axes[0] + self.offset["xspace"] * float(dx[0])
         if open:
             return [a.reshape([-1 if j == i else 1 for j in range(self.ndim)]) for i, a in enumerate(axes)]

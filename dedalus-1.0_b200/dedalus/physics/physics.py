@@ -138,19 +138,31 @@ class Physics(object):
             raise NotImplementedError(
                 "The fused RHS uses conservative products, which equal the reference's advective form only under "
                 "2/3 dealiasing; FFT.dealiasing=%r is not supported." % decfg.get("FFT", "dealiasing"))
-        state = []
+        state, out = [], []
+        state_clean = deriv_clean = True
         for _, _, c in data.components():
             c.require_space("kspace")
-            state.append(c.kdata)
-        out = []
+            state.append(c._k)
+            state_clean = state_clean and c._clean
         for _, _, c in deriv.components():
             c._curr_space = "kspace"
-            out.append(c.kdata)
+            out.append(c._k)
+            deriv_clean = deriv_clean and c._clean
+        # mask passes only where the buffers are not already known to be zero outside the mask
+        if deriv_clean:
+            flags &= ~_lib.RHS_ZERO_FILL
+        if state_clean:
+            flags &= ~_lib.RHS_DEALIAS_STATE
         pl = next(data.components())[2]._plan
         w = pl.rhs_workspace(self._physics_id)
         pp = self._phys_params()
         check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), _lib.ptr_array(out),
                           w.data_ptr(), w.numel(), flags, _plan.current_stream()))
+        for _, _, c in deriv.components():
+            c._clean = True
+        if flags & _lib.RHS_DEALIAS_STATE:
+            for _, _, c in data.components():
+                c._clean = True
         deriv.set_time(data.time)
 
     # ------------------------------------------------------------------ unfused helpers

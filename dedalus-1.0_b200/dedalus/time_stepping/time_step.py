@@ -32,8 +32,18 @@ def _kspace_tensors(sd):
     out = []
     for _, _, c in sd.components():
         c.require_space("kspace")
-        out.append(c.kdata)
+        out.append(c._k)
     return out
+
+
+def _all_clean(*sds):
+    """True when every component of every StateData is known to vanish outside the dealias mask."""
+    return all(c._clean for sd in sds if sd is not None for _, _, c in sd.components())
+
+
+def _mark(sd, clean):
+    for _, _, c in sd.components():
+        c._clean = clean
 
 
 def _plan_of(sd):
@@ -152,9 +162,11 @@ class TimeStepBase(object):
         s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
         b = _kspace_tensors(d2) if d2 is not None else None
         coeff, order = _if_coefficients(if_from)
+        clean = _all_clean(start, out, d1, d2)
         check(lib.ddl_stage(_plan_of(start).handle, kind, len(s), _lib.ptr_array(s), _lib.ptr_array(o),
                             _lib.ptr_array(a), _lib.ptr_array(b) if b is not None else None, coeff, order,
-                            float(dt), _plan.current_stream()))
+                            float(dt), _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
+        _mark(out, clean)
 
 
 class RKBase(TimeStepBase):
@@ -224,9 +236,12 @@ class RK4(RKBase):
         ys, ks = _kspace_tensors(y), _kspace_tensors(self.k_data)
         ts, os_ = _kspace_tensors(self.total_deriv), _kspace_tensors(out)
         coeff, order = self._coeff
+        clean = _all_clean(y, self.k_data, self.total_deriv, out)
         check(lib.ddl_rk4_stage(pl.handle, len(ys), _lib.ptr_array(ys), _lib.ptr_array(ks), _lib.ptr_array(ts),
                                 _lib.ptr_array(os_), coeff, order, float(wdiv), float(dt_step), int(first), int(last),
-                                _plan.current_stream()))
+                                _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
+        _mark(out, clean)
+        _mark(self.total_deriv, clean)
 
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
@@ -277,8 +292,10 @@ class CrankNicholsonVisc(TimeStepBase):
             self._coeff = _if_coefficients(self.deriv)
         ys, ks = _kspace_tensors(data), _kspace_tensors(self.deriv)
         coeff, order = self._coeff
+        clean = _all_clean(data, self.deriv)
         check(lib.ddl_cn_step(_plan_of(data).handle, len(ys), _lib.ptr_array(ys), _lib.ptr_array(ks), coeff, order,
-                              float(dt), _plan.current_stream()))
+                              float(dt), _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
+        _mark(data, clean)
         data.set_time(data.time + dt)
         self.time += dt
         self.iteration += 1

@@ -36,6 +36,12 @@ enum {
                                    representations.py:353) */
 };
 
+/* stage-update flags */
+enum {
+    DDL_STAGE_RETAINED_ONLY = 1 /* every operand is known to vanish outside the dealias mask:
+                                   sweep the retained modes only (the update maps 0 -> 0 there) */
+};
+
 typedef struct ddl_phys_params {
     double rho0;        /* physics.py:753 */
     double g, alpha_t, beta;  /* physics.py:643-645 */
@@ -82,18 +88,18 @@ int ddl_rhs(ddl_plan* plan, int physics, const ddl_phys_params* params,
  * Euler branch).  deriv2 may be NULL for EULER / ETD1.  out may alias start.            */
 int ddl_stage(ddl_plan* plan, int kind, int ncomp, void* const* start, void* const* out,
               void* const* deriv1, void* const* deriv2, const double* coeff, int visc_order,
-              double dt, void* stream);
+              double dt, int flags, void* stream);
 
 /* One stage of the restated RK4 (time_step.py:395-483 + forward_step :187-221):
  *   total = (first ? 0 : total) + k / wdiv ;  if (!last) out = S(y, k, dt_step)
  *   else out = S(y, total, dt_step),  S = euler / etd1(-IF)                              */
 int ddl_rk4_stage(ddl_plan* plan, int ncomp, void* const* y, void* const* k, void* const* total,
                   void* const* out, const double* coeff, int visc_order, double wdiv,
-                  double dt_step, int first, int last, void* stream);
+                  double dt_step, int first, int last, int flags, void* stream);
 
 /* restated CrankNicholsonVisc (time_step.py:486-506): y = (top/bottom) y + k / bottom */
 int ddl_cn_step(ddl_plan* plan, int ncomp, void* const* y, void* const* k, const double* coeff,
-                int visc_order, double dt, void* stream);
+                int visc_order, double dt, int flags, void* stream);
 
 /* launch accounting: cumulative number of kernels this library has launched in the process,
  * and optional per-launch CUDA-event timing aggregated by kernel label (bench.py roofline) */

@@ -104,10 +104,10 @@ class EmulPlan:
                                     flags, None))
         return np.stack(deriv), np.stack(state)
 
-    def stage(self, kind, start, d1, d2, coeff, vo, dt):
+    def stage(self, kind, start, d1, d2, coeff, vo, dt, flags=0):
         n = len(start)
-        out = [np.empty_like(s) for s in start]
+        out = [np.zeros_like(s) for s in start]
         co = np.ascontiguousarray(coeff, dtype=np.float64)
         self.check(self.lib.ddl_stage(self.plan, kind, n, _pa(start), _pa(out), _pa(d1), _pa(d2) if d2 is not None else None,
-                                      _p(co), vo, C.c_double(dt), None))
+                                      _p(co), vo, C.c_double(dt), flags, None))
         return out

@@ -114,3 +114,21 @@ def test_emulated_stage_kernels_match_oracle(lib, shape):
                 else:
                     fn(start[c], ref, d1[c], d2[c], IF, dt)
                 assert rel(out[c], ref) < 1e-15, (kind, c, vo)
+
+
+@pytest.mark.parametrize("shape", [(16, 32), (8, 16, 16)])
+def test_emulated_retained_only_sweep_equals_full_sweep(lib, shape):
+    """DDL_STAGE_RETAINED_ONLY visits only the modes inside the dealias mask; with operands that
+    vanish outside it the result must equal the full sweep bit for bit."""
+    g = orc.Grid(shape, None)
+    pl = emul.EmulPlan(lib, g)
+    rng = np.random.default_rng(9)
+    keep = ~g.dealias_mask()
+    mk = lambda: np.ascontiguousarray((rng.standard_normal(g.kshape) + 1j * rng.standard_normal(g.kshape)) * keep)
+    start, d1, d2 = [mk() for _ in range(2)], [mk() for _ in range(2)], [mk() for _ in range(2)]
+    for kind in (1, 2, 3):
+        full = pl.stage(kind, start, d1, d2, [0.01, 0.2], 1, 0.05, flags=0)
+        part = pl.stage(kind, start, d1, d2, [0.01, 0.2], 1, 0.05, flags=1)
+        for a, b in zip(full, part):
+            assert np.array_equal(a * keep, b * keep)
+            assert np.all(a[~keep] == 0)
