@@ -8,6 +8,7 @@
 #include "../../include/ddl.h"
 #include "pointwise.cuh"
 #include "tile_kernel.cuh"
+#include "fast_kernels.cuh"
 
 namespace ddl {
 
@@ -93,6 +94,23 @@ static int run_tile(int N, int mode, int dir, int phys, const TileParams& p, int
     set_error("unsupported transform length %d (powers of two 8..2048)", N);
     return -1;
 }
+
+#if DDL_DEVICE_BUILD
+#define DDL_DECLF(N) int run_fast_strided_##N(int, const FastParams&, int, int, const char*, ddl_stream_t);
+DDL_DECLF(8) DDL_DECLF(16) DDL_DECLF(32) DDL_DECLF(64) DDL_DECLF(128) DDL_DECLF(256) DDL_DECLF(512) DDL_DECLF(1024)
+DDL_DECLF(2048)
+static int run_fast_strided(int N, int dir, const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
+    switch (N) {
+#define DDL_CASEF(N) case N: return run_fast_strided_##N(dir, p, nf, n_outer, name, s);
+        DDL_CASEF(8) DDL_CASEF(16) DDL_CASEF(32) DDL_CASEF(64) DDL_CASEF(128) DDL_CASEF(256) DDL_CASEF(512)
+        DDL_CASEF(1024) DDL_CASEF(2048)
+    }
+    return 1;
+}
+#endif
+
+// generic kernels only (set by ddl_set_option("fast_kernels", 0); used by the tests to compare)
+static int g_use_fast = 1;
 
 template <class T>
 static T* upload_vec(const std::vector<T>& v) {
@@ -207,9 +225,13 @@ extern "C" int ddl_plan_destroy(ddl_plan* pl) {
 struct WsLayout {
     long long r0, r1, r2;   // region sizes in cplx elements
 };
+// pitch of the retained-kx axis in the 3-D workspace arrays: a multiple of 8 complex (128 B)
+// so that every CX-wide row segment of the strided passes is a whole number of cache lines
+static long long kx_pitch(const ddl_plan* pl) { return pl->ndim == 3 ? (pl->ax.cnt + 7) / 8 * 8 : pl->ax.cnt; }
+
 static WsLayout ws_layout(const ddl_plan* pl, int ni, int no) {
     WsLayout w;
-    const long long CX = pl->ax.cnt, CY = pl->ay.cnt;
+    const long long CX = kx_pitch(pl), CY = pl->ay.cnt;
     if (pl->ndim == 3) {
         const long long CZ = pl->az.cnt, ny = pl->ay.n, nz = pl->az.n;
         const int nmax = ni > no ? ni : no;
@@ -260,8 +282,26 @@ static int pick_c2c_group(int N, long long inner_len) {
 static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 1024 ? 1024 : t); }
 
 // complex pass of nf fields along an axis of length N
+struct RowSpec { int m; int compact; };   // retained rows of a pruned axis (m < 0: all rows present)
+static const RowSpec ALL_ROWS = {-1, 0};
+
 static int pass_c2c(const char* name, int N, int dir, int nf, const void* const* in, void* const* out, const TileSide& si,
-                    const TileSide& so, int inner_len, int n_outer, double scale, const cplx* tw, ddl_stream_t st) {
+                    const TileSide& so, RowSpec ri, RowSpec ro, int inner_len, int n_outer, double scale, const cplx* tw,
+                    ddl_stream_t st) {
+#if DDL_DEVICE_BUILD
+    if (g_use_fast && si.s_inner == 1 && so.s_inner == 1 && si.s_n != 1 && so.s_n != 1 && nf <= DDL_MAXF) {
+        FastParams f;
+        memset(&f, 0, sizeof(f));
+        for (int i = 0; i < nf; ++i) { f.in[i] = (const cplx*)in[i]; f.out[i] = (cplx*)out[i]; }
+        f.si.s_n = si.s_n; f.si.s_outer = si.s_outer; f.si.outer_tab = si.outer_tab; f.si.m = ri.m; f.si.compact = ri.compact;
+        f.so.s_n = so.s_n; f.so.s_outer = so.s_outer; f.so.outer_tab = so.outer_tab; f.so.m = ro.m; f.so.compact = ro.compact;
+        f.inner_len = inner_len; f.scale = scale; f.tw = tw;
+        int rc = run_fast_strided(N, dir, f, nf, n_outer, name, st);
+        if (rc <= 0) return rc;
+    }
+#else
+    (void)ri; (void)ro;
+#endif
     TileParams p;
     memset(&p, 0, sizeof(p));
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
@@ -308,24 +348,25 @@ static TileSide side(long long s_n, long long s_inner, long long s_outer, const 
 // arrays ready for the pair pass.  3-D: k -> A -> B ; 2-D: k -> A.
 static int inverse_head(ddl_plan* pl, int nf, const void* const* kin, cplx* r0, cplx* r1, void** heads, ddl_stream_t st) {
     const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
-    const long long CX = X.cnt;
+    const long long CX = kx_pitch(pl);
+    const int nkx = X.cnt;
     std::vector<void*> A(nf), B(nf);
     if (pl->ndim == 3) {
         const long long KP = X.nk, ny = Y.n, nz = Z.n, CY = Y.cnt;
         for (int f = 0; f < nf; ++f) { A[f] = r0 + f * CY * nz * CX; B[f] = r1 + f * nz * ny * CX; }
         // z pass: k[ky][kz][kx] -> A[ky_c][z][kx_c]
         DDL_TRY(pass_c2c("z_inv", Z.n, +1, nf, kin, A.data(), side(KP, 1, nz * KP, Z.f2f, Y.c2f), side(CX, 1, nz * CX, nullptr, nullptr),
-                         (int)CX, (int)CY, 1.0, Z.tw, st));
+                         RowSpec{Z.m, 0}, ALL_ROWS, nkx, (int)CY, 1.0, Z.tw, st));
         // y pass: A[ky_c][z][kx_c] -> B[z][y][kx_c]
         DDL_TRY(pass_c2c("y_inv", Y.n, +1, nf, A.data(), B.data(), side(nz * CX, 1, CX, Y.f2c, nullptr), side(CX, 1, ny * CX, nullptr, nullptr),
-                         (int)CX, (int)nz, 1.0, Y.tw, st));
+                         RowSpec{Y.m, 1}, ALL_ROWS, nkx, (int)nz, 1.0, Y.tw, st));
         for (int f = 0; f < nf; ++f) heads[f] = B[f];
     } else {
         const long long ny = Y.n;
         for (int f = 0; f < nf; ++f) A[f] = r0 + f * CX * ny;
         // ky pass along contiguous lines: k[kx][ky] -> A[kx_c][y]
         DDL_TRY(pass_c2c("y_inv", Y.n, +1, nf, kin, A.data(), side(1, ny, 0, Y.f2f, nullptr), side(1, ny, 0, nullptr, nullptr),
-                         (int)CX, 1, 1.0, Y.tw, st));
+                         RowSpec{Y.m, 0}, ALL_ROWS, nkx, 1, 1.0, Y.tw, st));
         for (int f = 0; f < nf; ++f) heads[f] = A[f];
     }
     return 0;
@@ -335,21 +376,24 @@ static int inverse_head(ddl_plan* pl, int nf, const void* const* kin, cplx* r0, 
 // full-layout k arrays (transform API) instead of the compact product arrays E.
 static int forward_tail(ddl_plan* pl, int nf, void* const* Cin, cplx* r0, void* const* dst, bool full_out, ddl_stream_t st) {
     const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
-    const long long CX = X.cnt;
+    const long long CX = kx_pitch(pl);
+    const int nkx = X.cnt;
     if (pl->ndim == 3) {
         const long long KP = X.nk, ny = Y.n, nz = Z.n, CY = Y.cnt, CZ = Z.cnt;
         std::vector<void*> D(nf);
         for (int f = 0; f < nf; ++f) D[f] = r0 + f * CY * nz * CX;
         // y pass: C[z][y][kx_c] -> D[ky_c][z][kx_c]
         DDL_TRY(pass_c2c("y_fwd", Y.n, -1, nf, Cin, D.data(), side(CX, 1, ny * CX, nullptr, nullptr), side(nz * CX, 1, CX, Y.f2c, nullptr),
-                         (int)CX, (int)nz, 1.0, Y.tw, st));
+                         ALL_ROWS, RowSpec{Y.m, 1}, nkx, (int)nz, 1.0, Y.tw, st));
         // z pass: D[ky_c][z][kx_c] -> E[ky_c][kz_c][kx_c]  or  k[ky][kz][kx]
         TileSide so = full_out ? side(KP, 1, nz * KP, Z.f2f, Y.c2f) : side(CX, 1, CZ * CX, Z.f2c, nullptr);
-        DDL_TRY(pass_c2c("z_fwd", Z.n, -1, nf, D.data(), dst, side(CX, 1, nz * CX, nullptr, nullptr), so, (int)CX, (int)CY, 1.0, Z.tw, st));
+        DDL_TRY(pass_c2c("z_fwd", Z.n, -1, nf, D.data(), dst, side(CX, 1, nz * CX, nullptr, nullptr), so, ALL_ROWS,
+                         RowSpec{Z.m, full_out ? 0 : 1}, nkx, (int)CY, 1.0, Z.tw, st));
     } else {
         const long long ny = Y.n, CY = Y.cnt;
         TileSide so = full_out ? side(1, ny, 0, Y.f2f, nullptr) : side(1, CY, 0, Y.f2c, nullptr);
-        DDL_TRY(pass_c2c("y_fwd", Y.n, -1, nf, Cin, dst, side(1, ny, 0, nullptr, nullptr), so, (int)CX, 1, 1.0, Y.tw, st));
+        DDL_TRY(pass_c2c("y_fwd", Y.n, -1, nf, Cin, dst, side(1, ny, 0, nullptr, nullptr), so, ALL_ROWS,
+                         RowSpec{Y.m, full_out ? 0 : 1}, nkx, 1, 1.0, Y.tw, st));
     }
     return 0;
 }
@@ -395,7 +439,7 @@ extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t
     void* xo[1] = {x};
     PhysConst pc = {};
     if (pl->ndim == 3)
-        return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr),
+        return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr),
                          side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr), Y.n, Z.n, X.cnt, 1.0, X.tw, pc, st);
     return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(Y.n, 1, 0, nullptr, nullptr), side(1, X.n, 0, nullptr, nullptr),
                      Y.n, 1, X.cnt, 1.0, X.tw, pc, st);
@@ -413,7 +457,7 @@ extern "C" int ddl_forward(ddl_plan* pl, const double* x, void* k, void* work, s
     const double sc = 1.0 / (double)pl->ntot;
     if (pl->ndim == 3)
         DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr),
-                          side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr), Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
+                          side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr), Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
     else
         DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, 0, nullptr, nullptr), side(Y.n, 1, 0, nullptr, nullptr),
                           Y.n, 1, X.cnt, sc, X.tw, pc, st));
@@ -435,19 +479,21 @@ template <class PHYS>
 static int assemble(ddl_plan* pl, cplx* E, void* const* state, void* const* deriv, const PhysConst& pc, ddl_stream_t st) {
     AssembleF<PHYS> f;
     const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
-    const long long CX = X.cnt, CY = Y.cnt;
-    long long per;
+    const long long CX = X.cnt, CY = Y.cnt, KXP = kx_pitch(pl);
+    long long per, count;
     if (pl->ndim == 3) {
         const long long CZ = Z.cnt;
-        per = CY * CZ * CX;
+        per = CY * CZ * KXP;
+        count = CY * CZ * CX;
         f.cdim[0] = (int)CY; f.cdim[1] = (int)CZ; f.cdim[2] = (int)CX;
-        f.cstride[0] = CZ * CX; f.cstride[1] = CX; f.cstride[2] = 1;
+        f.cstride[0] = CZ * KXP; f.cstride[1] = KXP; f.cstride[2] = 1;
         f.fstride[0] = (long long)Z.n * X.nk; f.fstride[1] = X.nk; f.fstride[2] = 1;
         f.ftab[0] = Y.c2f; f.ftab[1] = Z.c2f; f.ftab[2] = nullptr;
         f.kvc[0] = Y.kvc; f.kvc[1] = Z.kvc; f.kvc[2] = X.kvc;
         f.ax[0] = 1; f.ax[1] = 2; f.ax[2] = 0;
     } else {
         per = CX * CY;
+        count = per;
         f.cdim[0] = 1; f.cdim[1] = (int)CX; f.cdim[2] = (int)CY;
         f.cstride[0] = 0; f.cstride[1] = CY; f.cstride[2] = 1;
         f.fstride[0] = 0; f.fstride[1] = Y.n; f.fstride[2] = 1;
@@ -459,7 +505,7 @@ static int assemble(ddl_plan* pl, cplx* E, void* const* state, void* const* deri
     for (int i = 0; i < PHYS::NS; ++i) f.S[i] = (const cplx*)state[i];
     for (int i = 0; i < PHYS::NC; ++i) f.D[i] = (cplx*)deriv[i];
     f.pc = pc;
-    return launch_items(f, per, st, "assemble");
+    return launch_items(f, count, st, "assemble");
 }
 
 extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
@@ -490,10 +536,11 @@ extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, vo
     const double sc = 1.0 / (double)pl->ntot;
     cplx* Ebase;
     if (pl->ndim == 3) {
-        const long long per = (long long)Z.n * Y.n * X.cnt, pere = (long long)Y.cnt * Z.cnt * X.cnt;
+        const long long KXP = kx_pitch(pl);
+        const long long per = (long long)Z.n * Y.n * KXP, pere = (long long)Y.cnt * Z.cnt * KXP;
         for (int f = 0; f < no; ++f) { C[f] = r2 + f * per; E[f] = r1 + f * pere; }
         Ebase = r1;
-        TileSide s = side(1, X.cnt, (long long)Y.n * X.cnt, nullptr, nullptr);
+        TileSide s = side(1, KXP, (long long)Y.n * KXP, nullptr, nullptr);
         DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
     } else {
         const long long per = (long long)X.cnt * Y.n, pere = (long long)X.cnt * Y.cnt;
@@ -585,6 +632,12 @@ extern "C" int ddl_sync(void* stream) {
     (void)stream;
 #endif
     return 0;
+}
+
+extern "C" int ddl_set_option(const char* name, int value) {
+    if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
+    set_error("unknown option %s", name ? name : "(null)");
+    return -1;
 }
 
 extern "C" long long ddl_launch_count(void) { return g_launches; }

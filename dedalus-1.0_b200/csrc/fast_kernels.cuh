@@ -1,0 +1,177 @@
+// Specialised sm_100a kernels for the hot 3-D passes (device build only).  Same mathematics as
+// the generic tile kernel (tile_kernel.cuh), which stays as the reference implementation for
+// the host emulation and for the shapes these kernels do not cover; the GPU tests compare both
+// against the oracle.
+//
+//  strided_fast : complex pass along a strided axis (y / z passes).  One thread = one first-
+//                 stage butterfly of one pencil.  First-stage inputs go global -> registers,
+//                 last-stage outputs registers -> global (pruned rows predicated, no index
+//                 tables), so shared memory only carries the inter-stage exchanges.  All index
+//                 arithmetic is compile-time; CX*16 B contiguous per row keeps every warp access
+//                 on whole 128-B lines (workspace pitch is a multiple of 8 complex).
+#pragma once
+#include "ddl_common.cuh"
+#include "tile_kernel.cuh"
+
+#if DDL_DEVICE_BUILD
+namespace ddl {
+
+struct FastSide {
+    long long s_n, s_outer;   // element strides of the transform axis and of the outer index
+    const int* outer_tab;     // outer index -> stored outer index (NULL = identity)
+    int m;                    // retained rows |index| <= m, or -1 = every row present
+    int compact;              // retained rows stored contiguously (workspace) instead of in place (state)
+};
+
+struct FastParams {
+    const cplx* in[DDL_MAXF];
+    cplx* out[DDL_MAXF];
+    FastSide si, so;
+    int inner_len;
+    double scale;
+    const cplx* tw;
+};
+
+// stored row of logical row r, or -1 if the row is pruned
+template <int N>
+__device__ __forceinline__ int fast_row(int r, int m, int compact) {
+    if (m < 0) return r;
+    if (r <= m) return r;
+    if (r >= N - m) return compact ? r - (N - 2 * m - 1) : r;
+    return -1;
+}
+
+template <int R, int DIR>
+__device__ __forceinline__ void twiddles_ld(cplx (&v)[R], int step, const cplx* __restrict__ tw) {
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        cplx w = __ldg(&tw[r * step]);
+        if (DIR > 0) w.y = -w.y;
+        v[r] = cmul(v[r], w);
+    }
+}
+
+// middle stage s (neither first nor last): smem -> smem
+template <int N, int S_IDX, int DIR, int CX, int T>
+__device__ __forceinline__ void fast_mid_stage(cplx* tile, int c, int a, const cplx* __restrict__ tw) {
+    constexpr int R = Fac<N>::radix(S_IDX);
+    constexpr int P = Fac<N>::P(S_IDX);
+    constexpr int M = N / P;
+    constexpr int Q = M / R;
+    constexpr int ITEMS = N / R;
+#pragma unroll
+    for (int w = 0; w < ITEMS; w += T) {
+        const int wi = w + a;
+        if (ITEMS % T != 0 && wi >= ITEMS) break;
+        const int q = wi / Q, b = wi % Q;
+        cplx* base = tile + (q * M + b) * CX + c;
+        cplx v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = base[j * Q * CX];
+        dftR<R, DIR>(v);
+        twiddles_ld<R, DIR>(v, b * P, tw);
+#pragma unroll
+        for (int j = 0; j < R; ++j) base[j * Q * CX] = v[j];
+    }
+}
+
+template <int N, int DIR, int CX, int S_IDX>
+struct FastMid {
+    static constexpr int T = N / Fac<N>::radix(0);
+    __device__ __forceinline__ static void run(cplx* tile, int c, int a, const cplx* __restrict__ tw) {
+        if constexpr (S_IDX < Fac<N>::S - 1) {
+            fast_mid_stage<N, S_IDX, DIR, CX, T>(tile, c, a, tw);
+            __syncthreads();
+            FastMid<N, DIR, CX, S_IDX + 1>::run(tile, c, a, tw);
+        }
+    }
+};
+
+template <int N, int DIR, int CX>
+__global__ void __launch_bounds__(CX * (N / Fac<N>::radix(0)), (CX * (N / Fac<N>::radix(0)) <= 512) ? 2 : 1)
+strided_fast(const __grid_constant__ FastParams p) {
+    static_assert(Fac<N>::S >= 2, "strided_fast needs at least two stages");
+    constexpr int R0 = Fac<N>::radix(0);
+    constexpr int T = N / R0;              // threads per pencil
+    constexpr int Q0 = N / R0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
+    const cplx* __restrict__ tw = p.tw;
+
+    const int c = threadIdx.x % CX, a = threadIdx.x / CX;
+    const int inner = blockIdx.x * CX + c;
+    const bool live = inner < p.inner_len;
+    const int by = blockIdx.y;
+    const cplx* __restrict__ in = p.in[blockIdx.z];
+    cplx* __restrict__ out = p.out[blockIdx.z];
+    const long long ib = (long long)(p.si.outer_tab ? p.si.outer_tab[by] : by) * p.si.s_outer + inner;
+    const long long ob = (long long)(p.so.outer_tab ? p.so.outer_tab[by] : by) * p.so.s_outer + inner;
+
+    // ---- stage 0: global -> registers -> smem
+    {
+        cplx v[R0];
+#pragma unroll
+        for (int j = 0; j < R0; ++j) {
+            const int row = fast_row<N>(a + j * Q0, p.si.m, p.si.compact);
+            v[j] = (live && row >= 0) ? in[ib + (long long)row * p.si.s_n] : mk(0.0, 0.0);
+        }
+        dftR<R0, DIR>(v);
+        twiddles_ld<R0, DIR>(v, a, tw);
+#pragma unroll
+        for (int r = 0; r < R0; ++r) tile[(r * Q0 + a) * CX + c] = v[r];
+    }
+    __syncthreads();
+    // ---- middle stages: smem -> smem
+    FastMid<N, DIR, CX, 1>::run(tile, c, a, tw);
+    // ---- last stage: smem -> registers -> global
+    {
+        constexpr int SL = Fac<N>::S - 1;
+        constexpr int R = Fac<N>::radix(SL);
+        constexpr int ITEMS = N / R;
+        const double sc = p.scale;
+#pragma unroll
+        for (int w = 0; w < ITEMS; w += T) {
+            const int q = w + a;
+            if (ITEMS % T != 0 && q >= ITEMS) break;
+            cplx v[R];
+            const cplx* base = tile + (q * R) * CX + c;
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[j] = base[j * CX];
+            dftR<R, DIR>(v);
+            const int k0 = index_of_pos<N>(q * R);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int row = fast_row<N>(k0 + r * (N / R), p.so.m, p.so.compact);
+                if (live && row >= 0) out[ob + (long long)row * p.so.s_n] = scal(v[r], sc);
+            }
+        }
+    }
+}
+
+// pencils per tile for the strided pass of length N
+template <int N> struct FastCX {
+    static constexpr int T = N / Fac<N>::radix(0);
+    static constexpr int value = (T >= 128) ? 4 : (T >= 64 ? 8 : (T >= 32 ? 16 : 32));
+};
+
+template <int N, int DIR>
+int launch_strided_fast(const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t stream) {
+    constexpr int CX = FastCX<N>::value;
+    constexpr int T = N / Fac<N>::radix(0);
+    auto kern = strided_fast<N, DIR, CX>;
+    const size_t smem = (size_t)N * CX * sizeof(cplx);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((p.inner_len + CX - 1) / CX, n_outer, nf);
+    prof_begin(name, stream);
+    kern<<<grid, CX * T, smem, stream>>>(p);
+    prof_end(stream);
+    DDL_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ddl
+#endif  // DDL_DEVICE_BUILD

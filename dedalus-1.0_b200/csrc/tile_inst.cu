@@ -1,6 +1,7 @@
 // Instantiates the generic tile kernel for ONE transform length (compile with -DDDL_N=<N>);
 // one translation unit per length so the build parallelises.
 #include "tile_kernel.cuh"
+#include "fast_kernels.cuh"
 
 #ifndef DDL_N
 #error "compile with -DDDL_N=<transform length>"
@@ -31,5 +32,17 @@ int DDL_CAT(run_tile_, DDL_N)(int mode, int dir, int phys, const TileParams& p, 
     set_error("run_tile: bad mode/physics %d/%d", mode, phys);
     return -1;
 }
+
+#if DDL_DEVICE_BUILD
+// specialised strided pass; returns 1 if this length has no fast kernel (caller falls back)
+int DDL_CAT(run_fast_strided_, DDL_N)(int dir, const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
+    constexpr int N = DDL_N;
+    if constexpr (Fac<N>::S >= 2) {
+        return dir < 0 ? launch_strided_fast<N, -1>(p, nf, n_outer, name, s) : launch_strided_fast<N, +1>(p, nf, n_outer, name, s);
+    } else {
+        return 1;
+    }
+}
+#endif
 
 }  // namespace ddl

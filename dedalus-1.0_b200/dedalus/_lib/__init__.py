@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libddl_b200.so")
 EXPORTS = [
     "ddl_plan_create", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
     "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_deriv", "ddl_rhs", "ddl_stage",
-    "ddl_rk4_stage", "ddl_cn_step", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_rk4_stage", "ddl_cn_step", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
@@ -55,6 +55,7 @@ def _load():
     lib.ddl_launch_count.restype = C.c_longlong
     lib.ddl_profile_enable.argtypes = [i32]
     lib.ddl_profile_report.argtypes = [C.c_char_p, sz]
+    lib.ddl_set_option.argtypes = [C.c_char_p, i32]
     lib.ddl_sync.argtypes = [vp]
     lib.ddl_last_error.restype = C.c_char_p
     lib.ddl_version.restype = C.c_char_p
@@ -88,3 +89,7 @@ def profile_report():
     buf = C.create_string_buffer(1 << 16)
     check(lib.ddl_profile_report(buf, len(buf)))
     return json.loads(buf.value.decode())
+
+
+def set_option(name, value):
+    check(lib.ddl_set_option(name.encode(), int(value)))

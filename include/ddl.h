@@ -107,6 +107,9 @@ long long ddl_launch_count(void);
 int ddl_profile_enable(int on);
 int ddl_profile_report(char* json_out, size_t nbytes);
 
+/* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both) */
+int ddl_set_option(const char* name, int value);
+
 int ddl_sync(void* stream);
 const char* ddl_last_error(void);
 const char* ddl_version(void);

@@ -170,3 +170,26 @@ def test_rk4_properties_256cubed_roundtrip():
     assert va.mag_div_sum(data) / 128 ** 3 < 1e-12
     e1 = va.ekin(data) + va.emag(data)
     assert abs(e1 - e0) / e0 < 1e-2 and e1 < e0
+
+
+def test_generic_and_fast_kernels_agree():
+    """The specialised sm_100a kernels and the generic tile kernel implement the same maths."""
+    import dedalus._lib as L
+    import dedalus_oracle as orc
+    Po = oracle_physics("IncompressibleMHD", (32, 64, 32), None, dict(nu=1e-3, eta=1e-3))
+    y0 = orc.synthetic_ic(Po, 5).kvector()
+    out = []
+    for fast in (1, 0):
+        L.set_option("fast_kernels", fast)
+        P = dev_physics("IncompressibleMHD", (32, 64, 32), None, dict(nu=1e-3, eta=1e-3))
+        data, deriv = P.create_fields(0.), P.create_fields(0.)
+        set_state(data, y0)
+        P.RHS(data, deriv)
+        out.append(get_state(deriv))
+    L.set_option("fast_kernels", 1)
+    assert rel(out[0], out[1]) < 1e-14
+    do, ko = Po.create_fields(0.), Po.create_fields(0.)
+    for j, (_, _, c) in enumerate(do.components()):
+        c["kspace"] = y0[j]
+    Po.RHS(do, ko)
+    assert rel(out[0], ko.kvector()) < 1e-13
