@@ -9,6 +9,7 @@
 #include "pointwise.cuh"
 #include "tile_kernel.cuh"
 #include "fast_kernels.cuh"
+#include "xfused_kernel.cuh"
 
 namespace ddl {
 
@@ -93,6 +94,18 @@ static int run_tile(int N, int mode, int dir, int phys, const TileParams& p, int
     }
     set_error("unsupported transform length %d (powers of two 8..2048)", N);
     return -1;
+}
+
+#define DDL_DECLX(N) int run_xfused_##N(int, const XFusedParams&, int, ddl_stream_t);
+DDL_DECLX(8) DDL_DECLX(16) DDL_DECLX(32) DDL_DECLX(64) DDL_DECLX(128) DDL_DECLX(256) DDL_DECLX(512) DDL_DECLX(1024)
+DDL_DECLX(2048)
+static int run_xfused(int N, int phys, const XFusedParams& p, int n_outer, ddl_stream_t s) {
+    switch (N) {
+#define DDL_CASEX(N) case N: return run_xfused_##N(phys, p, n_outer, s);
+        DDL_CASEX(8) DDL_CASEX(16) DDL_CASEX(32) DDL_CASEX(64) DDL_CASEX(128) DDL_CASEX(256) DDL_CASEX(512)
+        DDL_CASEX(1024) DDL_CASEX(2048)
+    }
+    return 1;
 }
 
 #if DDL_DEVICE_BUILD
@@ -279,7 +292,8 @@ static int pick_c2c_group(int N, long long inner_len) {
     if (g > inner_len) g = (int)inner_len;
     return g;
 }
-static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 1024 ? 1024 : t); }
+// CTA size of the generic tile kernel (72 registers per thread: at most 896 threads fit an SM)
+static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 768 ? 768 : t); }
 
 // complex pass of nf fields along an axis of length N
 struct RowSpec { int m; int compact; };   // retained rows of a pruned axis (m < 0: all rows present)
@@ -540,8 +554,21 @@ extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, vo
         const long long per = (long long)Z.n * Y.n * KXP, pere = (long long)Y.cnt * Z.cnt * KXP;
         for (int f = 0; f < no; ++f) { C[f] = r2 + f * per; E[f] = r1 + f * pere; }
         Ebase = r1;
-        TileSide s = side(1, KXP, (long long)Y.n * KXP, nullptr, nullptr);
-        DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
+        int rcx = 1;
+        if (g_use_fast && Y.n % 2 == 0 && ni <= DDL_XF_MAXI && no <= DDL_XF_MAXO) {
+            XFusedParams xp;
+            memset(&xp, 0, sizeof(xp));
+            for (int f = 0; f < ni; ++f) xp.in[f] = (const cplx*)head[f];
+            for (int f = 0; f < no; ++f) xp.out[f] = (cplx*)C[f];
+            xp.pitch = KXP; xp.s_outer = (long long)Y.n * KXP; xp.n_lines = Y.n; xp.kn = X.cnt;
+            xp.scale = sc; xp.tw = X.tw; xp.pc = pc;
+            rcx = run_xfused(X.n, code, xp, Z.n, st);
+            if (rcx < 0) return rcx;
+        }
+        if (rcx > 0) {
+            TileSide s = side(1, KXP, (long long)Y.n * KXP, nullptr, nullptr);
+            DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
+        }
     } else {
         const long long per = (long long)X.cnt * Y.n, pere = (long long)X.cnt * Y.cnt;
         for (int f = 0; f < no; ++f) { C[f] = r1 + f * per; E[f] = r2 + f * pere; }

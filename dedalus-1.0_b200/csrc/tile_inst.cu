@@ -2,6 +2,7 @@
 // one translation unit per length so the build parallelises.
 #include "tile_kernel.cuh"
 #include "fast_kernels.cuh"
+#include "xfused_kernel.cuh"
 
 #ifndef DDL_N
 #error "compile with -DDDL_N=<transform length>"
@@ -31,6 +32,19 @@ int DDL_CAT(run_tile_, DDL_N)(int mode, int dir, int phys, const TileParams& p, 
     }
     set_error("run_tile: bad mode/physics %d/%d", mode, phys);
     return -1;
+}
+
+// specialised fused x-pass of the 3-D RHS; returns 1 if this length / physics has none
+int DDL_CAT(run_xfused_, DDL_N)(int phys, const XFusedParams& p, int n_outer, ddl_stream_t s) {
+    constexpr int N = DDL_N;
+    if constexpr (XFac<N>::ok) {
+        switch (phys) {
+            case 3: return launch_xfused<N, Hydro3C>(p, n_outer, s);
+            case 4: return launch_xfused<N, Bouss3C>(p, n_outer, s);
+            case 5: return launch_xfused<N, MHD3C>(p, n_outer, s);
+        }
+    }
+    return 1;
 }
 
 #if DDL_DEVICE_BUILD

@@ -1,0 +1,440 @@
+// Specialised fused x-pass of the 3-D RHS (the dominant kernel of the step):
+//
+//   half-spectra of a PAIR of adjacent x-lines  --pack-->  inverse FFT (DIF, natural -> scrambled)
+//     -->  real-space products at every grid point  -->  forward FFT (DIT, scrambled -> natural)
+//     --unpack-->  retained half-spectra of the product fields
+//
+// for all NI input and NO output fields of one line pair per CTA; the real-space fields never
+// leave the SM.  Same mathematics as tile_kernel.cuh TM_FUSED (which stays as the generic
+// implementation and as the comparison in the tests); what differs is the mapping:
+//   * factorisation N = R0 x R1 (x R2) x 2 with radix-16/8/4 register butterflies, so a
+//     512-point pencil crosses shared memory twice per transform instead of three times;
+//   * the last inverse stage (radix 2), the products and the first forward stage (radix 2) are
+//     one phase over 8-byte halves (one real line each), so the product fields are born in
+//     registers and stored once;
+//   * the first inverse stage reads the Hermitian-packed pencil straight from global memory
+//     (both lines, mirrored half included) - no staging pass;
+//   * the last forward stage leaves Z[k] and its mirror Z[N-k] in registers of lanes a and
+//     Q0-a of the same warp: the Hermitian unpack is a warp shuffle, the spectra go registers
+//     -> global (no shared-memory pass);
+//   * a pencil belongs to ONE group of N/R0 threads (a warp for N = 512) for all of its outer
+//     stages, so those stages synchronise with __syncwarp / a named barrier; only the product
+//     phase is bracketed by CTA-wide barriers;
+//   * XOR-swizzled pencils: every 16-byte and 8-byte access pattern of every phase is
+//     bank-conflict free for N <= 512 (profiles/ carries the model and the measured counters);
+//   * twiddles of a butterfly are powers of ONE table entry, generated in registers
+//     (the FP64 pipe has the headroom, the load/store pipe does not).
+// Replaces, per RHS, the x-direction halves of the reference's 15+21 transforms and every
+// real-space numpy pass between them (physics.py:197-228, 309-354; representations.py:318-357).
+#pragma once
+#include "ddl_common.cuh"
+#include "physics_ops.cuh"
+
+namespace ddl {
+
+#define DDL_XF_MAXI 8
+#define DDL_XF_MAXO 12
+
+struct XFusedParams {
+    const cplx* in[DDL_XF_MAXI];    // [outer][line][pitch] half-spectra, kn retained modes per line
+    cplx* out[DDL_XF_MAXO];
+    long long pitch;                // elements between consecutive lines (same for in and out)
+    long long s_outer;              // elements between consecutive outer planes
+    int n_lines;                    // lines per outer plane (even)
+    int kn;                         // retained non-negative modes along x (kn - 1 < N/2)
+    double scale;                   // forward normalisation 1/N_total
+    const cplx* tw;                 // exp(-2 pi i m / N)
+    PhysConst pc;
+};
+
+// Outer (shared-memory) stages of the length-N transform; the innermost radix-2 stage is fused
+// with the products.
+template <int N> struct XFac {
+    static constexpr bool ok = false;
+    static constexpr int S = 0;
+    static constexpr int radix(int) { return 1; }
+};
+template <> struct XFac<128> { static constexpr bool ok = true; static constexpr int S = 2; static constexpr int radix(int s) { return 8; } };
+template <> struct XFac<256> { static constexpr bool ok = true; static constexpr int S = 2; static constexpr int radix(int s) { return s == 0 ? 16 : 8; } };
+template <> struct XFac<512> { static constexpr bool ok = true; static constexpr int S = 2; static constexpr int radix(int s) { return 16; } };
+template <> struct XFac<1024> { static constexpr bool ok = true; static constexpr int S = 3; static constexpr int radix(int s) { return s == 0 ? 16 : (s == 1 ? 8 : 4); } };
+template <int N> constexpr int xfac_P(int s) { return s == 0 ? 1 : xfac_P<N>(s - 1) * XFac<N>::radix(s - 1); }
+
+// 16-byte element e of a pencil lives at swizzled slot xsw(e): a permutation inside aligned
+// groups of 8 elements (one 128-byte bank row)
+template <int N> DDL_HD int xsw(int e) {
+    constexpr int Q0 = N / XFac<N>::radix(0);
+    return e ^ ((e / Q0) & 7) ^ ((e >> 3) & 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// radix-16 butterfly as 4 x 4.  Input v[j] natural; output X[r] is left in v[reg16(r)].
+// ---------------------------------------------------------------------------------------
+DDL_HD constexpr int reg16(int r) { return (r >> 2) + 4 * (r & 3); }
+
+template <int DIR> DDL_HD cplx mul_w16(cplx a, int e) {
+    // a * exp(DIR * 2 pi i e / 16) for the exponents the 4x4 split needs
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    switch (e) {
+        case 1: return DIR < 0 ? mk(a.x * c1 + a.y * s1, a.y * c1 - a.x * s1) : mk(a.x * c1 - a.y * s1, a.y * c1 + a.x * s1);
+        case 2: return DIR < 0 ? mk((a.x + a.y) * h, (a.y - a.x) * h) : mk((a.x - a.y) * h, (a.x + a.y) * h);
+        case 3: return DIR < 0 ? mk(a.x * s1 + a.y * c1, a.y * s1 - a.x * c1) : mk(a.x * s1 - a.y * c1, a.y * s1 + a.x * c1);
+        case 4: return mul_i<DIR>(a);
+        case 6: return DIR < 0 ? mk((a.y - a.x) * h, -(a.x + a.y) * h) : mk(-(a.x + a.y) * h, (a.x - a.y) * h);
+        case 9: return DIR < 0 ? mk(-a.x * c1 - a.y * s1, a.x * s1 - a.y * c1) : mk(a.y * s1 - a.x * c1, -a.x * s1 - a.y * c1);
+        default: return a;
+    }
+}
+
+template <int DIR> DDL_HD void dft16(cplx (&v)[16]) {
+    // inner DFT4 over i2 for each j: elements j, j+4, j+8, j+12 -> output m at v[j + 4m]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dft4<DIR>(v[j], v[j + 4], v[j + 8], v[j + 12]);
+    // twiddle W16^(j m)
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+#pragma unroll
+        for (int m = 1; m < 4; ++m) v[j + 4 * m] = mul_w16<DIR>(v[j + 4 * m], j * m);
+    // outer DFT4 over j for each m: output n at v[n + 4m]  (X[m + 4n])
+#pragma unroll
+    for (int m = 0; m < 4; ++m) dft4<DIR>(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]);
+}
+
+template <int R> DDL_HD constexpr int xreg(int r) { return R == 16 ? reg16(r) : r; }
+
+template <int R, int DIR> DDL_HD void xdft(cplx (&v)[R]) {
+    if constexpr (R == 16) dft16<DIR>(v);
+    else dftR<R, DIR>(v);
+}
+
+DDL_HD cplx csq(cplx a) { return mk(a.x * a.x - a.y * a.y, 2.0 * a.x * a.y); }
+
+// v[idx(r)] *= w^r, r = 1..R-1; the powers come from two chains (odd / even) of products with
+// w^2, so only three twiddles are live at a time
+template <int R, bool OUT_ORDER>
+DDL_HD void xtwiddle(cplx (&v)[R], cplx w1) {
+    auto at = [&](int r) -> cplx& { return v[OUT_ORDER ? xreg<R>(r) : r]; };
+    at(1) = cmul(at(1), w1);
+    if constexpr (R > 2) {
+        const cplx w2 = csq(w1);
+        cplx wo = w1, we = w2;
+        at(2) = cmul(at(2), we);
+#pragma unroll
+        for (int r = 3; r < R; r += 2) {
+            wo = cmul(wo, w2);
+            at(r) = cmul(at(r), wo);
+            if (r + 1 < R) {
+                we = cmul(we, w2);
+                at(r + 1) = cmul(at(r + 1), we);
+            }
+        }
+    }
+}
+
+#if DDL_DEVICE_BUILD
+#define DDL_XF_ITEMS(i, count, NT) for (int i = threadIdx.x; i < (count); i += (NT))
+#define DDL_XF_THREADS(t, NT) for (int t = threadIdx.x, _once = 1; _once; _once = 0)
+#define DDL_LDG(p) __ldg(p)
+#else
+#define DDL_XF_ITEMS(i, count, NT) for (int i = 0; i < (count); ++i)
+#define DDL_XF_THREADS(t, NT) for (int t = 0; t < (NT); ++t)
+#define DDL_LDG(p) (*(p))
+#endif
+
+// barrier among the TP threads that own one pencil (emulation: phases run to completion in order)
+template <int TP>
+DDL_BODY void xgroup_sync(int group) {
+#if DDL_DEVICE_BUILD
+    if constexpr (TP <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(TP) : "memory");
+#else
+    (void)group;
+#endif
+}
+
+// Position of butterfly input/output j of an in-place stage: xsw(base + j*Q) = sb ^ xsw(j*Q)
+// (the swizzle is linear over GF(2) and base, j*Q occupy disjoint bits), sb = xsw(base).
+template <int N, int S_IDX, int DIR, bool DIT, int TP>
+DDL_BODY void xstage(cplx* T, int lane, const cplx* __restrict__ tw) {
+    constexpr int R = XFac<N>::radix(S_IDX);
+    constexpr int P = xfac_P<N>(S_IDX);
+    constexpr int M = N / P, Q = M / R;
+    constexpr int ITEMS = N / R;
+#pragma unroll
+    for (int w0 = 0; w0 < ITEMS; w0 += TP) {
+        const int w = w0 + lane;
+        const int b = w / P, q = w % P;          // q fastest across lanes: conflict-free with the swizzle
+        const int sb = xsw<N>(q * M + b);
+        cplx v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = T[sb ^ xsw<N>(j * Q)];
+        if constexpr (DIT) {
+            if (b != 0) {
+                cplx w1 = DDL_LDG(&tw[b * P]);
+                if (DIR > 0) w1 = conj(w1);
+                xtwiddle<R, false>(v, w1);
+            }
+            xdft<R, DIR>(v);
+        } else {
+            xdft<R, DIR>(v);
+            if (b != 0) {
+                cplx w1 = DDL_LDG(&tw[b * P]);
+                if (DIR > 0) w1 = conj(w1);
+                xtwiddle<R, true>(v, w1);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) T[sb ^ xsw<N>(r * Q)] = v[xreg<R>(r)];
+    }
+}
+
+// One CTA: G line pairs (lines 2*(bx*G+g), +1 of outer plane by), NT threads.
+template <int N, class PHYS, int NT, int G>
+DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
+    constexpr int NI = PHYS::NI, NO = PHYS::NO;
+    constexpr int NS = NI > NO ? NI : NO;     // pencil slots per line pair
+    constexpr int R0 = XFac<N>::radix(0);
+    constexpr int Q0 = N / R0;
+    constexpr int TP = Q0;                    // threads that own a pencil: one stage-0 butterfly each
+    constexpr int GPR = NT / TP;              // pencils in flight per round
+    static_assert(NT % TP == 0, "CTA size must be a multiple of the pencil group");
+    constexpr int S = XFac<N>::S;
+    const cplx* __restrict__ tw = p.tw;
+    const int kn = p.kn;
+    const long long plane = (long long)by * p.s_outer;
+    const int pair0 = bx * G;
+
+    // ================= inverse: per pencil, stage 0 (global -> registers -> shared) then the
+    //                   remaining outer stages, synchronised inside the pencil's own group
+#pragma unroll 1
+    for (int pen0 = 0; pen0 < G * NI; pen0 += GPR) {
+        DDL_XF_THREADS(t, NT) {
+            const int pen = pen0 + t / TP, a = t % TP;
+            if (pen < G * NI) {
+                const int g = pen / NI, f = pen % NI;
+                const int l0 = 2 * (pair0 + g);
+                cplx v[R0];
+                if (l0 < p.n_lines) {
+                    // Hermitian-packed pencil Z = A + iB of the two lines:
+                    //   Z[e] = A[e] + i B[e] (e < kn),  Z[N-e] = conj(A[e]) + i conj(B[e]),  else 0
+                    const cplx* __restrict__ A = p.in[f] + plane + (long long)l0 * p.pitch;
+                    const cplx* __restrict__ B = A + p.pitch;
+#pragma unroll
+                    for (int j = 0; j < R0; ++j) {
+                        const int e = a + j * Q0;
+                        cplx z = mk(0.0, 0.0);
+                        if (e < kn) {
+                            const cplx za = DDL_LDG(&A[e]), zb = DDL_LDG(&B[e]);
+                            z = (e == 0) ? mk(za.x, zb.x) : mk(za.x - zb.y, za.y + zb.x);
+                        } else if (N - e < kn) {
+                            const cplx za = DDL_LDG(&A[N - e]), zb = DDL_LDG(&B[N - e]);
+                            z = mk(za.x + zb.y, zb.x - za.y);
+                        }
+                        v[j] = z;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < R0; ++j) v[j] = mk(0.0, 0.0);
+                }
+                xdft<R0, +1>(v);
+                if (a != 0) xtwiddle<R0, true>(v, conj(DDL_LDG(&tw[a])));
+                cplx* T = tile + (g * NS + f) * N;
+                const int sb = xsw<N>(a);
+#pragma unroll
+                for (int r = 0; r < R0; ++r) T[sb ^ xsw<N>(r * Q0)] = v[xreg<R0>(r)];
+            }
+        }
+        DDL_XF_THREADS(t, NT) xgroup_sync<TP>(t / TP);
+        if constexpr (S >= 2) {
+            DDL_XF_THREADS(t, NT) {
+                const int pen = pen0 + t / TP;
+                if (pen < G * NI) xstage<N, 1, +1, false, TP>(tile + ((pen / NI) * NS + pen % NI) * N, t % TP, tw);
+            }
+        }
+        if constexpr (S >= 3) {
+            DDL_XF_THREADS(t, NT) xgroup_sync<TP>(t / TP);
+            DDL_XF_THREADS(t, NT) {
+                const int pen = pen0 + t / TP;
+                if (pen < G * NI) xstage<N, 2, +1, false, TP>(tile + ((pen / NI) * NS + pen % NI) * N, t % TP, tw);
+            }
+        }
+        static_assert(S <= 3, "at most three outer stages");
+    }
+    DDL_SYNC();
+
+    // ================= innermost radix-2 (inverse) -> products -> innermost radix-2 (forward);
+    //                   one item = one real line (8-byte half) of one position pair
+    {
+        double* td = reinterpret_cast<double*>(tile);
+        DDL_XF_ITEMS(i, G * N, NT) {
+            const int c = i & 1, wp = (i >> 1) % (N / 2), g = (i >> 1) / (N / 2);
+            const int s0 = 2 * xsw<N>(2 * wp) + c, s1 = s0 ^ 2;     // xsw(2wp+1) = xsw(2wp) ^ 1
+            double* T = td + (size_t)g * NS * N * 2;
+            double u0[NI], u1[NI], o0[NO], o1[NO];
+#pragma unroll
+            for (int f = 0; f < NI; ++f) {
+                const double x0 = T[f * 2 * N + s0], x1 = T[f * 2 * N + s1];
+                u0[f] = x0 + x1; u1[f] = x0 - x1;
+            }
+            PHYS::apply(u0, o0, p.pc);
+            PHYS::apply(u1, o1, p.pc);
+#pragma unroll
+            for (int f = 0; f < NO; ++f) {
+                T[f * 2 * N + s0] = o0[f] + o1[f];
+                T[f * 2 * N + s1] = o0[f] - o1[f];
+            }
+        }
+    }
+    DDL_SYNC();
+
+    // ================= forward: per pencil, outer stages S-1..1 (shared), then stage 0
+    //                   (shared -> registers), Hermitian unpack and store of the retained modes
+    const double h = 0.5 * p.scale;
+#pragma unroll 1
+    for (int pen0 = 0; pen0 < G * NO; pen0 += GPR) {
+        if constexpr (S >= 3) {
+            DDL_XF_THREADS(t, NT) {
+                const int pen = pen0 + t / TP;
+                if (pen < G * NO) xstage<N, 2, -1, true, TP>(tile + ((pen / NO) * NS + pen % NO) * N, t % TP, tw);
+            }
+            DDL_XF_THREADS(t, NT) xgroup_sync<TP>(t / TP);
+        }
+        if constexpr (S >= 2) {
+            DDL_XF_THREADS(t, NT) {
+                const int pen = pen0 + t / TP;
+                if (pen < G * NO) xstage<N, 1, -1, true, TP>(tile + ((pen / NO) * NS + pen % NO) * N, t % TP, tw);
+            }
+            DDL_XF_THREADS(t, NT) xgroup_sync<TP>(t / TP);
+        }
+#if DDL_DEVICE_BUILD
+        constexpr bool SHUFFLE_UNPACK = (TP <= 32);
+#else
+        constexpr bool SHUFFLE_UNPACK = false;
+#endif
+        DDL_XF_THREADS(t, NT) {
+            const int pen = pen0 + t / TP, a = t % TP;
+            const bool act = pen < G * NO;
+            const int g = act ? pen / NO : 0, f = act ? pen % NO : 0;
+            cplx* T = tile + (g * NS + f) * N;
+            const int sb = xsw<N>(a);
+            cplx v[R0];
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < R0; ++j) v[j] = T[sb ^ xsw<N>(j * Q0)];
+                if (a != 0) xtwiddle<R0, false>(v, DDL_LDG(&tw[a]));
+                xdft<R0, -1>(v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < R0; ++j) v[j] = mk(0.0, 0.0);
+            }
+            if constexpr (SHUFFLE_UNPACK) {
+#if DDL_DEVICE_BUILD
+                // Z[k], k = a + r Q0, is output r of lane a; its mirror Z[N-k] is output R0-1-r of
+                // lane Q0-a of the same group (lane 0: own output R0-r).  A[k] = (Z[k] + conj Z[N-k])/2,
+                // B[k] = (Z[k] - conj Z[N-k]) / 2i.
+                const int l0 = 2 * (pair0 + g);
+                const bool st = act && l0 < p.n_lines;
+                cplx* __restrict__ dst = p.out[f] + plane + (long long)l0 * p.pitch;
+                const int src = (threadIdx.x & ~(TP - 1) & 31) | ((TP - a) & (TP - 1));
+                const int rmax = (kn - 1) / Q0;          // uniform
+#pragma unroll
+                for (int r = 0; r < R0 / 2; ++r) {
+                    if (r <= rmax) {
+                        const cplx Zk = v[xreg<R0>(r)];
+                        const cplx mine = v[xreg<R0>(R0 - 1 - r)];
+                        cplx Zm;
+                        Zm.x = __shfl_sync(0xffffffffu, mine.x, src);
+                        Zm.y = __shfl_sync(0xffffffffu, mine.y, src);
+                        if (a == 0) Zm = v[xreg<R0>((R0 - r) % R0)];
+                        const int k = a + r * Q0;
+                        if (st && k < kn) {
+                            dst[k] = mk((Zk.x + Zm.x) * h, (Zk.y - Zm.y) * h);
+                            dst[p.pitch + k] = mk((Zk.y + Zm.y) * h, (Zm.x - Zk.x) * h);
+                        }
+                    }
+                }
+#endif
+            } else {
+                if (act) {
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) T[sb ^ xsw<N>(r * Q0)] = v[xreg<R0>(r)];
+                }
+            }
+        }
+        if constexpr (!SHUFFLE_UNPACK) {
+            DDL_XF_THREADS(t, NT) xgroup_sync<TP>(t / TP);
+            DDL_XF_THREADS(t, NT) {
+                const int pen = pen0 + t / TP, a = t % TP;
+                if (pen < G * NO) {
+                    const int g = pen / NO, f = pen % NO;
+                    const int l0 = 2 * (pair0 + g);
+                    if (l0 < p.n_lines) {
+                        const cplx* T = tile + (g * NS + f) * N;
+                        cplx* __restrict__ dst = p.out[f] + plane + (long long)l0 * p.pitch;
+                        for (int k = a; k < kn; k += TP) {
+                            const cplx Zk = T[xsw<N>(k)], Zm = T[xsw<N>((N - k) % N)];
+                            dst[k] = mk((Zk.x + Zm.x) * h, (Zk.y - Zm.y) * h);
+                            dst[p.pitch + k] = mk((Zk.y + Zm.y) * h, (Zm.x - Zk.x) * h);
+                        }
+                    }
+                }
+            }
+            // the next round reuses no slot of this one: no barrier needed here
+        }
+    }
+}
+
+template <int N, class PHYS> struct XFusedCfg {
+    static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
+    static constexpr int G = (N >= 512) ? 1 : 512 / N;
+    static constexpr int TP = N / XFac<N>::radix(0);
+    // six warps: one round of inverse pencils for MHD (6) and two of forward pencils (9); with
+    // 72 KB of pencils per CTA three CTAs share an SM at <= 112 registers per thread
+    static constexpr int NT = TP > 32 ? 9 * TP : 192;
+    static constexpr size_t SMEM = (size_t)G * NS * N * sizeof(cplx);
+    static constexpr int MINB = (SMEM * 3 <= 222 * 1024 && NT * 3 <= 1024) ? 3 : ((SMEM * 2 <= 222 * 1024 && NT * 2 <= 1024) ? 2 : 1);
+    // register budget that still lets MINB CTAs share an SM: each of the four sub-partitions owns
+    // 16 K registers and holds ceil(warps / 4) of the resident warps (allocation unit: 8 per thread)
+    static constexpr int WPS = (NT / 32 * MINB + 3) / 4;
+    static constexpr int MAXREG = (16384 / (WPS * 32) / 8 * 8) > 255 ? 255 : (16384 / (WPS * 32) / 8 * 8);
+};
+
+#if DDL_DEVICE_BUILD
+template <int N, class PHYS>
+__global__ void __maxnreg__((XFusedCfg<N, PHYS>::MAXREG))
+xfused_kernel(const __grid_constant__ XFusedParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    xfused_block<N, PHYS, XFusedCfg<N, PHYS>::NT, XFusedCfg<N, PHYS>::G>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
+}
+#endif
+
+// returns 0 on success, negative on error
+template <int N, class PHYS>
+int launch_xfused(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
+    using Cfg = XFusedCfg<N, PHYS>;
+    const int pairs = (p.n_lines + 1) / 2;
+    const int gx = (pairs + Cfg::G - 1) / Cfg::G;
+#if DDL_DEVICE_BUILD
+    auto kern = xfused_kernel<N, PHYS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_done = true;
+    }
+    dim3 grid(gx, n_outer, 1);
+    prof_begin("x_fused", stream);
+    kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(p);
+    prof_end(stream);
+    DDL_CUDA_CHECK(cudaGetLastError());
+#else
+    (void)stream;
+    cplx* tile = (cplx*)malloc(Cfg::SMEM);
+    for (int by = 0; by < n_outer; ++by)
+        for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G>(p, tile, bx, by);
+    free(tile);
+#endif
+    return 0;
+}
+
+}  // namespace ddl

@@ -172,16 +172,22 @@ def test_rk4_properties_256cubed_roundtrip():
     assert abs(e1 - e0) / e0 < 1e-2 and e1 < e0
 
 
-def test_generic_and_fast_kernels_agree():
-    """The specialised sm_100a kernels and the generic tile kernel implement the same maths."""
+@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (32, 64, 32)),
+                                           ("IncompressibleMHD", (16, 32, 128)), ("BoussinesqHydro", (32, 16, 256)),
+                                           ("IncompressibleHydro", (16, 16, 512)), ("IncompressibleMHD", (16, 16, 512)),
+                                           ("IncompressibleMHD", (8, 16, 1024))])
+def test_generic_and_fast_kernels_agree(physics, shape):
+    """The specialised sm_100a kernels (strided_fast, xfused_kernel for nx in 128..1024) and the
+    generic tile kernel implement the same maths, and both match the oracle."""
     import dedalus._lib as L
     import dedalus_oracle as orc
-    Po = oracle_physics("IncompressibleMHD", (32, 64, 32), None, dict(nu=1e-3, eta=1e-3))
+    params = dict(nu=1e-3, eta=1e-3) if physics == "IncompressibleMHD" else dict(nu=1e-3)
+    Po = oracle_physics(physics, shape, None, params)
     y0 = orc.synthetic_ic(Po, 5).kvector()
     out = []
     for fast in (1, 0):
         L.set_option("fast_kernels", fast)
-        P = dev_physics("IncompressibleMHD", (32, 64, 32), None, dict(nu=1e-3, eta=1e-3))
+        P = dev_physics(physics, shape, None, params)
         data, deriv = P.create_fields(0.), P.create_fields(0.)
         set_state(data, y0)
         P.RHS(data, deriv)
