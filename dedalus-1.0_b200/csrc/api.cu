@@ -96,12 +96,13 @@ static int run_tile(int N, int mode, int dir, int phys, const TileParams& p, int
     return -1;
 }
 
-#define DDL_DECLX(N) int run_xfused_##N(int, const XFusedParams&, int, ddl_stream_t);
+#define DDL_DECLX(N) int run_xfused_##N(int, const XFusedParams&, int, int, ddl_stream_t);
 DDL_DECLX(8) DDL_DECLX(16) DDL_DECLX(32) DDL_DECLX(64) DDL_DECLX(128) DDL_DECLX(256) DDL_DECLX(512) DDL_DECLX(1024)
 DDL_DECLX(2048)
+static int g_xfused_variant = 0;
 static int run_xfused(int N, int phys, const XFusedParams& p, int n_outer, ddl_stream_t s) {
     switch (N) {
-#define DDL_CASEX(N) case N: return run_xfused_##N(phys, p, n_outer, s);
+#define DDL_CASEX(N) case N: return run_xfused_##N(phys, p, n_outer, g_xfused_variant, s);
         DDL_CASEX(8) DDL_CASEX(16) DDL_CASEX(32) DDL_CASEX(64) DDL_CASEX(128) DDL_CASEX(256) DDL_CASEX(512)
         DDL_CASEX(1024) DDL_CASEX(2048)
     }
@@ -150,13 +151,31 @@ struct Axis {
     int* f2c = nullptr;             // [nk] stored -> compact or -1
     int* f2f = nullptr;             // [nk] stored -> stored or -1
     cplx* tw = nullptr;             // [n] exp(-2 pi i m / n)
+    std::vector<int> h_c2f;         // host copy of c2f
+};
+
+// The rows of the ky axis this rank owns (k-space slab, representations.py:231-233); with one
+// rank it is the whole axis.
+struct YSlab {
+    int nyl = 1, ky0 = 0;           // stored rows [ky0, ky0 + nyl)
+    int cyl = 1, cy0 = 0;           // retained rows: compact indices [cy0, cy0 + cyl)
+    const double* kv = nullptr;     // [nyl]
+    const unsigned char* keep = nullptr;
+    const double* kvc = nullptr;    // [cyl]
+    int* c2f = nullptr;             // [cyl] local compact -> local stored row
 };
 
 struct ddl_plan {
     int ndim = 0;
     Axis ax, ay, az;
+    // slab decomposition (3-D): x-space split along z, k-space along ky (FFTW-MPI transposed
+    // layout, dedalus/utils/fftw/_fftw.pyx:114-148, representations.py:180-186)
+    int nranks = 1, rank = 0;
+    int nzl = 1, z0 = 0;
+    YSlab yl;
+    std::vector<int> cyl_of;        // retained ky rows per rank
     long long ntot = 1;
-    KGeom geom;          // full k-array geometry
+    KGeom geom;          // local k-array geometry
     long long nmodes = 0;
     std::vector<void*> owned;
 };
@@ -183,6 +202,7 @@ static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv,
         int f = (j <= m) ? j : j + (a.nk - a.cnt);
         c2f[j] = f; f2c[f] = j; f2f[f] = f; kvc[j] = kv[f];
     }
+    a.h_c2f = c2f;
     std::vector<cplx> tw(n);
     const long double PI = acosl(-1.0L);
     for (int q = 0; q < n; ++q) { tw[q].x = (double)cosl(-2 * PI * q / n); tw[q].y = (double)sinl(-2 * PI * q / n); }
@@ -193,9 +213,12 @@ static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv,
     return 0;
 }
 
-extern "C" int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x, const double* kx, const double* ky,
-                               const double* kz, const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz) {
+extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* shape_x, const double* kx, const double* ky,
+                                    const double* kz, const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz,
+                                    int nranks, int rank) {
     if (!out || (ndim != 2 && ndim != 3)) { set_error("Must use either 2 or 3 dimensions."); return -1; }
+    if (nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad rank %d of %d", rank, nranks); return -1; }
+    if (nranks > 1 && ndim != 3) { set_error("slab decomposition is 3-D only (2-D grids run as replicas)"); return -1; }
     ddl_plan* pl = new ddl_plan();
     pl->ndim = ndim;
     int rc = 0;
@@ -208,12 +231,39 @@ extern "C" int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x,
         if (!rc) rc = build_axis(pl, pl->ax, (int)shape_x[1], true, kx, keepx);
     }
     if (rc) { ddl_plan_destroy(pl); return rc; }
+    const Axis& Y = pl->ay;
+    if (nranks > 1 && ((nranks & (nranks - 1)) || pl->az.n % nranks || Y.n % nranks)) {
+        set_error("slab decomposition needs a power-of-two rank count dividing nz=%d and ny=%d (got %d)", pl->az.n, Y.n, nranks);
+        ddl_plan_destroy(pl);
+        return -1;
+    }
+    pl->nranks = nranks; pl->rank = rank;
+    pl->nzl = (ndim == 3 ? pl->az.n : 1) / nranks; pl->z0 = rank * pl->nzl;
+    YSlab& L = pl->yl;
+    L.nyl = Y.nk / nranks; L.ky0 = rank * L.nyl;
+    pl->cyl_of.assign(nranks, 0);
+    std::vector<int> lc2f;
+    L.cy0 = -1;
+    for (int j = 0; j < Y.cnt; ++j) {
+        const int f = Y.h_c2f[j], r = f / L.nyl;
+        pl->cyl_of[r]++;
+        if (r == rank) { if (L.cy0 < 0) L.cy0 = j; lc2f.push_back(f - L.ky0); }
+    }
+    L.cyl = (int)lc2f.size();
+    if (L.cy0 < 0) L.cy0 = 0;
+    L.kv = Y.kv + L.ky0; L.keep = Y.keep + L.ky0; L.kvc = Y.kvc + L.cy0;
+    if (nranks == 1) L.c2f = Y.c2f;
+    else {
+        L.c2f = upload_vec(lc2f);
+        if (!L.c2f) { set_error("device allocation failed"); ddl_plan_destroy(pl); return -2; }
+        pl->owned.push_back(L.c2f);
+    }
     KGeom& g = pl->geom;
     if (ndim == 3) {
         pl->ntot = (long long)pl->ax.n * pl->ay.n * pl->az.n;
-        const Axis* lv[3] = {&pl->ay, &pl->az, &pl->ax};
-        const int axid[3] = {1, 2, 0};
-        for (int l = 0; l < 3; ++l) { g.dim[l] = lv[l]->nk; g.kv[l] = lv[l]->kv; g.keep[l] = lv[l]->keep; g.ax[l] = axid[l]; }
+        g.dim[0] = L.nyl; g.kv[0] = L.kv; g.keep[0] = L.keep; g.ax[0] = 1;
+        g.dim[1] = pl->az.nk; g.kv[1] = pl->az.kv; g.keep[1] = pl->az.keep; g.ax[1] = 2;
+        g.dim[2] = pl->ax.nk; g.kv[2] = pl->ax.kv; g.keep[2] = pl->ax.keep; g.ax[2] = 0;
         g.twod = 0;
     } else {
         pl->ntot = (long long)pl->ax.n * pl->ay.n;
@@ -227,6 +277,11 @@ extern "C" int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x,
     return 0;
 }
 
+extern "C" int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x, const double* kx, const double* ky,
+                               const double* kz, const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz) {
+    return ddl_plan_create_slab(out, ndim, shape_x, kx, ky, kz, keepx, keepy, keepz, 1, 0);
+}
+
 extern "C" int ddl_plan_destroy(ddl_plan* pl) {
     if (!pl) return 0;
     for (void* p : pl->owned) dev_free(p);
@@ -235,23 +290,40 @@ extern "C" int ddl_plan_destroy(ddl_plan* pl) {
 }
 
 // ---------------------------------------------------------------- workspace layout
-struct WsLayout {
-    long long r0, r1, r2;   // region sizes in cplx elements
-};
 // pitch of the retained-kx axis in the 3-D workspace arrays: a multiple of 8 complex (128 B)
 // so that every CX-wide row segment of the strided passes is a whole number of cache lines
 static long long kx_pitch(const ddl_plan* pl) { return pl->ndim == 3 ? (pl->ax.cnt + 7) / 8 * 8 : pl->ax.cnt; }
 
+// Per-field sizes (complex elements) of the pipeline arrays of THIS rank, 3-D:
+//   ks : k-side pencils  [peer][cyl][nzl][CX]   z-pass output (inverse) / input (forward); peer-blocked rows
+//   xs : x-side pencils  [cy][nzl][CX]          y-pass input (inverse) / output (forward)
+//   b  : half-transformed lines [nzl][y][CX]    y-pass output / x-pass input and output
+//   e  : retained product spectra [cyl][cz][CX]
+struct SlabSizes { long long ks, xs, b, e; };
+static SlabSizes slab_sizes(const ddl_plan* pl) {
+    SlabSizes s;
+    const long long CX = kx_pitch(pl);
+    s.ks = (long long)pl->yl.cyl * pl->az.n * CX;
+    s.xs = (long long)pl->ay.cnt * pl->nzl * CX;
+    s.b = (long long)pl->nzl * pl->ay.n * CX;
+    s.e = (long long)pl->yl.cyl * pl->az.cnt * CX;
+    return s;
+}
+
+struct WsLayout {
+    long long r0, r1, r2;   // region sizes in cplx elements
+};
 static WsLayout ws_layout(const ddl_plan* pl, int ni, int no) {
     WsLayout w;
     const long long CX = kx_pitch(pl), CY = pl->ay.cnt;
     if (pl->ndim == 3) {
-        const long long CZ = pl->az.cnt, ny = pl->ay.n, nz = pl->az.n;
+        const SlabSizes s = slab_sizes(pl);
         const int nmax = ni > no ? ni : no;
-        w.r0 = nmax * CY * nz * CX;                               // A (inverse) / D (forward): [f][ky_c][z][kx_c]
-        long long b = (long long)ni * nz * ny * CX, e = (long long)no * CY * CZ * CX;
-        w.r1 = b > e ? b : e;                                     // B [f][z][y][kx_c], later E [f][ky_c][kz_c][kx_c]
-        w.r2 = (long long)no * nz * ny * CX;                      // C [f][z][y][kx_c]
+        const long long a = s.ks > s.xs ? s.ks : s.xs;            // one rank: ks == xs
+        w.r0 = nmax * a;                                          // k-side / x-side pencils (inverse), again (forward)
+        long long b = (long long)ni * s.b, e = (long long)no * s.e;
+        w.r1 = b > e ? b : e;                                     // B, later E
+        w.r2 = (long long)no * s.b;                               // C
     } else {
         const long long ny = pl->ay.n;
         w.r0 = (long long)ni * CX * ny;                           // A [f][kx_c][y]
@@ -302,13 +374,19 @@ static const RowSpec ALL_ROWS = {-1, 0};
 static int pass_c2c(const char* name, int N, int dir, int nf, const void* const* in, void* const* out, const TileSide& si,
                     const TileSide& so, RowSpec ri, RowSpec ro, int inner_len, int n_outer, double scale, const cplx* tw,
                     ddl_stream_t st) {
+    if (n_outer <= 0 || nf <= 0 || inner_len <= 0) return 0;     // a rank may own no retained ky row
 #if DDL_DEVICE_BUILD
-    if (g_use_fast && si.s_inner == 1 && so.s_inner == 1 && si.s_n != 1 && so.s_n != 1 && nf <= DDL_MAXF) {
+    const bool pow2 = !(si.split & (si.split - 1)) && !(so.split & (so.split - 1));
+    if (g_use_fast && si.s_inner == 1 && so.s_inner == 1 && si.s_n != 1 && so.s_n != 1 && nf <= DDL_MAXF && pow2) {
         FastParams f;
         memset(&f, 0, sizeof(f));
         for (int i = 0; i < nf; ++i) { f.in[i] = (const cplx*)in[i]; f.out[i] = (cplx*)out[i]; }
-        f.si.s_n = si.s_n; f.si.s_outer = si.s_outer; f.si.outer_tab = si.outer_tab; f.si.m = ri.m; f.si.compact = ri.compact;
-        f.so.s_n = so.s_n; f.so.s_outer = so.s_outer; f.so.outer_tab = so.outer_tab; f.so.m = ro.m; f.so.compact = ro.compact;
+        auto conv = [](FastSide& d, const TileSide& s, RowSpec r) {
+            d.s_n = s.s_n; d.s_outer = s.s_outer; d.outer_tab = s.outer_tab; d.m = r.m; d.compact = r.compact;
+            d.split_shift = 31; d.split_mask = 0x7fffffff; d.s_blk = 0;
+            if (s.split) { int sh = 0; while ((1 << sh) < s.split) ++sh; d.split_shift = sh; d.split_mask = s.split - 1; d.s_blk = s.s_blk; }
+        };
+        conv(f.si, si, ri); conv(f.so, so, ro);
         f.inner_len = inner_len; f.scale = scale; f.tw = tw;
         int rc = run_fast_strided(N, dir, f, nf, n_outer, name, st);
         if (rc <= 0) return rc;
@@ -332,6 +410,7 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
 static int pass_pair(const char* name, int N, int mode, int phys, int ni, int no, const void* const* in, void* const* out,
                      const TileSide& si, const TileSide& so, int n_lines, int n_outer, int kn, double scale,
                      const cplx* tw, const PhysConst& pc, ddl_stream_t st) {
+    if (n_outer <= 0) return 0;
     TileParams p;
     memset(&p, 0, sizeof(p));
     for (int f = 0; f < ni; ++f) p.in[f] = in[f];
@@ -351,65 +430,124 @@ static int pass_pair(const char* name, int N, int mode, int phys, int ni, int no
     return run_tile(N, mode, 0, phys, p, round32(g * p.nft * (N / rmax)), st);
 }
 
-static TileSide side(long long s_n, long long s_inner, long long s_outer, const int* n_tab, const int* outer_tab) {
+static TileSide side(long long s_n, long long s_inner, long long s_outer, const int* n_tab, const int* outer_tab,
+                     int split = 0, long long s_blk = 0) {
     TileSide s; s.s_n = s_n; s.s_inner = s_inner; s.s_outer = s_outer; s.n_tab = n_tab; s.outer_tab = outer_tab;
+    s.split = split; s.s_blk = s_blk;
     return s;
 }
 
 #define DDL_TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
-// inverse passes up to (not including) the pair pass: state (full k layout) -> half-transformed
-// arrays ready for the pair pass.  3-D: k -> A -> B ; 2-D: k -> A.
-static int inverse_head(ddl_plan* pl, int nf, const void* const* kin, cplx* r0, cplx* r1, void** heads, ddl_stream_t st) {
-    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
-    const long long CX = kx_pitch(pl);
-    const int nkx = X.cnt;
-    std::vector<void*> A(nf), B(nf);
-    if (pl->ndim == 3) {
-        const long long KP = X.nk, ny = Y.n, nz = Z.n, CY = Y.cnt;
-        for (int f = 0; f < nf; ++f) { A[f] = r0 + f * CY * nz * CX; B[f] = r1 + f * nz * ny * CX; }
-        // z pass: k[ky][kz][kx] -> A[ky_c][z][kx_c]
-        DDL_TRY(pass_c2c("z_inv", Z.n, +1, nf, kin, A.data(), side(KP, 1, nz * KP, Z.f2f, Y.c2f), side(CX, 1, nz * CX, nullptr, nullptr),
-                         RowSpec{Z.m, 0}, ALL_ROWS, nkx, (int)CY, 1.0, Z.tw, st));
-        // y pass: A[ky_c][z][kx_c] -> B[z][y][kx_c]
-        DDL_TRY(pass_c2c("y_inv", Y.n, +1, nf, A.data(), B.data(), side(nz * CX, 1, CX, Y.f2c, nullptr), side(CX, 1, ny * CX, nullptr, nullptr),
-                         RowSpec{Y.m, 1}, ALL_ROWS, nkx, (int)nz, 1.0, Y.tw, st));
-        for (int f = 0; f < nf; ++f) heads[f] = B[f];
-    } else {
-        const long long ny = Y.n;
-        for (int f = 0; f < nf; ++f) A[f] = r0 + f * CX * ny;
-        // ky pass along contiguous lines: k[kx][ky] -> A[kx_c][y]
-        DDL_TRY(pass_c2c("y_inv", Y.n, +1, nf, kin, A.data(), side(1, ny, 0, Y.f2f, nullptr), side(1, ny, 0, nullptr, nullptr),
-                         RowSpec{Y.m, 0}, ALL_ROWS, nkx, 1, 1.0, Y.tw, st));
-        for (int f = 0; f < nf; ++f) heads[f] = A[f];
-    }
-    return 0;
+static PhysConst phys_const(const ddl_phys_params* prm) {
+    PhysConst pc;
+    pc.inv_fpr = 1.0 / (4.0 * 3.14159265358979323846 * prm->rho0);
+    pc.g_alpha = prm->g * prm->alpha_t;
+    pc.beta = prm->beta;
+    pc.bdir = prm->boussinesq_dir;
+    return pc;
 }
 
-// forward passes after the pair pass: C -> (D ->) destination.  `full_out`: write straight into
-// full-layout k arrays (transform API) instead of the compact product arrays E.
-static int forward_tail(ddl_plan* pl, int nf, void* const* Cin, cplx* r0, void* const* dst, bool full_out, ddl_stream_t st) {
-    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+// ---------------------------------------------------------------- 3-D pipeline phases
+// One RHS / transform is  zinv -> [exchange] -> yinv -> x pass -> yfwd -> [exchange] -> zfwd.
+// With one rank the exchanges are the identity (the k-side and x-side pencil layouts coincide);
+// with P ranks the host layer moves peer block s of every k-side array to rank s (and back) with
+// an all-to-all between the calls (dedalus/data_objects/slab.py).
+
+// k-side layout of this rank: stored row z of compact local ky row j at
+//   (z / nzl) * (cyl*nzl*CX) + j * (nzl*CX) + (z % nzl) * CX
+static TileSide kside(const ddl_plan* pl) {
     const long long CX = kx_pitch(pl);
-    const int nkx = X.cnt;
-    if (pl->ndim == 3) {
-        const long long KP = X.nk, ny = Y.n, nz = Z.n, CY = Y.cnt, CZ = Z.cnt;
-        std::vector<void*> D(nf);
-        for (int f = 0; f < nf; ++f) D[f] = r0 + f * CY * nz * CX;
-        // y pass: C[z][y][kx_c] -> D[ky_c][z][kx_c]
-        DDL_TRY(pass_c2c("y_fwd", Y.n, -1, nf, Cin, D.data(), side(CX, 1, ny * CX, nullptr, nullptr), side(nz * CX, 1, CX, Y.f2c, nullptr),
-                         ALL_ROWS, RowSpec{Y.m, 1}, nkx, (int)nz, 1.0, Y.tw, st));
-        // z pass: D[ky_c][z][kx_c] -> E[ky_c][kz_c][kx_c]  or  k[ky][kz][kx]
-        TileSide so = full_out ? side(KP, 1, nz * KP, Z.f2f, Y.c2f) : side(CX, 1, CZ * CX, Z.f2c, nullptr);
-        DDL_TRY(pass_c2c("z_fwd", Z.n, -1, nf, D.data(), dst, side(CX, 1, nz * CX, nullptr, nullptr), so, ALL_ROWS,
-                         RowSpec{Z.m, full_out ? 0 : 1}, nkx, (int)CY, 1.0, Z.tw, st));
-    } else {
-        const long long ny = Y.n, CY = Y.cnt;
-        TileSide so = full_out ? side(1, ny, 0, Y.f2f, nullptr) : side(1, CY, 0, Y.f2c, nullptr);
-        DDL_TRY(pass_c2c("y_fwd", Y.n, -1, nf, Cin, dst, side(1, ny, 0, nullptr, nullptr), so, ALL_ROWS,
-                         RowSpec{Y.m, full_out ? 0 : 1}, nkx, 1, 1.0, Y.tw, st));
+    if (pl->nranks == 1) return side(CX, 1, (long long)pl->az.n * CX, nullptr, nullptr);
+    return side(CX, 1, (long long)pl->nzl * CX, nullptr, nullptr, pl->nzl, (long long)pl->yl.cyl * pl->nzl * CX);
+}
+
+// z pass, inverse: k[kyl][kz][kx] (retained modes) -> k-side pencils
+static int phase_zinv(ddl_plan* pl, int nf, const void* const* kin, void* const* S, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Z = pl->az;
+    const long long KP = X.nk;
+    return pass_c2c("z_inv", Z.n, +1, nf, kin, S, side(KP, 1, (long long)Z.n * KP, Z.f2f, pl->yl.c2f), kside(pl),
+                    RowSpec{Z.m, 0}, ALL_ROWS, X.cnt, pl->yl.cyl, 1.0, Z.tw, st);
+}
+// y pass, inverse: x-side pencils A[cy][nzl][CX] -> B[nzl][y][CX]
+static int phase_yinv(ddl_plan* pl, int nf, const void* const* A, void* const* B, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long CX = kx_pitch(pl), nzl = pl->nzl;
+    return pass_c2c("y_inv", Y.n, +1, nf, A, B, side(nzl * CX, 1, CX, Y.f2c, nullptr), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
+                    RowSpec{Y.m, 1}, ALL_ROWS, X.cnt, (int)nzl, 1.0, Y.tw, st);
+}
+// y pass, forward: C[nzl][y][CX] -> x-side pencils D[cy][nzl][CX]
+static int phase_yfwd(ddl_plan* pl, int nf, const void* const* Cin, void* const* D, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long CX = kx_pitch(pl), nzl = pl->nzl;
+    return pass_c2c("y_fwd", Y.n, -1, nf, Cin, D, side(CX, 1, (long long)Y.n * CX, nullptr, nullptr), side(nzl * CX, 1, CX, Y.f2c, nullptr),
+                    ALL_ROWS, RowSpec{Y.m, 1}, X.cnt, (int)nzl, 1.0, Y.tw, st);
+}
+// z pass, forward: k-side pencils -> E[cyl][kz_c][CX] (compact products) or k[kyl][kz][kx] (full_out)
+static int phase_zfwd(ddl_plan* pl, int nf, const void* const* R, void* const* dst, bool full_out, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Z = pl->az;
+    const long long KP = X.nk, CX = kx_pitch(pl);
+    TileSide so = full_out ? side(KP, 1, (long long)Z.n * KP, Z.f2f, pl->yl.c2f) : side(CX, 1, (long long)Z.cnt * CX, Z.f2c, nullptr);
+    return pass_c2c("z_fwd", Z.n, -1, nf, R, dst, kside(pl), so, ALL_ROWS, RowSpec{Z.m, full_out ? 0 : 1}, X.cnt, pl->yl.cyl,
+                    1.0, Z.tw, st);
+}
+// x pass with the real-space products: B[f][nzl][y][CX] -> C[f][nzl][y][CX]
+static int phase_xfused(ddl_plan* pl, int code, int ni, int no, const void* const* B, void* const* Cout, const PhysConst& pc,
+                        ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long KXP = kx_pitch(pl);
+    const double sc = 1.0 / (double)pl->ntot;
+    if (pl->nzl <= 0) return 0;
+    if (g_use_fast && Y.n % 2 == 0 && ni <= DDL_XF_MAXI && no <= DDL_XF_MAXO) {
+        XFusedParams xp;
+        memset(&xp, 0, sizeof(xp));
+        for (int f = 0; f < ni; ++f) xp.in[f] = (const cplx*)B[f];
+        for (int f = 0; f < no; ++f) xp.out[f] = (cplx*)Cout[f];
+        xp.pitch = KXP; xp.s_outer = (long long)Y.n * KXP; xp.n_lines = Y.n; xp.kn = X.cnt;
+        xp.scale = sc; xp.tw = X.tw; xp.pc = pc;
+        const int rcx = run_xfused(X.n, code, xp, pl->nzl, st);
+        if (rcx <= 0) return rcx;
     }
+    TileSide s = side(1, KXP, (long long)Y.n * KXP, nullptr, nullptr);
+    return pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, B, Cout, s, s, Y.n, pl->nzl, X.cnt, sc, X.tw, pc, st);
+}
+// plain x passes of the transform API: B[nzl][y][CX] -> x[nzl][y][nx] and back (normalised)
+static int phase_xc2r(ddl_plan* pl, const void* B, double* x, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const void* in[1] = {B};
+    void* out[1] = {x};
+    PhysConst pc = {};
+    return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, in, out, side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr),
+                     side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr), Y.n, pl->nzl, X.cnt, 1.0, X.tw, pc, st);
+}
+static int phase_xr2c(ddl_plan* pl, const double* x, void* Cout, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const void* in[1] = {x};
+    void* out[1] = {Cout};
+    PhysConst pc = {};
+    return pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, in, out, side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr),
+                     side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr), Y.n, pl->nzl, X.cnt,
+                     1.0 / (double)pl->ntot, X.tw, pc, st);
+}
+
+// ---------------------------------------------------------------- 2-D passes
+// inverse: k[kx][ky] -> A[kx_c][y];  forward tail: C[kx_c][y] -> E[kx_c][ky_c] or k[kx][ky]
+static int inverse_head_2d(ddl_plan* pl, int nf, const void* const* kin, cplx* r0, void** heads, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long CX = kx_pitch(pl), ny = Y.n;
+    std::vector<void*> A(nf);
+    for (int f = 0; f < nf; ++f) A[f] = r0 + f * CX * ny;
+    DDL_TRY(pass_c2c("y_inv", Y.n, +1, nf, kin, A.data(), side(1, ny, 0, Y.f2f, nullptr), side(1, ny, 0, nullptr, nullptr),
+                     RowSpec{Y.m, 0}, ALL_ROWS, X.cnt, 1, 1.0, Y.tw, st));
+    for (int f = 0; f < nf; ++f) heads[f] = A[f];
     return 0;
+}
+static int forward_tail_2d(ddl_plan* pl, int nf, void* const* Cin, void* const* dst, bool full_out, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long ny = Y.n, CY = Y.cnt;
+    TileSide so = full_out ? side(1, ny, 0, Y.f2f, nullptr) : side(1, CY, 0, Y.f2c, nullptr);
+    return pass_c2c("y_fwd", Y.n, -1, nf, Cin, dst, side(1, ny, 0, nullptr, nullptr), so, ALL_ROWS,
+                    RowSpec{Y.m, full_out ? 0 : 1}, X.cnt, 1, 1.0, Y.tw, st);
 }
 
 static int mask_arrays(ddl_plan* pl, int n, void* const* arr, ddl_stream_t st) {
@@ -433,6 +571,13 @@ static int check_ws(const ddl_plan* pl, int ni, int no, void* work, size_t bytes
     }
     return 0;
 }
+static int need_one_rank(const ddl_plan* pl, const char* what) {
+    if (pl->nranks != 1) {
+        set_error("%s is the one-rank entry point; a slab-decomposed plan (%d ranks) goes through the ddl_slab_* phases", what, pl->nranks);
+        return -1;
+    }
+    return 0;
+}
 
 // ---------------------------------------------------------------- transforms
 extern "C" int ddl_dealias(ddl_plan* pl, void* k, void* stream) {
@@ -442,41 +587,50 @@ extern "C" int ddl_dealias(ddl_plan* pl, void* k, void* stream) {
 
 extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t work_bytes, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
+    DDL_TRY(need_one_rank(pl, "ddl_backward"));
     DDL_TRY(check_ws(pl, 1, 1, work, work_bytes));
     DDL_TRY(ddl_dealias(pl, k, stream));
     WsLayout w = ws_layout(pl, 1, 1);
     cplx* r0 = (cplx*)work; cplx* r1 = r0 + w.r0;
     const void* kin[1] = {k};
+    if (pl->ndim == 3) {
+        void* A[1] = {r0};
+        void* B[1] = {r1};
+        DDL_TRY(phase_zinv(pl, 1, kin, A, st));
+        DDL_TRY(phase_yinv(pl, 1, A, B, st));
+        return phase_xc2r(pl, r1, x, st);
+    }
+    const Axis &X = pl->ax, &Y = pl->ay;
     void* head[1];
-    DDL_TRY(inverse_head(pl, 1, kin, r0, r1, head, st));
-    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+    DDL_TRY(inverse_head_2d(pl, 1, kin, r0, head, st));
     void* xo[1] = {x};
     PhysConst pc = {};
-    if (pl->ndim == 3)
-        return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr),
-                         side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr), Y.n, Z.n, X.cnt, 1.0, X.tw, pc, st);
     return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(Y.n, 1, 0, nullptr, nullptr), side(1, X.n, 0, nullptr, nullptr),
                      Y.n, 1, X.cnt, 1.0, X.tw, pc, st);
 }
 
 extern "C" int ddl_forward(ddl_plan* pl, const double* x, void* k, void* work, size_t work_bytes, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
+    DDL_TRY(need_one_rank(pl, "ddl_forward"));
     DDL_TRY(check_ws(pl, 1, 1, work, work_bytes));
     WsLayout w = ws_layout(pl, 1, 1);
     cplx* r0 = (cplx*)work; cplx* r2 = r0 + w.r0 + w.r1;
-    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
-    const void* xi[1] = {x};
-    void* C[1] = {pl->ndim == 3 ? (void*)r2 : (void*)(r0 + w.r0)};
-    PhysConst pc = {};
-    const double sc = 1.0 / (double)pl->ntot;
-    if (pl->ndim == 3)
-        DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr),
-                          side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr), Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
-    else
-        DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, C, side(1, X.n, 0, nullptr, nullptr), side(Y.n, 1, 0, nullptr, nullptr),
-                          Y.n, 1, X.cnt, sc, X.tw, pc, st));
     void* dst[1] = {k};
-    DDL_TRY(forward_tail(pl, 1, C, r0, dst, true, st));
+    if (pl->ndim == 3) {
+        void* Cb[1] = {r2};
+        void* D[1] = {r0};
+        DDL_TRY(phase_xr2c(pl, x, r2, st));
+        DDL_TRY(phase_yfwd(pl, 1, Cb, D, st));
+        DDL_TRY(phase_zfwd(pl, 1, D, dst, true, st));
+        return ddl_dealias(pl, k, stream);
+    }
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const void* xi[1] = {x};
+    void* Cb[1] = {(void*)(r0 + w.r0)};
+    PhysConst pc = {};
+    DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, Cb, side(1, X.n, 0, nullptr, nullptr), side(Y.n, 1, 0, nullptr, nullptr),
+                      Y.n, 1, X.cnt, 1.0 / (double)pl->ntot, X.tw, pc, st));
+    DDL_TRY(forward_tail_2d(pl, 1, Cb, dst, true, st));
     return ddl_dealias(pl, k, stream);
 }
 
@@ -490,24 +644,23 @@ extern "C" int ddl_deriv(ddl_plan* pl, const void* k_in, void* k_out, int axis, 
 
 // ---------------------------------------------------------------- fused RHS
 template <class PHYS>
-static int assemble(ddl_plan* pl, cplx* E, void* const* state, void* const* deriv, const PhysConst& pc, ddl_stream_t st) {
+static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* const* deriv, const PhysConst& pc, ddl_stream_t st) {
     AssembleF<PHYS> f;
     const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
-    const long long CX = X.cnt, CY = Y.cnt, KXP = kx_pitch(pl);
-    long long per, count;
+    const long long CX = X.cnt, KXP = kx_pitch(pl);
+    long long count;
     if (pl->ndim == 3) {
-        const long long CZ = Z.cnt;
-        per = CY * CZ * KXP;
-        count = CY * CZ * CX;
-        f.cdim[0] = (int)CY; f.cdim[1] = (int)CZ; f.cdim[2] = (int)CX;
+        const long long CZ = Z.cnt, CYL = pl->yl.cyl;
+        count = CYL * CZ * CX;
+        f.cdim[0] = (int)CYL; f.cdim[1] = (int)CZ; f.cdim[2] = (int)CX;
         f.cstride[0] = CZ * KXP; f.cstride[1] = KXP; f.cstride[2] = 1;
         f.fstride[0] = (long long)Z.n * X.nk; f.fstride[1] = X.nk; f.fstride[2] = 1;
-        f.ftab[0] = Y.c2f; f.ftab[1] = Z.c2f; f.ftab[2] = nullptr;
-        f.kvc[0] = Y.kvc; f.kvc[1] = Z.kvc; f.kvc[2] = X.kvc;
+        f.ftab[0] = pl->yl.c2f; f.ftab[1] = Z.c2f; f.ftab[2] = nullptr;
+        f.kvc[0] = pl->yl.kvc; f.kvc[1] = Z.kvc; f.kvc[2] = X.kvc;
         f.ax[0] = 1; f.ax[1] = 2; f.ax[2] = 0;
     } else {
-        per = CX * CY;
-        count = per;
+        const long long CY = Y.cnt;
+        count = CX * CY;
         f.cdim[0] = 1; f.cdim[1] = (int)CX; f.cdim[2] = (int)CY;
         f.cstride[0] = 0; f.cstride[1] = CY; f.cstride[2] = 1;
         f.fstride[0] = 0; f.fstride[1] = Y.n; f.fstride[2] = 1;
@@ -515,76 +668,127 @@ static int assemble(ddl_plan* pl, cplx* E, void* const* state, void* const* deri
         f.kvc[0] = nullptr; f.kvc[1] = X.kvc; f.kvc[2] = Y.kvc;
         f.ax[0] = -1; f.ax[1] = 0; f.ax[2] = 1;
     }
-    for (int i = 0; i < PHYS::NO; ++i) f.P[i] = E + i * per;
+    for (int i = 0; i < PHYS::NO; ++i) f.P[i] = (const cplx*)E[i];
     for (int i = 0; i < PHYS::NS; ++i) f.S[i] = (const cplx*)state[i];
     for (int i = 0; i < PHYS::NC; ++i) f.D[i] = (cplx*)deriv[i];
     f.pc = pc;
     return launch_items(f, count, st, "assemble");
 }
 
+static int assemble_any(ddl_plan* pl, int code, void* const* E, void* const* state, void* const* deriv, const PhysConst& pc,
+                        ddl_stream_t st) {
+    switch (code) {
+        case 0: return assemble<Hydro2C>(pl, E, state, deriv, pc, st);
+        case 1: return assemble<Bouss2C>(pl, E, state, deriv, pc, st);
+        case 2: return assemble<MHD2C>(pl, E, state, deriv, pc, st);
+        case 3: return assemble<Hydro3C>(pl, E, state, deriv, pc, st);
+        case 4: return assemble<Bouss3C>(pl, E, state, deriv, pc, st);
+        default: return assemble<MHD3C>(pl, E, state, deriv, pc, st);
+    }
+}
+
+static int check_physics(const ddl_plan* pl, int physics, const ddl_phys_params* prm) {
+    if (physics < 0 || physics > 2) { set_error("unknown physics id %d", physics); return -1; }
+    if (physics == DDL_BOUSSINESQ && (prm->boussinesq_dir < 0 || prm->boussinesq_dir >= pl->ndim)) {
+        set_error("boussinesq_direction component %d not present in %d-D", prm->boussinesq_dir, pl->ndim);
+        return -1;
+    }
+    return 0;
+}
+
 extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
                        void* work, size_t work_bytes, int flags, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
     int ni, no, code;
-    if (physics < 0 || physics > 2) { set_error("unknown physics id %d", physics); return -1; }
+    DDL_TRY(need_one_rank(pl, "ddl_rhs"));
+    DDL_TRY(check_physics(pl, physics, prm));
     phys_counts(pl->ndim, physics, ni, no, code);
     DDL_TRY(check_ws(pl, ni, no, work, work_bytes));
-    PhysConst pc;
-    pc.inv_fpr = 1.0 / (4.0 * 3.14159265358979323846 * prm->rho0);
-    pc.g_alpha = prm->g * prm->alpha_t;
-    pc.beta = prm->beta;
-    pc.bdir = prm->boussinesq_dir;
-    if (physics == DDL_BOUSSINESQ && (pc.bdir < 0 || pc.bdir >= pl->ndim)) {
-        set_error("boussinesq_direction component %d not present in %d-D", pc.bdir, pl->ndim);
-        return -1;
-    }
+    const PhysConst pc = phys_const(prm);
     const int ncomp = ni;   // state components == inverse transforms in the conservative forms
     if (flags & DDL_RHS_DEALIAS_STATE) DDL_TRY(mask_arrays(pl, ncomp, state, st));
     if (flags & DDL_RHS_ZERO_FILL) DDL_TRY(mask_arrays(pl, ncomp, deriv, st));
 
     WsLayout w = ws_layout(pl, ni, no);
     cplx* r0 = (cplx*)work; cplx* r1 = r0 + w.r0; cplx* r2 = r1 + w.r1;
-    const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
-    std::vector<void*> head(ni), C(no), E(no);
-    DDL_TRY(inverse_head(pl, ni, (const void* const*)state, r0, r1, head.data(), st));
-    const double sc = 1.0 / (double)pl->ntot;
-    cplx* Ebase;
+    const Axis &X = pl->ax, &Y = pl->ay;
+    std::vector<void*> A(ni), B(ni), C(no), D(no), E(no);
     if (pl->ndim == 3) {
-        const long long KXP = kx_pitch(pl);
-        const long long per = (long long)Z.n * Y.n * KXP, pere = (long long)Y.cnt * Z.cnt * KXP;
-        for (int f = 0; f < no; ++f) { C[f] = r2 + f * per; E[f] = r1 + f * pere; }
-        Ebase = r1;
-        int rcx = 1;
-        if (g_use_fast && Y.n % 2 == 0 && ni <= DDL_XF_MAXI && no <= DDL_XF_MAXO) {
-            XFusedParams xp;
-            memset(&xp, 0, sizeof(xp));
-            for (int f = 0; f < ni; ++f) xp.in[f] = (const cplx*)head[f];
-            for (int f = 0; f < no; ++f) xp.out[f] = (cplx*)C[f];
-            xp.pitch = KXP; xp.s_outer = (long long)Y.n * KXP; xp.n_lines = Y.n; xp.kn = X.cnt;
-            xp.scale = sc; xp.tw = X.tw; xp.pc = pc;
-            rcx = run_xfused(X.n, code, xp, Z.n, st);
-            if (rcx < 0) return rcx;
-        }
-        if (rcx > 0) {
-            TileSide s = side(1, KXP, (long long)Y.n * KXP, nullptr, nullptr);
-            DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, Z.n, X.cnt, sc, X.tw, pc, st));
-        }
+        const SlabSizes s = slab_sizes(pl);
+        for (int f = 0; f < ni; ++f) { A[f] = r0 + f * s.ks; B[f] = r1 + f * s.b; }
+        for (int f = 0; f < no; ++f) { C[f] = r2 + f * s.b; D[f] = r0 + f * s.ks; E[f] = r1 + f * s.e; }
+        DDL_TRY(phase_zinv(pl, ni, (const void* const*)state, A.data(), st));
+        DDL_TRY(phase_yinv(pl, ni, A.data(), B.data(), st));
+        DDL_TRY(phase_xfused(pl, code, ni, no, B.data(), C.data(), pc, st));
+        DDL_TRY(phase_yfwd(pl, no, C.data(), D.data(), st));
+        DDL_TRY(phase_zfwd(pl, no, D.data(), E.data(), false, st));
     } else {
+        const double sc = 1.0 / (double)pl->ntot;
+        DDL_TRY(inverse_head_2d(pl, ni, (const void* const*)state, r0, A.data(), st));
         const long long per = (long long)X.cnt * Y.n, pere = (long long)X.cnt * Y.cnt;
         for (int f = 0; f < no; ++f) { C[f] = r1 + f * per; E[f] = r2 + f * pere; }
-        Ebase = r2;
         TileSide s = side(Y.n, 1, 0, nullptr, nullptr);
-        DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, head.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st));
+        DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, A.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st));
+        DDL_TRY(forward_tail_2d(pl, no, C.data(), E.data(), false, st));
     }
-    DDL_TRY(forward_tail(pl, no, C.data(), r0, E.data(), false, st));
-    switch (code) {
-        case 0: return assemble<Hydro2C>(pl, Ebase, state, deriv, pc, st);
-        case 1: return assemble<Bouss2C>(pl, Ebase, state, deriv, pc, st);
-        case 2: return assemble<MHD2C>(pl, Ebase, state, deriv, pc, st);
-        case 3: return assemble<Hydro3C>(pl, Ebase, state, deriv, pc, st);
-        case 4: return assemble<Bouss3C>(pl, Ebase, state, deriv, pc, st);
-        default: return assemble<MHD3C>(pl, Ebase, state, deriv, pc, st);
-    }
+    return assemble_any(pl, code, E.data(), state, deriv, pc, st);
+}
+
+// ---------------------------------------------------------------- slab phase API (include/ddl.h)
+extern "C" int ddl_slab_info(const ddl_plan* pl, int64_t* out) {
+    const SlabSizes s = slab_sizes(pl);
+    out[0] = pl->nranks; out[1] = pl->rank; out[2] = pl->nzl; out[3] = pl->yl.nyl; out[4] = pl->yl.cyl; out[5] = pl->yl.cy0;
+    out[6] = pl->ay.cnt; out[7] = pl->az.cnt; out[8] = kx_pitch(pl); out[9] = pl->ax.cnt;
+    out[10] = s.ks; out[11] = s.xs; out[12] = s.b; out[13] = s.e; out[14] = pl->z0; out[15] = pl->yl.ky0;
+    return 0;
+}
+extern "C" int ddl_slab_rows(const ddl_plan* pl, int64_t* cyl_of_rank) {
+    for (int r = 0; r < pl->nranks; ++r) cyl_of_rank[r] = pl->cyl_of[r];
+    return 0;
+}
+static int need_3d(const ddl_plan* pl) {
+    if (pl->ndim != 3) { set_error("the slab phase API is 3-D only"); return -1; }
+    return 0;
+}
+extern "C" int ddl_slab_zinv(ddl_plan* pl, int nf, void* const* k_in, void* const* ks_out, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_zinv(pl, nf, (const void* const*)k_in, ks_out, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_yinv(ddl_plan* pl, int nf, void* const* xs_in, void* const* b_out, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_yinv(pl, nf, (const void* const*)xs_in, b_out, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_xfused(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* b_in, void* const* c_out,
+                               void* stream) {
+    int ni, no, code;
+    DDL_TRY(need_3d(pl));
+    DDL_TRY(check_physics(pl, physics, prm));
+    phys_counts(3, physics, ni, no, code);
+    return phase_xfused(pl, code, ni, no, (const void* const*)b_in, c_out, phys_const(prm), (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_xc2r(ddl_plan* pl, const void* b_in, double* x_out, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_xc2r(pl, b_in, x_out, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_xr2c(ddl_plan* pl, const double* x_in, void* c_out, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_xr2c(pl, x_in, c_out, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_yfwd(ddl_plan* pl, int nf, void* const* c_in, void* const* xs_out, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_yfwd(pl, nf, (const void* const*)c_in, xs_out, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_zfwd(ddl_plan* pl, int nf, void* const* ks_in, void* const* out, int full_out, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_zfwd(pl, nf, (const void* const*)ks_in, out, full_out != 0, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_assemble(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* e_in, void* const* state,
+                                 void* const* deriv, void* stream) {
+    int ni, no, code;
+    DDL_TRY(need_3d(pl));
+    DDL_TRY(check_physics(pl, physics, prm));
+    phys_counts(3, physics, ni, no, code);
+    return assemble_any(pl, code, e_in, state, deriv, phys_const(prm), (ddl_stream_t)stream);
 }
 
 // ---------------------------------------------------------------- stage updates
@@ -598,10 +802,10 @@ static int fill_stage(ddl_plan* pl, StageArgs& a, int ncomp, const double* coeff
         const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
         a.compact = 1;
         if (pl->ndim == 3) {
-            a.cdim[0] = Y.cnt; a.cdim[1] = Z.cnt; a.cdim[2] = X.cnt;
+            a.cdim[0] = pl->yl.cyl; a.cdim[1] = Z.cnt; a.cdim[2] = X.cnt;
             a.fstride[0] = (long long)Z.n * X.nk; a.fstride[1] = X.nk; a.fstride[2] = 1;
-            a.ftab[0] = Y.c2f; a.ftab[1] = Z.c2f; a.ftab[2] = nullptr;
-            a.kvc[0] = Y.kvc; a.kvc[1] = Z.kvc; a.kvc[2] = X.kvc;
+            a.ftab[0] = pl->yl.c2f; a.ftab[1] = Z.c2f; a.ftab[2] = nullptr;
+            a.kvc[0] = pl->yl.kvc; a.kvc[1] = Z.kvc; a.kvc[2] = X.kvc;
         } else {
             a.cdim[0] = 1; a.cdim[1] = X.cnt; a.cdim[2] = Y.cnt;
             a.fstride[0] = 0; a.fstride[1] = Y.n; a.fstride[2] = 1;
@@ -663,6 +867,7 @@ extern "C" int ddl_sync(void* stream) {
 
 extern "C" int ddl_set_option(const char* name, int value) {
     if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
+    if (name && !strcmp(name, "xfused_variant")) { g_xfused_variant = value; return 0; }
     set_error("unknown option %s", name ? name : "(null)");
     return -1;
 }

@@ -21,7 +21,15 @@ struct FastSide {
     const int* outer_tab;     // outer index -> stored outer index (NULL = identity)
     int m;                    // retained rows |index| <= m, or -1 = every row present
     int compact;              // retained rows stored contiguously (workspace) instead of in place (state)
+    // slab exchange buffers: stored row r sits at (r >> split_shift) * s_blk + (r & split_mask) * s_n
+    // (split_shift = 31, split_mask = 0x7fffffff: plain rows)
+    int split_shift, split_mask;
+    long long s_blk;
 };
+
+__device__ __forceinline__ long long fast_row_off(const FastSide& s, int r) {
+    return (long long)(r >> s.split_shift) * s.s_blk + (long long)(r & s.split_mask) * s.s_n;
+}
 
 struct FastParams {
     const cplx* in[DDL_MAXF];
@@ -113,7 +121,7 @@ strided_fast(const __grid_constant__ FastParams p) {
 #pragma unroll
         for (int j = 0; j < R0; ++j) {
             const int row = fast_row<N>(a + j * Q0, p.si.m, p.si.compact);
-            v[j] = (live && row >= 0) ? in[ib + (long long)row * p.si.s_n] : mk(0.0, 0.0);
+            v[j] = (live && row >= 0) ? in[ib + fast_row_off(p.si, row)] : mk(0.0, 0.0);
         }
         dftR<R0, DIR>(v);
         twiddles_ld<R0, DIR>(v, a, tw);
@@ -142,7 +150,7 @@ strided_fast(const __grid_constant__ FastParams p) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int row = fast_row<N>(k0 + r * (N / R), p.so.m, p.so.compact);
-                if (live && row >= 0) out[ob + (long long)row * p.so.s_n] = scal(v[r], sc);
+                if (live && row >= 0) out[ob + fast_row_off(p.so, row)] = scal(v[r], sc);
             }
         }
     }

@@ -35,13 +35,13 @@ int DDL_CAT(run_tile_, DDL_N)(int mode, int dir, int phys, const TileParams& p, 
 }
 
 // specialised fused x-pass of the 3-D RHS; returns 1 if this length / physics has none
-int DDL_CAT(run_xfused_, DDL_N)(int phys, const XFusedParams& p, int n_outer, ddl_stream_t s) {
+int DDL_CAT(run_xfused_, DDL_N)(int phys, const XFusedParams& p, int n_outer, int variant, ddl_stream_t s) {
     constexpr int N = DDL_N;
     if constexpr (XFac<N>::ok) {
         switch (phys) {
-            case 3: return launch_xfused<N, Hydro3C>(p, n_outer, s);
-            case 4: return launch_xfused<N, Bouss3C>(p, n_outer, s);
-            case 5: return launch_xfused<N, MHD3C>(p, n_outer, s);
+            case 3: return launch_xfused<N, Hydro3C>(p, n_outer, variant, s);
+            case 4: return launch_xfused<N, Bouss3C>(p, n_outer, variant, s);
+            case 5: return launch_xfused<N, MHD3C>(p, n_outer, variant, s);
         }
     }
     return 1;

@@ -23,7 +23,15 @@ struct TileSide {
     long long s_n, s_inner, s_outer;   // element strides: transform axis, pencil (inner) index, outer index
     const int* n_tab;                  // spectral side: logical row -> stored row, -1 = absent (zero / skip); NULL = identity
     const int* outer_tab;              // outer index -> stored outer index; NULL = identity
+    // slab exchange buffers: rows come in `split` consecutive rows per peer block (0 = plain):
+    // stored row r sits at (r / split) * s_blk + (r % split) * s_n
+    int split;
+    long long s_blk;
 };
+
+DDL_HD long long row_off(const TileSide& s, int r) {
+    return s.split ? (long long)(r / s.split) * s.s_blk + (long long)(r % s.split) * s.s_n : (long long)r * s.s_n;
+}
 
 struct TileParams {
     const void* in[DDL_MAXF];
@@ -91,7 +99,7 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
             if (in_nfast) { n = i % N; c = i / N; } else { c = i % npc; n = i / npc; }
             const int pn = p.si.n_tab ? p.si.n_tab[n] : n;
             cplx v = mk(0.0, 0.0);
-            if (pn >= 0) v = in[ib + (long long)pn * p.si.s_n + (long long)c * p.si.s_inner];
+            if (pn >= 0) v = in[ib + row_off(p.si, pn) + (long long)c * p.si.s_inner];
             tile[n * ld + c] = v;
         }
         DDL_SYNC();
@@ -103,7 +111,7 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
             if (out_nfast) { k = i % N; c = i / N; pos = pos_of_index<N>(k); }
             else { c = i % npc; pos = i / npc; k = index_of_pos<N>(pos); }
             const int pk = p.so.n_tab ? p.so.n_tab[k] : k;
-            if (pk >= 0) out[ob + (long long)pk * p.so.s_n + (long long)c * p.so.s_inner] = scal(tile[pos * ld + c], sc);
+            if (pk >= 0) out[ob + row_off(p.so, pk) + (long long)c * p.so.s_inner] = scal(tile[pos * ld + c], sc);
         }
     } else {
         constexpr int NI = PHYS::NI, NO = PHYS::NO;

@@ -384,15 +384,16 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
     }
 }
 
-template <int N, class PHYS> struct XFusedCfg {
+// Launch variants (ddl_set_option("xfused_variant", v); the default is the measured best):
+//   0: 6 warps per CTA, 3 CTAs per SM   1: 9 warps per CTA, 2 CTAs per SM   2: 6 warps, 2 CTAs (more registers)
+template <int N, class PHYS, int V> struct XFusedCfg {
     static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
     static constexpr int G = (N >= 512) ? 1 : 512 / N;
     static constexpr int TP = N / XFac<N>::radix(0);
-    // six warps: one round of inverse pencils for MHD (6) and two of forward pencils (9); with
-    // 72 KB of pencils per CTA three CTAs share an SM at <= 112 registers per thread
-    static constexpr int NT = TP > 32 ? 9 * TP : 192;
+    static constexpr int NT = TP > 32 ? 9 * TP : (V == 1 ? 288 : 192);
     static constexpr size_t SMEM = (size_t)G * NS * N * sizeof(cplx);
-    static constexpr int MINB = (SMEM * 3 <= 222 * 1024 && NT * 3 <= 1024) ? 3 : ((SMEM * 2 <= 222 * 1024 && NT * 2 <= 1024) ? 2 : 1);
+    static constexpr int WANT = (V == 0) ? 3 : 2;
+    static constexpr int MINB = (SMEM * WANT <= 222 * 1024 && NT * WANT <= 1024) ? WANT : ((SMEM * 2 <= 222 * 1024 && NT * 2 <= 1024) ? 2 : 1);
     // register budget that still lets MINB CTAs share an SM: each of the four sub-partitions owns
     // 16 K registers and holds ceil(warps / 4) of the resident warps (allocation unit: 8 per thread)
     static constexpr int WPS = (NT / 32 * MINB + 3) / 4;
@@ -400,22 +401,22 @@ template <int N, class PHYS> struct XFusedCfg {
 };
 
 #if DDL_DEVICE_BUILD
-template <int N, class PHYS>
-__global__ void __maxnreg__((XFusedCfg<N, PHYS>::MAXREG))
+template <int N, class PHYS, int V>
+__global__ void __maxnreg__((XFusedCfg<N, PHYS, V>::MAXREG))
 xfused_kernel(const __grid_constant__ XFusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    xfused_block<N, PHYS, XFusedCfg<N, PHYS>::NT, XFusedCfg<N, PHYS>::G>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
+    xfused_block<N, PHYS, XFusedCfg<N, PHYS, V>::NT, XFusedCfg<N, PHYS, V>::G>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
 }
 #endif
 
 // returns 0 on success, negative on error
-template <int N, class PHYS>
-int launch_xfused(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
-    using Cfg = XFusedCfg<N, PHYS>;
+template <int N, class PHYS, int V>
+int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
+    using Cfg = XFusedCfg<N, PHYS, V>;
     const int pairs = (p.n_lines + 1) / 2;
     const int gx = (pairs + Cfg::G - 1) / Cfg::G;
 #if DDL_DEVICE_BUILD
-    auto kern = xfused_kernel<N, PHYS>;
+    auto kern = xfused_kernel<N, PHYS, V>;
     static bool attr_done = false;
     if (!attr_done) {
         DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -435,6 +436,17 @@ int launch_xfused(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     free(tile);
 #endif
     return 0;
+}
+
+template <int N, class PHYS>
+int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t stream) {
+#if DDL_DEVICE_BUILD
+    if (variant == 1) return launch_xfused_v<N, PHYS, 1>(p, n_outer, stream);
+    if (variant == 2) return launch_xfused_v<N, PHYS, 2>(p, n_outer, stream);
+#else
+    (void)variant;
+#endif
+    return launch_xfused_v<N, PHYS, 0>(p, n_outer, stream);
 }
 
 }  // namespace ddl

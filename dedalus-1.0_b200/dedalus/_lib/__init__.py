@@ -11,9 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libddl_b200.so")
 
 EXPORTS = [
-    "ddl_plan_create", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
+    "ddl_plan_create", "ddl_plan_create_slab", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
     "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_deriv", "ddl_rhs", "ddl_stage",
-    "ddl_rk4_stage", "ddl_cn_step", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_rk4_stage", "ddl_cn_step", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_zinv", "ddl_slab_yinv",
+    "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
@@ -31,6 +32,22 @@ class DDLError(RuntimeError):
     pass
 
 
+def bind_slab(lib):
+    """argtypes of the slab phase API (also applied to the host-emulation library in tests)."""
+    vp, i32 = C.c_void_p, C.c_int
+    lib.ddl_slab_info.argtypes = [vp, vp]
+    lib.ddl_slab_rows.argtypes = [vp, vp]
+    lib.ddl_slab_zinv.argtypes = [vp, i32, vp, vp, vp]
+    lib.ddl_slab_yinv.argtypes = [vp, i32, vp, vp, vp]
+    lib.ddl_slab_xfused.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.ddl_slab_xc2r.argtypes = [vp, vp, vp, vp]
+    lib.ddl_slab_xr2c.argtypes = [vp, vp, vp, vp]
+    lib.ddl_slab_yfwd.argtypes = [vp, i32, vp, vp, vp]
+    lib.ddl_slab_zfwd.argtypes = [vp, i32, vp, vp, i32, vp]
+    lib.ddl_slab_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.ddl_dealias.argtypes = [vp, vp, vp]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -39,7 +56,9 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
     lib.ddl_plan_create.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.ddl_plan_create_slab.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, vp, vp, i32, i32]
     lib.ddl_plan_destroy.argtypes = [vp]
+    bind_slab(lib)
     lib.ddl_workspace_bytes.argtypes = [vp, i32, i32]
     lib.ddl_workspace_bytes.restype = sz
     lib.ddl_rhs_workspace_bytes.argtypes = [vp, i32]

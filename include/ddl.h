@@ -62,6 +62,19 @@ int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x,
                     const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz);
 int ddl_plan_destroy(ddl_plan* plan);
 
+/* Same, for rank `rank` of an `nranks`-way slab decomposition (3-D only; nranks a power of two
+ * dividing nz and ny).  Partition of the reference / FFTW-MPI (_fftw.pyx:114-148,
+ * representations.py:180-186,231-233): x-space is split along z (nz/nranks planes per rank),
+ * k-space along ky (ny/nranks rows per rank).  kx,ky,kz,keep* are the GLOBAL axis arrays; every
+ * k-space pointer later passed with this plan is the rank's LOCAL slab [ny/nranks][nz][nx/2+1],
+ * every x-space pointer its local [nz/nranks][ny][nx].  ddl_dealias / ddl_deriv / ddl_stage /
+ * ddl_rk4_stage / ddl_cn_step work on the local slab unchanged; transforms and the RHS go
+ * through the ddl_slab_* phases below with the exchange done by the caller between them. */
+int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* shape_x,
+                         const double* kx, const double* ky, const double* kz,
+                         const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz,
+                         int nranks, int rank);
+
 /* scratch requirement of ddl_rhs / ddl_forward / ddl_backward for n_in inverse and n_out
  * forward transforms in flight (the transforms use n_in = n_out = 1) */
 size_t ddl_workspace_bytes(const ddl_plan* plan, int n_in, int n_out);
@@ -81,6 +94,41 @@ int ddl_deriv(ddl_plan* plan, const void* k_in, void* k_out, int axis, void* str
 int ddl_rhs(ddl_plan* plan, int physics, const ddl_phys_params* params,
             void* const* state, void* const* deriv, void* work, size_t work_bytes,
             int flags, void* stream);
+
+/* ---- 3-D pipeline phases (one rank: ddl_rhs / ddl_forward / ddl_backward chain them) --------
+ * A transform is  z pass -> [exchange] -> y pass -> x pass  (inverse) and the mirror (forward);
+ * FFTW-MPI hides the exchange inside fftw_execute (_fftw.pyx:232-234,272-304), here it is the
+ * caller's: between the z and y passes block s of every "k-side" array goes to rank s and lands
+ * as block r of the peer's "x-side" array (an all-to-all of contiguous blocks; sizes below).
+ *   k-side array, per field: [peer s][cyl][nzl][CX]      x-side array: [cy][nzl][CX]
+ *   b / c arrays (x-pass input / output): [nzl][ny][CX]  e array: [cyl][cz][CX]
+ * cyl = retained ky rows owned by this rank, cy = all retained ky rows, cz = retained kz rows,
+ * nzl = local z planes, CX = pitch of the retained kx axis.
+ * ddl_slab_info fills out[16] = {nranks, rank, nzl, nyl, cyl, cy0, cy, cz, CX, nkx,
+ *   k-side elements, x-side elements, b elements, e elements (per field), z0, ky0};
+ * ddl_slab_rows fills cyl of every rank: rank r's block in an x-side array is rows
+ * [sum_{q<r} cyl_q, +cyl_r), i.e. cyl_r*nzl*CX elements, and this rank sends cyl*nzl*CX
+ * elements to every peer. */
+int ddl_slab_info(const ddl_plan* plan, int64_t* out16);
+int ddl_slab_rows(const ddl_plan* plan, int64_t* cyl_of_rank);
+/* inverse z pass of nf fields: local k slabs (retained modes only are read) -> k-side arrays */
+int ddl_slab_zinv(ddl_plan* plan, int nf, void* const* k_in, void* const* kside_out, void* stream);
+/* inverse y pass: x-side arrays -> b arrays */
+int ddl_slab_yinv(ddl_plan* plan, int nf, void* const* xside_in, void* const* b_out, void* stream);
+/* x pass with the real-space products of `physics` fused in (physics.py:197-228,309-354):
+ * b arrays of the state components -> c arrays of the product fields, normalised by 1/N_total */
+int ddl_slab_xfused(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* b_in,
+                    void* const* c_out, void* stream);
+/* plain x passes of the transform API: b -> x-space (unnormalised), x-space -> c (1/N_total) */
+int ddl_slab_xc2r(ddl_plan* plan, const void* b_in, double* x_out, void* stream);
+int ddl_slab_xr2c(ddl_plan* plan, const double* x_in, void* c_out, void* stream);
+/* forward y pass: c arrays -> x-side arrays;  forward z pass: k-side arrays -> e arrays, or
+ * (full_out) straight into local k slabs (retained modes only are written) */
+int ddl_slab_yfwd(ddl_plan* plan, int nf, void* const* c_in, void* const* xside_out, void* stream);
+int ddl_slab_zfwd(ddl_plan* plan, int nf, void* const* kside_in, void* const* out, int full_out, void* stream);
+/* spectral assembly: derivatives, curl, solenoidal projection (physics.py:180-195,374-416,588-599) */
+int ddl_slab_assemble(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* e_in,
+                      void* const* state, void* const* deriv, void* stream);
 
 /* forward_step_cy_{2d,3d}.pyx euler/etd1/etd2rk1/etd2rk2 for ncomp components at once.
  * The integrating factor is not an array: Z = -coeff[c] * (k^2)^visc_order * dt is formed
@@ -107,7 +155,8 @@ long long ddl_launch_count(void);
 int ddl_profile_enable(int on);
 int ddl_profile_report(char* json_out, size_t nbytes);
 
-/* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both) */
+/* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both);
+ * "xfused_variant" = 0/1/2 picks the CTA shape of the fused x pass (csrc/xfused_kernel.cuh) */
 int ddl_set_option(const char* name, int value);
 
 int ddl_sync(void* stream);
