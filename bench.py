@@ -87,7 +87,9 @@ class ClockSampler(object):
 
 def make_state(n, seed=5):
     """Synthetic random-phase MHD state on the device (SURVEY.md 8d recipe, torch generator):
-    per component white noise -> forward -> k^(-5/6) amplitude -> solenoidal projection -> rms 1."""
+    per component white noise -> forward -> k^(-5/6) amplitude -> solenoidal projection -> rms 1.
+    Under a process group every rank draws the same global noise field and keeps its z-slab, so
+    the state is the same global field for every rank count."""
     import numpy as np
     import torch
     from dedalus.mods import IncompressibleMHD, FourierRepresentation
@@ -97,23 +99,25 @@ def make_state(n, seed=5):
     data = P.create_fields(0.)
     g = torch.Generator(device="cuda").manual_seed(seed)
     c0 = data["u"][0]
+    z0, nzl = int(c0.offset["xspace"]), int(c0.local_shape["xspace"][0])
     kk = torch.sqrt(c0.k2())
     shape = torch.where(kk > 0, kk.clamp(min=1e-30) ** (-5.0 / 6.0), torch.zeros_like(kk))
     del kk
     import dedalus.analysis.volume_average as va
-    umax2 = 0.0
     for _, f in data:
         for _, c in f:
-            c["xspace"] = torch.randn(n, n, n, dtype=torch.float64, device="cuda", generator=g)
+            noise = torch.randn(n, n, n, dtype=torch.float64, device="cuda", generator=g)
+            c["xspace"] = noise[z0:z0 + nzl]
+            del noise
             c["kspace"].mul_(shape)
             c._xdata = None
         f.div_free()
-        en = sum(va.volume_average(c["kspace"].abs() ** 2, kdict=c.k) for _, c in f)
+        en = sum(va.volume_average(c["kspace"].abs() ** 2, kdict=c.k, reduce_all=True) for _, c in f)
         for _, c in f:
             c["kspace"].mul_(1.0 / np.sqrt(en))
     del shape
+    umax2 = float(data["u"].max_square())
     for _, c in data["u"]:
-        umax2 = max(umax2, float((c["xspace"] ** 2).max()))
         c["kspace"]
         c._xdata = None
     torch.cuda.empty_cache()
@@ -135,44 +139,52 @@ def run_ours(args):
     from dedalus.mods import RK4
     import dedalus.analysis.volume_average as va
     n = args.n
-    if world > 1:
-        # TODO(multi-GPU): slab-decomposed transforms.  Until then refuse rather than report
-        # replicas as a strong-scaling number.
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world,
-                              "unavailable": "slab-decomposed multi-GPU path not implemented yet (round 1)"}))
-        dist.destroy_process_group()
-        return
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     P, data, dt = make_state(n)
     ti = RK4(P)
     nk = n * n * (n // 2 + 1)
     for _ in range(args.warmup):
         ti.do_advance(data, dt)
-    torch.cuda.synchronize()
+    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     if args.quick:
         torch.cuda.profiler.start()          # ncu --profile-from-start off captures only this region
     e0.record()
     for _ in range(args.steps):
         ti.do_advance(data, dt)
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     if args.quick:
         torch.cuda.profiler.stop()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = L.launch_count() - l0
     clocks = sampler.stop()
     value = args.steps * 4 * nk / (ms * 1e-3)
-    ekin, emag = va.ekin(data), va.emag(data)
+    ekin, emag = va.ekin(data, reduce_all=True), va.emag(data, reduce_all=True)
     assert np.isfinite(ekin) and np.isfinite(emag)
 
     if args.quick:
-        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "quick": True,
-                          "gpu_launches": launches}))
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "quick": True,
+                              "gpu_launches": launches, "n_gpus": world}))
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---- instrumented pass: per-kernel CUDA-event durations (not part of `value`)
     L.profile(True)
@@ -182,23 +194,32 @@ def run_ours(args):
     L.profile(False)
     peak, peak_src = measured_peak()
     tot_ms = sum(v["ms"] for v in prof.values())
+    # per launch each rank covers 1/world of the modes
     kern = {k: {"launches": v["n"], "ms_per_launch": v["ms"] / v["n"], "share": v["ms"] / tot_ms,
-                "algo_gbs": ALGO_BYTES_PER_MODE.get(k, 0.0) * nk / (v["ms"] / v["n"] * 1e-3) / 1e9}
+                "algo_gbs": ALGO_BYTES_PER_MODE.get(k, 0.0) * nk / world / (v["ms"] / v["n"] * 1e-3) / 1e9 / PER_LAUNCH_FIELDS(k, world)}
             for k, v in prof.items()}
     dom = max(prof, key=lambda k: prof[k]["ms"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["algo_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["algo_gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_MODE.get(dom, 0.0) * nk,
-                "step": {"achieved": A_STAGE_MHD3D * value / 1e9, "frac": A_STAGE_MHD3D * value / 1e9 / peak,
-                         "frac_of_8TBs": A_STAGE_MHD3D * value / 8e12, "bytes_per_mode_stage": A_STAGE_MHD3D},
+                "frac": kern[dom]["algo_gbs"] / peak, "traffic": TRAFFIC.get(dom) if world == 1 and n == 512 else None,
+                "traffic_source": TRAFFIC_SOURCE if world == 1 and n == 512 else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_MODE.get(dom, 0.0) * nk / world / PER_LAUNCH_FIELDS(dom, world),
+                "step": {"achieved": A_STAGE_MHD3D * value / 1e9 / world, "frac": A_STAGE_MHD3D * value / 1e9 / peak / world,
+                         "frac_of_8TBs": A_STAGE_MHD3D * value / 8e12 / world, "bytes_per_mode_stage": A_STAGE_MHD3D,
+                         "note": "per GPU"},
                 "kernels": kern}
+    if world > 1:
+        pipe = next(data.components())[2]._plan.pipeline
+        per_rhs = 15 * sum(pipe.to_peer[r] for r in range(world) if r != pipe.rank) * 16
+        roofline["nvlink"] = {"bytes_out_per_gpu_per_step": 4 * per_rhs, "transposes_per_step": 60,
+                              "peak_gbs_per_direction": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
+                              "floor_ms_per_step": 4 * per_rhs / 770e9 * 1e3}
 
     # ---- end to end with host buffers
     comps = [c for _, _, c in data.components()]
-    host = [torch.empty(c.kdata.shape, dtype=c.kdata.dtype, pin_memory=True) for c in comps]
+    host = [torch.empty(c._k.shape, dtype=c._k.dtype, pin_memory=True) for c in comps]
     for h, c in zip(host, comps):
-        h.copy_(c.kdata)
-    torch.cuda.synchronize()
+        h.copy_(c._k)
+    barrier()
     nbytes = sum(h.numel() * h.element_size() for h in host)
     ksteps = max(1, min(args.steps, 3))
     e0.record()
@@ -209,20 +230,39 @@ def run_ours(args):
         for h, c in zip(host, comps):
             h.copy_(c["kspace"], non_blocking=True)  # D2H of the step result
     e1.record()
-    torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1)
-    e2e = {"value": ksteps * 4 * nk / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
-           "d2h_bytes_per_step": nbytes, "steps": ksteps, "ms_per_step": ms_e2e / ksteps}
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": ksteps * 4 * nk / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
+           "d2h_bytes_per_step": nbytes * world, "steps": ksteps, "ms_per_step": ms_e2e / ksteps}
 
-    cpu = cpu_baseline(args)
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    cpu = cpu_baseline(args) if (world == 1 and rank == 0) else None
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": "3D incompressible MHD %d^3 RK4, 2/3 dealiasing, nu=eta=1e-3" % n, "n_components": 6,
-                      "N_k": nk, "stages_per_step": 4, "dt": dt, "cache": "inputs larger than L2 (state 6.5 GB)"},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-           "invariants": {"ekin": ekin, "emag": emag}}
-    print(json.dumps(out))
+                      "N_k": nk, "stages_per_step": 4, "dt": dt,
+                      "parallelism": "slab%d (x-space z-slabs, k-space ky-slabs, all-to-all per transform)" % world if world > 1 else "single GPU",
+                      "cache": "inputs larger than L2 (state %.1f GB per GPU)" % (6 * nk * 16 / world / 1e9)},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "invariants": {"ekin": ekin, "emag": emag}}
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# kernels launched once per FIELD under the slab pipeline (one launch covers all fields on one GPU)
+def PER_LAUNCH_FIELDS(kernel, world):
+    if world == 1:
+        return 1
+    return {"z_inv": 6, "y_inv": 6, "y_fwd": 9, "z_fwd": 9}.get(kernel, 1)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/), 512^3 single GPU; None where no capture exists for the current kernel version
+TRAFFIC = {}
+TRAFFIC_SOURCE = None
 
 
 def cpu_baseline(args):

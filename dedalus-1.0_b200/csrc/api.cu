@@ -174,6 +174,7 @@ struct ddl_plan {
     int nzl = 1, z0 = 0;
     YSlab yl;
     std::vector<int> cyl_of;        // retained ky rows per rank
+    unsigned char* y_owner = nullptr;   // [cy] owning rank of every compact ky row
     long long ntot = 1;
     KGeom geom;          // local k-array geometry
     long long nmodes = 0;
@@ -243,15 +244,19 @@ extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* sha
     L.nyl = Y.nk / nranks; L.ky0 = rank * L.nyl;
     pl->cyl_of.assign(nranks, 0);
     std::vector<int> lc2f;
+    std::vector<unsigned char> owner(Y.cnt);
     L.cy0 = -1;
     for (int j = 0; j < Y.cnt; ++j) {
         const int f = Y.h_c2f[j], r = f / L.nyl;
+        owner[j] = (unsigned char)r;
         pl->cyl_of[r]++;
         if (r == rank) { if (L.cy0 < 0) L.cy0 = j; lc2f.push_back(f - L.ky0); }
     }
     L.cyl = (int)lc2f.size();
     if (L.cy0 < 0) L.cy0 = 0;
     L.kv = Y.kv + L.ky0; L.keep = Y.keep + L.ky0; L.kvc = Y.kvc + L.cy0;
+    pl->y_owner = upload_vec(owner);
+    if (pl->y_owner) pl->owned.push_back(pl->y_owner);
     if (nranks == 1) L.c2f = Y.c2f;
     else {
         L.c2f = upload_vec(lc2f);
@@ -371,9 +376,13 @@ static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 76
 struct RowSpec { int m; int compact; };   // retained rows of a pruned axis (m < 0: all rows present)
 static const RowSpec ALL_ROWS = {-1, 0};
 
+// peer mode (slab exchange fused into the pass): the output blocks are given by a device table
+// of nf x nblk pointers into the peers' arenas
+struct PeerOut { void* const* tab; const unsigned char* own; int nblk; int mask_all; };
+
 static int pass_c2c(const char* name, int N, int dir, int nf, const void* const* in, void* const* out, const TileSide& si,
                     const TileSide& so, RowSpec ri, RowSpec ro, int inner_len, int n_outer, double scale, const cplx* tw,
-                    ddl_stream_t st) {
+                    ddl_stream_t st, const PeerOut* peer = nullptr) {
     if (n_outer <= 0 || nf <= 0 || inner_len <= 0) return 0;     // a rank may own no retained ky row
 #if DDL_DEVICE_BUILD
     const bool pow2 = !(si.split & (si.split - 1)) && !(so.split & (so.split - 1));
@@ -387,12 +396,18 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
             if (s.split) { int sh = 0; while ((1 << sh) < s.split) ++sh; d.split_shift = sh; d.split_mask = s.split - 1; d.s_blk = s.s_blk; }
         };
         conv(f.si, si, ri); conv(f.so, so, ro);
+        if (peer) {
+            f.so.peer_tab = (cplx* const*)peer->tab; f.so.own_tab = peer->own; f.so.nblk = peer->nblk;
+            if (peer->mask_all) f.so.split_mask = 0x7fffffff;
+        }
         f.inner_len = inner_len; f.scale = scale; f.tw = tw;
         int rc = run_fast_strided(N, dir, f, nf, n_outer, name, st);
         if (rc <= 0) return rc;
     }
+    if (peer) { set_error("peer-store passes need the specialised strided kernel (axis length %d)", N); return -1; }
 #else
     (void)ri; (void)ro;
+    if (peer) { set_error("peer-store passes need the CUDA build"); return -1; }
 #endif
     TileParams p;
     memset(&p, 0, sizeof(p));
@@ -468,6 +483,27 @@ static int phase_zinv(ddl_plan* pl, int nf, const void* const* kin, void* const*
     const long long KP = X.nk;
     return pass_c2c("z_inv", Z.n, +1, nf, kin, S, side(KP, 1, (long long)Z.n * KP, Z.f2f, pl->yl.c2f), kside(pl),
                     RowSpec{Z.m, 0}, ALL_ROWS, X.cnt, pl->yl.cyl, 1.0, Z.tw, st);
+}
+// z pass, inverse, with the exchange fused in: row z of local compact ky row j goes straight to
+//   tab[f][z / nzl] + j*(nzl*CX) + (z % nzl)*CX     (tab[f][s] = rank s's x-side field f + cy0_me*nzl*CX)
+static int phase_zinv_peer(ddl_plan* pl, int nf, const void* const* kin, void* const* tab, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Z = pl->az;
+    const long long KP = X.nk, CX = kx_pitch(pl);
+    PeerOut po = {tab, nullptr, pl->nranks, 0};
+    std::vector<void*> dummy(nf, nullptr);
+    TileSide so = side(CX, 1, (long long)pl->nzl * CX, nullptr, nullptr, pl->nzl, 0);
+    return pass_c2c("z_inv", Z.n, +1, nf, kin, dummy.data(), side(KP, 1, (long long)Z.n * KP, Z.f2f, pl->yl.c2f), so,
+                    RowSpec{Z.m, 0}, ALL_ROWS, X.cnt, pl->yl.cyl, 1.0, Z.tw, st, &po);
+}
+// y pass, forward, with the exchange fused in: compact ky row j of local plane zl goes to
+//   tab[f][owner(j)] + j*(nzl*CX) + zl*CX     (tab[f][s] = rank s's k-side field f + (me*cyl_s - cy0_s)*nzl*CX)
+static int phase_yfwd_peer(ddl_plan* pl, int nf, const void* const* Cin, void* const* tab, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long CX = kx_pitch(pl), nzl = pl->nzl;
+    PeerOut po = {tab, pl->y_owner, pl->nranks, 1};
+    std::vector<void*> dummy(nf, nullptr);
+    return pass_c2c("y_fwd", Y.n, -1, nf, Cin, dummy.data(), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
+                    side(nzl * CX, 1, CX, Y.f2c, nullptr), ALL_ROWS, RowSpec{Y.m, 1}, X.cnt, (int)nzl, 1.0, Y.tw, st, &po);
 }
 // y pass, inverse: x-side pencils A[cy][nzl][CX] -> B[nzl][y][CX]
 static int phase_yinv(ddl_plan* pl, int nf, const void* const* A, void* const* B, ddl_stream_t st) {
@@ -753,6 +789,14 @@ static int need_3d(const ddl_plan* pl) {
 extern "C" int ddl_slab_zinv(ddl_plan* pl, int nf, void* const* k_in, void* const* ks_out, void* stream) {
     DDL_TRY(need_3d(pl));
     return phase_zinv(pl, nf, (const void* const*)k_in, ks_out, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_zinv_peer(ddl_plan* pl, int nf, void* const* k_in, void* const* peer_tab, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_zinv_peer(pl, nf, (const void* const*)k_in, peer_tab, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_yfwd_peer(ddl_plan* pl, int nf, void* const* c_in, void* const* peer_tab, void* stream) {
+    DDL_TRY(need_3d(pl));
+    return phase_yfwd_peer(pl, nf, (const void* const*)c_in, peer_tab, (ddl_stream_t)stream);
 }
 extern "C" int ddl_slab_yinv(ddl_plan* pl, int nf, void* const* xs_in, void* const* b_out, void* stream) {
     DDL_TRY(need_3d(pl));

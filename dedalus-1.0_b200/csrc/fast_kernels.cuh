@@ -25,6 +25,12 @@ struct FastSide {
     // (split_shift = 31, split_mask = 0x7fffffff: plain rows)
     int split_shift, split_mask;
     long long s_blk;
+    // output side only, slab exchange fused into the pass: block b of field f starts at
+    // peer_tab[f * nblk + b] (a pointer into rank b's arena, mapped through CUDA IPC) instead of
+    // out[f] + b * s_blk; the block of a row is own_tab[row] if given, else row >> split_shift
+    cplx* const* peer_tab;
+    const unsigned char* own_tab;
+    int nblk;
 };
 
 __device__ __forceinline__ long long fast_row_off(const FastSide& s, int r) {
@@ -150,7 +156,15 @@ strided_fast(const __grid_constant__ FastParams p) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int row = fast_row<N>(k0 + r * (N / R), p.so.m, p.so.compact);
-                if (live && row >= 0) out[ob + fast_row_off(p.so, row)] = scal(v[r], sc);
+                if (live && row >= 0) {
+                    if (p.so.peer_tab) {
+                        const int blk = p.so.own_tab ? p.so.own_tab[row] : (row >> p.so.split_shift);
+                        cplx* __restrict__ dst = p.so.peer_tab[blockIdx.z * p.so.nblk + blk];
+                        dst[ob + (long long)(row & p.so.split_mask) * p.so.s_n] = scal(v[r], sc);
+                    } else {
+                        out[ob + fast_row_off(p.so, row)] = scal(v[r], sc);
+                    }
+                }
             }
         }
     }

@@ -14,7 +14,9 @@ EXPORTS = [
     "ddl_plan_create", "ddl_plan_create_slab", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
     "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_deriv", "ddl_rhs", "ddl_stage",
     "ddl_rk4_stage", "ddl_cn_step", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_zinv", "ddl_slab_yinv",
-    "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
+    "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
+    "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
@@ -46,6 +48,21 @@ def bind_slab(lib):
     lib.ddl_slab_zfwd.argtypes = [vp, i32, vp, vp, i32, vp]
     lib.ddl_slab_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.ddl_dealias.argtypes = [vp, vp, vp]
+    if hasattr(lib, "ddl_p2p_create"):
+        lib.ddl_p2p_create.argtypes = [C.POINTER(vp), i32, i32, C.c_size_t, C.c_char_p]
+        lib.ddl_p2p_connect.argtypes = [vp, C.c_char_p]
+        lib.ddl_p2p_base.argtypes = [vp]
+        lib.ddl_p2p_base.restype = vp
+        lib.ddl_p2p_exchange.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        lib.ddl_p2p_exchange.restype = C.c_longlong
+        lib.ddl_p2p_wait.argtypes = [vp, C.c_longlong, vp]
+        lib.ddl_p2p_destroy.argtypes = [vp]
+        lib.ddl_p2p_peer_base.argtypes = [vp, i32]
+        lib.ddl_p2p_peer_base.restype = vp
+        lib.ddl_p2p_signal.argtypes = [vp, vp]
+        lib.ddl_p2p_signal.restype = C.c_longlong
+        lib.ddl_slab_zinv_peer.argtypes = [vp, i32, vp, vp, vp]
+        lib.ddl_slab_yfwd_peer.argtypes = [vp, i32, vp, vp, vp]
 
 
 def _load():

@@ -73,22 +73,22 @@ class VolumeAverageSet(object):
 task = VolumeAverageSet.register_task
 
 
-def _energy(field, space):
+def _energy(field, space, reduce_all=False):
     if space == "kspace":
         acc = sum(0.5 * c["kspace"].abs() ** 2 for _, c in field)
-        return volume_average(acc, kdict=field[0].k if field.ncomp > 1 else field.components[0].k)
+        return volume_average(acc, kdict=field[0].k if field.ncomp > 1 else field.components[0].k, reduce_all=reduce_all)
     acc = sum(0.5 * c["xspace"] ** 2 for _, c in field)
     return volume_average(acc, space="xspace")
 
 
 @task
-def ekin(data, scratch=None, space="kspace"):
-    return _energy(data["u"], space)
+def ekin(data, scratch=None, space="kspace", reduce_all=False):
+    return _energy(data["u"], space, reduce_all)
 
 
 @task
-def emag(data, scratch=None, space="kspace"):
-    return _energy(data["B"], space)
+def emag(data, scratch=None, space="kspace", reduce_all=False):
+    return _energy(data["B"], space, reduce_all)
 
 
 def _mean_square(comp):

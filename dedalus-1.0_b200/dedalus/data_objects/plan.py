@@ -9,7 +9,7 @@ import numpy.fft as npfft
 import torch
 
 from .._lib import lib, check
-from ..utils.parallelism import swap_indices
+from ..utils.parallelism import swap_indices, com_sys
 
 _PLANS = {}
 
@@ -73,11 +73,17 @@ def keep_masks(dealiasing, ktrans, kny, k):
 
 
 class Plan(object):
-    def __init__(self, shape, length, dealiasing):
+    """nranks > 1: this rank's part of a slab decomposition (3-D only).  x-space is split along
+    z, k-space along ky, as FFTW-MPI does for the reference (_fftw.pyx:114-148,
+    representations.py:180-186,231-233); `k['y']`, `kshape_local`, `xshape_local` and the
+    offsets describe the local slab, the `*_np` arrays stay global."""
+
+    def __init__(self, shape, length, dealiasing, nranks=1, rank=0):
         self.shape = tuple(int(s) for s in shape)
         self.ndim = len(self.shape)
         self.length = tuple(float(x) for x in length)
         self.dealiasing = dealiasing
+        self.nranks, self.rank = int(nranks), int(rank)
         self.kshape, self.ktrans, self.dk, self.kny, self.k_np = wavenumbers(self.shape, self.length)
         self.keep_np = keep_masks(dealiasing, self.ktrans, self.kny, self.k_np)
         self.device = device()
@@ -85,18 +91,42 @@ class Plan(object):
         keep8 = {n: np.ascontiguousarray(v.astype(np.uint8)) for n, v in self.keep_np.items()}
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
         self.handle = C.c_void_p()
-        check(lib.ddl_plan_create(C.byref(self.handle), self.ndim, vp(shp), vp(self.k_np["x"]), vp(self.k_np["y"]),
-                                  vp(self.k_np["z"]) if self.ndim == 3 else None, vp(keep8["x"]), vp(keep8["y"]),
-                                  vp(keep8["z"]) if self.ndim == 3 else None))
-        # broadcast-shaped device copies for the Python-level API (comp.k['x'] etc.)
+        if self.nranks > 1 and self.ndim != 3:
+            raise NotImplementedError("Slab decomposition is 3-D only: 2-D grids fit one GPU and run as replicas.")
+        check(lib.ddl_plan_create_slab(C.byref(self.handle), self.ndim, vp(shp), vp(self.k_np["x"]), vp(self.k_np["y"]),
+                                       vp(self.k_np["z"]) if self.ndim == 3 else None, vp(keep8["x"]), vp(keep8["y"]),
+                                       vp(keep8["z"]) if self.ndim == 3 else None, self.nranks, self.rank))
+        self.kshape_local = self.kshape.copy()
+        self.xshape_local = np.array(self.shape)
+        self.koffset = self.xoffset = 0
+        if self.nranks > 1:
+            self.kshape_local[0] = self.kshape[0] // self.nranks
+            self.xshape_local[0] = self.shape[0] // self.nranks
+            self.koffset = self.rank * int(self.kshape_local[0])
+            self.xoffset = self.rank * int(self.xshape_local[0])
+        # broadcast-shaped device copies for the Python-level API (comp.k['x'] etc.); axis 0 of
+        # k-space is restricted to the local slab (representations.py:232-233)
         self.k = {}
         for name, kv in self.k_np.items():
             i = self.ktrans[name]
+            if i == 0 and self.nranks > 1:
+                kv = kv[self.koffset:self.koffset + int(self.kshape_local[0])]
             shp_b = [1] * self.ndim
             shp_b[i] = len(kv)
-            self.k[name] = torch.from_numpy(kv).to(self.device).reshape(shp_b)
+            self.k[name] = torch.from_numpy(np.ascontiguousarray(kv)).to(self.device).reshape(shp_b)
         self._work = None
+        self._pipe = None
         self.nmodes = int(np.prod(self.kshape))
+
+    @property
+    def pipeline(self):
+        """The slab pipeline of this rank (dedalus/data_objects/slab.py); 3-D plans only."""
+        if self._pipe is None:
+            from .slab import SlabPipeline
+            import os
+            kind = os.environ.get("DEDALUS_SLAB_EXCHANGE", "peer")
+            self._pipe = SlabPipeline(lib, self.handle, self.device, stream=current_stream, exchange=kind)
+        return self._pipe
 
     def workspace(self, nbytes):
         if self._work is None or self._work.numel() < nbytes:
@@ -119,9 +149,12 @@ class Plan(object):
 
 
 def get_plan(shape, length, dealiasing):
+    """One plan per (grid, dealiasing, device, process-group size): with a torch.distributed
+    process group of P > 1 ranks a 3-D grid is slab-decomposed over it."""
+    nranks, rank = com_sys.nproc, com_sys.myproc
     key = (tuple(int(s) for s in shape), tuple(float(x) for x in length), str(dealiasing),
-           torch.cuda.current_device() if torch.cuda.is_available() else -1)
+           torch.cuda.current_device() if torch.cuda.is_available() else -1, nranks, rank)
     pl = _PLANS.get(key)
     if pl is None:
-        pl = _PLANS[key] = Plan(shape, length, dealiasing)
+        pl = _PLANS[key] = Plan(shape, length, dealiasing, nranks, rank)
     return pl

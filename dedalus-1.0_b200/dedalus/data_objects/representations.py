@@ -49,8 +49,6 @@ class FourierRepresentation(Representation):
         dealiasing = decfg.get("FFT", "dealiasing")
         if method not in ("cuda", "fftw", "numpy"):
             raise NotImplementedError("Specified FFT method not implemented.")
-        if com_sys.nproc > 1:
-            raise NotImplementedError("Slab-decomposed runs go through dedalus.parallel (one plan per rank).")
 
         if self.ndim == 2:
             self.xtrans = {"x": 1, 1: "x", "y": 0, 0: "y"}
@@ -61,12 +59,12 @@ class FourierRepresentation(Representation):
         pl = self._plan
         self.ktrans = pl.ktrans
         self.global_shape["kspace"] = pl.kshape.copy()
-        self.local_shape = {"kspace": pl.kshape.copy(), "xspace": self.global_shape["xspace"].copy()}
-        self.offset = {"xspace": 0, "kspace": 0}
+        self.local_shape = {"kspace": pl.kshape_local.copy(), "xspace": pl.xshape_local.copy()}
+        self.offset = {"xspace": pl.xoffset, "kspace": pl.koffset}
         self.dk, self.kny, self.k = pl.dk, pl.kny, pl.k
         self.set_dealiasing(dealiasing)
 
-        self._k = torch.zeros(tuple(int(n) for n in pl.kshape), dtype=torch.complex128, device=pl.device)
+        self._k = torch.zeros(tuple(int(n) for n in pl.kshape_local), dtype=torch.complex128, device=pl.device)
         self._xdata = None          # allocated on first use: most components never leave k-space
         # True while the spectrum is KNOWN to vanish outside the dealias mask (set by our own
         # kernels, cleared whenever the buffer is handed to the caller, who may write to it);
@@ -81,7 +79,7 @@ class FourierRepresentation(Representation):
     @property
     def xdata(self):
         if self._xdata is None:
-            self._xdata = torch.zeros(tuple(int(n) for n in self.global_shape["xspace"]), dtype=torch.float64,
+            self._xdata = torch.zeros(tuple(int(n) for n in self.local_shape["xspace"]), dtype=torch.float64,
                                       device=self._plan.device)
         return self._xdata
 
@@ -138,9 +136,12 @@ class FourierRepresentation(Representation):
         if self._curr_space == "kspace":
             raise ValueError("Forward transform cannot be called from kspace.")
         pl = self._plan
-        w = pl.transform_workspace()
-        check(lib.ddl_forward(pl.handle, self.xdata.data_ptr(), self._k.data_ptr(), w.data_ptr(), w.numel(),
-                              _plan.current_stream()))
+        if pl.nranks > 1:
+            pl.pipeline.forward(self.xdata, self._k)
+        else:
+            w = pl.transform_workspace()
+            check(lib.ddl_forward(pl.handle, self.xdata.data_ptr(), self._k.data_ptr(), w.data_ptr(), w.numel(),
+                                  _plan.current_stream()))
         self._curr_space = "kspace"
         self._clean = True
         self.fwd_count += 1
@@ -151,9 +152,12 @@ class FourierRepresentation(Representation):
         if self._curr_space == "xspace":
             raise ValueError("Backward transform cannot be called from xspace.")
         pl = self._plan
-        w = pl.transform_workspace()
-        check(lib.ddl_backward(pl.handle, self._k.data_ptr(), self.xdata.data_ptr(), w.data_ptr(), w.numel(),
-                               _plan.current_stream()))
+        if pl.nranks > 1:
+            pl.pipeline.backward(self._k, self.xdata)
+        else:
+            w = pl.transform_workspace()
+            check(lib.ddl_backward(pl.handle, self._k.data_ptr(), self.xdata.data_ptr(), w.data_ptr(), w.numel(),
+                                   _plan.current_stream()))
         self._curr_space = "xspace"
         self._clean = True
         self.rev_count += 1
@@ -210,11 +214,14 @@ class FourierRepresentation(Representation):
         return k2
 
     def find_mode(self, mode, exact=False):
-        """Index of the mode closest to the physical wavevector `mode`, given in k-space axis
-        order ((ky,kz,kx) / (kx,ky)); None if absent (representations.py:247-288)."""
+        """LOCAL index of the mode closest to the physical wavevector `mode`, given in k-space
+        axis order ((ky,kz,kx) / (kx,ky)); None if absent or owned by another rank
+        (representations.py:247-288)."""
         idx = []
         for i in range(self.ndim):
             kv = self._plan.k_np[self.ktrans[i]]
+            if i == 0:
+                kv = kv[self.offset["kspace"]:self.offset["kspace"] + int(self.local_shape["kspace"][0])]
             if exact:
                 hit = np.nonzero(kv == mode[i])[0]
             else:
@@ -229,7 +236,8 @@ class FourierRepresentation(Representation):
 
     def enforce_hermitian(self):
         """Zero the Nyquist planes and overwrite the redundant half of the kx = 0 plane with
-        the conjugate of its Hermitian partner (representations.py:457-503)."""
+        the conjugate of its Hermitian partner (representations.py:457-503; with several ranks
+        the plane is gathered, fixed and scattered back as the reference does, :480,:500)."""
         self.require_space("kspace")
         self.zero_nyquist()
         d = self.kdata
@@ -237,12 +245,23 @@ class FourierRepresentation(Representation):
             ny = d.shape[1] // 2
             d[0, 0] = d[0, 0].real
             d[0, -ny:] = d[0, 1:ny + 1].flip(0).conj()
+            return
+        nranks = self._plan.nranks
+        if nranks > 1:
+            import torch.distributed as dist
+            mine = torch.view_as_real(d[:, :, 0].contiguous())
+            parts = [torch.empty_like(mine) for _ in range(nranks)]
+            dist.all_gather(parts, mine)
+            plane = torch.view_as_complex(torch.cat(parts, 0))
         else:
             plane = d[:, :, 0]
-            nyy, nyz = plane.shape[0] // 2, plane.shape[1] // 2
-            plane[0, -nyz:] = plane[0, 1:nyz + 1].flip(0).conj()
-            plane[-nyy:, 0] = plane[1:nyy + 1, 0].flip(0).conj()
-            plane[-nyy:, 1:] = plane[1:nyy + 1, 1:].flip(0, 1).conj()
+        nyy, nyz = plane.shape[0] // 2, plane.shape[1] // 2
+        plane[0, -nyz:] = plane[0, 1:nyz + 1].flip(0).conj()
+        plane[-nyy:, 0] = plane[1:nyy + 1, 0].flip(0).conj()
+        plane[-nyy:, 1:] = plane[1:nyy + 1, 1:].flip(0, 1).conj()
+        if nranks > 1:
+            k0 = self.offset["kspace"]
+            d[:, :, 0] = plane[k0:k0 + d.shape[0]]
 
     def zero_under_eps(self):
         self.require_space("kspace")

@@ -30,9 +30,36 @@ class _Done(object):
         return True
 
 
+class _Raw(object):
+    """A device address inside the IPC arena, quacking like a tensor for the C calls."""
+
+    def __init__(self, ptr):
+        self.ptr = int(ptr)
+
+    def data_ptr(self):
+        return self.ptr
+
+
+class _Ticket(object):
+    def __init__(self, pipe, seq):
+        self.pipe, self.seq = pipe, seq
+
+    def wait(self):
+        p = self.pipe
+        p._check(p.lib.ddl_p2p_wait(p._p2p, self.seq, p._stream()))
+        return True
+
+
 class SlabPipeline(object):
-    def __init__(self, lib, handle, device, group=None, stream=None):
+    def __init__(self, lib, handle, device, group=None, stream=None, exchange="collective"):
+        """exchange of the RHS pipeline (the plain transforms always use the collective):
+        "collective" = torch.distributed all_to_all_single (NCCL / gloo);
+        "p2p"  = CUDA-IPC arenas + copy-engine pushes + arrival flags (csrc/p2p.cu);
+        "peer" = the producing z / y pass stores straight into the peers' arenas over NVLink
+                 (no send buffer, no copy) + arrival flags; the default on the GPU box."""
         self.lib, self.h, self.device, self.group = lib, handle, device, group
+        self.exchange_kind = exchange
+        self._p2p = None
         self._stream = stream or (lambda: None)
         info = (C.c_int64 * 16)()
         self._check(lib.ddl_slab_info(handle, info))
@@ -47,10 +74,18 @@ class SlabPipeline(object):
         self.from_peer = [r * blk for r in self.rows]
         self._bufs = {}
         self.exchanges = 0
+        self.trace = None               # profiling only: list collecting (label, torch.cuda.Event) marks of rhs()
+        self.skip_exchange = False      # profiling only (profiles/slab_breakdown.py): time the passes without the all-to-all
 
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError(self.lib.ddl_last_error().decode())
+
+    def _mark(self, label):
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((label, ev))
 
     # ------------------------------------------------------------------ buffers
     def buffers(self, ni, no):
@@ -66,13 +101,145 @@ class SlabPipeline(object):
             cut = lambda t, n, k: [t[i * n:(i + 1) * n] for i in range(k)]
             b = {"ks": cut(ks, self.n_ks, nmax), "xs": cut(xs, self.n_xs, nmax), "b": cut(be, self.n_b, ni),
                  "e": cut(be, self.n_e, no), "c": cut(c, self.n_b, no)}
-            self._bufs = {key: b}          # keep one set alive (the largest use in practice)
+            self._bufs[key] = b
+        return b
+
+    # ------------------------------------------------------------------ p2p arena (RHS pipeline)
+    def _p2p_setup(self, nmax):
+        """Arena layout, identical on every rank up to the peer's own k-side size:
+        [nmax x-side fields | nmax k-side fields | flags]."""
+        lib, P, me = self.lib, self.P, self.rank
+        el = 16
+        blk = self.nzl * self.cx
+        nz_total = self.nzl * P
+        n_ks_of = [r * nz_total * self.cx for r in self.rows]
+        xs_total = nmax * self.n_xs * el
+        data_bytes = xs_total + nmax * self.n_ks * el
+        ctx = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(lib.ddl_p2p_create(C.byref(ctx), P, me, data_bytes, handle))
+        gathered = [None] * P
+        dist.all_gather_object(gathered, handle.raw, group=self.group)
+        self._check(lib.ddl_p2p_connect(ctx, b"".join(gathered)))
+        self._p2p = ctx
+        self._p2p_nmax = nmax
+        base = int(lib.ddl_p2p_base(ctx))
+        self._p2p_xs = [_Raw(base + f * self.n_xs * el) for f in range(nmax)]
+        self._p2p_ks = [_Raw(base + xs_total + f * self.n_ks * el) for f in range(nmax)]
+        cy0_of = [sum(self.rows[:r]) for r in range(P)]
+        order = [(me + i) % P for i in range(P)]
+        arr = lambda vals, t: (t * len(vals))(*vals)
+        self._p2p_lists = {}
+        for f in range(nmax):
+            # inverse: my k-side block s -> rows [cy0(me), +cyl) of rank s's x-side field f
+            src = [xs_total + (f * self.n_ks + s * self.cyl * blk) * el for s in order]
+            dst = [(f * self.n_xs + self.cy0 * blk) * el for s in order]
+            nb = [self.cyl * blk * el for s in order]
+            self._p2p_lists[(f, True)] = (arr(order, C.c_int), arr(src, C.c_int64), arr(dst, C.c_int64), arr(nb, C.c_int64))
+            # forward: rows of rank s in my x-side field f -> block `me` of rank s's k-side field f
+            src = [(f * self.n_xs + cy0_of[s] * blk) * el for s in order]
+            dst = [xs_total + (f * n_ks_of[s] + me * self.rows[s] * blk) * el for s in order]
+            nb = [self.rows[s] * blk * el for s in order]
+            self._p2p_lists[(f, False)] = (arr(order, C.c_int), arr(src, C.c_int64), arr(dst, C.c_int64), arr(nb, C.c_int64))
+        # tables of the peer-store passes (exchange fused into the z / y pass): [f][s] block bases
+        pb = [int(lib.ddl_p2p_peer_base(ctx, s)) for s in range(P)]
+        zt = [[pb[s] + (f * self.n_xs + self.cy0 * blk) * el for s in range(P)] for f in range(nmax)]
+        yt = [[pb[s] + xs_total + (f * n_ks_of[s] + (me * self.rows[s] - cy0_of[s]) * blk) * el for s in range(P)]
+              for f in range(nmax)]
+        self._zinv_tab = torch.tensor(zt, dtype=torch.int64, device=self.device)
+        self._yfwd_tab = torch.tensor(yt, dtype=torch.int64, device=self.device)
+        self._side = torch.cuda.Stream(device=self.device)
+        dist.barrier(group=self.group)
+
+    def _signal(self):
+        self.exchanges += 1
+        seq = self.lib.ddl_p2p_signal(self._p2p, self._stream())
+        if seq <= 0:
+            self._check(int(seq) or -1)
+        return _Ticket(self, seq)
+
+    def _rhs_peer(self, physics_id, pp, state, deriv, ni, no):
+        """RHS with the exchange fused into the producing passes: the inverse z pass and the
+        forward y pass store their output rows straight into the owning rank's arena over
+        NVLink; a second stream runs the consuming passes of field f while the producing pass
+        of field f+1 (NVLink-bound) is in flight."""
+        lib, h = self.lib, self.h
+        b = self._p2p_buffers(ni, no)
+        ks, xs = b["ks"], b["xs"]
+        main = torch.cuda.current_stream()
+        side = self._side
+        el = 8 * self.P          # bytes per table row
+        zt, yt = self._zinv_tab.data_ptr(), self._yfwd_tab.data_ptr()
+        self._mark("start")
+        side.wait_stream(main)
+        done = []
+        for f in range(ni):
+            self._check(lib.ddl_slab_zinv_peer(h, 1, _ptrs([state[f]]), zt + f * el, main.cuda_stream))
+            t = self._signal()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            done.append((t, ev))
+        self._mark("z_inv")
+        with torch.cuda.stream(side):
+            for f in range(ni):
+                t, ev = done[f]
+                side.wait_event(ev)             # my own block is written by my own pass
+                t.wait()                        # the peers' blocks: arrival flags
+                self._check(lib.ddl_slab_yinv(h, 1, _ptrs([xs[f]]), _ptrs([b["b"][f]]), side.cuda_stream))
+        main.wait_stream(side)
+        self._mark("wait+y_inv")
+        self._check(lib.ddl_slab_xfused(h, physics_id, pp, _ptrs(b["b"][:ni]), _ptrs(b["c"][:no]), main.cuda_stream))
+        self._mark("x_fused")
+        done = []
+        for f in range(no):
+            self._check(lib.ddl_slab_yfwd_peer(h, 1, _ptrs([b["c"][f]]), yt + f * el, main.cuda_stream))
+            t = self._signal()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            done.append((t, ev))
+        self._mark("y_fwd")
+        with torch.cuda.stream(side):
+            for f in range(no):
+                t, ev = done[f]
+                side.wait_event(ev)
+                t.wait()
+                self._check(lib.ddl_slab_zfwd(h, 1, _ptrs([ks[f]]), _ptrs([b["e"][f]]), 0, side.cuda_stream))
+        main.wait_stream(side)
+        self._mark("wait+z_fwd")
+        self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(b["e"][:no]), _ptrs(state), _ptrs(deriv), main.cuda_stream))
+        self._mark("assemble")
+
+    def _exchange_p2p(self, f, inverse):
+        self.exchanges += 1
+        ranks, src, dst, nb = self._p2p_lists[(f, inverse)]
+        seq = self.lib.ddl_p2p_exchange(self._p2p, self.P, ranks, src, dst, nb, self._stream())
+        if seq <= 0:
+            self._check(int(seq) or -1)
+        return _Ticket(self, seq)
+
+    def _p2p_buffers(self, ni, no):
+        """RHS buffer set whose exchange endpoints (k-side / x-side) live in the IPC arena."""
+        nmax = max(ni, no)
+        if self._p2p is None:
+            self._p2p_setup(9)
+        if nmax > self._p2p_nmax:
+            raise RuntimeError("p2p arena holds %d fields, %d requested" % (self._p2p_nmax, nmax))
+        key = ("p2p", ni, no)
+        b = self._bufs.get(key)
+        if b is None:
+            z = lambda n: torch.zeros(max(int(n), 1), dtype=torch.complex128, device=self.device)
+            be = z(max(ni * self.n_b, no * self.n_e))
+            c = z(no * self.n_b)
+            cut = lambda t, n, k: [t[i * n:(i + 1) * n] for i in range(k)]
+            b = {"ks": self._p2p_ks[:nmax], "xs": self._p2p_xs[:nmax], "b": cut(be, self.n_b, ni),
+                 "e": cut(be, self.n_e, no), "c": cut(c, self.n_b, no)}
+            self._bufs[key] = b
         return b
 
     # ------------------------------------------------------------------ exchange
     def _exchange(self, dst, src, inverse):
         """inverse: k-side (peer-blocked) -> x-side; forward: x-side -> k-side.  Asynchronous."""
-        if self.P == 1:
+        if self.P == 1 or self.skip_exchange:
             return _Done()
         self.exchanges += 1
         out_split, in_split = (self.from_peer, self.to_peer) if inverse else (self.to_peer, self.from_peer)
@@ -105,7 +272,8 @@ class SlabPipeline(object):
         """deriv = RHS(state) (physics.py:527-599 / 664-712 / 770-819), local slabs in and out."""
         lib, h, st = self.lib, self.h, self._stream()
         ni, no = _COUNTS[physics_id]
-        b = self.buffers(ni, no)
+        p2p = self.exchange_kind == "p2p" and self.P > 1 and not self.skip_exchange
+        peer = self.exchange_kind == "peer" and self.P > 1 and not self.skip_exchange
         pp = C.byref(params)
         if dealias_state:
             for t in state:
@@ -113,22 +281,32 @@ class SlabPipeline(object):
         if zero_fill:
             for t in deriv:
                 self._check(lib.ddl_dealias(h, t.data_ptr(), st))
+        if peer:
+            return self._rhs_peer(physics_id, pp, state, deriv, ni, no)
+        b = dict(self.buffers(ni, no)) if not p2p else dict(self._p2p_buffers(ni, no))
         ks, xs = b["ks"], b["xs"]
+        self._mark("start")
         # inverse: z pass of field f, its exchange in flight while field f+1 is transformed
         pending = []
         for f in range(ni):
             self._check(lib.ddl_slab_zinv(h, 1, _ptrs([state[f]]), _ptrs([ks[f]]), st))
-            pending.append(self._exchange(xs[f], ks[f], True))
+            pending.append(self._exchange_p2p(f, True) if p2p else self._exchange(xs[f], ks[f], True))
+        self._mark("z_inv")
         for f in range(ni):
             pending[f].wait()
             self._check(lib.ddl_slab_yinv(h, 1, _ptrs([xs[f]]), _ptrs([b["b"][f]]), st))
+        self._mark("wait+y_inv")
         self._check(lib.ddl_slab_xfused(h, physics_id, pp, _ptrs(b["b"][:ni]), _ptrs(b["c"][:no]), st))
+        self._mark("x_fused")
         # forward: y pass of product f, exchange, z pass
         pending = []
         for f in range(no):
             self._check(lib.ddl_slab_yfwd(h, 1, _ptrs([b["c"][f]]), _ptrs([xs[f]]), st))
-            pending.append(self._exchange(ks[f], xs[f], False))
+            pending.append(self._exchange_p2p(f, False) if p2p else self._exchange(ks[f], xs[f], False))
+        self._mark("y_fwd")
         for f in range(no):
             pending[f].wait()
             self._check(lib.ddl_slab_zfwd(h, 1, _ptrs([ks[f]]), _ptrs([b["e"][f]]), 0, st))
+        self._mark("wait+z_fwd")
         self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(b["e"][:no]), _ptrs(state), _ptrs(deriv), st))
+        self._mark("assemble")

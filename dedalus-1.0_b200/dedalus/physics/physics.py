@@ -154,10 +154,15 @@ class Physics(object):
         if state_clean:
             flags &= ~_lib.RHS_DEALIAS_STATE
         pl = next(data.components())[2]._plan
-        w = pl.rhs_workspace(self._physics_id)
         pp = self._phys_params()
-        check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), _lib.ptr_array(out),
-                          w.data_ptr(), w.numel(), flags, _plan.current_stream()))
+        if pl.nranks > 1:
+            # slab-decomposed: pipeline phases with the all-to-all between the z and y passes
+            pl.pipeline.rhs(self._physics_id, pp, state, out, bool(flags & _lib.RHS_DEALIAS_STATE),
+                            bool(flags & _lib.RHS_ZERO_FILL))
+        else:
+            w = pl.rhs_workspace(self._physics_id)
+            check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), _lib.ptr_array(out),
+                              w.data_ptr(), w.numel(), flags, _plan.current_stream()))
         for _, _, c in deriv.components():
             c._clean = True
         if flags & _lib.RHS_DEALIAS_STATE:

@@ -130,6 +130,32 @@ int ddl_slab_zfwd(ddl_plan* plan, int nf, void* const* kside_in, void* const* ou
 int ddl_slab_assemble(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* e_in,
                       void* const* state, void* const* deriv, void* stream);
 
+/* ---- peer-to-peer exchange over NVLink (one process per GPU; csrc/p2p.cu) -------------------
+ * Replaces the MPI all-to-all FFTW-MPI performs inside every transform (_fftw.pyx:272-304).
+ * Each rank owns an "arena" (cudaMalloc + CUDA IPC handle) holding its k-side / x-side arrays;
+ * ddl_p2p_connect maps every peer's arena.  ddl_p2p_exchange enqueues, behind the work already
+ * on `stream`, copy-engine pushes of n blocks into the peers' arenas on an internal stream and
+ * then raises this rank's arrival flag (the returned sequence number) in every peer's arena;
+ * ddl_p2p_wait makes `stream` wait (device-side spin on the flags) until all peers' pushes of
+ * that sequence number have landed here.  Every rank must issue the same sequence of exchanges. */
+typedef struct ddl_p2p ddl_p2p;
+int ddl_p2p_create(ddl_p2p** out, int nranks, int rank, size_t data_bytes, char* ipc_handle_out64);
+int ddl_p2p_connect(ddl_p2p* ctx, const char* ipc_handles /* nranks x 64 bytes */);
+void* ddl_p2p_base(ddl_p2p* ctx);
+long long ddl_p2p_exchange(ddl_p2p* ctx, int n, const int* dst_rank, const int64_t* src_off,
+                           const int64_t* dst_off, const int64_t* nbytes, void* stream);
+int ddl_p2p_wait(ddl_p2p* ctx, long long seq, void* stream);
+/* Exchange fused into the producing pass: ddl_slab_zinv_peer / ddl_slab_yfwd_peer store every
+ * output row straight into the owning rank's arena over NVLink (no send buffer, no copy);
+ * peer_tab is a DEVICE array of nf x nranks pointers, entry [f][s] =
+ *   zinv: rank s's x-side field f + cy0_me*nzl*CX      yfwd: rank s's k-side field f + (me*cyl_s - cy0_s)*nzl*CX
+ * built from ddl_p2p_peer_base.  ddl_p2p_signal then publishes the arrival flag behind the pass. */
+void* ddl_p2p_peer_base(ddl_p2p* ctx, int rank);
+long long ddl_p2p_signal(ddl_p2p* ctx, void* stream);
+int ddl_slab_zinv_peer(ddl_plan* plan, int nf, void* const* k_in, void* const* peer_tab, void* stream);
+int ddl_slab_yfwd_peer(ddl_plan* plan, int nf, void* const* c_in, void* const* peer_tab, void* stream);
+int ddl_p2p_destroy(ddl_p2p* ctx);
+
 /* forward_step_cy_{2d,3d}.pyx euler/etd1/etd2rk1/etd2rk2 for ncomp components at once.
  * The integrating factor is not an array: Z = -coeff[c] * (k^2)^visc_order * dt is formed
  * from the plan's wavenumbers (coeff = nu / kappa / eta, 0 => the reference's IF None =>

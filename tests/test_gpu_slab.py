@@ -1,0 +1,43 @@
+"""GPU, N > 1: the slab-decomposed path (one process per GPU, NCCL all-to-all between the z and y
+passes) against the single-GPU path and the oracle.  Needs >= 2 visible GPUs (gpurun --gpus 2);
+skipped on a one-GPU box."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_ranks_match_oracle_and_single_gpu(world, tmp_path):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    out = str(tmp_path / "res.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "gpu_slab_worker.py"), out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    res = json.load(open(out))
+    for case in res:
+        assert case["rel_vs_oracle"] < 1e-10, case
+        assert case["rhs_rel"] < 1e-12, case
+        assert abs(case["ekin"] - case["ekin_oracle"]) < 1e-12, case
+        assert case["exchanges"] > 0
