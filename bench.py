@@ -135,6 +135,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # balanced ky ownership and the exchange fused into the passes (config.py [parallel]);
+        # DEDALUS_KY_LAYOUT=block gives the reference's contiguous ky slabs
+        os.environ.setdefault("DEDALUS_KY_LAYOUT", "cyclic")
+        os.environ.setdefault("DEDALUS_SLAB_EXCHANGE", "peer")
     import dedalus._lib as L
     from dedalus.mods import RK4
     import dedalus.analysis.volume_average as va
@@ -241,7 +245,8 @@ def run_ours(args):
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": "3D incompressible MHD %d^3 RK4, 2/3 dealiasing, nu=eta=1e-3" % n, "n_components": 6,
                       "N_k": nk, "stages_per_step": 4, "dt": dt,
-                      "parallelism": "slab%d (x-space z-slabs, k-space ky-slabs, all-to-all per transform)" % world if world > 1 else "single GPU",
+                      "parallelism": ("slab%d: x-space z-slabs, k-space %s ky ownership, exchange=%s" % (
+                          world, os.environ.get("DEDALUS_KY_LAYOUT"), os.environ.get("DEDALUS_SLAB_EXCHANGE"))) if world > 1 else "single GPU",
                       "cache": "inputs larger than L2 (state %.1f GB per GPU)" % (6 * nk * 16 / world / 1e9)},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "invariants": {"ekin": ekin, "emag": emag}}
     if cpu is not None:

@@ -173,8 +173,10 @@ struct ddl_plan {
     int nranks = 1, rank = 0;
     int nzl = 1, z0 = 0;
     YSlab yl;
+    int layout = 0;                 // ky ownership: 0 block (reference), 1 cyclic
     std::vector<int> cyl_of;        // retained ky rows per rank
-    unsigned char* y_owner = nullptr;   // [cy] owning rank of every compact ky row
+    unsigned char* y_owner = nullptr;   // [cy] owning rank of every x-side row position
+    int* ypos = nullptr;            // [ny] stored ky row -> x-side row position (owner-major), -1 = pruned
     long long ntot = 1;
     KGeom geom;          // local k-array geometry
     long long nmodes = 0;
@@ -216,7 +218,9 @@ static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv,
 
 extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* shape_x, const double* kx, const double* ky,
                                     const double* kz, const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz,
-                                    int nranks, int rank) {
+                                    int nranks, int rank, int layout) {
+    const double* kv_host_y = ky;
+    if (layout != 0 && layout != 1) { set_error("ky layout must be 0 (block) or 1 (cyclic)"); return -1; }
     if (!out || (ndim != 2 && ndim != 3)) { set_error("Must use either 2 or 3 dimensions."); return -1; }
     if (nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad rank %d of %d", rank, nranks); return -1; }
     if (nranks > 1 && ndim != 3) { set_error("slab decomposition is 3-D only (2-D grids run as replicas)"); return -1; }
@@ -240,29 +244,49 @@ extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* sha
     }
     pl->nranks = nranks; pl->rank = rank;
     pl->nzl = (ndim == 3 ? pl->az.n : 1) / nranks; pl->z0 = rank * pl->nzl;
+    // Ownership of the stored ky rows.  layout 0 ("block", the reference's): rank r owns rows
+    // [r*nyl, (r+1)*nyl).  layout 1 ("cyclic"): rank r owns rows r, r+P, r+2P, ... - under 2/3
+    // dealiasing the retained rows sit at both ends of the FFT-ordered axis, so block slabs leave
+    // the middle ranks without work (8 ranks, ny = 512: 64,64,43,0,0,42,64,64 retained rows)
+    // while cyclic ownership gives every rank 42 or 43.
     YSlab& L = pl->yl;
-    L.nyl = Y.nk / nranks; L.ky0 = rank * L.nyl;
+    pl->layout = layout;
+    L.nyl = Y.nk / nranks; L.ky0 = layout == 0 ? rank * L.nyl : rank;
+    auto owner_of = [&](int i) { return layout == 0 ? i / L.nyl : i % nranks; };
+    auto local_of = [&](int i) { return layout == 0 ? i % L.nyl : i / nranks; };
     pl->cyl_of.assign(nranks, 0);
-    std::vector<int> lc2f;
-    std::vector<unsigned char> owner(Y.cnt);
-    L.cy0 = -1;
-    for (int j = 0; j < Y.cnt; ++j) {
-        const int f = Y.h_c2f[j], r = f / L.nyl;
-        owner[j] = (unsigned char)r;
-        pl->cyl_of[r]++;
-        if (r == rank) { if (L.cy0 < 0) L.cy0 = j; lc2f.push_back(f - L.ky0); }
+    for (int j = 0; j < Y.cnt; ++j) pl->cyl_of[owner_of(Y.h_c2f[j])]++;
+    std::vector<int> cy0_of(nranks, 0);
+    for (int r = 1; r < nranks; ++r) cy0_of[r] = cy0_of[r - 1] + pl->cyl_of[r - 1];
+    // x-side row order: owner-major (rank 0's retained rows, then rank 1's, ...), each rank's rows
+    // in stored order; block layout: identical to the compact order
+    std::vector<int> ypos(Y.nk, -1), lc2f, fill(nranks, 0);
+    std::vector<unsigned char> owner(Y.cnt > 0 ? Y.cnt : 1);
+    std::vector<double> lkv(L.nyl), lkvc;
+    std::vector<unsigned char> lkeep(L.nyl);
+    for (int i = 0; i < Y.nk; ++i) {
+        const int r = owner_of(i);
+        const bool kept = i <= Y.m || i >= Y.nk - Y.m;
+        if (r == rank) { lkv[local_of(i)] = kv_host_y[i]; lkeep[local_of(i)] = kept ? 1 : 0; }
+        if (!kept) continue;
+        const int pos = cy0_of[r] + fill[r]++;
+        ypos[i] = pos; owner[pos] = (unsigned char)r;
+        if (r == rank) { lc2f.push_back(local_of(i)); lkvc.push_back(kv_host_y[i]); }
     }
     L.cyl = (int)lc2f.size();
-    if (L.cy0 < 0) L.cy0 = 0;
-    L.kv = Y.kv + L.ky0; L.keep = Y.keep + L.ky0; L.kvc = Y.kvc + L.cy0;
+    L.cy0 = cy0_of[rank];
     pl->y_owner = upload_vec(owner);
-    if (pl->y_owner) pl->owned.push_back(pl->y_owner);
-    if (nranks == 1) L.c2f = Y.c2f;
-    else {
-        L.c2f = upload_vec(lc2f);
-        if (!L.c2f) { set_error("device allocation failed"); ddl_plan_destroy(pl); return -2; }
-        pl->owned.push_back(L.c2f);
+    pl->ypos = upload_vec(ypos);
+    if (lkvc.empty()) lkvc.push_back(0.0);
+    if (lc2f.empty()) lc2f.push_back(0);
+    double* d_kv = upload_vec(lkv); unsigned char* d_keep = upload_vec(lkeep); double* d_kvc = upload_vec(lkvc);
+    L.c2f = upload_vec(lc2f);
+    void* mine[] = {pl->y_owner, pl->ypos, d_kv, d_keep, d_kvc, L.c2f};
+    for (void* q : mine) {
+        if (!q) { set_error("device allocation failed"); ddl_plan_destroy(pl); return -2; }
+        pl->owned.push_back(q);
     }
+    L.kv = d_kv; L.keep = d_keep; L.kvc = d_kvc;
     KGeom& g = pl->geom;
     if (ndim == 3) {
         pl->ntot = (long long)pl->ax.n * pl->ay.n * pl->az.n;
@@ -284,7 +308,7 @@ extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* sha
 
 extern "C" int ddl_plan_create(ddl_plan** out, int ndim, const int64_t* shape_x, const double* kx, const double* ky,
                                const double* kz, const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz) {
-    return ddl_plan_create_slab(out, ndim, shape_x, kx, ky, kz, keepx, keepy, keepz, 1, 0);
+    return ddl_plan_create_slab(out, ndim, shape_x, kx, ky, kz, keepx, keepy, keepz, 1, 0, 0);
 }
 
 extern "C" int ddl_plan_destroy(ddl_plan* pl) {
@@ -373,12 +397,14 @@ static int pick_c2c_group(int N, long long inner_len) {
 static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 768 ? 768 : t); }
 
 // complex pass of nf fields along an axis of length N
-struct RowSpec { int m; int compact; };   // retained rows of a pruned axis (m < 0: all rows present)
+// retained rows of a pruned axis (m < 0: all rows present); compact: 0 stored in place, 1 stored
+// contiguously in FFT order, 2 stored at the positions of the side's n_tab (owner-major order)
+struct RowSpec { int m; int compact; };
 static const RowSpec ALL_ROWS = {-1, 0};
 
 // peer mode (slab exchange fused into the pass): the output blocks are given by a device table
 // of nf x nblk pointers into the peers' arenas
-struct PeerOut { void* const* tab; const unsigned char* own; int nblk; int mask_all; };
+struct PeerOut { void* const* tab; const unsigned char* own; int nblk; int mask_all; long long off; };
 
 static int pass_c2c(const char* name, int N, int dir, int nf, const void* const* in, void* const* out, const TileSide& si,
                     const TileSide& so, RowSpec ri, RowSpec ro, int inner_len, int n_outer, double scale, const cplx* tw,
@@ -392,12 +418,13 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
         for (int i = 0; i < nf; ++i) { f.in[i] = (const cplx*)in[i]; f.out[i] = (cplx*)out[i]; }
         auto conv = [](FastSide& d, const TileSide& s, RowSpec r) {
             d.s_n = s.s_n; d.s_outer = s.s_outer; d.outer_tab = s.outer_tab; d.m = r.m; d.compact = r.compact;
+            d.row_tab = (r.compact == 2) ? s.n_tab : nullptr;
             d.split_shift = 31; d.split_mask = 0x7fffffff; d.s_blk = 0;
             if (s.split) { int sh = 0; while ((1 << sh) < s.split) ++sh; d.split_shift = sh; d.split_mask = s.split - 1; d.s_blk = s.s_blk; }
         };
         conv(f.si, si, ri); conv(f.so, so, ro);
         if (peer) {
-            f.so.peer_tab = (cplx* const*)peer->tab; f.so.own_tab = peer->own; f.so.nblk = peer->nblk;
+            f.so.peer_tab = (cplx* const*)peer->tab; f.so.own_tab = peer->own; f.so.nblk = peer->nblk; f.so.peer_off = peer->off;
             if (peer->mask_all) f.so.split_mask = 0x7fffffff;
         }
         f.inner_len = inner_len; f.scale = scale; f.tw = tw;
@@ -489,7 +516,7 @@ static int phase_zinv(ddl_plan* pl, int nf, const void* const* kin, void* const*
 static int phase_zinv_peer(ddl_plan* pl, int nf, const void* const* kin, void* const* tab, ddl_stream_t st) {
     const Axis &X = pl->ax, &Z = pl->az;
     const long long KP = X.nk, CX = kx_pitch(pl);
-    PeerOut po = {tab, nullptr, pl->nranks, 0};
+    PeerOut po = {tab, nullptr, pl->nranks, 0, 0};
     std::vector<void*> dummy(nf, nullptr);
     TileSide so = side(CX, 1, (long long)pl->nzl * CX, nullptr, nullptr, pl->nzl, 0);
     return pass_c2c("z_inv", Z.n, +1, nf, kin, dummy.data(), side(KP, 1, (long long)Z.n * KP, Z.f2f, pl->yl.c2f), so,
@@ -497,27 +524,30 @@ static int phase_zinv_peer(ddl_plan* pl, int nf, const void* const* kin, void* c
 }
 // y pass, forward, with the exchange fused in: compact ky row j of local plane zl goes to
 //   tab[f][owner(j)] + j*(nzl*CX) + zl*CX     (tab[f][s] = rank s's k-side field f + (me*cyl_s - cy0_s)*nzl*CX)
-static int phase_yfwd_peer(ddl_plan* pl, int nf, const void* const* Cin, void* const* tab, ddl_stream_t st) {
+// planes [z0, z0 + nzc) of the local slab only (chunked so that it overlaps the x pass of the next chunk)
+static int phase_yfwd_peer(ddl_plan* pl, int nf, const void* const* Cin, void* const* tab, int z0, int nzc, ddl_stream_t st) {
     const Axis &X = pl->ax, &Y = pl->ay;
     const long long CX = kx_pitch(pl), nzl = pl->nzl;
-    PeerOut po = {tab, pl->y_owner, pl->nranks, 1};
+    PeerOut po = {tab, pl->y_owner, pl->nranks, 1, (long long)z0 * CX};
     std::vector<void*> dummy(nf, nullptr);
-    return pass_c2c("y_fwd", Y.n, -1, nf, Cin, dummy.data(), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
-                    side(nzl * CX, 1, CX, Y.f2c, nullptr), ALL_ROWS, RowSpec{Y.m, 1}, X.cnt, (int)nzl, 1.0, Y.tw, st, &po);
+    std::vector<const void*> cin(nf);
+    for (int f = 0; f < nf; ++f) cin[f] = (const cplx*)Cin[f] + (long long)z0 * Y.n * CX;
+    return pass_c2c("y_fwd", Y.n, -1, nf, cin.data(), dummy.data(), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
+                    side(nzl * CX, 1, CX, pl->ypos, nullptr), ALL_ROWS, RowSpec{Y.m, pl->layout ? 2 : 1}, X.cnt, nzc, 1.0, Y.tw, st, &po);
 }
 // y pass, inverse: x-side pencils A[cy][nzl][CX] -> B[nzl][y][CX]
 static int phase_yinv(ddl_plan* pl, int nf, const void* const* A, void* const* B, ddl_stream_t st) {
     const Axis &X = pl->ax, &Y = pl->ay;
     const long long CX = kx_pitch(pl), nzl = pl->nzl;
-    return pass_c2c("y_inv", Y.n, +1, nf, A, B, side(nzl * CX, 1, CX, Y.f2c, nullptr), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
-                    RowSpec{Y.m, 1}, ALL_ROWS, X.cnt, (int)nzl, 1.0, Y.tw, st);
+    return pass_c2c("y_inv", Y.n, +1, nf, A, B, side(nzl * CX, 1, CX, pl->ypos, nullptr), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
+                    RowSpec{Y.m, pl->layout ? 2 : 1}, ALL_ROWS, X.cnt, (int)nzl, 1.0, Y.tw, st);
 }
 // y pass, forward: C[nzl][y][CX] -> x-side pencils D[cy][nzl][CX]
 static int phase_yfwd(ddl_plan* pl, int nf, const void* const* Cin, void* const* D, ddl_stream_t st) {
     const Axis &X = pl->ax, &Y = pl->ay;
     const long long CX = kx_pitch(pl), nzl = pl->nzl;
-    return pass_c2c("y_fwd", Y.n, -1, nf, Cin, D, side(CX, 1, (long long)Y.n * CX, nullptr, nullptr), side(nzl * CX, 1, CX, Y.f2c, nullptr),
-                    ALL_ROWS, RowSpec{Y.m, 1}, X.cnt, (int)nzl, 1.0, Y.tw, st);
+    return pass_c2c("y_fwd", Y.n, -1, nf, Cin, D, side(CX, 1, (long long)Y.n * CX, nullptr, nullptr), side(nzl * CX, 1, CX, pl->ypos, nullptr),
+                    ALL_ROWS, RowSpec{Y.m, pl->layout ? 2 : 1}, X.cnt, (int)nzl, 1.0, Y.tw, st);
 }
 // z pass, forward: k-side pencils -> E[cyl][kz_c][CX] (compact products) or k[kyl][kz][kx] (full_out)
 static int phase_zfwd(ddl_plan* pl, int nf, const void* const* R, void* const* dst, bool full_out, ddl_stream_t st) {
@@ -528,12 +558,19 @@ static int phase_zfwd(ddl_plan* pl, int nf, const void* const* R, void* const* d
                     1.0, Z.tw, st);
 }
 // x pass with the real-space products: B[f][nzl][y][CX] -> C[f][nzl][y][CX]
-static int phase_xfused(ddl_plan* pl, int code, int ni, int no, const void* const* B, void* const* Cout, const PhysConst& pc,
-                        ddl_stream_t st) {
+static int phase_xfused(ddl_plan* pl, int code, int ni, int no, const void* const* Bin, void* const* Cin, const PhysConst& pc,
+                        ddl_stream_t st, int z0 = 0, int nzc = -1) {
     const Axis &X = pl->ax, &Y = pl->ay;
     const long long KXP = kx_pitch(pl);
     const double sc = 1.0 / (double)pl->ntot;
-    if (pl->nzl <= 0) return 0;
+    if (nzc < 0) nzc = pl->nzl;
+    if (nzc <= 0) return 0;
+    std::vector<const void*> Bv(ni);
+    std::vector<void*> Cv(no);
+    for (int f = 0; f < ni; ++f) Bv[f] = (const cplx*)Bin[f] + (long long)z0 * Y.n * KXP;
+    for (int f = 0; f < no; ++f) Cv[f] = (cplx*)Cin[f] + (long long)z0 * Y.n * KXP;
+    const void* const* B = Bv.data();
+    void* const* Cout = Cv.data();
     if (g_use_fast && Y.n % 2 == 0 && ni <= DDL_XF_MAXI && no <= DDL_XF_MAXO) {
         XFusedParams xp;
         memset(&xp, 0, sizeof(xp));
@@ -541,11 +578,11 @@ static int phase_xfused(ddl_plan* pl, int code, int ni, int no, const void* cons
         for (int f = 0; f < no; ++f) xp.out[f] = (cplx*)Cout[f];
         xp.pitch = KXP; xp.s_outer = (long long)Y.n * KXP; xp.n_lines = Y.n; xp.kn = X.cnt;
         xp.scale = sc; xp.tw = X.tw; xp.pc = pc;
-        const int rcx = run_xfused(X.n, code, xp, pl->nzl, st);
+        const int rcx = run_xfused(X.n, code, xp, nzc, st);
         if (rcx <= 0) return rcx;
     }
     TileSide s = side(1, KXP, (long long)Y.n * KXP, nullptr, nullptr);
-    return pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, B, Cout, s, s, Y.n, pl->nzl, X.cnt, sc, X.tw, pc, st);
+    return pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, B, Cout, s, s, Y.n, nzc, X.cnt, sc, X.tw, pc, st);
 }
 // plain x passes of the transform API: B[nzl][y][CX] -> x[nzl][y][nx] and back (normalised)
 static int phase_xc2r(ddl_plan* pl, const void* B, double* x, ddl_stream_t st) {
@@ -776,6 +813,7 @@ extern "C" int ddl_slab_info(const ddl_plan* pl, int64_t* out) {
     out[0] = pl->nranks; out[1] = pl->rank; out[2] = pl->nzl; out[3] = pl->yl.nyl; out[4] = pl->yl.cyl; out[5] = pl->yl.cy0;
     out[6] = pl->ay.cnt; out[7] = pl->az.cnt; out[8] = kx_pitch(pl); out[9] = pl->ax.cnt;
     out[10] = s.ks; out[11] = s.xs; out[12] = s.b; out[13] = s.e; out[14] = pl->z0; out[15] = pl->yl.ky0;
+    out[16] = pl->layout;
     return 0;
 }
 extern "C" int ddl_slab_rows(const ddl_plan* pl, int64_t* cyl_of_rank) {
@@ -794,9 +832,23 @@ extern "C" int ddl_slab_zinv_peer(ddl_plan* pl, int nf, void* const* k_in, void*
     DDL_TRY(need_3d(pl));
     return phase_zinv_peer(pl, nf, (const void* const*)k_in, peer_tab, (ddl_stream_t)stream);
 }
-extern "C" int ddl_slab_yfwd_peer(ddl_plan* pl, int nf, void* const* c_in, void* const* peer_tab, void* stream) {
+static int check_planes(const ddl_plan* pl, int z0, int nzc) {
+    if (z0 < 0 || nzc < 0 || z0 + nzc > pl->nzl) { set_error("plane range [%d, %d) outside the local slab of %d planes", z0, z0 + nzc, pl->nzl); return -1; }
+    return 0;
+}
+extern "C" int ddl_slab_yfwd_peer(ddl_plan* pl, int nf, void* const* c_in, void* const* peer_tab, int z0, int nzc, void* stream) {
     DDL_TRY(need_3d(pl));
-    return phase_yfwd_peer(pl, nf, (const void* const*)c_in, peer_tab, (ddl_stream_t)stream);
+    DDL_TRY(check_planes(pl, z0, nzc));
+    return phase_yfwd_peer(pl, nf, (const void* const*)c_in, peer_tab, z0, nzc, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_xfused_planes(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* b_in, void* const* c_out,
+                                      int z0, int nzc, void* stream) {
+    int ni, no, code;
+    DDL_TRY(need_3d(pl));
+    DDL_TRY(check_physics(pl, physics, prm));
+    DDL_TRY(check_planes(pl, z0, nzc));
+    phys_counts(3, physics, ni, no, code);
+    return phase_xfused(pl, code, ni, no, (const void* const*)b_in, c_out, phys_const(prm), (ddl_stream_t)stream, z0, nzc);
 }
 extern "C" int ddl_slab_yinv(ddl_plan* pl, int nf, void* const* xs_in, void* const* b_out, void* stream) {
     DDL_TRY(need_3d(pl));

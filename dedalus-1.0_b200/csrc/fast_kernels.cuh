@@ -21,6 +21,7 @@ struct FastSide {
     const int* outer_tab;     // outer index -> stored outer index (NULL = identity)
     int m;                    // retained rows |index| <= m, or -1 = every row present
     int compact;              // retained rows stored contiguously (workspace) instead of in place (state)
+    const int* row_tab;       // if set: stored row of logical row r is row_tab[r] (-1 = pruned)
     // slab exchange buffers: stored row r sits at (r >> split_shift) * s_blk + (r & split_mask) * s_n
     // (split_shift = 31, split_mask = 0x7fffffff: plain rows)
     int split_shift, split_mask;
@@ -31,6 +32,7 @@ struct FastSide {
     cplx* const* peer_tab;
     const unsigned char* own_tab;
     int nblk;
+    long long peer_off;       // added to every peer address (sub-range of outer planes)
 };
 
 __device__ __forceinline__ long long fast_row_off(const FastSide& s, int r) {
@@ -101,7 +103,9 @@ struct FastMid {
     }
 };
 
-template <int N, int DIR, int CX>
+// EXT = false: plain rows on both sides (every single-GPU pass) - the lean path;
+// EXT = true : slab extensions (peer-blocked rows, row-position tables, peer-store output)
+template <int N, int DIR, int CX, bool EXT>
 __global__ void __launch_bounds__(CX * (N / Fac<N>::radix(0)), (CX * (N / Fac<N>::radix(0)) <= 512) ? 2 : 1)
 strided_fast(const __grid_constant__ FastParams p) {
     static_assert(Fac<N>::S >= 2, "strided_fast needs at least two stages");
@@ -126,8 +130,13 @@ strided_fast(const __grid_constant__ FastParams p) {
         cplx v[R0];
 #pragma unroll
         for (int j = 0; j < R0; ++j) {
-            const int row = fast_row<N>(a + j * Q0, p.si.m, p.si.compact);
-            v[j] = (live && row >= 0) ? in[ib + fast_row_off(p.si, row)] : mk(0.0, 0.0);
+            if constexpr (EXT) {
+                const int row = p.si.row_tab ? p.si.row_tab[a + j * Q0] : fast_row<N>(a + j * Q0, p.si.m, p.si.compact);
+                v[j] = (live && row >= 0) ? in[ib + fast_row_off(p.si, row)] : mk(0.0, 0.0);
+            } else {
+                const int row = fast_row<N>(a + j * Q0, p.si.m, p.si.compact);
+                v[j] = (live && row >= 0) ? in[ib + (long long)row * p.si.s_n] : mk(0.0, 0.0);
+            }
         }
         dftR<R0, DIR>(v);
         twiddles_ld<R0, DIR>(v, a, tw);
@@ -155,12 +164,17 @@ strided_fast(const __grid_constant__ FastParams p) {
             const int k0 = index_of_pos<N>(q * R);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int row = fast_row<N>(k0 + r * (N / R), p.so.m, p.so.compact);
+                if constexpr (!EXT) {
+                    const int row = fast_row<N>(k0 + r * (N / R), p.so.m, p.so.compact);
+                    if (live && row >= 0) out[ob + (long long)row * p.so.s_n] = scal(v[r], sc);
+                    continue;
+                }
+                const int row = p.so.row_tab ? p.so.row_tab[k0 + r * (N / R)] : fast_row<N>(k0 + r * (N / R), p.so.m, p.so.compact);
                 if (live && row >= 0) {
                     if (p.so.peer_tab) {
                         const int blk = p.so.own_tab ? p.so.own_tab[row] : (row >> p.so.split_shift);
                         cplx* __restrict__ dst = p.so.peer_tab[blockIdx.z * p.so.nblk + blk];
-                        dst[ob + (long long)(row & p.so.split_mask) * p.so.s_n] = scal(v[r], sc);
+                        dst[ob + p.so.peer_off + (long long)(row & p.so.split_mask) * p.so.s_n] = scal(v[r], sc);
                     } else {
                         out[ob + fast_row_off(p.so, row)] = scal(v[r], sc);
                     }
@@ -176,11 +190,21 @@ template <int N> struct FastCX {
     static constexpr int value = (T >= 128) ? 4 : (T >= 64 ? 8 : (T >= 32 ? 16 : 32));
 };
 
+template <int N, int DIR, bool EXT>
+int launch_strided_fast_v(const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t stream);
+
 template <int N, int DIR>
 int launch_strided_fast(const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t stream) {
+    const bool ext = p.si.row_tab || p.so.row_tab || p.so.peer_tab || p.si.split_shift != 31 || p.so.split_shift != 31;
+    return ext ? launch_strided_fast_v<N, DIR, true>(p, nf, n_outer, name, stream)
+               : launch_strided_fast_v<N, DIR, false>(p, nf, n_outer, name, stream);
+}
+
+template <int N, int DIR, bool EXT>
+int launch_strided_fast_v(const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t stream) {
     constexpr int CX = FastCX<N>::value;
     constexpr int T = N / Fac<N>::radix(0);
-    auto kern = strided_fast<N, DIR, CX>;
+    auto kern = strided_fast<N, DIR, CX, EXT>;
     const size_t smem = (size_t)N * CX * sizeof(cplx);
     static bool attr_done = false;
     if (!attr_done) {

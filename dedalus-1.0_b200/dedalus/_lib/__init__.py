@@ -16,7 +16,7 @@ EXPORTS = [
     "ddl_rk4_stage", "ddl_cn_step", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_zinv", "ddl_slab_yinv",
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
-    "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
@@ -62,7 +62,8 @@ def bind_slab(lib):
         lib.ddl_p2p_signal.argtypes = [vp, vp]
         lib.ddl_p2p_signal.restype = C.c_longlong
         lib.ddl_slab_zinv_peer.argtypes = [vp, i32, vp, vp, vp]
-        lib.ddl_slab_yfwd_peer.argtypes = [vp, i32, vp, vp, vp]
+        lib.ddl_slab_yfwd_peer.argtypes = [vp, i32, vp, vp, i32, i32, vp]
+        lib.ddl_slab_xfused_planes.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]
 
 
 def _load():
@@ -73,7 +74,7 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
     lib.ddl_plan_create.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, vp, vp]
-    lib.ddl_plan_create_slab.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, vp, vp, i32, i32]
+    lib.ddl_plan_create_slab.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32]
     lib.ddl_plan_destroy.argtypes = [vp]
     bind_slab(lib)
     lib.ddl_workspace_bytes.argtypes = [vp, i32, i32]

@@ -13,6 +13,12 @@ decfg = configparser.ConfigParser()
 
 _DEFAULTS = {
     "FFT": {"method": "cuda", "dealiasing": "2/3 cython"},
+    # slab decomposition over the ranks of the process group (one per GPU).  ky_layout:
+    # 'block' = the reference's contiguous ky slabs (representations.py:231-233);
+    # 'cyclic' = rank r owns ky rows r, r+P, ... (balanced under 2/3 dealiasing).
+    # exchange: 'peer' (stores into the peers' memory fused into the passes), 'p2p' (copy
+    # engines), 'collective' (torch.distributed all_to_all_single)
+    "parallel": {"ky_layout": "block", "exchange": "peer"},
     "physics": {"use_tracer": "False", "boussinesq_direction": "z"},
     "forcing": {},
     "utils": {"loglevel": "warning", "loadplugins": "False", "pluginfilename": "dedalus_plugins.py"},

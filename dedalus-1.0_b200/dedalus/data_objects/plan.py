@@ -78,12 +78,15 @@ class Plan(object):
     representations.py:180-186,231-233); `k['y']`, `kshape_local`, `xshape_local` and the
     offsets describe the local slab, the `*_np` arrays stay global."""
 
-    def __init__(self, shape, length, dealiasing, nranks=1, rank=0):
+    def __init__(self, shape, length, dealiasing, nranks=1, rank=0, ky_layout="block"):
         self.shape = tuple(int(s) for s in shape)
         self.ndim = len(self.shape)
         self.length = tuple(float(x) for x in length)
         self.dealiasing = dealiasing
         self.nranks, self.rank = int(nranks), int(rank)
+        if ky_layout not in ("block", "cyclic"):
+            raise ValueError("parallel.ky_layout must be 'block' or 'cyclic'")
+        self.ky_layout = ky_layout if self.nranks > 1 else "block"
         self.kshape, self.ktrans, self.dk, self.kny, self.k_np = wavenumbers(self.shape, self.length)
         self.keep_np = keep_masks(dealiasing, self.ktrans, self.kny, self.k_np)
         self.device = device()
@@ -95,22 +98,29 @@ class Plan(object):
             raise NotImplementedError("Slab decomposition is 3-D only: 2-D grids fit one GPU and run as replicas.")
         check(lib.ddl_plan_create_slab(C.byref(self.handle), self.ndim, vp(shp), vp(self.k_np["x"]), vp(self.k_np["y"]),
                                        vp(self.k_np["z"]) if self.ndim == 3 else None, vp(keep8["x"]), vp(keep8["y"]),
-                                       vp(keep8["z"]) if self.ndim == 3 else None, self.nranks, self.rank))
+                                       vp(keep8["z"]) if self.ndim == 3 else None, self.nranks, self.rank,
+                                       1 if self.ky_layout == "cyclic" else 0))
         self.kshape_local = self.kshape.copy()
         self.xshape_local = np.array(self.shape)
         self.koffset = self.xoffset = 0
+        self.krows = np.arange(int(self.kshape[0]))          # global ky index of every local k-space row
         if self.nranks > 1:
             self.kshape_local[0] = self.kshape[0] // self.nranks
             self.xshape_local[0] = self.shape[0] // self.nranks
-            self.koffset = self.rank * int(self.kshape_local[0])
             self.xoffset = self.rank * int(self.xshape_local[0])
+            if self.ky_layout == "cyclic":
+                self.koffset = self.rank
+                self.krows = np.arange(self.rank, int(self.kshape[0]), self.nranks)
+            else:
+                self.koffset = self.rank * int(self.kshape_local[0])
+                self.krows = np.arange(self.koffset, self.koffset + int(self.kshape_local[0]))
         # broadcast-shaped device copies for the Python-level API (comp.k['x'] etc.); axis 0 of
         # k-space is restricted to the local slab (representations.py:232-233)
         self.k = {}
         for name, kv in self.k_np.items():
             i = self.ktrans[name]
             if i == 0 and self.nranks > 1:
-                kv = kv[self.koffset:self.koffset + int(self.kshape_local[0])]
+                kv = kv[self.krows]
             shp_b = [1] * self.ndim
             shp_b[i] = len(kv)
             self.k[name] = torch.from_numpy(np.ascontiguousarray(kv)).to(self.device).reshape(shp_b)
@@ -124,7 +134,8 @@ class Plan(object):
         if self._pipe is None:
             from .slab import SlabPipeline
             import os
-            kind = os.environ.get("DEDALUS_SLAB_EXCHANGE", "peer")
+            from ..config import decfg
+            kind = os.environ.get("DEDALUS_SLAB_EXCHANGE", decfg.get("parallel", "exchange"))
             self._pipe = SlabPipeline(lib, self.handle, self.device, stream=current_stream, exchange=kind)
         return self._pipe
 
@@ -151,10 +162,13 @@ class Plan(object):
 def get_plan(shape, length, dealiasing):
     """One plan per (grid, dealiasing, device, process-group size): with a torch.distributed
     process group of P > 1 ranks a 3-D grid is slab-decomposed over it."""
+    import os
+    from ..config import decfg
     nranks, rank = com_sys.nproc, com_sys.myproc
+    layout = os.environ.get("DEDALUS_KY_LAYOUT", decfg.get("parallel", "ky_layout")) if nranks > 1 else "block"
     key = (tuple(int(s) for s in shape), tuple(float(x) for x in length), str(dealiasing),
-           torch.cuda.current_device() if torch.cuda.is_available() else -1, nranks, rank)
+           torch.cuda.current_device() if torch.cuda.is_available() else -1, nranks, rank, layout)
     pl = _PLANS.get(key)
     if pl is None:
-        pl = _PLANS[key] = Plan(shape, length, dealiasing, nranks, rank)
+        pl = _PLANS[key] = Plan(shape, length, dealiasing, nranks, rank, layout)
     return pl

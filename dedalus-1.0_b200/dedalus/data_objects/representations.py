@@ -61,6 +61,8 @@ class FourierRepresentation(Representation):
         self.global_shape["kspace"] = pl.kshape.copy()
         self.local_shape = {"kspace": pl.kshape_local.copy(), "xspace": pl.xshape_local.copy()}
         self.offset = {"xspace": pl.xoffset, "kspace": pl.koffset}
+        # global ky index of every local k-space row (block slabs: offset + arange; cyclic: rank::P)
+        self.local_rows = {"kspace": pl.krows}
         self.dk, self.kny, self.k = pl.dk, pl.kny, pl.k
         self.set_dealiasing(dealiasing)
 
@@ -221,7 +223,7 @@ class FourierRepresentation(Representation):
         for i in range(self.ndim):
             kv = self._plan.k_np[self.ktrans[i]]
             if i == 0:
-                kv = kv[self.offset["kspace"]:self.offset["kspace"] + int(self.local_shape["kspace"][0])]
+                kv = kv[self.local_rows["kspace"]]
             if exact:
                 hit = np.nonzero(kv == mode[i])[0]
             else:
@@ -253,6 +255,9 @@ class FourierRepresentation(Representation):
             parts = [torch.empty_like(mine) for _ in range(nranks)]
             dist.all_gather(parts, mine)
             plane = torch.view_as_complex(torch.cat(parts, 0))
+            if self._plan.ky_layout == "cyclic":      # rank-major rows -> global ky order
+                ny = plane.shape[0]
+                plane = plane.reshape(nranks, ny // nranks, -1).transpose(0, 1).reshape(ny, -1).contiguous()
         else:
             plane = d[:, :, 0]
         nyy, nyz = plane.shape[0] // 2, plane.shape[1] // 2
@@ -260,8 +265,7 @@ class FourierRepresentation(Representation):
         plane[-nyy:, 0] = plane[1:nyy + 1, 0].flip(0).conj()
         plane[-nyy:, 1:] = plane[1:nyy + 1, 1:].flip(0, 1).conj()
         if nranks > 1:
-            k0 = self.offset["kspace"]
-            d[:, :, 0] = plane[k0:k0 + d.shape[0]]
+            d[:, :, 0] = plane[torch.as_tensor(self.local_rows["kspace"], device=d.device)]
 
     def zero_under_eps(self):
         self.require_space("kspace")

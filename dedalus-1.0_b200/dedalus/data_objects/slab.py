@@ -61,10 +61,10 @@ class SlabPipeline(object):
         self.exchange_kind = exchange
         self._p2p = None
         self._stream = stream or (lambda: None)
-        info = (C.c_int64 * 16)()
+        info = (C.c_int64 * 32)()
         self._check(lib.ddl_slab_info(handle, info))
         (self.P, self.rank, self.nzl, self.nyl, self.cyl, self.cy0, self.cy, self.cz, self.cx, self.nkx,
-         self.n_ks, self.n_xs, self.n_b, self.n_e, self.z0, self.ky0) = [int(v) for v in info]
+         self.n_ks, self.n_xs, self.n_b, self.n_e, self.z0, self.ky0, self.ky_layout) = [int(v) for v in info[:17]]
         rows = (C.c_int64 * self.P)()
         self._check(lib.ddl_slab_rows(handle, rows))
         self.rows = [int(v) for v in rows]
@@ -74,6 +74,7 @@ class SlabPipeline(object):
         self.from_peer = [r * blk for r in self.rows]
         self._bufs = {}
         self.exchanges = 0
+        self.chunks = 4                 # plane chunks of the forward x / y passes (peer exchange)
         self.trace = None               # profiling only: list collecting (label, torch.cuda.Event) marks of rhs()
         self.skip_exchange = False      # profiling only (profiles/slab_breakdown.py): time the passes without the all-to-all
 
@@ -188,24 +189,25 @@ class SlabPipeline(object):
                 self._check(lib.ddl_slab_yinv(h, 1, _ptrs([xs[f]]), _ptrs([b["b"][f]]), side.cuda_stream))
         main.wait_stream(side)
         self._mark("wait+y_inv")
-        self._check(lib.ddl_slab_xfused(h, physics_id, pp, _ptrs(b["b"][:ni]), _ptrs(b["c"][:no]), main.cuda_stream))
-        self._mark("x_fused")
-        done = []
-        for f in range(no):
-            self._check(lib.ddl_slab_yfwd_peer(h, 1, _ptrs([b["c"][f]]), yt + f * el, main.cuda_stream))
-            t = self._signal()
+        # forward, chunked over the local planes: the x pass of chunk c+1 (compute-bound) runs on
+        # the main stream while the y pass of chunk c pushes its rows to the peers (NVLink-bound)
+        # on the side stream; one arrival signal once every chunk has been stored
+        nch = self.chunks if self.nzl % self.chunks == 0 else 1
+        zc = self.nzl // nch
+        bin_, cout = _ptrs(b["b"][:ni]), _ptrs(b["c"][:no])
+        for c in range(nch):
+            self._check(lib.ddl_slab_xfused_planes(h, physics_id, pp, bin_, cout, c * zc, zc, main.cuda_stream))
             ev = torch.cuda.Event()
             ev.record(main)
-            done.append((t, ev))
-        self._mark("y_fwd")
+            side.wait_event(ev)
+            self._check(lib.ddl_slab_yfwd_peer(h, no, cout, yt, c * zc, zc, side.cuda_stream))
+        self._mark("x_fused")
         with torch.cuda.stream(side):
-            for f in range(no):
-                t, ev = done[f]
-                side.wait_event(ev)
-                t.wait()
-                self._check(lib.ddl_slab_zfwd(h, 1, _ptrs([ks[f]]), _ptrs([b["e"][f]]), 0, side.cuda_stream))
+            t = self._signal()
+            t.wait()
+            self._check(lib.ddl_slab_zfwd(h, no, _ptrs(ks[:no]), _ptrs(b["e"][:no]), 0, side.cuda_stream))
         main.wait_stream(side)
-        self._mark("wait+z_fwd")
+        self._mark("y_fwd+z_fwd")
         self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(b["e"][:no]), _ptrs(state), _ptrs(deriv), main.cuda_stream))
         self._mark("assemble")
 

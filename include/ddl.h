@@ -69,11 +69,14 @@ int ddl_plan_destroy(ddl_plan* plan);
  * k-space pointer later passed with this plan is the rank's LOCAL slab [ny/nranks][nz][nx/2+1],
  * every x-space pointer its local [nz/nranks][ny][nx].  ddl_dealias / ddl_deriv / ddl_stage /
  * ddl_rk4_stage / ddl_cn_step work on the local slab unchanged; transforms and the RHS go
- * through the ddl_slab_* phases below with the exchange done by the caller between them. */
+ * through the ddl_slab_* phases below with the exchange done by the caller between them.
+ * ky_layout 0 = block slabs (the reference's: rank r owns ky rows [r*ny/P, (r+1)*ny/P));
+ * ky_layout 1 = cyclic (rank r owns rows r, r+P, ...): same local shape, balanced under 2/3
+ * dealiasing, where block slabs leave the middle ranks without retained modes. */
 int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* shape_x,
                          const double* kx, const double* ky, const double* kz,
                          const uint8_t* keepx, const uint8_t* keepy, const uint8_t* keepz,
-                         int nranks, int rank);
+                         int nranks, int rank, int ky_layout);
 
 /* scratch requirement of ddl_rhs / ddl_forward / ddl_backward for n_in inverse and n_out
  * forward transforms in flight (the transforms use n_in = n_out = 1) */
@@ -104,8 +107,8 @@ int ddl_rhs(ddl_plan* plan, int physics, const ddl_phys_params* params,
  *   b / c arrays (x-pass input / output): [nzl][ny][CX]  e array: [cyl][cz][CX]
  * cyl = retained ky rows owned by this rank, cy = all retained ky rows, cz = retained kz rows,
  * nzl = local z planes, CX = pitch of the retained kx axis.
- * ddl_slab_info fills out[16] = {nranks, rank, nzl, nyl, cyl, cy0, cy, cz, CX, nkx,
- *   k-side elements, x-side elements, b elements, e elements (per field), z0, ky0};
+ * ddl_slab_info fills out[17] = {nranks, rank, nzl, nyl, cyl, cy0, cy, cz, CX, nkx,
+ *   k-side elements, x-side elements, b elements, e elements (per field), z0, ky0, ky_layout};
  * ddl_slab_rows fills cyl of every rank: rank r's block in an x-side array is rows
  * [sum_{q<r} cyl_q, +cyl_r), i.e. cyl_r*nzl*CX elements, and this rank sends cyl*nzl*CX
  * elements to every peer. */
@@ -153,7 +156,11 @@ int ddl_p2p_wait(ddl_p2p* ctx, long long seq, void* stream);
 void* ddl_p2p_peer_base(ddl_p2p* ctx, int rank);
 long long ddl_p2p_signal(ddl_p2p* ctx, void* stream);
 int ddl_slab_zinv_peer(ddl_plan* plan, int nf, void* const* k_in, void* const* peer_tab, void* stream);
-int ddl_slab_yfwd_peer(ddl_plan* plan, int nf, void* const* c_in, void* const* peer_tab, void* stream);
+/* yfwd_peer and xfused_planes work on local planes [z0, z0 + nzc) only, so that the forward y
+ * pass of one chunk (NVLink-bound) overlaps the x pass of the next (compute-bound) */
+int ddl_slab_yfwd_peer(ddl_plan* plan, int nf, void* const* c_in, void* const* peer_tab, int z0, int nzc, void* stream);
+int ddl_slab_xfused_planes(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* b_in,
+                           void* const* c_out, int z0, int nzc, void* stream);
 int ddl_p2p_destroy(ddl_p2p* ctx);
 
 /* forward_step_cy_{2d,3d}.pyx euler/etd1/etd2rk1/etd2rk2 for ncomp components at once.

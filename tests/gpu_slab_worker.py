@@ -37,15 +37,15 @@ def main(out_path):
         P = dev_physics(physics, shape, None, params)
         data, deriv = P.create_fields(0.), P.create_fields(0.)
         comps = [c for _, _, c in data.components()]
-        k0, nyl = comps[0].offset["kspace"], int(comps[0].local_shape["kspace"][0])
+        rows, nyl = comps[0].local_rows["kspace"], int(comps[0].local_shape["kspace"][0])
         assert nyl == shape[1] // world and comps[0]._plan.nranks == world
         for j, c in enumerate(comps):
-            c["kspace"] = torch.from_numpy(np.ascontiguousarray(y0[j][k0:k0 + nyl]))
+            c["kspace"] = torch.from_numpy(np.ascontiguousarray(y0[j][rows]))
         P.RHS(data, deriv)
         d_loc = np.stack([c["kspace"].cpu().numpy() for _, _, c in deriv.components()])
-        rhs_rel = rel(d_loc, dy0[:, k0:k0 + nyl])
+        rhs_rel = rel(d_loc, dy0[:, rows])
         for j, c in enumerate(comps):
-            c["kspace"] = torch.from_numpy(np.ascontiguousarray(y0[j][k0:k0 + nyl]))
+            c["kspace"] = torch.from_numpy(np.ascontiguousarray(y0[j][rows]))
         dt = 2e-3
         ti = getattr(tapi, integ)(P)
         to = getattr(orc, integ)(Po)
@@ -54,7 +54,7 @@ def main(out_path):
             to.do_advance(do, dt)
         y1 = do.kvector()
         loc = np.stack([c["kspace"].cpu().numpy() for c in comps])
-        num = torch.tensor([np.linalg.norm(loc - y1[:, k0:k0 + nyl]) ** 2, np.linalg.norm(y1[:, k0:k0 + nyl]) ** 2, rhs_rel],
+        num = torch.tensor([np.linalg.norm(loc - y1[:, rows]) ** 2, np.linalg.norm(y1[:, rows]) ** 2, rhs_rel],
                            dtype=torch.float64, device="cuda")
         mx = num[2:].clone()
         dist.all_reduce(num, op=dist.ReduceOp.SUM)
@@ -62,7 +62,8 @@ def main(out_path):
         ek = va.ekin(data, reduce_all=True)
         results.append({"physics": physics, "shape": shape, "world": world, "rel_vs_oracle": float(torch.sqrt(num[0] / num[1])),
                         "rhs_rel": float(mx[0]), "ekin": float(ek), "ekin_oracle": float(orc.energy(do, "u")),
-                        "exchanges": comps[0]._plan.pipeline.exchanges})
+                        "exchanges": comps[0]._plan.pipeline.exchanges, "ky_layout": comps[0]._plan.ky_layout,
+                        "exchange": comps[0]._plan.pipeline.exchange_kind})
     if rank == 0:
         with open(out_path, "w") as f:
             json.dump(results, f)

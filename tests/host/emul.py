@@ -43,7 +43,7 @@ def _pa(arrs):
 class EmulPlan:
     PHYS = {"IncompressibleHydro": 0, "BoussinesqHydro": 1, "IncompressibleMHD": 2}
 
-    def __init__(self, lib, grid, nranks=1, rank=0):
+    def __init__(self, lib, grid, nranks=1, rank=0, layout=0):
         """grid: oracle Grid (supplies k values and the dealias mask exactly as the host layer will).
         nranks > 1: plan of rank `rank` of a slab decomposition (k arrays stay global)."""
         self.lib, self.g = lib, grid
@@ -61,7 +61,7 @@ class EmulPlan:
         self.plan = C.c_void_p()
         rc = lib.ddl_plan_create_slab(C.byref(self.plan), nd, _p(shape), _p(k["x"]), _p(k["y"]),
                                       _p(k["z"]) if nd == 3 else None, _p(keep["x"]), _p(keep["y"]),
-                                      _p(keep["z"]) if nd == 3 else None, nranks, rank)
+                                      _p(keep["z"]) if nd == 3 else None, nranks, rank, layout)
         self.check(rc)
         self.work = None
 

@@ -31,7 +31,7 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def worker(rank, world, port, case, out_path):
+def worker(rank, world, port, case, out_path, layout=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -44,7 +44,7 @@ def worker(rank, world, port, case, out_path):
         z = np.load(os.path.join(HERE, "golden", case + ".npz"))
         meta = ast.literal_eval(str(z["meta"]))
         g = orc.Grid(meta["shape"], meta["length"], meta.get("dealiasing", "2/3 cython"))
-        pl = emul.EmulPlan(lib, g, world, rank)
+        pl = emul.EmulPlan(lib, g, world, rank, layout)
         # argtypes as the product binding sets them
         import ctypes as C
         vp, i32 = C.c_void_p, C.c_int
@@ -60,7 +60,7 @@ def worker(rank, world, port, case, out_path):
         nz, ny, nx = g.shape
         nyl, nzl = ny // world, nz // world
         assert (pipe.P, pipe.rank, pipe.nzl, pipe.nyl) == (world, rank, nzl, nyl)
-        ksl = slice(rank * nyl, (rank + 1) * nyl)
+        ksl = slice(rank * nyl, (rank + 1) * nyl) if layout == 0 else slice(rank, ny, world)
         zsl = slice(rank * nzl, (rank + 1) * nzl)
         res = {}
         # ---- transforms: backward / forward of one component against the oracle

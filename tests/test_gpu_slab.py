@@ -26,18 +26,21 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_ranks_match_oracle_and_single_gpu(world, tmp_path):
+@pytest.mark.parametrize("world,layout,exchange", [(2, "block", "peer"), (2, "cyclic", "peer"), (2, "block", "collective"),
+                                                   (2, "cyclic", "p2p"), (4, "cyclic", "peer"), (8, "block", "peer"),
+                                                   (8, "cyclic", "peer")])
+def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, tmp_path):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     out = str(tmp_path / "res.json")
+    env = dict(os.environ, DEDALUS_KY_LAYOUT=layout, DEDALUS_SLAB_EXCHANGE=exchange)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "gpu_slab_worker.py"), out]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     res = json.load(open(out))
     for case in res:
         assert case["rel_vs_oracle"] < 1e-10, case
         assert case["rhs_rel"] < 1e-12, case
         assert abs(case["ekin"] - case["ekin_oracle"]) < 1e-12, case
-        assert case["exchanges"] > 0
+        assert case["exchanges"] > 0 and case["ky_layout"] == layout and case["exchange"] == exchange

@@ -19,15 +19,17 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,case", [(2, "mhd3d_16_rk2mid"), (4, "mhd3d_16_rk2mid"), (2, "bouss3d_16_rk2mid"),
-                                        (2, "hydro3d_16_rk2mid"), (4, "mhd3d_8x16x32_rk2trap")])
-def test_slab_pipeline_matches_reference(tmp_path, world, case):
+@pytest.mark.parametrize("world,case,layout", [(2, "mhd3d_16_rk2mid", 0), (4, "mhd3d_16_rk2mid", 0), (2, "bouss3d_16_rk2mid", 0),
+                                               (2, "hydro3d_16_rk2mid", 1), (4, "mhd3d_8x16x32_rk2trap", 0),
+                                               (4, "mhd3d_16_rk2mid", 1), (2, "mhd3d_8x16x32_rk2trap", 1)])
+def test_slab_pipeline_matches_reference(tmp_path, world, case, layout):
+    """layout 0: the reference's block ky slabs; 1: cyclic ky ownership (balanced under dealiasing)."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "host"))
     import emul
     emul.load()          # build the emulation library once, before the ranks race for it
     out = str(tmp_path / "res.json")
-    mp.spawn(slab_worker.worker, args=(world, _free_port(), case, out), nprocs=world, join=True)
+    mp.spawn(slab_worker.worker, args=(world, _free_port(), case, out, layout), nprocs=world, join=True)
     res = json.load(open(out))
     assert len(res) == world
     for r in res:
