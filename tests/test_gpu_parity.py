@@ -199,3 +199,102 @@ def test_generic_and_fast_kernels_agree(physics, shape):
         c["kspace"] = y0[j]
     Po.RHS(do, ko)
     assert rel(out[0], ko.kvector()) < 1e-13
+
+
+def test_config2_orszag_tang_512_rk4_vs_oracle():
+    """BASELINE config 2 at full size: 2-D MHD Orszag-Tang vortex 512^2, RK4, 2/3 dealiasing."""
+    import torch
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    import dedalus.analysis.volume_average as va
+    params = dict(nu=1e-3, eta=1e-3)
+    Po = oracle_physics("IncompressibleMHD", (512, 512), None, params)
+    do = orc.orszag_tang(Po.create_fields(0.))
+    P = dev_physics("IncompressibleMHD", (512, 512), None, params)
+    data = P.create_fields(0.)
+    set_state(data, do.kvector())
+    to, ti = orc.RK4(Po), tapi.RK4(P)
+    for _ in range(5):
+        to.do_advance(do, 2e-3)
+        ti.do_advance(data, 2e-3)
+    assert rel(get_state(data), do.kvector()) < TOL
+    assert abs(va.ekin(data) - orc.energy(do, "u")) < 1e-12 and abs(va.emag(data) - orc.energy(do, "B")) < 1e-12
+
+
+def test_mhd_128cubed_rk4_step_vs_oracle():
+    """One RK4 step of 3-D MHD at 128^3 (the size of the bounded CPU baseline) against the oracle."""
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    params = dict(nu=1e-3, eta=1e-3)
+    Po = oracle_physics("IncompressibleMHD", (128, 128, 128), None, params)
+    do = orc.synthetic_ic(Po, 5)
+    P = dev_physics("IncompressibleMHD", (128, 128, 128), None, params)
+    data = P.create_fields(0.)
+    set_state(data, do.kvector())
+    orc.RK4(Po).do_advance(do, 2e-3)
+    tapi.RK4(P).do_advance(data, 2e-3)
+    assert rel(get_state(data), do.kvector()) < TOL
+
+
+@pytest.mark.parametrize("physics,n,params", [("IncompressibleHydro", 256, dict(nu=1e-3)),
+                                              ("BoussinesqHydro", 512, dict(nu=1e-3, kappa=1e-3)),
+                                              ("IncompressibleMHD", 512, dict(nu=1e-3, eta=1e-3))])
+def test_full_size_properties(physics, n, params):
+    """BASELINE configs 3-5 at full single-GPU size, through properties that need no oracle:
+    transform round trip, linearity of the transform, Hermitian symmetry of the kx = 0 plane,
+    solenoidal u (and B) and decaying energy after RK4 steps, zero outside the dealias mask."""
+    import torch
+    import dedalus.time_stepping.api as tapi
+    import dedalus.analysis.volume_average as va
+    P = dev_physics(physics, (n, n, n), None, params)
+    data = P.create_fields(0.)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    kk = torch.sqrt(data["u"][0].k2())
+    amp = torch.where(kk > 0, kk.clamp(min=1e-30) ** (-5.0 / 6.0), torch.zeros_like(kk))
+    del kk
+    for _, f in data:
+        for _, c in f:
+            c["xspace"] = torch.randn(n, n, n, dtype=torch.float64, device="cuda", generator=g)
+            c["kspace"].mul_(amp)
+            c._xdata = None
+        if f.ncomp > 1:
+            f.div_free()
+        en = sum(va.volume_average(c["kspace"].abs() ** 2, kdict=c.k) for _, c in f)
+        for _, c in f:
+            c["kspace"].mul_(1.0 / np.sqrt(en))
+    del amp
+    c = data["u"][0]
+    k0 = c["kspace"].clone()
+    x0 = c["xspace"].clone()
+    k1 = c["kspace"]
+    assert float((k1 - k0).norm() / k0.norm()) < 1e-13                      # round trip
+    c["xspace"] = 2.5 * x0
+    assert float((c["kspace"] - 2.5 * k0).norm() / k0.norm()) < 1e-13       # linearity
+    c["kspace"] = k0
+    del x0, k1
+    c._xdata = None
+    torch.cuda.empty_cache()
+    e0 = va.ekin(data)
+    ti = tapi.RK4(P)
+    umax = float(data["u"].max_square()) ** 0.5
+    for _, cc in data["u"]:
+        cc["kspace"]
+        cc._xdata = None
+    dt = 0.2 * (2 * np.pi / n) / umax
+    for _ in range(2):
+        ti.do_advance(data, dt)
+    assert va.divergence_sum(data) / n ** 3 < 1e-12
+    if physics == "IncompressibleMHD":
+        assert va.mag_div_sum(data) / n ** 3 < 1e-12
+    e1 = va.ekin(data)
+    assert np.isfinite(e1) and (physics != "IncompressibleHydro" or e1 < e0)
+    k = data["u"][0]["kspace"]
+    keep = None
+    for name, kv in data["u"][0].k.items():
+        kn = float(data["u"][0].kny[data["u"][0].ktrans[name]])
+        m = kv.abs() < 2.0 / 3.0 * kn
+        keep = m if keep is None else (keep & m)
+    assert float(k[~keep.expand_as(k)].abs().max()) == 0.0                  # dealiased
+    plane = k[:, :, 0]
+    mirror = plane[1:, 1:].flip(0, 1).conj()
+    assert float((plane[1:, 1:] - mirror).abs().max()) < 1e-12 * float(plane.abs().max())   # Hermitian kx = 0 plane
