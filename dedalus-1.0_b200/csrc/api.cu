@@ -717,8 +717,8 @@ extern "C" int ddl_deriv(ddl_plan* pl, const void* k_in, void* k_out, int axis, 
 
 // ---------------------------------------------------------------- fused RHS
 template <class PHYS>
-static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* const* deriv, const PhysConst& pc, ddl_stream_t st) {
-    AssembleF<PHYS> f;
+static long long fill_assemble(ddl_plan* pl, AssembleF<PHYS>& f, void* const* E, void* const* state, void* const* deriv,
+                               const PhysConst& pc) {
     const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
     const long long CX = X.cnt, KXP = kx_pitch(pl);
     long long count;
@@ -743,9 +743,42 @@ static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* cons
     }
     for (int i = 0; i < PHYS::NO; ++i) f.P[i] = (const cplx*)E[i];
     for (int i = 0; i < PHYS::NS; ++i) f.S[i] = (const cplx*)state[i];
-    for (int i = 0; i < PHYS::NC; ++i) f.D[i] = (cplx*)deriv[i];
+    for (int i = 0; i < PHYS::NC; ++i) f.D[i] = deriv ? (cplx*)deriv[i] : nullptr;
     f.pc = pc;
+    return count;
+}
+
+template <class PHYS>
+static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* const* deriv, const PhysConst& pc, ddl_stream_t st) {
+    AssembleF<PHYS> f;
+    const long long count = fill_assemble<PHYS>(pl, f, E, state, deriv, pc);
     return launch_items(f, count, st, "assemble");
+}
+
+template <class PHYS>
+static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_rk4_fuse* fu,
+                        ddl_stream_t st) {
+    AssembleStageF<PHYS> f;
+    const long long count = fill_assemble<PHYS>(pl, f.a, E, state, nullptr, pc);
+    for (int c = 0; c < PHYS::NC; ++c) {
+        f.y[c] = (const cplx*)fu->y[c]; f.total[c] = (cplx*)fu->total[c]; f.out[c] = (cplx*)fu->out[c];
+        f.coeff[c] = fu->coeff ? fu->coeff[c] : 0.0;
+    }
+    f.vo = fu->visc_order; f.first = fu->first; f.last = fu->last; f.twod = pl->geom.twod;
+    f.dt = fu->dt_step; f.wdiv = fu->wdiv;
+    return launch_items(f, count, st, "assemble_stage");
+}
+
+static int assemble_rk4_any(ddl_plan* pl, int code, void* const* E, void* const* state, const PhysConst& pc,
+                            const ddl_rk4_fuse* fu, ddl_stream_t st) {
+    switch (code) {
+        case 0: return assemble_rk4<Hydro2C>(pl, E, state, pc, fu, st);
+        case 1: return assemble_rk4<Bouss2C>(pl, E, state, pc, fu, st);
+        case 2: return assemble_rk4<MHD2C>(pl, E, state, pc, fu, st);
+        case 3: return assemble_rk4<Hydro3C>(pl, E, state, pc, fu, st);
+        case 4: return assemble_rk4<Bouss3C>(pl, E, state, pc, fu, st);
+        default: return assemble_rk4<MHD3C>(pl, E, state, pc, fu, st);
+    }
 }
 
 static int assemble_any(ddl_plan* pl, int code, void* const* E, void* const* state, void* const* deriv, const PhysConst& pc,
@@ -769,8 +802,8 @@ static int check_physics(const ddl_plan* pl, int physics, const ddl_phys_params*
     return 0;
 }
 
-extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
-                       void* work, size_t work_bytes, int flags, void* stream) {
+static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
+                    void* work, size_t work_bytes, int flags, const ddl_rk4_fuse* fuse, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
     int ni, no, code;
     DDL_TRY(need_one_rank(pl, "ddl_rhs"));
@@ -780,7 +813,7 @@ extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, vo
     const PhysConst pc = phys_const(prm);
     const int ncomp = ni;   // state components == inverse transforms in the conservative forms
     if (flags & DDL_RHS_DEALIAS_STATE) DDL_TRY(mask_arrays(pl, ncomp, state, st));
-    if (flags & DDL_RHS_ZERO_FILL) DDL_TRY(mask_arrays(pl, ncomp, deriv, st));
+    if ((flags & DDL_RHS_ZERO_FILL) && deriv) DDL_TRY(mask_arrays(pl, ncomp, deriv, st));
 
     WsLayout w = ws_layout(pl, ni, no);
     cplx* r0 = (cplx*)work; cplx* r1 = r0 + w.r0; cplx* r2 = r1 + w.r1;
@@ -804,7 +837,19 @@ extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, vo
         DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, A.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st));
         DDL_TRY(forward_tail_2d(pl, no, C.data(), E.data(), false, st));
     }
+    if (fuse) return assemble_rk4_any(pl, code, E.data(), state, pc, fuse, st);
     return assemble_any(pl, code, E.data(), state, deriv, pc, st);
+}
+
+extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
+                       void* work, size_t work_bytes, int flags, void* stream) {
+    return rhs_impl(pl, physics, prm, state, deriv, work, work_bytes, flags, nullptr, stream);
+}
+
+extern "C" int ddl_rhs_rk4(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* work,
+                           size_t work_bytes, int flags, const ddl_rk4_fuse* fuse, void* stream) {
+    if (!fuse || !fuse->y || !fuse->total || !fuse->out) { set_error("ddl_rhs_rk4: incomplete stage descriptor"); return -1; }
+    return rhs_impl(pl, physics, prm, state, nullptr, work, work_bytes, flags, fuse, stream);
 }
 
 // ---------------------------------------------------------------- slab phase API (include/ddl.h)
@@ -877,6 +922,15 @@ extern "C" int ddl_slab_yfwd(ddl_plan* pl, int nf, void* const* c_in, void* cons
 extern "C" int ddl_slab_zfwd(ddl_plan* pl, int nf, void* const* ks_in, void* const* out, int full_out, void* stream) {
     DDL_TRY(need_3d(pl));
     return phase_zfwd(pl, nf, (const void* const*)ks_in, out, full_out != 0, (ddl_stream_t)stream);
+}
+extern "C" int ddl_slab_assemble_rk4(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* e_in, void* const* state,
+                                     const ddl_rk4_fuse* fuse, void* stream) {
+    int ni, no, code;
+    DDL_TRY(need_3d(pl));
+    DDL_TRY(check_physics(pl, physics, prm));
+    if (!fuse || !fuse->y || !fuse->total || !fuse->out) { set_error("ddl_slab_assemble_rk4: incomplete stage descriptor"); return -1; }
+    phys_counts(3, physics, ni, no, code);
+    return assemble_rk4_any(pl, code, e_in, state, phys_const(prm), fuse, (ddl_stream_t)stream);
 }
 extern "C" int ddl_slab_assemble(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* e_in, void* const* state,
                                  void* const* deriv, void* stream) {

@@ -228,6 +228,57 @@ struct AssembleF {
     }
 };
 
+// Spectral assembly fused with one stage of the restated RK4 (ddl_rk4_stage): the derivative k
+// is formed in registers from the product spectra and consumed at once,
+//   total = (first ? 0 : total) + k / wdiv ;  out = S(y, last ? total : k, dt)
+// so k never exists in memory (saves its 16 B write + 16 B read per mode and component, and a
+// launch).  Retained modes only: every operand must vanish outside the dealias mask.
+template <class PHYS>
+struct AssembleStageF {
+    AssembleF<PHYS> a;
+    const cplx* y[PHYS::NC];
+    cplx* total[PHYS::NC];
+    cplx* out[PHYS::NC];
+    double coeff[PHYS::NC];
+    int vo, first, last, twod;
+    double dt, wdiv;
+    DDL_HD void operator()(long long i) const {
+        int j[3];
+        split3(i, a.cdim, j[0], j[1], j[2]);
+        long long ci = 0, fi = 0;
+        double kk[3] = {0.0, 0.0, 0.0};
+        double k2 = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            ci += j[l] * a.cstride[l];
+            fi += (long long)(a.ftab[l] ? a.ftab[l][j[l]] : j[l]) * a.fstride[l];
+            if (a.ax[l] >= 0) { const double v = a.kvc[l][j[l]]; kk[a.ax[l]] = v; k2 += v * v; }   // StageF's summation order
+        }
+        cplx p[PHYS::NO], s[PHYS::NS ? PHYS::NS : 1], d[PHYS::NC];
+#pragma unroll
+        for (int f = 0; f < PHYS::NO; ++f) p[f] = a.P[f][ci];
+#pragma unroll
+        for (int f = 0; f < PHYS::NS; ++f) s[f] = a.S[f][fi];
+        PHYS::assemble(p, s, d, kk[0], kk[1], kk[2], a.pc);
+        const double pw = ipow(k2, vo);
+        double lastc = -1.0, Z = 0.0, f0 = 1.0, f1 = 1.0, f2 = 0.5;
+#pragma unroll
+        for (int c = 0; c < PHYS::NC; ++c) {
+            const double co = coeff[c];
+            if (co != lastc) {
+                lastc = co;
+                Z = -(co * pw) * dt;
+                if (Z != 0.0) phi_funcs(Z, twod, f0, f1, f2);
+            }
+            const cplx kc = d[c];
+            cplx t = mk(kc.x / wdiv, kc.y / wdiv);
+            if (!first) { const cplx o = total[c][fi]; t = mk(o.x + t.x, o.y + t.y); }
+            if (!last) total[c][fi] = t;
+            out[c][fi] = etd1_step(y[c][fi], last ? t : kc, Z, f0, f1, dt);
+        }
+    }
+};
+
 #if DDL_DEVICE_BUILD
 template <class F>
 __global__ void items_kernel(const __grid_constant__ F f, long long count) {

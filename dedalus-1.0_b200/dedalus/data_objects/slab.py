@@ -159,7 +159,7 @@ class SlabPipeline(object):
             self._check(int(seq) or -1)
         return _Ticket(self, seq)
 
-    def _rhs_peer(self, physics_id, pp, state, deriv, ni, no):
+    def _rhs_peer(self, physics_id, pp, state, deriv, ni, no, fuse=None):
         """RHS with the exchange fused into the producing passes: the inverse z pass and the
         forward y pass store their output rows straight into the owning rank's arena over
         NVLink; a second stream runs the consuming passes of field f while the producing pass
@@ -208,7 +208,7 @@ class SlabPipeline(object):
             self._check(lib.ddl_slab_zfwd(h, no, _ptrs(ks[:no]), _ptrs(b["e"][:no]), 0, side.cuda_stream))
         main.wait_stream(side)
         self._mark("y_fwd+z_fwd")
-        self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(b["e"][:no]), _ptrs(state), _ptrs(deriv), main.cuda_stream))
+        self._assemble(physics_id, pp, b["e"][:no], state, deriv, fuse, main.cuda_stream)
         self._mark("assemble")
 
     def _exchange_p2p(self, f, inverse):
@@ -270,7 +270,14 @@ class SlabPipeline(object):
         self._check(lib.ddl_dealias(h, k.data_ptr(), st))
 
     # ------------------------------------------------------------------ fused RHS
-    def rhs(self, physics_id, params, state, deriv, dealias_state, zero_fill):
+    def _assemble(self, physics_id, pp, e, state, deriv, fuse, st):
+        lib, h = self.lib, self.h
+        if fuse is not None:
+            self._check(lib.ddl_slab_assemble_rk4(h, physics_id, pp, _ptrs(e), _ptrs(state), C.byref(fuse), st))
+        else:
+            self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(e), _ptrs(state), _ptrs(deriv), st))
+
+    def rhs(self, physics_id, params, state, deriv, dealias_state, zero_fill, fuse=None):
         """deriv = RHS(state) (physics.py:527-599 / 664-712 / 770-819), local slabs in and out."""
         lib, h, st = self.lib, self.h, self._stream()
         ni, no = _COUNTS[physics_id]
@@ -284,7 +291,7 @@ class SlabPipeline(object):
             for t in deriv:
                 self._check(lib.ddl_dealias(h, t.data_ptr(), st))
         if peer:
-            return self._rhs_peer(physics_id, pp, state, deriv, ni, no)
+            return self._rhs_peer(physics_id, pp, state, deriv, ni, no, fuse)
         b = dict(self.buffers(ni, no)) if not p2p else dict(self._p2p_buffers(ni, no))
         ks, xs = b["ks"], b["xs"]
         self._mark("start")
@@ -310,5 +317,5 @@ class SlabPipeline(object):
             pending[f].wait()
             self._check(lib.ddl_slab_zfwd(h, 1, _ptrs([ks[f]]), _ptrs([b["e"][f]]), 0, st))
         self._mark("wait+z_fwd")
-        self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(b["e"][:no]), _ptrs(state), _ptrs(deriv), st))
+        self._assemble(physics_id, pp, b["e"][:no], state, deriv, fuse, st)
         self._mark("assemble")

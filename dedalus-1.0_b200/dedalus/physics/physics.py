@@ -131,7 +131,16 @@ class Physics(object):
             field.zero_all()
         deriv.set_time(data.time)
 
-    def _fused_rhs(self, data, deriv, flags):
+    def can_fuse_stage(self):
+        """True when nothing is added to deriv after the fused pipeline (rotation, forcing), so an
+        integrator may ask for the spectral assembly fused with its stage update."""
+        if not self._is_finalized:
+            self._finalize()
+        return not getattr(self, "_rotation", False) and not self.forcing_functions
+
+    def _fused_rhs(self, data, deriv, flags, fuse=None):
+        """deriv = RHS(data).  With `fuse` (an _lib.RK4Fuse; deriv is None) the derivative is
+        consumed in registers by one RK4 stage update instead of being written (ddl_rhs_rk4)."""
         if not self._is_finalized:
             self._finalize()
         if decfg.get("FFT", "dealiasing") not in ("2/3", "2/3 cython"):
@@ -144,7 +153,7 @@ class Physics(object):
             c.require_space("kspace")
             state.append(c._k)
             state_clean = state_clean and c._clean
-        for _, _, c in deriv.components():
+        for _, _, c in (deriv.components() if deriv is not None else ()):
             c._curr_space = "kspace"
             out.append(c._k)
             deriv_clean = deriv_clean and c._clean
@@ -156,19 +165,24 @@ class Physics(object):
         pl = next(data.components())[2]._plan
         pp = self._phys_params()
         if pl.nranks > 1:
-            # slab-decomposed: pipeline phases with the all-to-all between the z and y passes
+            # slab-decomposed: pipeline phases with the exchange between the z and y passes
             pl.pipeline.rhs(self._physics_id, pp, state, out, bool(flags & _lib.RHS_DEALIAS_STATE),
-                            bool(flags & _lib.RHS_ZERO_FILL))
+                            bool(flags & _lib.RHS_ZERO_FILL) and fuse is None, fuse=fuse)
+        elif fuse is not None:
+            w = pl.rhs_workspace(self._physics_id)
+            check(lib.ddl_rhs_rk4(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), w.data_ptr(), w.numel(),
+                                  flags & ~_lib.RHS_ZERO_FILL, C.byref(fuse), _plan.current_stream()))
         else:
             w = pl.rhs_workspace(self._physics_id)
             check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), _lib.ptr_array(out),
                               w.data_ptr(), w.numel(), flags, _plan.current_stream()))
-        for _, _, c in deriv.components():
+        for _, _, c in (deriv.components() if deriv is not None else ()):
             c._clean = True
         if flags & _lib.RHS_DEALIAS_STATE:
             for _, _, c in data.components():
                 c._clean = True
-        deriv.set_time(data.time)
+        if deriv is not None:
+            deriv.set_time(data.time)
 
     # ------------------------------------------------------------------ unfused helpers
     def gradX(self, X, output):

@@ -243,8 +243,47 @@ class RK4(RKBase):
         _mark(out, clean)
         _mark(self.total_deriv, clean)
 
+    def _fusable(self, data):
+        """The spectral assembly of the RHS can be fused with the stage update (ddl_rhs_rk4) when
+        nothing else touches deriv and every operand vanishes outside the dealias mask."""
+        R = self.RHS
+        if self._coeff is None or not self.fuse_stages or not hasattr(R, "_fused_rhs") or not R.can_fuse_stage():
+            return False
+        if R.aux_eqns:
+            return False
+        return _all_clean(data, self.total_deriv, self.temp_data)
+
+    def _rk4_fused(self, state_in, y, out, wdiv, dt_step, first, last):
+        R = self.RHS
+        ys, ts, os_ = _kspace_tensors(y), _kspace_tensors(self.total_deriv), _kspace_tensors(out)
+        coeff, order = self._coeff
+        pa, pt, po = _lib.ptr_array(ys), _lib.ptr_array(ts), _lib.ptr_array(os_)
+        fuse = _lib.RK4Fuse(C.cast(pa, C.c_void_p), C.cast(pt, C.c_void_p), C.cast(po, C.c_void_p),
+                            C.cast(coeff, C.c_void_p), int(order), int(first), int(last), float(wdiv), float(dt_step))
+        R._fused_rhs(state_in, None, R._rhs_flags(), fuse=fuse)
+        _mark(out, True)
+        _mark(self.total_deriv, True)
+
+    def _advance_fused(self, data, dt):
+        tmp = self.temp_data
+        self._rk4_fused(data, data, tmp, 6., dt / 2., True, False)      # k1
+        tmp.set_time(data.time + dt / 2.)
+        self._rk4_fused(tmp, data, tmp, 3., dt / 2., False, False)      # k2
+        self._rk4_fused(tmp, data, tmp, 3., dt, False, False)           # k3
+        tmp.set_time(data.time + dt)
+        self._rk4_fused(tmp, data, data, 6., dt, False, True)           # k4 ; y+ = S(y, total + k4/6, dt)
+        data.set_time(data.time + dt)
+        self.time += dt
+        self.iteration += 1
+
+    fuse_stages = True      # set False to force the unfused RHS + ddl_rk4_stage path (tests compare both)
+
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
+        for _, _, c in data.components():
+            c.require_space("kspace")
+        if self._fusable(data):
+            return self._advance_fused(data, dt)
         aux = list(R.aux_eqns.values())
         a_old = [a.value for a in aux]
         a_final = [a.RHS(a.value) / 6. for a in aux]

@@ -298,3 +298,32 @@ def test_full_size_properties(physics, n, params):
     plane = k[:, :, 0]
     mirror = plane[1:, 1:].flip(0, 1).conj()
     assert float((plane[1:, 1:] - mirror).abs().max()) < 1e-12 * float(plane.abs().max())   # Hermitian kx = 0 plane
+
+
+@pytest.mark.parametrize("physics,shape,params", [("IncompressibleMHD", (32, 32, 64), dict(nu=1e-3, eta=0.2)),
+                                                  ("BoussinesqHydro", (32, 32, 32), dict(nu=1e-3, kappa=1e-3)),
+                                                  ("IncompressibleMHD", (64, 64), dict(nu=1e-3, eta=1e-3))])
+def test_rk4_fused_assembly_equals_unfused(physics, shape, params):
+    """RK4 with the spectral assembly fused into the stage update (ddl_rhs_rk4, taken from the second
+    step on when everything is dealiased) == RHS + ddl_rk4_stage, and both match the oracle."""
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    Po = oracle_physics(physics, shape, None, params)
+    do = orc.synthetic_ic(Po, 9)
+    y0 = do.kvector()
+    res = []
+    for fuse in (True, False):
+        P = dev_physics(physics, shape, None, params)
+        data = P.create_fields(0.)
+        set_state(data, y0)
+        ti = tapi.RK4(P)
+        ti.fuse_stages = fuse
+        for _ in range(4):
+            ti.do_advance(data, 3e-3)
+        res.append(get_state(data))
+        assert abs(data.time - 4 * 3e-3) < 1e-14
+    assert rel(res[0], res[1]) < 1e-14
+    to = orc.RK4(Po)
+    for _ in range(4):
+        to.do_advance(do, 3e-3)
+    assert rel(res[0], do.kvector()) < TOL

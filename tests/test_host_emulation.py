@@ -132,3 +132,26 @@ def test_emulated_retained_only_sweep_equals_full_sweep(lib, shape):
         for a, b in zip(full, part):
             assert np.array_equal(a * keep, b * keep)
             assert np.all(a[~keep] == 0)
+
+
+@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (8, 16, 16)), ("BoussinesqHydro", (16, 8, 16)),
+                                           ("IncompressibleHydro", (16, 32)), ("IncompressibleMHD", (16, 16))])
+@pytest.mark.parametrize("first,last", [(1, 0), (0, 0), (0, 1)])
+def test_emulated_fused_rk4_stage_equals_rhs_then_stage(lib, physics, shape, first, last):
+    """ddl_rhs_rk4 (derivative consumed in registers) == ddl_rhs followed by ddl_rk4_stage."""
+    g = orc.Grid(shape, None)
+    pl = emul.EmulPlan(lib, g)
+    kw = {"direction": "y" if len(shape) == 2 else "z"} if physics == "BoussinesqHydro" else {}
+    P = orc.PHYSICS[physics](shape, None, "2/3 cython", **kw)
+    state = list(orc.synthetic_ic(P, 3).kvector())
+    y = list(orc.synthetic_ic(P, 4).kvector())
+    total = list(orc.synthetic_ic(P, 6).kvector())
+    params = {"boussinesq_direction": "y" if len(shape) == 2 else "z"}
+    n = len(state)
+    coeff = ([0.0, 0.01, 0.3, 0.3, 0.02, 0.0])[:n]
+    k, _ = pl.rhs(physics, params, state, flags=1)
+    ref_out, ref_total = pl.rk4_stage(y, list(k), total, coeff, 1, 3.0, 0.05, first, last)
+    out, tot = pl.rhs_rk4(physics, params, state, y, total, coeff, 1, 3.0, 0.05, first, last)
+    assert rel(out, ref_out) < 1e-15
+    if not last:
+        assert rel(tot, ref_total) < 1e-15
