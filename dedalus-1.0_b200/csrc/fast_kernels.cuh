@@ -187,7 +187,11 @@ strided_fast(const __grid_constant__ FastParams p) {
 // pencils per tile for the strided pass of length N
 template <int N> struct FastCX {
     static constexpr int T = N / Fac<N>::radix(0);
+#ifdef DDL_FAST_CX_HALF      // experiment: half-width tiles (profiles/kernel_times.py with DEDALUS_DDL_LIB)
+    static constexpr int value = (T >= 128) ? 2 : (T >= 64 ? 4 : (T >= 32 ? 8 : 16));
+#else
     static constexpr int value = (T >= 128) ? 4 : (T >= 64 ? 8 : (T >= 32 ? 16 : 32));
+#endif
 };
 
 template <int N, int DIR, bool EXT>

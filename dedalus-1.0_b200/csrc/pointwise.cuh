@@ -281,7 +281,7 @@ struct AssembleStageF {
 
 #if DDL_DEVICE_BUILD
 template <class F>
-__global__ void items_kernel(const __grid_constant__ F f, long long count) {
+__global__ void __launch_bounds__(256, 4) items_kernel(const __grid_constant__ F f, long long count) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) f(i);
 }

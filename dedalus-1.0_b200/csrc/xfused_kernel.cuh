@@ -131,6 +131,44 @@ DDL_HD void xtwiddle(cplx (&v)[R], cplx w1) {
     }
 }
 
+// Stages whose sub-problems have length 2R (Q == 2) have only the twiddles w^r = exp(-2 pi i r / 2R)
+// (butterflies with b == 1; b == 0 has none): compile-time constants, no generation, no load.
+// Value (cos, sin) of exp(+2 pi i r / 2R); the forward sign conjugates.
+template <int R> DDL_HD cplx xconst_twiddle(int r) {
+    constexpr double c16 = 0.9238795325112867561282, s16 = 0.3826834323650897717285, h = 0.7071067811865475244008;
+    constexpr double c32a = 0.9807852804032304491262, s32a = 0.1950903220161282678483;
+    constexpr double c32b = 0.8314696123025452370788, s32b = 0.5555702330196022247428;
+    if constexpr (R == 16) {          // exp(2 pi i r / 32)
+        switch (r) {
+            case 1: return mk(c32a, s32a);   case 2: return mk(c16, s16);     case 3: return mk(c32b, s32b);
+            case 4: return mk(h, h);         case 5: return mk(s32b, c32b);   case 6: return mk(s16, c16);
+            case 7: return mk(s32a, c32a);   case 8: return mk(0.0, 1.0);     case 9: return mk(-s32a, c32a);
+            case 10: return mk(-s16, c16);   case 11: return mk(-s32b, c32b); case 12: return mk(-h, h);
+            case 13: return mk(-c32b, s32b); case 14: return mk(-c16, s16);   case 15: return mk(-c32a, s32a);
+            default: return mk(1.0, 0.0);
+        }
+    } else {                          // R == 8: exp(2 pi i r / 16)
+        switch (r) {
+            case 1: return mk(c16, s16);  case 2: return mk(h, h);    case 3: return mk(s16, c16);  case 4: return mk(0.0, 1.0);
+            case 5: return mk(-s16, c16); case 6: return mk(-h, h);   case 7: return mk(-c16, s16);
+            default: return mk(1.0, 0.0);
+        }
+    }
+}
+
+// v[idx(r)] *= exp(DIR * 2 pi i r / 2R) with constant operands
+template <int R, int DIR, bool OUT_ORDER>
+DDL_HD void xtwiddle_const(cplx (&v)[R]) {
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        cplx w = xconst_twiddle<R>(r);
+        if (DIR < 0) w.y = -w.y;
+        cplx& a = v[OUT_ORDER ? xreg<R>(r) : r];
+        if (2 * r == R) a = mul_i<DIR>(a);            // w = +-i
+        else a = cmul(a, w);
+    }
+}
+
 #if DDL_DEVICE_BUILD
 #define DDL_XF_ITEMS(i, count, NT) for (int i = threadIdx.x; i < (count); i += (NT))
 #define DDL_XF_THREADS(t, NT) for (int t = threadIdx.x, _once = 1; _once; _once = 0)
@@ -168,19 +206,26 @@ DDL_BODY void xstage(cplx* T, int lane, const cplx* __restrict__ tw) {
         cplx v[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) v[j] = T[sb ^ xsw<N>(j * Q)];
+        constexpr bool CONST_TW = (Q == 2) && (R == 16 || R == 8);
         if constexpr (DIT) {
             if (b != 0) {
-                cplx w1 = DDL_LDG(&tw[b * P]);
-                if (DIR > 0) w1 = conj(w1);
-                xtwiddle<R, false>(v, w1);
+                if constexpr (CONST_TW) xtwiddle_const<R, DIR, false>(v);
+                else {
+                    cplx w1 = DDL_LDG(&tw[b * P]);
+                    if (DIR > 0) w1 = conj(w1);
+                    xtwiddle<R, false>(v, w1);
+                }
             }
             xdft<R, DIR>(v);
         } else {
             xdft<R, DIR>(v);
             if (b != 0) {
-                cplx w1 = DDL_LDG(&tw[b * P]);
-                if (DIR > 0) w1 = conj(w1);
-                xtwiddle<R, true>(v, w1);
+                if constexpr (CONST_TW) xtwiddle_const<R, DIR, true>(v);
+                else {
+                    cplx w1 = DDL_LDG(&tw[b * P]);
+                    if (DIR > 0) w1 = conj(w1);
+                    xtwiddle<R, true>(v, w1);
+                }
             }
         }
 #pragma unroll

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddl_b200.so")
+LIB_PATH = os.environ.get("DEDALUS_DDL_LIB") or os.path.join(_HERE, "libddl_b200.so")   # override: kernel experiments only
 
 EXPORTS = [
     "ddl_plan_create", "ddl_plan_create_slab", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
