@@ -74,7 +74,9 @@ class SlabPipeline(object):
         self.from_peer = [r * blk for r in self.rows]
         self._bufs = {}
         self.exchanges = 0
-        self.chunks = 4                 # plane chunks of the forward x / y passes (peer exchange)
+        import os
+        self.chunks = int(os.environ.get("DEDALUS_SLAB_CHUNKS", "4"))     # plane chunks of the forward x / y passes (peer exchange)
+        self.inverse_batched = os.environ.get("DEDALUS_SLAB_INVERSE", "batched") == "batched"
         self.trace = None               # profiling only: list collecting (label, torch.cuda.Event) marks of rhs()
         self.skip_exchange = False      # profiling only (profiles/slab_breakdown.py): time the passes without the all-to-all
 
@@ -173,21 +175,29 @@ class SlabPipeline(object):
         zt, yt = self._zinv_tab.data_ptr(), self._yfwd_tab.data_ptr()
         self._mark("start")
         side.wait_stream(main)
-        done = []
-        for f in range(ni):
-            self._check(lib.ddl_slab_zinv_peer(h, 1, _ptrs([state[f]]), zt + f * el, main.cuda_stream))
+        if self.inverse_batched:
+            # one launch per pass for all fields: at 8 ranks a single field is only ~3 waves of CTAs
+            self._check(lib.ddl_slab_zinv_peer(h, ni, _ptrs(state[:ni]), zt, main.cuda_stream))
             t = self._signal()
-            ev = torch.cuda.Event()
-            ev.record(main)
-            done.append((t, ev))
-        self._mark("z_inv")
-        with torch.cuda.stream(side):
+            self._mark("z_inv")
+            t.wait()
+            self._check(lib.ddl_slab_yinv(h, ni, _ptrs(xs[:ni]), _ptrs(b["b"][:ni]), main.cuda_stream))
+        else:
+            done = []
             for f in range(ni):
-                t, ev = done[f]
-                side.wait_event(ev)             # my own block is written by my own pass
-                t.wait()                        # the peers' blocks: arrival flags
-                self._check(lib.ddl_slab_yinv(h, 1, _ptrs([xs[f]]), _ptrs([b["b"][f]]), side.cuda_stream))
-        main.wait_stream(side)
+                self._check(lib.ddl_slab_zinv_peer(h, 1, _ptrs([state[f]]), zt + f * el, main.cuda_stream))
+                t = self._signal()
+                ev = torch.cuda.Event()
+                ev.record(main)
+                done.append((t, ev))
+            self._mark("z_inv")
+            with torch.cuda.stream(side):
+                for f in range(ni):
+                    t, ev = done[f]
+                    side.wait_event(ev)             # my own block is written by my own pass
+                    t.wait()                        # the peers' blocks: arrival flags
+                    self._check(lib.ddl_slab_yinv(h, 1, _ptrs([xs[f]]), _ptrs([b["b"][f]]), side.cuda_stream))
+            main.wait_stream(side)
         self._mark("wait+y_inv")
         # forward, chunked over the local planes: the x pass of chunk c+1 (compute-bound) runs on
         # the main stream while the y pass of chunk c pushes its rows to the peers (NVLink-bound)
