@@ -311,7 +311,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=512, help="grid size per axis (headline: 512)")
+    ap.add_argument("--grid", "--n", dest="n", type=int, default=512, help="grid size per axis (headline: 512); use --grid under torchrun")
     ap.add_argument("--cpu-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--quick", action="store_true", help="timed region only (for runs under ncu)")
