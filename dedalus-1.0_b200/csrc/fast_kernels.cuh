@@ -187,11 +187,10 @@ strided_fast(const __grid_constant__ FastParams p) {
 // pencils per tile for the strided pass of length N
 template <int N> struct FastCX {
     static constexpr int T = N / Fac<N>::radix(0);
-#ifdef DDL_FAST_CX_HALF      // experiment: half-width tiles (profiles/kernel_times.py with DEDALUS_DDL_LIB)
-    static constexpr int value = (T >= 128) ? 2 : (T >= 64 ? 4 : (T >= 32 ? 8 : 16));
-#else
+    // N = 512: 128-byte row segments (CX = 8, two 512-thread CTAs per SM); 64-byte segments cost 25 % there.
+    // N = 1024: measured the other way round (y passes 5 % faster with two 512-thread CTAs of CX = 4 than with
+    // one 1024-thread CTA of CX = 8), profiles/ncu_r1.md
     static constexpr int value = (T >= 128) ? 4 : (T >= 64 ? 8 : (T >= 32 ? 16 : 32));
-#endif
 };
 
 template <int N, int DIR, bool EXT>
