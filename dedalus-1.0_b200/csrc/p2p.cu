@@ -34,7 +34,7 @@ __global__ void p2p_signal_kernel(unsigned* const* flags, int n, int slot, unsig
 }
 
 // spin until every watched flag has reached `value` (monotone sequence numbers; the
-// comparison is wrap-safe); trap after ~10 s so that a lost peer fails loudly instead of hanging
+// comparison is wrap-safe); trap after ~30 s so that a lost peer fails loudly instead of hanging
 __global__ void p2p_wait_kernel(const unsigned* flags, int n, int skip, unsigned value, long long timeout_cycles) {
     const int i = threadIdx.x;
     if (i < n && i != skip) {
@@ -162,7 +162,7 @@ extern "C" int ddl_p2p_wait(ddl_p2p* c, long long seq, void* stream) {
     const int slot = (unsigned)seq % DDL_P2P_RING;
     if (c->copied[slot]) DDL_CUDA_CHECK(cudaStreamWaitEvent(st, c->self[slot], 0));
     const unsigned* flags = (const unsigned*)c->base;
-    p2p_wait_kernel<<<1, 32, 0, st>>>(flags, c->nranks, c->rank, (unsigned)seq, 20000000000LL);
+    p2p_wait_kernel<<<1, 32, 0, st>>>(flags, c->nranks, c->rank, (unsigned)seq, 60000000000LL);   // ~30 s at 2 GHz
     DDL_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

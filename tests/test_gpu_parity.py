@@ -327,3 +327,25 @@ def test_rk4_fused_assembly_equals_unfused(physics, shape, params):
     for _ in range(4):
         to.do_advance(do, 3e-3)
     assert rel(res[0], do.kvector()) < TOL
+
+
+@pytest.mark.parametrize("physics,shape,integ", [("IncompressibleMHD", (512, 512), "RK4"), ("IncompressibleHydro", (128, 128), "RK2mid"),
+                                                 ("IncompressibleMHD", (32, 32, 32), "RK4")])
+def test_cuda_graph_replay_equals_eager_steps(physics, shape, integ):
+    """do_advance_graph (one captured step replayed) == the same number of eager do_advance calls."""
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    params = dict(nu=1e-3, eta=1e-3) if physics == "IncompressibleMHD" else dict(nu=1e-3)
+    Po = oracle_physics(physics, shape, None, params)
+    y0 = orc.synthetic_ic(Po, 2).kvector()
+    res = []
+    for graph in (True, False):
+        P = dev_physics(physics, shape, None, params)
+        data = P.create_fields(0.)
+        set_state(data, y0)
+        ti = getattr(tapi, integ)(P)
+        for _ in range(6):
+            (ti.do_advance_graph if graph else ti.do_advance)(data, 1e-3)
+        assert ti.iteration == 6 and abs(data.time - 6e-3) < 1e-14
+        res.append(get_state(data))
+    assert rel(res[0], res[1]) < 1e-14
