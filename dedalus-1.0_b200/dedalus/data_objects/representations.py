@@ -72,6 +72,7 @@ class FourierRepresentation(Representation):
         # kernels, cleared whenever the buffer is handed to the caller, who may write to it);
         # lets the RHS skip mask passes and the RK sweep visit the retained modes only
         self._clean = True
+        self._checked = False       # _clean is False and a device check has confirmed modes outside the mask
         self._curr_space = "kspace"
         self.integrating_factor = None
         self.fwd_count = 0
@@ -90,6 +91,7 @@ class FourierRepresentation(Representation):
         """The k-space buffer.  Handing it out means the caller may modify it: the
         'zero outside the mask' knowledge is dropped (internal code uses _k)."""
         self._clean = False
+        self._checked = False
         return self._k
 
     @property
@@ -107,6 +109,7 @@ class FourierRepresentation(Representation):
         elif space == "kspace":
             target = self._k
             self._clean = isinstance(data, (float, complex, int)) and data == 0
+            self._checked = False
         else:
             raise KeyError("space must be either xspace or kspace.")
         if isinstance(data, (float, complex, int)):
@@ -187,6 +190,34 @@ class FourierRepresentation(Representation):
 
     dealias_23 = dealias
     dealias_23_cython = dealias
+
+    def verify_clean(self):
+        """Re-establish the 'zero outside the dealias mask' knowledge after the buffer was handed
+        to the caller: one device pass over the masked-out slabs and one host read.  The
+        integrators call it before a step so that states that ARE dealiased (every state that came
+        out of forward(), div_free(), our own kernels) get the retained-modes-only sweeps and the
+        fused stage kernel; states with genuine content outside the mask (hydro never dealiases
+        its state) keep the full sweeps.  The verdict is cached until the next hand-out."""
+        if self._clean or self._checked or self._curr_space != "kspace":
+            return self._clean
+        pl = self._plan
+        dirty = torch.zeros((), dtype=torch.bool, device=self._k.device)
+        for name, keep in pl.keep_np.items():
+            axis = self.ktrans[name]
+            if axis == 0 and pl.nranks > 1:
+                keep = keep[pl.krows]
+            idx = np.nonzero(~keep)[0]
+            if len(idx):
+                sel = self._k.index_select(axis, torch.as_tensor(idx, device=self._k.device))
+                dirty |= (sel != 0).any()
+        if pl.nranks > 1:
+            import torch.distributed as dist
+            flag = dirty.to(torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            dirty = flag > 0
+        self._clean = not bool(dirty.item())
+        self._checked = True
+        return self._clean
 
     def zero_nyquist(self):
         """Zero the Nyquist planes (representations.py:442-455)."""

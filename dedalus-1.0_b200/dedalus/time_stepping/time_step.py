@@ -46,6 +46,15 @@ def _mark(sd, clean):
         c._clean = clean
 
 
+def _settle(sd):
+    """Before a step: components whose buffer was handed out since the last step get their
+    'dealiased' bit re-checked on the device (FourierRepresentation.verify_clean)."""
+    for _, _, c in sd.components():
+        c.require_space("kspace")
+        if not c._clean and not c._checked:
+            c.verify_clean()
+
+
 def _plan_of(sd):
     return next(sd.components())[2]._plan
 
@@ -244,6 +253,7 @@ class RK2mid(RKBase):
         self.deriv2 = self.RHS.create_fields(0.)
 
     def do_advance(self, data, dt):
+        _settle(data)
         data2, k1, k2 = self.data2, self.deriv1, self.deriv2
         self.RHS.RHS(data, k1)
         self._stage(_lib.ETD1, data, data2, k1, None, k1, dt / 2.)        # a_n (euler where IF is None)
@@ -264,6 +274,7 @@ class RK2trap(RKBase):
         self.deriv2 = self.RHS.create_fields(0.)
 
     def do_advance(self, data, dt):
+        _settle(data)
         k1, k2 = self.deriv1, self.deriv2
         self.RHS.RHS(data, k1)
         self._stage(_lib.ETD1, data, data, k1, None, k1, dt)
@@ -333,8 +344,7 @@ class RK4(RKBase):
 
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
-        for _, _, c in data.components():
-            c.require_space("kspace")
+        _settle(data)
         if self._fusable(data):
             return self._advance_fused(data, dt)
         aux = list(R.aux_eqns.values())
@@ -379,6 +389,7 @@ class CrankNicholsonVisc(TimeStepBase):
         self._coeff = None
 
     def do_advance(self, data, dt):
+        _settle(data)
         self.RHS.RHS(data, self.deriv)
         if self._coeff is None:
             self._coeff = _if_coefficients(self.deriv)

@@ -349,3 +349,39 @@ def test_cuda_graph_replay_equals_eager_steps(physics, shape, integ):
         assert ti.iteration == 6 and abs(data.time - 6e-3) < 1e-14
         res.append(get_state(data))
     assert rel(res[0], res[1]) < 1e-14
+
+
+def test_dealiased_flag_is_reestablished_and_junk_is_kept():
+    """States handed to the caller lose their 'dealiased' bit; the integrators re-check it on the device.
+    A dealiased hydro state then takes the retained-only / fused path; a state with content outside
+    the mask (which hydro never removes) keeps evolving it by the viscous factor, as the
+    reference does.  Both must match the oracle."""
+    import torch
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    import dedalus._lib as L
+    shape, params = (32, 32, 32), dict(nu=0.05)
+    for junk in (False, True):
+        Po = oracle_physics("IncompressibleHydro", shape, None, params)
+        do = orc.synthetic_ic(Po, 8)
+        y0 = do.kvector()
+        if junk:
+            y0[:, 14, 3, 2] = 0.3 - 0.1j          # |ky| = 14 >= 2/3 * 16: outside the mask
+            for j, (_, _, c) in enumerate(do.components()):
+                c.kdata[...] = y0[j]
+        P = dev_physics("IncompressibleHydro", shape, None, params)
+        data = P.create_fields(0.)
+        set_state(data, y0)
+        comps = [c for _, _, c in data.components()]
+        for c in comps:
+            c.kdata                                  # hand the buffers out: knowledge dropped
+        assert not any(c._clean for c in comps)
+        ti, to = tapi.RK4(P), orc.RK4(Po)
+        n0 = L.launch_count()
+        for _ in range(3):
+            ti.do_advance(data, 5e-3)
+            to.do_advance(do, 5e-3)
+        assert all(c._clean for c in comps) == (not junk)
+        assert rel(get_state(data), do.kvector()) < TOL
+        if junk:
+            assert abs(get_state(data)[0, 14, 3, 2]) > 0.05     # still there, only damped
