@@ -61,10 +61,11 @@ template <> struct XFac<1024> { static constexpr bool ok = true; static constexp
 template <int N> constexpr int xfac_P(int s) { return s == 0 ? 1 : xfac_P<N>(s - 1) * XFac<N>::radix(s - 1); }
 
 // 16-byte element e of a pencil lives at swizzled slot xsw(e): a permutation inside aligned
-// groups of 8 elements (one 128-byte bank row)
+// groups of 8 elements (one 128-byte bank row), linear over GF(2).  With bits 3-5 and 6-8 folded
+// into the low three bits every access pattern of every stage (strides N/R0, 2R, 2, ...; 16- and
+// 8-byte accesses) is conflict-free for N = 128 ... 1024 (profiles/xfused_banks.py).
 template <int N> DDL_HD int xsw(int e) {
-    constexpr int Q0 = N / XFac<N>::radix(0);
-    return e ^ ((e / Q0) & 7) ^ ((e >> 3) & 1);
+    return e ^ ((e >> 3) & 7) ^ ((e >> 6) & 7);
 }
 
 // ---------------------------------------------------------------------------------------

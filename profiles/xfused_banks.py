@@ -66,11 +66,56 @@ def analyse(N, radices, NP, NT, sw, verbose=True):
         res[name]=(w,wi)
     return res
 
-N=512
-cands={
- 'none': lambda e:e,
- 'q5': lambda e: e^((e>>5)&7),
- 'q5b3': lambda e: e^((e>>5)&7)^((e>>3)&1),
-}
-for nm,sw in cands.items():
+if __name__ == "__main__":
+  N=512
+  cands={
+   'none': lambda e:e,
+   'q5': lambda e: e^((e>>5)&7),
+   'q5b3': lambda e: e^((e>>5)&7)^((e>>3)&1),
+   'b3b6 (adopted)': lambda e: e^((e>>3)&7)^((e>>6)&7),
+  }
+  for nm,sw in cands.items():
     print(nm, analyse(512,[16,16],6,288,sw))
+
+
+def report(N, radices):
+    sw = lambda e: e ^ ((e >> 3) & 7) ^ ((e >> 6) & 7)
+    res = analyse_tp(N, radices, sw)
+    print(N, radices, {k: "%d/%d" % v for k, v in res.items()})
+
+
+def analyse_tp(N, radices, sw):
+    """Wavefronts (actual/ideal) per pencil and stage with the kernel's thread mapping: TP = N/R0 threads per pencil,
+    butterfly w = lane + it*TP, b = w // P, q = w % P."""
+    TP = N // radices[0]
+    P = 1
+    out = {}
+    for s, R in enumerate(radices):
+        M = N // P
+        Q = M // R
+        items = N // R
+        w_act = w_id = 0
+        for w0 in range(0, items, TP):
+            lanes = list(range(w0, min(w0 + TP, items)))
+            for warp0 in range(0, len(lanes), 32):
+                grp = lanes[warp0:warp0 + 32]
+                for j in range(R):
+                    units = []
+                    for w in grp:
+                        b, q = w // P, w % P
+                        units.append(sw(q * M + b + j * Q))
+                    units += [None] * (32 - len(units))
+                    w_act += wf128(units)
+                    w_id += len(grp) / 8.0
+        out["stage%d(R=%d)" % (s, R)] = (w_act, int(w_id))
+        P *= R
+    return out
+
+
+if __name__ == "__main__":
+    for N, rad in ((512, [16, 16]), (256, [16, 8]), (128, [8, 8]), (1024, [16, 8, 4]), (1024, [16, 16, 2]), (1024, [8, 8, 8]),
+                   (1024, [16, 4, 8]), (1024, [4, 16, 8]), (1024, [32, 16])):
+        try:
+            report(N, rad)
+        except Exception as e:
+            print(N, rad, "n/a", e)
