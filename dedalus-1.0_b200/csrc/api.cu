@@ -756,21 +756,25 @@ static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* cons
 }
 
 template <class PHYS>
-static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_rk4_fuse* fu,
+static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_stage_fuse* fu,
                         ddl_stream_t st) {
     AssembleStageF<PHYS> f;
     const long long count = fill_assemble<PHYS>(pl, f.a, E, state, nullptr, pc);
     for (int c = 0; c < PHYS::NC; ++c) {
-        f.y[c] = (const cplx*)fu->y[c]; f.total[c] = (cplx*)fu->total[c]; f.out[c] = (cplx*)fu->out[c];
+        f.y[c] = (const cplx*)fu->y[c]; f.out[c] = (cplx*)fu->out[c];
+        f.total[c] = fu->total ? (cplx*)fu->total[c] : nullptr;
+        f.d1[c] = fu->deriv1 ? (const cplx*)fu->deriv1[c] : nullptr;
+        f.kout[c] = fu->k_out ? (cplx*)fu->k_out[c] : nullptr;
         f.coeff[c] = fu->coeff ? fu->coeff[c] : 0.0;
     }
+    f.kind = fu->kind; f.has_d1 = fu->deriv1 != nullptr; f.has_kout = fu->k_out != nullptr;
     f.vo = fu->visc_order; f.first = fu->first; f.last = fu->last; f.twod = pl->geom.twod;
     f.dt = fu->dt_step; f.wdiv = fu->wdiv;
     return launch_items(f, count, st, "assemble_stage");
 }
 
 static int assemble_rk4_any(ddl_plan* pl, int code, void* const* E, void* const* state, const PhysConst& pc,
-                            const ddl_rk4_fuse* fu, ddl_stream_t st) {
+                            const ddl_stage_fuse* fu, ddl_stream_t st) {
     switch (code) {
         case 0: return assemble_rk4<Hydro2C>(pl, E, state, pc, fu, st);
         case 1: return assemble_rk4<Bouss2C>(pl, E, state, pc, fu, st);
@@ -793,6 +797,14 @@ static int assemble_any(ddl_plan* pl, int code, void* const* E, void* const* sta
     }
 }
 
+static int check_fuse(const ddl_stage_fuse* fu) {
+    if (!fu || !fu->y || !fu->out) { set_error("fused stage: incomplete descriptor"); return -1; }
+    if (fu->kind < DDL_EULER || fu->kind > DDL_FUSE_CN) { set_error("fused stage: bad kind %d", fu->kind); return -1; }
+    if (fu->kind == DDL_FUSE_RK4 && !fu->total) { set_error("fused RK4 stage needs the total arrays"); return -1; }
+    if ((fu->kind == DDL_ETD2RK1 || fu->kind == DDL_ETD2RK2) && !fu->deriv1) { set_error("fused ETD2 stage needs deriv1"); return -1; }
+    return 0;
+}
+
 static int check_physics(const ddl_plan* pl, int physics, const ddl_phys_params* prm) {
     if (physics < 0 || physics > 2) { set_error("unknown physics id %d", physics); return -1; }
     if (physics == DDL_BOUSSINESQ && (prm->boussinesq_dir < 0 || prm->boussinesq_dir >= pl->ndim)) {
@@ -803,7 +815,7 @@ static int check_physics(const ddl_plan* pl, int physics, const ddl_phys_params*
 }
 
 static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
-                    void* work, size_t work_bytes, int flags, const ddl_rk4_fuse* fuse, void* stream) {
+                    void* work, size_t work_bytes, int flags, const ddl_stage_fuse* fuse, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
     int ni, no, code;
     DDL_TRY(need_one_rank(pl, "ddl_rhs"));
@@ -846,9 +858,9 @@ extern "C" int ddl_rhs(ddl_plan* pl, int physics, const ddl_phys_params* prm, vo
     return rhs_impl(pl, physics, prm, state, deriv, work, work_bytes, flags, nullptr, stream);
 }
 
-extern "C" int ddl_rhs_rk4(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* work,
-                           size_t work_bytes, int flags, const ddl_rk4_fuse* fuse, void* stream) {
-    if (!fuse || !fuse->y || !fuse->total || !fuse->out) { set_error("ddl_rhs_rk4: incomplete stage descriptor"); return -1; }
+extern "C" int ddl_rhs_stage(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* work,
+                           size_t work_bytes, int flags, const ddl_stage_fuse* fuse, void* stream) {
+    DDL_TRY(check_fuse(fuse));
     return rhs_impl(pl, physics, prm, state, nullptr, work, work_bytes, flags, fuse, stream);
 }
 
@@ -923,12 +935,12 @@ extern "C" int ddl_slab_zfwd(ddl_plan* pl, int nf, void* const* ks_in, void* con
     DDL_TRY(need_3d(pl));
     return phase_zfwd(pl, nf, (const void* const*)ks_in, out, full_out != 0, (ddl_stream_t)stream);
 }
-extern "C" int ddl_slab_assemble_rk4(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* e_in, void* const* state,
-                                     const ddl_rk4_fuse* fuse, void* stream) {
+extern "C" int ddl_slab_assemble_stage(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* e_in, void* const* state,
+                                     const ddl_stage_fuse* fuse, void* stream) {
     int ni, no, code;
     DDL_TRY(need_3d(pl));
     DDL_TRY(check_physics(pl, physics, prm));
-    if (!fuse || !fuse->y || !fuse->total || !fuse->out) { set_error("ddl_slab_assemble_rk4: incomplete stage descriptor"); return -1; }
+    DDL_TRY(check_fuse(fuse));
     phys_counts(3, physics, ni, no, code);
     return assemble_rk4_any(pl, code, e_in, state, phys_const(prm), fuse, (ddl_stream_t)stream);
 }

@@ -99,6 +99,36 @@ DDL_HD cplx etd1_step(cplx s, cplx d, double Z, double f0, double f1, double dt)
     return mk(s.x * f0 + d.x * a, s.y * f0 + d.y * a);
 }
 
+// One component of one mode: the update of stage kind `kind` given the start value s, the
+// derivative(s) and the phi functions of Z.  Shared by the plain sweep (StageF) and by the sweep
+// fused with the spectral assembly (AssembleStageF), so that both are the same arithmetic.
+//   EULER / ETD1 / CN: d1 = derivative;  ETD2RK1/2: d1 = first, d2 = second derivative;
+//   RK4: d1 = k_i, `total` = running weighted sum (read unless first, written unless last)
+DDL_HD cplx stage_apply(int kind, cplx s, cplx d1, cplx d2, cplx* total, int first, int last, double wdiv, double Z,
+                        double f0, double f1, double f2, double dt, double IF) {
+    if (kind == SK_EULER) return mk(s.x + dt * d1.x, s.y + dt * d1.y);
+    if (kind == SK_ETD1) return etd1_step(s, d1, Z, f0, f1, dt);
+    if (kind == SK_ETD2RK1) {
+        const double w = (Z == 0.0) ? dt / 2.0 : f2 * dt;
+        return mk(s.x + (d2.x - d1.x) * w, s.y + (d2.y - d1.y) * w);
+    }
+    if (kind == SK_ETD2RK2) {
+        if (Z == 0.0) return mk(s.x + dt * d2.x, s.y + dt * d2.y);
+        const double w2 = 2.0 * f2 * dt, w1 = f1 * dt;
+        return mk(s.x * f0 + (d2.x - d1.x) * w2 + d1.x * w1, s.y * f0 + (d2.y - d1.y) * w2 + d1.y * w1);
+    }
+    if (kind == SK_RK4) {
+        cplx t = mk(d1.x / wdiv, d1.y / wdiv);
+        if (!first) { const cplx o = *total; t = mk(o.x + t.x, o.y + t.y); }
+        if (!last) *total = t;
+        return etd1_step(s, last ? t : d1, Z, f0, f1, dt);
+    }
+    // SK_CN
+    const double top = 1.0 / dt - 0.5 * IF, bottom = 1.0 / dt + 0.5 * IF;
+    const double r1 = top / bottom, r2 = 1.0 / bottom;
+    return mk(r1 * s.x + r2 * d1.x, r1 * s.y + r2 * d1.y);
+}
+
 struct StageF {
     StageArgs a;
     DDL_HD void operator()(long long i) const {
@@ -128,37 +158,10 @@ struct StageF {
                 Z = -(co * pw) * a.dt;
                 if (Z != 0.0 && a.kind != SK_CN) phi_funcs(Z, a.g.twod, f0, f1, f2);
             }
-            const double dt = a.dt;
-            if (a.kind == SK_EULER) {
-                cplx s = a.start[c][i], d = a.d1[c][i];
-                a.out[c][i] = mk(s.x + dt * d.x, s.y + dt * d.y);
-            } else if (a.kind == SK_ETD1) {
-                a.out[c][i] = etd1_step(a.start[c][i], a.d1[c][i], Z, f0, f1, dt);
-            } else if (a.kind == SK_ETD2RK1) {
-                cplx s = a.start[c][i], p = a.d1[c][i], q = a.d2[c][i];
-                const double w = (Z == 0.0) ? dt / 2.0 : f2 * dt;
-                a.out[c][i] = mk(s.x + (q.x - p.x) * w, s.y + (q.y - p.y) * w);
-            } else if (a.kind == SK_ETD2RK2) {
-                cplx s = a.start[c][i], p = a.d1[c][i], q = a.d2[c][i];
-                if (Z == 0.0) {
-                    a.out[c][i] = mk(s.x + dt * q.x, s.y + dt * q.y);
-                } else {
-                    const double w2 = 2.0 * f2 * dt, w1 = f1 * dt;
-                    a.out[c][i] = mk(s.x * f0 + (q.x - p.x) * w2 + p.x * w1, s.y * f0 + (q.y - p.y) * w2 + p.y * w1);
-                }
-            } else if (a.kind == SK_RK4) {
-                cplx kk = a.d1[c][i];
-                cplx t = mk(kk.x / a.wdiv, kk.y / a.wdiv);
-                if (!a.first) { cplx o = a.total[c][i]; t = mk(o.x + t.x, o.y + t.y); }
-                if (!a.last) a.total[c][i] = t;
-                a.out[c][i] = etd1_step(a.start[c][i], a.last ? t : kk, Z, f0, f1, dt);
-            } else {  // SK_CN
-                const double IF = co * pw;
-                const double top = 1.0 / dt - 0.5 * IF, bottom = 1.0 / dt + 0.5 * IF;
-                const double r1 = top / bottom, r2 = 1.0 / bottom;
-                cplx s = a.start[c][i], d = a.d1[c][i];
-                a.out[c][i] = mk(r1 * s.x + r2 * d.x, r1 * s.y + r2 * d.y);
-            }
+            const bool two = (a.kind == SK_ETD2RK1 || a.kind == SK_ETD2RK2);
+            const cplx d2 = two ? a.d2[c][i] : mk(0.0, 0.0);
+            a.out[c][i] = stage_apply(a.kind, a.start[c][i], a.d1[c][i], d2, a.kind == SK_RK4 ? &a.total[c][i] : nullptr,
+                                      a.first, a.last, a.wdiv, Z, f0, f1, f2, a.dt, co * pw);
         }
     }
 };
@@ -228,19 +231,21 @@ struct AssembleF {
     }
 };
 
-// Spectral assembly fused with one stage of the restated RK4 (ddl_rk4_stage): the derivative k
-// is formed in registers from the product spectra and consumed at once,
-//   total = (first ? 0 : total) + k / wdiv ;  out = S(y, last ? total : k, dt)
-// so k never exists in memory (saves its 16 B write + 16 B read per mode and component, and a
-// launch).  Retained modes only: every operand must vanish outside the dealias mask.
+// Spectral assembly fused with a stage update of any integrator: the derivative k is formed in
+// registers from the product spectra and consumed at once (ETD1 / Euler / RK4 / CN: as the
+// derivative; ETD2RK1/2: as the SECOND derivative, the first is read from deriv1), so it is not
+// written unless a later stage needs it (kout, RK2's k1).  Saves the 16 B write + 16 B read per mode
+// and component, and a launch.  Retained modes only: every operand must vanish outside the mask.
 template <class PHYS>
 struct AssembleStageF {
     AssembleF<PHYS> a;
-    const cplx* y[PHYS::NC];
-    cplx* total[PHYS::NC];
+    const cplx* y[PHYS::NC];        // start
+    const cplx* d1[PHYS::NC];       // ETD2RK1/2: first derivative
+    cplx* kout[PHYS::NC];           // optional: store k
+    cplx* total[PHYS::NC];          // RK4
     cplx* out[PHYS::NC];
     double coeff[PHYS::NC];
-    int vo, first, last, twod;
+    int kind, vo, first, last, twod, has_d1, has_kout;
     double dt, wdiv;
     DDL_HD void operator()(long long i) const {
         int j[3];
@@ -265,16 +270,16 @@ struct AssembleStageF {
 #pragma unroll
         for (int c = 0; c < PHYS::NC; ++c) {
             const double co = coeff[c];
-            if (co != lastc) {
+            if (kind != SK_EULER && co != lastc) {
                 lastc = co;
                 Z = -(co * pw) * dt;
-                if (Z != 0.0) phi_funcs(Z, twod, f0, f1, f2);
+                if (Z != 0.0 && kind != SK_CN) phi_funcs(Z, twod, f0, f1, f2);
             }
             const cplx kc = d[c];
-            cplx t = mk(kc.x / wdiv, kc.y / wdiv);
-            if (!first) { const cplx o = total[c][fi]; t = mk(o.x + t.x, o.y + t.y); }
-            if (!last) total[c][fi] = t;
-            out[c][fi] = etd1_step(y[c][fi], last ? t : kc, Z, f0, f1, dt);
+            if (has_kout) kout[c][fi] = kc;
+            const cplx first_d = has_d1 ? d1[c][fi] : kc;
+            out[c][fi] = stage_apply(kind, y[c][fi], first_d, kc, kind == SK_RK4 ? &total[c][fi] : nullptr, first, last, wdiv,
+                                     Z, f0, f1, f2, dt, co * pw);
         }
     }
 };

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("DEDALUS_DDL_LIB") or os.path.join(_HERE, "libddl_b200
 EXPORTS = [
     "ddl_plan_create", "ddl_plan_create_slab", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
     "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_deriv", "ddl_rhs", "ddl_stage",
-    "ddl_rk4_stage", "ddl_cn_step", "ddl_rhs_rk4", "ddl_slab_assemble_rk4", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_zinv", "ddl_slab_yinv",
+    "ddl_rk4_stage", "ddl_cn_step", "ddl_rhs_stage", "ddl_slab_assemble_stage", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_zinv", "ddl_slab_yinv",
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
     "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
@@ -30,10 +30,14 @@ class PhysParams(C.Structure):
                 ("boussinesq_dir", C.c_int), ("reserved", C.c_int)]
 
 
-class RK4Fuse(C.Structure):
-    """include/ddl.h: ddl_rk4_fuse."""
+FUSE_RK4, FUSE_CN = 4, 5
+
+
+class StageFuse(C.Structure):
+    """include/ddl.h: ddl_stage_fuse."""
     _fields_ = [("y", C.c_void_p), ("total", C.c_void_p), ("out", C.c_void_p), ("coeff", C.c_void_p),
-                ("visc_order", C.c_int), ("first", C.c_int), ("last", C.c_int), ("wdiv", C.c_double), ("dt_step", C.c_double)]
+                ("visc_order", C.c_int), ("first", C.c_int), ("last", C.c_int), ("wdiv", C.c_double), ("dt_step", C.c_double),
+                ("kind", C.c_int), ("reserved", C.c_int), ("deriv1", C.c_void_p), ("k_out", C.c_void_p)]
 
 
 class DDLError(RuntimeError):
@@ -54,8 +58,8 @@ def bind_slab(lib):
     lib.ddl_slab_zfwd.argtypes = [vp, i32, vp, vp, i32, vp]
     lib.ddl_slab_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.ddl_dealias.argtypes = [vp, vp, vp]
-    lib.ddl_slab_assemble_rk4.argtypes = [vp, i32, vp, vp, vp, vp, vp]
-    lib.ddl_rhs_rk4.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, i32, vp, vp]
+    lib.ddl_slab_assemble_stage.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.ddl_rhs_stage.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, i32, vp, vp]
     if hasattr(lib, "ddl_p2p_create"):
         lib.ddl_p2p_create.argtypes = [C.POINTER(vp), i32, i32, C.c_size_t, C.c_char_p]
         lib.ddl_p2p_connect.argtypes = [vp, C.c_char_p]

@@ -283,7 +283,7 @@ class SlabPipeline(object):
     def _assemble(self, physics_id, pp, e, state, deriv, fuse, st):
         lib, h = self.lib, self.h
         if fuse is not None:
-            self._check(lib.ddl_slab_assemble_rk4(h, physics_id, pp, _ptrs(e), _ptrs(state), C.byref(fuse), st))
+            self._check(lib.ddl_slab_assemble_stage(h, physics_id, pp, _ptrs(e), _ptrs(state), C.byref(fuse), st))
         else:
             self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(e), _ptrs(state), _ptrs(deriv), st))
 

@@ -139,8 +139,8 @@ class Physics(object):
         return not getattr(self, "_rotation", False) and not self.forcing_functions
 
     def _fused_rhs(self, data, deriv, flags, fuse=None):
-        """deriv = RHS(data).  With `fuse` (an _lib.RK4Fuse; deriv is None) the derivative is
-        consumed in registers by one RK4 stage update instead of being written (ddl_rhs_rk4)."""
+        """deriv = RHS(data).  With `fuse` (an _lib.StageFuse; deriv is None) the derivative is
+        consumed in registers by the integrator's stage update instead of being written (ddl_rhs_stage)."""
         if not self._is_finalized:
             self._finalize()
         if decfg.get("FFT", "dealiasing") not in ("2/3", "2/3 cython"):
@@ -170,7 +170,7 @@ class Physics(object):
                             bool(flags & _lib.RHS_ZERO_FILL) and fuse is None, fuse=fuse)
         elif fuse is not None:
             w = pl.rhs_workspace(self._physics_id)
-            check(lib.ddl_rhs_rk4(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), w.data_ptr(), w.numel(),
+            check(lib.ddl_rhs_stage(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), w.data_ptr(), w.numel(),
                                   flags & ~_lib.RHS_ZERO_FILL, C.byref(fuse), _plan.current_stream()))
         else:
             w = pl.rhs_workspace(self._physics_id)

@@ -219,6 +219,43 @@ class TimeStepBase(object):
         mylog.info("dt = %10.5e" % dt)
         return dt
 
+    # ---- stage update fused with the spectral assembly of the RHS --------------------------
+    fuse_stages = True      # set False to force the unfused RHS + stage-kernel path (tests compare both)
+
+    def _can_fuse(self, *sds):
+        """ddl_rhs_stage applies: nothing else touches deriv (rotation, forcing, aux equations), the
+        integrating-factor coefficients are known (after the first unfused step), and every operand
+        vanishes outside the dealias mask (the fused sweep visits the retained modes only)."""
+        R = self.RHS
+        if not self.fuse_stages or getattr(self, "_coeff", None) is None or not hasattr(R, "_fused_rhs"):
+            return False
+        if R.aux_eqns or not R.can_fuse_stage():
+            return False
+        return _all_clean(*sds)
+
+    def _stage_fused(self, kind, state_in, start, out, dt_step, deriv1=None, k_out=None, total=None, wdiv=1., first=0, last=0):
+        """out = stage(kind)(start, RHS(state_in)[, deriv1]) with the derivative consumed in registers
+        (include/ddl.h: ddl_rhs_stage); k_out: also store it (a later stage needs it)."""
+        R = self.RHS
+        coeff, order = self._coeff
+        keep = [_lib.ptr_array(_kspace_tensors(start)), _lib.ptr_array(_kspace_tensors(out))]
+        opt = []
+        for sd in (total, deriv1, k_out):
+            if sd is None:
+                opt.append(None)
+            else:
+                arr = _lib.ptr_array(_kspace_tensors(sd))
+                keep.append(arr)
+                opt.append(C.cast(arr, C.c_void_p))
+        fuse = _lib.StageFuse(C.cast(keep[0], C.c_void_p), opt[0], C.cast(keep[1], C.c_void_p), C.cast(coeff, C.c_void_p),
+                              int(order), int(first), int(last), float(wdiv), float(dt_step), int(kind), 0, opt[1], opt[2])
+        R._fused_rhs(state_in, None, R._rhs_flags(), fuse=fuse)
+        for sd in (out, total, k_out):
+            if sd is not None:
+                _mark(sd, True)
+        if k_out is not None:
+            k_out.set_time(state_in.time)
+
     # ---- device stage launches ---------------------------------------------------------
     def _stage(self, kind, start, out, d1, d2, if_from, dt):
         s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
@@ -255,7 +292,17 @@ class RK2mid(RKBase):
     def do_advance(self, data, dt):
         _settle(data)
         data2, k1, k2 = self.data2, self.deriv1, self.deriv2
+        if self._can_fuse(data, data2, k1):
+            self._stage_fused(_lib.ETD1, data, data, data2, dt / 2., k_out=k1)              # k1 kept for the second stage
+            data2.set_time(data.time + dt / 2.)
+            self._stage_fused(_lib.ETD2RK2, data2, data, data, dt, deriv1=k1)               # k2 never stored
+            data.set_time(data.time + dt)
+            self.time += dt
+            self.iteration += 1
+            return
         self.RHS.RHS(data, k1)
+        if getattr(self, "_coeff", None) is None:
+            self._coeff = _if_coefficients(k1)
         self._stage(_lib.ETD1, data, data2, k1, None, k1, dt / 2.)        # a_n (euler where IF is None)
         data2.set_time(data.time + dt / 2.)
         self.RHS.RHS(data2, k2)
@@ -276,7 +323,16 @@ class RK2trap(RKBase):
     def do_advance(self, data, dt):
         _settle(data)
         k1, k2 = self.deriv1, self.deriv2
+        if self._can_fuse(data, k1):
+            self._stage_fused(_lib.ETD1, data, data, data, dt, k_out=k1)
+            data.set_time(data.time + dt)
+            self._stage_fused(_lib.ETD2RK1, data, data, data, dt, deriv1=k1)
+            self.time += dt
+            self.iteration += 1
+            return
         self.RHS.RHS(data, k1)
+        if getattr(self, "_coeff", None) is None:
+            self._coeff = _if_coefficients(k1)
         self._stage(_lib.ETD1, data, data, k1, None, k1, dt)
         data.set_time(data.time + dt)
         self.RHS.RHS(data, k2)
@@ -307,26 +363,8 @@ class RK4(RKBase):
         _mark(out, clean)
         _mark(self.total_deriv, clean)
 
-    def _fusable(self, data):
-        """The spectral assembly of the RHS can be fused with the stage update (ddl_rhs_rk4) when
-        nothing else touches deriv and every operand vanishes outside the dealias mask."""
-        R = self.RHS
-        if self._coeff is None or not self.fuse_stages or not hasattr(R, "_fused_rhs") or not R.can_fuse_stage():
-            return False
-        if R.aux_eqns:
-            return False
-        return _all_clean(data, self.total_deriv, self.temp_data)
-
     def _rk4_fused(self, state_in, y, out, wdiv, dt_step, first, last):
-        R = self.RHS
-        ys, ts, os_ = _kspace_tensors(y), _kspace_tensors(self.total_deriv), _kspace_tensors(out)
-        coeff, order = self._coeff
-        pa, pt, po = _lib.ptr_array(ys), _lib.ptr_array(ts), _lib.ptr_array(os_)
-        fuse = _lib.RK4Fuse(C.cast(pa, C.c_void_p), C.cast(pt, C.c_void_p), C.cast(po, C.c_void_p),
-                            C.cast(coeff, C.c_void_p), int(order), int(first), int(last), float(wdiv), float(dt_step))
-        R._fused_rhs(state_in, None, R._rhs_flags(), fuse=fuse)
-        _mark(out, True)
-        _mark(self.total_deriv, True)
+        self._stage_fused(_lib.FUSE_RK4, state_in, y, out, dt_step, total=self.total_deriv, wdiv=wdiv, first=first, last=last)
 
     def _advance_fused(self, data, dt):
         tmp = self.temp_data
@@ -340,12 +378,10 @@ class RK4(RKBase):
         self.time += dt
         self.iteration += 1
 
-    fuse_stages = True      # set False to force the unfused RHS + ddl_rk4_stage path (tests compare both)
-
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
         _settle(data)
-        if self._fusable(data):
+        if self._can_fuse(data, self.total_deriv, self.temp_data):
             return self._advance_fused(data, dt)
         aux = list(R.aux_eqns.values())
         a_old = [a.value for a in aux]
@@ -390,6 +426,12 @@ class CrankNicholsonVisc(TimeStepBase):
 
     def do_advance(self, data, dt):
         _settle(data)
+        if self._can_fuse(data):
+            self._stage_fused(_lib.FUSE_CN, data, data, data, dt)
+            data.set_time(data.time + dt)
+            self.time += dt
+            self.iteration += 1
+            return
         self.RHS.RHS(data, self.deriv)
         if self._coeff is None:
             self._coeff = _if_coefficients(self.deriv)

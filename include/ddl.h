@@ -178,23 +178,32 @@ int ddl_rk4_stage(ddl_plan* plan, int ncomp, void* const* y, void* const* k, voi
                   void* const* out, const double* coeff, int visc_order, double wdiv,
                   double dt_step, int first, int last, int flags, void* stream);
 
-/* The RHS with the spectral assembly fused into one RK4 stage: deriv (k_i) is formed in registers
- * and consumed by the stage update of ddl_rk4_stage, never written.  Only valid when state, y and
- * total vanish outside the dealias mask (what DDL_STAGE_RETAINED_ONLY asserts): the sweep visits
- * the retained modes only.  ddl_slab_assemble_rk4 is the same tail for the slab phases. */
-typedef struct ddl_rk4_fuse {
-    void* const* y;       /* step base state (ncomp k-space arrays) */
-    void* const* total;   /* running (k1 + 2k2 + 2k3 + k4)/6 */
-    void* const* out;     /* stage state written (may alias y on the last stage) */
+/* The RHS with the spectral assembly fused into a stage update: the derivative is formed in
+ * registers and consumed by the update (same arithmetic as ddl_stage / ddl_rk4_stage / ddl_cn_step),
+ * written only if k_out is given.  kind: DDL_EULER / DDL_ETD1 (the derivative of this RHS is THE
+ * derivative), DDL_ETD2RK1 / DDL_ETD2RK2 (it is the SECOND one; deriv1 holds the first),
+ * DDL_FUSE_RK4 (ddl_rk4_stage semantics with total / wdiv / first / last), DDL_FUSE_CN.
+ * Only valid when state, y, total, deriv1 vanish outside the dealias mask (what
+ * DDL_STAGE_RETAINED_ONLY asserts): the sweep visits the retained modes only.
+ * ddl_slab_assemble_stage is the same tail for the slab phases. */
+enum { DDL_FUSE_RK4 = 4, DDL_FUSE_CN = 5 };
+typedef struct ddl_stage_fuse {
+    void* const* y;       /* start state of the update (ncomp k-space arrays) */
+    void* const* total;   /* RK4: running (k1 + 2k2 + 2k3 + k4)/6, else NULL */
+    void* const* out;     /* state written (may alias y) */
     const double* coeff;  /* nu / kappa / eta per component (0: no integrating factor) */
     int visc_order;
-    int first, last;
-    double wdiv, dt_step;
-} ddl_rk4_fuse;
-int ddl_rhs_rk4(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* state, void* work,
-                size_t work_bytes, int flags, const ddl_rk4_fuse* fuse, void* stream);
-int ddl_slab_assemble_rk4(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* e_in,
-                          void* const* state, const ddl_rk4_fuse* fuse, void* stream);
+    int first, last;      /* RK4 */
+    double wdiv, dt_step; /* RK4 weight divisor; step of this update */
+    int kind;
+    int reserved;
+    void* const* deriv1;  /* ETD2RK1/2: first derivative (read), else NULL */
+    void* const* k_out;   /* optional: where to store the derivative formed here, else NULL */
+} ddl_stage_fuse;
+int ddl_rhs_stage(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* state, void* work,
+                  size_t work_bytes, int flags, const ddl_stage_fuse* fuse, void* stream);
+int ddl_slab_assemble_stage(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* e_in,
+                            void* const* state, const ddl_stage_fuse* fuse, void* stream);
 
 /* restated CrankNicholsonVisc (time_step.py:486-506): y = (top/bottom) y + k / bottom */
 int ddl_cn_step(ddl_plan* plan, int ncomp, void* const* y, void* const* k, const double* coeff,

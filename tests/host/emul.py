@@ -105,26 +105,39 @@ class EmulPlan:
                                     flags, None))
         return np.stack(deriv), np.stack(state)
 
-    def rhs_rk4(self, physics, params, state, y, total, coeff, vo, wdiv, dt, first, last, flags=0):
-        """ddl_rhs_rk4: returns (out, total) after the fused assembly + stage update."""
+    def rhs_stage(self, physics, params, state, kind, y, coeff, vo, dt, total=None, deriv1=None, want_k=False, wdiv=1.0,
+                  first=0, last=0, flags=0):
+        """ddl_rhs_stage: returns dict(out=..., total=..., k=...) after the fused assembly + stage update."""
         class Fuse(C.Structure):
             _fields_ = [("y", C.c_void_p), ("total", C.c_void_p), ("out", C.c_void_p), ("coeff", C.c_void_p),
-                        ("visc_order", C.c_int), ("first", C.c_int), ("last", C.c_int), ("wdiv", C.c_double), ("dt_step", C.c_double)]
+                        ("visc_order", C.c_int), ("first", C.c_int), ("last", C.c_int), ("wdiv", C.c_double), ("dt_step", C.c_double),
+                        ("kind", C.c_int), ("reserved", C.c_int), ("deriv1", C.c_void_p), ("k_out", C.c_void_p)]
         pid = self.PHYS[physics]
         pp = PhysParams(params.get("rho0", 1.0), params.get("g", 1.0), params.get("alpha_t", 1.0),
                         params.get("beta", 1.0), {"x": 0, "y": 1, "z": 2}[params.get("boussinesq_direction", "z")], 0)
-        state = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in state]
-        y = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in y]
-        total = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in total]
+        cp = lambda arrs: [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in arrs]
+        state, y = cp(state), cp(y)
         out = [np.zeros_like(s) for s in state]
         co = np.ascontiguousarray(coeff, dtype=np.float64)
         w = self._ws(self.lib.ddl_rhs_workspace_bytes(self.plan, pid))
-        pa, pt, po = _pa(y), _pa(total), _pa(out)
-        fu = Fuse(C.cast(pa, C.c_void_p), C.cast(pt, C.c_void_p), C.cast(po, C.c_void_p), _p(co), vo, int(first), int(last),
-                  float(wdiv), float(dt))
-        self.check(self.lib.ddl_rhs_rk4(self.plan, pid, C.byref(pp), _pa(state), _p(w), C.c_size_t(w.nbytes), flags,
-                                        C.byref(fu), None))
-        return np.stack(out), np.stack(total)
+        keep = [_pa(y), _pa(out)]
+        res = {}
+        opt = []
+        for name, arrs in (("total", total), ("deriv1", deriv1), ("k", [np.zeros_like(s) for s in state] if want_k else None)):
+            if arrs is None:
+                opt.append(None)
+            else:
+                arrs = cp(arrs)
+                res[name] = arrs
+                pa = _pa(arrs)
+                keep.append(pa)
+                opt.append(C.cast(pa, C.c_void_p))
+        fu = Fuse(C.cast(keep[0], C.c_void_p), opt[0], C.cast(keep[1], C.c_void_p), _p(co), vo, int(first), int(last),
+                  float(wdiv), float(dt), int(kind), 0, opt[1], opt[2])
+        self.check(self.lib.ddl_rhs_stage(self.plan, pid, C.byref(pp), _pa(state), _p(w), C.c_size_t(w.nbytes), flags,
+                                          C.byref(fu), None))
+        res["out"] = out
+        return {k: np.stack(v) for k, v in res.items()}
 
     def rk4_stage(self, y, k, total, coeff, vo, wdiv, dt, first, last, flags=1):
         y = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in y]
@@ -134,6 +147,12 @@ class EmulPlan:
         self.check(self.lib.ddl_rk4_stage(self.plan, len(y), _pa(y), _pa(list(k)), _pa(total), _pa(out), _p(co), vo,
                                           C.c_double(wdiv), C.c_double(dt), int(first), int(last), flags, None))
         return np.stack(out), np.stack(total)
+
+    def cn_step(self, y, k, coeff, vo, dt, flags=1):
+        y = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in y]
+        co = np.ascontiguousarray(coeff, dtype=np.float64)
+        self.check(self.lib.ddl_cn_step(self.plan, len(y), _pa(y), _pa(list(k)), _p(co), vo, C.c_double(dt), flags, None))
+        return np.stack(y)
 
     def stage(self, kind, start, d1, d2, coeff, vo, dt, flags=0):
         n = len(start)

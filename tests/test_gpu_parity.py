@@ -385,3 +385,31 @@ def test_dealiased_flag_is_reestablished_and_junk_is_kept():
         assert rel(get_state(data), do.kvector()) < TOL
         if junk:
             assert abs(get_state(data)[0, 14, 3, 2]) > 0.05     # still there, only damped
+
+
+@pytest.mark.parametrize("integ", ["RK2mid", "RK2trap", "CrankNicholsonVisc"])
+@pytest.mark.parametrize("physics,shape,params", [("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3, eta=0.2)),
+                                                  ("BoussinesqHydro", (32, 64), dict(nu=1e-3, kappa=2e-3))])
+def test_fused_stage_integrators_equal_unfused_and_oracle(integ, physics, shape, params):
+    """RK2mid / RK2trap / CN with the assembly fused into their stage updates (from the second step on)
+    == the unfused launches, and both match the oracle (RK2mid / RK2trap are pinned by the reference)."""
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    Po = oracle_physics(physics, shape, None, params)
+    do = orc.synthetic_ic(Po, 12)
+    y0 = do.kvector()
+    res = []
+    for fuse in (True, False):
+        P = dev_physics(physics, shape, None, params)
+        data = P.create_fields(0.)
+        set_state(data, y0)
+        ti = getattr(tapi, integ)(P)
+        ti.fuse_stages = fuse
+        for _ in range(4):
+            ti.do_advance(data, 2e-3)
+        res.append(get_state(data))
+    assert rel(res[0], res[1]) < 1e-14
+    to = orc.INTEGRATORS[integ](Po)
+    for _ in range(4):
+        to.do_advance(do, 2e-3)
+    assert rel(res[0], do.kvector()) < TOL

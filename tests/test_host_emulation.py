@@ -134,24 +134,55 @@ def test_emulated_retained_only_sweep_equals_full_sweep(lib, shape):
             assert np.all(a[~keep] == 0)
 
 
-@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (8, 16, 16)), ("BoussinesqHydro", (16, 8, 16)),
-                                           ("IncompressibleHydro", (16, 32)), ("IncompressibleMHD", (16, 16))])
-@pytest.mark.parametrize("first,last", [(1, 0), (0, 0), (0, 1)])
-def test_emulated_fused_rk4_stage_equals_rhs_then_stage(lib, physics, shape, first, last):
-    """ddl_rhs_rk4 (derivative consumed in registers) == ddl_rhs followed by ddl_rk4_stage."""
+FUSE_SHAPES = [("IncompressibleMHD", (8, 16, 16)), ("BoussinesqHydro", (16, 8, 16)), ("IncompressibleHydro", (16, 32)),
+               ("IncompressibleMHD", (16, 16))]
+
+
+def _fuse_case(lib, physics, shape):
     g = orc.Grid(shape, None)
     pl = emul.EmulPlan(lib, g)
     kw = {"direction": "y" if len(shape) == 2 else "z"} if physics == "BoussinesqHydro" else {}
     P = orc.PHYSICS[physics](shape, None, "2/3 cython", **kw)
     state = list(orc.synthetic_ic(P, 3).kvector())
     y = list(orc.synthetic_ic(P, 4).kvector())
-    total = list(orc.synthetic_ic(P, 6).kvector())
+    other = list(orc.synthetic_ic(P, 6).kvector())
     params = {"boussinesq_direction": "y" if len(shape) == 2 else "z"}
-    n = len(state)
-    coeff = ([0.0, 0.01, 0.3, 0.3, 0.02, 0.0])[:n]
+    coeff = ([0.0, 0.01, 0.3, 0.3, 0.02, 0.0])[:len(state)]
     k, _ = pl.rhs(physics, params, state, flags=1)
-    ref_out, ref_total = pl.rk4_stage(y, list(k), total, coeff, 1, 3.0, 0.05, first, last)
-    out, tot = pl.rhs_rk4(physics, params, state, y, total, coeff, 1, 3.0, 0.05, first, last)
-    assert rel(out, ref_out) < 1e-15
+    return pl, params, state, y, other, coeff, list(k)
+
+
+@pytest.mark.parametrize("physics,shape", FUSE_SHAPES)
+@pytest.mark.parametrize("first,last", [(1, 0), (0, 0), (0, 1)])
+def test_emulated_fused_rk4_stage_equals_rhs_then_stage(lib, physics, shape, first, last):
+    """ddl_rhs_stage (derivative consumed in registers) == ddl_rhs followed by ddl_rk4_stage."""
+    pl, params, state, y, total, coeff, k = _fuse_case(lib, physics, shape)
+    ref_out, ref_total = pl.rk4_stage(y, k, total, coeff, 1, 3.0, 0.05, first, last)
+    r = pl.rhs_stage(physics, params, state, 4, y, coeff, 1, 0.05, total=total, wdiv=3.0, first=first, last=last)
+    assert rel(r["out"], ref_out) < 1e-15
     if not last:
-        assert rel(tot, ref_total) < 1e-15
+        assert rel(r["total"], ref_total) < 1e-15
+
+
+@pytest.mark.parametrize("physics,shape", FUSE_SHAPES)
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_emulated_fused_etd_stages_equal_rhs_then_stage(lib, physics, shape, kind):
+    """Fused EULER / ETD1 (derivative also stored, as RK2's first stage needs) and ETD2RK1 / ETD2RK2 (derivative
+    of this RHS is the second one, the first is read) == ddl_rhs followed by ddl_stage (retained-only sweep)."""
+    pl, params, state, y, d_first, coeff, k = _fuse_case(lib, physics, shape)
+    if kind in (0, 1):
+        ref = np.stack(pl.stage(kind, y, k, None, coeff, 1, 0.05, flags=1))
+        r = pl.rhs_stage(physics, params, state, kind, y, coeff, 1, 0.05, want_k=True)
+        assert rel(r["k"], np.stack(k)) < 1e-15
+    else:
+        ref = np.stack(pl.stage(kind, y, d_first, k, coeff, 1, 0.05, flags=1))
+        r = pl.rhs_stage(physics, params, state, kind, y, coeff, 1, 0.05, deriv1=d_first)
+    assert rel(r["out"], ref) < 1e-15
+
+
+@pytest.mark.parametrize("physics,shape", FUSE_SHAPES)
+def test_emulated_fused_cn_step_equals_rhs_then_cn(lib, physics, shape):
+    pl, params, state, y, _, coeff, k = _fuse_case(lib, physics, shape)
+    ref = pl.cn_step(state, k, coeff, 1, 0.05)                 # CN updates the state it evaluated the RHS on
+    r = pl.rhs_stage(physics, params, state, 5, state, coeff, 1, 0.05)
+    assert rel(r["out"], ref) < 1e-15
