@@ -30,7 +30,7 @@ A_STAGE_MHD3D = 1920.0     # algorithmic bytes per mode-stage (SURVEY.md section
 ALGO_BYTES_PER_MODE = {
     "z_inv": 6 * 32.0, "y_inv": 6 * 32.0, "x_fused": 15 * 32.0, "y_fwd": 9 * 32.0, "z_fwd": 9 * 32.0,
     "stage": 30 * 16.0, "assemble": 0.0, "mask": 0.0,
-    "assemble_stage": 30 * 16.0,      # spectral assembly fused into the RK4 stage sweep (ddl_rhs_rk4)
+    "assemble_stage": 30 * 16.0,      # spectral assembly fused into the RK4 stage sweep (ddl_rhs_stage)
 }
 
 

@@ -304,7 +304,7 @@ def test_full_size_properties(physics, n, params):
                                                   ("BoussinesqHydro", (32, 32, 32), dict(nu=1e-3, kappa=1e-3)),
                                                   ("IncompressibleMHD", (64, 64), dict(nu=1e-3, eta=1e-3))])
 def test_rk4_fused_assembly_equals_unfused(physics, shape, params):
-    """RK4 with the spectral assembly fused into the stage update (ddl_rhs_rk4, taken from the second
+    """RK4 with the spectral assembly fused into the stage update (ddl_rhs_stage, taken from the second
     step on when everything is dealiased) == RHS + ddl_rk4_stage, and both match the oracle."""
     import dedalus_oracle as orc
     import dedalus.time_stepping.api as tapi
