@@ -109,8 +109,8 @@ class SlabPipeline(object):
 
     # ------------------------------------------------------------------ p2p arena (RHS pipeline)
     def _p2p_setup(self, nmax):
-        """Arena layout, identical on every rank up to the peer's own k-side size:
-        [nmax x-side fields | nmax k-side fields | flags]."""
+        """Arena data layout (after the flag header, csrc/p2p.cu), identical on every rank up to the
+        peer's own k-side size: [nmax x-side fields | nmax k-side fields]."""
         lib, P, me = self.lib, self.P, self.rank
         el = 16
         blk = self.nzl * self.cx
