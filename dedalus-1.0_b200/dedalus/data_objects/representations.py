@@ -210,11 +210,9 @@ class FourierRepresentation(Representation):
             if len(idx):
                 sel = self._k.index_select(axis, torch.as_tensor(idx, device=self._k.device))
                 dirty |= (sel != 0).any()
-        if pl.nranks > 1:
-            import torch.distributed as dist
-            flag = dirty.to(torch.int32)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            dirty = flag > 0
+        # deliberately rank-local (no collective): ranks may disagree (one of them printed a mode, say) and
+        # then take different local tails (mask / full sweep vs fused sweep); the exchange sequence of the
+        # RHS pipeline is the same on every path, so that is safe - a collective here could deadlock
         self._clean = not bool(dirty.item())
         self._checked = True
         return self._clean
