@@ -1,0 +1,1 @@
+"""dedalus.analysis (B200 backend): see api.py for the public names."""

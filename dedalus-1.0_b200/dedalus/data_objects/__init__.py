@@ -1,0 +1,1 @@
+"""dedalus.data_objects (B200 backend): see api.py for the public names."""

@@ -1,0 +1,1 @@
+"""dedalus.time_stepping (B200 backend): see api.py for the public names."""
