@@ -1,0 +1,1 @@
+"""dedalus.utils (B200 backend): parallelism, timers, logging."""
