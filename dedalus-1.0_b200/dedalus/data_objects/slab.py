@@ -25,6 +25,43 @@ def _ptrs(tensors):
     return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
+def arena_layout(P, me, rows, nzl, cx, nz, nmax, el=16):
+    """Byte offsets of the slab exchange inside the ranks' arenas (pure arithmetic; tests/test_slab_layout.py).
+
+    Every arena's data part is [nmax x-side fields | nmax k-side fields]:
+      x-side field f of any rank : [cy][nzl][cx], rows in owner-major order  (cy = sum(rows))
+      k-side field f of rank r   : [peer][rows[r]][nzl][cx]
+    Returns a dict with, for this rank `me`:
+      xs[f], ks[f]            offsets of its own fields
+      inv[f] = (dst_rank, src_off, dst_off, nbytes) lists: my k-side block s -> rows of `me` in rank s's x-side field f
+      fwd[f] = the mirror: rows of rank s in my x-side field f -> block `me` of rank s's k-side field f
+      zinv_peer[f][s], yfwd_peer[f][s]   block bases (relative to rank s's data base) for the peer-store passes:
+            z pass: row z of my local compact row j goes to  base + (j*nzl + z % nzl)*cx
+            y pass: x-side position p of plane zl goes to     base + (p*nzl + zl)*cx      (base absorbs -cy0[s])
+    """
+    blk = nzl * cx
+    cy = sum(rows)
+    cy0 = [sum(rows[:r]) for r in range(P)]
+    n_xs = cy * blk
+    n_ks = [r * nz * cx for r in rows]
+    xs_total = nmax * n_xs * el
+    order = [(me + i) % P for i in range(P)]            # start with myself, then staggered peers
+    out = {"xs": [f * n_xs * el for f in range(nmax)], "ks": [xs_total + f * n_ks[me] * el for f in range(nmax)],
+           "bytes": xs_total + nmax * n_ks[me] * el, "order": order, "inv": [], "fwd": [], "zinv_peer": [], "yfwd_peer": []}
+    for f in range(nmax):
+        out["inv"].append((order,
+                           [xs_total + (f * n_ks[me] + s * rows[me] * blk) * el for s in order],
+                           [(f * n_xs + cy0[me] * blk) * el for s in order],
+                           [rows[me] * blk * el for s in order]))
+        out["fwd"].append((order,
+                           [(f * n_xs + cy0[s] * blk) * el for s in order],
+                           [xs_total + (f * n_ks[s] + me * rows[s] * blk) * el for s in order],
+                           [rows[s] * blk * el for s in order]))
+        out["zinv_peer"].append([(f * n_xs + cy0[me] * blk) * el for s in range(P)])
+        out["yfwd_peer"].append([xs_total + (f * n_ks[s] + (me * rows[s] - cy0[s]) * blk) * el for s in range(P)])
+    return out
+
+
 class _Done(object):
     def wait(self):
         return True
@@ -112,43 +149,28 @@ class SlabPipeline(object):
         """Arena data layout (after the flag header, csrc/p2p.cu), identical on every rank up to the
         peer's own k-side size: [nmax x-side fields | nmax k-side fields]."""
         lib, P, me = self.lib, self.P, self.rank
-        el = 16
-        blk = self.nzl * self.cx
-        nz_total = self.nzl * P
-        n_ks_of = [r * nz_total * self.cx for r in self.rows]
-        xs_total = nmax * self.n_xs * el
-        data_bytes = xs_total + nmax * self.n_ks * el
+        lay = arena_layout(P, me, self.rows, self.nzl, self.cx, self.nzl * P, nmax)
         ctx = C.c_void_p()
         handle = C.create_string_buffer(64)
-        self._check(lib.ddl_p2p_create(C.byref(ctx), P, me, data_bytes, handle))
+        self._check(lib.ddl_p2p_create(C.byref(ctx), P, me, lay["bytes"], handle))
         gathered = [None] * P
         dist.all_gather_object(gathered, handle.raw, group=self.group)
         self._check(lib.ddl_p2p_connect(ctx, b"".join(gathered)))
         self._p2p = ctx
         self._p2p_nmax = nmax
         base = int(lib.ddl_p2p_base(ctx))
-        self._p2p_xs = [_Raw(base + f * self.n_xs * el) for f in range(nmax)]
-        self._p2p_ks = [_Raw(base + xs_total + f * self.n_ks * el) for f in range(nmax)]
-        cy0_of = [sum(self.rows[:r]) for r in range(P)]
-        order = [(me + i) % P for i in range(P)]
+        self._p2p_xs = [_Raw(base + o) for o in lay["xs"]]
+        self._p2p_ks = [_Raw(base + o) for o in lay["ks"]]
         arr = lambda vals, t: (t * len(vals))(*vals)
         self._p2p_lists = {}
         for f in range(nmax):
-            # inverse: my k-side block s -> rows [cy0(me), +cyl) of rank s's x-side field f
-            src = [xs_total + (f * self.n_ks + s * self.cyl * blk) * el for s in order]
-            dst = [(f * self.n_xs + self.cy0 * blk) * el for s in order]
-            nb = [self.cyl * blk * el for s in order]
-            self._p2p_lists[(f, True)] = (arr(order, C.c_int), arr(src, C.c_int64), arr(dst, C.c_int64), arr(nb, C.c_int64))
-            # forward: rows of rank s in my x-side field f -> block `me` of rank s's k-side field f
-            src = [(f * self.n_xs + cy0_of[s] * blk) * el for s in order]
-            dst = [xs_total + (f * n_ks_of[s] + me * self.rows[s] * blk) * el for s in order]
-            nb = [self.rows[s] * blk * el for s in order]
-            self._p2p_lists[(f, False)] = (arr(order, C.c_int), arr(src, C.c_int64), arr(dst, C.c_int64), arr(nb, C.c_int64))
+            for inverse, key in ((True, "inv"), (False, "fwd")):
+                ranks, src, dst, nb = lay[key][f]
+                self._p2p_lists[(f, inverse)] = (arr(ranks, C.c_int), arr(src, C.c_int64), arr(dst, C.c_int64), arr(nb, C.c_int64))
         # tables of the peer-store passes (exchange fused into the z / y pass): [f][s] block bases
         pb = [int(lib.ddl_p2p_peer_base(ctx, s)) for s in range(P)]
-        zt = [[pb[s] + (f * self.n_xs + self.cy0 * blk) * el for s in range(P)] for f in range(nmax)]
-        yt = [[pb[s] + xs_total + (f * n_ks_of[s] + (me * self.rows[s] - cy0_of[s]) * blk) * el for s in range(P)]
-              for f in range(nmax)]
+        zt = [[pb[s] + lay["zinv_peer"][f][s] for s in range(P)] for f in range(nmax)]
+        yt = [[pb[s] + lay["yfwd_peer"][f][s] for s in range(P)] for f in range(nmax)]
         self._zinv_tab = torch.tensor(zt, dtype=torch.int64, device=self.device)
         self._yfwd_tab = torch.tensor(yt, dtype=torch.int64, device=self.device)
         self._side = torch.cuda.Stream(device=self.device)

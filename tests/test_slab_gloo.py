@@ -21,7 +21,9 @@ def _free_port():
 
 @pytest.mark.parametrize("world,case,layout", [(2, "mhd3d_16_rk2mid", 0), (4, "mhd3d_16_rk2mid", 0), (2, "bouss3d_16_rk2mid", 0),
                                                (2, "hydro3d_16_rk2mid", 1), (4, "mhd3d_8x16x32_rk2trap", 0),
-                                               (4, "mhd3d_16_rk2mid", 1), (2, "mhd3d_8x16x32_rk2trap", 1)])
+                                               (4, "mhd3d_16_rk2mid", 1), (2, "mhd3d_8x16x32_rk2trap", 1),
+                                               (8, "mhd3d_16_rk2mid", 0),      # block slabs: two ranks own NO retained ky row
+                                               (8, "mhd3d_16_rk2mid", 1)])
 def test_slab_pipeline_matches_reference(tmp_path, world, case, layout):
     """layout 0: the reference's block ky slabs; 1: cyclic ky ownership (balanced under dealiasing)."""
     import sys
@@ -36,3 +38,5 @@ def test_slab_pipeline_matches_reference(tmp_path, world, case, layout):
         assert r["bwd"] < 1e-13 and r["fwd"] < 1e-13 and r["bwd_dealias"] == 0.0, r
         assert r["rhs"] < 1e-12 and r["state_after"] < 1e-13, r
         assert sum(r["rows"]) > 0
+    if world == 8 and layout == 0:
+        assert 0 in res[0]["rows"]            # the empty-rank edge case really occurred

@@ -1,0 +1,80 @@
+"""CPU: the byte arithmetic of the peer-to-peer slab exchange (dedalus/data_objects/slab.py: arena_layout) -
+every block a rank pushes lands inside the destination arena, blocks of different sources never overlap, the
+forward exchange is the mirror of the inverse one, and the peer-store tables address exactly the same bytes as
+the copy lists.  Covers ranks that own no retained ky row (block slabs under 2/3 dealiasing)."""
+import importlib.util
+import itertools
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("ddl_slab_layout", os.path.join(ROOT, "dedalus-1.0_b200", "dedalus", "data_objects", "slab.py"))
+slab = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(slab)
+
+CASES = [
+    (8, [64, 64, 43, 0, 0, 42, 64, 64], 64, 176, 512, 9),      # 512^3, block ky slabs
+    (8, [43, 43, 43, 43, 43, 42, 42, 42], 64, 176, 512, 9),     # 512^3, cyclic
+    (2, [11, 10], 16, 16, 32, 6),
+    (4, [3, 0, 0, 2], 4, 8, 16, 4),
+]
+
+
+@pytest.mark.parametrize("P,rows,nzl,cx,nz,nmax", CASES)
+def test_exchange_blocks_tile_the_destination_arenas(P, rows, nzl, cx, nz, nmax):
+    lays = [slab.arena_layout(P, me, rows, nzl, cx, nz, nmax) for me in range(P)]
+    blk = nzl * cx * 16
+    cy = sum(rows)
+    for direction in ("inv", "fwd"):
+        for f in range(nmax):
+            landed = {r: [] for r in range(P)}
+            for me in range(P):
+                ranks, src, dst, nb = lays[me][direction][f]
+                assert sorted(ranks) == list(range(P)) and ranks[0] == me
+                for s, so, do, n in zip(ranks, src, dst, nb):
+                    assert 0 <= so and so + n <= lays[me]["bytes"]                  # source inside my arena
+                    assert 0 <= do and do + n <= lays[s]["bytes"]                   # destination inside the peer's
+                    landed[s].append((do, do + n, me))
+                    # source region: my k-side field (inverse) / my x-side field (forward)
+                    region = lays[me]["ks"][f] if direction == "inv" else lays[me]["xs"][f]
+                    size = rows[me] * nz * cx * 16 if direction == "inv" else cy * blk
+                    assert region <= so and so + n <= region + size
+            for r in range(P):
+                spans = sorted((a, b) for a, b, _ in landed[r] if b > a)
+                for (a0, b0), (a1, b1) in zip(spans[:-1], spans[1:]):
+                    assert b0 <= a1                                                 # no overlap
+                total = sum(b - a for a, b in spans)
+                want = cy * blk if direction == "inv" else rows[r] * nz * cx * 16   # exactly one field is filled
+                assert total == want
+                if spans:
+                    base = lays[r]["xs"][f] if direction == "inv" else lays[r]["ks"][f]
+                    assert spans[0][0] == base and spans[-1][1] == base + want
+
+
+@pytest.mark.parametrize("P,rows,nzl,cx,nz,nmax", CASES)
+def test_forward_is_the_mirror_of_inverse(P, rows, nzl, cx, nz, nmax):
+    lays = [slab.arena_layout(P, me, rows, nzl, cx, nz, nmax) for me in range(P)]
+    for f, me in itertools.product(range(nmax), range(P)):
+        inv = {s: (so, do, n) for s, so, do, n in zip(*lays[me]["inv"][f])}
+        for s in range(P):
+            fwd_s = {t: (so, do, n) for t, so, do, n in zip(*lays[s]["fwd"][f])}
+            so, do, n = inv[s]
+            so2, do2, n2 = fwd_s[me]
+            assert (so2, do2, n2) == (do, so, n)       # what I pushed to s comes back from s to where it came from
+
+
+@pytest.mark.parametrize("P,rows,nzl,cx,nz,nmax", CASES)
+def test_peer_store_tables_address_the_copy_destinations(P, rows, nzl, cx, nz, nmax):
+    cy0 = [sum(rows[:r]) for r in range(P)]
+    blk = nzl * cx * 16
+    for me in range(P):
+        lay = slab.arena_layout(P, me, rows, nzl, cx, nz, nmax)
+        for f in range(nmax):
+            inv = {s: do for s, so, do, n in zip(*lay["inv"][f])}
+            fwd = {s: do for s, so, do, n in zip(*lay["fwd"][f])}
+            for s in range(P):
+                assert lay["zinv_peer"][f][s] == inv[s]                              # first row of my block in s's x-side field
+                # y pass: x-side position p = cy0[s] + j (rank s's j-th row) -> base + p*blk = block `me`, row j of s's k-side field
+                if rows[s]:
+                    assert lay["yfwd_peer"][f][s] + cy0[s] * blk == fwd[s]
