@@ -7,6 +7,7 @@
 
 #include "../../include/ddl.h"
 #include "pointwise.cuh"
+#include "reduce.cuh"
 #include "tile_kernel.cuh"
 #include "fast_kernels.cuh"
 #include "xfused_kernel.cuh"
@@ -180,6 +181,8 @@ struct ddl_plan {
     long long ntot = 1;
     KGeom geom;          // local k-array geometry
     long long nmodes = 0;
+    double* cfl_out = nullptr;      // CFL capture target of the x passes (ddl_rhs_capture_max), caller-owned
+    double* red_partial = nullptr;  // block partials of the reductions (reduce.cuh)
     std::vector<void*> owned;
 };
 
@@ -302,6 +305,9 @@ extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* sha
         g.twod = 1;
     }
     pl->nmodes = (long long)g.dim[0] * g.dim[1] * g.dim[2];
+    pl->red_partial = (double*)dev_alloc((size_t)DDL_RED_MAXBLOCKS * DDL_RED_MAXV * sizeof(double));
+    if (!pl->red_partial) { set_error("device allocation failed"); ddl_plan_destroy(pl); return -2; }
+    pl->owned.push_back(pl->red_partial);
     *out = pl;
     return 0;
 }
@@ -451,7 +457,7 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
 // pair-mode pass (C2R / R2C / FUSED) over real lines
 static int pass_pair(const char* name, int N, int mode, int phys, int ni, int no, const void* const* in, void* const* out,
                      const TileSide& si, const TileSide& so, int n_lines, int n_outer, int kn, double scale,
-                     const cplx* tw, const PhysConst& pc, ddl_stream_t st) {
+                     const cplx* tw, const PhysConst& pc, ddl_stream_t st, double* cfl = nullptr) {
     if (n_outer <= 0) return 0;
     TileParams p;
     memset(&p, 0, sizeof(p));
@@ -467,7 +473,7 @@ static int pass_pair(const char* name, int N, int mode, int phys, int ni, int no
     p.G = g;
     p.inner_len = n_lines; p.n_outer = n_outer; p.kn = kn;
     p.ld = (g * p.nft) | 1;
-    p.scale = scale; p.tw = tw; p.pc = pc; p.name = name;
+    p.scale = scale; p.tw = tw; p.pc = pc; p.name = name; p.cfl = cfl;
     const int rmax = N >= 8 ? 8 : 4;
     return run_tile(N, mode, 0, phys, p, round32(g * p.nft * (N / rmax)), st);
 }
@@ -577,12 +583,12 @@ static int phase_xfused(ddl_plan* pl, int code, int ni, int no, const void* cons
         for (int f = 0; f < ni; ++f) xp.in[f] = (const cplx*)B[f];
         for (int f = 0; f < no; ++f) xp.out[f] = (cplx*)Cout[f];
         xp.pitch = KXP; xp.s_outer = (long long)Y.n * KXP; xp.n_lines = Y.n; xp.kn = X.cnt;
-        xp.scale = sc; xp.tw = X.tw; xp.pc = pc;
+        xp.scale = sc; xp.tw = X.tw; xp.pc = pc; xp.cfl = pl->cfl_out;
         const int rcx = run_xfused(X.n, code, xp, nzc, st);
         if (rcx <= 0) return rcx;
     }
     TileSide s = side(1, KXP, (long long)Y.n * KXP, nullptr, nullptr);
-    return pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, B, Cout, s, s, Y.n, nzc, X.cnt, sc, X.tw, pc, st);
+    return pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, B, Cout, s, s, Y.n, nzc, X.cnt, sc, X.tw, pc, st, pl->cfl_out);
 }
 // plain x passes of the transform API: B[nzl][y][CX] -> x[nzl][y][nx] and back (normalised)
 static int phase_xc2r(ddl_plan* pl, const void* B, double* x, ddl_stream_t st) {
@@ -815,7 +821,7 @@ static int check_physics(const ddl_plan* pl, int physics, const ddl_phys_params*
 }
 
 static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
-                    void* work, size_t work_bytes, int flags, const ddl_stage_fuse* fuse, void* stream) {
+                    void* work, size_t work_bytes, int flags, const ddl_stage_fuse* fuse, void* stream, bool front_only = false) {
     ddl_stream_t st = (ddl_stream_t)stream;
     int ni, no, code;
     DDL_TRY(need_one_rank(pl, "ddl_rhs"));
@@ -838,6 +844,7 @@ static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void*
         DDL_TRY(phase_zinv(pl, ni, (const void* const*)state, A.data(), st));
         DDL_TRY(phase_yinv(pl, ni, A.data(), B.data(), st));
         DDL_TRY(phase_xfused(pl, code, ni, no, B.data(), C.data(), pc, st));
+        if (front_only) return 0;
         DDL_TRY(phase_yfwd(pl, no, C.data(), D.data(), st));
         DDL_TRY(phase_zfwd(pl, no, D.data(), E.data(), false, st));
     } else {
@@ -846,7 +853,8 @@ static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void*
         const long long per = (long long)X.cnt * Y.n, pere = (long long)X.cnt * Y.cnt;
         for (int f = 0; f < no; ++f) { C[f] = r1 + f * per; E[f] = r2 + f * pere; }
         TileSide s = side(Y.n, 1, 0, nullptr, nullptr);
-        DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, A.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st));
+        DDL_TRY(pass_pair("x_fused", X.n, TM_FUSED, code, ni, no, A.data(), C.data(), s, s, Y.n, 1, X.cnt, sc, X.tw, pc, st, pl->cfl_out));
+        if (front_only) return 0;
         DDL_TRY(forward_tail_2d(pl, no, C.data(), E.data(), false, st));
     }
     if (fuse) return assemble_rk4_any(pl, code, E.data(), state, pc, fuse, st);
@@ -951,6 +959,76 @@ extern "C" int ddl_slab_assemble(ddl_plan* pl, int physics, const ddl_phys_param
     DDL_TRY(check_physics(pl, physics, prm));
     phys_counts(3, physics, ni, no, code);
     return assemble_any(pl, code, e_in, state, deriv, phys_const(prm), (ddl_stream_t)stream);
+}
+
+// ---------------------------------------------------------------- reductions (include/ddl.h)
+extern "C" int ddl_rhs_capture_max(ddl_plan* pl, double* out2) {
+    pl->cfl_out = out2;
+    return 0;
+}
+
+static int zero_doubles(double* p, int n, ddl_stream_t st) {
+#if DDL_DEVICE_BUILD
+    DDL_CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(double), st));
+#else
+    (void)st;
+    memset(p, 0, n * sizeof(double));
+#endif
+    return 0;
+}
+
+extern "C" int ddl_reduce_max_square(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* work,
+                                     size_t work_bytes, int flags, double* out2, void* stream) {
+    if (!out2) { set_error("ddl_reduce_max_square: out2 is NULL"); return -1; }
+    DDL_TRY(need_one_rank(pl, "ddl_reduce_max_square"));
+    DDL_TRY(zero_doubles(out2, 2, (ddl_stream_t)stream));
+    double* saved = pl->cfl_out;
+    pl->cfl_out = out2;
+    const int rc = rhs_impl(pl, physics, prm, state, nullptr, work, work_bytes, flags & DDL_RHS_DEALIAS_STATE, nullptr, stream, true);
+    pl->cfl_out = saved;
+    return rc;
+}
+
+template <int ND, int NB>
+static int invariants_t(ddl_plan* pl, void* const* state, int flags, double* out, ddl_stream_t st) {
+    InvariantsF<ND, NB> f;
+    memset(&f, 0, sizeof(f));
+    for (int c = 0; c < ND + NB; ++c) f.S[c] = (const cplx*)state[c];
+    f.g = pl->geom;
+    long long count = pl->nmodes;
+    if (flags & DDL_STAGE_RETAINED_ONLY) {
+        const Axis &X = pl->ax, &Y = pl->ay, &Z = pl->az;
+        f.compact = 1;
+        if (ND == 3) {
+            f.cdim[0] = pl->yl.cyl; f.cdim[1] = Z.cnt; f.cdim[2] = X.cnt;
+            f.fstride[0] = (long long)Z.n * X.nk; f.fstride[1] = X.nk; f.fstride[2] = 1;
+            f.ftab[0] = pl->yl.c2f; f.ftab[1] = Z.c2f; f.ftab[2] = nullptr;
+            f.kvc[0] = pl->yl.kvc; f.kvc[1] = Z.kvc; f.kvc[2] = X.kvc;
+        } else {
+            f.cdim[0] = 1; f.cdim[1] = X.cnt; f.cdim[2] = Y.cnt;
+            f.fstride[0] = 0; f.fstride[1] = Y.n; f.fstride[2] = 1;
+            f.ftab[0] = nullptr; f.ftab[1] = nullptr; f.ftab[2] = Y.c2f;
+            f.kvc[0] = nullptr; f.kvc[1] = X.kvc; f.kvc[2] = Y.kvc;
+        }
+        count = (long long)f.cdim[0] * f.cdim[1] * f.cdim[2];
+    }
+    if (count <= 0) return zero_doubles(out, DDL_NINV, st);      // a rank may own no retained ky row
+    return launch_reduce<InvariantsF<ND, NB>, RED_SUM>(f, count, pl->red_partial, out, 0, st, "invariants");
+}
+
+extern "C" int ddl_reduce_invariants(ddl_plan* pl, int physics, void* const* state, int flags, double* out, void* stream) {
+    static_assert(DDL_NINV == DDL_NINV_, "include/ddl.h and reduce.cuh disagree on the invariant count");
+    ddl_stream_t st = (ddl_stream_t)stream;
+    if (!out || !state) { set_error("ddl_reduce_invariants: NULL argument"); return -1; }
+    if (physics < 0 || physics > 2) { set_error("unknown physics id %d", physics); return -1; }
+    if (pl->ndim == 3) {
+        if (physics == DDL_HYDRO) return invariants_t<3, 0>(pl, state, flags, out, st);
+        if (physics == DDL_BOUSSINESQ) return invariants_t<3, 1>(pl, state, flags, out, st);
+        return invariants_t<3, 3>(pl, state, flags, out, st);
+    }
+    if (physics == DDL_HYDRO) return invariants_t<2, 0>(pl, state, flags, out, st);
+    if (physics == DDL_BOUSSINESQ) return invariants_t<2, 1>(pl, state, flags, out, st);
+    return invariants_t<2, 2>(pl, state, flags, out, st);
 }
 
 // ---------------------------------------------------------------- stage updates

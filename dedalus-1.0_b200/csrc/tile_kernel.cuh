@@ -48,6 +48,8 @@ struct TileParams {
     const cplx* tw;
     PhysConst pc;
     const char* name;     // label for launch accounting / profiling (host side only)
+    double* cfl;          // TM_FUSED: optional CFL capture, cfl[0] = max(cfl[0], max_{x,i} u_i(x)^2), cfl[1]: second group
+                          // (B or T) -- fields.py:153-157 max_square without a transform of its own; NULL = off
 };
 
 template <int N, int S_IDX, int DIR, bool DIT>
@@ -76,6 +78,9 @@ DDL_BODY void tile_fft_dit(cplx* tile, int ld, int nfa, int nft, int G, const cp
     DDL_SYNC();
     if constexpr (S_IDX > 0) tile_fft_dit<N, DIR, S_IDX - 1>(tile, ld, nfa, nft, G, tw);
 }
+
+// running maximum of non-negative values; NaN wins (numpy's max propagates it)
+DDL_HD double tmax_nn(double m, double a) { return (a > m || a != a) ? a : m; }
 
 DDL_HD long long outer_off(const TileSide& s, int o) {
     return (long long)(s.outer_tab ? s.outer_tab[o] : o) * s.s_outer;
@@ -170,16 +175,43 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
 
         if constexpr (MODE == TM_FUSED) {
             // real-space products at every grid point of both lines of the pair
+            double m0 = 0.0, m1 = 0.0;
             DDL_FOR_ITEMS(i, N * ng) {
                 const int g = i % ng, pos = i / ng;
                 cplx* row = tile + pos * ld + g * nft;
                 double ax[NI], ay[NI], ox[NO], oy[NO];
 #pragma unroll
                 for (int f = 0; f < NI; ++f) { cplx v = row[f]; ax[f] = v.x; ay[f] = v.y; }
+                if (p.cfl) {
+                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+                    for (int f = 0; f < NI; ++f) {
+                        if (f < PHYS::NDIM) { a0 = tmax_nn(a0, ax[f] * ax[f]); a1 = tmax_nn(a1, ay[f] * ay[f]); }
+                        else { b0 = tmax_nn(b0, ax[f] * ax[f]); b1 = tmax_nn(b1, ay[f] * ay[f]); }
+                    }
+                    m0 = tmax_nn(tmax_nn(m0, a0), a1);
+                    m1 = tmax_nn(tmax_nn(m1, b0), b1);
+                }
                 PHYS::apply(ax, ox, p.pc);
                 PHYS::apply(ay, oy, p.pc);
 #pragma unroll
                 for (int f = 0; f < NO; ++f) row[f] = mk(ox[f], oy[f]);
+            }
+            if (p.cfl) {      // uniform over the CTA
+#if DDL_DEVICE_BUILD
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    m0 = tmax_nn(m0, __shfl_xor_sync(0xffffffffu, m0, off));
+                    m1 = tmax_nn(m1, __shfl_xor_sync(0xffffffffu, m1, off));
+                }
+                if ((threadIdx.x & 31) == 0) {     // non-negative doubles order like their bit patterns
+                    atomicMax(reinterpret_cast<unsigned long long*>(p.cfl), (unsigned long long)__double_as_longlong(m0));
+                    atomicMax(reinterpret_cast<unsigned long long*>(p.cfl) + 1, (unsigned long long)__double_as_longlong(m1));
+                }
+#else
+                p.cfl[0] = tmax_nn(p.cfl[0], m0);
+                p.cfl[1] = tmax_nn(p.cfl[1], m1);
+#endif
             }
             DDL_SYNC();
         }

@@ -45,6 +45,8 @@ struct XFusedParams {
     double scale;                   // forward normalisation 1/N_total
     const cplx* tw;                 // exp(-2 pi i m / N)
     PhysConst pc;
+    double* cfl;                    // CFL capture (kernels instantiated with CFL = true): cfl[0] = max(cfl[0], max_{x,i} u_i(x)^2),
+                                    // cfl[1] likewise for the second group (B or T); fields.py:153-157 max_square
 };
 
 // Outer (shared-memory) stages of the length-N transform; the innermost radix-2 stage is fused
@@ -234,8 +236,14 @@ DDL_BODY void xstage(cplx* T, int lane, const cplx* __restrict__ tw) {
     }
 }
 
+// running maximum of non-negative values; NaN wins (numpy's max propagates it)
+DDL_HD double xmax_nn(double m, double a) { return (a > m || a != a) ? a : m; }
+
 // One CTA: G line pairs (lines 2*(bx*G+g), +1 of outer plane by), NT threads.
-template <int N, class PHYS, int NT, int G>
+// CFL: also reduce max_{x,i} u_i(x)^2 and max_{x,i} B_i(x)^2 (T^2) over the grid points of this CTA into p.cfl -
+// the real-space fields exist only here, so the time-step limit (physics.py:601-610,821-836) costs
+// no transform of its own.
+template <int N, class PHYS, int NT, int G, bool CFL = false>
 DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
     constexpr int NI = PHYS::NI, NO = PHYS::NO;
     constexpr int NS = NI > NO ? NI : NO;     // pencil slots per line pair
@@ -312,6 +320,7 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
     //                   one item = one real line (8-byte half) of one position pair
     {
         double* td = reinterpret_cast<double*>(tile);
+        double m0 = 0.0, m1 = 0.0;
         DDL_XF_ITEMS(i, G * N, NT) {
             const int c = i & 1, wp = (i >> 1) % (N / 2), g = (i >> 1) / (N / 2);
             const int s0 = 2 * xsw<N>(2 * wp) + c, s1 = s0 ^ 2;     // xsw(2wp+1) = xsw(2wp) ^ 1
@@ -322,6 +331,16 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
                 const double x0 = T[f * 2 * N + s0], x1 = T[f * 2 * N + s1];
                 u0[f] = x0 + x1; u1[f] = x0 - x1;
             }
+            if constexpr (CFL) {
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+                for (int f = 0; f < NI; ++f) {
+                    if (f < PHYS::NDIM) { a0 = xmax_nn(a0, u0[f] * u0[f]); a1 = xmax_nn(a1, u1[f] * u1[f]); }
+                    else { b0 = xmax_nn(b0, u0[f] * u0[f]); b1 = xmax_nn(b1, u1[f] * u1[f]); }
+                }
+                m0 = xmax_nn(xmax_nn(m0, a0), a1);
+                m1 = xmax_nn(xmax_nn(m1, b0), b1);
+            }
             PHYS::apply(u0, o0, p.pc);
             PHYS::apply(u1, o1, p.pc);
 #pragma unroll
@@ -329,6 +348,24 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
                 T[f * 2 * N + s0] = o0[f] + o1[f];
                 T[f * 2 * N + s1] = o0[f] - o1[f];
             }
+        }
+        if constexpr (CFL) {
+#if DDL_DEVICE_BUILD
+            // every thread of the CTA is here (the item loop is uniform in its exit): full-warp tree,
+            // then one atomic per warp; non-negative doubles order like their bit patterns
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                m0 = xmax_nn(m0, __shfl_xor_sync(0xffffffffu, m0, off));
+                m1 = xmax_nn(m1, __shfl_xor_sync(0xffffffffu, m1, off));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMax(reinterpret_cast<unsigned long long*>(p.cfl), (unsigned long long)__double_as_longlong(m0));
+                atomicMax(reinterpret_cast<unsigned long long*>(p.cfl) + 1, (unsigned long long)__double_as_longlong(m1));
+            }
+#else
+            p.cfl[0] = xmax_nn(p.cfl[0], m0);
+            p.cfl[1] = xmax_nn(p.cfl[1], m1);
+#endif
         }
     }
     DDL_SYNC();
@@ -447,22 +484,22 @@ template <int N, class PHYS, int V> struct XFusedCfg {
 };
 
 #if DDL_DEVICE_BUILD
-template <int N, class PHYS, int V>
+template <int N, class PHYS, int V, bool CFL>
 __global__ void __maxnreg__((XFusedCfg<N, PHYS, V>::MAXREG))
 xfused_kernel(const __grid_constant__ XFusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    xfused_block<N, PHYS, XFusedCfg<N, PHYS, V>::NT, XFusedCfg<N, PHYS, V>::G>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
+    xfused_block<N, PHYS, XFusedCfg<N, PHYS, V>::NT, XFusedCfg<N, PHYS, V>::G, CFL>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
 }
 #endif
 
 // returns 0 on success, negative on error
-template <int N, class PHYS, int V>
+template <int N, class PHYS, int V, bool CFL = false>
 int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     using Cfg = XFusedCfg<N, PHYS, V>;
     const int pairs = (p.n_lines + 1) / 2;
     const int gx = (pairs + Cfg::G - 1) / Cfg::G;
 #if DDL_DEVICE_BUILD
-    auto kern = xfused_kernel<N, PHYS, V>;
+    auto kern = xfused_kernel<N, PHYS, V, CFL>;
     static bool attr_done = false;
     if (!attr_done) {
         DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -478,7 +515,7 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     (void)stream;
     cplx* tile = (cplx*)malloc(Cfg::SMEM);
     for (int by = 0; by < n_outer; ++by)
-        for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G>(p, tile, bx, by);
+        for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G, CFL>(p, tile, bx, by);
     free(tile);
 #endif
     return 0;
@@ -486,6 +523,7 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
 
 template <int N, class PHYS>
 int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t stream) {
+    if (p.cfl) return launch_xfused_v<N, PHYS, 0, true>(p, n_outer, stream);     // capture: default CTA shape only
 #if DDL_DEVICE_BUILD
     if (variant == 1) return launch_xfused_v<N, PHYS, 1>(p, n_outer, stream);
     if (variant == 2) return launch_xfused_v<N, PHYS, 2>(p, n_outer, stream);

@@ -209,6 +209,50 @@ int ddl_slab_assemble_stage(ddl_plan* plan, int physics, const ddl_phys_params* 
 int ddl_cn_step(ddl_plan* plan, int ncomp, void* const* y, void* const* k, const double* coeff,
                 int visc_order, double dt, int flags, void* stream);
 
+/* ---- reductions: invariants and the CFL limit -------------------------------------------------
+ * Replace the volume-average tasks of dedalus/analysis/volume_average.py:71-331 and
+ * VectorFieldBase.max_square / compute_dt / set_dtlist (dedalus/data_objects/fields.py:153-157,
+ * dedalus/physics/physics.py:151-158,601-610,714-721,821-836).  Results land in DEVICE memory
+ * (caller-owned); a rank reduces its own slab, the caller combines ranks (sum / max).
+ *
+ * ddl_reduce_invariants: ONE sweep over the state (u, then T or B; StateData order) fills
+ * out[DDL_NINV].  w = 1 on the kx = 0 plane, 2 elsewhere (volume_average.py:84-97); W = k x u,
+ * J = k x B.  flags: DDL_STAGE_RETAINED_ONLY when the state is known to vanish outside the mask. */
+enum {
+    DDL_INV_EKIN = 0,        /* sum w |u|^2 / 2                        ekin      :108-118 */
+    DDL_INV_E2 = 1,          /* sum w |B|^2 / 2 (emag :179-188) or sum w |T|^2 / 2 (temp2 / 2 :172-177) */
+    DDL_INV_DIV_SUM = 2,     /* sum |i k.u|, unweighted                divergence_sum :287-295 */
+    DDL_INV_MAG_DIV_SUM = 3, /* sum |i k.B|                            mag_div_sum    :315-322 */
+    DDL_INV_ENSTROPHY = 4,   /* sum w |W|^2 / 2   (2-D: enstrophy :190-199; 3-D: energy_dissipation / (2 nu) :250-260) */
+    DDL_INV_CURRENT2 = 5,    /* sum w |J|^2 / 2 */
+    DDL_INV_HEL_KIN = 6,     /* sum w Re(u . conj(i W)),  3-D only */
+    DDL_INV_HEL_CROSS = 7,   /* sum w Re(u . conj(B)) */
+    DDL_INV_DIV_RE = 8, DDL_INV_DIV_IM = 9,         /* sum w (i k.u)  divergence :273-280 */
+    DDL_INV_MAG_DIV_RE = 10, DDL_INV_MAG_DIV_IM = 11, /* mag_div :305-312 */
+    DDL_INV_CENK_NUM = 12,   /* sum (k^2)^1.5 |u|^2/2 and */
+    DDL_INV_CENK_DEN = 13,   /* sum k^2 |u|^2/2, k^2(0) := 1, en[0,0] := 0   vort_cenk :201-212 */
+    DDL_INV_MSQ = 14,        /* +c: sum w |component c|^2, c < 6       ux2 .. bz2, temp2 :123-177 */
+    DDL_INV_HEL_MAG = 20,    /* sum w Re(A . conj(B)), A = i J / k^2, 3-D MHD only */
+    DDL_INV_GRAD2_T = 21,    /* sum w k^2 |T|^2                        thermal_energy_dissipation / kappa :262-271 */
+    DDL_NINV = 24
+};
+int ddl_reduce_invariants(ddl_plan* plan, int physics, void* const* state, int flags, double* out, void* stream);
+
+/* CFL capture: the only place where u(x), B(x) exist is inside the x pass of the RHS, so the
+ * maxima the time-step limit needs are reduced THERE.  While out2 (device, 2 doubles, zeroed by
+ * the caller) is set, every x pass of ddl_rhs / ddl_rhs_stage / ddl_slab_xfused* on this plan does
+ *   out2[0] = max(out2[0], max_{x,i} u_i(x)^2),   out2[1] = max(out2[1], max_{x,i} B_i(x)^2)
+ * (Boussinesq: T(x)^2) -- the maximum over space AND components of the squared component, which is what
+ * VectorFieldBase.max_square returns (fields.py:153-157) -- of the state the RHS was evaluated at.
+ * NULL switches the capture off (the default; the x pass then is the plain kernel). */
+int ddl_rhs_capture_max(ddl_plan* plan, double* out2);
+/* max_square on its own (compute_dt outside a step): the inverse half of the RHS pipeline with
+ * the capture on, nothing else written but workspace.  One-rank plans; a slab-decomposed caller
+ * runs ddl_slab_zinv / yinv / xfused with ddl_rhs_capture_max set.  flags: DDL_RHS_DEALIAS_STATE
+ * (the reference's max_square transforms the state itself, which masks it in place). */
+int ddl_reduce_max_square(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* state,
+                          void* work, size_t work_bytes, int flags, double* out2, void* stream);
+
 /* launch accounting: cumulative number of kernels this library has launched in the process,
  * and optional per-launch CUDA-event timing aggregated by kernel label (bench.py roofline) */
 long long ddl_launch_count(void);

@@ -154,6 +154,34 @@ class EmulPlan:
         self.check(self.lib.ddl_cn_step(self.plan, len(y), _pa(y), _pa(list(k)), _p(co), vo, C.c_double(dt), flags, None))
         return np.stack(y)
 
+    # ---- reductions (include/ddl.h: ddl_reduce_invariants / ddl_reduce_max_square / ddl_rhs_capture_max)
+    NINV = 24
+
+    def _pp(self, params):
+        return PhysParams(params.get("rho0", 1.0), params.get("g", 1.0), params.get("alpha_t", 1.0),
+                          params.get("beta", 1.0), {"x": 0, "y": 1, "z": 2}[params.get("boussinesq_direction", "z")], 0)
+
+    def invariants(self, physics, state, flags=0):
+        state = [np.ascontiguousarray(s, dtype=np.complex128) for s in state]
+        out = np.full(self.NINV, np.nan)
+        self.check(self.lib.ddl_reduce_invariants(self.plan, self.PHYS[physics], _pa(state), flags, _p(out), None))
+        return out
+
+    def max_square(self, physics, params, state, flags=0):
+        pid = self.PHYS[physics]
+        pp = self._pp(params)
+        state = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in state]
+        out = np.full(2, np.nan)
+        w = self._ws(self.lib.ddl_rhs_workspace_bytes(self.plan, pid))
+        self.check(self.lib.ddl_reduce_max_square(self.plan, pid, C.byref(pp), _pa(state), _p(w), C.c_size_t(w.nbytes),
+                                                  flags, _p(out), None))
+        return out, np.stack(state)
+
+    def capture_max(self, out2):
+        """out2: float64[2] the next RHS evaluations maximise into, or None to switch the capture off."""
+        self._cap = out2
+        self.check(self.lib.ddl_rhs_capture_max(self.plan, _p(out2) if out2 is not None else None))
+
     def stage(self, kind, start, d1, d2, coeff, vo, dt, flags=0):
         n = len(start)
         out = [np.zeros_like(s) for s in start]
