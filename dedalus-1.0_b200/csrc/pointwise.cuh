@@ -305,7 +305,7 @@ int launch_items(const F& f, long long count, ddl_stream_t stream, const char* n
     prof_end(stream);
     DDL_CUDA_CHECK(cudaGetLastError());
 #else
-    (void)stream; (void)name;
+    prof_begin(name, stream);       // the emulation counts launches like the device build (tests/ launch accounting)
     for (long long i = 0; i < count; ++i) f(i);
 #endif
     return 0;

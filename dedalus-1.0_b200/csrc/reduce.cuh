@@ -89,7 +89,9 @@ int launch_reduce(const F& f, long long count, double* partial, double* out, int
     prof_end(stream);
     DDL_CUDA_CHECK(cudaGetLastError());
 #else
-    (void)partial; (void)stream; (void)name;
+    (void)partial;
+    prof_begin(name, stream);
+    prof_begin("reduce_final", stream);
     double acc[NR];
     for (int r = 0; r < NR; ++r) acc[r] = red_identity<OP>();
     for (long long i = 0; i < count; ++i) f(i, acc);

@@ -281,7 +281,8 @@ int launch_tile(const TileParams& p, int nthreads, ddl_stream_t stream) {
     prof_end(stream);
     DDL_CUDA_CHECK(cudaGetLastError());
 #else
-    (void)nthreads; (void)stream;
+    (void)nthreads;
+    prof_begin(p.name, stream);
     cplx* tile = (cplx*)malloc(smem);
     for (int bz = 0; bz < gz; ++bz)
         for (int by = 0; by < p.n_outer; ++by)

@@ -512,7 +512,7 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     prof_end(stream);
     DDL_CUDA_CHECK(cudaGetLastError());
 #else
-    (void)stream;
+    prof_begin("x_fused", stream);
     cplx* tile = (cplx*)malloc(Cfg::SMEM);
     for (int by = 0; by < n_outer; ++by)
         for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G, CFL>(p, tile, bx, by);

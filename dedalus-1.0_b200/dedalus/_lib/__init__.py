@@ -16,13 +16,18 @@ EXPORTS = [
     "ddl_rk4_stage", "ddl_cn_step", "ddl_rhs_stage", "ddl_slab_assemble_stage", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_zinv", "ddl_slab_yinv",
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
-    "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count",
+    "ddl_reduce_invariants", "ddl_reduce_max_square", "ddl_rhs_capture_max", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
 EULER, ETD1, ETD2RK1, ETD2RK2 = 0, 1, 2, 3
 RHS_ZERO_FILL, RHS_DEALIAS_STATE = 1, 2
 STAGE_RETAINED_ONLY = 1
+# include/ddl.h DDL_INV_*: entries of the vector ddl_reduce_invariants fills
+INV = dict(ekin=0, e2=1, div_sum=2, mag_div_sum=3, enstrophy=4, current2=5, hel_kin=6, hel_cross=7, div_re=8, div_im=9,
+           mag_div_re=10, mag_div_im=11, cenk_num=12, cenk_den=13, msq=14, hel_mag=20, grad2_T=21)
+NINV = 24
 
 
 class PhysParams(C.Structure):
@@ -60,6 +65,9 @@ def bind_slab(lib):
     lib.ddl_dealias.argtypes = [vp, vp, vp]
     lib.ddl_slab_assemble_stage.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.ddl_rhs_stage.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, i32, vp, vp]
+    lib.ddl_reduce_invariants.argtypes = [vp, i32, vp, i32, vp, vp]
+    lib.ddl_reduce_max_square.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, i32, vp, vp]
+    lib.ddl_rhs_capture_max.argtypes = [vp, vp]
     if hasattr(lib, "ddl_p2p_create"):
         lib.ddl_p2p_create.argtypes = [C.POINTER(vp), i32, i32, C.c_size_t, C.c_char_p]
         lib.ddl_p2p_connect.argtypes = [vp, C.c_char_p]

@@ -1,10 +1,61 @@
 """Volume-averaged diagnostics (reference: dedalus/analysis/volume_average.py): the invariants
-the parity gate compares (ekin, emag, divergence_sum, mag_div_sum, ...).  Reductions run on the
-device; only the scalar result crosses to the host."""
+the parity gate compares (ekin, emag, divergence_sum, mag_div_sum, ...).
+
+Every k-space task of a standard state (u [+ T | B]) is an entry of ONE device sweep
+(include/ddl.h: ddl_reduce_invariants; csrc/reduce.cuh) that reads each component once -- the
+reference spends one or more full-array numpy passes, with deriv temporaries, on EACH task.  A
+VolumeAverageSet.run() shares a single sweep between all its tasks; 24 doubles cross to the host.
+States with other field lists and the x-space variants use tensor operations."""
+import ctypes as C
+
 import numpy as np
 import torch
 
+from .. import _lib
+from .._lib import lib, check, INV
+from ..data_objects import plan as _plan
 from ..utils.parallelism import com_sys, reduce_sum, reduce_mean, reduce_max
+
+_PHYSICS_OF = {("u",): _lib.HYDRO, ("u", "T"): _lib.BOUSSINESQ, ("u", "B"): _lib.MHD}
+_shared = {"on": False, "key": None, "val": None}     # one sweep per VolumeAverageSet.run()
+
+
+def invariants(data):
+    """(total, local): the DDL_INV_* vector of `data` summed over ranks, and this rank's own part
+    (the reference's divergence_sum / mag_div_sum / vort_cenk are rank-local), as numpy arrays;
+    None when `data` is not a standard u [+ T | B] state."""
+    pid = _PHYSICS_OF.get(tuple(data.fields.keys()))
+    if pid is None:
+        return None
+    comps = [c for _, _, c in data.components()]
+    key = (id(data), data.time, tuple(c._k.data_ptr() for c in comps))
+    if _shared["on"] and _shared["key"] == key:
+        return _shared["val"]
+    state = []
+    for c in comps:
+        c.require_space("kspace")
+        state.append(c._k)
+    pl = comps[0]._plan
+    out = torch.empty(_lib.NINV, dtype=torch.float64, device=pl.device)
+    flags = _lib.STAGE_RETAINED_ONLY if all(c._clean for c in comps) else 0
+    check(lib.ddl_reduce_invariants(pl.handle, pid, _lib.ptr_array(state), flags, out.data_ptr(), _plan.current_stream()))
+    local = out.cpu().numpy()
+    total = local
+    if com_sys.comm is not None:
+        t = out.clone()
+        com_sys.comm.all_reduce(t)
+        total = t.cpu().numpy()
+    val = (total, local)
+    if _shared["on"]:
+        _shared["key"], _shared["val"] = key, val
+    return val
+
+
+def _on_root(value, reduce_all=False):
+    """reduce_sum's convention (parallelism.py:96-118): the value on rank 0, or everywhere with reduce_all."""
+    if com_sys.comm is None or reduce_all or com_sys.myproc == 0:
+        return value
+    return None
 
 
 def volume_average(data, kdict=None, space="kspace", reduce_all=False):
@@ -56,8 +107,12 @@ class VolumeAverageSet(object):
 
     def run(self):
         line = ["%10.5f" % self.data.time]
-        for f, fmt, kwargs in self.tasks:
-            val = f(self.data, self.scratch, **kwargs)
+        _shared.update(on=True, key=None, val=None)
+        try:
+            vals = [f(self.data, self.scratch, **kwargs) for f, fmt, kwargs in self.tasks]
+        finally:
+            _shared.update(on=False, key=None, val=None)
+        for (f, fmt, kwargs), val in zip(self.tasks, vals):
             if com_sys.myproc == 0:
                 line.append(fmt % val)
         if com_sys.myproc == 0:
@@ -73,7 +128,10 @@ class VolumeAverageSet(object):
 task = VolumeAverageSet.register_task
 
 
-def _energy(field, space, reduce_all=False):
+def _energy(field, space, reduce_all=False, data=None, slot=None):
+    inv = invariants(data) if (space == "kspace" and data is not None) else None
+    if inv is not None:
+        return _on_root(float(inv[0][INV[slot]]), reduce_all)
     if space == "kspace":
         acc = sum(0.5 * c["kspace"].abs() ** 2 for _, c in field)
         return volume_average(acc, kdict=field[0].k if field.ncomp > 1 else field.components[0].k, reduce_all=reduce_all)
@@ -83,52 +141,55 @@ def _energy(field, space, reduce_all=False):
 
 @task
 def ekin(data, scratch=None, space="kspace", reduce_all=False):
-    return _energy(data["u"], space, reduce_all)
+    return _energy(data["u"], space, reduce_all, data, "ekin")
 
 
 @task
 def emag(data, scratch=None, space="kspace", reduce_all=False):
-    return _energy(data["B"], space, reduce_all)
+    return _energy(data["B"], space, reduce_all, data, "e2")
 
 
-def _mean_square(comp):
+def _mean_square(comp, data=None, index=None):
+    inv = invariants(data) if data is not None else None
+    if inv is not None:
+        return _on_root(float(inv[0][INV["msq"] + index]))
     k = comp["kspace"]
     return volume_average((k * k.conj()).real, kdict=comp.k)
 
 
 @task
 def ux2(data, scratch=None, space="kspace"):
-    return _mean_square(data["u"]["x"])
+    return _mean_square(data["u"]["x"], data, 0)
 
 
 @task
 def uy2(data, scratch=None, space="kspace"):
-    return _mean_square(data["u"]["y"])
+    return _mean_square(data["u"]["y"], data, 1)
 
 
 @task
 def uz2(data, scratch=None, space="kspace"):
-    return _mean_square(data["u"]["z"])
+    return _mean_square(data["u"]["z"], data, 2)
 
 
 @task
 def bx2(data, scratch=None, space="kspace"):
-    return _mean_square(data["B"]["x"])
+    return _mean_square(data["B"]["x"], data, data.ndim + 0)
 
 
 @task
 def by2(data, scratch=None, space="kspace"):
-    return _mean_square(data["B"]["y"])
+    return _mean_square(data["B"]["y"], data, data.ndim + 1)
 
 
 @task
 def bz2(data, scratch=None, space="kspace"):
-    return _mean_square(data["B"]["z"])
+    return _mean_square(data["B"]["z"], data, data.ndim + 2)
 
 
 @task
 def temp2(data, scratch=None, space="kspace"):
-    return _mean_square(data["T"].components[0])
+    return _mean_square(data["T"].components[0], data, data.ndim)
 
 
 @task
@@ -139,12 +200,18 @@ def comp_mean(data, scratch, fname, cindex):
 @task
 def enstrophy(data, scratch=None, space="kspace"):
     """2-D enstrophy 0.5 <w_z^2> (volume_average.py:190-199)."""
+    inv = invariants(data) if data.ndim == 2 else None
+    if inv is not None:
+        return _on_root(float(inv[0][INV["enstrophy"]]))
     w = data["u"]["y"].deriv("x") - data["u"]["x"].deriv("y")
     return volume_average(0.5 * w.abs() ** 2, kdict=data["u"]["x"].k)
 
 
 @task
 def energy_dissipation(data, scratch=None):
+    inv = invariants(data) if data.ndim == 3 else None
+    if inv is not None:
+        return _on_root(2 * data.parameters["nu"] * float(inv[0][INV["enstrophy"]]))
     u = data["u"]
     w2 = ((u["z"].deriv("y") - u["y"].deriv("z")).abs() ** 2 + (u["x"].deriv("z") - u["z"].deriv("x")).abs() ** 2
           + (u["y"].deriv("x") - u["x"].deriv("y")).abs() ** 2)
@@ -160,23 +227,46 @@ def _div(field):
 
 @task
 def divergence(data, scratch=None):
+    inv = invariants(data)
+    if inv is not None:
+        return _on_root(complex(inv[0][INV["div_re"]], inv[0][INV["div_im"]]))
     return volume_average(_div(data["u"]), kdict=data["u"]["x"].k)
 
 
 @task
 def divergence_sum(data, scratch=None):
-    """sum over stored modes of |i k . u| (volume_average.py:287-295)."""
+    """sum over this rank's stored modes of |i k . u| (volume_average.py:287-295)."""
+    inv = invariants(data)
+    if inv is not None:
+        return float(inv[1][INV["div_sum"]])
     return _div(data["u"]).abs().sum().item()
 
 
 @task
 def mag_div(data, scratch=None):
+    inv = invariants(data)
+    if inv is not None and "B" in data.fields:
+        return _on_root(complex(inv[0][INV["mag_div_re"]], inv[0][INV["mag_div_im"]]))
     return volume_average(_div(data["B"]), kdict=data["B"]["x"].k)
 
 
 @task
 def mag_div_sum(data, scratch=None):
+    inv = invariants(data)
+    if inv is not None and "B" in data.fields:
+        return float(inv[1][INV["mag_div_sum"]])
     return _div(data["B"]).abs().sum().item()
+
+
+@task
+def thermal_energy_dissipation(data, scratch=None):
+    """kappa <(d_i T)^2> (volume_average.py:262-271)."""
+    inv = invariants(data)
+    if inv is not None and "T" in data.fields:
+        return _on_root(data.parameters["kappa"] * float(inv[0][INV["grad2_T"]]))
+    T = data["T"].components[0]
+    g2 = sum(T.deriv(d).abs() ** 2 for d in "xyz"[:data.ndim])
+    return volume_average(data.parameters["kappa"] * g2, kdict=T.k)
 
 
 def _max_task(fname, cname):
@@ -192,10 +282,14 @@ bx_max, by_max, bz_max = _max_task("B", "x"), _max_task("B", "y"), _max_task("B"
 
 @task
 def vort_cenk(data, scratch=None):
-    """Centroid wavenumber of McWilliams 1990 (volume_average.py:201-212)."""
+    """Centroid wavenumber of McWilliams 1990 (volume_average.py:201-212; rank-local like the
+    reference, and `en[0,0] = 0.` clears the origin of the first two stored axes as it does there)."""
+    inv = invariants(data)
+    if inv is not None:
+        return float(inv[1][INV["cenk_num"]] / inv[1][INV["cenk_den"]])
     k2 = data["u"]["x"].k2(no_zero=True)
     en = sum(0.5 * c["kspace"].abs() ** 2 for _, c in data["u"])
-    en[(0,) * en.dim()] = 0.
+    en[0, 0] = 0.
     return ((k2 ** 1.5 * en).sum() / (k2 * en).sum()).item()
 
 
@@ -204,6 +298,9 @@ def kinetic_helicity(data):
     u = data["u"]
     if u.ncomp != 3:
         return 0.0
+    inv = invariants(data)
+    if inv is not None:
+        return _on_root(float(inv[0][INV["hel_kin"]]))
     w = [u["z"].deriv("y") - u["y"].deriv("z"), u["x"].deriv("z") - u["z"].deriv("x"), u["y"].deriv("x") - u["x"].deriv("y")]
     acc = sum((u[i]["kspace"] * w[i].conj()).real for i in range(3))
     return volume_average(acc, kdict=u["x"].k)
@@ -211,5 +308,24 @@ def kinetic_helicity(data):
 
 def cross_helicity(data):
     """<u . B> (not in the reference)."""
+    inv = invariants(data)
+    if inv is not None and "B" in data.fields:
+        return _on_root(float(inv[0][INV["hel_cross"]]))
     acc = sum((data["u"][i]["kspace"] * data["B"][i]["kspace"].conj()).real for i in range(data["u"].ncomp))
     return volume_average(acc, kdict=data["u"]["x"].k)
+
+
+def magnetic_helicity(data):
+    """<A . B> with A = curl^-1 B in the Coulomb gauge (3-D MHD; not in the reference)."""
+    inv = invariants(data)
+    if inv is None or "B" not in data.fields or data.ndim != 3:
+        raise NotImplementedError("magnetic_helicity needs a 3-D (u, B) state")
+    return _on_root(float(inv[0][INV["hel_mag"]]))
+
+
+def current_squared(data):
+    """<|curl B|^2> / 2 (not in the reference; Ohmic dissipation = 2 eta * this)."""
+    inv = invariants(data)
+    if inv is None or "B" not in data.fields:
+        raise NotImplementedError("current_squared needs a (u, B) state")
+    return _on_root(float(inv[0][INV["current2"]]))

@@ -301,6 +301,29 @@ class SlabPipeline(object):
         self._check(lib.ddl_slab_zfwd(h, 1, _ptrs([b["ks"][0]]), _ptrs([k]), 1, st))
         self._check(lib.ddl_dealias(h, k.data_ptr(), st))
 
+    def max_square(self, physics_id, params, state, out2, dealias_state):
+        """out2[0:2] = max u_i(x)^2, max B_i(x)^2 over the local planes: the inverse half of the RHS
+        pipeline with the CFL capture of the x pass on (include/ddl.h: ddl_rhs_capture_max); the
+        caller reduces over ranks."""
+        lib, h, st = self.lib, self.h, self._stream()
+        ni, no = _COUNTS[physics_id]
+        b = self.buffers(ni, no)
+        if dealias_state:
+            for t in state:
+                self._check(lib.ddl_dealias(h, t.data_ptr(), st))
+        pending = []
+        for f in range(ni):
+            self._check(lib.ddl_slab_zinv(h, 1, _ptrs([state[f]]), _ptrs([b["ks"][f]]), st))
+            pending.append(self._exchange(b["xs"][f], b["ks"][f], True))
+        for f in range(ni):
+            pending[f].wait()
+            self._check(lib.ddl_slab_yinv(h, 1, _ptrs([b["xs"][f]]), _ptrs([b["b"][f]]), st))
+        self._check(lib.ddl_rhs_capture_max(h, out2.data_ptr()))
+        try:
+            self._check(lib.ddl_slab_xfused(h, physics_id, C.byref(params), _ptrs(b["b"][:ni]), _ptrs(b["c"][:no]), st))
+        finally:
+            self._check(lib.ddl_rhs_capture_max(h, None))
+
     # ------------------------------------------------------------------ fused RHS
     def _assemble(self, physics_id, pp, e, state, deriv, fuse, st):
         lib, h = self.lib, self.h

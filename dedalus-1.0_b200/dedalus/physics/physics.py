@@ -111,10 +111,80 @@ class Physics(object):
             self.aux_eqns[f] = AuxEquation(r, kwargs, ic)
 
     def compute_dt(self, data):
-        """Raw time-step limit without the CFL number (physics.py:151-158)."""
+        """Raw time-step limit without the CFL number (physics.py:151-158).
+
+        The reference takes every component of u (and B) to x-space and back for this (6 + 6
+        transforms per call in 3-D MHD, fields.py:153-157); here the maxima come out of ONE pass of
+        the inverse half of the RHS pipeline with the reduction inside the x pass
+        (include/ddl.h: ddl_reduce_max_square), and nothing is written but workspace."""
+        return self.dt_from_maxima(data, self.max_squares(data))
+
+    def dt_from_maxima(self, data, maxima):
+        """min(dtlist) with max_square of u / B already known: `maxima` = (max u_i^2, max B_i^2) as
+        returned by max_squares() or captured inside an RHS evaluation (capture_begin/_end)."""
         self.dtlist = []
-        self.set_dtlist(data)
+        self._maxsq = maxima
+        try:
+            self.set_dtlist(data)
+        finally:
+            self._maxsq = None
         return min(self.dtlist)
+
+    # ------------------------------------------------------------------ CFL maxima on the device
+    _maxsq = None
+
+    def _field_max_square(self, data, fname, slot):
+        """data[fname].max_square(): from the fused reduction inside compute_dt, else the
+        reference's component-by-component route (fields.py:153-157)."""
+        if self._maxsq is not None:
+            return self._maxsq[slot]
+        return data[fname].max_square()
+
+    def max_squares(self, data):
+        """(max_{x,i} u_i^2, max_{x,i} B_i^2 [T^2; 0 for hydro]) of `data`, reduced over ranks."""
+        import torch
+        from ..utils.parallelism import reduce_max
+        if not self._is_finalized:
+            self._finalize()
+        state = []
+        for _, _, c in data.components():
+            c.require_space("kspace")
+            state.append(c._k)
+        pl = next(data.components())[2]._plan
+        out = torch.zeros(2, dtype=torch.float64, device=pl.device)
+        pp = self._phys_params()
+        clean = all(c._clean for _, _, c in data.components())
+        flags = 0 if clean else _lib.RHS_DEALIAS_STATE        # max_square masks the spectra in place (representations.py:353)
+        if pl.nranks > 1:
+            pl.pipeline.max_square(self._physics_id, pp, state, out, bool(flags))
+        else:
+            w = pl.rhs_workspace(self._physics_id)
+            check(lib.ddl_reduce_max_square(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), w.data_ptr(),
+                                            w.numel(), flags, out.data_ptr(), _plan.current_stream()))
+        for _, _, c in data.components():
+            c._clean = True
+        return self._finish_maxima(out)
+
+    @staticmethod
+    def _finish_maxima(out):
+        from ..utils.parallelism import reduce_max
+        return (reduce_max(out[0], reduce_all=True), reduce_max(out[1], reduce_all=True))
+
+    def capture_begin(self, data):
+        """Ask the x passes of the following RHS evaluations to maximise u_i(x)^2 / B_i(x)^2 into a
+        device buffer (include/ddl.h: ddl_rhs_capture_max): the time-step limit of the state an RHS
+        is evaluated at then costs no transform at all.  Returns the token for capture_end()."""
+        import torch
+        pl = next(data.components())[2]._plan
+        out = torch.zeros(2, dtype=torch.float64, device=pl.device)
+        check(lib.ddl_rhs_capture_max(pl.handle, out.data_ptr()))
+        return (pl, out)
+
+    def capture_end(self, token):
+        """Switch the capture off and return the maxima (one 16-byte device -> host read)."""
+        pl, out = token
+        check(lib.ddl_rhs_capture_max(pl.handle, None))
+        return self._finish_maxima(out)
 
     # ------------------------------------------------------------------ fused RHS
     def _phys_params(self):
@@ -358,7 +428,7 @@ class IncompressibleHydro(Physics):
             deriv["u"][i]["kspace"].sub_(k[i] * kdot)
 
     def max_abs_vel(self, data):
-        return np.sqrt(data["u"].max_square())
+        return np.sqrt(self._field_max_square(data, "u", 0))
 
     def set_dtlist(self, data):
         dx = data["u"]["x"].dx().min()
@@ -425,7 +495,7 @@ class IncompressibleMHD(IncompressibleHydro):
 
     def max_alfven_speed(self, data):
         fpr = 4 * np.pi * self.parameters["rho0"]
-        return np.sqrt(data["B"].max_square() / fpr)
+        return np.sqrt(self._field_max_square(data, "B", 1) / fpr)
 
     def set_dtlist(self, data):
         IncompressibleHydro.set_dtlist(self, data)

@@ -111,9 +111,9 @@ class TimeStepBase(object):
     def advance(self, data, dt=None):
         if (self.iteration % self.save_cadence) == 0 or (self.time - self._tlastsnap >= self.max_save_period):
             self.snapshot(data)
-        if dt is None:
+        if dt is None and not (self.fuse_cfl and self._lazy_dt_ok()):
             dt = self.cfl_dt(data)
-        self.do_advance(data, dt)
+        self.do_advance(data, dt)          # dt None: the step takes its CFL limit from its own first RHS evaluation
         mylog.info("step %i" % self.iteration)
 
     def do_advance(self, data, dt):
@@ -212,12 +212,36 @@ class TimeStepBase(object):
         self.final_stats()
 
     def cfl_dt(self, data):
-        dt = self.CFL * self.RHS.compute_dt(data)
+        return self._limit_dt(self.CFL * self.RHS.compute_dt(data))
+
+    def _limit_dt(self, dt):
         if dt > 1.05 * self.dt_old:      # at most 5% growth per step
             dt = 1.05 * self.dt_old
         self.dt_old = dt
         mylog.info("dt = %10.5e" % dt)
         return dt
+
+    # ---- CFL limit taken from the step's own first RHS evaluation ---------------------------
+    # advance(data) in the reference is compute_dt(data) -- every component of u and B to x-space and
+    # back, 12 + 12 transforms in 3-D MHD -- followed by do_advance.  The first RHS evaluation of a
+    # step is AT that very state and has u(x), B(x) in registers inside its x pass, so the maxima are
+    # reduced there (include/ddl.h: ddl_rhs_capture_max): do_advance(data, None) evaluates k1 unfused
+    # (no dt needed), reads the two maxima back, fixes dt and carries on with the fused stages.
+    fuse_cfl = True         # set False for the reference's route (tests compare both)
+
+    def _lazy_dt_ok(self):
+        R = self.RHS
+        return hasattr(R, "capture_begin") and not R.aux_eqns
+
+    def _rhs_and_dt(self, data, k):
+        """k = RHS(data) and the CFL-limited dt of `data`, from the same x pass."""
+        R = self.RHS
+        token = R.capture_begin(data)
+        try:
+            R.RHS(data, k)
+        finally:
+            maxima = R.capture_end(token)
+        return self._limit_dt(self.CFL * R.dt_from_maxima(data, maxima))
 
     # ---- stage update fused with the spectral assembly of the RHS --------------------------
     fuse_stages = True      # set False to force the unfused RHS + stage-kernel path (tests compare both)
@@ -292,7 +316,8 @@ class RK2mid(RKBase):
     def do_advance(self, data, dt):
         _settle(data)
         data2, k1, k2 = self.data2, self.deriv1, self.deriv2
-        if self._can_fuse(data, data2, k1):
+        lazy = dt is None
+        if not lazy and self._can_fuse(data, data2, k1):
             self._stage_fused(_lib.ETD1, data, data, data2, dt / 2., k_out=k1)              # k1 kept for the second stage
             data2.set_time(data.time + dt / 2.)
             self._stage_fused(_lib.ETD2RK2, data2, data, data, dt, deriv1=k1)               # k2 never stored
@@ -300,13 +325,19 @@ class RK2mid(RKBase):
             self.time += dt
             self.iteration += 1
             return
-        self.RHS.RHS(data, k1)
+        if lazy:
+            dt = self._rhs_and_dt(data, k1)
+        else:
+            self.RHS.RHS(data, k1)
         if getattr(self, "_coeff", None) is None:
             self._coeff = _if_coefficients(k1)
         self._stage(_lib.ETD1, data, data2, k1, None, k1, dt / 2.)        # a_n (euler where IF is None)
         data2.set_time(data.time + dt / 2.)
-        self.RHS.RHS(data2, k2)
-        self._stage(_lib.ETD2RK2, data, data, k1, k2, k1, dt)
+        if lazy and self._can_fuse(data, data2, k1):
+            self._stage_fused(_lib.ETD2RK2, data2, data, data, dt, deriv1=k1)
+        else:
+            self.RHS.RHS(data2, k2)
+            self._stage(_lib.ETD2RK2, data, data, k1, k2, k1, dt)
         data.set_time(data.time + dt)
         self.time += dt
         self.iteration += 1
@@ -323,20 +354,27 @@ class RK2trap(RKBase):
     def do_advance(self, data, dt):
         _settle(data)
         k1, k2 = self.deriv1, self.deriv2
-        if self._can_fuse(data, k1):
+        lazy = dt is None
+        if not lazy and self._can_fuse(data, k1):
             self._stage_fused(_lib.ETD1, data, data, data, dt, k_out=k1)
             data.set_time(data.time + dt)
             self._stage_fused(_lib.ETD2RK1, data, data, data, dt, deriv1=k1)
             self.time += dt
             self.iteration += 1
             return
-        self.RHS.RHS(data, k1)
+        if lazy:
+            dt = self._rhs_and_dt(data, k1)
+        else:
+            self.RHS.RHS(data, k1)
         if getattr(self, "_coeff", None) is None:
             self._coeff = _if_coefficients(k1)
         self._stage(_lib.ETD1, data, data, k1, None, k1, dt)
         data.set_time(data.time + dt)
-        self.RHS.RHS(data, k2)
-        self._stage(_lib.ETD2RK1, data, data, k1, k2, k1, dt)
+        if lazy and self._can_fuse(data, k1):
+            self._stage_fused(_lib.ETD2RK1, data, data, data, dt, deriv1=k1)
+        else:
+            self.RHS.RHS(data, k2)
+            self._stage(_lib.ETD2RK1, data, data, k1, k2, k1, dt)
         self.time += dt
         self.iteration += 1
 
@@ -381,18 +419,31 @@ class RK4(RKBase):
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
         _settle(data)
-        if self._can_fuse(data, self.total_deriv, self.temp_data):
+        lazy = dt is None
+        if not lazy and self._can_fuse(data, self.total_deriv, self.temp_data):
             return self._advance_fused(data, dt)
         aux = list(R.aux_eqns.values())
         a_old = [a.value for a in aux]
         a_final = [a.RHS(a.value) / 6. for a in aux]
-        R.RHS(data, k)                                     # k1
+        if lazy:
+            dt = self._rhs_and_dt(data, k)                 # k1 and the CFL limit of y from the same x pass
+        else:
+            R.RHS(data, k)                                 # k1
         if self._coeff is None:
             self._coeff = _if_coefficients(k)
             for (_, _, ct), (_, _, ck) in zip(self.total_deriv.components(), k.components()):
                 ct.integrating_factor = ck.integrating_factor
         self._rk4(data, tmp, 6., dt / 2., True, False)     # total = k1/6 ; tmp = S(y, k1, dt/2)
         tmp.set_time(data.time + dt / 2.)
+        if lazy and self._can_fuse(data, self.total_deriv, tmp):
+            self._rk4_fused(tmp, data, tmp, 3., dt / 2., False, False)      # k2
+            self._rk4_fused(tmp, data, tmp, 3., dt, False, False)           # k3
+            tmp.set_time(data.time + dt)
+            self._rk4_fused(tmp, data, data, 6., dt, False, True)           # k4
+            data.set_time(data.time + dt)
+            self.time += dt
+            self.iteration += 1
+            return
         for j, a in enumerate(aux):
             a.value = a_old[j] + dt / 2. * a.RHS(a.value)
             a_final[j] += a.RHS(a.value) / 3.
@@ -426,13 +477,17 @@ class CrankNicholsonVisc(TimeStepBase):
 
     def do_advance(self, data, dt):
         _settle(data)
-        if self._can_fuse(data):
+        lazy = dt is None
+        if not lazy and self._can_fuse(data):
             self._stage_fused(_lib.FUSE_CN, data, data, data, dt)
             data.set_time(data.time + dt)
             self.time += dt
             self.iteration += 1
             return
-        self.RHS.RHS(data, self.deriv)
+        if lazy:
+            dt = self._rhs_and_dt(data, self.deriv)
+        else:
+            self.RHS.RHS(data, self.deriv)
         if self._coeff is None:
             self._coeff = _if_coefficients(self.deriv)
         ys, ks = _kspace_tensors(data), _kspace_tensors(self.deriv)

@@ -20,10 +20,8 @@ TOL = 1e-10
 
 @pytest.fixture(scope="module", autouse=True)
 def _native_lib_loaded():
-    import torch
-    assert torch.cuda.is_available()
-    import dedalus._lib as L
-    assert b"sm_100a" in L.lib.ddl_version()
+    from conftest import native_lib_expected
+    native_lib_expected()
     yield
 
 

@@ -1,0 +1,187 @@
+"""GPU tests of the SURVEY 8(f) rows built on device reductions: volume-average diagnostics from one
+sweep (ddl_reduce_invariants), the CFL limit from inside the x pass (ddl_reduce_max_square,
+ddl_rhs_capture_max) and advance(dt=None) taking its time step from the step's own first RHS.
+Through the drop-in Python API -> C ABI -> kernels, against the oracle's restatement of
+dedalus/analysis/volume_average.py, fields.py:153-157 and physics.py:151-158,601-610,714-721,821-836."""
+import numpy as np
+import pytest
+
+from devutil import rel, dev_physics, oracle_physics, set_state, get_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_lib_loaded():
+    from conftest import native_lib_expected
+    native_lib_expected()
+    yield
+
+
+def close(a, b, rtol=1e-12, atol=1e-13):
+    return abs(a - b) <= atol + rtol * abs(b)
+
+
+def both(physics, shape, params, cfg):
+    import dedalus_oracle as orc
+    Po = oracle_physics(physics, shape, None, params)
+    do = orc.synthetic_ic(Po, cfg)
+    P = dev_physics(physics, shape, None, params)
+    data = P.create_fields(0.)
+    set_state(data, do.kvector())
+    return Po, do, P, data
+
+
+CASES = [("IncompressibleHydro", (64, 32), dict(nu=1e-3), 1), ("BoussinesqHydro", (32, 64), dict(nu=1e-3, kappa=2e-3), 4),
+         ("IncompressibleMHD", (64, 64), dict(nu=1e-3, eta=1e-3), 2), ("IncompressibleHydro", (32, 32, 32), dict(nu=1e-3), 3),
+         ("BoussinesqHydro", (16, 32, 64), dict(nu=1e-3, kappa=1e-3), 4), ("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3, eta=2e-3), 5)]
+
+
+@pytest.mark.parametrize("physics,shape,params,cfg", CASES)
+def test_volume_average_tasks_match_reference_definitions(physics, shape, params, cfg):
+    import dedalus_oracle as orc
+    import dedalus.analysis.volume_average as va
+    Po, do, P, data = both(physics, shape, params, cfg)
+    ref = orc.invariants(do)
+    assert close(va.ekin(data), ref["ekin"])
+    assert close(va.divergence_sum(data), ref["div_sum"], atol=1e-11)
+    assert abs(va.divergence(data) - ref["divergence"]) < 1e-11
+    assert close(va.vort_cenk(data), ref["cenk_num"] / ref["cenk_den"])
+    names = ["ux2", "uy2", "uz2"][:len(shape)]
+    for j, n in enumerate(names):
+        assert close(getattr(va, n)(data), ref["msq"][j])
+    if len(shape) == 2:
+        assert close(va.enstrophy(data), ref["enstrophy"])
+    else:
+        assert close(va.energy_dissipation(data), 2 * params["nu"] * ref["enstrophy"])
+        assert close(va.kinetic_helicity(data), ref["hel_kin"], atol=1e-12)
+    if physics == "IncompressibleMHD":
+        assert close(va.emag(data), ref["e2"])
+        assert close(va.mag_div_sum(data), ref["mag_div_sum"], atol=1e-11)
+        assert abs(va.mag_div(data) - ref["mag_div"]) < 1e-11
+        assert close(va.cross_helicity(data), ref["hel_cross"], atol=1e-12)
+        assert close(va.current_squared(data), ref["current2"])
+        for j, n in enumerate(["bx2", "by2", "bz2"][:len(shape)]):
+            assert close(getattr(va, n)(data), ref["msq"][len(shape) + j])
+        if len(shape) == 3:
+            assert close(va.magnetic_helicity(data), ref["hel_mag"], atol=1e-12)
+    if physics == "BoussinesqHydro":
+        assert close(va.temp2(data), 2 * ref["e2"])
+        assert close(va.thermal_energy_dissipation(data), params["kappa"] * ref["grad2_T"])
+
+
+def test_fused_invariants_equal_the_tensor_level_route():
+    """Same numbers from the one-sweep kernel and from the reference-shaped tensor operations it replaces
+    (forced by hiding the standard field list), also for a state with energy outside the dealias mask."""
+    import torch
+    import dedalus.analysis.volume_average as va
+    Po, do, P, data = both("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3), 5)
+    g = torch.Generator().manual_seed(3)
+    for _, _, c in data.components():
+        k = c["kspace"]                                 # handing the buffer out drops the 'dealiased' bit
+        k += 1e-3 * torch.view_as_complex(torch.randn(k.shape + (2,), generator=g, dtype=torch.float64)).to(k.device)
+    fused = [va.ekin(data), va.emag(data), va.divergence_sum(data), va.mag_div_sum(data), va.ux2(data), va.bz2(data),
+             va.cross_helicity(data), va.kinetic_helicity(data)]
+    saved = dict(va._PHYSICS_OF)
+    va._PHYSICS_OF.clear()
+    try:
+        plain = [va.ekin(data), va.emag(data), va.divergence_sum(data), va.mag_div_sum(data), va.ux2(data), va.bz2(data),
+                 va.cross_helicity(data), va.kinetic_helicity(data)]
+    finally:
+        va._PHYSICS_OF.update(saved)
+    for a, b in zip(fused, plain):
+        assert close(a, b, rtol=1e-12, atol=1e-11)
+
+
+def test_volume_average_set_shares_one_sweep(tmp_path):
+    import dedalus._lib as L
+    import dedalus.analysis.volume_average as va
+    Po, do, P, data = both("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3), 5)
+    vs = va.VolumeAverageSet(data, filename=str(tmp_path / "ts.dat"))
+    for name in ("ekin", "emag", "ux2", "by2", "divergence_sum", "mag_div_sum", "energy_dissipation"):
+        vs.add(name, "%10.5e")
+    n0 = L.launch_count()
+    vs.run()
+    assert L.launch_count() - n0 == 2            # the sweep and its final reduction, for seven tasks
+    line = open(str(tmp_path / "ts.dat")).read().strip().splitlines()[-1].split("\t")
+    assert len(line) == 8 and abs(float(line[1]) - va.ekin(data)) < 1e-5 * abs(va.ekin(data))
+
+
+@pytest.mark.parametrize("physics,shape,params,cfg", CASES)
+def test_compute_dt_matches_reference_route(physics, shape, params, cfg):
+    """compute_dt from the reduction inside the x pass == the reference's route (every component to x-space,
+    fields.py:153-157) == the oracle; and it leaves the state where it was."""
+    Po, do, P, data = both(physics, shape, params, cfg)
+    y0 = get_state(data)
+    dt_fused = P.compute_dt(data)
+    assert np.array_equal(get_state(data), y0)
+    assert all(c._curr_space == "kspace" for _, _, c in data.components())
+    P.dtlist = []
+    P.set_dtlist(data)                              # outside compute_dt: field.max_square(), component by component
+    dt_plain = min(P.dtlist)
+    assert close(dt_fused, dt_plain, rtol=1e-13)
+    assert close(dt_fused, Po.compute_dt(do), rtol=1e-13)
+
+
+def test_compute_dt_dealiases_like_the_reference():
+    """max_square goes through backward(), which masks the spectrum in place (representations.py:347-357)."""
+    import torch
+    Po, do, P, data = both("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3), 5)
+    for _, _, c in data.components():
+        k = c["kspace"]
+        k[5, 15, 3] = 0.3 + 0.1j                    # |kz index| = 15 >= 2/3 * 16: outside the mask
+    do2 = Po.create_fields(0.)
+    for (_, _, a), y in zip(do2.components(), get_state(data)):
+        a["kspace"] = y
+    dt_ref = Po.compute_dt(do2)
+    assert close(P.compute_dt(data), dt_ref, rtol=1e-13)
+    assert all(abs(c["kspace"][5, 15, 3].item()) == 0 for _, _, c in data.components())
+
+
+@pytest.mark.parametrize("integ", ["RK2mid", "RK2trap", "RK4", "CrankNicholsonVisc"])
+@pytest.mark.parametrize("physics,shape,params,cfg", [CASES[2], CASES[5], CASES[4]])
+def test_advance_takes_dt_from_its_first_rhs(integ, physics, shape, params, cfg):
+    """advance(data) with the CFL maxima captured in the step's first RHS == the reference's sequence
+    dt = CFL * compute_dt(data); do_advance(data, dt) == the oracle doing the same."""
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    Po, do, P, data = both(physics, shape, params, cfg)
+    P2 = dev_physics(physics, shape, None, params)
+    data2 = P2.create_fields(0.)
+    set_state(data2, do.kvector())
+    ti, ti2, to = getattr(tapi, integ)(P, CFL=0.3), getattr(tapi, integ)(P2, CFL=0.3), orc.INTEGRATORS[integ](Po)
+    ti.save_cadence = ti2.save_cadence = 10 ** 9
+    ti.max_save_period = ti2.max_save_period = 1e300
+    ti.iteration = ti2.iteration = 1                 # no snapshot at iteration 0
+    ti2.fuse_cfl = False
+    dt_old = np.finfo("d").max / 10.
+    for step in range(3):
+        dt = 0.3 * Po.compute_dt(do)
+        dt = min(dt, 1.05 * dt_old)
+        dt_old = dt
+        to.do_advance(do, dt)
+        ti.advance(data)
+        ti2.advance(data2)
+        assert close(ti.dt_old, dt, rtol=1e-12) and close(ti2.dt_old, dt, rtol=1e-12)
+    assert rel(get_state(data), do.kvector()) < 1e-10
+    assert rel(get_state(data), get_state(data2)) < 1e-11
+    assert close(data.time, do.time) and ti.iteration == 4
+
+
+def test_capture_costs_no_extra_transform():
+    """Launch accounting of advance(data) for 3-D MHD RK4 once the fused path is on: the lazy-dt step is
+    the fixed-dt step plus one stage launch (k1 evaluated unfused), while the reference's route adds the
+    passes of a whole inverse pipeline."""
+    import dedalus._lib as L
+    import dedalus.time_stepping.api as tapi
+    Po, do, P, data = both("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3, eta=1e-3), 5)
+    ti = tapi.RK4(P, CFL=0.3)
+    ti.save_cadence, ti.max_save_period, ti.iteration = 10 ** 9, 1e300, 1
+    ti.do_advance(data, 1e-3)
+    ti.do_advance(data, 1e-3)
+    n0 = L.launch_count(); ti.do_advance(data, 1e-3); fixed = L.launch_count() - n0
+    n0 = L.launch_count(); ti.advance(data); lazy = L.launch_count() - n0
+    ti.fuse_cfl = False
+    n0 = L.launch_count(); ti.advance(data); plain = L.launch_count() - n0
+    assert lazy == fixed + 1
+    assert plain >= fixed + 3
