@@ -14,10 +14,19 @@ for p in (os.path.join(ROOT, "dedalus-1.0_b200"), os.path.join(ROOT, "oracle"), 
     sys.path.insert(0, p)
 
 
+EMUL = os.environ.get("DDL_TEST_HOST_EMUL") == "1"    # tests/conftest.py host-emulation harness: gloo + CPU tensors
+
+
 def main(out_path):
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if EMUL:
+        import conftest  # noqa: F401  (points the package at the host-emulation library, in this process only)
+        dist.init_process_group("gloo")
+        dev = "cpu"
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dev = "cuda"
     import dedalus_oracle as orc
     from devutil import rel, dev_physics, oracle_physics
     import dedalus.time_stepping.api as tapi
@@ -55,13 +64,28 @@ def main(out_path):
         y1 = do.kvector()
         loc = np.stack([c["kspace"].cpu().numpy() for c in comps])
         num = torch.tensor([np.linalg.norm(loc - y1[:, rows]) ** 2, np.linalg.norm(y1[:, rows]) ** 2, rhs_rel],
-                           dtype=torch.float64, device="cuda")
+                           dtype=torch.float64, device=dev)
         mx = num[2:].clone()
         dist.all_reduce(num, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         ek = va.ekin(data, reduce_all=True)
+        ek_orc = orc.energy(do, "u")
+        # CFL limit from the reduction inside the x pass (slab: per-rank maxima, all-reduced),
+        # then one advance() that takes its dt from its own first RHS evaluation
+        dt_dev, dt_orc = P.compute_dt(data), Po.compute_dt(do)
+        ti.CFL, ti.iteration, ti.save_cadence, ti.max_save_period = 0.3, 1, 10 ** 9, 1e300
+        ti.advance(data)
+        to.do_advance(do, 0.3 * dt_orc)
+        y2 = do.kvector()
+        loc = np.stack([c["kspace"].cpu().numpy() for c in comps])
+        num2 = torch.tensor([np.linalg.norm(loc - y2[:, rows]) ** 2, np.linalg.norm(y2[:, rows]) ** 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(num2, op=dist.ReduceOp.SUM)
+        emag = va.emag(data, reduce_all=True) if physics == "IncompressibleMHD" else 0.0
         results.append({"physics": physics, "shape": shape, "world": world, "rel_vs_oracle": float(torch.sqrt(num[0] / num[1])),
-                        "rhs_rel": float(mx[0]), "ekin": float(ek), "ekin_oracle": float(orc.energy(do, "u")),
+                        "rhs_rel": float(mx[0]), "ekin": float(ek), "ekin_oracle": float(ek_orc),
+                        "dt": float(dt_dev), "dt_oracle": float(dt_orc), "rel_after_cfl_step": float(torch.sqrt(num2[0] / num2[1])),
+                        "dt_taken": float(ti.dt_old), "emag": float(emag),
+                        "emag_oracle": float(orc.energy(do, "B")) if physics == "IncompressibleMHD" else 0.0,
                         "exchanges": comps[0]._plan.pipeline.exchanges, "ky_layout": comps[0]._plan.ky_layout,
                         "exchange": comps[0]._plan.pipeline.exchange_kind})
     if rank == 0:

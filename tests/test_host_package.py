@@ -19,3 +19,36 @@ def test_gpu_test_files_pass_under_host_emulation():
     tail = "\n".join(r.stdout.strip().splitlines()[-15:])
     assert r.returncode == 0, tail
     assert " passed" in tail and "failed" not in tail, tail
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+import pytest
+
+
+@pytest.mark.parametrize("world,layout", [(2, "block"), (2, "cyclic"), (4, "cyclic")])
+def test_slab_package_under_host_emulation_gloo(world, layout, tmp_path):
+    """The N > 1 worker of tests/test_gpu_slab.py (drop-in API on every rank: RHS, steps, diagnostics,
+    compute_dt, advance with the captured CFL limit) over gloo with the collective exchange."""
+    import json
+    out = str(tmp_path / "res.json")
+    env = dict(os.environ, DDL_TEST_HOST_EMUL="1", DEDALUS_KY_LAYOUT=layout, DEDALUS_SLAB_EXCHANGE="collective", OMP_NUM_THREADS="1")
+    env.pop("DEDALUS_DDL_LIB", None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "gpu_slab_worker.py"), out]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:]
+    for case in json.load(open(out)):
+        assert case["rel_vs_oracle"] < 1e-10 and case["rhs_rel"] < 1e-12, case
+        assert abs(case["ekin"] - case["ekin_oracle"]) < 1e-12 and abs(case["emag"] - case["emag_oracle"]) < 1e-12, case
+        assert abs(case["dt"] - case["dt_oracle"]) < 1e-12 * case["dt_oracle"], case
+        assert abs(case["dt_taken"] - 0.3 * case["dt_oracle"]) < 1e-12 * case["dt_oracle"], case
+        assert case["rel_after_cfl_step"] < 1e-10, case
+        assert case["ky_layout"] == layout and case["exchanges"] > 0
