@@ -73,6 +73,11 @@ class FourierRepresentation(Representation):
         # lets the RHS skip mask passes and the RK sweep visit the retained modes only
         self._clean = True
         self._checked = False       # _clean is False and a device check has confirmed modes outside the mask
+        # True while the kx = 0 plane is KNOWN to be Hermitian-consistent (the spectrum of a real field):
+        # true of everything forward() and our kernels produce, dropped when the caller gets the buffer.
+        # The reference's x-space round trips (MHD RHS physics.py:797-815, max_square fields.py:153-157)
+        # replace a spectrum by that of its real part; _hermitian_project() is that image.
+        self._sym = True
         self._curr_space = "kspace"
         self.integrating_factor = None
         self.fwd_count = 0
@@ -92,6 +97,7 @@ class FourierRepresentation(Representation):
         'zero outside the mask' knowledge is dropped (internal code uses _k)."""
         self._clean = False
         self._checked = False
+        self._sym = False
         return self._k
 
     @property
@@ -109,6 +115,7 @@ class FourierRepresentation(Representation):
         elif space == "kspace":
             target = self._k
             self._clean = isinstance(data, (float, complex, int)) and data == 0
+            self._sym = self._clean
             self._checked = False
         else:
             raise KeyError("space must be either xspace or kspace.")
@@ -149,6 +156,7 @@ class FourierRepresentation(Representation):
                                   _plan.current_stream()))
         self._curr_space = "kspace"
         self._clean = True
+        self._sym = True
         self.fwd_count += 1
 
     @timer
@@ -190,6 +198,40 @@ class FourierRepresentation(Representation):
 
     dealias_23 = dealias
     dealias_23_cython = dealias
+
+    def _hermitian_project(self):
+        """k <- spectrum of the REAL PART of the field k describes: the kx = 0 plane becomes
+        (k(ky,kz,0) + conj k(-ky,-kz,0)) / 2, every other stored plane is unchanged.  This is what a
+        backward() + forward() round trip of the reference does to a spectrum whose kx = 0 plane is not
+        Hermitian-consistent (c2r reads only the real part of the kx = 0 line values) -- e.g. the 3-D
+        fields of turb_new, which never symmetrises that plane (init_cond.py:334-341).  Off the hot path:
+        runs once for a buffer the caller has written, as tensor operations on one plane."""
+        if self._sym:
+            return
+        self.require_space("kspace")
+        d = self._k
+        if self.ndim == 2:
+            row = d[0]
+            d[0] = 0.5 * (row + row.flip(0).roll(1, 0).conj())
+            self._sym = True
+            return
+        nranks = self._plan.nranks
+        if nranks > 1:
+            import torch.distributed as dist
+            mine = torch.view_as_real(d[:, :, 0].contiguous())
+            parts = [torch.empty_like(mine) for _ in range(nranks)]
+            dist.all_gather(parts, mine)
+            plane = torch.view_as_complex(torch.cat(parts, 0))
+            if self._plan.ky_layout == "cyclic":      # rank-major rows -> global ky order
+                ny = plane.shape[0]
+                plane = plane.reshape(nranks, ny // nranks, -1).transpose(0, 1).reshape(ny, -1).contiguous()
+        else:
+            plane = d[:, :, 0]
+        plane = 0.5 * (plane + plane.flip(0, 1).roll((1, 1), (0, 1)).conj())
+        if nranks > 1:
+            plane = plane[torch.as_tensor(self.local_rows["kspace"], device=d.device)]
+        d[:, :, 0] = plane
+        self._sym = True
 
     def verify_clean(self):
         """Re-establish the 'zero outside the dealias mask' knowledge after the buffer was handed

@@ -16,7 +16,7 @@ def _set(comp, index, value):
 def taylor_green(data):
     """Taylor-Green vortex.  The 2-D branch writes the very same eight entries as the reference
     (init_cond.py:43-51), including the four that land in the Nyquist-kx row of the transposed
-    layout; the 3-D branch follows :52-85."""
+    layout; the 3-D branch follows :52-85 (entries guarded by find_mode)."""
     mylog.info("Initializing Taylor Green Vortex.")
     u = data["u"]
     if u.ndim == 2:
@@ -29,10 +29,15 @@ def taylor_green(data):
         sy = {(1, 1, 1): 1, (1, 1, -1): 1, (-1, 1, 1): -1, (-1, 1, -1): -1,
               (1, -1, 1): 1, (1, -1, -1): 1, (-1, -1, 1): -1, (-1, -1, -1): -1}
         amp = 1j / 8.
-    for idx, s in sx.items():
-        _set(u["x"], idx, s * amp)
-    for idx, s in sy.items():
-        _set(u["y"], idx, s * amp)
+    for comp, table in ((u["x"], sx), (u["y"], sy)):
+        for idx, s in table.items():
+            if u.ndim == 3:
+                # the 3-D branch writes an entry only where find_mode() has the wavevector (:53-85): the
+                # four kx = -1 entries do not exist in the half-complex layout and are skipped
+                idx = comp.find_mode(idx)
+                if idx is None:
+                    continue
+            _set(comp, idx, s * amp)
 
 
 def sin_k(f, kindex, ampl=1.):
@@ -75,9 +80,21 @@ def alfven(data, k=(1, 0, 0), B0mag=5.0, u1mag=5e-6, p_vec=(0., 1., 0.)):
             data["B"][i].kdata[idx] = sign * B1[i] * 1j / 2.
 
 
-def turb_new(data, spec, tot_en=0.5, **kwargs):
+def _uniform(shape, device, rng):
+    """Uniform [0, 1) draws.  rng None: numpy's global generator on the host, exactly what the reference
+    calls (`na.random.random`, init_cond.py:312-322,455), so `np.random.seed(s)` reproduces its fields
+    number for number; rng "device": torch's generator on the GPU (no host pass; different numbers);
+    else a numpy Generator / RandomState."""
+    shape = tuple(int(n) for n in shape)
+    if rng == "device":
+        return torch.rand(shape, dtype=torch.float64, device=device)
+    draw = np.random.random(shape) if rng is None else rng.random(shape)
+    return torch.from_numpy(np.ascontiguousarray(draw)).to(device)
+
+
+def turb_new(data, spec, tot_en=0.5, rng=None, **kwargs):
     """Random-phase solenoidal velocity field with spectrum `spec` (Rogallo 1981; reference
-    init_cond.py:281-341).  Random numbers come from torch's generator on the device."""
+    init_cond.py:281-341).  `rng`: see _uniform (default: the reference's numpy global generator)."""
     c0 = data["u"][0]
     kk = torch.sqrt(c0.k2())
     kx, ky = c0.k["x"], c0.k["y"]
@@ -93,8 +110,7 @@ def turb_new(data, spec, tot_en=0.5, **kwargs):
     eps = np.finfo(np.complex128).eps
 
     def random_phase():
-        c0["xspace"] = torch.rand(tuple(int(n) for n in c0.local_shape["xspace"]), dtype=torch.float64,
-                                  device=c0.kdata.device)
+        c0["xspace"] = _uniform(c0.local_shape["xspace"], c0._k.device, rng)
         th = c0["kspace"].clone()
         return th / torch.abs(th + eps)
 
@@ -151,10 +167,10 @@ def vorticity_wave(data, mode, w_amp):
         data["u"]["y"]["kspace"] = -aux["psi"].deriv("x")
 
 
-def add_gaussian_white_noise(comp, std):
+def add_gaussian_white_noise(comp, std, rng=None):
     """Add a phasor of fixed amplitude and random phase to every mode, then restore Hermitian
-    symmetry (init_cond.py:440-464)."""
-    phase = 2 * np.pi * torch.rand(comp.kdata.shape, dtype=torch.float64, device=comp.kdata.device)
+    symmetry (init_cond.py:440-464).  `rng`: see _uniform."""
+    phase = 2 * np.pi * _uniform(comp._k.shape, comp._k.device, rng)
     amp = std / np.sqrt(comp.nmodes - 1)
     noise = amp * torch.exp(1j * phase)
     zero = comp.find_mode([0.] * comp.ndim)

@@ -146,24 +146,32 @@ class Physics(object):
         from ..utils.parallelism import reduce_max
         if not self._is_finalized:
             self._finalize()
-        state = []
-        for _, _, c in data.components():
-            c.require_space("kspace")
-            state.append(c._k)
+        state = self._max_square_side_effects(data)
         pl = next(data.components())[2]._plan
         out = torch.zeros(2, dtype=torch.float64, device=pl.device)
         pp = self._phys_params()
-        clean = all(c._clean for _, _, c in data.components())
-        flags = 0 if clean else _lib.RHS_DEALIAS_STATE        # max_square masks the spectra in place (representations.py:353)
         if pl.nranks > 1:
-            pl.pipeline.max_square(self._physics_id, pp, state, out, bool(flags))
+            pl.pipeline.max_square(self._physics_id, pp, state, out, False)
         else:
             w = pl.rhs_workspace(self._physics_id)
             check(lib.ddl_reduce_max_square(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), w.data_ptr(),
-                                            w.numel(), flags, out.data_ptr(), _plan.current_stream()))
-        for _, _, c in data.components():
-            c._clean = True
+                                            w.numel(), 0, out.data_ptr(), _plan.current_stream()))
         return self._finish_maxima(out)
+
+    @staticmethod
+    def _max_square_side_effects(data):
+        """What the reference's max_square leaves behind: u and B (not T) have been through x-space and
+        back (fields.py:153-157), so their spectra are the dealiased spectra of real fields, in place
+        (representations.py:347-357).  No-ops for buffers our own kernels produced.  Returns the k tensors."""
+        state = []
+        for name, _, c in data.components():
+            c.require_space("kspace")
+            if name in ("u", "B"):
+                c._hermitian_project()
+                if not c._clean:
+                    c.dealias()
+            state.append(c._k)
+        return state
 
     @staticmethod
     def _finish_maxima(out):
@@ -175,6 +183,7 @@ class Physics(object):
         device buffer (include/ddl.h: ddl_rhs_capture_max): the time-step limit of the state an RHS
         is evaluated at then costs no transform at all.  Returns the token for capture_end()."""
         import torch
+        self._max_square_side_effects(data)
         pl = next(data.components())[2]._plan
         out = torch.zeros(2, dtype=torch.float64, device=pl.device)
         check(lib.ddl_rhs_capture_max(pl.handle, out.data_ptr()))
@@ -221,6 +230,8 @@ class Physics(object):
         state_clean = deriv_clean = True
         for _, _, c in data.components():
             c.require_space("kspace")
+            if flags & _lib.RHS_DEALIAS_STATE:
+                c._hermitian_project()      # with the mask: the image of the reference's x-space round trip of the state
             state.append(c._k)
             state_clean = state_clean and c._clean
         for _, _, c in (deriv.components() if deriv is not None else ()):
@@ -455,11 +466,54 @@ class BoussinesqHydro(IncompressibleHydro):
         comp = deriv["T"][0]
         comp.integrating_factor = None if kappa == 0. else IntegratingFactor(comp, kappa, vo)
 
+    def _linear_terms_outside_mask(self, data, deriv):
+        """The reference adds buoyancy (g alpha_t T on u_dir, then the projection) and stratification
+        (-beta u_dir on T) to the FULL k-space arrays (physics.py:691-708), so a state with content
+        outside the 2/3 mask (hydro-type physics never dealias their state; e.g. the Nyquist-row
+        entries sin_k / cos_k write, init_cond.py:137-143) feels them there too, while the nonlinear terms
+        vanish there.  The fused pipeline covers the retained modes; this adds the masked-out ones.  Off the
+        hot path: only for a state the caller has written modes outside the mask into (tensor operations)."""
+        import torch
+        c0 = deriv["u"][0]
+        pl = c0._plan
+        outside = getattr(pl, "_outside_mask", None)
+        if outside is None:
+            keep = None
+            for name, kp in pl.keep_np.items():
+                i = pl.ktrans[name]
+                if i == 0 and pl.nranks > 1:
+                    kp = kp[pl.krows]
+                shp = [1] * pl.ndim
+                shp[i] = len(kp)
+                t = torch.from_numpy(np.ascontiguousarray(kp)).to(pl.device).reshape(shp)
+                keep = t if keep is None else keep & t
+            outside = pl._outside_mask = ~keep
+        p = self.parameters
+        d = {"x": 0, "y": 1, "z": 2}[p["boussinesq_direction"]]
+        zero = torch.zeros((), dtype=torch.complex128, device=pl.device)
+        buoy = torch.where(outside, (p["g"] * p["alpha_t"]) * data["T"].components[0]._k, zero)
+        k = [c0.k[self._trans[i]] for i in self.dims]
+        kdot = k[d] * buoy / c0.k2(no_zero=True)
+        for i in self.dims:
+            ci = deriv["u"][i]
+            ci._k.sub_(k[i] * kdot)
+            if i == d:
+                ci._k.add_(buoy)
+            ci._clean = False
+            ci._checked = False
+        dT = deriv["T"].components[0]
+        dT._k.sub_(torch.where(outside, p["beta"] * data["u"][d]._k, zero))
+        dT._clean = False
+        dT._checked = False
+
     def set_thermal_forcing(self, func):
         self.forcing_functions["ThermalForcing"] = func
 
     def RHS(self, data, deriv):
+        junk = not all(c._clean for _, _, c in data.components())
         IncompressibleHydro.RHS(self, data, deriv)
+        if junk:
+            self._linear_terms_outside_mask(data, deriv)
         if "ThermalForcing" in self.forcing_functions:
             deriv["T"]["kspace"].add_(self.forcing_functions["ThermalForcing"](data))
 

@@ -111,3 +111,61 @@ def test_oracle_transforms_match_reference(name, shape, L, dl):
     assert rel(c.deriv("y"), z[name + "_derivy"]) < 1e-15
     assert rel(g.k2(), z[name + "_k2"]) < 1e-15
     assert rel(c["xspace"], z[name + "_xb"]) < 1e-14
+
+
+# ---- goldens of the reference's own CFL-controlled advance() loop, IC generators and volume-average tasks
+# (tests/golden/make_sample_goldens.py -> tests/golden/samples/)
+SAMPLES = os.path.join(GOLDEN, "samples")
+TASK_KEY = {"ekin": "ekin", "emag": "e2", "enstrophy": "enstrophy", "divergence_sum": "div_sum", "mag_div_sum": "mag_div_sum",
+            "divergence": "divergence", "mag_div": "mag_div"}
+
+
+def oracle_task(P, data, name):
+    inv = orc.invariants(data)
+    nd = P.g.ndim
+    if name in TASK_KEY:
+        return inv[TASK_KEY[name]]
+    if name in ("ux2", "uy2", "uz2"):
+        return inv["msq"]["xyz".index(name[1])]
+    if name in ("bx2", "by2", "bz2"):
+        return inv["msq"][nd + "xyz".index(name[1])]
+    if name == "temp2":
+        return 2 * inv["e2"]
+    if name == "vort_cenk":
+        return inv["cenk_num"] / inv["cenk_den"]
+    if name == "energy_dissipation":
+        return 2 * P.parameters["nu"] * inv["enstrophy"]
+    if name == "thermal_energy_dissipation":
+        return P.parameters["kappa"] * inv["grad2_T"]
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("tag", ["cfl_turb2d", "cfl_mhd3d", "cfl_bouss2d", "cfl_bouss3d"])
+def test_oracle_cfl_runs_and_tasks_match_reference(tag):
+    z = np.load(os.path.join(SAMPLES, tag + ".npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    meta["length"] = None
+    P = make_physics(meta)
+    data = P.create_fields(0.0)
+    set_state(data, z["y0"])
+    names = [str(n) for n in z["task_names"]]
+    for n, want in zip(names, z["tasks0"]):
+        assert abs(oracle_task(P, data, n) - want) <= 1e-12 * max(1.0, abs(want)), n
+    ti = orc.INTEGRATORS[meta["integ"]](P)
+    dt_old = np.finfo("d").max / 10.0
+    for want in z["dts"]:
+        dt = min(meta["CFL"] * P.compute_dt(data), 1.05 * dt_old)      # time_step.py:170-179
+        dt_old = dt
+        assert abs(dt - want) <= 1e-12 * want
+        ti.do_advance(data, dt)
+    assert rel(data.kvector(), z["y1"]) < 1e-12
+    for n, want in zip(names, z["tasks1"]):
+        assert abs(oracle_task(P, data, n) - want) <= 1e-12 * max(1.0, abs(want)), n
+
+
+def test_oracle_taylor_green_3d_matches_reference():
+    z = np.load(os.path.join(SAMPLES, "init_cond.npz"))
+    P = orc.IncompressibleHydro((16, 16, 16))
+    data = P.create_fields(0.0)
+    orc.taylor_green(data)
+    assert np.array_equal(data.kvector(), z["tg3d"])
