@@ -373,16 +373,47 @@ extern "C" size_t ddl_workspace_bytes(const ddl_plan* pl, int n_in, int n_out) {
     return (size_t)(w.r0 + w.r1 + w.r2) * sizeof(cplx);
 }
 
-static void phys_counts(int ndim, int physics, int& ni, int& no, int& code) {
+// ni / no: inverse / forward transforms, code: kernel policy (tile_inst.cu), nc: state components.
+// The *_ADV ids are the advective-form policies for non-solenoidal states: ni = nc + (1 or 2) divergence
+// spectra, which live in caller-provided scratch arrays after the state in the pointer list.
+static void phys_counts(int ndim, int physics, int& ni, int& no, int& code, int* nc_out = nullptr) {
+    const bool adv = physics >= DDL_HYDRO_ADV;
+    const int base = adv ? physics - DDL_HYDRO_ADV : physics;
+    int nc;
     if (ndim == 3) {
-        if (physics == DDL_HYDRO) { ni = 3; no = 6; code = 3; }
-        else if (physics == DDL_BOUSSINESQ) { ni = 4; no = 9; code = 4; }
-        else { ni = 6; no = 9; code = 5; }
+        if (base == DDL_HYDRO) { nc = 3; no = 6; code = 3; }
+        else if (base == DDL_BOUSSINESQ) { nc = 4; no = 9; code = 4; }
+        else { nc = 6; no = 9; code = 5; }
     } else {
-        if (physics == DDL_HYDRO) { ni = 2; no = 3; code = 0; }
-        else if (physics == DDL_BOUSSINESQ) { ni = 3; no = 5; code = 1; }
-        else { ni = 4; no = 4; code = 2; }
+        if (base == DDL_HYDRO) { nc = 2; no = 3; code = 0; }
+        else if (base == DDL_BOUSSINESQ) { nc = 3; no = 5; code = 1; }
+        else { nc = 4; no = 4; code = 2; }
     }
+    ni = nc;
+    if (adv) {
+        ni += (base == DDL_MHD) ? 2 : 1;
+        no += ndim + (base == DDL_BOUSSINESQ ? 1 : 0);
+        code = (ndim == 3 ? 9 : 6) + base;
+    }
+    if (nc_out) *nc_out = nc;
+}
+
+// theta = i k.u (and i k.B) into the scratch arrays that follow the state (advective-form policies only)
+static int phase_theta(ddl_plan* pl, int physics, void* const* state, ddl_stream_t st) {
+    if (physics < DDL_HYDRO_ADV) return 0;
+    const int base = physics - DDL_HYDRO_ADV, nd = pl->ndim;
+    int ni, no, code, nc;
+    phys_counts(nd, physics, ni, no, code, &nc);
+    ThetaF f;
+    memset(&f, 0, sizeof(f));
+    f.g = pl->geom; f.nd = nd;
+    for (int c = 0; c < nd; ++c) f.U[c] = (const cplx*)state[c];
+    f.thu = (cplx*)state[nc];
+    if (base == DDL_MHD) {
+        for (int c = 0; c < nd; ++c) f.B[c] = (const cplx*)state[nd + c];
+        f.thb = (cplx*)state[nc + 1];
+    }
+    return launch_items(f, pl->nmodes, st, "theta");
 }
 
 extern "C" size_t ddl_rhs_workspace_bytes(const ddl_plan* pl, int physics) {
@@ -781,6 +812,7 @@ static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const 
 
 static int assemble_rk4_any(ddl_plan* pl, int code, void* const* E, void* const* state, const PhysConst& pc,
                             const ddl_stage_fuse* fu, ddl_stream_t st) {
+    if (code > 5) { set_error("the fused stage update exists for the solenoidal policies only (use ddl_rhs + ddl_stage)"); return -1; }
     switch (code) {
         case 0: return assemble_rk4<Hydro2C>(pl, E, state, pc, fu, st);
         case 1: return assemble_rk4<Bouss2C>(pl, E, state, pc, fu, st);
@@ -799,7 +831,13 @@ static int assemble_any(ddl_plan* pl, int code, void* const* E, void* const* sta
         case 2: return assemble<MHD2C>(pl, E, state, deriv, pc, st);
         case 3: return assemble<Hydro3C>(pl, E, state, deriv, pc, st);
         case 4: return assemble<Bouss3C>(pl, E, state, deriv, pc, st);
-        default: return assemble<MHD3C>(pl, E, state, deriv, pc, st);
+        case 5: return assemble<MHD3C>(pl, E, state, deriv, pc, st);
+        case 6: return assemble<Hydro2A>(pl, E, state, deriv, pc, st);
+        case 7: return assemble<Bouss2A>(pl, E, state, deriv, pc, st);
+        case 8: return assemble<MHD2A>(pl, E, state, deriv, pc, st);
+        case 9: return assemble<Hydro3A>(pl, E, state, deriv, pc, st);
+        case 10: return assemble<Bouss3A>(pl, E, state, deriv, pc, st);
+        default: return assemble<MHD3A>(pl, E, state, deriv, pc, st);
     }
 }
 
@@ -812,8 +850,8 @@ static int check_fuse(const ddl_stage_fuse* fu) {
 }
 
 static int check_physics(const ddl_plan* pl, int physics, const ddl_phys_params* prm) {
-    if (physics < 0 || physics > 2) { set_error("unknown physics id %d", physics); return -1; }
-    if (physics == DDL_BOUSSINESQ && (prm->boussinesq_dir < 0 || prm->boussinesq_dir >= pl->ndim)) {
+    if (physics < 0 || physics > DDL_MHD_ADV) { set_error("unknown physics id %d", physics); return -1; }
+    if ((physics == DDL_BOUSSINESQ || physics == DDL_BOUSSINESQ_ADV) && (prm->boussinesq_dir < 0 || prm->boussinesq_dir >= pl->ndim)) {
         set_error("boussinesq_direction component %d not present in %d-D", prm->boussinesq_dir, pl->ndim);
         return -1;
     }
@@ -823,15 +861,15 @@ static int check_physics(const ddl_plan* pl, int physics, const ddl_phys_params*
 static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* state, void* const* deriv,
                     void* work, size_t work_bytes, int flags, const ddl_stage_fuse* fuse, void* stream, bool front_only = false) {
     ddl_stream_t st = (ddl_stream_t)stream;
-    int ni, no, code;
+    int ni, no, code, ncomp;
     DDL_TRY(need_one_rank(pl, "ddl_rhs"));
     DDL_TRY(check_physics(pl, physics, prm));
-    phys_counts(pl->ndim, physics, ni, no, code);
+    phys_counts(pl->ndim, physics, ni, no, code, &ncomp);
     DDL_TRY(check_ws(pl, ni, no, work, work_bytes));
     const PhysConst pc = phys_const(prm);
-    const int ncomp = ni;   // state components == inverse transforms in the conservative forms
     if (flags & DDL_RHS_DEALIAS_STATE) DDL_TRY(mask_arrays(pl, ncomp, state, st));
     if ((flags & DDL_RHS_ZERO_FILL) && deriv) DDL_TRY(mask_arrays(pl, ncomp, deriv, st));
+    DDL_TRY(phase_theta(pl, physics, state, st));     // advective-form policies: divergence spectra into the scratch arrays
 
     WsLayout w = ws_layout(pl, ni, no);
     cplx* r0 = (cplx*)work; cplx* r1 = r0 + w.r0; cplx* r2 = r1 + w.r1;
@@ -888,6 +926,10 @@ extern "C" int ddl_slab_rows(const ddl_plan* pl, int64_t* cyl_of_rank) {
 static int need_3d(const ddl_plan* pl) {
     if (pl->ndim != 3) { set_error("the slab phase API is 3-D only"); return -1; }
     return 0;
+}
+extern "C" int ddl_slab_theta(ddl_plan* pl, int physics, void* const* state, void* stream) {
+    if (physics < 0 || physics > DDL_MHD_ADV) { set_error("unknown physics id %d", physics); return -1; }
+    return phase_theta(pl, physics, state, (ddl_stream_t)stream);
 }
 extern "C" int ddl_slab_zinv(ddl_plan* pl, int nf, void* const* k_in, void* const* ks_out, void* stream) {
     DDL_TRY(need_3d(pl));
@@ -1020,7 +1062,8 @@ extern "C" int ddl_reduce_invariants(ddl_plan* pl, int physics, void* const* sta
     static_assert(DDL_NINV == DDL_NINV_, "include/ddl.h and reduce.cuh disagree on the invariant count");
     ddl_stream_t st = (ddl_stream_t)stream;
     if (!out || !state) { set_error("ddl_reduce_invariants: NULL argument"); return -1; }
-    if (physics < 0 || physics > 2) { set_error("unknown physics id %d", physics); return -1; }
+    if (physics < 0 || physics > DDL_MHD_ADV) { set_error("unknown physics id %d", physics); return -1; }
+    if (physics >= DDL_HYDRO_ADV) physics -= DDL_HYDRO_ADV;
     if (pl->ndim == 3) {
         if (physics == DDL_HYDRO) return invariants_t<3, 0>(pl, state, flags, out, st);
         if (physics == DDL_BOUSSINESQ) return invariants_t<3, 1>(pl, state, flags, out, st);

@@ -50,7 +50,7 @@ DDL_HD double k2nz2(double kx, double ky) {
 
 // ------------------------------------------------------------------ 3-D hydro
 struct Hydro3C {
-    static constexpr int NI = 3, NO = 6, NS = 0, NC = 3, NDIM = 3;
+    static constexpr int NI = 3, NO = 6, NS = 0, NC = 3, NDIM = 3, NG1 = 0;
     DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
         const double u = in[0], v = in[1], w = in[2];
         o[0] = u * u; o[1] = u * v; o[2] = u * w; o[3] = v * v; o[4] = v * w; o[5] = w * w;
@@ -66,7 +66,7 @@ struct Hydro3C {
 
 // ------------------------------------------------------------------ 3-D Boussinesq
 struct Bouss3C {
-    static constexpr int NI = 4, NO = 9, NS = 4, NC = 4, NDIM = 3;
+    static constexpr int NI = 4, NO = 9, NS = 4, NC = 4, NDIM = 3, NG1 = 1;
     DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
         const double u = in[0], v = in[1], w = in[2], T = in[3];
         o[0] = u * u; o[1] = u * v; o[2] = u * w; o[3] = v * v; o[4] = v * w; o[5] = w * w;
@@ -86,7 +86,7 @@ struct Bouss3C {
 
 // ------------------------------------------------------------------ 3-D MHD
 struct MHD3C {
-    static constexpr int NI = 6, NO = 9, NS = 0, NC = 6, NDIM = 3;
+    static constexpr int NI = 6, NO = 9, NS = 0, NC = 6, NDIM = 3, NG1 = 3;
     DDL_HD static void apply(const double* in, double* o, const PhysConst& pc) {
         const double u = in[0], v = in[1], w = in[2], a = in[3], b = in[4], c = in[5];
         const double f = pc.inv_fpr;
@@ -108,7 +108,7 @@ struct MHD3C {
 
 // ------------------------------------------------------------------ 2-D
 struct Hydro2C {
-    static constexpr int NI = 2, NO = 3, NS = 0, NC = 2, NDIM = 2;
+    static constexpr int NI = 2, NO = 3, NS = 0, NC = 2, NDIM = 2, NG1 = 0;
     DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
         o[0] = in[0] * in[0]; o[1] = in[0] * in[1]; o[2] = in[1] * in[1];
     }
@@ -121,7 +121,7 @@ struct Hydro2C {
 };
 
 struct Bouss2C {
-    static constexpr int NI = 3, NO = 5, NS = 3, NC = 3, NDIM = 2;
+    static constexpr int NI = 3, NO = 5, NS = 3, NC = 3, NDIM = 2, NG1 = 1;
     DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
         const double u = in[0], v = in[1], T = in[2];
         o[0] = u * u; o[1] = u * v; o[2] = v * v; o[3] = u * T; o[4] = v * T;
@@ -138,7 +138,7 @@ struct Bouss2C {
 };
 
 struct MHD2C {
-    static constexpr int NI = 4, NO = 4, NS = 0, NC = 4, NDIM = 2;
+    static constexpr int NI = 4, NO = 4, NS = 0, NC = 4, NDIM = 2, NG1 = 2;
     DDL_HD static void apply(const double* in, double* o, const PhysConst& pc) {
         const double u = in[0], v = in[1], a = in[2], b = in[3];
         const double f = pc.inv_fpr;
@@ -155,9 +155,59 @@ struct MHD2C {
     }
 };
 
+
+// ------------------------------------------------------------------ advective-form variants
+// The conservative forms above equal the reference's advective forms only for SOLENOIDAL u (and B):
+//   d_j(u_i u_j) = (u.grad) u_i + u_i (div u),   d_j(u_j T) = u.grad T + T (div u),
+//   ((curl B) x B)_i = d_j(B_i B_j) - B_i (div B) - d_i(B^2/2).
+// The reference (physics.py:197-228, 527-599, 664-712, 770-819) evaluates the advective forms whatever the
+// state, and never removes a compressive part the caller put there (e.g. the kz axis of turb_new's 3-D
+// fields, init_cond.py:334-341).  For such states the host layer switches to these policies: the
+// divergences theta_u = div u (theta_B = div B) are extra inverse-transform inputs (their spectra i k.u are
+// written by ThetaF into caller-provided scratch arrays that follow the state in the pointer list), the
+// products u_i theta_u (- B_i theta_B / 4 pi rho0, T theta_u) extra forward transforms, and the assembly
+// adds them back.  Same results as the reference for ANY state; ~1.4x the transforms of the solenoidal path.
+template <class BASE, int ND, int NB>
+struct AdvOf {
+    // inputs: BASE inputs, theta_u [, theta_B when NB == ND]; outputs: BASE outputs, c_i (ND) [, T theta when NB == 1]
+    static constexpr int NTH = (NB == ND) ? 2 : 1;
+    static constexpr int NI = BASE::NI + NTH, NO = BASE::NO + ND + (NB == 1 ? 1 : 0);
+    static constexpr int NS = BASE::NS, NC = BASE::NC, NDIM = ND, NG1 = BASE::NG1;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst& pc) {
+        BASE::apply(in, o, pc);
+        const double thu = in[BASE::NI];
+#pragma unroll
+        for (int i = 0; i < ND; ++i) o[BASE::NO + i] = in[i] * thu;
+        if (NB == ND) {
+            const double thb = in[BASE::NI + 1] * pc.inv_fpr;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) o[BASE::NO + i] -= in[ND + i] * thb;
+        }
+        if (NB == 1) o[BASE::NO + ND] = in[ND] * thu;
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx* S, cplx* D, double kx, double ky, double kz, const PhysConst& pc) {
+        BASE::assemble(P, S, D, kx, ky, kz, pc);
+        // the momentum correction c goes through the projector, which is linear: D_u += P[c]
+        cplx c[3] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
+#pragma unroll
+        for (int i = 0; i < ND; ++i) c[i] = P[BASE::NO + i];
+        if (ND == 3) project3(c[0], c[1], c[2], kx, ky, kz, k2nz3(kx, ky, kz));
+        else project2(c[0], c[1], kx, ky, k2nz2(kx, ky));
+#pragma unroll
+        for (int i = 0; i < ND; ++i) D[i] = D[i] + c[i];
+        if (NB == 1) D[ND] = D[ND] + P[BASE::NO + ND];
+    }
+};
+typedef AdvOf<Hydro3C, 3, 0> Hydro3A;
+typedef AdvOf<Bouss3C, 3, 1> Bouss3A;
+typedef AdvOf<MHD3C, 3, 3> MHD3A;
+typedef AdvOf<Hydro2C, 2, 0> Hydro2A;
+typedef AdvOf<Bouss2C, 2, 1> Bouss2A;
+typedef AdvOf<MHD2C, 2, 2> MHD2A;
+
 // identity policy for the plain real<->complex transforms
 struct PhysNone {
-    static constexpr int NI = 1, NO = 1, NS = 0, NC = 1, NDIM = 0;
+    static constexpr int NI = 1, NO = 1, NS = 0, NC = 1, NDIM = 0, NG1 = 0;
     DDL_HD static void apply(const double* in, double* o, const PhysConst&) { o[0] = in[0]; }
 };
 

@@ -196,6 +196,32 @@ struct DerivF {
     }
 };
 
+// divergence spectra theta = i k.F of the velocity (and magnetic) field, the extra inverse-transform inputs
+// of the advective-form policies (physics_ops.cuh AdvOf)
+struct ThetaF {
+    KGeom g;
+    const cplx* U[3];
+    const cplx* B[3];
+    cplx* thu;
+    cplx* thb;          // NULL unless the state carries B
+    int nd;
+    DDL_HD void operator()(long long i) const {
+        int idx[3];
+        split3(i, g.dim, idx[0], idx[1], idx[2]);
+        double kk[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+            if (g.ax[l] >= 0) kk[g.ax[l]] = g.kv[l][idx[l]];
+        cplx du = mk(0.0, 0.0), db = mk(0.0, 0.0);
+        for (int c = 0; c < nd; ++c) {
+            du = du + scal(U[c][i], kk[c]);
+            if (thb) db = db + scal(B[c][i], kk[c]);
+        }
+        thu[i] = mk(-du.y, du.x);
+        if (thb) thb[i] = mk(-db.y, db.x);
+    }
+};
+
 // spectral assembly over the retained modes: compact product arrays -> full deriv arrays
 template <class PHYS>
 struct AssembleF {

@@ -161,6 +161,7 @@ struct InvariantsF {
             du = du + scal(v[c], kk[c]);
         }
         acc[0] += w * 0.5 * eu;
+        acc[22] += w * (du.x * du.x + du.y * du.y);         // |k.u|^2: compressive part of sum |k|^2 |u|^2 = |k.u|^2 + |k x u|^2
         acc[2] += sqrt(du.x * du.x + du.y * du.y);          // |i k.u|, unweighted (volume_average.py:287-295)
         acc[8] += w * (-du.y);                               // i k.u = (-Im, Re)
         acc[9] += w * du.x;
@@ -198,6 +199,7 @@ struct InvariantsF {
             }
             acc[1] += w * 0.5 * eb;
             acc[3] += sqrt(db.x * db.x + db.y * db.y);
+            acc[23] += w * (db.x * db.x + db.y * db.y);
             acc[10] += w * (-db.y);
             acc[11] += w * db.x;
             acc[7] += w * ub;

@@ -28,6 +28,13 @@ int DDL_CAT(run_tile_, DDL_N)(int mode, int dir, int phys, const TileParams& p, 
                 case 3: return launch_tile<N, TM_FUSED, 0, Hydro3C>(p, nthreads, s);
                 case 4: return launch_tile<N, TM_FUSED, 0, Bouss3C>(p, nthreads, s);
                 case 5: return launch_tile<N, TM_FUSED, 0, MHD3C>(p, nthreads, s);
+                // advective-form policies for non-solenoidal states (physics_ops.cuh AdvOf)
+                case 6: return launch_tile<N, TM_FUSED, 0, Hydro2A>(p, nthreads, s);
+                case 7: return launch_tile<N, TM_FUSED, 0, Bouss2A>(p, nthreads, s);
+                case 8: return launch_tile<N, TM_FUSED, 0, MHD2A>(p, nthreads, s);
+                case 9: return launch_tile<N, TM_FUSED, 0, Hydro3A>(p, nthreads, s);
+                case 10: return launch_tile<N, TM_FUSED, 0, Bouss3A>(p, nthreads, s);
+                case 11: return launch_tile<N, TM_FUSED, 0, MHD3A>(p, nthreads, s);
             }
     }
     set_error("run_tile: bad mode/physics %d/%d", mode, phys);

@@ -187,7 +187,7 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
 #pragma unroll
                     for (int f = 0; f < NI; ++f) {
                         if (f < PHYS::NDIM) { a0 = tmax_nn(a0, ax[f] * ax[f]); a1 = tmax_nn(a1, ay[f] * ay[f]); }
-                        else { b0 = tmax_nn(b0, ax[f] * ax[f]); b1 = tmax_nn(b1, ay[f] * ay[f]); }
+                        else if (f < PHYS::NDIM + PHYS::NG1) { b0 = tmax_nn(b0, ax[f] * ax[f]); b1 = tmax_nn(b1, ay[f] * ay[f]); }
                     }
                     m0 = tmax_nn(tmax_nn(m0, a0), a1);
                     m1 = tmax_nn(tmax_nn(m1, b0), b1);

@@ -336,7 +336,7 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
 #pragma unroll
                 for (int f = 0; f < NI; ++f) {
                     if (f < PHYS::NDIM) { a0 = xmax_nn(a0, u0[f] * u0[f]); a1 = xmax_nn(a1, u1[f] * u1[f]); }
-                    else { b0 = xmax_nn(b0, u0[f] * u0[f]); b1 = xmax_nn(b1, u1[f] * u1[f]); }
+                    else if (f < PHYS::NDIM + PHYS::NG1) { b0 = xmax_nn(b0, u0[f] * u0[f]); b1 = xmax_nn(b1, u1[f] * u1[f]); }
                 }
                 m0 = xmax_nn(xmax_nn(m0, a0), a1);
                 m1 = xmax_nn(xmax_nn(m1, b0), b1);

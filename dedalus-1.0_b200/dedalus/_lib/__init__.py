@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("DEDALUS_DDL_LIB") or os.path.join(_HERE, "libddl_b200
 EXPORTS = [
     "ddl_plan_create", "ddl_plan_create_slab", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
     "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_deriv", "ddl_rhs", "ddl_stage",
-    "ddl_rk4_stage", "ddl_cn_step", "ddl_rhs_stage", "ddl_slab_assemble_stage", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_zinv", "ddl_slab_yinv",
+    "ddl_rk4_stage", "ddl_cn_step", "ddl_rhs_stage", "ddl_slab_assemble_stage", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_theta", "ddl_slab_zinv", "ddl_slab_yinv",
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
     "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count",
@@ -21,12 +21,13 @@ EXPORTS = [
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
+ADV = 3     # DDL_*_ADV = base id + 3: advective-form policies for states that are not solenoidal
 EULER, ETD1, ETD2RK1, ETD2RK2 = 0, 1, 2, 3
 RHS_ZERO_FILL, RHS_DEALIAS_STATE = 1, 2
 STAGE_RETAINED_ONLY = 1
 # include/ddl.h DDL_INV_*: entries of the vector ddl_reduce_invariants fills
 INV = dict(ekin=0, e2=1, div_sum=2, mag_div_sum=3, enstrophy=4, current2=5, hel_kin=6, hel_cross=7, div_re=8, div_im=9,
-           mag_div_re=10, mag_div_im=11, cenk_num=12, cenk_den=13, msq=14, hel_mag=20, grad2_T=21)
+           mag_div_re=10, mag_div_im=11, cenk_num=12, cenk_den=13, msq=14, hel_mag=20, grad2_T=21, div2=22, mag_div2=23)
 NINV = 24
 
 
@@ -55,6 +56,7 @@ def bind_slab(lib):
     lib.ddl_slab_info.argtypes = [vp, vp]
     lib.ddl_slab_rows.argtypes = [vp, vp]
     lib.ddl_slab_zinv.argtypes = [vp, i32, vp, vp, vp]
+    lib.ddl_slab_theta.argtypes = [vp, i32, vp, vp]
     lib.ddl_slab_yinv.argtypes = [vp, i32, vp, vp, vp]
     lib.ddl_slab_xfused.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.ddl_slab_xc2r.argtypes = [vp, vp, vp, vp]

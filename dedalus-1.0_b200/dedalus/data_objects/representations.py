@@ -78,6 +78,10 @@ class FourierRepresentation(Representation):
         # The reference's x-space round trips (MHD RHS physics.py:797-815, max_square fields.py:153-157)
         # replace a spectrum by that of its real part; _hermitian_project() is that image.
         self._sym = True
+        # vector components: True while the field this component belongs to is KNOWN to be solenoidal (the
+        # fused RHS may then use the conservative products), False: known compressive (advective-form
+        # policies), None: the caller has written the buffer since the last check (physics.verify_solenoidal)
+        self._soln = True
         self._curr_space = "kspace"
         self.integrating_factor = None
         self.fwd_count = 0
@@ -98,6 +102,7 @@ class FourierRepresentation(Representation):
         self._clean = False
         self._checked = False
         self._sym = False
+        self._soln = None
         return self._k
 
     @property
@@ -116,6 +121,7 @@ class FourierRepresentation(Representation):
             target = self._k
             self._clean = isinstance(data, (float, complex, int)) and data == 0
             self._sym = self._clean
+            self._soln = True if self._clean else None
             self._checked = False
         else:
             raise KeyError("space must be either xspace or kspace.")
@@ -157,6 +163,7 @@ class FourierRepresentation(Representation):
         self._curr_space = "kspace"
         self._clean = True
         self._sym = True
+        self._soln = None           # an x-space field the caller wrote: divergence unknown
         self.fwd_count += 1
 
     @timer

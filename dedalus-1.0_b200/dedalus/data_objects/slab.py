@@ -18,7 +18,9 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
-_COUNTS = {0: (3, 6), 1: (4, 9), 2: (6, 9)}     # physics id -> (inverse, forward) transforms, 3-D
+# physics id -> (inverse, forward) transforms, 3-D; 3..5: advective-form policies for non-solenoidal states
+# (include/ddl.h DDL_*_ADV: the divergence spectra are extra inverse inputs, their products extra forward outputs)
+_COUNTS = {0: (3, 6), 1: (4, 9), 2: (6, 9), 3: (4, 9), 4: (5, 13), 5: (8, 12)}
 
 
 def _ptrs(tensors):
@@ -332,16 +334,22 @@ class SlabPipeline(object):
         else:
             self._check(lib.ddl_slab_assemble(h, physics_id, pp, _ptrs(e), _ptrs(state), _ptrs(deriv), st))
 
-    def rhs(self, physics_id, params, state, deriv, dealias_state, zero_fill, fuse=None):
-        """deriv = RHS(state) (physics.py:527-599 / 664-712 / 770-819), local slabs in and out."""
+    def rhs(self, physics_id, params, state, deriv, dealias_state, zero_fill, fuse=None, ncomp=None):
+        """deriv = RHS(state) (physics.py:527-599 / 664-712 / 770-819), local slabs in and out.
+        Advective-form policies (physics_id >= 3): `state` = the ncomp state slabs followed by the scratch
+        slabs for the divergence spectra; they take the collective exchange (the arenas of the peer-store
+        path are sized for the solenoidal policies)."""
         lib, h, st = self.lib, self.h, self._stream()
         ni, no = _COUNTS[physics_id]
-        p2p = self.exchange_kind == "p2p" and self.P > 1 and not self.skip_exchange
-        peer = self.exchange_kind == "peer" and self.P > 1 and not self.skip_exchange
+        adv = physics_id >= 3
+        p2p = self.exchange_kind == "p2p" and self.P > 1 and not self.skip_exchange and not adv
+        peer = self.exchange_kind == "peer" and self.P > 1 and not self.skip_exchange and not adv
         pp = C.byref(params)
         if dealias_state:
-            for t in state:
+            for t in state[:ncomp]:
                 self._check(lib.ddl_dealias(h, t.data_ptr(), st))
+        if adv:
+            self._check(lib.ddl_slab_theta(h, physics_id, _ptrs(state), st))
         if zero_fill:
             for t in deriv:
                 self._check(lib.ddl_dealias(h, t.data_ptr(), st))

@@ -210,6 +210,32 @@ class Physics(object):
             field.zero_all()
         deriv.set_time(data.time)
 
+    # ------------------------------------------------------------------ solenoidal or not
+    SOLENOIDAL_TOL = 1e-12      # compressive fraction sqrt(sum |k.u|^2 / sum |k|^2 |u|^2) below which u counts as div-free
+
+    def verify_solenoidal(self, data):
+        """Make sure every vector component of `data` knows whether its field is solenoidal (`_soln`).
+
+        The fused pipeline's conservative products equal the reference's advective forms only for
+        div u = div B = 0 (include/ddl.h DDL_*_ADV).  Buffers our own kernels wrote inherit the answer
+        (derivatives are projected / curls, so an update keeps whatever its start state had); for a buffer
+        the CALLER has written since the last check one sweep of ddl_reduce_invariants measures the
+        compressive fraction of u and B.  Returns True when the whole state is solenoidal."""
+        vec = [(n, f) for n, f in data if n in ("u", "B")]
+        if any(c._soln is None for _, f in vec for _, c in f):
+            from ..analysis.volume_average import invariants
+            from .._lib import INV
+            inv = invariants(data)
+            if inv is None:
+                raise NotImplementedError("verify_solenoidal: not a standard u [+ T | B] state")
+            tot = inv[0]
+            for n, f in vec:
+                comp, rot = (tot[INV["div2"]], 2 * tot[INV["enstrophy"]]) if n == "u" else (tot[INV["mag_div2"]], 2 * tot[INV["current2"]])
+                ok = bool(comp <= self.SOLENOIDAL_TOL ** 2 * (comp + rot))
+                for _, c in f:
+                    c._soln = ok
+        return all(c._soln for _, f in vec for _, c in f)
+
     def can_fuse_stage(self):
         """True when nothing is added to deriv after the fused pipeline (rotation, forcing), so an
         integrator may ask for the spectral assembly fused with its stage update."""
@@ -245,6 +271,12 @@ class Physics(object):
             flags &= ~_lib.RHS_DEALIAS_STATE
         pl = next(data.components())[2]._plan
         pp = self._phys_params()
+        if not self.verify_solenoidal(data):
+            # a compressive part in u or B (whatever put it there, the reference keeps it): advective-form
+            # policies, which need scratch arrays for the divergence spectra after the state
+            if fuse is not None:
+                raise RuntimeError("the fused stage update needs a solenoidal state (time_step._can_fuse checks it)")
+            return self._advective_rhs(pl, pp, data, deriv, state, out, flags)
         if pl.nranks > 1:
             # slab-decomposed: pipeline phases with the exchange between the z and y passes
             pl.pipeline.rhs(self._physics_id, pp, state, out, bool(flags & _lib.RHS_DEALIAS_STATE),
@@ -259,11 +291,35 @@ class Physics(object):
                               w.data_ptr(), w.numel(), flags, _plan.current_stream()))
         for _, _, c in (deriv.components() if deriv is not None else ()):
             c._clean = True
+            c._soln = True
         if flags & _lib.RHS_DEALIAS_STATE:
             for _, _, c in data.components():
                 c._clean = True
         if deriv is not None:
             deriv.set_time(data.time)
+
+    def _advective_rhs(self, pl, pp, data, deriv, state, out, flags):
+        import torch
+        pid = self._physics_id + _lib.ADV
+        nth = 2 if self._physics_id == _lib.MHD else 1
+        scratch = getattr(pl, "_theta_scratch", None)
+        if scratch is None or len(scratch) < nth:
+            scratch = pl._theta_scratch = [torch.empty_like(state[0]) for _ in range(nth)]
+        ptrs = state + scratch[:nth]
+        if pl.nranks > 1:
+            pl.pipeline.rhs(pid, pp, ptrs, out, bool(flags & _lib.RHS_DEALIAS_STATE), bool(flags & _lib.RHS_ZERO_FILL),
+                            ncomp=len(state))
+        else:
+            w = pl.rhs_workspace(pid)
+            check(lib.ddl_rhs(pl.handle, pid, C.byref(pp), _lib.ptr_array(ptrs), _lib.ptr_array(out), w.data_ptr(), w.numel(),
+                              flags, _plan.current_stream()))
+        for _, _, c in deriv.components():
+            c._clean = True
+            c._soln = True
+        if flags & _lib.RHS_DEALIAS_STATE:
+            for _, _, c in data.components():
+                c._clean = True
+        deriv.set_time(data.time)
 
     # ------------------------------------------------------------------ unfused helpers
     def gradX(self, X, output):

@@ -46,13 +46,25 @@ def _mark(sd, clean):
         c._clean = clean
 
 
-def _settle(sd):
+def _inherit(out, start):
+    """A stage update out = a * start + (combination of derivatives) keeps the solenoidal-or-not verdict of
+    its start state: derivatives of u are projected, those of B are curls (physics.verify_solenoidal)."""
+    if out is start:
+        return
+    for (_, _, co), (_, _, cs) in zip(out.components(), start.components()):
+        co._soln = cs._soln
+
+
+def _settle(sd, R=None):
     """Before a step: components whose buffer was handed out since the last step get their
-    'dealiased' bit re-checked on the device (FourierRepresentation.verify_clean)."""
+    'dealiased' bit re-checked on the device (FourierRepresentation.verify_clean) and, given the physics
+    object, their fields' 'solenoidal' verdict (Physics.verify_solenoidal): both decide which kernels run."""
     for _, _, c in sd.components():
         c.require_space("kspace")
         if not c._clean and not c._checked:
             c.verify_clean()
+    if R is not None and hasattr(R, "verify_solenoidal"):
+        R.verify_solenoidal(sd)
 
 
 def _plan_of(sd):
@@ -255,6 +267,8 @@ class TimeStepBase(object):
             return False
         if R.aux_eqns or not R.can_fuse_stage():
             return False
+        if not all(c._soln for sd in sds if sd is not None for _, _, c in sd.components()):
+            return False            # compressive (or unchecked) state: advective-form RHS, which has no fused stage
         return _all_clean(*sds)
 
     def _stage_fused(self, kind, state_in, start, out, dt_step, deriv1=None, k_out=None, total=None, wdiv=1., first=0, last=0):
@@ -277,6 +291,7 @@ class TimeStepBase(object):
         for sd in (out, total, k_out):
             if sd is not None:
                 _mark(sd, True)
+        _inherit(out, start)
         if k_out is not None:
             k_out.set_time(state_in.time)
 
@@ -290,6 +305,7 @@ class TimeStepBase(object):
                             _lib.ptr_array(a), _lib.ptr_array(b) if b is not None else None, coeff, order,
                             float(dt), _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
         _mark(out, clean)
+        _inherit(out, start)
 
 
 class RKBase(TimeStepBase):
@@ -314,7 +330,7 @@ class RK2mid(RKBase):
         self.deriv2 = self.RHS.create_fields(0.)
 
     def do_advance(self, data, dt):
-        _settle(data)
+        _settle(data, self.RHS)
         data2, k1, k2 = self.data2, self.deriv1, self.deriv2
         lazy = dt is None
         if not lazy and self._can_fuse(data, data2, k1):
@@ -352,7 +368,7 @@ class RK2trap(RKBase):
         self.deriv2 = self.RHS.create_fields(0.)
 
     def do_advance(self, data, dt):
-        _settle(data)
+        _settle(data, self.RHS)
         k1, k2 = self.deriv1, self.deriv2
         lazy = dt is None
         if not lazy and self._can_fuse(data, k1):
@@ -400,6 +416,7 @@ class RK4(RKBase):
                                 _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
         _mark(out, clean)
         _mark(self.total_deriv, clean)
+        _inherit(out, y)
 
     def _rk4_fused(self, state_in, y, out, wdiv, dt_step, first, last):
         self._stage_fused(_lib.FUSE_RK4, state_in, y, out, dt_step, total=self.total_deriv, wdiv=wdiv, first=first, last=last)
@@ -418,7 +435,7 @@ class RK4(RKBase):
 
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
-        _settle(data)
+        _settle(data, self.RHS)
         lazy = dt is None
         if not lazy and self._can_fuse(data, self.total_deriv, self.temp_data):
             return self._advance_fused(data, dt)
@@ -476,7 +493,7 @@ class CrankNicholsonVisc(TimeStepBase):
         self._coeff = None
 
     def do_advance(self, data, dt):
-        _settle(data)
+        _settle(data, self.RHS)
         lazy = dt is None
         if not lazy and self._can_fuse(data):
             self._stage_fused(_lib.FUSE_CN, data, data, data, dt)

@@ -23,7 +23,16 @@ extern "C" {
 typedef struct ddl_plan ddl_plan;
 
 /* physics ids (dedalus/physics/physics.py:419,612,724) */
-enum { DDL_HYDRO = 0, DDL_BOUSSINESQ = 1, DDL_MHD = 2 };
+enum { DDL_HYDRO = 0, DDL_BOUSSINESQ = 1, DDL_MHD = 2,
+       /* The same right-hand sides for a state that is NOT solenoidal.  The fused pipeline evaluates the
+        * nonlinear terms in conservative form (d_j(u_i u_j), ...), which equals the reference's advective
+        * form (physics.py:197-228 XgradY) only where div u = div B = 0; the reference evaluates u.grad u
+        * whatever the state.  The *_ADV policies add the missing u_i div u (- B_i div B / 4 pi rho0,
+        * T div u) products: every `state` pointer list then carries, AFTER the state components, one
+        * scratch k-space array (two for MHD) that receives the divergence spectra.  ddl_rhs,
+        * ddl_reduce_max_square and the ddl_slab_* phases accept them (ddl_slab_theta fills the scratch
+        * arrays); ddl_rhs_stage / ddl_slab_assemble_stage do not. */
+       DDL_HYDRO_ADV = 3, DDL_BOUSSINESQ_ADV = 4, DDL_MHD_ADV = 5 };
 
 /* stage-update kinds (dedalus/time_stepping/forward_step_cy_3d.pyx:17,34,63,95) */
 enum { DDL_EULER = 0, DDL_ETD1 = 1, DDL_ETD2RK1 = 2, DDL_ETD2RK2 = 3 };
@@ -114,6 +123,8 @@ int ddl_rhs(ddl_plan* plan, int physics, const ddl_phys_params* params,
  * elements to every peer. */
 int ddl_slab_info(const ddl_plan* plan, int64_t* out16);
 int ddl_slab_rows(const ddl_plan* plan, int64_t* cyl_of_rank);
+/* *_ADV physics only: theta_u = i k.u (theta_B = i k.B) into the scratch arrays that follow the state */
+int ddl_slab_theta(ddl_plan* plan, int physics, void* const* state, void* stream);
 /* inverse z pass of nf fields: local k slabs (retained modes only are read) -> k-side arrays */
 int ddl_slab_zinv(ddl_plan* plan, int nf, void* const* k_in, void* const* kside_out, void* stream);
 /* inverse y pass: x-side arrays -> b arrays */
@@ -234,6 +245,8 @@ enum {
     DDL_INV_MSQ = 14,        /* +c: sum w |component c|^2, c < 6       ux2 .. bz2, temp2 :123-177 */
     DDL_INV_HEL_MAG = 20,    /* sum w Re(A . conj(B)), A = i J / k^2, 3-D MHD only */
     DDL_INV_GRAD2_T = 21,    /* sum w k^2 |T|^2                        thermal_energy_dissipation / kappa :262-271 */
+    DDL_INV_DIV2 = 22,       /* sum w |k.u|^2: with 2 * ENSTROPHY it splits sum w |k|^2 |u|^2 into compressive + solenoidal */
+    DDL_INV_MAG_DIV2 = 23,   /* sum w |k.B|^2 (with 2 * CURRENT2); the host layer picks the *_ADV policies from these */
     DDL_NINV = 24
 };
 int ddl_reduce_invariants(ddl_plan* plan, int physics, void* const* state, int flags, double* out, void* stream);

@@ -42,6 +42,7 @@ def _pa(arrs):
 
 class EmulPlan:
     PHYS = {"IncompressibleHydro": 0, "BoussinesqHydro": 1, "IncompressibleMHD": 2}
+    ADV = 3          # include/ddl.h DDL_*_ADV = base + 3: advective-form policies for non-solenoidal states
 
     def __init__(self, lib, grid, nranks=1, rank=0, layout=0):
         """grid: oracle Grid (supplies k values and the dealias mask exactly as the host layer will).
@@ -94,14 +95,17 @@ class EmulPlan:
         self.check(self.lib.ddl_deriv(self.plan, _p(k), _p(o), axis, None))
         return o
 
-    def rhs(self, physics, params, state, flags=1):
-        pid = self.PHYS[physics]
+    def rhs(self, physics, params, state, flags=1, adv=False):
+        """adv: use the advective-form policy (state need not be solenoidal); the divergence scratch arrays the
+        ABI wants after the state are appended here."""
+        pid = self.PHYS[physics] + (self.ADV if adv else 0)
         pp = PhysParams(params.get("rho0", 1.0), params.get("g", 1.0), params.get("alpha_t", 1.0),
                         params.get("beta", 1.0), {"x": 0, "y": 1, "z": 2}[params.get("boussinesq_direction", "z")], 0)
         state = [np.ascontiguousarray(s, dtype=np.complex128).copy() for s in state]
-        deriv = [np.full(self.g.kshape, np.nan + 0j, dtype=np.complex128) for _ in state]
+        deriv = [np.full(state[0].shape, np.nan + 0j, dtype=np.complex128) for _ in state]
+        scratch = [np.full(state[0].shape, np.nan + 0j, dtype=np.complex128) for _ in range(2 if physics == "IncompressibleMHD" else 1)] if adv else []
         w = self._ws(self.lib.ddl_rhs_workspace_bytes(self.plan, pid))
-        self.check(self.lib.ddl_rhs(self.plan, pid, C.byref(pp), _pa(state), _pa(deriv), _p(w), C.c_size_t(w.nbytes),
+        self.check(self.lib.ddl_rhs(self.plan, pid, C.byref(pp), _pa(state + scratch), _pa(deriv), _p(w), C.c_size_t(w.nbytes),
                                     flags, None))
         return np.stack(deriv), np.stack(state)
 

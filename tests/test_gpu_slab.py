@@ -46,5 +46,6 @@ def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, tmp_pat
         assert abs(case["dt"] - case["dt_oracle"]) < 1e-12 * case["dt_oracle"], case
         assert abs(case["dt_taken"] - 0.3 * case["dt_oracle"]) < 1e-12 * case["dt_oracle"], case
         assert case["rel_after_cfl_step"] < 1e-10, case
+        assert case["solenoidal_verdict"] == (not case["compressive"]), case
         assert abs(case["emag"] - case["emag_oracle"]) < 1e-12, case
         assert case["exchanges"] > 0 and case["ky_layout"] == layout and case["exchange"] == exchange

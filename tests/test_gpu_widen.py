@@ -286,3 +286,81 @@ def test_cfl_controlled_runs_match_the_reference(tag, fuse_cfl):
     for n, want in zip(names, z["tasks1"]):
         got = known[n](data)
         assert abs(got - want) <= 1e-11 * max(1.0, abs(want)), (n, got, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# States that are not solenoidal: the reference evaluates u.grad u whatever the state (physics.py:197-228);
+# the package measures the compressive fraction of caller-written states and switches to the advective-form
+# policies (include/ddl.h DDL_*_ADV)
+# ---------------------------------------------------------------------------------------------
+def _compressive_state(Po, seed):
+    import dedalus_oracle as orc
+    do = Po.create_fields(0.)
+    rng = np.random.default_rng(seed)
+    for _, _, c in do.components():
+        c["xspace"] = 0.3 * rng.standard_normal(Po.g.shape)
+        c.require_space("kspace")
+    return do
+
+
+NONSOL = [("IncompressibleHydro", (32, 64), dict(nu=1e-3)), ("BoussinesqHydro", (32, 32), dict(nu=1e-3, kappa=2e-3, g=1.5, beta=0.5)),
+          ("IncompressibleMHD", (64, 32), dict(nu=1e-3, eta=2e-3, rho0=0.7)), ("IncompressibleHydro", (16, 32, 32), dict(nu=1e-2)),
+          ("BoussinesqHydro", (32, 16, 32), dict(nu=1e-2, kappa=1e-2, alpha_t=0.5)), ("IncompressibleMHD", (32, 32, 16), dict(nu=1e-2, eta=1e-2))]
+
+
+@pytest.mark.parametrize("physics,shape,params", NONSOL)
+def test_rhs_of_a_compressive_state_matches_the_reference_form(physics, shape, params):
+    Po = oracle_physics(physics, shape, None, params)
+    do = _compressive_state(Po, 17)
+    P = dev_physics(physics, shape, None, params)
+    data, deriv = P.create_fields(0.), P.create_fields(0.)
+    set_state(data, do.kvector())
+    ko = Po.create_fields(0.)
+    Po.RHS(do, ko)
+    P.RHS(data, deriv)
+    assert not P.verify_solenoidal(data)
+    assert rel(get_state(deriv), ko.kvector()) < 1e-13
+    assert rel(get_state(data), do.kvector()) < 1e-14          # MHD: the state is replaced by its x-space round-trip image
+    # the same state made solenoidal takes the conservative pipeline again and still matches
+    for name, f in data:
+        if name in ("u", "B"):
+            f.div_free()
+    for name, f in do:
+        if f.ncomp > 1:
+            f.div_free()
+    Po.RHS(do, ko)
+    P.RHS(data, deriv)
+    assert P.verify_solenoidal(data)
+    assert rel(get_state(deriv), ko.kvector()) < 1e-13
+
+
+@pytest.mark.parametrize("integ", ["RK2mid", "RK2trap", "RK4", "CrankNicholsonVisc"])
+@pytest.mark.parametrize("physics,shape,params", [NONSOL[2], NONSOL[3], NONSOL[4], NONSOL[5]])
+def test_steps_from_a_compressive_state_match_oracle(integ, physics, shape, params):
+    """The compressive part is never removed (the derivative is projected, the state is not): every stage state
+    inherits it, every RHS of the run takes the advective-form policy, no stage is fused."""
+    import dedalus_oracle as orc
+    import dedalus.time_stepping.api as tapi
+    Po = oracle_physics(physics, shape, None, params)
+    do = _compressive_state(Po, 23)
+    P = dev_physics(physics, shape, None, params)
+    data = P.create_fields(0.)
+    set_state(data, do.kvector())
+    ti, to = getattr(tapi, integ)(P), orc.INTEGRATORS[integ](Po)
+    for _ in range(4):
+        ti.do_advance(data, 2e-3)
+        to.do_advance(do, 2e-3)
+    assert rel(get_state(data), do.kvector()) < 1e-10
+    assert not any(c._soln for n, _, c in data.components() if n == "u")
+    assert orc.divergence_sum(do, "u") > 1.0
+
+
+def test_roundoff_divergence_keeps_the_conservative_pipeline():
+    Po, do, P, data = both("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3, eta=1e-3), 5)
+    assert P.verify_solenoidal(data)
+    import dedalus._lib as L
+    n0 = L.launch_count()
+    assert P.verify_solenoidal(data) and L.launch_count() == n0       # cached: no sweep, no sync
+    data["u"]["x"]["kspace"]                                          # handing a buffer out asks for a re-check
+    assert data["u"]["x"]._soln is None
+    assert P.verify_solenoidal(data) and L.launch_count() == n0 + 2

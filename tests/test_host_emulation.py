@@ -186,3 +186,30 @@ def test_emulated_fused_cn_step_equals_rhs_then_cn(lib, physics, shape):
     ref = pl.cn_step(state, k, coeff, 1, 0.05)                 # CN updates the state it evaluated the RHS on
     r = pl.rhs_stage(physics, params, state, 5, state, coeff, 1, 0.05)
     assert rel(r["out"], ref) < 1e-15
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (16, 32), (8, 32, 16)])
+@pytest.mark.parametrize("physics", ["IncompressibleHydro", "BoussinesqHydro", "IncompressibleMHD"])
+def test_emulated_advective_policies_match_reference_form_for_compressive_states(lib, physics, shape):
+    """include/ddl.h DDL_*_ADV: for a state with div u, div B != 0 the conservative pipeline is O(1) away from
+    the reference's advective forms (physics.py:197-228); the advective-form policies reproduce them."""
+    kw = dict(direction="y") if (physics == "BoussinesqHydro" and len(shape) == 2) else {}
+    P = orc.PHYSICS[physics](shape, **kw)
+    if physics != "IncompressibleHydro":
+        P.parameters.update(dict(g=1.3, beta=0.7, rho0=0.6))
+    d = P.create_fields(0.)
+    rng = np.random.default_rng(1)
+    for _, _, c in d.components():
+        c["xspace"] = rng.standard_normal(P.g.shape)
+        c.require_space("kspace")
+    y = d.kvector()
+    k = P.create_fields(0.)
+    P.RHS(d, k)
+    params = dict(P.parameters)
+    if kw:
+        params["boussinesq_direction"] = "y"
+    pl = emul.EmulPlan(lib, P.g)
+    dk, _ = pl.rhs(physics, params, y, adv=True)
+    assert rel(dk, k.kvector()) < 1e-14
+    dk0, _ = pl.rhs(physics, params, y, adv=False)
+    assert rel(dk0, k.kvector()) > 0.1

@@ -51,4 +51,5 @@ def test_slab_package_under_host_emulation_gloo(world, layout, tmp_path):
         assert abs(case["dt"] - case["dt_oracle"]) < 1e-12 * case["dt_oracle"], case
         assert abs(case["dt_taken"] - 0.3 * case["dt_oracle"]) < 1e-12 * case["dt_oracle"], case
         assert case["rel_after_cfl_step"] < 1e-10, case
+        assert case["solenoidal_verdict"] == (not case["compressive"]), case
         assert case["ky_layout"] == layout and case["exchanges"] > 0
