@@ -16,7 +16,8 @@ from .._lib import lib, check, INV
 from ..data_objects import plan as _plan
 from ..utils.parallelism import com_sys, reduce_sum, reduce_mean, reduce_max
 
-_PHYSICS_OF = {("u",): _lib.HYDRO, ("u", "T"): _lib.BOUSSINESQ, ("u", "B"): _lib.MHD}
+_PHYSICS_OF = {("u",): _lib.HYDRO, ("u", "T"): _lib.BOUSSINESQ, ("u", "B"): _lib.MHD,
+               ("u", "c"): _lib.BOUSSINESQ}         # passive tracer: a scalar in the T slot
 _shared = {"on": False, "key": None, "val": None}     # one sweep per VolumeAverageSet.run()
 
 

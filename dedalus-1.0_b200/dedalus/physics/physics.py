@@ -199,6 +199,8 @@ class Physics(object):
     def _phys_params(self):
         p = self.parameters
         d = p.get("boussinesq_direction", "z")
+        if self._tracer:
+            return _lib.PhysParams(float(p.get("rho0", 1.0)), 0.0, 0.0, 0.0, 0, 0)      # tracer in the T slot, no coupling
         return _lib.PhysParams(float(p.get("rho0", 1.0)), float(p.get("g", 1.0)), float(p.get("alpha_t", 1.0)),
                                float(p.get("beta", 1.0)), {"x": 0, "y": 1, "z": 2}[d], 0)
 
@@ -424,7 +426,14 @@ class IncompressibleHydro(Physics):
         self.parameters["shear_rate"] = 0.
         self.parameters["Omega"] = None
         if self._tracer:
-            raise NotImplementedError("Passive tracer (physics.use_tracer) is not implemented in the CUDA backend.")
+            # passive scalar c advected by u (physics.py:468-470,516-522,580-582): d_t c = -u.grad c + c_diff lap c.
+            # That is the Boussinesq temperature equation without buoyancy and stratification, so the plain
+            # hydro class runs the Boussinesq kernels with g = alpha_t = beta = 0 and c in the T slot.
+            if type(self) is not IncompressibleHydro:
+                raise NotImplementedError("Passive tracer (physics.use_tracer) is implemented for IncompressibleHydro only.")
+            self._field_list.append(("c", "ScalarField"))
+            self.parameters["c_diff"] = 0.
+            self._physics_id = _lib.BOUSSINESQ
         self._first_rhs = True
 
     def __reduce__(self):
@@ -444,6 +453,9 @@ class IncompressibleHydro(Physics):
         nu, vo = self.parameters["nu"], self.parameters["viscosity_order"]
         for _, comp in deriv["u"]:
             comp.integrating_factor = None if nu == 0. else IntegratingFactor(comp, nu, vo)
+        if self._tracer:
+            comp, diff = deriv["c"][0], self.parameters["c_diff"]
+            comp.integrating_factor = None if diff == 0. else IntegratingFactor(comp, diff, vo)
 
     def set_velocity_forcing(self, func):
         self.forcing_functions["VelocityForcing"] = func

@@ -147,7 +147,77 @@ def run_cases():
         print("%-12s dts=%s t=%.6g |y1|=%.12e" % (tag, ["%.5e" % d for d in dts], data.time, np.linalg.norm(kvec(data))))
 
 
+def noise_state(data, seed, solenoidal=True):
+    rng = np.random.default_rng(seed)
+    for fn, f in data:
+        for i, c in f:
+            c['xspace'] = 0.5 * rng.standard_normal(tuple(c.local_shape['xspace']))
+            c['kspace']
+        if solenoidal and f.ncomp > 1:
+            f.div_free()
+
+
+def forcing_arrays(RHS, seed, n):
+    """n fixed, dealiased, Hermitian-consistent spectra (the forward transform of real noise)."""
+    aux = RHS.create_fields(0.)
+    rng = np.random.default_rng(seed)
+    out = []
+    c = aux['u'][0]
+    for _ in range(n):
+        c['xspace'] = 0.2 * rng.standard_normal(tuple(c.local_shape['xspace']))
+        out.append(c['kspace'].copy())
+    return out
+
+
+def option_cases():
+    """Rotation, forcing and passive-tracer branches of the reference RHS (physics.py:560-586,709-711), fixed dt."""
+    out = {}
+
+    def run(tag, RHS, data, integ, dt, nsteps, extra=None):
+        y0 = kvec(data)
+        ti = getattr(ts, integ)(RHS)
+        for _ in range(nsteps):
+            ti.do_advance(data, dt)
+        out[tag + "_y0"], out[tag + "_y1"] = y0, kvec(data)
+        for k, v in (extra or {}).items():
+            out[tag + "_" + k] = v
+        print("%-10s |y1|=%.12e" % (tag, np.linalg.norm(out[tag + "_y1"])))
+
+    RHS, d = physics("IncompressibleHydro", (16, 16, 16), dict(nu=1e-2, Omega=np.array([1.0, 0.2, 0.3])))
+    noise_state(d, 31)
+    run("rot3d", RHS, d, "RK2mid", 1e-2, 3)
+
+    RHS, d = physics("IncompressibleHydro", (16, 32), dict(nu=1e-2, Omega=0.7))
+    noise_state(d, 32)
+    run("rot2d", RHS, d, "RK2trap", 1e-2, 3)
+
+    RHS, d = physics("IncompressibleHydro", (16, 32), dict(nu=1e-2))
+    noise_state(d, 33)
+    F = forcing_arrays(RHS, 34, 2)
+    RHS.set_velocity_forcing(lambda data, i: F[i])
+    run("force2d", RHS, d, "RK2mid", 1e-2, 3, dict(F=np.stack(F)))
+
+    RHS, d = physics("BoussinesqHydro", (16, 16, 16), dict(nu=1e-2, kappa=1e-2))
+    noise_state(d, 35)
+    F = forcing_arrays(RHS, 36, 1)
+    RHS.set_thermal_forcing(lambda data: F[0])
+    run("heat3d", RHS, d, "RK2mid", 1e-2, 3, dict(F=np.stack(F)))
+
+    decfg.set('physics', 'use_tracer', 'True')
+    try:
+        RHS, d = physics("IncompressibleHydro", (16, 32), dict(nu=1e-2, c_diff=2e-2))
+        noise_state(d, 37)
+        run("tracer2d", RHS, d, "RK2mid", 1e-2, 3)
+        RHS, d = physics("IncompressibleHydro", (16, 16, 16), dict(nu=1e-2, c_diff=0.))
+        noise_state(d, 38)
+        run("tracer3d", RHS, d, "RK2trap", 1e-2, 3)
+    finally:
+        decfg.set('physics', 'use_tracer', 'False')
+    np.savez_compressed(os.path.join(OUT, "options.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ic_cases()
     run_cases()
+    option_cases()

@@ -364,3 +364,56 @@ def test_roundoff_divergence_keeps_the_conservative_pipeline():
     data["u"]["x"]["kspace"]                                          # handing a buffer out asks for a re-check
     assert data["u"]["x"]._soln is None
     assert P.verify_solenoidal(data) and L.launch_count() == n0 + 2
+
+
+# ---------------------------------------------------------------------------------------------
+# Rotation, forcing and passive-tracer branches of the reference RHS (physics.py:560-586,709-711) against
+# runs of the reference itself (tests/golden/samples/options.npz)
+# ---------------------------------------------------------------------------------------------
+OPTION_CASES = {
+    "rot3d": ("IncompressibleHydro", (16, 16, 16), dict(nu=1e-2, Omega=np.array([1.0, 0.2, 0.3])), "RK2mid"),
+    "rot2d": ("IncompressibleHydro", (16, 32), dict(nu=1e-2, Omega=0.7), "RK2trap"),
+    "force2d": ("IncompressibleHydro", (16, 32), dict(nu=1e-2), "RK2mid"),
+    "heat3d": ("BoussinesqHydro", (16, 16, 16), dict(nu=1e-2, kappa=1e-2), "RK2mid"),
+    "tracer2d": ("IncompressibleHydro", (16, 32), dict(nu=1e-2, c_diff=2e-2), "RK2mid"),
+    "tracer3d": ("IncompressibleHydro", (16, 16, 16), dict(nu=1e-2, c_diff=0.), "RK2trap"),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(OPTION_CASES))
+def test_rhs_options_match_reference_runs(tag):
+    import torch
+    import dedalus.time_stepping.api as tapi
+    from dedalus.config import decfg
+    z = np.load(os.path.join(SAMPLES, "options.npz"))
+    physics, shape, params, integ = OPTION_CASES[tag]
+    decfg.set("physics", "use_tracer", "True" if tag.startswith("tracer") else "False")
+    try:
+        P = dev_physics(physics, shape, None, params)
+        data = P.create_fields(0.)
+        if tag.startswith("tracer"):
+            assert list(data.fields) == ["u", "c"]
+        set_state(data, z[tag + "_y0"])
+        dev = next(data.components())[2]._k.device
+        if tag == "force2d":
+            F = [torch.from_numpy(f).to(dev) for f in z[tag + "_F"]]
+            P.set_velocity_forcing(lambda d, i: F[i])
+        if tag == "heat3d":
+            F = [torch.from_numpy(f).to(dev) for f in z[tag + "_F"]]
+            P.set_thermal_forcing(lambda d: F[0])
+        ti = getattr(tapi, integ)(P)
+        for _ in range(3):
+            ti.do_advance(data, 1e-2)
+        assert rel(get_state(data), z[tag + "_y1"]) < 1e-10
+    finally:
+        decfg.set("physics", "use_tracer", "False")
+
+
+def test_tracer_with_other_physics_is_refused_loudly():
+    from dedalus.config import decfg
+    decfg.set("physics", "use_tracer", "True")
+    try:
+        with pytest.raises(NotImplementedError):
+            dev_physics("IncompressibleMHD", (16, 16, 16))
+    finally:
+        decfg.set("physics", "use_tracer", "False")
