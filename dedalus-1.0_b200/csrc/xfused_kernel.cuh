@@ -243,7 +243,9 @@ DDL_HD double xmax_nn(double m, double a) { return (a > m || a != a) ? a : m; }
 // CFL: also reduce max_{x,i} u_i(x)^2 and max_{x,i} B_i(x)^2 (T^2) over the grid points of this CTA into p.cfl -
 // the real-space fields exist only here, so the time-step limit (physics.py:601-610,821-836) costs
 // no transform of its own.
-template <int N, class PHYS, int NT, int G, bool CFL = false>
+// KNC > 0: the retained-mode count is the compile-time constant KNC (the 2/3 rule: N/3 + 1) instead of p.kn, so the
+// zero tests of the Hermitian pack and the bounds of the unpack fold at compile time (launch variant 3, below).
+template <int N, class PHYS, int NT, int G, bool CFL = false, int KNC = 0>
 DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
     constexpr int NI = PHYS::NI, NO = PHYS::NO;
     constexpr int NS = NI > NO ? NI : NO;     // pencil slots per line pair
@@ -254,7 +256,7 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
     static_assert(NT % TP == 0, "CTA size must be a multiple of the pencil group");
     constexpr int S = XFac<N>::S;
     const cplx* __restrict__ tw = p.tw;
-    const int kn = p.kn;
+    const int kn = KNC > 0 ? KNC : p.kn;
     const long long plane = (long long)by * p.s_outer;
     const int pair0 = bx * G;
 
@@ -469,6 +471,9 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
 
 // Launch variants (ddl_set_option("xfused_variant", v); the default is the measured best):
 //   0: 6 warps per CTA, 3 CTAs per SM   1: 9 warps per CTA, 2 CTAs per SM   2: 6 warps, 2 CTAs (more registers)
+//   3: shape 0 with the retained-mode count of the 2/3 rule (N/3 + 1) as a compile-time constant; falls back to 0 for
+//      any other mask.  NOT YET TIMED (added after the round's GPU budget was spent; cuobjdump: 2 296 -> 1 960 static
+//      instructions for <512, MHD3C>): round 2 measures it with profiles/kernel_times.py --opt xfused_variant=0,3
 template <int N, class PHYS, int V> struct XFusedCfg {
     static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
     static constexpr int G = (N >= 512) ? 1 : 512 / N;
@@ -484,22 +489,22 @@ template <int N, class PHYS, int V> struct XFusedCfg {
 };
 
 #if DDL_DEVICE_BUILD
-template <int N, class PHYS, int V, bool CFL>
+template <int N, class PHYS, int V, bool CFL, int KNC = 0>
 __global__ void __maxnreg__((XFusedCfg<N, PHYS, V>::MAXREG))
 xfused_kernel(const __grid_constant__ XFusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    xfused_block<N, PHYS, XFusedCfg<N, PHYS, V>::NT, XFusedCfg<N, PHYS, V>::G, CFL>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
+    xfused_block<N, PHYS, XFusedCfg<N, PHYS, V>::NT, XFusedCfg<N, PHYS, V>::G, CFL, KNC>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
 }
 #endif
 
 // returns 0 on success, negative on error
-template <int N, class PHYS, int V, bool CFL = false>
+template <int N, class PHYS, int V, bool CFL = false, int KNC = 0>
 int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     using Cfg = XFusedCfg<N, PHYS, V>;
     const int pairs = (p.n_lines + 1) / 2;
     const int gx = (pairs + Cfg::G - 1) / Cfg::G;
 #if DDL_DEVICE_BUILD
-    auto kern = xfused_kernel<N, PHYS, V, CFL>;
+    auto kern = xfused_kernel<N, PHYS, V, CFL, KNC>;
     static bool attr_done = false;
     if (!attr_done) {
         DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -515,7 +520,7 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     prof_begin("x_fused", stream);
     cplx* tile = (cplx*)malloc(Cfg::SMEM);
     for (int by = 0; by < n_outer; ++by)
-        for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G, CFL>(p, tile, bx, by);
+        for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G, CFL, KNC>(p, tile, bx, by);
     free(tile);
 #endif
     return 0;
@@ -524,6 +529,7 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
 template <int N, class PHYS>
 int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t stream) {
     if (p.cfl) return launch_xfused_v<N, PHYS, 0, true>(p, n_outer, stream);     // capture: default CTA shape only
+    if (variant == 3 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 0, false, N / 3 + 1>(p, n_outer, stream);
 #if DDL_DEVICE_BUILD
     if (variant == 1) return launch_xfused_v<N, PHYS, 1>(p, n_outer, stream);
     if (variant == 2) return launch_xfused_v<N, PHYS, 2>(p, n_outer, stream);

@@ -417,3 +417,30 @@ def test_tracer_with_other_physics_is_refused_loudly():
             dev_physics("IncompressibleMHD", (16, 16, 16))
     finally:
         decfg.set("physics", "use_tracer", "False")
+
+
+@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (16, 32, 128)), ("BoussinesqHydro", (16, 16, 256)),
+                                           ("IncompressibleHydro", (16, 16, 512)), ("IncompressibleMHD", (8, 16, 512)),
+                                           ("IncompressibleMHD", (8, 16, 1024))])
+def test_xfused_launch_variants_agree(physics, shape):
+    """ddl_set_option("xfused_variant", v): the CTA shapes 0-2 and variant 3 (retained-mode count of the 2/3 rule as
+    a compile-time constant) are the same arithmetic per pencil (bit-identical in the host emulation; the device
+    build is held to round-off because the compiler may contract multiply-adds differently per instantiation)."""
+    import dedalus._lib as L
+    import dedalus_oracle as orc
+    params = dict(nu=1e-3, eta=1e-3) if physics == "IncompressibleMHD" else dict(nu=1e-3)
+    Po = oracle_physics(physics, shape, None, params)
+    y0 = orc.synthetic_ic(Po, 5).kvector()
+    out = []
+    try:
+        for v in (0, 1, 2, 3):
+            L.set_option("xfused_variant", v)
+            P = dev_physics(physics, shape, None, params)
+            data, deriv = P.create_fields(0.), P.create_fields(0.)
+            set_state(data, y0)
+            P.RHS(data, deriv)
+            out.append(get_state(deriv))
+    finally:
+        L.set_option("xfused_variant", 0)
+    for o in out[1:]:
+        assert rel(o, out[0]) < 1e-14
