@@ -1,0 +1,327 @@
+// devcheck -- a torch-free, Python-free device check of libddl_b200.so through its C ABI (include/ddl.h).
+//
+// Test infrastructure.  Purpose: (1) prove the C ABI is usable from plain C/C++ (what a cgo / ctypes /
+// Cython binding of the reference would call), (2) check the device-only parts of the reductions and
+// of the CFL capture against straightforward evaluations, in a few seconds of GPU time:
+//   A  ddl_reduce_invariants (retained-only and full sweeps) vs a host loop over the downloaded state
+//   B  ddl_reduce_max_square / ddl_rhs_capture_max vs ddl_backward of every component + host max
+//   C  ddl_rhs: every x-pass variant and the generic tile kernels against each other
+//   T  (size argument >= 256) CUDA-event timings of the RHS per x-pass variant and of the reductions
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I include tests/native/devcheck.cu \
+//        -L dedalus-1.0_b200/dedalus/_lib -lddl_b200 -o tests/native/_build/devcheck
+//   g++ -x c++ -DDEVCHECK_EMUL ... -lddl_emul      (same checks against the host-emulation build)
+//
+//   devcheck [n_check=64] [n_time=0] [outfile]
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ddl.h"
+
+#ifndef DEVCHECK_EMUL
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { say("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(3); } } while (0)
+#endif
+
+static FILE* g_out = nullptr;
+static int g_fail = 0;
+template <class... A> static void say(const char* fmt, A... a) {
+    printf(fmt, a...); fflush(stdout);
+    if (g_out) { fprintf(g_out, fmt, a...); fflush(g_out); }
+}
+static void say(const char* s) { say("%s", s); }
+#define DDL(x) do { int rc_ = (x); if (rc_ != 0) { say("ddl error %d: %s  [%s]\n", rc_, ddl_last_error(), #x); exit(2); } } while (0)
+
+// ---------------------------------------------------------------- memory + timing shims
+static void* dmalloc(size_t bytes) {
+#ifndef DEVCHECK_EMUL
+    void* p; CK(cudaMalloc(&p, bytes)); return p;
+#else
+    return malloc(bytes);
+#endif
+}
+static void dfree(void* p) {
+#ifndef DEVCHECK_EMUL
+    cudaFree(p);
+#else
+    free(p);
+#endif
+}
+static void d2h(void* h, const void* d, size_t bytes) {
+#ifndef DEVCHECK_EMUL
+    CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+#else
+    memcpy(h, d, bytes);
+#endif
+}
+static void dzero(void* d, size_t bytes) {
+#ifndef DEVCHECK_EMUL
+    CK(cudaMemset(d, 0, bytes));
+#else
+    memset(d, 0, bytes);
+#endif
+}
+static void dsync() {
+#ifndef DEVCHECK_EMUL
+    CK(cudaDeviceSynchronize());
+#endif
+}
+
+// x-space noise: a hash of the index, in [-1, 1)
+#ifndef DEVCHECK_EMUL
+__host__ __device__
+#endif
+static inline double hash01(unsigned long long i, unsigned long long seed) {
+    unsigned long long z = i * 0x9E3779B97F4A7C15ull + seed * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+#ifndef DEVCHECK_EMUL
+__global__ void fill_kernel(double* x, long long n, unsigned long long seed) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = hash01(i, seed);
+}
+#endif
+static void fill(double* x, long long n, unsigned long long seed) {
+#ifndef DEVCHECK_EMUL
+    fill_kernel<<<148 * 8, 256>>>(x, n, seed);
+    CK(cudaGetLastError());
+#else
+    for (long long i = 0; i < n; ++i) x[i] = hash01(i, seed);
+#endif
+}
+
+struct Timer {
+#ifndef DEVCHECK_EMUL
+    cudaEvent_t a, b;
+    Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    void start() { cudaEventRecord(a, 0); }
+    double stop_ms() { cudaEventRecord(b, 0); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
+#else
+    void start() {}
+    double stop_ms() { return 0.0; }
+#endif
+};
+
+// ---------------------------------------------------------------- a cubic MHD problem
+struct Problem {
+    int n; long long nk, nx3;
+    std::vector<double> k;          // wavenumbers, fftfreq order with the Nyquist positive (representations.py:204-233)
+    std::vector<uint8_t> keep;      // 2/3 rule: |k| < 2/3 kny survives (dealias_cy_3d.pyx:34-36)
+    std::vector<double> kx; std::vector<uint8_t> keepx;
+    ddl_plan* plan = nullptr;
+    void* state[8]; void* deriv[6]; void* deriv2[6];
+    void* work = nullptr; size_t work_bytes = 0;
+    double* xbuf = nullptr;         // one x-space array
+    double* dout = nullptr;         // device scratch for reduction outputs
+    ddl_phys_params prm;
+
+    explicit Problem(int n_, bool second_deriv) : n(n_) {
+        nk = (long long)n * n * (n / 2 + 1); nx3 = (long long)n * n * n;
+        k.resize(n); keep.resize(n); kx.resize(n / 2 + 1); keepx.resize(n / 2 + 1);
+        const double kny = n / 2.0;
+        for (int i = 0; i < n; ++i) { k[i] = (i <= n / 2) ? i : i - n; keep[i] = std::fabs(k[i]) < 2.0 / 3.0 * kny; }
+        for (int i = 0; i <= n / 2; ++i) { kx[i] = i; keepx[i] = std::fabs(kx[i]) < 2.0 / 3.0 * kny; }
+        int64_t shape[3] = {n, n, n};
+        DDL(ddl_plan_create(&plan, 3, shape, kx.data(), k.data(), k.data(), keepx.data(), keep.data(), keep.data()));
+        work_bytes = ddl_rhs_workspace_bytes(plan, DDL_MHD);
+        size_t wb = ddl_workspace_bytes(plan, 1, 1);
+        if (wb > work_bytes) work_bytes = wb;
+        work = dmalloc(work_bytes);
+        for (int c = 0; c < 6; ++c) { state[c] = dmalloc(nk * 16); deriv[c] = dmalloc(nk * 16); deriv2[c] = second_deriv ? dmalloc(nk * 16) : nullptr; }
+        state[6] = state[7] = nullptr;
+        xbuf = (double*)dmalloc(nx3 * 8);
+        dout = (double*)dmalloc(64 * 8);
+        prm.rho0 = 1.0; prm.g = 1.0; prm.alpha_t = 1.0; prm.beta = 1.0; prm.boussinesq_dir = 2; prm.reserved = 0;
+        // state: noise -> forward (normalised, dealiased, Hermitian-consistent)
+        for (int c = 0; c < 6; ++c) {
+            fill(xbuf, nx3, 17 + c);
+            DDL(ddl_forward(plan, xbuf, state[c], work, work_bytes, nullptr));
+        }
+        dsync();
+    }
+    ~Problem() {
+        for (int c = 0; c < 6; ++c) { dfree(state[c]); dfree(deriv[c]); if (deriv2[c]) dfree(deriv2[c]); }
+        dfree(work); dfree(xbuf); dfree(dout);
+        ddl_plan_destroy(plan);
+    }
+};
+
+static void verdict(const char* what, double err, double tol) {
+    const bool ok = err <= tol;      // NaN fails
+    if (!ok) g_fail++;
+    say("  %-58s err %.3e  tol %.1e  %s\n", what, err, tol, ok ? "ok" : "FAIL");
+}
+static double rel(double a, double b) { return std::fabs(a - b) / (std::fabs(b) > 1e-300 ? std::fabs(b) : 1.0); }
+
+static double max_rel_diff(Problem& P, void* const* a, void* const* b) {
+    std::vector<double> ha(P.nk * 2), hb(P.nk * 2);
+    double num = 0, den = 0;
+    for (int c = 0; c < 6; ++c) {
+        d2h(ha.data(), a[c], P.nk * 16); d2h(hb.data(), b[c], P.nk * 16);
+        for (long long i = 0; i < P.nk * 2; ++i) { const double d = ha[i] - hb[i]; num += d * d; den += hb[i] * hb[i]; }
+    }
+    return (num == num && den > 0) ? std::sqrt(num / den) : NAN;
+}
+
+static void check(int n) {
+    say("== devcheck: MHD %d^3, %s\n", n, ddl_version());
+    Problem P(n, true);
+    const long long nk = P.nk;
+    const int nh = n / 2 + 1;
+    // ---------------- A: invariants
+    double inv_c[DDL_NINV], inv_f[DDL_NINV];
+    DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, DDL_STAGE_RETAINED_ONLY, P.dout, nullptr));
+    dsync(); d2h(inv_c, P.dout, sizeof inv_c);
+    DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, 0, P.dout, nullptr));
+    dsync(); d2h(inv_f, P.dout, sizeof inv_f);
+    std::vector<std::vector<double>> h(6, std::vector<double>(nk * 2));
+    for (int c = 0; c < 6; ++c) d2h(h[c].data(), P.state[c], nk * 16);
+    double ref[DDL_NINV] = {0};
+    for (int iy = 0; iy < n; ++iy) for (int iz = 0; iz < n; ++iz) for (int ix = 0; ix < nh; ++ix) {
+        const long long i = ((long long)iy * n + iz) * nh + ix;
+        const double kk[3] = {P.kx[ix], P.k[iy], P.k[iz]};
+        const double w = ix == 0 ? 1.0 : 2.0;
+        double re[6], im[6];
+        for (int c = 0; c < 6; ++c) { re[c] = h[c][2 * i]; im[c] = h[c][2 * i + 1]; }
+        double eu = 0, eb = 0, dur = 0, dui = 0, dbr = 0, dbi = 0, ub = 0;
+        for (int c = 0; c < 3; ++c) {
+            eu += re[c] * re[c] + im[c] * im[c]; eb += re[3 + c] * re[3 + c] + im[3 + c] * im[3 + c];
+            dur += kk[c] * re[c]; dui += kk[c] * im[c]; dbr += kk[c] * re[3 + c]; dbi += kk[c] * im[3 + c];
+            ub += re[c] * re[3 + c] + im[c] * im[3 + c];
+            ref[DDL_INV_MSQ + c] += w * (re[c] * re[c] + im[c] * im[c]);
+            ref[DDL_INV_MSQ + 3 + c] += w * (re[3 + c] * re[3 + c] + im[3 + c] * im[3 + c]);
+        }
+        ref[DDL_INV_EKIN] += w * 0.5 * eu; ref[DDL_INV_E2] += w * 0.5 * eb;
+        ref[DDL_INV_DIV2] += w * (dur * dur + dui * dui); ref[DDL_INV_MAG_DIV2] += w * (dbr * dbr + dbi * dbi);
+        ref[DDL_INV_DIV_SUM] += std::sqrt(dur * dur + dui * dui); ref[DDL_INV_MAG_DIV_SUM] += std::sqrt(dbr * dbr + dbi * dbi);
+        ref[DDL_INV_HEL_CROSS] += w * ub;
+        auto cross2 = [&](const double* r, const double* m) {      // |k x v|^2
+            const double wxr = kk[1] * r[2] - kk[2] * r[1], wxi = kk[1] * m[2] - kk[2] * m[1];
+            const double wyr = kk[2] * r[0] - kk[0] * r[2], wyi = kk[2] * m[0] - kk[0] * m[2];
+            const double wzr = kk[0] * r[1] - kk[1] * r[0], wzi = kk[0] * m[1] - kk[1] * m[0];
+            return wxr * wxr + wxi * wxi + wyr * wyr + wyi * wyi + wzr * wzr + wzi * wzi;
+        };
+        ref[DDL_INV_ENSTROPHY] += w * 0.5 * cross2(re, im);
+        ref[DDL_INV_CURRENT2] += w * 0.5 * cross2(re + 3, im + 3);
+    }
+    say("A  ddl_reduce_invariants\n");
+    const int idx[] = {DDL_INV_EKIN, DDL_INV_E2, DDL_INV_DIV_SUM, DDL_INV_MAG_DIV_SUM, DDL_INV_ENSTROPHY, DDL_INV_CURRENT2,
+                       DDL_INV_HEL_CROSS, DDL_INV_MSQ, DDL_INV_MSQ + 1, DDL_INV_MSQ + 2, DDL_INV_MSQ + 3, DDL_INV_MSQ + 4, DDL_INV_MSQ + 5,
+                       DDL_INV_DIV2, DDL_INV_MAG_DIV2};
+    double e_c = 0, e_f = 0;
+    for (int j : idx) { e_c = std::fmax(e_c, rel(inv_c[j], ref[j])); e_f = std::fmax(e_f, rel(inv_f[j], ref[j])); }
+    if (inv_c[0] != inv_c[0]) e_c = NAN;
+    if (inv_f[0] != inv_f[0]) e_f = NAN;
+    say("  ekin %.15e (host %.15e)  emag %.15e  enstrophy %.15e\n", inv_c[0], ref[0], inv_c[1], inv_c[4]);
+    verdict("retained-only sweep vs host loop (15 entries)", e_c, 1e-11);
+    verdict("full sweep vs host loop", e_f, 1e-11);
+    double e_cf = 0;
+    for (int j = 0; j < DDL_NINV; ++j) e_cf = std::fmax(e_cf, std::fabs(inv_c[j] - inv_f[j]) / (std::fabs(inv_f[j]) + std::fabs(ref[0])));
+    verdict("retained-only vs full sweep (all 24 entries)", e_cf, 1e-11);
+    // bit reproducibility
+    double again[DDL_NINV];
+    DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, 0, P.dout, nullptr));
+    dsync(); d2h(again, P.dout, sizeof again);
+    verdict("full sweep twice: identical bits", memcmp(again, inv_f, sizeof again) ? 1.0 : 0.0, 0.0);
+
+    // ---------------- B: max_square
+    say("B  CFL maxima\n");
+    double brute[2] = {0, 0};
+    {
+        std::vector<double> hx(P.nx3);
+        void* tmp = dmalloc(nk * 16);
+        for (int c = 0; c < 6; ++c) {
+#ifndef DEVCHECK_EMUL
+            CK(cudaMemcpy(tmp, P.state[c], nk * 16, cudaMemcpyDeviceToDevice));
+#else
+            memcpy(tmp, P.state[c], nk * 16);
+#endif
+            DDL(ddl_backward(P.plan, tmp, P.xbuf, P.work, P.work_bytes, nullptr));
+            dsync(); d2h(hx.data(), P.xbuf, P.nx3 * 8);
+            double m = 0; for (double v : hx) m = std::fmax(m, v * v);
+            brute[c / 3] = std::fmax(brute[c / 3], m);
+        }
+        dfree(tmp);
+    }
+    double got[2];
+    for (int fast = 1; fast >= 0; --fast) {
+        ddl_set_option("fast_kernels", fast);
+        DDL(ddl_reduce_max_square(P.plan, DDL_MHD, &P.prm, P.state, P.work, P.work_bytes, 0, P.dout, nullptr));
+        dsync(); d2h(got, P.dout, sizeof got);
+        say("  max u^2 %.15e (brute %.15e)  max B^2 %.15e (brute %.15e)\n", got[0], brute[0], got[1], brute[1]);
+        verdict(fast ? "ddl_reduce_max_square, specialised kernels" : "ddl_reduce_max_square, generic tile kernels",
+                std::fmax(rel(got[0], brute[0]), rel(got[1], brute[1])), 1e-12);
+    }
+    ddl_set_option("fast_kernels", 1);
+
+    // ---------------- C: RHS variants
+    say("C  ddl_rhs variants\n");
+    ddl_set_option("fast_kernels", 0);
+    DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv2, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
+    dsync();
+    ddl_set_option("fast_kernels", 1);
+    for (int v = 0; v <= 3; ++v) {
+        ddl_set_option("xfused_variant", v);
+        for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
+        dzero(P.dout, 16);
+        DDL(ddl_rhs_capture_max(P.plan, v == 0 ? P.dout : nullptr));     // variant 0 also with the capture on
+        DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
+        DDL(ddl_rhs_capture_max(P.plan, nullptr));
+        dsync();
+        char label[96]; snprintf(label, sizeof label, "x-pass variant %d vs generic tile kernels (rel L2)", v);
+        verdict(label, max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
+        if (v == 0) {
+            d2h(got, P.dout, sizeof got);
+            verdict("maxima captured inside that RHS", std::fmax(rel(got[0], brute[0]), rel(got[1], brute[1])), 1e-12);
+        }
+    }
+    ddl_set_option("xfused_variant", 0);
+}
+
+static void timing(int n) {
+    say("== timing: MHD %d^3 (CUDA events, ms per call, best of 3 after 1 warm-up)\n", n);
+    Problem P(n, false);
+    Timer t;
+    for (int v = 0; v <= 3; ++v) {
+        ddl_set_option("xfused_variant", v);
+        double best = 1e30;
+        for (int r = 0; r < 4; ++r) {
+            t.start();
+            DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
+            const double ms = t.stop_ms();
+            if (r > 0 && ms < best) best = ms;
+        }
+        say("  ddl_rhs, x-pass variant %d: %.3f ms\n", v, best);
+    }
+    ddl_set_option("xfused_variant", 0);
+    for (int mode = 0; mode < 3; ++mode) {
+        double best = 1e30;
+        for (int r = 0; r < 4; ++r) {
+            t.start();
+            if (mode == 0) DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, DDL_STAGE_RETAINED_ONLY, P.dout, nullptr));
+            if (mode == 1) DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, 0, P.dout, nullptr));
+            if (mode == 2) DDL(ddl_reduce_max_square(P.plan, DDL_MHD, &P.prm, P.state, P.work, P.work_bytes, 0, P.dout, nullptr));
+            const double ms = t.stop_ms();
+            if (r > 0 && ms < best) best = ms;
+        }
+        say("  %s: %.3f ms\n", mode == 0 ? "invariants, retained-only sweep" : mode == 1 ? "invariants, full sweep" : "max_square (inverse half + capture)", best);
+    }
+    dsync();
+}
+
+int main(int argc, char** argv) {
+    const int n_check = argc > 1 ? atoi(argv[1]) : 64;
+    const int n_time = argc > 2 ? atoi(argv[2]) : 0;
+    if (argc > 3) g_out = fopen(argv[3], "w");
+    if (n_check > 0) check(n_check);
+    if (n_time > 0) timing(n_time);
+    say("devcheck: %s (%d failure%s)\n", g_fail ? "FAILED" : "all ok", g_fail, g_fail == 1 ? "" : "s");
+    if (g_out) fclose(g_out);
+    return g_fail ? 1 : 0;
+}
