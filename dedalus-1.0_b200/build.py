@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "dedalus", "_lib")
 LIB = os.path.join(LIBDIR, "libddl_b200.so")
-SIZES = [8, 16, 32, 64, 128, 256, 512, 1024, 2048]
+SIZES = [0, 8, 16, 32, 64, 128, 256, 512, 1024, 2048]      # 0: the runtime-length (mixed radix) instantiation
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

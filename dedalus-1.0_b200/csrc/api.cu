@@ -85,16 +85,40 @@ int dev_upload(void* dst, const void* src, size_t bytes) {
 // ---------------------------------------------------------------- per-length kernels
 #define DDL_DECL(N) int run_tile_##N(int, int, int, const TileParams&, int, ddl_stream_t);
 DDL_DECL(8) DDL_DECL(16) DDL_DECL(32) DDL_DECL(64) DDL_DECL(128) DDL_DECL(256) DDL_DECL(512) DDL_DECL(1024)
-DDL_DECL(2048)
+DDL_DECL(2048) DDL_DECL(0)
 
-static int run_tile(int N, int mode, int dir, int phys, const TileParams& p, int nthreads, ddl_stream_t s) {
+// largest tile the generic kernel may ask for (227 KB of shared memory per CTA on sm_100)
+static const size_t TILE_SMEM_MAX = 227 * 1024;
+
+// Lengths with a translation unit of their own run the compile-time kernels; every other length
+// (the reference transforms any N through FFTW) runs the runtime-length instantiation.
+static int run_tile(int N, int mode, int dir, int phys, TileParams& p, int nthreads, ddl_stream_t s) {
+    if ((size_t)N * p.ld * sizeof(cplx) > TILE_SMEM_MAX) {
+        set_error("transform length %d with %d pencils per tile needs %zu bytes of shared memory (limit %zu)", N, p.ld,
+                  (size_t)N * p.ld * sizeof(cplx), TILE_SMEM_MAX);
+        return -1;
+    }
     switch (N) {
 #define DDL_CASE(N) case N: return run_tile_##N(mode, dir, phys, p, nthreads, s);
         DDL_CASE(8) DDL_CASE(16) DDL_CASE(32) DDL_CASE(64) DDL_CASE(128) DDL_CASE(256) DDL_CASE(512)
         DDL_CASE(1024) DDL_CASE(2048)
     }
-    set_error("unsupported transform length %d (powers of two 8..2048)", N);
-    return -1;
+    if (!rt_factor(N, p.rt)) {
+        set_error("unsupported transform length %d (prime factors up to %d)", N, DDL_RT_MAXR);
+        return -1;
+    }
+    return run_tile_0(mode, dir, phys, p, nthreads, s);
+}
+
+// threads one pencil keeps busy: butterflies of the widest stage
+static int pencil_threads(int N) {
+    if (N >= 8 && !(N & (N - 1))) return N / 8;
+    RtFac f;
+    if (!rt_factor(N, f)) return 1;
+    int rmin = f.radix[0];
+    for (int i = 1; i < f.S; ++i) if (f.radix[i] < rmin) rmin = f.radix[i];
+    const int t = N / (rmin > 0 ? rmin : 1);
+    return t < 1 ? 1 : t;
 }
 
 #define DDL_DECLX(N) int run_xfused_##N(int, const XFusedParams&, int, int, ddl_stream_t);
@@ -188,7 +212,13 @@ struct ddl_plan {
 
 static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv, const uint8_t* keep) {
     a.n = n; a.half = half; a.nk = half ? n / 2 + 1 : n;
-    if (n < 8 || n > 2048 || (n & (n - 1))) { set_error("axis length %d unsupported (power of two in 8..2048)", n); return -1; }
+    {
+        RtFac f;
+        if (n < 2 || n > 2048 || !rt_factor(n, f)) {
+            set_error("axis length %d unsupported (2..2048 with prime factors up to %d)", n, DDL_RT_MAXR);
+            return -1;
+        }
+    }
     int m = -1;
     for (int j = 0; j < a.nk; ++j) {
         int mi = (j <= n / 2) ? j : n - j;
@@ -431,7 +461,7 @@ static int pick_c2c_group(int N, long long inner_len) {
     return g;
 }
 // CTA size of the generic tile kernel (72 registers per thread: at most 896 threads fit an SM)
-static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > 768 ? 768 : t); }
+static int round32(int t) { t = (t + 31) / 32 * 32; return t < 64 ? 64 : (t > DDL_TILE_MAX_THREADS ? DDL_TILE_MAX_THREADS : t); }
 
 // complex pass of nf fields along an axis of length N
 // retained rows of a pruned axis (m < 0: all rows present); compact: 0 stored in place, 1 stored
@@ -481,8 +511,7 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
     p.inner_len = inner_len; p.n_outer = n_outer; p.kn = 0;
     p.ld = (si.s_n == 1 || so.s_n == 1) ? (p.G | 1) : p.G;
     p.scale = scale; p.tw = tw; p.name = name;
-    const int rmax = N >= 8 ? 8 : 4;
-    return run_tile(N, TM_C2C, dir, 0, p, round32(p.G * (N / rmax)), st);
+    return run_tile(N, TM_C2C, dir, 0, p, round32(p.G * pencil_threads(N)), st);
 }
 
 // pair-mode pass (C2R / R2C / FUSED) over real lines
@@ -505,8 +534,7 @@ static int pass_pair(const char* name, int N, int mode, int phys, int ni, int no
     p.inner_len = n_lines; p.n_outer = n_outer; p.kn = kn;
     p.ld = (g * p.nft) | 1;
     p.scale = scale; p.tw = tw; p.pc = pc; p.name = name; p.cfl = cfl;
-    const int rmax = N >= 8 ? 8 : 4;
-    return run_tile(N, mode, 0, phys, p, round32(g * p.nft * (N / rmax)), st);
+    return run_tile(N, mode, 0, phys, p, round32(g * p.nft * pencil_threads(N)), st);
 }
 
 static TileSide side(long long s_n, long long s_inner, long long s_outer, const int* n_tab, const int* outer_tab,

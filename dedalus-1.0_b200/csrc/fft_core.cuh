@@ -164,4 +164,147 @@ DDL_HD void stage_item(cplx* tile, int ld, int c, int w, const cplx* __restrict_
     for (int j = 0; j < R; ++j) base[(size_t)j * Q * ld] = v[j];
 }
 
+// ---------------------------------------------------------------------------------------
+// Runtime factorisation: any length whose prime factors are <= DDL_RT_MAXR.  The reference
+// transforms through FFTW, which takes any N (its own samples run 450 x 450, 48 x 2 x 48,
+// 100 x 100, 30 x 10 grids); the compile-time kernels above cover the powers of two, every
+// other length goes through the same stage structure with the radices in a table:
+// 8 / 4 / 2 for the power-of-two part, hand-written 3- and 5-point butterflies, and a direct
+// O(R^2) DFT for any other prime factor (compatibility path: correctness over speed).
+// ---------------------------------------------------------------------------------------
+#define DDL_RT_MAXS 16
+#define DDL_RT_MAXR 64
+
+struct RtFac {
+    int n;                      // transform length
+    int S;                      // number of stages
+    int rmax;                   // largest radix (sizes the CTA)
+    int radix[DDL_RT_MAXS];
+};
+
+// host side: fills f, returns false when n has a prime factor > DDL_RT_MAXR
+inline bool rt_factor(int n, RtFac& f) {
+    f.n = n; f.S = 0; f.rmax = 1;
+    if (n < 1) return false;
+    int rem = n;
+    auto push = [&](int r) { f.radix[f.S++] = r; if (r > f.rmax) f.rmax = r; rem /= r; };
+    while (rem % 8 == 0) push(8);
+    while (rem % 4 == 0) push(4);
+    while (rem % 2 == 0) push(2);
+    for (int p = 3; p <= DDL_RT_MAXR && rem > 1; p += 2)
+        while (rem % p == 0) { if (f.S >= DDL_RT_MAXS) return false; push(p); }
+    if (rem != 1) return false;
+    if (f.S == 0) push(1);      // n == 1: one trivial stage
+    return f.S <= DDL_RT_MAXS;
+}
+
+DDL_HD int pos_of_index_rt(const RtFac& f, int k) {
+    int p = 0, rem = f.n;
+    for (int s = 0; s < f.S; ++s) {
+        const int R = f.radix[s];
+        rem /= R;
+        p += (k % R) * rem;
+        k /= R;
+    }
+    return p;
+}
+DDL_HD int index_of_pos_rt(const RtFac& f, int p) {
+    int k = 0, rem = f.n, w = 1;
+    for (int s = 0; s < f.S; ++s) {
+        const int R = f.radix[s];
+        rem /= R;
+        k += (p / rem) * w;
+        p %= rem;
+        w *= R;
+    }
+    return k;
+}
+
+template <int DIR> DDL_HD void dft3(cplx& a, cplx& b, cplx& c) {
+    const double s = 0.86602540378443864676;            // sin(2 pi / 3)
+    const cplx t = b + c, d = scal(mul_i<DIR>(b - c), s);
+    const cplx m = mk(a.x - 0.5 * t.x, a.y - 0.5 * t.y);
+    a = a + t; b = m + d; c = m - d;
+}
+
+template <int DIR> DDL_HD void dft5(cplx (&v)[5]) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;    // cos(2 pi/5), cos(4 pi/5)
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;     // sin(2 pi/5), sin(4 pi/5)
+    const cplx a1 = v[1] + v[4], a2 = v[2] + v[3], b1 = v[1] - v[4], b2 = v[2] - v[3];
+    const cplx m1 = mk(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+    const cplx m2 = mk(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    const cplx d1 = mul_i<DIR>(mk(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y));
+    const cplx d2 = mul_i<DIR>(mk(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y));
+    v[0] = v[0] + a1 + a2;
+    v[1] = m1 + d1; v[4] = m1 - d1;
+    v[2] = m2 + d2; v[3] = m2 - d2;
+}
+
+template <int DIR> DDL_HD cplx tw_at(const cplx* __restrict__ tw, int m) { return DIR > 0 ? conj(tw[m]) : tw[m]; }
+
+// stage item with a compile-time radix and runtime geometry (M = n / P, Q = M / R)
+template <int R, int DIR, bool DIT>
+DDL_HD void stage_item_g(cplx* tile, int ld, int c, int w, int M, int Q, int P, const cplx* __restrict__ tw) {
+    const int q = w / Q, b = w % Q;
+    cplx* base = tile + (size_t)(q * M + b) * ld + c;
+    cplx v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = base[(size_t)j * Q * ld];
+    const int step = b * P;
+    if (DIT && step) {
+#pragma unroll
+        for (int j = 1; j < R; ++j) v[j] = cmul(v[j], tw_at<DIR>(tw, j * step));
+    }
+    if constexpr (R == 2) dft2<DIR>(v[0], v[1]);
+    else if constexpr (R == 3) dft3<DIR>(v[0], v[1], v[2]);
+    else if constexpr (R == 4) dft4<DIR>(v[0], v[1], v[2], v[3]);
+    else if constexpr (R == 5) dft5<DIR>(v);
+    else dft8<DIR>(v);
+    if (!DIT && step) {
+#pragma unroll
+        for (int j = 1; j < R; ++j) v[j] = cmul(v[j], tw_at<DIR>(tw, j * step));
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) base[(size_t)j * Q * ld] = v[j];
+}
+
+// any other prime radix: direct DFT, X[r] = sum_j v[j] W^(j r), W = exp(DIR 2 pi i / R) = tw[n / R]
+template <int DIR, bool DIT>
+DDL_HD void stage_item_prime(cplx* tile, int ld, int c, int w, int n, int R, int M, int Q, int P, const cplx* __restrict__ tw) {
+    const int q = w / Q, b = w % Q;
+    cplx* base = tile + (size_t)(q * M + b) * ld + c;
+    cplx v[DDL_RT_MAXR], o[DDL_RT_MAXR];
+    const int step = b * P, unit = n / R;
+    for (int j = 0; j < R; ++j) {
+        v[j] = base[(size_t)j * Q * ld];
+        if (DIT && step && j) v[j] = cmul(v[j], tw_at<DIR>(tw, j * step));
+    }
+    for (int r = 0; r < R; ++r) {
+        cplx acc = v[0];
+        int e = 0;
+        for (int j = 1; j < R; ++j) {
+            e += r; if (e >= R) e -= R;                  // (j r) mod R
+            acc = acc + cmul(v[j], tw_at<DIR>(tw, e * unit));
+        }
+        o[r] = acc;
+    }
+    for (int r = 0; r < R; ++r) {
+        if (!DIT && step && r) o[r] = cmul(o[r], tw_at<DIR>(tw, r * step));
+        base[(size_t)r * Q * ld] = o[r];
+    }
+}
+
+template <int DIR, bool DIT>
+DDL_HD void stage_item_rt(cplx* tile, int ld, int c, int w, int n, int R, int M, int Q, int P, const cplx* __restrict__ tw) {
+    switch (R) {
+        case 1: break;
+        case 2: stage_item_g<2, DIR, DIT>(tile, ld, c, w, M, Q, P, tw); break;
+        case 3: stage_item_g<3, DIR, DIT>(tile, ld, c, w, M, Q, P, tw); break;
+        case 4: stage_item_g<4, DIR, DIT>(tile, ld, c, w, M, Q, P, tw); break;
+        case 5: stage_item_g<5, DIR, DIT>(tile, ld, c, w, M, Q, P, tw); break;
+        case 8: stage_item_g<8, DIR, DIT>(tile, ld, c, w, M, Q, P, tw); break;
+        default: stage_item_prime<DIR, DIT>(tile, ld, c, w, n, R, M, Q, P, tw); break;
+    }
+}
+
 }  // namespace ddl

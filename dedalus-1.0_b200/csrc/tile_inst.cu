@@ -1,5 +1,6 @@
 // Instantiates the generic tile kernel for ONE transform length (compile with -DDDL_N=<N>);
-// one translation unit per length so the build parallelises.
+// one translation unit per length so the build parallelises.  -DDDL_N=0 is the runtime-length
+// instantiation (mixed radix, fft_core.cuh RtFac) that serves every length without a unit of its own.
 #include "tile_kernel.cuh"
 #include "fast_kernels.cuh"
 #include "xfused_kernel.cuh"
@@ -56,13 +57,20 @@ int DDL_CAT(run_xfused_, DDL_N)(int phys, const XFusedParams& p, int n_outer, in
 
 #if DDL_DEVICE_BUILD
 // specialised strided pass; returns 1 if this length has no fast kernel (caller falls back)
-int DDL_CAT(run_fast_strided_, DDL_N)(int dir, const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
-    constexpr int N = DDL_N;
-    if constexpr (Fac<N>::S >= 2) {
-        return dir < 0 ? launch_strided_fast<N, -1>(p, nf, n_outer, name, s) : launch_strided_fast<N, +1>(p, nf, n_outer, name, s);
-    } else {
-        return 1;
+template <int N> struct FastStrided {      // a template, so that the discarded branch is never instantiated (Fac<0>)
+    static int run(int dir, const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
+        if constexpr (Fac<N>::S >= 2) {
+            return dir < 0 ? launch_strided_fast<N, -1>(p, nf, n_outer, name, s) : launch_strided_fast<N, +1>(p, nf, n_outer, name, s);
+        } else {
+            return 1;
+        }
     }
+};
+template <> struct FastStrided<0> {
+    static int run(int, const FastParams&, int, int, const char*, ddl_stream_t) { return 1; }
+};
+int DDL_CAT(run_fast_strided_, DDL_N)(int dir, const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
+    return FastStrided<DDL_N>::run(dir, p, nf, n_outer, name, s);
 }
 #endif
 

@@ -48,6 +48,7 @@ struct TileParams {
     const cplx* tw;
     PhysConst pc;
     const char* name;     // label for launch accounting / profiling (host side only)
+    RtFac rt;             // N == 0 instantiation (runtime length): the factorisation of the transform length
     double* cfl;          // TM_FUSED: optional CFL capture, cfl[0] = max(cfl[0], max_{x,i} u_i(x)^2), cfl[1]: second group
                           // (B or T) -- fields.py:153-157 max_square without a transform of its own; NULL = off
 };
@@ -79,6 +80,43 @@ DDL_BODY void tile_fft_dit(cplx* tile, int ld, int nfa, int nft, int G, const cp
     if constexpr (S_IDX > 0) tile_fft_dit<N, DIR, S_IDX - 1>(tile, ld, nfa, nft, G, tw);
 }
 
+// ---- runtime-length variants (template length 0): same stage structure, radices from p.rt (fft_core.cuh)
+template <int DIR, bool DIT>
+DDL_BODY void stage_all_rt(cplx* tile, int ld, int nfa, int nft, int G, const cplx* __restrict__ tw, const RtFac& rt, int s) {
+    int P = 1;
+    for (int t = 0; t < s; ++t) P *= rt.radix[t];
+    const int R = rt.radix[s], M = rt.n / P, Q = M / R;
+    const int items = nfa * G * (rt.n / R);
+    DDL_FOR_ITEMS(i, items) {
+        const int f = i % nfa, t = i / nfa;
+        const int g = t % G, w = t / G;
+        stage_item_rt<DIR, DIT>(tile, ld, g * nft + f, w, rt.n, R, M, Q, P, tw);
+    }
+}
+
+template <int N, int DIR>
+DDL_BODY void fft_dif(const RtFac& rt, cplx* tile, int ld, int nfa, int nft, int G, const cplx* __restrict__ tw) {
+    if constexpr (N > 0) {
+        tile_fft_dif<N, DIR>(tile, ld, nfa, nft, G, tw);
+    } else {
+        for (int s = 0; s < rt.S; ++s) { stage_all_rt<DIR, false>(tile, ld, nfa, nft, G, tw, rt, s); DDL_SYNC(); }
+    }
+}
+template <int N, int DIR>
+DDL_BODY void fft_dit(const RtFac& rt, cplx* tile, int ld, int nfa, int nft, int G, const cplx* __restrict__ tw) {
+    if constexpr (N > 0) {
+        tile_fft_dit<N, DIR>(tile, ld, nfa, nft, G, tw);
+    } else {
+        for (int s = rt.S - 1; s >= 0; --s) { stage_all_rt<DIR, true>(tile, ld, nfa, nft, G, tw, rt, s); DDL_SYNC(); }
+    }
+}
+template <int N> DDL_HD int tpos(const RtFac& rt, int k) {
+    if constexpr (N > 0) return pos_of_index<N>(k); else return pos_of_index_rt(rt, k);
+}
+template <int N> DDL_HD int tidx(const RtFac& rt, int pos) {
+    if constexpr (N > 0) return index_of_pos<N>(pos); else return index_of_pos_rt(rt, pos);
+}
+
 // running maximum of non-negative values; NaN wins (numpy's max propagates it)
 DDL_HD double tmax_nn(double m, double a) { return (a > m || a != a) ? a : m; }
 
@@ -89,6 +127,7 @@ DDL_HD long long outer_off(const TileSide& s, int o) {
 template <int N, int MODE, int DIR, class PHYS>
 DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz) {
     const int ld = p.ld;
+    const int n_len = (N > 0) ? N : p.rt.n;      // compile-time length, or the runtime one of the N == 0 instantiation
     const cplx* __restrict__ tw = p.tw;
 
     if constexpr (MODE == TM_C2C) {
@@ -99,22 +138,22 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
         const long long ib = outer_off(p.si, by) + (long long)i0 * p.si.s_inner;
         const long long ob = outer_off(p.so, by) + (long long)i0 * p.so.s_inner;
         const bool in_nfast = (p.si.s_n == 1);
-        DDL_FOR_ITEMS(i, N * npc) {
+        DDL_FOR_ITEMS(i, n_len * npc) {
             int n, c;
-            if (in_nfast) { n = i % N; c = i / N; } else { c = i % npc; n = i / npc; }
+            if (in_nfast) { n = i % n_len; c = i / n_len; } else { c = i % npc; n = i / npc; }
             const int pn = p.si.n_tab ? p.si.n_tab[n] : n;
             cplx v = mk(0.0, 0.0);
             if (pn >= 0) v = in[ib + row_off(p.si, pn) + (long long)c * p.si.s_inner];
             tile[n * ld + c] = v;
         }
         DDL_SYNC();
-        tile_fft_dif<N, DIR>(tile, ld, 1, 1, npc, tw);
+        fft_dif<N, DIR>(p.rt, tile, ld, 1, 1, npc, tw);
         const bool out_nfast = (p.so.s_n == 1);
         const double sc = p.scale;
-        DDL_FOR_ITEMS(i, N * npc) {
+        DDL_FOR_ITEMS(i, n_len * npc) {
             int k, c, pos;
-            if (out_nfast) { k = i % N; c = i / N; pos = pos_of_index<N>(k); }
-            else { c = i % npc; pos = i / npc; k = index_of_pos<N>(pos); }
+            if (out_nfast) { k = i % n_len; c = i / n_len; pos = tpos<N>(p.rt, k); }
+            else { c = i % npc; pos = i / npc; k = tidx<N>(p.rt, pos); }
             const int pk = p.so.n_tab ? p.so.n_tab[k] : k;
             if (pk >= 0) out[ob + row_off(p.so, pk) + (long long)c * p.so.s_inner] = scal(tile[pos * ld + c], sc);
         }
@@ -128,7 +167,7 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
 
         if constexpr (MODE == TM_C2R || MODE == TM_FUSED) {
             // Hermitian pack of line pairs: Z[k] = A[k] + i B[k], Z[N-k] = conj(A[k]) + i conj(B[k])
-            constexpr int H = N / 2 + 1;
+            const int H = n_len / 2 + 1;
             const bool nfast = (p.si.s_n == 1);
             DDL_FOR_ITEMS(i, H * ng * NI) {
                 int k, g, f;
@@ -146,29 +185,29 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
                     }
                 }
                 const int c = g * nft + f;
-                if (k == 0 || 2 * k == N) {
+                if (k == 0 || 2 * k == n_len) {
                     tile[k * ld + c] = mk(A.x, B.x);
                 } else {
                     tile[k * ld + c] = mk(A.x - B.y, A.y + B.x);
-                    tile[(N - k) * ld + c] = mk(A.x + B.y, B.x - A.y);
+                    tile[(n_len - k) * ld + c] = mk(A.x + B.y, B.x - A.y);
                 }
             }
             DDL_SYNC();
-            tile_fft_dif<N, +1>(tile, ld, NI, nft, ng, tw);
+            fft_dif<N, +1>(p.rt, tile, ld, NI, nft, ng, tw);
         }
 
         if constexpr (MODE == TM_R2C) {
             const bool nfast = (p.si.s_n == 1);
-            DDL_FOR_ITEMS(i, N * ng * NI) {
+            DDL_FOR_ITEMS(i, n_len * ng * NI) {
                 int n, g, f;
-                if (nfast) { n = i % N; int r = i / N; f = r % NI; g = r / NI; }
-                else { g = i % ng; int r = i / ng; n = r % N; f = r / N; }
+                if (nfast) { n = i % n_len; int r = i / n_len; f = r % NI; g = r / NI; }
+                else { g = i % ng; int r = i / ng; n = r % n_len; f = r / n_len; }
                 const int l0 = line0 + 2 * g, l1 = l0 + 1;
                 const double* __restrict__ src = (const double*)p.in[f];
                 const long long a = ib + (long long)n * p.si.s_n;
                 const double va = src[a + (long long)l0 * p.si.s_inner];
                 const double vb = (l1 < p.inner_len) ? src[a + (long long)l1 * p.si.s_inner] : 0.0;
-                tile[pos_of_index<N>(n) * ld + g * nft + f] = mk(va, vb);
+                tile[tpos<N>(p.rt, n) * ld + g * nft + f] = mk(va, vb);
             }
             DDL_SYNC();
         }
@@ -176,7 +215,7 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
         if constexpr (MODE == TM_FUSED) {
             // real-space products at every grid point of both lines of the pair
             double m0 = 0.0, m1 = 0.0;
-            DDL_FOR_ITEMS(i, N * ng) {
+            DDL_FOR_ITEMS(i, n_len * ng) {
                 const int g = i % ng, pos = i / ng;
                 cplx* row = tile + pos * ld + g * nft;
                 double ax[NI], ay[NI], ox[NO], oy[NO];
@@ -217,7 +256,7 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
         }
 
         if constexpr (MODE == TM_R2C || MODE == TM_FUSED) {
-            tile_fft_dit<N, -1>(tile, ld, NO, nft, ng, tw);
+            fft_dit<N, -1>(p.rt, tile, ld, NO, nft, ng, tw);
             const bool nfast = (p.so.s_n == 1);
             const double h = 0.5 * p.scale;
             const int kn = p.kn;
@@ -228,7 +267,7 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
                 const int pk = p.so.n_tab ? p.so.n_tab[k] : k;
                 if (pk < 0) continue;
                 const int c = g * nft + f;
-                const cplx Zk = tile[k * ld + c], Zm = tile[((N - k) % N) * ld + c];
+                const cplx Zk = tile[k * ld + c], Zm = tile[((n_len - k) % n_len) * ld + c];
                 const int l0 = line0 + 2 * g, l1 = l0 + 1;
                 cplx* __restrict__ dst = (cplx*)p.out[f];
                 const long long a = ob + (long long)pk * p.so.s_n;
@@ -240,12 +279,12 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
         if constexpr (MODE == TM_C2R) {
             const bool nfast = (p.so.s_n == 1);
             const double sc = p.scale;
-            DDL_FOR_ITEMS(i, N * ng * NI) {
+            DDL_FOR_ITEMS(i, n_len * ng * NI) {
                 int n, g, f;
-                if (nfast) { n = i % N; int r = i / N; f = r % NI; g = r / NI; }
-                else { g = i % ng; int r = i / ng; n = r % N; f = r / N; }
+                if (nfast) { n = i % n_len; int r = i / n_len; f = r % NI; g = r / NI; }
+                else { g = i % ng; int r = i / ng; n = r % n_len; f = r / n_len; }
                 const int l0 = line0 + 2 * g, l1 = l0 + 1;
-                const cplx z = tile[pos_of_index<N>(n) * ld + g * nft + f];
+                const cplx z = tile[tpos<N>(p.rt, n) * ld + g * nft + f];
                 double* __restrict__ dst = (double*)p.out[f];
                 const long long a = ob + (long long)n * p.so.s_n;
                 dst[a + (long long)l0 * p.so.s_inner] = z.x * sc;
@@ -255,9 +294,12 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
     }
 }
 
+#define DDL_TILE_MAX_THREADS 768
 #if DDL_DEVICE_BUILD
+// round32() in api.cu launches at most 768 threads: the bound keeps every instantiation within the 64 K registers of an SM
+// at that size (the advective-form MHD policy would otherwise take 88 registers x 768 threads and fail to launch)
 template <int N, int MODE, int DIR, class PHYS>
-__global__ void tile_kernel(const __grid_constant__ TileParams p) {
+__global__ void __launch_bounds__(DDL_TILE_MAX_THREADS) tile_kernel(const __grid_constant__ TileParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tile_block<N, MODE, DIR, PHYS>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y, blockIdx.z);
 }
@@ -271,7 +313,7 @@ int launch_tile(const TileParams& p, int nthreads, ddl_stream_t stream) {
     const int gz = (MODE == TM_C2C) ? p.nf_in : 1;
     const int np = (MODE == TM_C2C) ? p.G : p.G * p.nft;
     if (p.ld < np) { set_error("launch_tile: ld %d < pencils %d", p.ld, np); return -1; }
-    const size_t smem = (size_t)N * p.ld * sizeof(cplx);
+    const size_t smem = (size_t)(N > 0 ? N : p.rt.n) * p.ld * sizeof(cplx);
 #if DDL_DEVICE_BUILD
     auto kern = tile_kernel<N, MODE, DIR, PHYS>;
     if (smem > 48 * 1024) DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

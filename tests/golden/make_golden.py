@@ -57,6 +57,21 @@ CASES = [
          ic="synthetic", cfg=5),
     dict(name="hydro3d_16_rk2mid_nodealias", physics="IncompressibleHydro", shape=(16, 16, 16), length=None,
          params=dict(nu=0.01), integ="RK2mid", dt=5e-3, nsteps=2, ic="synthetic", cfg=3, dealiasing="None"),
+    # grids that are not powers of two (the reference transforms any N through FFTW / numpy.fft; its samples run
+    # 30 x 10, 48 x 2 x 48, 450 x 450, 100 x 100): mixed radix 2 / 3 / 5, odd lengths, a length-2 axis, a factor 7
+    dict(name="hydro2d_10x30_rk2mid", physics="IncompressibleHydro", shape=(10, 30), length=(2 * np.pi, 6 * np.pi),
+         params=dict(nu=0.02), integ="RK2mid", dt=1e-2, nsteps=3, ic="synthetic", cfg=1),
+    dict(name="hydro2d_50_rk2trap", physics="IncompressibleHydro", shape=(50, 50), length=None,
+         params=dict(nu=0.01), integ="RK2trap", dt=5e-3, nsteps=2, ic="synthetic", cfg=1),
+    dict(name="mhd2d_18x24_rk2mid", physics="IncompressibleMHD", shape=(18, 24), length=None,
+         params=dict(nu=0.02, eta=0.03), integ="RK2mid", dt=1e-2, nsteps=3, ic="synthetic", cfg=2),
+    dict(name="bouss3d_48x2x48_rk2mid", physics="BoussinesqHydro", shape=(48, 2, 48), length=None,
+         params=dict(nu=0.01, kappa=0.02, g=1.3, alpha_t=0.7, beta=1.1), integ="RK2mid", dt=1e-2, nsteps=2,
+         ic="synthetic", cfg=4),
+    dict(name="mhd3d_9x15x14_rk2trap", physics="IncompressibleMHD", shape=(9, 15, 14), length=(2.0, 3.0, 5.0),
+         params=dict(nu=0.02, eta=0.01, rho0=1.7), integ="RK2trap", dt=2e-3, nsteps=2, ic="synthetic", cfg=5),
+    dict(name="hydro3d_12x20x24_rk2mid", physics="IncompressibleHydro", shape=(12, 20, 24), length=None,
+         params=dict(nu=0.01), integ="RK2mid", dt=1e-2, nsteps=2, ic="synthetic", cfg=3),
     dict(name="hydro2d_16_rk2mid_visc2", physics="IncompressibleHydro", shape=(16, 16), length=None,
          params=dict(nu=1e-3, viscosity_order=2), integ="RK2mid", dt=1e-2, nsteps=3, ic="synthetic", cfg=1),
 ]
