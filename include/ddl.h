@@ -61,7 +61,8 @@ typedef struct ddl_phys_params {
 /* Plan = wavenumbers, dealias mask, twiddles, index tables.  Replaces
  * fftw.create_data / fftw.rPlan (dedalus/utils/fftw/_fftw.pyx:81-185,246-309),
  * FourierRepresentation._setup_k and set_dealiasing (representations.py:204-233,359-382).
- *   shape_x  : x-space shape, (nz,ny,nx) or (ny,nx); powers of two >= 8
+ *   shape_x  : x-space shape, (nz,ny,nx) or (ny,nx); every length in 2..2048 with prime factors <= 64 (FFTW, the
+ *              reference's backend, takes any length; powers of two >= 8 run the specialised kernels)
  *   kx,ky,kz : the wavenumber VALUES along each axis exactly as the host computed them
  *              (kx: nx/2+1 entries, ky: ny, kz: nz; kz NULL in 2-D)
  *   keepx..  : 1 where the mode survives the dealias mask on that axis, 0 where it is zeroed
