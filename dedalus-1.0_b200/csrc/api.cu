@@ -225,7 +225,7 @@ static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv,
         if (keep[j] && mi > m) m = mi;
     }
     if (m < 0) { set_error("dealias mask removes every mode"); return -1; }
-    if (m >= n / 2) { set_error("dealias mask keeps the Nyquist mode; unsupported"); return -1; }
+    if (2 * m >= n) { set_error("dealias mask keeps the Nyquist mode; unsupported"); return -1; }      // odd n has none
     for (int j = 0; j < a.nk; ++j) {
         int mi = (j <= n / 2) ? j : n - j;
         if ((keep[j] != 0) != (mi <= m)) { set_error("dealias mask is not of the form |k index| <= m"); return -1; }

@@ -12,7 +12,7 @@
 //        -L dedalus-1.0_b200/dedalus/_lib -lddl_b200 -o tests/native/_build/devcheck
 //   g++ -x c++ -DDEVCHECK_EMUL ... -lddl_emul      (same checks against the host-emulation build)
 //
-//   devcheck [n_check=64] [n_time=0] [outfile]
+//   devcheck [n_check=64] [n_time=0] [outfile] [option=value ...]   e.g.  devcheck 0 512 out.txt reps=5 xfused_variant=1
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -29,6 +29,7 @@
 
 static FILE* g_out = nullptr;
 static int g_fail = 0;
+static int g_variant = 0;      // x-pass variant in force outside the variant sweeps (set by an xfused_variant=V argument)
 template <class... A> static void say(const char* fmt, A... a) {
     printf(fmt, a...); fflush(stdout);
     if (g_out) { fprintf(g_out, fmt, a...); fflush(g_out); }
@@ -281,17 +282,32 @@ static void check(int n) {
             verdict("maxima captured inside that RHS", std::fmax(rel(got[0], brute[0]), rel(got[1], brute[1])), 1e-12);
         }
     }
-    ddl_set_option("xfused_variant", 0);
+    ddl_set_option("xfused_variant", g_variant);
 }
 
-static void timing(int n) {
-    say("== timing: MHD %d^3 (CUDA events, ms per call, best of 3 after 1 warm-up)\n", n);
+// one RK4 step the way the Python integrator issues it once the state is dealiased (time_step.py RK4._advance_fused):
+// four ddl_rhs_stage calls, the spectral assembly fused with the stage update, y advanced in place
+static void rk4_fused_step(Problem& P, void* const* tmp, void* const* total, const double* coeff, double dt) {
+    ddl_stage_fuse f;
+    memset(&f, 0, sizeof f);
+    f.total = total; f.coeff = coeff; f.visc_order = 1; f.kind = DDL_FUSE_RK4;
+    const int flags = DDL_STAGE_RETAINED_ONLY * 0;      // ddl_rhs flags: state already dealiased, nothing to zero-fill
+    struct { void* const* in; void* const* out; double wdiv, h; int first, last; } st[4] = {
+        {P.state, tmp, 6., dt / 2., 1, 0}, {tmp, tmp, 3., dt / 2., 0, 0}, {tmp, tmp, 3., dt, 0, 0}, {tmp, P.state, 6., dt, 0, 1}};
+    for (int i = 0; i < 4; ++i) {
+        f.y = P.state; f.out = st[i].out; f.wdiv = st[i].wdiv; f.dt_step = st[i].h; f.first = st[i].first; f.last = st[i].last;
+        DDL(ddl_rhs_stage(P.plan, DDL_MHD, &P.prm, st[i].in, P.work, P.work_bytes, flags, &f, nullptr));
+    }
+}
+
+static void timing(int n, int reps) {
+    say("== timing: MHD %d^3 (CUDA events, ms per call, best of %d after 1 warm-up)\n", n, reps);
     Problem P(n, false);
     Timer t;
     for (int v = 0; v <= 3; ++v) {
         ddl_set_option("xfused_variant", v);
         double best = 1e30;
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r <= reps; ++r) {
             t.start();
             DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
             const double ms = t.stop_ms();
@@ -299,10 +315,10 @@ static void timing(int n) {
         }
         say("  ddl_rhs, x-pass variant %d: %.3f ms\n", v, best);
     }
-    ddl_set_option("xfused_variant", 0);
+    ddl_set_option("xfused_variant", g_variant);
     for (int mode = 0; mode < 3; ++mode) {
         double best = 1e30;
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r <= reps; ++r) {
             t.start();
             if (mode == 0) DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, DDL_STAGE_RETAINED_ONLY, P.dout, nullptr));
             if (mode == 1) DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, 0, P.dout, nullptr));
@@ -312,15 +328,54 @@ static void timing(int n) {
         }
         say("  %s: %.3f ms\n", mode == 0 ? "invariants, retained-only sweep" : mode == 1 ? "invariants, full sweep" : "max_square (inverse half + capture)", best);
     }
+    // the bench's step, natively: RK4 with fused stages (the deriv arrays double as `total` and the stage state)
+    {
+        void* tmp[6]; void* total[6];
+        for (int c = 0; c < 6; ++c) { total[c] = P.deriv[c]; tmp[c] = dmalloc(P.nk * 16); dzero(tmp[c], P.nk * 16); dzero(total[c], P.nk * 16); }
+        const double coeff[6] = {1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
+        double inv[DDL_NINV];
+        DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, 0, P.dout, nullptr)); dsync(); d2h(inv, P.dout, sizeof inv);
+        const double dt = 0.2 * (2 * 3.14159265358979323846 / n) / std::sqrt(2.0 * inv[0] + 1e-300);      // ~ CFL 0.2 on the rms speed
+        double best = 1e30;
+        for (int r = 0; r <= reps; ++r) {
+            t.start();
+            rk4_fused_step(P, tmp, total, coeff, dt);
+            const double ms = t.stop_ms();
+            if (r > 0 && ms < best) best = ms;
+        }
+        double after[DDL_NINV];
+        DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, 0, P.dout, nullptr)); dsync(); d2h(after, P.dout, sizeof after);
+        say("  RK4 step, fused stages (4 x ddl_rhs_stage): %.3f ms = %.3e mode-stage updates/s   (ekin %.6e -> %.6e, div2 %.1e)\n",
+            best, 4.0 * P.nk / (best * 1e-3), inv[0], after[0], after[DDL_INV_DIV2]);
+        if (!(after[0] == after[0]) || after[0] > 4 * inv[0]) { g_fail++; say("  RK4 step: energy not sane  FAIL\n"); }
+        // per-kernel CUDA-event times of one such step (ddl_profile_*)
+        ddl_profile_enable(1);
+        rk4_fused_step(P, tmp, total, coeff, dt);
+        static char buf[1 << 16];
+        DDL(ddl_profile_report(buf, sizeof buf));
+        ddl_profile_enable(0);
+        say("  per-kernel totals of one step: %s\n", buf);
+        for (int c = 0; c < 6; ++c) dfree(tmp[c]);
+    }
     dsync();
 }
 
 int main(int argc, char** argv) {
-    const int n_check = argc > 1 ? atoi(argv[1]) : 64;
-    const int n_time = argc > 2 ? atoi(argv[2]) : 0;
-    if (argc > 3) g_out = fopen(argv[3], "w");
+    // devcheck [n_check=64] [n_time=0] [outfile] [option=value ...]      options: ddl_set_option names, reps=R
+    int n_check = 64, n_time = 0, reps = 3, pos = 0;
+    for (int i = 1; i < argc; ++i) {
+        const char* eq = strchr(argv[i], '=');
+        if (eq) {
+            char name[64]; snprintf(name, sizeof name, "%.*s", (int)(eq - argv[i]), argv[i]);
+            const int val = atoi(eq + 1);
+            if (!strcmp(name, "reps")) reps = val;
+            else { if (!strcmp(name, "xfused_variant")) g_variant = val; DDL(ddl_set_option(name, val)); }
+        } else if (pos == 0) { n_check = atoi(argv[i]); pos++; }
+        else if (pos == 1) { n_time = atoi(argv[i]); pos++; }
+        else if (pos == 2) { g_out = fopen(argv[i], "w"); pos++; }
+    }
     if (n_check > 0) check(n_check);
-    if (n_time > 0) timing(n_time);
+    if (n_time > 0) timing(n_time, reps);
     say("devcheck: %s (%d failure%s)\n", g_fail ? "FAILED" : "all ok", g_fail, g_fail == 1 ? "" : "s");
     if (g_out) fclose(g_out);
     return g_fail ? 1 : 0;

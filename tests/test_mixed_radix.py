@@ -53,6 +53,21 @@ def test_emulated_transforms_any_length(lib, shape):
     assert np.array_equal(kd, c2.kdata)          # backward() masks its source in place (representations.py:347-357)
 
 
+@pytest.mark.parametrize("shape", [(9, 15), (10, 6), (5, 9, 7)])
+def test_emulated_transforms_without_dealiasing(lib, shape):
+    """FFT.dealiasing = None zeroes the Nyquist planes only (representations.py:442-455); odd lengths have none."""
+    import emul
+    g = orc.Grid(shape, None, "None")
+    pl = emul.EmulPlan(lib, g)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(shape)
+    c = orc.Comp(g)
+    c["xspace"] = x
+    assert rel(pl.forward(x), c["kspace"]) < 2e-15
+    xb, _ = pl.backward(c["kspace"].copy())
+    assert rel(xb, c["xspace"]) < 2e-15
+
+
 def test_sample_grid_450(lib):
     """The 2-D decaying-turbulence sample's grid: 450 = 2 * 3^2 * 5^2."""
     import emul

@@ -39,3 +39,11 @@ def test_devcheck_device(n):
     import build_devcheck
     out = _run(build_devcheck.device(), [n], env=build_devcheck.cuda_env())
     assert "sm_100a" in out and "FAIL" not in out
+
+
+@pytest.mark.gpu
+def test_devcheck_device_timing_mode():
+    """The native RK4 step (4 x ddl_rhs_stage) and the per-kernel profile: the 20-second measurement loop for kernel work."""
+    import build_devcheck
+    out = _run(build_devcheck.device(), [0, 128, "reps=2"], env=build_devcheck.cuda_env())
+    assert "RK4 step, fused stages" in out and "x_fused" in out and "assemble_stage" in out
