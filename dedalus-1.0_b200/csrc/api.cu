@@ -98,10 +98,12 @@ static int run_tile(int N, int mode, int dir, int phys, TileParams& p, int nthre
                   (size_t)N * p.ld * sizeof(cplx), TILE_SMEM_MAX);
         return -1;
     }
-    switch (N) {
+    if (!p.sh_on) {        // the shearing-box phase hook lives in the runtime-length instantiation only
+        switch (N) {
 #define DDL_CASE(N) case N: return run_tile_##N(mode, dir, phys, p, nthreads, s);
-        DDL_CASE(8) DDL_CASE(16) DDL_CASE(32) DDL_CASE(64) DDL_CASE(128) DDL_CASE(256) DDL_CASE(512)
-        DDL_CASE(1024) DDL_CASE(2048)
+            DDL_CASE(8) DDL_CASE(16) DDL_CASE(32) DDL_CASE(64) DDL_CASE(128) DDL_CASE(256) DDL_CASE(512)
+            DDL_CASE(1024) DDL_CASE(2048)
+        }
     }
     if (!rt_factor(N, p.rt)) {
         set_error("unsupported transform length %d (prime factors up to %d)", N, DDL_RT_MAXR);
@@ -205,12 +207,14 @@ struct ddl_plan {
     long long ntot = 1;
     KGeom geom;          // local k-array geometry
     long long nmodes = 0;
+    int shear_on = 0;               // shearing box (ddl_set_shear): phase factors in the x passes of ddl_forward / ddl_backward
+    double sh_S = 0.0, sh_t = 0.0, sh_dy = 0.0;
     double* cfl_out = nullptr;      // CFL capture target of the x passes (ddl_rhs_capture_max), caller-owned
     double* red_partial = nullptr;  // block partials of the reductions (reduce.cuh)
     std::vector<void*> owned;
 };
 
-static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv, const uint8_t* keep) {
+static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv, const uint8_t* keep, bool allow_full = false) {
     a.n = n; a.half = half; a.nk = half ? n / 2 + 1 : n;
     {
         RtFac f;
@@ -225,12 +229,16 @@ static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv,
         if (keep[j] && mi > m) m = mi;
     }
     if (m < 0) { set_error("dealias mask removes every mode"); return -1; }
-    if (2 * m >= n) { set_error("dealias mask keeps the Nyquist mode; unsupported"); return -1; }      // odd n has none
+    // a full axis keeps every row, the Nyquist one included: no pruning along it (the shearing box, whose ky mask
+    // depends on kx and time and is applied by the caller, representations.py:627-642); only the ky axis may be full
+    const bool full = !half && 2 * m >= n && n % 2 == 0;
+    if (full && !allow_full) { set_error("dealias mask keeps the Nyquist mode; unsupported on this axis"); return -1; }
+    if (half && 2 * m >= n) { set_error("dealias mask keeps the Nyquist mode; unsupported"); return -1; }      // odd n has none
     for (int j = 0; j < a.nk; ++j) {
         int mi = (j <= n / 2) ? j : n - j;
         if ((keep[j] != 0) != (mi <= m)) { set_error("dealias mask is not of the form |k index| <= m"); return -1; }
     }
-    a.m = m; a.cnt = half ? m + 1 : 2 * m + 1;
+    a.m = m; a.cnt = half ? m + 1 : (full ? n : 2 * m + 1);
     std::vector<double> kvh(kv, kv + a.nk), kvc(a.cnt);
     std::vector<unsigned char> kp(keep, keep + a.nk);
     std::vector<int> c2f(a.cnt), f2c(a.nk, -1), f2f(a.nk, -1);
@@ -262,10 +270,10 @@ extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* sha
     int rc = 0;
     if (ndim == 3) {
         rc = build_axis(pl, pl->az, (int)shape_x[0], false, kz, keepz);
-        if (!rc) rc = build_axis(pl, pl->ay, (int)shape_x[1], false, ky, keepy);
+        if (!rc) rc = build_axis(pl, pl->ay, (int)shape_x[1], false, ky, keepy, nranks == 1);
         if (!rc) rc = build_axis(pl, pl->ax, (int)shape_x[2], true, kx, keepx);
     } else {
-        rc = build_axis(pl, pl->ay, (int)shape_x[0], false, ky, keepy);
+        rc = build_axis(pl, pl->ay, (int)shape_x[0], false, ky, keepy, true);
         if (!rc) rc = build_axis(pl, pl->ax, (int)shape_x[1], true, kx, keepx);
     }
     if (rc) { ddl_plan_destroy(pl); return rc; }
@@ -517,10 +525,13 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
 // pair-mode pass (C2R / R2C / FUSED) over real lines
 static int pass_pair(const char* name, int N, int mode, int phys, int ni, int no, const void* const* in, void* const* out,
                      const TileSide& si, const TileSide& so, int n_lines, int n_outer, int kn, double scale,
-                     const cplx* tw, const PhysConst& pc, ddl_stream_t st, double* cfl = nullptr) {
+                     const cplx* tw, const PhysConst& pc, ddl_stream_t st, double* cfl = nullptr, const ddl_plan* shear = nullptr) {
     if (n_outer <= 0) return 0;
     TileParams p;
     memset(&p, 0, sizeof(p));
+    if (shear && shear->shear_on) {
+        p.sh_on = 1; p.sh_S = shear->sh_S; p.sh_t = shear->sh_t; p.sh_dy = shear->sh_dy; p.sh_kx = shear->ax.kv;
+    }
     for (int f = 0; f < ni; ++f) p.in[f] = in[f];
     for (int f = 0; f < no; ++f) p.out[f] = out[f];
     p.si = si; p.so = so; p.nf_in = ni; p.nf_out = no;
@@ -656,7 +667,7 @@ static int phase_xc2r(ddl_plan* pl, const void* B, double* x, ddl_stream_t st) {
     void* out[1] = {x};
     PhysConst pc = {};
     return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, in, out, side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr),
-                     side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr), Y.n, pl->nzl, X.cnt, 1.0, X.tw, pc, st);
+                     side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr), Y.n, pl->nzl, X.cnt, 1.0, X.tw, pc, st, nullptr, pl);
 }
 static int phase_xr2c(ddl_plan* pl, const double* x, void* Cout, ddl_stream_t st) {
     const Axis &X = pl->ax, &Y = pl->ay;
@@ -665,7 +676,7 @@ static int phase_xr2c(ddl_plan* pl, const double* x, void* Cout, ddl_stream_t st
     PhysConst pc = {};
     return pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, in, out, side(1, X.n, (long long)Y.n * X.n, nullptr, nullptr),
                      side(1, kx_pitch(pl), (long long)Y.n * kx_pitch(pl), nullptr, nullptr), Y.n, pl->nzl, X.cnt,
-                     1.0 / (double)pl->ntot, X.tw, pc, st);
+                     1.0 / (double)pl->ntot, X.tw, pc, st, nullptr, pl);
 }
 
 // ---------------------------------------------------------------- 2-D passes
@@ -717,6 +728,13 @@ static int need_one_rank(const ddl_plan* pl, const char* what) {
     return 0;
 }
 
+// shearing-box plans (full ky axis) take the generic kernels for every pass
+struct FastGuard {
+    int saved;
+    explicit FastGuard(bool off) : saved(g_use_fast) { if (off) g_use_fast = 0; }
+    ~FastGuard() { g_use_fast = saved; }
+};
+
 // ---------------------------------------------------------------- transforms
 extern "C" int ddl_dealias(ddl_plan* pl, void* k, void* stream) {
     void* arr[1] = {k};
@@ -726,6 +744,7 @@ extern "C" int ddl_dealias(ddl_plan* pl, void* k, void* stream) {
 extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t work_bytes, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
     DDL_TRY(need_one_rank(pl, "ddl_backward"));
+    FastGuard fg(pl->shear_on != 0);
     DDL_TRY(check_ws(pl, 1, 1, work, work_bytes));
     DDL_TRY(ddl_dealias(pl, k, stream));
     WsLayout w = ws_layout(pl, 1, 1);
@@ -744,12 +763,13 @@ extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t
     void* xo[1] = {x};
     PhysConst pc = {};
     return pass_pair("x_c2r", X.n, TM_C2R, 0, 1, 1, head, xo, side(Y.n, 1, 0, nullptr, nullptr), side(1, X.n, 0, nullptr, nullptr),
-                     Y.n, 1, X.cnt, 1.0, X.tw, pc, st);
+                     Y.n, 1, X.cnt, 1.0, X.tw, pc, st, nullptr, pl);
 }
 
 extern "C" int ddl_forward(ddl_plan* pl, const double* x, void* k, void* work, size_t work_bytes, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
     DDL_TRY(need_one_rank(pl, "ddl_forward"));
+    FastGuard fg(pl->shear_on != 0);
     DDL_TRY(check_ws(pl, 1, 1, work, work_bytes));
     WsLayout w = ws_layout(pl, 1, 1);
     cplx* r0 = (cplx*)work; cplx* r2 = r0 + w.r0 + w.r1;
@@ -767,7 +787,7 @@ extern "C" int ddl_forward(ddl_plan* pl, const double* x, void* k, void* work, s
     void* Cb[1] = {(void*)(r0 + w.r0)};
     PhysConst pc = {};
     DDL_TRY(pass_pair("x_r2c", X.n, TM_R2C, 0, 1, 1, xi, Cb, side(1, X.n, 0, nullptr, nullptr), side(Y.n, 1, 0, nullptr, nullptr),
-                      Y.n, 1, X.cnt, 1.0 / (double)pl->ntot, X.tw, pc, st));
+                      Y.n, 1, X.cnt, 1.0 / (double)pl->ntot, X.tw, pc, st, nullptr, pl));
     DDL_TRY(forward_tail_2d(pl, 1, Cb, dst, true, st));
     return ddl_dealias(pl, k, stream);
 }
@@ -1173,6 +1193,15 @@ extern "C" int ddl_sync(void* stream) {
 #else
     (void)stream;
 #endif
+    return 0;
+}
+
+// shearing box: phase factors of the following ddl_forward / ddl_backward calls on this plan (include/ddl.h)
+extern "C" int ddl_set_shear(ddl_plan* pl, int enable, double shear_rate, double time, double dy) {
+    if (!pl) { set_error("ddl_set_shear: NULL plan"); return -1; }
+    if (enable && pl->nranks != 1) { set_error("the shearing box runs on one-rank plans"); return -1; }
+    pl->shear_on = enable ? 1 : 0;
+    pl->sh_S = shear_rate; pl->sh_t = time; pl->sh_dy = dy;
     return 0;
 }
 

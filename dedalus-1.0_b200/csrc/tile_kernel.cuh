@@ -12,6 +12,7 @@
 // Replaces, per transform, fftw rPlan execute + "/= N" + dealias passes of the reference
 // (dedalus/data_objects/representations.py:318-357, dealias_cy_3d.pyx:13-46).
 #pragma once
+#include <cmath>
 #include "ddl_common.cuh"
 #include "physics_ops.cuh"
 
@@ -49,6 +50,11 @@ struct TileParams {
     PhysConst pc;
     const char* name;     // label for launch accounting / profiling (host side only)
     RtFac rt;             // N == 0 instantiation (runtime length): the factorisation of the transform length
+    // shearing box (representations.py:558-740), pair modes of the N == 0 instantiation only: the spectrum of the line
+    // at y = l * sh_dy is multiplied by exp(-+ i ((S kx) y) t) between the x pass and the y pass (rev_np / fwd_np :700-740)
+    int sh_on;
+    double sh_S, sh_t, sh_dy;
+    const double* sh_kx;  // kx value per stored non-negative mode
     double* cfl;          // TM_FUSED: optional CFL capture, cfl[0] = max(cfl[0], max_{x,i} u_i(x)^2), cfl[1]: second group
                           // (B or T) -- fields.py:153-157 max_square without a transform of its own; NULL = off
 };
@@ -124,6 +130,18 @@ DDL_HD long long outer_off(const TileSide& s, int o) {
     return (long long)(s.outer_tab ? s.outer_tab[o] : o) * s.s_outer;
 }
 
+// exp(sign * i * ((S kx) y) t), the argument rounded in the reference's order (representations.py:607-611,674,692)
+DDL_HD cplx shear_phase(const TileParams& p, int k, int line, double sign) {
+    const double arg = ((p.sh_S * p.sh_kx[k]) * ((double)line * p.sh_dy)) * p.sh_t;
+    double s, c;
+#if DDL_DEVICE_BUILD
+    sincos(arg, &s, &c);
+#else
+    s = std::sin(arg); c = std::cos(arg);
+#endif
+    return mk(c, sign * s);
+}
+
 template <int N, int MODE, int DIR, class PHYS>
 DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz) {
     const int ld = p.ld;
@@ -182,6 +200,9 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
                         const long long a = ib + (long long)pk * p.si.s_n;
                         A = src[a + (long long)l0 * p.si.s_inner];
                         if (l1 < p.inner_len) B = src[a + (long long)l1 * p.si.s_inner];
+                        if constexpr (N == 0) {
+                            if (p.sh_on) { A = cmul(A, shear_phase(p, k, l0, -1.0)); B = cmul(B, shear_phase(p, k, l1, -1.0)); }
+                        }
                     }
                 }
                 const int c = g * nft + f;
@@ -271,8 +292,12 @@ DDL_BODY void tile_block(const TileParams& p, cplx* tile, int bx, int by, int bz
                 const int l0 = line0 + 2 * g, l1 = l0 + 1;
                 cplx* __restrict__ dst = (cplx*)p.out[f];
                 const long long a = ob + (long long)pk * p.so.s_n;
-                dst[a + (long long)l0 * p.so.s_inner] = mk((Zk.x + Zm.x) * h, (Zk.y - Zm.y) * h);
-                if (l1 < p.inner_len) dst[a + (long long)l1 * p.so.s_inner] = mk((Zk.y + Zm.y) * h, (Zm.x - Zk.x) * h);
+                cplx Ak = mk((Zk.x + Zm.x) * h, (Zk.y - Zm.y) * h), Bk = mk((Zk.y + Zm.y) * h, (Zm.x - Zk.x) * h);
+                if constexpr (N == 0) {
+                    if (p.sh_on) { Ak = cmul(Ak, shear_phase(p, k, l0, +1.0)); Bk = cmul(Bk, shear_phase(p, k, l1, +1.0)); }
+                }
+                dst[a + (long long)l0 * p.so.s_inner] = Ak;
+                if (l1 < p.inner_len) dst[a + (long long)l1 * p.so.s_inner] = Bk;
             }
         }
 

@@ -29,6 +29,8 @@ def invariants(data):
     if pid is None:
         return None
     comps = [c for _, _, c in data.components()]
+    if not comps[0]._static_k:
+        return None             # shearing box: the sweep's wavenumber tables are static; tensor-level route
     key = (id(data), data.time, tuple(c._k.data_ptr() for c in comps))
     if _shared["on"] and _shared["key"] == key:
         return _shared["val"]

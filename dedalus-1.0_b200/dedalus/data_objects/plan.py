@@ -78,7 +78,7 @@ class Plan(object):
     representations.py:180-186,231-233); `k['y']`, `kshape_local`, `xshape_local` and the
     offsets describe the local slab, the `*_np` arrays stay global."""
 
-    def __init__(self, shape, length, dealiasing, nranks=1, rank=0, ky_layout="block"):
+    def __init__(self, shape, length, dealiasing, nranks=1, rank=0, ky_layout="block", full_ky=False):
         self.shape = tuple(int(s) for s in shape)
         self.ndim = len(self.shape)
         self.length = tuple(float(x) for x in length)
@@ -89,6 +89,13 @@ class Plan(object):
         self.ky_layout = ky_layout if self.nranks > 1 else "block"
         self.kshape, self.ktrans, self.dk, self.kny, self.k_np = wavenumbers(self.shape, self.length)
         self.keep_np = keep_masks(dealiasing, self.ktrans, self.kny, self.k_np)
+        # shearing box: the ky mask depends on kx and time and is applied by the representation
+        # (representations.py:627-642); the plan keeps every ky row, the passes prune nothing along y
+        self.full_ky = bool(full_ky)
+        if self.full_ky:
+            if self.nranks > 1:
+                raise NotImplementedError("FourierShearRepresentation runs on one GPU (no slab decomposition).")
+            self.keep_np["y"] = np.ones_like(self.keep_np["y"])
         self.device = device()
         shp = np.array(self.shape, dtype=np.int64)
         keep8 = {n: np.ascontiguousarray(v.astype(np.uint8)) for n, v in self.keep_np.items()}
@@ -159,7 +166,7 @@ class Plan(object):
             pass
 
 
-def get_plan(shape, length, dealiasing):
+def get_plan(shape, length, dealiasing, full_ky=False):
     """One plan per (grid, dealiasing, device, process-group size): with a torch.distributed
     process group of P > 1 ranks a 3-D grid is slab-decomposed over it."""
     import os
@@ -167,8 +174,8 @@ def get_plan(shape, length, dealiasing):
     nranks, rank = com_sys.nproc, com_sys.myproc
     layout = os.environ.get("DEDALUS_KY_LAYOUT", decfg.get("parallel", "ky_layout")) if nranks > 1 else "block"
     key = (tuple(int(s) for s in shape), tuple(float(x) for x in length), str(dealiasing),
-           torch.cuda.current_device() if torch.cuda.is_available() else -1, nranks, rank, layout)
+           torch.cuda.current_device() if torch.cuda.is_available() else -1, nranks, rank, layout, bool(full_ky))
     pl = _PLANS.get(key)
     if pl is None:
-        pl = _PLANS[key] = Plan(shape, length, dealiasing, nranks, rank, layout)
+        pl = _PLANS[key] = Plan(shape, length, dealiasing, nranks, rank, layout, full_ky=full_ky)
     return pl

@@ -55,7 +55,7 @@ class FourierRepresentation(Representation):
         else:
             self.xtrans = {"x": 2, 2: "x", "y": 1, 1: "y", "z": 0, 0: "z"}
 
-        self._plan = _plan.get_plan(shape, self.length, dealiasing)
+        self._plan = _plan.get_plan(shape, self.length, dealiasing, full_ky=not self._static_k)
         pl = self._plan
         self.ktrans = pl.ktrans
         self.global_shape["kspace"] = pl.kshape.copy()
@@ -367,3 +367,97 @@ class FourierRepresentation(Representation):
         """Write the current data into an h5py-like dataset (representations.py:511-526)."""
         dataset[:] = self.data.cpu().numpy()
         dataset.attrs["space"] = self._curr_space
+
+
+class FourierShearRepresentation(FourierRepresentation):
+    """Fourier representation in a shearing-box domain (representations.py:558-740).
+
+    The wavenumber ky of every mode drifts with time, ky(kx, t) = ky0 - S kx t, wrapped once past the Nyquist value
+    (:627-642), so `k['y']` is a dense array over (kx, ky) / (ky, 1, kx) and the 2/3 mask along y depends on kx and t.
+    Transforms: x pass, the phase factor exp(+-i S kx y t) on the half-transformed lines, then the y (z) passes
+    (fwd_np / rev_np :700-740) -- here the factor is applied INSIDE the x pass of ddl_forward / ddl_backward
+    (include/ddl.h: ddl_set_shear), on a plan that keeps every ky row.  A compatibility path: the physics classes
+    evaluate their right-hand side through the reference's unfused helpers for this representation and the
+    integrators update with tensor operations; one GPU."""
+
+    _static_k = False
+
+    def __init__(self, sd, shape, length):
+        FourierRepresentation.__init__(self, sd, shape, length)
+        self.k = dict(self._plan.k)                       # private copy: k['y'] is this component's own, time dependent
+        self._ky = self.k["y"].clone()
+        self.k["y"] = self._ky * torch.ones_like(self.k["x"])
+        S = float(self.sd.parameters["shear_rate"])
+        self._shear_rate = S
+        self._wave_rate = S * self.k["x"]
+        self._dy = float(self.dx()[self.xtrans["y"]])
+        self._update_k()
+
+    def _update_k(self):
+        """Evolve the wavenumbers with the shear (representations.py:627-642): shift, wrap once, dealias."""
+        ky = self.k["y"]
+        torch.sub(self._ky, self._wave_rate * float(self.sd.time), out=ky)
+        kny_y = float(self.kny[3 - self.ndim])
+        ky.copy_(torch.where(ky <= -kny_y, ky + 2 * kny_y, ky))
+        ky.copy_(torch.where(ky > kny_y, ky - 2 * kny_y, ky))
+        self.dealias()
+
+    def _set_shear(self):
+        check(lib.ddl_set_shear(self._plan.handle, 1, self._shear_rate, float(self.sd.time), self._dy))
+
+    def dealias(self):
+        """The configured rule with the sheared ky (dealias_cy_2d.pyx:36-41, dealias_cy_3d.pyx:38-46;
+        zero_nyquist :442-455 for FFT.dealiasing = None)."""
+        self.require_space("kspace")
+        mask = None
+        for name, kv in self.k.items():
+            kn = float(self.kny[self.ktrans[name]])
+            if self._dealiasing in ("2/3", "2/3 cython"):
+                m = (kv >= 2.0 / 3.0 * kn) | (kv <= -2.0 / 3.0 * kn)
+            else:
+                m = kv.abs() == kn
+            mask = m if mask is None else (mask | m)
+        self._k.masked_fill_(mask.expand_as(self._k), 0.0)
+        self._clean = True
+
+    dealias_23 = dealias
+    dealias_23_cython = dealias
+
+    def zero_nyquist(self):
+        self.require_space("kspace")
+        mask = None
+        for name, kv in self.k.items():
+            m = kv.abs() == float(self.kny[self.ktrans[name]])
+            mask = m if mask is None else (mask | m)
+        self.kdata.masked_fill_(mask.expand_as(self._k), 0.0)
+
+    @timer
+    def forward(self):
+        if self._curr_space == "kspace":
+            raise ValueError("Forward transform cannot be called from kspace.")
+        self._set_shear()
+        FourierRepresentation.forward(self)
+        self.dealias()
+
+    @timer
+    def backward(self):
+        if self._curr_space == "xspace":
+            raise ValueError("Backward transform cannot be called from xspace.")
+        self.dealias()
+        self._set_shear()
+        FourierRepresentation.backward(self)
+
+    fft = forward
+    ifft = backward
+
+    def deriv(self, dim):
+        if dim != "y":
+            return FourierRepresentation.deriv(self, dim)
+        self.require_space("kspace")
+        return self._k * (1j * self.k["y"])
+
+    def verify_clean(self):
+        return self._clean
+
+    def _hermitian_project(self):
+        raise NotImplementedError("FourierShearRepresentation: not on the fused path")

@@ -34,7 +34,12 @@ class StateData(object):
         return self.__class__(self.time, self.shape, self.length, self._field_classes, params=self.parameters)
 
     def set_time(self, time):
+        # shearing-box components follow the time: their wavenumbers drift with it (state_data.py:115-121)
         self.time = time
+        for _, f in self.fields.items():
+            if not f.representation._static_k:
+                for _, c in f:
+                    c._update_k()
 
     def add_field(self, name, fieldtype):
         if name in self.fields:

@@ -117,6 +117,10 @@ class Physics(object):
         transforms per call in 3-D MHD, fields.py:153-157); here the maxima come out of ONE pass of
         the inverse half of the RHS pipeline with the reduction inside the x pass
         (include/ddl.h: ddl_reduce_max_square), and nothing is written but workspace."""
+        if self._unfused:
+            self.dtlist = []
+            self.set_dtlist(data)          # field.max_square(), component by component (fields.py:153-157)
+            return min(self.dtlist)
         return self.dt_from_maxima(data, self.max_squares(data))
 
     def dt_from_maxima(self, data, maxima):
@@ -211,6 +215,18 @@ class Physics(object):
         for _, field in deriv:
             field.zero_all()
         deriv.set_time(data.time)
+        if not self._representation._static_k:
+            # shearing box: the scratch fields' wavenumbers follow the state's time too (physics.py:143-149)
+            for _, field in self.aux_fields:
+                field.zero_all(space="kspace")
+            self.aux_fields.set_time(data.time)
+
+    @property
+    def _unfused(self):
+        """True for representations whose wavenumbers depend on time (FourierShearRepresentation): the fused
+        pipeline's index tables are static, so the right-hand side is evaluated the reference's way, helper by
+        helper (a compatibility path), and the integrators update with tensor operations."""
+        return not self._representation._static_k
 
     # ------------------------------------------------------------------ solenoidal or not
     SOLENOIDAL_TOL = 1e-12      # compressive fraction sqrt(sum |k.u|^2 / sum |k|^2 |u|^2) below which u counts as div-free
@@ -224,6 +240,8 @@ class Physics(object):
         the CALLER has written since the last check one sweep of ddl_reduce_invariants measures the
         compressive fraction of u and B.  Returns True when the whole state is solenoidal."""
         vec = [(n, f) for n, f in data if n in ("u", "B")]
+        if self._unfused:
+            return True                    # the unfused path evaluates the advective forms themselves
         if any(c._soln is None for _, f in vec for _, c in f):
             from ..analysis.volume_average import invariants
             from .._lib import INV
@@ -243,6 +261,8 @@ class Physics(object):
         integrator may ask for the spectral assembly fused with its stage update."""
         if not self._is_finalized:
             self._finalize()
+        if self._unfused:
+            return False
         return not getattr(self, "_rotation", False) and not self.forcing_functions
 
     def _fused_rhs(self, data, deriv, flags, fuse=None):
@@ -411,8 +431,8 @@ class Physics(object):
 class IncompressibleHydro(Physics):
     """Homogeneous incompressible hydrodynamics (physics.py:419-610).
 
-    parameters: 'nu' (0.), 'viscosity_order' (1), 'shear_rate' (0., shearing box not
-    supported by this backend), 'Omega' (None)."""
+    parameters: 'nu' (0.), 'viscosity_order' (1), 'shear_rate' (0.; nonzero needs
+    FourierShearRepresentation), 'Omega' (None)."""
 
     _physics_id = _lib.HYDRO
 
@@ -442,9 +462,15 @@ class IncompressibleHydro(Physics):
 
     def _finalize(self):
         Physics._finalize(self)
-        if self.parameters["shear_rate"] != 0.:
-            raise NotImplementedError("Linear shear needs FourierShearRepresentation, which this backend does not provide.")
-        self._shear = False
+        # physics.py:486-494
+        if self.parameters["shear_rate"] == 0.:
+            self._shear = False
+            if self._unfused:
+                mylog.warning("Performance suffers when using a shearing representation without a linear shear.")
+        else:
+            self._shear = True
+            if not self._unfused:
+                raise ValueError("A shearing representation must be used if shear_rate is nonzero.")
         self._rotation = self.parameters["Omega"] is not None
         if self._rotation and self.ndim == 2:
             mylog.warning("Rotation is dynamically insignificant in 2D incompressible hydrodynamics.")
@@ -468,8 +494,50 @@ class IncompressibleHydro(Physics):
         if self._first_rhs:
             self._setup_integrating_factors(deriv)
             self._first_rhs = False
+        if not self._is_finalized:
+            self._finalize()
+        if self._unfused:
+            return self._unfused_hydro_rhs(data, deriv)
         self._fused_rhs(data, deriv, self._rhs_flags())
         self._extra_momentum_terms(data, deriv)
+
+    def _unfused_hydro_rhs(self, data, deriv):
+        """The reference's own sequence for the velocity (and tracer) equation, physics.py:527-599, in the form
+        d_t f + S y d_x f - c lap f = RHS(f); used for the shearing box."""
+        Physics.RHS(self, data, deriv)
+        ms, mv = self.aux_fields["mathscalar"], self.aux_fields["mathvector"]
+        S, Om = self.parameters["shear_rate"], self.parameters["Omega"]
+        self.XgradY(data["u"], data["u"], ms, mv, deriv["u"])
+        for i in self.dims:
+            deriv["u"][i]["kspace"].mul_(-1.)
+        if self._shear:
+            deriv["u"]["x"]["kspace"].sub_(S * data["u"]["y"]["kspace"])
+        if self._rotation:
+            self.XconstcrossY(Om, data["u"], mv)
+            for i in self.dims:
+                deriv["u"][i]["kspace"].sub_(2 * mv[i]["kspace"])
+        if "VelocityForcing" in self.forcing_functions:
+            for i in self.dims:
+                deriv["u"][i]["kspace"].add_(self.forcing_functions["VelocityForcing"](data, i))
+        if type(self) is IncompressibleHydro:
+            self._unfused_pressure_projection(data, deriv)
+        if self._tracer:
+            self.XgradY(data["u"], data["c"], ms, mv, deriv["c"])
+            deriv["c"]["kspace"].mul_(-1.)
+        if self._shear:
+            self._setup_integrating_factors(deriv)      # k^2 has moved with the shear (physics.py:584-586)
+
+    def _unfused_pressure_projection(self, data, deriv):
+        """physics.py:588-599, including the shear source -S d_x u_y of the pressure equation and the k^2 array
+        that laplace_solve caches at its FIRST call (physics.py:412-413): in a shearing box the reference keeps
+        dividing by the k^2 of that first time level, and so does this."""
+        ms = self.aux_fields["mathscalar"]
+        self.divX(deriv["u"], ms)
+        if self._shear:
+            ms["kspace"].sub_(self.parameters["shear_rate"] * data["u"]["y"].deriv("x"))
+        self.laplace_solve(ms, ms)
+        for i in self.dims:
+            deriv["u"][i]["kspace"].sub_(ms.deriv(self._trans[i]))
 
     def _extra_momentum_terms(self, data, deriv):
         """Rotation and user forcing (physics.py:563-572), added through the projector, which is
@@ -577,7 +645,29 @@ class BoussinesqHydro(IncompressibleHydro):
     def set_thermal_forcing(self, func):
         self.forcing_functions["ThermalForcing"] = func
 
+    def _unfused_bouss_rhs(self, data, deriv):
+        """physics.py:664-712 helper by helper (shearing box)."""
+        IncompressibleHydro.RHS(self, data, deriv)
+        ms, mv = self.aux_fields["mathscalar"], self.aux_fields["mathvector"]
+        p = self.parameters
+        d = p["boussinesq_direction"]
+        ms["kspace"] = data["T"]["kspace"]
+        ms["kspace"].mul_(p["g"])
+        ms["kspace"].mul_(p["alpha_t"])
+        deriv["u"][d]["kspace"].add_(ms["kspace"])
+        if type(self) is BoussinesqHydro:
+            self._unfused_pressure_projection(data, deriv)
+        self.XgradY(data["u"], data["T"], ms, mv, deriv["T"])
+        deriv["T"]["kspace"].mul_(-1.)
+        ms["kspace"] = data["u"][d]["kspace"]
+        ms["kspace"].mul_(p["beta"])
+        deriv["T"]["kspace"].sub_(ms["kspace"])
+        if "ThermalForcing" in self.forcing_functions:
+            deriv["T"]["kspace"].add_(self.forcing_functions["ThermalForcing"](data))
+
     def RHS(self, data, deriv):
+        if self._unfused:
+            return self._unfused_bouss_rhs(data, deriv)
         junk = not all(c._clean for _, _, c in data.components())
         IncompressibleHydro.RHS(self, data, deriv)
         if junk:
@@ -609,6 +699,29 @@ class IncompressibleMHD(IncompressibleHydro):
         eta, vo = self.parameters["eta"], self.parameters["viscosity_order"]
         for _, comp in deriv["B"]:
             comp.integrating_factor = None if eta == 0. else IntegratingFactor(comp, eta, vo)
+
+    def RHS(self, data, deriv):
+        if self._unfused:
+            return self._unfused_mhd_rhs(data, deriv)
+        IncompressibleHydro.RHS(self, data, deriv)
+
+    def _unfused_mhd_rhs(self, data, deriv):
+        """physics.py:770-819 helper by helper (shearing box): Lorentz force, projection, induction, S B_y e_x."""
+        IncompressibleHydro.RHS(self, data, deriv)
+        aux = self.aux_fields
+        ms, mv, mv2 = aux["mathscalar"], aux["mathvector"], aux["mathvector2"]
+        fpr = 4 * np.pi * self.parameters["rho0"]
+        cur = ms if self.ndim == 2 else mv
+        self.curlX(data["B"], cur)
+        self.XcrossY(cur, data["B"], mv2)
+        for i in self.dims:
+            deriv["u"][i]["kspace"].add_(mv2[i]["kspace"] / fpr)
+        if type(self) is IncompressibleMHD:
+            self._unfused_pressure_projection(data, deriv)
+        self.XcrossY(data["u"], data["B"], cur)
+        self.curlX(cur, deriv["B"])
+        if self._shear:
+            deriv["B"]["x"]["kspace"].add_(self.parameters["shear_rate"] * data["B"]["y"]["kspace"])
 
     def _rhs_flags(self):
         # the reference transforms the MHD state itself to x-space and back (physics.py:797-815),

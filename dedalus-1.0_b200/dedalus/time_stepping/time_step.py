@@ -59,6 +59,8 @@ def _settle(sd, R=None):
     """Before a step: components whose buffer was handed out since the last step get their
     'dealiased' bit re-checked on the device (FourierRepresentation.verify_clean) and, given the physics
     object, their fields' 'solenoidal' verdict (Physics.verify_solenoidal): both decide which kernels run."""
+    if R is not None and getattr(R, "_unfused", False):
+        return                      # shearing box: no fused kernels to choose between
     for _, _, c in sd.components():
         c.require_space("kspace")
         if not c._clean and not c._checked:
@@ -243,7 +245,7 @@ class TimeStepBase(object):
 
     def _lazy_dt_ok(self):
         R = self.RHS
-        return hasattr(R, "capture_begin") and not R.aux_eqns
+        return hasattr(R, "capture_begin") and not R.aux_eqns and not getattr(R, "_unfused", False)
 
     def _rhs_and_dt(self, data, k):
         """k = RHS(data) and the CFL-limited dt of `data`, from the same x pass."""
@@ -264,6 +266,8 @@ class TimeStepBase(object):
         vanishes outside the dealias mask (the fused sweep visits the retained modes only)."""
         R = self.RHS
         if not self.fuse_stages or getattr(self, "_coeff", None) is None or not hasattr(R, "_fused_rhs"):
+            return False
+        if getattr(R, "_unfused", False):
             return False
         if R.aux_eqns or not R.can_fuse_stage():
             return False
@@ -296,7 +300,32 @@ class TimeStepBase(object):
             k_out.set_time(state_in.time)
 
     # ---- device stage launches ---------------------------------------------------------
+    def _stage_tensor(self, kind, start, out, d1, d2, if_from, dt):
+        """The same updates with the integrating factor as an ARRAY (shearing box: k^2 moves with time), component by
+        component like the reference's loops (time_step.py:285-304): Euler where the factor is None."""
+        from . import etd_tensor as E
+        s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
+        b = _kspace_tensors(d2) if d2 is not None else [None] * len(s)
+        for j, (_, _, c) in enumerate(if_from.components()):
+            IF = c.integrating_factor
+            if IF is None:
+                if kind == _lib.ETD1:
+                    E.euler(s[j], o[j], a[j], dt)
+                elif kind == _lib.ETD2RK2:
+                    E.euler(s[j], o[j], b[j], dt)
+                else:                                       # ETD2RK1 (time_step.py:383-386)
+                    E.euler(s[j], o[j], b[j] - a[j], dt / 2.)
+            elif kind == _lib.ETD1:
+                E.etd1(s[j], o[j], a[j], -IF.tensor(), dt)
+            elif kind == _lib.ETD2RK2:
+                E.etd2rk2(s[j], o[j], a[j], b[j], -IF.tensor(), dt)
+            else:
+                E.etd2rk1(s[j], o[j], a[j], b[j], -IF.tensor(), dt)
+        _mark(out, False)
+
     def _stage(self, kind, start, out, d1, d2, if_from, dt):
+        if getattr(self.RHS, "_unfused", False):
+            return self._stage_tensor(kind, start, out, d1, d2, if_from, dt)
         s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
         b = _kspace_tensors(d2) if d2 is not None else None
         coeff, order = _if_coefficients(if_from)
@@ -435,6 +464,8 @@ class RK4(RKBase):
 
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
+        if getattr(R, "_unfused", False):
+            raise NotImplementedError("RK4 in a shearing box: use RK2mid / RK2trap (the reference's RK4 does not run, SURVEY F1-F3)")
         _settle(data, self.RHS)
         lazy = dt is None
         if not lazy and self._can_fuse(data, self.total_deriv, self.temp_data):
@@ -493,6 +524,8 @@ class CrankNicholsonVisc(TimeStepBase):
         self._coeff = None
 
     def do_advance(self, data, dt):
+        if getattr(self.RHS, "_unfused", False):
+            raise NotImplementedError("CrankNicholsonVisc in a shearing box: use RK2mid / RK2trap")
         _settle(data, self.RHS)
         lazy = dt is None
         if not lazy and self._can_fuse(data):

@@ -102,6 +102,14 @@ int ddl_dealias(ddl_plan* plan, void* k, void* stream);
 /* representations.py:419-425 deriv(): out = i * k_axis * in   (axis: 0=x, 1=y, 2=z) */
 int ddl_deriv(ddl_plan* plan, const void* k_in, void* k_out, int axis, void* stream);
 
+/* Shearing box (FourierShearRepresentation, representations.py:558-740): between the x pass and the y pass the
+ * half-transformed line at y = j * dy is multiplied by exp(+i ((S kx) y) t) on the way to k-space and by its conjugate
+ * on the way back (fwd_np / rev_np :700-740; FFTW route :667-698).  While enabled, ddl_forward / ddl_backward of this
+ * plan apply that factor inside their x pass (no extra pass over memory).  The plan of a shearing box is created with a
+ * ky mask that keeps EVERY row (all ones, Nyquist included): the sheared wavenumber ky - S kx t, its wrap and its 2/3 mask
+ * depend on kx and time (:627-642) and belong to the caller; kx and kz are masked as usual.  One-rank plans. */
+int ddl_set_shear(ddl_plan* plan, int enable, double shear_rate, double time, double dy);
+
 /* physics.py:527-599 / 664-712 / 770-819: deriv = RHS(state), all pointers k-space arrays in
  * StateData insertion order (u_x,u_y[,u_z] then T or B_x,B_y[,B_z]) */
 int ddl_rhs(ddl_plan* plan, int physics, const ddl_phys_params* params,

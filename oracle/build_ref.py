@@ -126,6 +126,8 @@ SPECIFIC = {
         (r"index = zip\(\*test\.nonzero\(\)\)", "index = list(zip(*test.nonzero()))"),
         (r"refgrid\[\[slice\(i\) for i in np\.asarray\(self\.local_shape\['xspace'\], dtype=float\)\]\]",
          "refgrid[tuple(slice(float(i)) for i in self.local_shape['xspace'])]"),
+        # np.ogrid[...] returned a list in the numpy the reference was written for and returns a tuple now
+        (r"^(\s*)grid\[0\] \+= self\.offset\['xspace'\]", r"\1grid = list(grid) if open else grid\n\1grid[0] += self.offset['xspace']"),
     ],
     "dedalus/physics/physics.py": [
         (r"if self\.k2 == None:", "if self.k2 is None:"),
