@@ -63,6 +63,10 @@ CASES = [
          params=dict(nu=0.01, eta=0.02, rho0=1.3), integ="RK2mid", dt=5e-3, nsteps=3, t0=0.0),
     dict(name="mhd2d_16x32_rk2trap", physics="IncompressibleMHD", shape=(16, 32), length=None, S=-1.0,
          params=dict(nu=0.01, eta=0.0), integ="RK2trap", dt=5e-3, nsteps=3, t0=0.2),
+    # samples/incompressible_hydro/swinging_wave/simulation.py: its grid, box, rotation, shear rate, initial vorticity wave,
+    # integrator and time step (the first 40 of its 80 100 steps)
+    dict(name="swinging_wave_sample", physics="IncompressibleHydro", shape=(30, 10), length=(2 * np.pi, 100 * 2 * np.pi), S=1.5,
+         params=dict(Omega=1.), integ="RK2mid", dt=1. / 150., nsteps=40, t0=0.0, ic="vorticity_wave", mode=(0.01, 4), w_amp=0.01),
     dict(name="bouss2d_16_rk2trap", physics="BoussinesqHydro", shape=(16, 16), length=None, S=2.0,
          params=dict(nu=0.01, kappa=0.0), integ="RK2trap", dt=1e-2, nsteps=3, t0=0.0),
 ]
@@ -79,6 +83,10 @@ def build(c, noise):
     RHS.parameters['shear_rate'] = c["S"]
     RHS.parameters.update(c["params"])
     data = RHS.create_fields(c["t0"])
+    if c.get("ic") == "vorticity_wave":
+        import dedalus.init_cond.init_cond as ic
+        ic.vorticity_wave(data, c["mode"], c["w_amp"])
+        return RHS, data
     j = 0
     for fn, f in data:
         for i, comp in f:
