@@ -143,6 +143,10 @@ class Plan(object):
             import os
             from ..config import decfg
             kind = os.environ.get("DEDALUS_SLAB_EXCHANGE", decfg.get("parallel", "exchange"))
+            if kind == "peer" and any(n < 16 or (n & (n - 1)) for n in self.shape[:2]):
+                # the peer-store passes exist in the specialised strided kernels only (powers of two >= 16);
+                # any other nz / ny exchanges through the collective
+                kind = "collective"
             self._pipe = SlabPipeline(lib, self.handle, self.device, stream=current_stream, exchange=kind)
         return self._pipe
 

@@ -23,7 +23,9 @@ def _free_port():
                                                (2, "hydro3d_16_rk2mid", 1), (4, "mhd3d_8x16x32_rk2trap", 0),
                                                (4, "mhd3d_16_rk2mid", 1), (2, "mhd3d_8x16x32_rk2trap", 1),
                                                (8, "mhd3d_16_rk2mid", 0),      # block slabs: two ranks own NO retained ky row
-                                               (8, "mhd3d_16_rk2mid", 1)])
+                                               (8, "mhd3d_16_rk2mid", 1),
+                                               # grids that are not powers of two (runtime-length kernels): 12 x 20 x 24
+                                               (2, "hydro3d_12x20x24_rk2mid", 0), (4, "hydro3d_12x20x24_rk2mid", 1)])
 def test_slab_pipeline_matches_reference(tmp_path, world, case, layout):
     """layout 0: the reference's block ky slabs; 1: cyclic ky ownership (balanced under dealiasing)."""
     import sys
