@@ -187,15 +187,51 @@ class TimeStepBase(object):
         self.iteration += 1
 
     @timer
+    def __getstate__(self):
+        """Pickled into every snapshot (time_step.py:133-138): the integrating-factor coefficients are a ctypes
+        array at run time and travel as a plain list."""
+        state = dict(self.__dict__)
+        co = state.get("_coeff")
+        if co is not None:
+            state["_coeff"] = ("coeff", list(co[0]), int(co[1]))
+        return state
+
+    def __setstate__(self, state):
+        co = state.get("_coeff")
+        if isinstance(co, tuple) and co and co[0] == "coeff":
+            state["_coeff"] = ((C.c_double * len(co[1]))(*co[1]), co[2])
+        self.__dict__.update(state)
+
     def snapshot(self, data):
-        """Per-rank snapshot directory snap_%05i (time_step.py:112-151): HDF5 when h5py is
-        importable (same /time, /fields/<name>/<comp> layout), otherwise one .npy per component."""
+        """Per-rank snapshot directory snap_%05i with the reference's contents (time_step.py:112-151): the source of
+        the forcing functions (forcing_functions.py), the pickled physics / state-layout / integrator objects
+        (dedalus_obj_%04i.cpkl; the field arrays are not in the pickle) and the fields.  Field file: HDF5 with the
+        reference's layout -- /time, attribute hg_version, /fields/<name>/<comp> with a 'space' attribute
+        (fields.py:118-125) -- when h5py is importable; otherwise one .npy per component plus fields.cpu%04i.json
+        naming the space each one was saved in.  dedalus.utils.restart.restart() reads both."""
+        import inspect
+        import json
         rank = com_sys.myproc
         path = "snap_%05i" % self._nsnap
         if rank == 0 and not os.path.exists(path):
             os.mkdir(path)
         if com_sys.comm:
             com_sys.comm.barrier()
+        source = ""
+        for k, forcer in self.RHS.forcing_functions.items():
+            if forcer:
+                try:
+                    source += inspect.getsource(forcer) + "\n"
+                except (OSError, TypeError):
+                    pass                    # defined interactively: the pickle keeps only its name
+                self.RHS._forcing_function_names[k] = forcer.__name__
+        if rank == 0:
+            with open(os.path.join(path, "forcing_functions.py"), "w") as f:
+                f.write(source)
+        with open(os.path.join(path, "dedalus_obj_%04i.cpkl" % rank), "wb") as f:
+            pickle.dump(self.RHS, f)
+            pickle.dump(data, f)
+            pickle.dump(self, f)
         try:
             import h5py
         except ImportError:
@@ -206,9 +242,14 @@ class TimeStepBase(object):
                 out.attrs["hg_version"] = hg_version
                 data.snapshot(out.create_group("/fields"))
         else:
-            np.save(os.path.join(path, "time.cpu%04i.npy" % rank), np.array(self.time))
+            index = {"time": float(self.time), "hg_version": hg_version, "fields": {}}
             for name, i, c in data.components():
-                np.save(os.path.join(path, "%s_%i_%s.cpu%04i.npy" % (name, i, c._curr_space, rank)), c.data.cpu().numpy())
+                fn = "%s_%i.cpu%04i.npy" % (name, i, rank)
+                buf = c._k if c._curr_space == "kspace" else c.xdata      # internal buffers: saving does not hand them out
+                np.save(os.path.join(path, fn), buf.cpu().numpy())
+                index["fields"]["%s/%i" % (name, i)] = {"file": fn, "space": c._curr_space}
+            with open(os.path.join(path, "fields.cpu%04i.json" % rank), "w") as f:
+                json.dump(index, f)
         self._nsnap += 1
         self._tlastsnap = self.time
 

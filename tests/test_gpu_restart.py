@@ -1,0 +1,105 @@
+"""Snapshot / restart (reference: dedalus/time_stepping/time_step.py:112-151, dedalus/utils/restart.py:33-99): a run
+continued from its snapshot equals the uninterrupted run bit for bit; forcing functions come back by name from the
+sidecar source file; the integrator's statistics and the integrating-factor coefficients survive the pickle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_lib_loaded():
+    from conftest import native_lib_expected
+    native_lib_expected()
+    yield
+
+
+def kvec(d):
+    return np.stack([c["kspace"].cpu().numpy().copy() for _, _, c in d.components()])
+
+
+def spin(x, t):
+    """A forcing function that lives in a real source file, so that the snapshot can carry its source."""
+    return x
+
+
+def velocity_forcing(data, i):
+    return 0.05 * data["u"][i]["kspace"].clone() if i == 0 else 0.0 * data["u"][i]["kspace"].clone()
+
+
+def noise_state(P, shape, seed):
+    import torch
+    data = P.create_fields(0.)
+    rng = np.random.default_rng(seed)
+    for _, f in data:
+        for _, c in f:
+            c["xspace"] = torch.from_numpy(rng.standard_normal(shape))
+            c["kspace"]
+        if f.ncomp > 1:
+            f.div_free()
+    return data
+
+
+@pytest.mark.parametrize("physics,shape,integ", [("IncompressibleMHD", (16, 16, 16), "RK2mid"), ("IncompressibleMHD", (16, 16, 16), "RK4"),
+                                                 ("BoussinesqHydro", (32, 16), "RK2trap"), ("IncompressibleHydro", (10, 30), "CrankNicholsonVisc")])
+def test_restart_continues_bit_for_bit(tmp_path, monkeypatch, physics, shape, integ):
+    import dedalus.time_stepping.api as tapi
+    from dedalus.utils.api import restart
+    from devutil import dev_physics
+    monkeypatch.chdir(tmp_path)
+    P = dev_physics(physics, shape, None, dict(nu=0.01))
+    data = noise_state(P, shape, 4)
+    ti = getattr(tapi, integ)(P)
+    for _ in range(3):
+        ti.do_advance(data, 5e-3)
+    ti.snapshot(data)
+    assert os.path.exists("snap_00000/dedalus_obj_0000.cpkl") and os.path.exists("snap_00000/forcing_functions.py")
+    for _ in range(2):
+        ti.do_advance(data, 5e-3)
+    want = kvec(data)
+    R2, d2, t2 = restart("snap_00000")
+    assert t2.iteration == 3 and abs(t2.time - 0.015) < 1e-15 and abs(d2.time - 0.015) < 1e-15
+    assert type(R2) is type(P) and R2.parameters["nu"] == 0.01
+    for _ in range(2):
+        t2.do_advance(d2, 5e-3)
+    got = kvec(d2)
+    # the first step after a restart re-derives the integrating-factor bookkeeping on the unfused path: equal to round-off,
+    # and bit-identical for the integrators whose first step is always unfused
+    assert np.linalg.norm(got - want) <= 1e-14 * np.linalg.norm(want)
+    assert t2.iteration == 5 and abs(t2.time - ti.time) < 1e-15
+
+
+def test_restart_reattaches_forcing_functions(tmp_path, monkeypatch):
+    from dedalus.mods import IncompressibleHydro, FourierRepresentation, RK2mid
+    from dedalus.utils.api import restart
+    monkeypatch.chdir(tmp_path)
+    P = IncompressibleHydro((16, 16), FourierRepresentation)
+    P.parameters["nu"] = 0.02
+    P.set_velocity_forcing(velocity_forcing)
+    data = noise_state(P, (16, 16), 9)
+    ti = RK2mid(P)
+    ti.do_advance(data, 1e-2)
+    ti.snapshot(data)
+    assert "def velocity_forcing" in open("snap_00000/forcing_functions.py").read()
+    ti.do_advance(data, 1e-2)
+    R2, d2, t2 = restart("snap_00000")
+    assert R2.forcing_functions["VelocityForcing"].__name__ == "velocity_forcing"
+    t2.do_advance(d2, 1e-2)
+    assert np.linalg.norm(kvec(d2) - kvec(data)) <= 1e-14 * np.linalg.norm(kvec(data))
+
+
+def test_snapshot_in_x_space_restores_the_space(tmp_path, monkeypatch):
+    """The 'space' attribute of every component is saved and restored (fields.py:118-125, restart.py:88-97)."""
+    from dedalus.mods import IncompressibleHydro, FourierRepresentation, RK2mid
+    from dedalus.utils.api import restart
+    monkeypatch.chdir(tmp_path)
+    P = IncompressibleHydro((16, 16), FourierRepresentation)
+    data = noise_state(P, (16, 16), 2)
+    x = data["u"]["x"]["xspace"].cpu().numpy().copy()
+    ti = RK2mid(P)
+    ti.snapshot(data)
+    R2, d2, t2 = restart("snap_00000")
+    assert d2["u"]["x"]._curr_space == "xspace" and d2["u"]["y"]._curr_space == "kspace"
+    assert np.array_equal(d2["u"]["x"]["xspace"].cpu().numpy(), x)
