@@ -67,7 +67,24 @@ def _points(item):
     return best
 
 
+# Order of the -m gpu run (the driver uses -x): what has already passed on a B200 first, then the files added after the
+# round's GPU budget was spent (verified through the host emulation and, for the kernels, by tests/native/devcheck.cu), so that
+# a device-only surprise in new code cannot hide the state of everything before it.
+_FILE_ORDER = ["test_gpu_parity", "test_gpu_slab", "test_native_abi", "test_gpu_widen", "test_mixed_radix", "test_gpu_restart",
+               "test_gpu_shear"]
+_NEW_GOLDENS = ("10x30", "50_rk2trap", "18x24", "48x2x48", "9x15x14", "12x20x24")
+
+
+def _order_key(item):
+    name = os.path.basename(str(item.fspath))[:-3]
+    rank = _FILE_ORDER.index(name) if name in _FILE_ORDER else -1
+    if name == "test_gpu_parity" and any(g in item.nodeid for g in _NEW_GOLDENS):
+        rank = _FILE_ORDER.index("test_mixed_radix")        # grids that are not powers of two: with their own file
+    return rank
+
+
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=_order_key)          # stable: the order inside a file is kept
     if not HOST_EMUL:
         return
     big = pytest.mark.skip(reason="host emulation: grid too large for one CPU thread")
