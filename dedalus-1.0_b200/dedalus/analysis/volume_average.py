@@ -117,6 +117,10 @@ class VolumeAverageSet(object):
             _shared.update(on=False, key=None, val=None)
         for (f, fmt, kwargs), val in zip(self.tasks, vals):
             if com_sys.myproc == 0:
+                if isinstance(val, complex):
+                    # the reference formats numpy complex scalars with '%e', which (in its numpy) casts to the
+                    # real part with a ComplexWarning (samples/boussinesq_hydro/gravity_wave: 'divergence')
+                    val = val.real
                 line.append(fmt % val)
         if com_sys.myproc == 0:
             self.outfile.write("\t".join(line) + "\n")
