@@ -20,7 +20,16 @@ def ok(self):
 
 ts.TimeStepBase.ok = property(ok)
 os.chdir(workdir)
-ns = runpy.run_path(script, run_name="__main__")
+src = open(script).read()
+try:
+    compile(src, script, "exec")
+    ns = runpy.run_path(script, run_name="__main__")
+except SyntaxError:
+    # a Python-2 script: the mechanical edits of oracle/build_ref.py (print statements, xrange, ...), in memory only
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import build_ref
+    ns = {"__name__": "__main__", "__file__": script}
+    exec(compile(build_ref.transliterate("sample", src), script, "exec"), ns)
 import numpy as np  # noqa: E402
 data, ti = ns["data"], ns["ti"]
 state = np.stack([c["kspace"].cpu().numpy() for _, _, c in data.components()])
