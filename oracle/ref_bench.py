@@ -10,7 +10,9 @@ RK4 does not run in the reference as shipped (time_step.py:209,214,449; SURVEY.m
 "RK4" timed here is the restated glue of SURVEY.md section 8(c) around the REFERENCE's
 RHS (physics.py) and the REFERENCE's Cython euler/etd1 kernels -- labelled "restated".
 The path is single-threaded by construction (numpy pocketfft; the reference has no threading);
-its MPI / FFTW-MPI mode cannot be reproduced in this image (no MPI, no FFTW).
+its MPI / FFTW-MPI mode cannot be reproduced in this image (no MPI, no FFTW).  `--threads T` is the
+best-effort use of the host's cores without touching the reference's code: its numpy.fft calls are served by
+scipy.fft with T workers (same pocketfft algorithm); everything else stays as it is.
 """
 import argparse
 import json
@@ -65,9 +67,27 @@ def restated_rk4(ts_mod, RHS):
     return RK4(RHS)
 
 
-def run(n, ndim, steps, warmup, physics="IncompressibleMHD", integ="RK4"):
+class _ThreadedFFT(object):
+    """numpy.fft's interface on scipy.fft with `workers` threads: the one part of the reference's numpy route
+    (representations.py:327-333) that can use more than one core without touching its code."""
+
+    def __init__(self, workers):
+        import scipy.fft as sfft
+        self._s, self._w = sfft, workers
+
+    def __getattr__(self, name):
+        f = getattr(self._s, name)
+        if name in ("fftfreq", "rfftfreq", "fftshift", "ifftshift"):
+            return f
+        return lambda *a, **kw: f(*a, workers=self._w, **kw)
+
+
+def run(n, ndim, steps, warmup, physics="IncompressibleMHD", integ="RK4", threads=1):
     decfg, data_api, physics_api, ts = build_ref.import_ref()
     from dedalus.data_objects.api import FourierRepresentation
+    import dedalus.data_objects.representations as rep_mod
+    if threads > 1:
+        rep_mod.npfft = _ThreadedFFT(threads)
     shape = (n,) * ndim
     RHS = getattr(physics_api, physics)(shape, FourierRepresentation)
     RHS.parameters['nu'] = 1e-3
@@ -98,7 +118,7 @@ def run(n, ndim, steps, warmup, physics="IncompressibleMHD", integ="RK4"):
     sec = time.perf_counter() - t0
     nk = (n // 2 + 1) * n ** (ndim - 1)
     assert np.isfinite(data['u'][0]['kspace']).all()
-    return dict(value=steps * nstage * nk / sec, ms_per_step=1e3 * sec / steps, n=n, ndim=ndim, steps=steps,
+    return dict(value=steps * nstage * nk / sec, ms_per_step=1e3 * sec / steps, n=n, ndim=ndim, steps=steps, threads=threads,
                 warmup=warmup, nk=nk, integrator=integ + (" (restated)" if integ == "RK4" else ""), physics=physics)
 
 
@@ -108,5 +128,6 @@ if __name__ == "__main__":
     ap.add_argument("--ndim", type=int, default=3)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--threads", type=int, default=1, help="FFT worker threads (scipy.fft behind the reference's numpy.fft calls)")
     a = ap.parse_args()
-    print(json.dumps(run(a.n, a.ndim, a.steps, a.warmup)))
+    print(json.dumps(run(a.n, a.ndim, a.steps, a.warmup, threads=a.threads)))

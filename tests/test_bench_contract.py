@@ -21,7 +21,9 @@ def test_reference_arm_prints_the_contract_line():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
-    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] in (1, cb["threaded_fft_workers"]) and cb["host_cores"] >= cb["cores"]
+    assert cb["single_thread_value"] > 0 and cb["threaded_fft_value"] > 0 and cb["value"] == max(cb["single_thread_value"], cb["threaded_fft_value"])
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
 
