@@ -127,6 +127,7 @@ static int pencil_threads(int N) {
 DDL_DECLX(8) DDL_DECLX(16) DDL_DECLX(32) DDL_DECLX(64) DDL_DECLX(128) DDL_DECLX(256) DDL_DECLX(512) DDL_DECLX(1024)
 DDL_DECLX(2048)
 static int g_xfused_variant = 0;
+static int g_plane_chunk = 0;     // ddl_set_option("rhs_plane_chunk", n): see rhs_impl
 static int run_xfused(int N, int phys, const XFusedParams& p, int n_outer, ddl_stream_t s) {
     switch (N) {
 #define DDL_CASEX(N) case N: return run_xfused_##N(phys, p, n_outer, g_xfused_variant, s);
@@ -618,6 +619,23 @@ static int phase_yinv(ddl_plan* pl, int nf, const void* const* A, void* const* B
     return pass_c2c("y_inv", Y.n, +1, nf, A, B, side(nzl * CX, 1, CX, pl->ypos, nullptr), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
                     RowSpec{Y.m, pl->layout ? 2 : 1}, ALL_ROWS, X.cnt, (int)nzl, 1.0, Y.tw, st);
 }
+// the same two passes for local planes [z0, z0 + nzc) with CHUNK-LOCAL b / c arrays Bc, Cc[nzc][y][CX] (rhs_plane_chunk)
+static int phase_yinv_planes(ddl_plan* pl, int nf, const void* const* A, void* const* Bc, int z0, int nzc, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long CX = kx_pitch(pl), nzl = pl->nzl;
+    std::vector<const void*> a(nf);
+    for (int f = 0; f < nf; ++f) a[f] = (const cplx*)A[f] + (long long)z0 * CX;
+    return pass_c2c("y_inv", Y.n, +1, nf, a.data(), Bc, side(nzl * CX, 1, CX, pl->ypos, nullptr), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr),
+                    RowSpec{Y.m, pl->layout ? 2 : 1}, ALL_ROWS, X.cnt, nzc, 1.0, Y.tw, st);
+}
+static int phase_yfwd_planes(ddl_plan* pl, int nf, const void* const* Cc, void* const* D, int z0, int nzc, ddl_stream_t st) {
+    const Axis &X = pl->ax, &Y = pl->ay;
+    const long long CX = kx_pitch(pl), nzl = pl->nzl;
+    std::vector<void*> d(nf);
+    for (int f = 0; f < nf; ++f) d[f] = (cplx*)D[f] + (long long)z0 * CX;
+    return pass_c2c("y_fwd", Y.n, -1, nf, Cc, d.data(), side(CX, 1, (long long)Y.n * CX, nullptr, nullptr), side(nzl * CX, 1, CX, pl->ypos, nullptr),
+                    ALL_ROWS, RowSpec{Y.m, pl->layout ? 2 : 1}, X.cnt, nzc, 1.0, Y.tw, st);
+}
 // y pass, forward: C[nzl][y][CX] -> x-side pencils D[cy][nzl][CX]
 static int phase_yfwd(ddl_plan* pl, int nf, const void* const* Cin, void* const* D, ddl_stream_t st) {
     const Axis &X = pl->ax, &Y = pl->ay;
@@ -928,11 +946,28 @@ static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void*
         for (int f = 0; f < ni; ++f) { A[f] = r0 + f * s.ks; B[f] = r1 + f * s.b; }
         for (int f = 0; f < no; ++f) { C[f] = r2 + f * s.b; D[f] = r0 + f * s.ks; E[f] = r1 + f * s.e; }
         DDL_TRY(phase_zinv(pl, ni, (const void* const*)state, A.data(), st));
-        DDL_TRY(phase_yinv(pl, ni, A.data(), B.data(), st));
-        DDL_TRY(phase_xfused(pl, code, ni, no, B.data(), C.data(), pc, st));
-        if (front_only) return 0;
-        DDL_TRY(phase_yfwd(pl, no, C.data(), D.data(), st));
-        DDL_TRY(phase_zfwd(pl, no, D.data(), E.data(), false, st));
+        // Opt-in experiment (ddl_set_option("rhs_plane_chunk", n), default off, NOT YET TIMED): y_inv -> x -> y_fwd over chunks of n
+        // z-planes with chunk-sized b / c arrays that every chunk reuses, so that the half-transformed lines (22 of the 52 GB a
+        // 512^3 MHD stage moves) can live in the 126 MB L2 instead of crossing HBM twice.  15 fields x 1.44 MB per plane: n <= 4.
+        const long long cb = (long long)g_plane_chunk * Y.n * kx_pitch(pl);
+        if (g_plane_chunk > 0 && !front_only && (long long)(ni + no) * cb <= w.r1 && (long long)no * s.xs <= w.r2) {
+            std::vector<void*> Bc(ni), Cc(no);
+            for (int f = 0; f < ni; ++f) Bc[f] = r1 + f * cb;
+            for (int f = 0; f < no; ++f) { Cc[f] = r1 + (ni + f) * cb; D[f] = r2 + f * s.xs; }
+            for (int z0 = 0; z0 < pl->nzl; z0 += g_plane_chunk) {
+                const int nzc = pl->nzl - z0 < g_plane_chunk ? pl->nzl - z0 : g_plane_chunk;
+                DDL_TRY(phase_yinv_planes(pl, ni, A.data(), Bc.data(), z0, nzc, st));
+                DDL_TRY(phase_xfused(pl, code, ni, no, Bc.data(), Cc.data(), pc, st, 0, nzc));
+                DDL_TRY(phase_yfwd_planes(pl, no, Cc.data(), D.data(), z0, nzc, st));
+            }
+            DDL_TRY(phase_zfwd(pl, no, D.data(), E.data(), false, st));
+        } else {
+            DDL_TRY(phase_yinv(pl, ni, A.data(), B.data(), st));
+            DDL_TRY(phase_xfused(pl, code, ni, no, B.data(), C.data(), pc, st));
+            if (front_only) return 0;
+            DDL_TRY(phase_yfwd(pl, no, C.data(), D.data(), st));
+            DDL_TRY(phase_zfwd(pl, no, D.data(), E.data(), false, st));
+        }
     } else {
         const double sc = 1.0 / (double)pl->ntot;
         DDL_TRY(inverse_head_2d(pl, ni, (const void* const*)state, r0, A.data(), st));
@@ -1208,6 +1243,7 @@ extern "C" int ddl_set_shear(ddl_plan* pl, int enable, double shear_rate, double
 extern "C" int ddl_set_option(const char* name, int value) {
     if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
     if (name && !strcmp(name, "xfused_variant")) { g_xfused_variant = value; return 0; }
+    if (name && !strcmp(name, "rhs_plane_chunk")) { g_plane_chunk = value < 0 ? 0 : value; return 0; }
     set_error("unknown option %s", name ? name : "(null)");
     return -1;
 }

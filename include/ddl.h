@@ -282,7 +282,9 @@ int ddl_profile_enable(int on);
 int ddl_profile_report(char* json_out, size_t nbytes);
 
 /* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both);
- * "xfused_variant" = 0/1/2 picks the CTA shape of the fused x pass (csrc/xfused_kernel.cuh) */
+ * "xfused_variant" = 0/1/2/3 picks the variant of the fused x pass (csrc/xfused_kernel.cuh);
+ * "rhs_plane_chunk" = n > 0 runs y_inv -> x -> y_fwd of the one-rank 3-D RHS over chunks of n z-planes with chunk-sized,
+ *   reused half-transformed arrays (an L2-residency experiment, default 0 = off) */
 int ddl_set_option(const char* name, int value);
 
 int ddl_sync(void* stream);

@@ -283,6 +283,15 @@ static void check(int n) {
         }
     }
     ddl_set_option("xfused_variant", g_variant);
+    for (int chunk : {1, 3}) {
+        ddl_set_option("rhs_plane_chunk", chunk);
+        for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
+        DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
+        dsync();
+        char label[96]; snprintf(label, sizeof label, "rhs_plane_chunk %d vs generic tile kernels (rel L2)", chunk);
+        verdict(label, max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
+    }
+    ddl_set_option("rhs_plane_chunk", 0);
 }
 
 // one RK4 step the way the Python integrator issues it once the state is dealiased (time_step.py RK4._advance_fused):
@@ -316,6 +325,19 @@ static void timing(int n, int reps) {
         say("  ddl_rhs, x-pass variant %d: %.3f ms\n", v, best);
     }
     ddl_set_option("xfused_variant", g_variant);
+    // opt-in L2-residency experiment: y_inv -> x -> y_fwd over chunks of z-planes (include/ddl.h "rhs_plane_chunk")
+    for (int chunk : {1, 2, 4, 8}) {
+        ddl_set_option("rhs_plane_chunk", chunk);
+        double best = 1e30;
+        for (int r = 0; r <= reps; ++r) {
+            t.start();
+            DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
+            const double ms = t.stop_ms();
+            if (r > 0 && ms < best) best = ms;
+        }
+        say("  ddl_rhs, rhs_plane_chunk %d: %.3f ms\n", chunk, best);
+    }
+    ddl_set_option("rhs_plane_chunk", 0);
     for (int mode = 0; mode < 3; ++mode) {
         double best = 1e30;
         for (int r = 0; r <= reps; ++r) {

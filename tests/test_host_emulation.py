@@ -213,3 +213,26 @@ def test_emulated_advective_policies_match_reference_form_for_compressive_states
     assert rel(dk, k.kvector()) < 1e-14
     dk0, _ = pl.rhs(physics, params, y, adv=False)
     assert rel(dk0, k.kvector()) > 0.1
+
+
+@pytest.mark.parametrize("physics,shape,cfg", [("IncompressibleMHD", (16, 16, 16), 5), ("BoussinesqHydro", (8, 16, 32), 4),
+                                               ("IncompressibleHydro", (12, 20, 24), 3)])
+def test_emulated_plane_chunked_rhs_equals_the_default(lib, physics, shape, cfg):
+    """ddl_set_option("rhs_plane_chunk", n): the same RHS with y_inv -> x -> y_fwd over chunks of n z-planes and reused
+    chunk-sized arrays (an opt-in L2-residency experiment); chunk sizes that do and do not divide nz."""
+    kw = {"direction": "z"} if physics == "BoussinesqHydro" else {}
+    Po = orc.PHYSICS[physics](shape, None, "2/3 cython", **kw)
+    Po.parameters.update(dict(nu=1e-3))
+    y0 = orc.synthetic_ic(Po, cfg).kvector()
+    pl = emul.EmulPlan(lib, orc.Grid(shape))
+    params = dict(Po.parameters)
+    if kw:
+        params["boussinesq_direction"] = "z"
+    ref, _ = pl.rhs(physics, params, list(y0))
+    try:
+        for n in (1, 3, shape[0]):
+            assert lib.ddl_set_option(b"rhs_plane_chunk", n) == 0
+            d, _ = pl.rhs(physics, params, list(y0))
+            assert np.array_equal(d, ref), n
+    finally:
+        lib.ddl_set_option(b"rhs_plane_chunk", 0)
