@@ -63,8 +63,7 @@ def load_all_data(data, location):
             except (KeyError, OSError):
                 raise KeyError("Data File field %s component %i is missing or corrupt" % (name, i))
             c[entry["space"]] = torch.from_numpy(arr)
-        data.set_time(meta["time"])
-        return
+        return                      # data.time travels in the pickle (the file's /time is the integrator's clock)
     import h5py
     with h5py.File(h5, mode="r") as f:
         for name, i, c in data.components():
@@ -77,4 +76,3 @@ def load_all_data(data, location):
             if isinstance(space, bytes):
                 space = space.decode()
             c[space] = torch.from_numpy(np.asarray(dset[...]))
-        data.set_time(float(np.asarray(f["time"])))

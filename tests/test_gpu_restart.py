@@ -103,3 +103,31 @@ def test_snapshot_in_x_space_restores_the_space(tmp_path, monkeypatch):
     R2, d2, t2 = restart("snap_00000")
     assert d2["u"]["x"]._curr_space == "xspace" and d2["u"]["y"]._curr_space == "kspace"
     assert np.array_equal(d2["u"]["x"]["xspace"].cpu().numpy(), x)
+
+
+def test_restart_in_a_shearing_box(tmp_path, monkeypatch):
+    """The drifting wavenumbers are rebuilt from the restored time (state_data.py:115-121 on load)."""
+    import torch
+    from dedalus.mods import IncompressibleHydro, FourierShearRepresentation, RK2mid
+    from dedalus.utils.api import restart
+    monkeypatch.chdir(tmp_path)
+    P = IncompressibleHydro((16, 32), FourierShearRepresentation)
+    P.parameters.update(dict(nu=0.01, shear_rate=1.5))
+    data = P.create_fields(0.4)
+    rng = np.random.default_rng(6)
+    for _, c in data["u"]:
+        c["xspace"] = torch.from_numpy(rng.standard_normal((16, 32)))
+        c["kspace"]
+    data["u"].div_free()
+    ti = RK2mid(P)
+    for _ in range(2):
+        ti.do_advance(data, 1e-2)
+    ti.snapshot(data)
+    for _ in range(2):
+        ti.do_advance(data, 1e-2)
+    R2, d2, t2 = restart("snap_00000")
+    assert abs(d2.time - 0.42) < 1e-14 and not d2["u"][0]._static_k
+    for _ in range(2):
+        t2.do_advance(d2, 1e-2)
+    assert np.array_equal(d2["u"][0].k["y"].cpu().numpy(), data["u"][0].k["y"].cpu().numpy())
+    assert np.linalg.norm(kvec(d2) - kvec(data)) <= 1e-14 * np.linalg.norm(kvec(data))
