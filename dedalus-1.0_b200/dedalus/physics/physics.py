@@ -226,7 +226,12 @@ class Physics(object):
         """True for representations whose wavenumbers depend on time (FourierShearRepresentation): the fused
         pipeline's index tables are static, so the right-hand side is evaluated the reference's way, helper by
         helper (a compatibility path), and the integrators update with tensor operations."""
-        return not self._representation._static_k
+        if not self._representation._static_k:
+            return True
+        # without 2/3 dealiasing the reference's x-space products are ALIASED and its advective forms are what they are:
+        # the fused pipeline (conservative products, transforms pruned to the retained modes) has no equivalent, the
+        # helper sequence reproduces it exactly (FFT.dealiasing = None zeroes the Nyquist planes only, :442-455)
+        return decfg.get("FFT", "dealiasing") not in ("2/3", "2/3 cython")
 
     # ------------------------------------------------------------------ solenoidal or not
     SOLENOIDAL_TOL = 1e-12      # compressive fraction sqrt(sum |k.u|^2 / sum |k|^2 |u|^2) below which u counts as div-free

@@ -72,6 +72,11 @@ CASES = [
          params=dict(nu=0.02, eta=0.01, rho0=1.7), integ="RK2trap", dt=2e-3, nsteps=2, ic="synthetic", cfg=5),
     dict(name="hydro3d_12x20x24_rk2mid", physics="IncompressibleHydro", shape=(12, 20, 24), length=None,
          params=dict(nu=0.01), integ="RK2mid", dt=1e-2, nsteps=2, ic="synthetic", cfg=3),
+    # FFT.dealiasing = None (Nyquist planes zeroed only, aliased products): more physics classes, 2-D, a grid that is not a power of two
+    dict(name="mhd3d_16_rk2trap_nodealias", physics="IncompressibleMHD", shape=(16, 16, 16), length=None,
+         params=dict(nu=0.01, eta=0.02), integ="RK2trap", dt=5e-3, nsteps=2, ic="synthetic", cfg=5, dealiasing="None"),
+    dict(name="bouss2d_12x20_rk2mid_nodealias", physics="BoussinesqHydro", shape=(12, 20), length=None,
+         params=dict(nu=0.01, kappa=0.02), integ="RK2mid", dt=5e-3, nsteps=2, ic="synthetic", cfg=4, dealiasing="None"),
     dict(name="hydro2d_16_rk2mid_visc2", physics="IncompressibleHydro", shape=(16, 16), length=None,
          params=dict(nu=1e-3, viscosity_order=2), integ="RK2mid", dt=1e-2, nsteps=3, ic="synthetic", cfg=1),
 ]
