@@ -66,7 +66,9 @@ def keep_masks(dealiasing, ktrans, kny, k):
         elif dealiasing in ("None", None, 0):
             keep[name] = ~(np.abs(kv) == kn)
         elif dealiasing == "2/3 spherical":
-            raise NotImplementedError("'2/3 spherical' dealiasing is not implemented in the CUDA backend.")
+            # representations.py:410-417: zero where |k| >= 2/3 min(kny).  The plan prunes to the cube that bounds this
+            # sphere; the representation applies the sphere itself (FourierRepresentation._sphere)
+            keep[name] = ~(np.abs(kv) >= 2.0 / 3.0 * np.min(kny))
         else:
             raise NotImplementedError("Specified dealiasing method not implemented.")
     return keep

@@ -86,6 +86,10 @@ class FourierRepresentation(Representation):
         self.integrating_factor = None
         self.fwd_count = 0
         self.rev_count = 0
+        self._sphere = None
+        if dealiasing == "2/3 spherical":
+            # '2/3 spherical' (representations.py:410-417): the library masks the bounding cube, this mask the rest
+            self._sphere = (torch.sqrt(self.k2()) >= 2.0 / 3.0 * float(np.min(self.kny))).expand(self._k.shape)
 
     # ------------------------------------------------------------------ storage
     @property
@@ -160,6 +164,8 @@ class FourierRepresentation(Representation):
             w = pl.transform_workspace()
             check(lib.ddl_forward(pl.handle, self.xdata.data_ptr(), self._k.data_ptr(), w.data_ptr(), w.numel(),
                                   _plan.current_stream()))
+        if self._sphere is not None:
+            self._k.masked_fill_(self._sphere, 0.0)
         self._curr_space = "kspace"
         self._clean = True
         self._sym = True
@@ -172,6 +178,8 @@ class FourierRepresentation(Representation):
         if self._curr_space == "xspace":
             raise ValueError("Backward transform cannot be called from xspace.")
         pl = self._plan
+        if self._sphere is not None:
+            self._k.masked_fill_(self._sphere, 0.0)
         if pl.nranks > 1:
             pl.pipeline.backward(self._k, self.xdata)
         else:
@@ -191,6 +199,8 @@ class FourierRepresentation(Representation):
         n = self.global_shape["xspace"]
         if dealiasing in ("2/3", "2/3 cython"):
             self.nmodes = np.prod(2 * np.ceil(n / 3.0 - 1) + 1)
+        elif dealiasing == "2/3 spherical":
+            self.nmodes = None
         elif dealiasing in ("None", None, 0):
             self.nmodes = np.prod(2 * np.ceil(n / 2.0 - 1) + 1)
         else:
@@ -201,8 +211,11 @@ class FourierRepresentation(Representation):
         """Zero the modes outside the plan's mask, in place (dealias_cy_{2,3}d.pyx)."""
         self.require_space("kspace")
         check(lib.ddl_dealias(self._plan.handle, self._k.data_ptr(), _plan.current_stream()))
+        if self._sphere is not None:
+            self._k.masked_fill_(self._sphere, 0.0)
         self._clean = True
 
+    dealias_23_spherical = dealias
     dealias_23 = dealias
     dealias_23_cython = dealias
 

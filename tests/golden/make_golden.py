@@ -77,6 +77,11 @@ CASES = [
          params=dict(nu=0.01, eta=0.02), integ="RK2trap", dt=5e-3, nsteps=2, ic="synthetic", cfg=5, dealiasing="None"),
     dict(name="bouss2d_12x20_rk2mid_nodealias", physics="BoussinesqHydro", shape=(12, 20), length=None,
          params=dict(nu=0.01, kappa=0.02), integ="RK2mid", dt=5e-3, nsteps=2, ic="synthetic", cfg=4, dealiasing="None"),
+    # FFT.dealiasing = '2/3 spherical' (representations.py:410-417), a box that is not cubic so that min(kny) matters
+    dict(name="mhd3d_16_rk2mid_nodealias_spherical", physics="IncompressibleMHD", shape=(16, 16, 16), length=(2 * np.pi, 3.0, 2 * np.pi),
+         params=dict(nu=0.01, eta=0.02), integ="RK2mid", dt=5e-3, nsteps=2, ic="synthetic", cfg=5, dealiasing="2/3 spherical"),
+    dict(name="hydro2d_24x16_rk2trap_nodealias_spherical", physics="IncompressibleHydro", shape=(24, 16), length=None,
+         params=dict(nu=0.01), integ="RK2trap", dt=5e-3, nsteps=2, ic="synthetic", cfg=1, dealiasing="2/3 spherical"),
     dict(name="hydro2d_16_rk2mid_visc2", physics="IncompressibleHydro", shape=(16, 16), length=None,
          params=dict(nu=1e-3, viscosity_order=2), integ="RK2mid", dt=1e-2, nsteps=3, ic="synthetic", cfg=1),
 ]
