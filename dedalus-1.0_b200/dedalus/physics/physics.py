@@ -222,6 +222,11 @@ class Physics(object):
             self.aux_fields.set_time(data.time)
 
     @property
+    def _dynamic_k(self):
+        """Wavenumbers that move with time (shearing box): the stage kernels' static tables do not apply either."""
+        return not self._representation._static_k
+
+    @property
     def _unfused(self):
         """True for representations whose wavenumbers depend on time (FourierShearRepresentation): the fused
         pipeline's index tables are static, so the right-hand side is evaluated the reference's way, helper by

@@ -365,7 +365,7 @@ class TimeStepBase(object):
         _mark(out, False)
 
     def _stage(self, kind, start, out, d1, d2, if_from, dt):
-        if getattr(self.RHS, "_unfused", False):
+        if getattr(self.RHS, "_dynamic_k", False):
             return self._stage_tensor(kind, start, out, d1, d2, if_from, dt)
         s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
         b = _kspace_tensors(d2) if d2 is not None else None
@@ -505,7 +505,7 @@ class RK4(RKBase):
 
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
-        if getattr(R, "_unfused", False):
+        if getattr(R, "_dynamic_k", False):
             raise NotImplementedError("RK4 in a shearing box: use RK2mid / RK2trap (the reference's RK4 does not run, SURVEY F1-F3)")
         _settle(data, self.RHS)
         lazy = dt is None
@@ -565,7 +565,7 @@ class CrankNicholsonVisc(TimeStepBase):
         self._coeff = None
 
     def do_advance(self, data, dt):
-        if getattr(self.RHS, "_unfused", False):
+        if getattr(self.RHS, "_dynamic_k", False):
             raise NotImplementedError("CrankNicholsonVisc in a shearing box: use RK2mid / RK2trap")
         _settle(data, self.RHS)
         lazy = dt is None
