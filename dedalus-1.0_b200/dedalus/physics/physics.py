@@ -430,10 +430,16 @@ class Physics(object):
             output[0]["kspace"] = X[0].deriv(t[1])
             output[1]["kspace"] = -X[0].deriv(t[0])
 
+    # physics.py:412-413 caches k^2 at the FIRST laplace_solve and keeps it -- also in a shearing box, where the wavenumbers
+    # drift, so that the reference's pressure solve divides by the k^2 of that first time level (the swinging-wave sample then
+    # departs from Lithwick's analytic solution, tests/test_gpu_known_answers.py).  True reproduces the reference (the
+    # default: drop-in parity); False re-evaluates k^2 at every solve.
+    cache_k2 = True
+
     @timer
     def laplace_solve(self, X, output):
         """Solve laplace(output) = X (physics.py:407-416)."""
-        if self.k2 is None:
+        if self.k2 is None or not self.cache_k2:
             self.k2 = output.k2(no_zero=True)
         output["kspace"] = -X["kspace"] / self.k2
 
