@@ -1158,6 +1158,20 @@ extern "C" int ddl_reduce_invariants(ddl_plan* pl, int physics, void* const* sta
 }
 
 // ---------------------------------------------------------------- stage updates
+extern "C" int ddl_step_array(int kind, int ndim, long long count, const void* start, void* out, const void* deriv1, const void* deriv2,
+                              const double* intfactor, double dt, void* stream) {
+    if (kind < DDL_EULER || kind > DDL_ETD2RK2) { set_error("ddl_step_array: kind %d is not euler / etd1 / etd2rk1 / etd2rk2", kind); return -1; }
+    if (ndim != 2 && ndim != 3) { set_error("Must use either 2 or 3 dimensions."); return -1; }
+    if (!start || !out || !deriv1 || ((kind == DDL_ETD2RK1 || kind == DDL_ETD2RK2) && !deriv2)) {
+        set_error("ddl_step_array: NULL array"); return -1;
+    }
+    if (count <= 0) return 0;
+    StageArrayF f;
+    f.start = (const cplx*)start; f.out = (cplx*)out; f.d1 = (const cplx*)deriv1; f.d2 = (const cplx*)deriv2;
+    f.intfactor = intfactor; f.kind = kind; f.twod = ndim == 2; f.dt = dt;
+    return launch_items(f, count, (ddl_stream_t)stream, "stage_array");
+}
+
 static int fill_stage(ddl_plan* pl, StageArgs& a, int ncomp, const double* coeff, int vo, int flags, long long& count) {
     if (ncomp < 1 || ncomp > DDL_MAXC) { set_error("ncomp %d out of range 1..%d", ncomp, DDL_MAXC); return -1; }
     memset(&a, 0, sizeof(a));

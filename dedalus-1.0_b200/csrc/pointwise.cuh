@@ -166,6 +166,28 @@ struct StageF {
     }
 };
 
+// euler / etd1 / etd2rk1 / etd2rk2 with the integrating factor as an ARRAY: the literal signature of the reference's Cython
+// kernels (forward_step_cy_3d.pyx:17-124, _2d:21-120: start, output, deriv1[, deriv2], intfactor, dt; Z = intfactor * dt),
+// for callers whose factor is not c (k^2)^n of static wavenumbers (shearing box) or who bind the kernels one to one
+struct StageArrayF {
+    const cplx* start;
+    cplx* out;
+    const cplx* d1;
+    const cplx* d2;
+    const double* intfactor;    // NULL: Euler forms (the reference's `integrating_factor is None` branches)
+    int kind, twod;
+    double dt;
+    DDL_HD void operator()(long long i) const {
+        double Z = 0.0, f0 = 1.0, f1 = 1.0, f2 = 0.5;
+        if (intfactor && kind != SK_EULER) {
+            Z = intfactor[i] * dt;
+            if (Z != 0.0) phi_funcs(Z, twod, f0, f1, f2);
+        }
+        const bool two = (kind == SK_ETD2RK1 || kind == SK_ETD2RK2);
+        out[i] = stage_apply(kind, start[i], d1[i], two ? d2[i] : mk(0.0, 0.0), nullptr, 0, 0, 1.0, Z, f0, f1, f2, dt, 0.0);
+    }
+};
+
 // zero the masked-out modes of up to DDL_MAXF arrays, touching only those entries
 struct MaskF {
     KGeom g;

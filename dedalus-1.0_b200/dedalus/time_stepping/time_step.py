@@ -343,25 +343,17 @@ class TimeStepBase(object):
     # ---- device stage launches ---------------------------------------------------------
     def _stage_tensor(self, kind, start, out, d1, d2, if_from, dt):
         """The same updates with the integrating factor as an ARRAY (shearing box: k^2 moves with time), component by
-        component like the reference's loops (time_step.py:285-304): Euler where the factor is None."""
-        from . import etd_tensor as E
+        component like the reference's loops (time_step.py:285-304,372-386): one launch of the array-factor kernel per
+        component (include/ddl.h: ddl_step_array), Euler forms where the factor is None."""
         s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
         b = _kspace_tensors(d2) if d2 is not None else [None] * len(s)
+        ndim = s[0].dim()
         for j, (_, _, c) in enumerate(if_from.components()):
             IF = c.integrating_factor
-            if IF is None:
-                if kind == _lib.ETD1:
-                    E.euler(s[j], o[j], a[j], dt)
-                elif kind == _lib.ETD2RK2:
-                    E.euler(s[j], o[j], b[j], dt)
-                else:                                       # ETD2RK1 (time_step.py:383-386)
-                    E.euler(s[j], o[j], b[j] - a[j], dt / 2.)
-            elif kind == _lib.ETD1:
-                E.etd1(s[j], o[j], a[j], -IF.tensor(), dt)
-            elif kind == _lib.ETD2RK2:
-                E.etd2rk2(s[j], o[j], a[j], b[j], -IF.tensor(), dt)
-            else:
-                E.etd2rk1(s[j], o[j], a[j], b[j], -IF.tensor(), dt)
+            neg = None if IF is None else (-IF.tensor()).contiguous()
+            check(lib.ddl_step_array(kind, ndim, s[j].numel(), s[j].data_ptr(), o[j].data_ptr(), a[j].data_ptr(),
+                                     b[j].data_ptr() if b[j] is not None else None, neg.data_ptr() if neg is not None else None,
+                                     float(dt), _plan.current_stream()))
         _mark(out, False)
 
     def _stage(self, kind, start, out, d1, d2, if_from, dt):

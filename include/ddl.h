@@ -191,6 +191,14 @@ int ddl_stage(ddl_plan* plan, int kind, int ncomp, void* const* start, void* con
               void* const* deriv1, void* const* deriv2, const double* coeff, int visc_order,
               double dt, int flags, void* stream);
 
+/* The same four kernels with the reference's own signature (forward_step_cy_3d.pyx:17-21,34-38,63-68,95-100; _2d: f0 from
+ * the series in the small-|Z| branch, :55): complex arrays of `count` elements and the integrating factor as a real ARRAY
+ * (Z = intfactor[i] * dt; callers pass -IF, time_step.py:289,301).  intfactor NULL = the Euler forms the reference takes
+ * where integrating_factor is None (time_step.py:285-304,372-386).  No plan: nothing but the arrays.  For factors that are
+ * not c (k^2)^n of static wavenumbers (shearing box), and for binding the Cython kernels one to one. */
+int ddl_step_array(int kind, int ndim, long long count, const void* start, void* out, const void* deriv1, const void* deriv2,
+                   const double* intfactor, double dt, void* stream);
+
 /* One stage of the restated RK4 (time_step.py:395-483 + forward_step :187-221):
  *   total = (first ? 0 : total) + k / wdiv ;  if (!last) out = S(y, k, dt_step)
  *   else out = S(y, total, dt_step),  S = euler / etd1(-IF)                              */

@@ -236,3 +236,32 @@ def test_emulated_plane_chunked_rhs_equals_the_default(lib, physics, shape, cfg)
             assert np.array_equal(d, ref), n
     finally:
         lib.ddl_set_option(b"rhs_plane_chunk", 0)
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_emulated_array_factor_kernels_match_reference_cython(lib, nd):
+    """ddl_step_array = euler / etd1 / etd2rk1 / etd2rk2 with the reference's own signature (integrating factor as an array)
+    against the DIRECT outputs of the reference's Cython kernels (tests/golden/stage_kernels.npz): Z == 0, |Z| < 0.5 and the
+    closed-form branch all occur, 2-D takes f0 from the series (forward_step_cy_2d.pyx:55)."""
+    import ctypes as C
+    z = np.load(os.path.join(GOLDEN, "stage_kernels.npz"))
+    p = "k%dd_" % nd
+    s, d1, d2, IF = (np.ascontiguousarray(z[p + n]) for n in ("start", "d1", "d2", "IF"))
+    dt = float(z[p + "dt"])
+    lib.ddl_step_array.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_double, C.c_void_p]
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for kind, name, two in ((0, "euler", False), (1, "etd1", False), (2, "etd2rk1", True), (3, "etd2rk2", True)):
+        o = np.full_like(s, np.nan)
+        rc = lib.ddl_step_array(kind, nd, s.size, ptr(s), ptr(o), ptr(d1), ptr(d2) if two else None, ptr(IF), dt, None)
+        assert rc == 0, lib.ddl_last_error()
+        assert rel(o, z[p + name]) < 1e-15, name
+    # no factor at all: the Euler forms of the integrators' `integrating_factor is None` branches
+    o = np.empty_like(s)
+    assert lib.ddl_step_array(1, nd, s.size, ptr(s), ptr(o), ptr(d1), None, None, dt, None) == 0
+    assert np.array_equal(o, s + dt * d1)
+    assert lib.ddl_step_array(3, nd, s.size, ptr(s), ptr(o), ptr(d1), ptr(d2), None, dt, None) == 0
+    assert np.array_equal(o, s + dt * d2)
+    assert lib.ddl_step_array(2, nd, s.size, ptr(s), ptr(o), ptr(d1), ptr(d2), None, dt, None) == 0
+    assert rel(o, s + dt / 2. * (d2 - d1)) < 1e-16
+    assert lib.ddl_step_array(7, nd, s.size, ptr(s), ptr(o), ptr(d1), None, None, dt, None) != 0
