@@ -759,6 +759,23 @@ extern "C" int ddl_dealias(ddl_plan* pl, void* k, void* stream) {
     return mask_arrays(pl, 1, arr, (ddl_stream_t)stream);
 }
 
+extern "C" int ddl_dealias_array(int ndim, const int64_t* kshape, void* data, const double* kx, const double* ky, const double* kz,
+                                 int ky_dense, const double* knyquist, void* stream) {
+    if (ndim != 2 && ndim != 3) { set_error("Must use either 2 or 3 dimensions."); return -1; }
+    if (!kshape || !data || !kx || !ky || !knyquist || (ndim == 3 && !kz)) { set_error("ddl_dealias_array: NULL argument"); return -1; }
+    DealiasArrayF f;
+    memset(&f, 0, sizeof(f));
+    f.data = (cplx*)data; f.kx = kx; f.ky = ky; f.kz = kz; f.ndim = ndim; f.ky_dense = ky_dense;
+    if (ndim == 3) {            // k-space axes (ky, kz, kx); knyquist in the same order (representations.py:208-211)
+        f.dim[0] = (int)kshape[0]; f.dim[1] = (int)kshape[1]; f.dim[2] = (int)kshape[2];
+        f.cut[0] = 2. / 3. * knyquist[2]; f.cut[1] = 2. / 3. * knyquist[0]; f.cut[2] = 2. / 3. * knyquist[1];
+    } else {                    // (kx, ky)
+        f.dim[0] = 1; f.dim[1] = (int)kshape[0]; f.dim[2] = (int)kshape[1];
+        f.cut[0] = 2. / 3. * knyquist[0]; f.cut[1] = 2. / 3. * knyquist[1];
+    }
+    return launch_items(f, (long long)f.dim[0] * f.dim[1] * f.dim[2], (ddl_stream_t)stream, "dealias_array");
+}
+
 extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t work_bytes, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
     DDL_TRY(need_one_rank(pl, "ddl_backward"));

@@ -188,6 +188,30 @@ struct StageArrayF {
     }
 };
 
+// dealias_23 with the reference's own signature (dealias_cy_2d.pyx:13-41, dealias_cy_3d.pyx:13-46): wavenumber VALUES per
+// axis, ky optionally dense over (kx, ky) / (ky, kx) -- the shearing box's second branch -- and the Nyquist values
+struct DealiasArrayF {
+    cplx* data;
+    const double* kx; const double* ky; const double* kz;
+    int ndim, ky_dense;
+    int dim[3];                 // 3-D: (ny, nz, nkx); 2-D: (1, nkx, ny)
+    double cut[3];              // 2/3 k_nyquist for x, y, z
+    DDL_HD static bool out(double k, double c) { return k >= c || k <= -c; }
+    DDL_HD void operator()(long long i) const {
+        int a, b, c;
+        split3(i, dim, a, b, c);
+        bool zero;
+        if (ndim == 3) {        // data[y][z][x]
+            const double kyv = ky_dense ? ky[(long long)a * dim[2] + c] : ky[a];
+            zero = out(kx[c], cut[0]) || out(kyv, cut[1]) || out(kz[b], cut[2]);
+        } else {                // data[x][y]
+            const double kyv = ky_dense ? ky[(long long)b * dim[2] + c] : ky[c];
+            zero = out(kx[b], cut[0]) || out(kyv, cut[1]);
+        }
+        if (zero) data[i] = mk(0.0, 0.0);
+    }
+};
+
 // zero the masked-out modes of up to DDL_MAXF arrays, touching only those entries
 struct MaskF {
     KGeom g;

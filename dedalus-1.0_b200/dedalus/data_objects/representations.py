@@ -399,11 +399,13 @@ class FourierShearRepresentation(FourierRepresentation):
         FourierRepresentation.__init__(self, sd, shape, length)
         self.k = dict(self._plan.k)                       # private copy: k['y'] is this component's own, time dependent
         self._ky = self.k["y"].clone()
-        self.k["y"] = self._ky * torch.ones_like(self.k["x"])
+        self.k["y"] = (self._ky * torch.ones_like(self.k["x"])).contiguous()
         S = float(self.sd.parameters["shear_rate"])
         self._shear_rate = S
         self._wave_rate = S * self.k["x"]
         self._dy = float(self.dx()[self.xtrans["y"]])
+        self._kshape64 = np.ascontiguousarray(self.local_shape["kspace"], dtype=np.int64)
+        self._kny64 = np.ascontiguousarray(self.kny, dtype=np.float64)
         self._update_k()
 
     def _update_k(self):
@@ -422,15 +424,18 @@ class FourierShearRepresentation(FourierRepresentation):
         """The configured rule with the sheared ky (dealias_cy_2d.pyx:36-41, dealias_cy_3d.pyx:38-46;
         zero_nyquist :442-455 for FFT.dealiasing = None)."""
         self.require_space("kspace")
-        mask = None
-        for name, kv in self.k.items():
-            kn = float(self.kny[self.ktrans[name]])
-            if self._dealiasing in ("2/3", "2/3 cython"):
-                m = (kv >= 2.0 / 3.0 * kn) | (kv <= -2.0 / 3.0 * kn)
-            else:
-                m = kv.abs() == kn
-            mask = m if mask is None else (mask | m)
-        self._k.masked_fill_(mask.expand_as(self._k), 0.0)
+        if self._dealiasing in ("2/3", "2/3 cython"):
+            # one launch of the kernel with the Cython kernels' own signature, dense-ky branch (include/ddl.h: ddl_dealias_array)
+            kz = self.k["z"] if self.ndim == 3 else None
+            check(lib.ddl_dealias_array(self.ndim, self._kshape64.ctypes.data_as(C.c_void_p), self._k.data_ptr(), self.k["x"].data_ptr(),
+                                        self.k["y"].data_ptr(), kz.data_ptr() if kz is not None else None, 1,
+                                        self._kny64.ctypes.data_as(C.c_void_p), _plan.current_stream()))
+        else:
+            mask = None
+            for name, kv in self.k.items():
+                m = kv.abs() == float(self.kny[self.ktrans[name]])
+                mask = m if mask is None else (mask | m)
+            self._k.masked_fill_(mask.expand_as(self._k), 0.0)
         self._clean = True
 
     dealias_23 = dealias

@@ -99,6 +99,12 @@ int ddl_forward(ddl_plan* plan, const double* x, void* k, void* work, size_t wor
 int ddl_backward(ddl_plan* plan, void* k, double* x, void* work, size_t work_bytes, void* stream);
 /* dealias_cy_{2,3}d.pyx dealias_23 / representations.py:442-455 zero_nyquist, in place */
 int ddl_dealias(ddl_plan* plan, void* k, void* stream);
+/* dealias_23 with the reference's own signature (dealias_cy_2d.pyx:13-41, dealias_cy_3d.pyx:13-46), no plan: the k-space
+ * array (shape kshape: (ky,kz,kx) or (kx,ky)), the wavenumber VALUES of every axis, the Nyquist values in k-space axis order, and
+ * ky either per row (ky_dense = 0) or dense over (ky, kx) / (kx, ky) (ky_dense = 1: the kernels' second branch, taken by the
+ * shearing box, whose ky drifts with kx and time).  Zero where any k >= 2/3 k_nyquist or k <= -2/3 k_nyquist. */
+int ddl_dealias_array(int ndim, const int64_t* kshape, void* data, const double* kx, const double* ky, const double* kz,
+                      int ky_dense, const double* knyquist, void* stream);
 /* representations.py:419-425 deriv(): out = i * k_axis * in   (axis: 0=x, 1=y, 2=z) */
 int ddl_deriv(ddl_plan* plan, const void* k_in, void* k_out, int axis, void* stream);
 

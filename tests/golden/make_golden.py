@@ -230,6 +230,44 @@ def transform_vectors():
     print("transforms.npz written")
 
 
+
+
+def dealias_kernel_vectors():
+    """Direct outputs of the reference's Cython dealias_23 (dealias_cy_2d.pyx, dealias_cy_3d.pyx), both branches: ky per row
+    and ky dense over (kx, ky) / (ky, 1, kx) as the shearing box passes it."""
+    import dealias_cy_2d as d2
+    import dealias_cy_3d as d3
+    rng = np.random.default_rng(23)
+    out = {}
+    # 2-D: data[x][y]
+    nkx, ny = 9, 12
+    kx = (np.arange(nkx, dtype=float) * 0.5).reshape(nkx, 1)
+    ky0 = (np.fft.fftfreq(ny) * ny * 1.5).reshape(1, ny)
+    kny = np.array([kx.max(), np.abs(ky0).max()])
+    data = rng.standard_normal((nkx, ny)) + 1j * rng.standard_normal((nkx, ny))
+    dense = np.ascontiguousarray(ky0 - 0.7 * kx * 1.3)
+    for tag, ky in (("row", ky0), ("dense", dense)):
+        o = data.copy()
+        d2.dealias_23(o, kx, np.ascontiguousarray(ky), kny)
+        out["d2_" + tag] = o
+    out.update(d2_data=data, d2_kx=kx, d2_ky=ky0, d2_kydense=dense, d2_kny=kny)
+    # 3-D: data[y][z][x]
+    ny, nz, nkx = 10, 6, 5
+    kx = np.arange(nkx, dtype=float).reshape(1, 1, nkx)
+    ky0 = (np.fft.fftfreq(ny) * ny).reshape(ny, 1, 1)
+    kz = (np.fft.fftfreq(nz) * nz * 2.0).reshape(1, nz, 1)
+    kny = np.array([np.abs(ky0).max(), np.abs(kz).max(), kx.max()])
+    data = rng.standard_normal((ny, nz, nkx)) + 1j * rng.standard_normal((ny, nz, nkx))
+    dense = np.ascontiguousarray(ky0 - 1.1 * kx * 0.9)
+    for tag, ky in (("row", ky0), ("dense", dense)):
+        o = data.copy()
+        d3.dealias_23(o, kx, np.ascontiguousarray(ky), kz, kny)
+        out["d3_" + tag] = o
+    out.update(d3_data=data, d3_kx=kx, d3_ky=ky0, d3_kydense=dense, d3_kz=kz, d3_kny=kny)
+    np.savez_compressed(os.path.join(HERE, "dealias_kernels.npz"), **out)
+    print("dealias_kernels.npz written")
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for c in CASES:
@@ -238,3 +276,5 @@ if __name__ == "__main__":
     if not only:
         stage_kernel_vectors()
         transform_vectors()
+    if not only or "dealias_kernels" in only:
+        dealias_kernel_vectors()
