@@ -6,6 +6,7 @@
 //   A  ddl_reduce_invariants (retained-only and full sweeps) vs a host loop over the downloaded state
 //   B  ddl_reduce_max_square / ddl_rhs_capture_max vs ddl_backward of every component + host max
 //   C  ddl_rhs: every x-pass variant and the generic tile kernels against each other
+//   D  ddl_step_array / ddl_dealias_array (the Cython kernels' own signatures) and the shearing-box transform (ddl_set_shear)
 //   T  (size argument >= 256) CUDA-event timings of the RHS per x-pass variant and of the reductions
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I include tests/native/devcheck.cu \
@@ -294,6 +295,116 @@ static void check(int n) {
     ddl_set_option("rhs_plane_chunk", 0);
 }
 
+// ---------------------------------------------------------------- D: the one-to-one kernels and the shearing-box phase hook
+static void h2d(void* d, const void* h, size_t bytes) {
+#ifndef DEVCHECK_EMUL
+    CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+#else
+    memcpy(d, h, bytes);
+#endif
+}
+
+static void check_seams(int n) {
+    say("D  kernels with the reference's own signatures, shearing-box transform (%d^3)\n", n);
+    const int nh = n / 2 + 1;
+    const long long nk = (long long)n * n * nh, nx3 = (long long)n * n * n;
+    // ---- ddl_step_array (forward_step_cy_3d.pyx etd1 / etd2rk2) vs the formulas on the host
+    {
+        const long long cnt = 4096;
+        std::vector<double> s(2 * cnt), d1(2 * cnt), d2(2 * cnt), IF(cnt), o(2 * cnt);
+        for (long long i = 0; i < 2 * cnt; ++i) { s[i] = hash01(i, 1); d1[i] = hash01(i, 2); d2[i] = hash01(i, 3); }
+        for (long long i = 0; i < cnt; ++i) IF[i] = (i % 7 == 0) ? 0.0 : -std::fabs(hash01(i, 4)) * ((i % 5 == 1) ? 0.4 : 40.0);
+        void *ds = dmalloc(16 * cnt), *dd1 = dmalloc(16 * cnt), *dd2 = dmalloc(16 * cnt), *dout = dmalloc(16 * cnt);
+        double* dIF = (double*)dmalloc(8 * cnt);
+        h2d(ds, s.data(), 16 * cnt); h2d(dd1, d1.data(), 16 * cnt); h2d(dd2, d2.data(), 16 * cnt); h2d(dIF, IF.data(), 8 * cnt);
+        const double dt = 0.02;
+        double worst = 0;
+        for (int kind : {DDL_ETD1, DDL_ETD2RK2}) {
+            DDL(ddl_step_array(kind, 3, cnt, ds, dout, dd1, dd2, dIF, dt, nullptr));
+            dsync(); d2h(o.data(), dout, 16 * cnt);
+            for (long long i = 0; i < cnt; ++i) {
+                const double Z = IF[i] * dt;
+                if (std::fabs(Z) < 0.5 && Z != 0.0) continue;          // the series branch is pinned by the CPU goldens
+                for (int c = 0; c < 2; ++c) {
+                    const double S = s[2 * i + c], A = d1[2 * i + c], B = d2[2 * i + c];
+                    double want;
+                    if (Z == 0.0) want = S + dt * (kind == DDL_ETD1 ? A : B);
+                    else {
+                        const double f0 = std::exp(Z), f1 = (f0 - 1.0) / Z, f2 = (f1 - 1.0) / Z;
+                        want = kind == DDL_ETD1 ? S * f0 + A * f1 * dt : S * f0 + (B - A) * 2.0 * f2 * dt + A * f1 * dt;
+                    }
+                    worst = std::fmax(worst, std::fabs(o[2 * i + c] - want) / (std::fabs(want) + 1.0));
+                }
+            }
+        }
+        verdict("ddl_step_array (etd1, etd2rk2) vs the closed forms", worst, 1e-14);
+        dfree(ds); dfree(dd1); dfree(dd2); dfree(dout); dfree(dIF);
+    }
+    // ---- shearing box: a plane wave cos(a x + b y) transforms to a single coefficient at ky0 = b + S t a (S t a an integer)
+    {
+        std::vector<double> k(n), kx(nh);
+        std::vector<uint8_t> keep(n), keepx(nh), full(n, 1);
+        const double kny = n / 2.0;
+        for (int i = 0; i < n; ++i) { k[i] = (i <= n / 2) ? i : i - n; keep[i] = std::fabs(k[i]) < 2.0 / 3.0 * kny; }
+        for (int i = 0; i < nh; ++i) { kx[i] = i; keepx[i] = std::fabs(kx[i]) < 2.0 / 3.0 * kny; }
+        int64_t shape[3] = {n, n, n};
+        ddl_plan* pl = nullptr;
+        DDL(ddl_plan_create(&pl, 3, shape, kx.data(), k.data(), k.data(), keepx.data(), full.data(), keep.data()));
+        const size_t wb = ddl_workspace_bytes(pl, 1, 1);
+        void* work = dmalloc(wb);
+        double* x = (double*)dmalloc(nx3 * 8);
+        void* kk = dmalloc(nk * 16);
+        const int a = 3, b = 2;
+        const double S = 1.5, t = 2.0 / (S * a) * 1.0;           // S t a = 2: the wave sits at stored ky index b + 2
+        const double two_pi = 6.283185307179586476925286766559, dy = two_pi / n;
+        std::vector<double> hx(nx3);
+        for (int iz = 0; iz < n; ++iz) for (int iy = 0; iy < n; ++iy) for (int ix = 0; ix < n; ++ix)
+            hx[((long long)iz * n + iy) * n + ix] = std::cos(a * (two_pi * ix / n) + b * (iy * dy));
+        h2d(x, hx.data(), nx3 * 8);
+        DDL(ddl_set_shear(pl, 1, S, t, dy));
+        DDL(ddl_forward(pl, x, kk, work, wb, nullptr));
+        dsync();
+        std::vector<double> hk(2 * nk);
+        d2h(hk.data(), kk, nk * 16);
+        const long long hit = ((long long)(b + 2) * n + 0) * nh + a;       // [ky][kz][kx]
+        double off = 0;
+        for (long long i = 0; i < nk; ++i) if (i != hit) off = std::fmax(off, std::hypot(hk[2 * i], hk[2 * i + 1]));
+        verdict("sheared forward of a plane wave: the one coefficient", std::hypot(hk[2 * hit] - 0.5, hk[2 * hit + 1]), 1e-13);
+        verdict("sheared forward of a plane wave: everything else", off, 1e-13);
+        DDL(ddl_backward(pl, kk, x, work, wb, nullptr));
+        dsync();
+        std::vector<double> hb(nx3);
+        d2h(hb.data(), x, nx3 * 8);
+        double e = 0;
+        for (long long i = 0; i < nx3; ++i) e = std::fmax(e, std::fabs(hb[i] - hx[i]));
+        verdict("sheared backward returns the wave", e, 1e-12);
+        // ---- ddl_dealias_array, dense-ky branch, vs a host loop
+        std::vector<double> kyd((size_t)n * nh), data(2 * nk);
+        for (int iy = 0; iy < n; ++iy) for (int ix = 0; ix < nh; ++ix) kyd[(size_t)iy * nh + ix] = k[iy] - 0.37 * kx[ix];
+        for (long long i = 0; i < 2 * nk; ++i) data[i] = hash01(i, 9);
+        double *dkx = (double*)dmalloc(8 * nh), *dky = (double*)dmalloc(8 * (size_t)n * nh), *dkz = (double*)dmalloc(8 * n);
+        h2d(dkx, kx.data(), 8 * nh); h2d(dky, kyd.data(), 8 * (size_t)n * nh); h2d(dkz, k.data(), 8 * n); h2d(kk, data.data(), 16 * nk);
+        int64_t kshape[3] = {n, n, nh};
+        const double knyq[3] = {kny, kny, kny};
+        DDL(ddl_dealias_array(3, kshape, kk, dkx, dky, dkz, 1, knyq, nullptr));
+        dsync(); d2h(hk.data(), kk, nk * 16);
+        long long bad = 0, zeroed = 0;
+        const double cut = 2.0 / 3.0 * kny;
+        for (int iy = 0; iy < n; ++iy) for (int iz = 0; iz < n; ++iz) for (int ix = 0; ix < nh; ++ix) {
+            const long long i = ((long long)iy * n + iz) * nh + ix;
+            const double ky = kyd[(size_t)iy * nh + ix];
+            const bool z = kx[ix] >= cut || kx[ix] <= -cut || ky >= cut || ky <= -cut || k[iz] >= cut || k[iz] <= -cut;
+            zeroed += z;
+            const double wr = z ? 0.0 : data[2 * i], wi = z ? 0.0 : data[2 * i + 1];
+            if (hk[2 * i] != wr || hk[2 * i + 1] != wi) bad++;
+        }
+        verdict("ddl_dealias_array, dense ky: entries differing from the host loop", (double)bad, 0.0);
+        if (zeroed == 0 || zeroed == nk) { g_fail++; say("  dealias_array: degenerate mask  FAIL\n"); }
+        dfree(dkx); dfree(dky); dfree(dkz); dfree(work); dfree(x); dfree(kk);
+        ddl_plan_destroy(pl);
+    }
+}
+
 // one RK4 step the way the Python integrator issues it once the state is dealiased (time_step.py RK4._advance_fused):
 // four ddl_rhs_stage calls, the spectral assembly fused with the stage update, y advanced in place
 static void rk4_fused_step(Problem& P, void* const* tmp, void* const* total, const double* coeff, double dt) {
@@ -396,7 +507,7 @@ int main(int argc, char** argv) {
         else if (pos == 1) { n_time = atoi(argv[i]); pos++; }
         else if (pos == 2) { g_out = fopen(argv[i], "w"); pos++; }
     }
-    if (n_check > 0) check(n_check);
+    if (n_check > 0) { check(n_check); check_seams(n_check < 64 ? n_check : 64); }
     if (n_time > 0) timing(n_time, reps);
     say("devcheck: %s (%d failure%s)\n", g_fail ? "FAILED" : "all ok", g_fail, g_fail == 1 ? "" : "s");
     if (g_out) fclose(g_out);
