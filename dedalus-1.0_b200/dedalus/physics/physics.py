@@ -231,12 +231,19 @@ class Physics(object):
         """True for representations whose wavenumbers depend on time (FourierShearRepresentation): the fused
         pipeline's index tables are static, so the right-hand side is evaluated the reference's way, helper by
         helper (a compatibility path), and the integrators update with tensor operations."""
-        if not self._representation._static_k:
-            return True
-        # without 2/3 dealiasing the reference's x-space products are ALIASED and its advective forms are what they are:
-        # the fused pipeline (conservative products, transforms pruned to the retained modes) has no equivalent, the
-        # helper sequence reproduces it exactly (FFT.dealiasing = None zeroes the Nyquist planes only, :442-455)
-        return decfg.get("FFT", "dealiasing") not in ("2/3", "2/3 cython")
+        flag = self.__dict__.get("_unfused_flag")
+        if flag is None:
+            # decided once per physics object (the representation reads FFT.dealiasing when it is constructed, too): this
+            # property sits on the per-step path of the launch-bound 2-D configurations
+            if not self._representation._static_k:
+                flag = True
+            else:
+                # without the per-axis 2/3 rule the reference's x-space products are ALIASED and its advective forms are what
+                # they are: the fused pipeline (conservative products, transforms pruned to the retained modes) has no
+                # equivalent, the helper sequence reproduces it exactly
+                flag = decfg.get("FFT", "dealiasing") not in ("2/3", "2/3 cython")
+            self._unfused_flag = flag
+        return flag
 
     # ------------------------------------------------------------------ solenoidal or not
     SOLENOIDAL_TOL = 1e-12      # compressive fraction sqrt(sum |k.u|^2 / sum |k|^2 |u|^2) below which u counts as div-free
