@@ -56,3 +56,22 @@ def test_slab_package_under_host_emulation_gloo(world, layout, tmp_path):
         assert case["rel_after_cfl_step"] < 1e-10, case
         assert case["solenoidal_verdict"] == (not case["compressive"]), case
         assert case["ky_layout"] == layout and case["exchanges"] > 0
+
+
+@pytest.mark.parametrize("world,layout", [(2, "block"), (4, "cyclic")])
+def test_slab_unfused_and_odd_grids_under_host_emulation_gloo(world, layout, tmp_path):
+    """Slab-decomposed runs on the paths added late in round 1 (tests/slab_unfused_worker.py): the unfused helper sequence
+    (FFT.dealiasing = None, '2/3 spherical') and a 12 x 20 x 24 grid, against the oracle."""
+    import json
+    out = str(tmp_path / "res.json")
+    env = dict(os.environ, DDL_TEST_HOST_EMUL="1", DEDALUS_KY_LAYOUT=layout, DEDALUS_SLAB_EXCHANGE="collective", OMP_NUM_THREADS="1")
+    env.pop("DEDALUS_DDL_LIB", None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_unfused_worker.py"), out]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:]
+    res = json.load(open(out))
+    assert len(res) == 3 and [c["unfused"] for c in res] == [True, True, False]
+    for case in res:
+        assert case["rel"] < 1e-10, case
+        assert abs(case["dt"] - case["dt_oracle"]) < 1e-11 * case["dt_oracle"], case
