@@ -172,6 +172,7 @@ struct Axis {
     int m = 0;          // retained modes: |index| <= m
     int cnt = 1;        // retained count: 2m+1 (full axis) or m+1 (half axis)
     bool half = false;
+    bool full = false;   // every row kept, Nyquist included (shearing box, ky axis only)
     double* kv = nullptr;           // [nk] wavenumber per stored index
     unsigned char* keep = nullptr;  // [nk]
     double* kvc = nullptr;          // [cnt] wavenumber per compact index
@@ -239,7 +240,7 @@ static int build_axis(ddl_plan* pl, Axis& a, int n, bool half, const double* kv,
         int mi = (j <= n / 2) ? j : n - j;
         if ((keep[j] != 0) != (mi <= m)) { set_error("dealias mask is not of the form |k index| <= m"); return -1; }
     }
-    a.m = m; a.cnt = half ? m + 1 : (full ? n : 2 * m + 1);
+    a.m = m; a.cnt = half ? m + 1 : (full ? n : 2 * m + 1); a.full = full;
     std::vector<double> kvh(kv, kv + a.nk), kvc(a.cnt);
     std::vector<unsigned char> kp(keep, keep + a.nk);
     std::vector<int> c2f(a.cnt), f2c(a.nk, -1), f2f(a.nk, -1);
@@ -271,7 +272,7 @@ extern "C" int ddl_plan_create_slab(ddl_plan** out, int ndim, const int64_t* sha
     int rc = 0;
     if (ndim == 3) {
         rc = build_axis(pl, pl->az, (int)shape_x[0], false, kz, keepz);
-        if (!rc) rc = build_axis(pl, pl->ay, (int)shape_x[1], false, ky, keepy, nranks == 1);
+        if (!rc) rc = build_axis(pl, pl->ay, (int)shape_x[1], false, ky, keepy, true);
         if (!rc) rc = build_axis(pl, pl->ax, (int)shape_x[2], true, kx, keepx);
     } else {
         rc = build_axis(pl, pl->ay, (int)shape_x[0], false, ky, keepy, true);
@@ -1033,6 +1034,7 @@ extern "C" int ddl_slab_theta(ddl_plan* pl, int physics, void* const* state, voi
 }
 extern "C" int ddl_slab_zinv(ddl_plan* pl, int nf, void* const* k_in, void* const* ks_out, void* stream) {
     DDL_TRY(need_3d(pl));
+    FastGuard fg(pl->ay.full);
     return phase_zinv(pl, nf, (const void* const*)k_in, ks_out, (ddl_stream_t)stream);
 }
 extern "C" int ddl_slab_zinv_peer(ddl_plan* pl, int nf, void* const* k_in, void* const* peer_tab, void* stream) {
@@ -1059,6 +1061,7 @@ extern "C" int ddl_slab_xfused_planes(ddl_plan* pl, int physics, const ddl_phys_
 }
 extern "C" int ddl_slab_yinv(ddl_plan* pl, int nf, void* const* xs_in, void* const* b_out, void* stream) {
     DDL_TRY(need_3d(pl));
+    FastGuard fg(pl->ay.full);
     return phase_yinv(pl, nf, (const void* const*)xs_in, b_out, (ddl_stream_t)stream);
 }
 extern "C" int ddl_slab_xfused(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* b_in, void* const* c_out,
@@ -1079,10 +1082,12 @@ extern "C" int ddl_slab_xr2c(ddl_plan* pl, const double* x_in, void* c_out, void
 }
 extern "C" int ddl_slab_yfwd(ddl_plan* pl, int nf, void* const* c_in, void* const* xs_out, void* stream) {
     DDL_TRY(need_3d(pl));
+    FastGuard fg(pl->ay.full);
     return phase_yfwd(pl, nf, (const void* const*)c_in, xs_out, (ddl_stream_t)stream);
 }
 extern "C" int ddl_slab_zfwd(ddl_plan* pl, int nf, void* const* ks_in, void* const* out, int full_out, void* stream) {
     DDL_TRY(need_3d(pl));
+    FastGuard fg(pl->ay.full);
     return phase_zfwd(pl, nf, (const void* const*)ks_in, out, full_out != 0, (ddl_stream_t)stream);
 }
 extern "C" int ddl_slab_assemble_stage(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* e_in, void* const* state,
@@ -1265,7 +1270,6 @@ extern "C" int ddl_sync(void* stream) {
 // shearing box: phase factors of the following ddl_forward / ddl_backward calls on this plan (include/ddl.h)
 extern "C" int ddl_set_shear(ddl_plan* pl, int enable, double shear_rate, double time, double dy) {
     if (!pl) { set_error("ddl_set_shear: NULL plan"); return -1; }
-    if (enable && pl->nranks != 1) { set_error("the shearing box runs on one-rank plans"); return -1; }
     pl->shear_on = enable ? 1 : 0;
     pl->sh_S = shear_rate; pl->sh_t = time; pl->sh_dy = dy;
     return 0;

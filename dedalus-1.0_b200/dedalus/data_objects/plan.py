@@ -95,8 +95,6 @@ class Plan(object):
         # (representations.py:627-642); the plan keeps every ky row, the passes prune nothing along y
         self.full_ky = bool(full_ky)
         if self.full_ky:
-            if self.nranks > 1:
-                raise NotImplementedError("FourierShearRepresentation runs on one GPU (no slab decomposition).")
             self.keep_np["y"] = np.ones_like(self.keep_np["y"])
         self.device = device()
         shp = np.array(self.shape, dtype=np.int64)
@@ -145,7 +143,7 @@ class Plan(object):
             import os
             from ..config import decfg
             kind = os.environ.get("DEDALUS_SLAB_EXCHANGE", decfg.get("parallel", "exchange"))
-            if kind == "peer" and any(n < 16 or (n & (n - 1)) for n in self.shape[:2]):
+            if self.full_ky or (kind == "peer" and any(n < 16 or (n & (n - 1)) for n in self.shape[:2])):
                 # the peer-store passes exist in the specialised strided kernels only (powers of two >= 16);
                 # any other nz / ny exchanges through the collective
                 kind = "collective"

@@ -391,7 +391,7 @@ class FourierShearRepresentation(FourierRepresentation):
     (fwd_np / rev_np :700-740) -- here the factor is applied INSIDE the x pass of ddl_forward / ddl_backward
     (include/ddl.h: ddl_set_shear), on a plan that keeps every ky row.  A compatibility path: the physics classes
     evaluate their right-hand side through the reference's unfused helpers for this representation and the
-    integrators update with tensor operations; one GPU."""
+    integrators update with the array-factor stage kernel; one GPU or a slab decomposition (collective exchange)."""
 
     _static_k = False
 

@@ -113,7 +113,8 @@ int ddl_deriv(ddl_plan* plan, const void* k_in, void* k_out, int axis, void* str
  * on the way back (fwd_np / rev_np :700-740; FFTW route :667-698).  While enabled, ddl_forward / ddl_backward of this
  * plan apply that factor inside their x pass (no extra pass over memory).  The plan of a shearing box is created with a
  * ky mask that keeps EVERY row (all ones, Nyquist included): the sheared wavenumber ky - S kx t, its wrap and its 2/3 mask
- * depend on kx and time (:627-642) and belong to the caller; kx and kz are masked as usual.  One-rank plans. */
+ * depend on kx and time (:627-642) and belong to the caller (ddl_dealias_array); kx and kz are masked as usual.  Slab-decomposed
+ * plans too: ddl_slab_xr2c / ddl_slab_xc2r apply the factor, the other phases take the generic kernels for such a plan. */
 int ddl_set_shear(ddl_plan* plan, int enable, double shear_rate, double time, double dy);
 
 /* physics.py:527-599 / 664-712 / 770-819: deriv = RHS(state), all pointers k-space arrays in

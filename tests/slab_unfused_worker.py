@@ -56,6 +56,61 @@ def main(out_path):
         results.append({"physics": physics, "shape": shape, "dealiasing": dl, "rel": float(torch.sqrt(num[0] / num[1])),
                         "dt": float(dt_dev), "dt_oracle": float(dt_orc), "unfused": bool(P._unfused)})
         decfg.set("FFT", "dealiasing", "2/3 cython")
+    # shearing box, slab-decomposed, against the oracle's restatement (pinned to the reference goldens by tests/test_oracle_shear.py)
+    import dedalus.physics.api as papi
+    from dedalus.data_objects.api import FourierShearRepresentation
+    for physics, shape, integ, S, t0 in [("IncompressibleHydro", (8, 16, 16), "RK2mid", 1.5, 0.0),
+                                         ("IncompressibleMHD", (16, 16, 16), "RK2trap", -1.0, 1.3),
+                                         ("BoussinesqHydro", (8, 16, 24), "RK2mid", 1.0, 0.4)]:
+        params = dict(nu=1e-2, eta=2e-2, kappa=1e-2)
+        decfg.set("physics", "boussinesq_direction", "z")
+        kw = {"direction": "z"} if physics == "BoussinesqHydro" else {}
+        Po = orc.PHYSICS[physics](shape, None, "2/3 cython", shear=True, **kw)
+        Po.parameters.update({k: v for k, v in params.items() if k in Po.parameters or k in ("nu",)})
+        Po.parameters["shear_rate"] = S
+        do = Po.create_fields(t0)
+        ncomp = len(list(do.components()))
+        noise = np.random.default_rng(41).standard_normal((ncomp,) + tuple(shape))
+        j = 0
+        for _, f in do:
+            for _, c in f:
+                c["xspace"] = noise[j]
+                c["kspace"]
+                j += 1
+            if f.ncomp > 1:
+                f.div_free()
+        P = getattr(papi, physics)(tuple(shape), FourierShearRepresentation)
+        P.parameters.update({k: v for k, v in params.items() if k in P.parameters})
+        P.parameters["shear_rate"] = S
+        data = P.create_fields(t0)
+        comps = [c for _, _, c in data.components()]
+        rows = comps[0].local_rows["kspace"]
+        z0, nzl = int(comps[0].offset["xspace"]), int(comps[0].local_shape["xspace"][0])
+        assert comps[0]._plan.nranks == world and comps[0]._plan.full_ky
+        j = 0
+        for _, f in data:
+            for _, c in f:
+                c["xspace"] = torch.from_numpy(np.ascontiguousarray(noise[j][z0:z0 + nzl]))
+                c["kspace"]
+                j += 1
+            if f.ncomp > 1:
+                f.div_free()
+        y0 = do.kvector()
+        loc = np.stack([c["kspace"].cpu().numpy() for c in comps])
+        init = torch.tensor([np.linalg.norm(loc - y0[:, rows]) ** 2, np.linalg.norm(y0[:, rows]) ** 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(init)
+        ti, to = getattr(tapi, integ)(P), orc.INTEGRATORS[integ](Po)
+        for _ in range(2):
+            ti.do_advance(data, 5e-3)
+            to.do_advance(do, 5e-3)
+        y1 = do.kvector()
+        loc = np.stack([c["kspace"].cpu().numpy() for c in comps])
+        num = torch.tensor([np.linalg.norm(loc - y1[:, rows]) ** 2, np.linalg.norm(y1[:, rows]) ** 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(num)
+        dt_dev, dt_orc = P.compute_dt(data), Po.compute_dt(do)
+        results.append({"physics": physics, "shape": shape, "dealiasing": "shear %g" % S, "rel": float(torch.sqrt(num[0] / num[1])),
+                        "rel_init": float(torch.sqrt(init[0] / init[1])), "dt": float(dt_dev), "dt_oracle": float(dt_orc),
+                        "unfused": bool(P._unfused)})
     if rank == 0:
         with open(out_path, "w") as f:
             json.dump(results, f)

@@ -71,7 +71,8 @@ def test_slab_unfused_and_odd_grids_under_host_emulation_gloo(world, layout, tmp
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:]
     res = json.load(open(out))
-    assert len(res) == 3 and [c["unfused"] for c in res] == [True, True, False]
+    assert len(res) == 6 and [c["unfused"] for c in res] == [True, True, False, True, True, True]
+    assert all(c["rel_init"] < 1e-13 for c in res[3:])
     for case in res:
         assert case["rel"] < 1e-10, case
         assert abs(case["dt"] - case["dt_oracle"]) < 1e-11 * case["dt_oracle"], case
