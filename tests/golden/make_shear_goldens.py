@@ -124,6 +124,15 @@ def run_case(c):
     out["time"] = data.time
     out["dt_cfl"] = RHS.compute_dt(data)
     out["y1_after_cfl"] = kvec(data)
+    # the reference's CFL-controlled loop from here: advance(data) with dt = None (time_step.py:100-107,170-179)
+    ti.CFL = 0.4
+    ti.save_cadence, ti.max_save_period, ti.iteration = 10 ** 9, 1e300, 1          # no snapshots (h5py is not installed)
+    dts = []
+    for _ in range(3):
+        ti.advance(data)
+        dts.append(ti.dt_old)
+    out["cfl_dts"] = np.array(dts)
+    out["y2"] = kvec(data)
     meta = dict(c)
     meta["length"] = list(c["length"]) if c["length"] else None
     out["meta"] = np.array(repr(meta))
