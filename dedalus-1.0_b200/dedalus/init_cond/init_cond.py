@@ -135,6 +135,44 @@ def turb_new(data, spec, tot_en=0.5, rng=None, **kwargs):
         data["u"]["z"]["kspace"] = -(beta * kh) / kk
 
 
+def turb(ux, uy, spec, tot_en=0.5, rng=None, **kwargs):
+    """The older 2-D random-phase generator on two components (init_cond.py:343-375): spectrum `spec`, one random phase
+    array (numpy's global generator by default, like the reference), the kx = 0 column made Hermitian by hand.  `tot_en`
+    is accepted and unused, as there."""
+    kk = torch.zeros(ux._k.shape, dtype=torch.float64, device=ux._k.device)
+    for kv in ux.k.values():
+        kk = kk + kv ** 2
+    kk = torch.sqrt(kk)
+    k2 = torch.sqrt(ux.k["x"] ** 2 + ux.k["y"] ** 2)
+    k2 = torch.where(k2 == 0, torch.ones_like(k2), k2)
+    sp = spec(kk, **kwargs)
+    kk = torch.where(kk == 0, torch.ones_like(kk), kk)
+    ampl = torch.sqrt(sp / (2 * np.pi * kk))
+    alpha = ampl * torch.exp(1j * 2 * np.pi * _uniform(ux._k.shape, ux._k.device, rng))
+    a, b = ux.kdata, uy.kdata
+    a[:, :] = alpha * kk * ux.k["y"] / (kk * k2)
+    b[:, :] = -alpha * kk * ux.k["x"] / (kk * k2)
+    n1 = a.shape[1]
+    nh = n1 // 2 + 1
+    if n1 % 2 == 0:
+        start = nh - 2
+        a[0, nh - 1] = 0.
+    else:
+        start = nh - 1
+    idx = torch.arange(start, 0, -1, device=a.device)
+    a[0, nh:] = a[0, idx].conj()
+    b[0, nh:] = b[0, idx].conj()
+
+
+def remove_compressible(ux, uy, renorm=False):
+    """Project the compressive part off a 2-D velocity field (init_cond.py:377-389)."""
+    if renorm:
+        raise NotImplementedError
+    ku = ux.kdata * ux.k["x"] + uy.kdata * uy.k["y"]
+    ux.kdata.sub_(ku * ux.k["x"] / ux.k2(no_zero=True))
+    uy.kdata.sub_(ku * uy.k["y"] / uy.k2(no_zero=True))
+
+
 def MIT_vortices(data):
     """Three Gaussian vortices of the MIT 18.336 spectral NS demo (init_cond.py:391-408)."""
     y, x = data["u"]["x"].xspace_grid()

@@ -141,6 +141,7 @@ SPECIFIC = {
     ],
     "dedalus/init_cond/init_cond.py": [
         (r"kshape/2 \+ 1", "kshape//2 + 1"),
+        (r"ux\.data\.shape\[1\]/2 \+ 1", "ux.data.shape[1]//2 + 1"),
     ],
     "dedalus/utils/parallelism.py": [],
 }

@@ -78,6 +78,14 @@ def ic_cases():
     # (representations.py:480): not runnable without MPI -> no golden; the port is pinned by properties
     # (realness of the x-space field, <noise^2> = std^2) in tests/test_gpu_widen.py
 
+    # the older 2-D generator turb() followed by remove_compressible() (init_cond.py:343-389)
+    np.random.seed(99)
+    RHS, d = physics("IncompressibleHydro", (24, 32))
+    ic.turb(d['u']['x'], d['u']['y'], mcwilliams_spec, k0=4., E0=1.)
+    out["turb_old"] = kvec(d)
+    ic.remove_compressible(d['u']['x'], d['u']['y'])
+    out["turb_old_projected"] = kvec(d)
+
     RHS, d = physics("BoussinesqHydro", (16, 16))
     ic.sin_k(d['u']['x']['kspace'], (2, 3), ampl=0.5)
     ic.cos_k(d['u']['y']['kspace'], (1, 2), ampl=-1.5)

@@ -231,6 +231,19 @@ def test_initial_conditions_match_reference_generators(kind, physics, shape):
     assert np.abs(got - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), kind
 
 
+def test_old_turb_generator_and_projection_match_reference():
+    """turb() + remove_compressible() (init_cond.py:343-389) against the reference's own run (seeded numpy generator)."""
+    import dedalus.init_cond.api as ic
+    z = np.load(os.path.join(SAMPLES, "init_cond.npz"))
+    P = dev_physics("IncompressibleHydro", (24, 32))
+    data = P.create_fields(0.)
+    np.random.seed(99)
+    ic.turb(data["u"]["x"], data["u"]["y"], ic.mcwilliams_spec, k0=4., E0=1.)
+    assert np.abs(get_state(data) - z["turb_old"]).max() <= 1e-13 * np.abs(z["turb_old"]).max()
+    ic.remove_compressible(data["u"]["x"], data["u"]["y"])
+    assert np.abs(get_state(data) - z["turb_old_projected"]).max() <= 1e-13 * np.abs(z["turb_old_projected"]).max()
+
+
 def _set_run_ic(tag, data):
     import torch
     import dedalus.init_cond.api as ic
