@@ -483,6 +483,45 @@ class RK4(RKBase):
     def _rk4_fused(self, state_in, y, out, wdiv, dt_step, first, last):
         self._stage_fused(_lib.FUSE_RK4, state_in, y, out, dt_step, total=self.total_deriv, wdiv=wdiv, first=first, last=last)
 
+    def _advance_dynamic_k(self, data, dt):
+        """Shearing box (restated like the rest of RK4; no run of the reference can pin it): every stage step takes the
+        integrating factor of the container holding its derivative -- each RHS evaluation rewrites it at its own time level
+        (physics.py:584-586) -- and the final combination the copy taken at k1 (time_step.py:437-441).  Array-factor kernel per
+        component (include/ddl.h: ddl_step_array), accumulation as tensor operations."""
+        if dt is None:
+            dt = self.cfl_dt(data)
+        R, tmp, k, tot = self.RHS, self.temp_data, self.k_data, self.total_deriv
+        ndim = data.ndim
+
+        def neg_factors(sd):
+            return [None if c.integrating_factor is None else (-c.integrating_factor.tensor()).contiguous() for _, _, c in sd.components()]
+
+        def step(deriv, out, h, factors):
+            s, d, o = _kspace_tensors(data), _kspace_tensors(deriv), _kspace_tensors(out)
+            for j in range(len(s)):
+                f = factors[j]
+                check(lib.ddl_step_array(_lib.ETD1, ndim, s[j].numel(), s[j].data_ptr(), o[j].data_ptr(), d[j].data_ptr(), None,
+                                         f.data_ptr() if f is not None else None, float(h), _plan.current_stream()))
+            _mark(out, False)
+
+        R.RHS(data, k)                                            # k1
+        initial = neg_factors(k)
+        for t, kk in zip(_kspace_tensors(tot), _kspace_tensors(k)):
+            t.copy_(kk / 6.)
+        step(k, tmp, dt / 2., initial)
+        tmp.set_time(data.time + dt / 2.)
+        for w, h in ((3., dt / 2.), (3., dt), (6., None)):
+            R.RHS(tmp, k)                                         # k2, k3, k4
+            for t, kk in zip(_kspace_tensors(tot), _kspace_tensors(k)):
+                t.add_(kk / w)
+            if h is not None:
+                step(k, tmp, h, neg_factors(k))
+                tmp.set_time(data.time + h)
+        step(tot, data, dt, initial)
+        data.set_time(data.time + dt)
+        self.time += dt
+        self.iteration += 1
+
     def _advance_fused(self, data, dt):
         tmp = self.temp_data
         self._rk4_fused(data, data, tmp, 6., dt / 2., True, False)      # k1
@@ -498,7 +537,7 @@ class RK4(RKBase):
     def do_advance(self, data, dt):
         R, tmp, k = self.RHS, self.temp_data, self.k_data
         if getattr(R, "_dynamic_k", False):
-            raise NotImplementedError("RK4 in a shearing box: use RK2mid / RK2trap (the reference's RK4 does not run, SURVEY F1-F3)")
+            return self._advance_dynamic_k(data, dt)
         _settle(data, self.RHS)
         lazy = dt is None
         if not lazy and self._can_fuse(data, self.total_deriv, self.temp_data):
@@ -558,7 +597,19 @@ class CrankNicholsonVisc(TimeStepBase):
 
     def do_advance(self, data, dt):
         if getattr(self.RHS, "_dynamic_k", False):
-            raise NotImplementedError("CrankNicholsonVisc in a shearing box: use RK2mid / RK2trap")
+            # shearing box (restated): the factor of this RHS evaluation's time level, as tensor operations
+            if dt is None:
+                dt = self.cfl_dt(data)
+            self.RHS.RHS(data, self.deriv)
+            for (_, _, c), y, kk in zip(self.deriv.components(), _kspace_tensors(data), _kspace_tensors(self.deriv)):
+                IF = 0. if c.integrating_factor is None else c.integrating_factor.tensor()
+                top, bottom = 1. / dt - 0.5 * IF, 1. / dt + 0.5 * IF
+                y.copy_(top / bottom * y + kk / bottom)
+            _mark(data, False)
+            data.set_time(data.time + dt)
+            self.time += dt
+            self.iteration += 1
+            return
         _settle(data, self.RHS)
         lazy = dt is None
         if not lazy and self._can_fuse(data):
