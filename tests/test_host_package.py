@@ -11,9 +11,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_gpu_test_files_pass_under_host_emulation():
-    env = dict(os.environ, DDL_TEST_HOST_EMUL="1")
+    env = dict(os.environ, DDL_TEST_HOST_EMUL="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
     env.pop("DEDALUS_DDL_LIB", None)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+    try:
+        import xdist  # noqa: F401
+        par = ["-n", str(min(6, os.cpu_count() or 1))]
+    except ImportError:
+        par = []
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + par + [
                         os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_widen.py"),
                         os.path.join(ROOT, "tests", "test_mixed_radix.py"), os.path.join(ROOT, "tests", "test_gpu_shear.py"),
                         os.path.join(ROOT, "tests", "test_gpu_restart.py"), os.path.join(ROOT, "tests", "test_gpu_analysis.py"),

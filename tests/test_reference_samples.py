@@ -24,7 +24,7 @@ SAMPLES = [("samples/incompressible_hydro/swinging_wave/simulation.py", 6),
 def run(script, iters, workdir, impl):
     os.makedirs(workdir, exist_ok=True)
     out = os.path.join(workdir, "final.npz")
-    env = dict(os.environ, DDL_TEST_HOST_EMUL="1")
+    env = dict(os.environ, DDL_TEST_HOST_EMUL="1", OMP_NUM_THREADS="2")
     env.pop("DEDALUS_DDL_LIB", None)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_sample.py"), os.path.join(REF, script), str(iters),
                         workdir, impl, out], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
