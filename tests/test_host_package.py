@@ -22,7 +22,7 @@ def test_gpu_test_files_pass_under_host_emulation():
                         os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_widen.py"),
                         os.path.join(ROOT, "tests", "test_mixed_radix.py"), os.path.join(ROOT, "tests", "test_gpu_shear.py"),
                         os.path.join(ROOT, "tests", "test_gpu_restart.py"), os.path.join(ROOT, "tests", "test_gpu_analysis.py"),
-                        os.path.join(ROOT, "tests", "test_gpu_known_answers.py")],
+                        os.path.join(ROOT, "tests", "test_gpu_known_answers.py"), os.path.join(ROOT, "tests", "test_gpu_errors.py")],
                        cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     tail = "\n".join(r.stdout.strip().splitlines()[-15:])
     assert r.returncode == 0, tail
