@@ -36,15 +36,35 @@ class StateData(object):
     def set_time(self, time):
         # shearing-box components follow the time: their wavenumbers drift with it (state_data.py:115-121)
         self.time = time
-        for _, f in self.fields.items():
-            if not f.representation._static_k:
-                for _, c in f:
-                    c._update_k()
+        for f in self._cached()[4]:
+            for _, c in f:
+                c._update_k()
 
     def add_field(self, name, fieldtype):
         if name in self.fields:
             raise ValueError("Field with this name already exists.")
         self.fields[name] = self._field_classes[fieldtype](self)
+        self._cache = None
+
+    # Per-step host overhead matters for the small, launch-bound grids (tens of microseconds of kernels per step): the
+    # integrators and the fused RHS walk the components through these cached lists instead of the generators.  Valid because a
+    # component's k-space buffer never changes identity (representations.py:144-149) and fields are only ever added.
+    _cache = None
+
+    def _cached(self):
+        c = self._cache
+        if c is None:
+            comps = [comp for _, f in self.fields.items() for _, comp in f]
+            ks = [comp._k for comp in comps]
+            import ctypes as C
+            arr = (C.c_void_p * len(ks))(*[t.data_ptr() for t in ks])
+            dyn = [f for _, f in self.fields.items() if not f.representation._static_k]
+            c = self._cache = (comps, ks, arr, C.cast(arr, C.c_void_p), dyn)
+        return c
+
+    def comp_list(self):
+        """All components, insertion order (cached)."""
+        return self._cached()[0]
 
     def components(self):
         """(field name, component index, representation) in insertion order."""
@@ -68,7 +88,7 @@ class StateData(object):
             f.report_counts()
 
     def __reduce__(self):
-        state = {k: v for k, v in self.__dict__.items() if k not in ("fields", "_field_classes")}
+        state = {k: v for k, v in self.__dict__.items() if k not in ("fields", "_field_classes", "_cache")}
         rep = next(iter(self._field_classes.values())).representation
         keys = [(n, f.__class__.__name__) for n, f in self.fields.items()]
         return (_rebuild_state, (self.__class__, state, rep, keys))

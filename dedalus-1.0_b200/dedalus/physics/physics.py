@@ -86,7 +86,8 @@ class Physics(object):
 
     def __reduce__(self):
         self._is_finalized = False
-        keep = {k: v for k, v in self.__dict__.items() if k not in ("aux_fields", "_field_classes", "forcing_functions")}
+        keep = {k: v for k, v in self.__dict__.items() if k not in ("aux_fields", "_field_classes", "forcing_functions", "_pp_cache",
+                                                                    "_aux_fields")}
         return (_reconstruct_object, (self.__class__, keep))
 
     def _finalize(self):
@@ -202,6 +203,16 @@ class Physics(object):
     # ------------------------------------------------------------------ fused RHS
     def _phys_params(self):
         p = self.parameters
+        key = (p.get("rho0"), p.get("g"), p.get("alpha_t"), p.get("beta"), p.get("boussinesq_direction"), self._tracer)
+        hit = self.__dict__.get("_pp_cache")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        pp = self._build_phys_params()
+        self._pp_cache = (key, pp)
+        return pp
+
+    def _build_phys_params(self):
+        p = self.parameters
         d = p.get("boussinesq_direction", "z")
         if self._tracer:
             return _lib.PhysParams(float(p.get("rho0", 1.0)), 0.0, 0.0, 0.0, 0, 0)      # tracer in the T slot, no coupling
@@ -256,9 +267,18 @@ class Physics(object):
         (derivatives are projected / curls, so an update keeps whatever its start state had); for a buffer
         the CALLER has written since the last check one sweep of ddl_reduce_invariants measures the
         compressive fraction of u and B.  Returns True when the whole state is solenoidal."""
-        vec = [(n, f) for n, f in data if n in ("u", "B")]
         if self._unfused:
             return True                    # the unfused path evaluates the advective forms themselves
+        for c in data.comp_list():
+            if c._soln is not True:
+                break
+        else:
+            return True                    # steady state of a run: every verdict known and positive
+        vec = [(n, f) for n, f in data if n in ("u", "B")]
+        for n, f in data:
+            if n not in ("u", "B"):
+                for _, c in f:
+                    c._soln = True         # scalars (T, tracer) have no divergence to speak of: never hold the fused path back
         if any(c._soln is None for _, f in vec for _, c in f):
             from ..analysis.volume_average import invariants
             from .._lib import INV
@@ -287,28 +307,31 @@ class Physics(object):
         consumed in registers by the integrator's stage update instead of being written (ddl_rhs_stage)."""
         if not self._is_finalized:
             self._finalize()
-        if decfg.get("FFT", "dealiasing") not in ("2/3", "2/3 cython"):
+        if self._unfused:
             raise NotImplementedError(
                 "The fused RHS uses conservative products, which equal the reference's advective form only under "
                 "2/3 dealiasing; FFT.dealiasing=%r is not supported." % decfg.get("FFT", "dealiasing"))
-        state, out = [], []
+        comps = data.comp_list()
         state_clean = deriv_clean = True
-        for _, _, c in data.components():
-            c.require_space("kspace")
-            if flags & _lib.RHS_DEALIAS_STATE:
+        for c in comps:
+            if c._curr_space != "kspace":
+                c.require_space("kspace")
+            if (flags & _lib.RHS_DEALIAS_STATE) and not c._sym:
                 c._hermitian_project()      # with the mask: the image of the reference's x-space round trip of the state
-            state.append(c._k)
             state_clean = state_clean and c._clean
-        for _, _, c in (deriv.components() if deriv is not None else ()):
-            c._curr_space = "kspace"
-            out.append(c._k)
-            deriv_clean = deriv_clean and c._clean
+        state = data._cached()[1]
+        out = []
+        if deriv is not None:
+            for c in deriv.comp_list():
+                c._curr_space = "kspace"
+                deriv_clean = deriv_clean and c._clean
+            out = deriv._cached()[1]
         # mask passes only where the buffers are not already known to be zero outside the mask
         if deriv_clean:
             flags &= ~_lib.RHS_ZERO_FILL
         if state_clean:
             flags &= ~_lib.RHS_DEALIAS_STATE
-        pl = next(data.components())[2]._plan
+        pl = comps[0]._plan
         pp = self._phys_params()
         if not self.verify_solenoidal(data):
             # a compressive part in u or B (whatever put it there, the reference keeps it): advective-form
@@ -322,17 +345,18 @@ class Physics(object):
                             bool(flags & _lib.RHS_ZERO_FILL) and fuse is None, fuse=fuse)
         elif fuse is not None:
             w = pl.rhs_workspace(self._physics_id)
-            check(lib.ddl_rhs_stage(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), w.data_ptr(), w.numel(),
+            check(lib.ddl_rhs_stage(pl.handle, self._physics_id, C.byref(pp), data._cached()[3], w.data_ptr(), w.numel(),
                                   flags & ~_lib.RHS_ZERO_FILL, C.byref(fuse), _plan.current_stream()))
         else:
             w = pl.rhs_workspace(self._physics_id)
             check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), _lib.ptr_array(out),
                               w.data_ptr(), w.numel(), flags, _plan.current_stream()))
-        for _, _, c in (deriv.components() if deriv is not None else ()):
-            c._clean = True
-            c._soln = True
+        if deriv is not None:
+            for c in deriv.comp_list():
+                c._clean = True
+                c._soln = True
         if flags & _lib.RHS_DEALIAS_STATE:
-            for _, _, c in data.components():
+            for c in comps:
                 c._clean = True
         if deriv is not None:
             deriv.set_time(data.time)

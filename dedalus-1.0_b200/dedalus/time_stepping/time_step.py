@@ -29,20 +29,35 @@ hg_version = "b200-native"
 
 
 def _kspace_tensors(sd):
-    out = []
-    for _, _, c in sd.components():
-        c.require_space("kspace")
-        out.append(c._k)
-    return out
+    """The k-space buffers of every component (each brought to k-space first); the list itself is cached on the StateData."""
+    comps, ks = sd._cached()[:2]
+    for c in comps:
+        if c._curr_space != "kspace":
+            c.require_space("kspace")
+    return ks
+
+
+def _kspace_ptrs(sd):
+    """(void*)[n] of those buffers as ctypes passes it: built once, the buffers never change identity."""
+    comps, _, arr, ptr, _ = sd._cached()
+    for c in comps:
+        if c._curr_space != "kspace":
+            c.require_space("kspace")
+    return arr, ptr
 
 
 def _all_clean(*sds):
     """True when every component of every StateData is known to vanish outside the dealias mask."""
-    return all(c._clean for sd in sds if sd is not None for _, _, c in sd.components())
+    for sd in sds:
+        if sd is not None:
+            for c in sd._cached()[0]:
+                if not c._clean:
+                    return False
+    return True
 
 
 def _mark(sd, clean):
-    for _, _, c in sd.components():
+    for c in sd._cached()[0]:
         c._clean = clean
 
 
@@ -51,7 +66,7 @@ def _inherit(out, start):
     its start state: derivatives of u are projected, those of B are curls (physics.verify_solenoidal)."""
     if out is start:
         return
-    for (_, _, co), (_, _, cs) in zip(out.components(), start.components()):
+    for co, cs in zip(out._cached()[0], start._cached()[0]):
         co._soln = cs._soln
 
 
@@ -61,8 +76,9 @@ def _settle(sd, R=None):
     object, their fields' 'solenoidal' verdict (Physics.verify_solenoidal): both decide which kernels run."""
     if R is not None and getattr(R, "_unfused", False):
         return                      # shearing box: no fused kernels to choose between
-    for _, _, c in sd.components():
-        c.require_space("kspace")
+    for c in sd._cached()[0]:
+        if c._curr_space != "kspace":
+            c.require_space("kspace")
         if not c._clean and not c._checked:
             c.verify_clean()
     if R is not None and hasattr(R, "verify_solenoidal"):
@@ -70,7 +86,7 @@ def _settle(sd, R=None):
 
 
 def _plan_of(sd):
-    return next(sd.components())[2]._plan
+    return sd._cached()[0][0]._plan
 
 
 def _if_coefficients(deriv):
@@ -191,6 +207,9 @@ class TimeStepBase(object):
         """Pickled into every snapshot (time_step.py:133-138): the integrating-factor coefficients are a ctypes
         array at run time and travel as a plain list."""
         state = dict(self.__dict__)
+        state.pop("_fuse_cache", None)          # argument blocks of the fused stage calls: rebuilt on demand
+        state.pop("_graph", None)
+        state.pop("_graph_warm", None)
         co = state.get("_coeff")
         if co is not None:
             state["_coeff"] = ("coeff", list(co[0]), int(co[1]))
@@ -312,30 +331,37 @@ class TimeStepBase(object):
             return False
         if R.aux_eqns or not R.can_fuse_stage():
             return False
-        if not all(c._soln for sd in sds if sd is not None for _, _, c in sd.components()):
-            return False            # compressive (or unchecked) state: advective-form RHS, which has no fused stage
-        return _all_clean(*sds)
+        for sd in sds:
+            if sd is not None:
+                for c in sd._cached()[0]:
+                    if not c._soln or not c._clean:
+                        return False    # compressive / unchecked state (advective-form RHS: no fused stage), or junk outside the mask
+        return True
 
     def _stage_fused(self, kind, state_in, start, out, dt_step, deriv1=None, k_out=None, total=None, wdiv=1., first=0, last=0):
         """out = stage(kind)(start, RHS(state_in)[, deriv1]) with the derivative consumed in registers
-        (include/ddl.h: ddl_rhs_stage); k_out: also store it (a later stage needs it)."""
+        (include/ddl.h: ddl_rhs_stage); k_out: also store it (a later stage needs it).  The argument block of a call site
+        (pointer lists, the ddl_stage_fuse struct) is built once and reused: only the step sizes change from call to call."""
         R = self.RHS
-        coeff, order = self._coeff
-        keep = [_lib.ptr_array(_kspace_tensors(start)), _lib.ptr_array(_kspace_tensors(out))]
-        opt = []
-        for sd in (total, deriv1, k_out):
-            if sd is None:
-                opt.append(None)
-            else:
-                arr = _lib.ptr_array(_kspace_tensors(sd))
-                keep.append(arr)
-                opt.append(C.cast(arr, C.c_void_p))
-        fuse = _lib.StageFuse(C.cast(keep[0], C.c_void_p), opt[0], C.cast(keep[1], C.c_void_p), C.cast(coeff, C.c_void_p),
-                              int(order), int(first), int(last), float(wdiv), float(dt_step), int(kind), 0, opt[1], opt[2])
-        R._fused_rhs(state_in, None, R._rhs_flags(), fuse=fuse)
-        for sd in (out, total, k_out):
+        key = (kind, id(state_in), id(start), id(out), id(deriv1), id(k_out), id(total), first, last)
+        cache = self.__dict__.setdefault("_fuse_cache", {})
+        ent = cache.get(key)
+        if ent is None or ent[1] is not self._coeff:
+            coeff, order = self._coeff
+            opt = [None if sd is None else _kspace_ptrs(sd)[1] for sd in (total, deriv1, k_out)]
+            fuse = _lib.StageFuse(_kspace_ptrs(start)[1], opt[0], _kspace_ptrs(out)[1], C.cast(coeff, C.c_void_p),
+                                  int(order), int(first), int(last), float(wdiv), float(dt_step), int(kind), 0, opt[1], opt[2])
+            marks = [sd for sd in (out, total, k_out) if sd is not None]
+            # the StateData objects are kept alive with the entry: their ids are the key
+            ent = cache[key] = (fuse, self._coeff, marks, (state_in, start, out, deriv1, k_out, total))
+        fuse, _, marks, _ = ent
+        fuse.wdiv, fuse.dt_step = float(wdiv), float(dt_step)
+        for sd in (start, out, total, deriv1, k_out):
             if sd is not None:
-                _mark(sd, True)
+                _kspace_tensors(sd)                 # everything in k-space (no-ops in steady state)
+        R._fused_rhs(state_in, None, R._rhs_flags(), fuse=fuse)
+        for sd in marks:
+            _mark(sd, True)
         _inherit(out, start)
         if k_out is not None:
             k_out.set_time(state_in.time)

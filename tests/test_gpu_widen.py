@@ -457,3 +457,32 @@ def test_xfused_launch_variants_agree(physics, shape):
         L.set_option("xfused_variant", 0)
     for o in out[1:]:
         assert rel(o, out[0]) < 1e-14
+
+
+@pytest.mark.parametrize("physics,shape", [("BoussinesqHydro", (16, 16, 16)), ("IncompressibleMHD", (16, 16, 16)), ("IncompressibleHydro", (32, 32))])
+def test_caller_written_states_reach_the_fused_stage_path(physics, shape):
+    """After the first (unfused) step every stage of a solenoidal, dealiased run is ONE ddl_rhs_stage call -- also for states
+    the caller wrote, scalar components included (a temperature field has no divergence verdict to wait for)."""
+    import torch
+    import dedalus._lib as L
+    import dedalus.time_stepping.api as tapi
+    P = dev_physics(physics, shape, None, dict(nu=1e-3))
+    data = P.create_fields(0.)
+    rng = np.random.default_rng(0)
+    for _, f in data:
+        for _, c in f:
+            c["xspace"] = torch.from_numpy(rng.standard_normal(shape))
+            c["kspace"]
+        if f.ncomp > 1:
+            f.div_free()
+    ti = tapi.RK4(P)
+    ti.do_advance(data, 1e-3)
+    n0 = L.launch_count()
+    ti.do_advance(data, 1e-3)
+    per_step = L.launch_count() - n0
+    n0 = L.launch_count()
+    ti.fuse_stages = False
+    ti.do_advance(data, 1e-3)
+    unfused = L.launch_count() - n0
+    assert all(c._soln is True and c._clean for c in data.comp_list())
+    assert per_step < unfused and per_step <= 4 * (6 if len(shape) == 3 else 4)
