@@ -349,7 +349,7 @@ class Physics(object):
                                   flags & ~_lib.RHS_ZERO_FILL, C.byref(fuse), _plan.current_stream()))
         else:
             w = pl.rhs_workspace(self._physics_id)
-            check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), _lib.ptr_array(state), _lib.ptr_array(out),
+            check(lib.ddl_rhs(pl.handle, self._physics_id, C.byref(pp), data._cached()[3], deriv._cached()[3],
                               w.data_ptr(), w.numel(), flags, _plan.current_stream()))
         if deriv is not None:
             for c in deriv.comp_list():

@@ -385,12 +385,11 @@ class TimeStepBase(object):
     def _stage(self, kind, start, out, d1, d2, if_from, dt):
         if getattr(self.RHS, "_dynamic_k", False):
             return self._stage_tensor(kind, start, out, d1, d2, if_from, dt)
-        s, o, a = _kspace_tensors(start), _kspace_tensors(out), _kspace_tensors(d1)
-        b = _kspace_tensors(d2) if d2 is not None else None
+        s, o, a = _kspace_ptrs(start)[0], _kspace_ptrs(out)[0], _kspace_ptrs(d1)[0]
+        b = _kspace_ptrs(d2)[0] if d2 is not None else None
         coeff, order = _if_coefficients(if_from)
         clean = _all_clean(start, out, d1, d2)
-        check(lib.ddl_stage(_plan_of(start).handle, kind, len(s), _lib.ptr_array(s), _lib.ptr_array(o),
-                            _lib.ptr_array(a), _lib.ptr_array(b) if b is not None else None, coeff, order,
+        check(lib.ddl_stage(_plan_of(start).handle, kind, len(s), s, o, a, b, coeff, order,
                             float(dt), _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
         _mark(out, clean)
         _inherit(out, start)
@@ -495,12 +494,11 @@ class RK4(RKBase):
 
     def _rk4(self, y, out, wdiv, dt_step, first, last):
         pl = _plan_of(y)
-        ys, ks = _kspace_tensors(y), _kspace_tensors(self.k_data)
-        ts, os_ = _kspace_tensors(self.total_deriv), _kspace_tensors(out)
+        ys, ks = _kspace_ptrs(y)[0], _kspace_ptrs(self.k_data)[0]
+        ts, os_ = _kspace_ptrs(self.total_deriv)[0], _kspace_ptrs(out)[0]
         coeff, order = self._coeff
         clean = _all_clean(y, self.k_data, self.total_deriv, out)
-        check(lib.ddl_rk4_stage(pl.handle, len(ys), _lib.ptr_array(ys), _lib.ptr_array(ks), _lib.ptr_array(ts),
-                                _lib.ptr_array(os_), coeff, order, float(wdiv), float(dt_step), int(first), int(last),
+        check(lib.ddl_rk4_stage(pl.handle, len(ys), ys, ks, ts, os_, coeff, order, float(wdiv), float(dt_step), int(first), int(last),
                                 _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
         _mark(out, clean)
         _mark(self.total_deriv, clean)
