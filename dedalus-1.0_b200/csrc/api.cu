@@ -1163,6 +1163,16 @@ static int invariants_t(ddl_plan* pl, void* const* state, int flags, double* out
     return launch_reduce<InvariantsF<ND, NB>, RED_SUM>(f, count, pl->red_partial, out, 0, st, "invariants");
 }
 
+extern "C" int ddl_reduce_outside_mask(ddl_plan* pl, int n, void* const* arrays, double* out, void* stream) {
+    if (!pl || !arrays || !out) { set_error("ddl_reduce_outside_mask: NULL argument"); return -1; }
+    if (n < 1 || n > DDL_MAXC) { set_error("ddl_reduce_outside_mask: %d arrays (1..%d)", n, DDL_MAXC); return -1; }
+    OutsideF f;
+    memset(&f, 0, sizeof(f));
+    f.g = pl->geom; f.narr = n;
+    for (int i = 0; i < n; ++i) f.arr[i] = (const cplx*)arrays[i];
+    return launch_reduce<OutsideF, RED_SUM>(f, pl->nmodes, pl->red_partial, out, 0, (ddl_stream_t)stream, "outside_mask");
+}
+
 extern "C" int ddl_reduce_invariants(ddl_plan* pl, int physics, void* const* state, int flags, double* out, void* stream) {
     static_assert(DDL_NINV == DDL_NINV_, "include/ddl.h and reduce.cuh disagree on the invariant count");
     ddl_stream_t st = (ddl_stream_t)stream;

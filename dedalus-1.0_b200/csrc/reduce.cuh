@@ -100,6 +100,28 @@ int launch_reduce(const F& f, long long count, double* partial, double* out, int
     return 0;
 }
 
+// number of non-zero entries OUTSIDE the dealias mask, per array (ddl_reduce_outside_mask): the check that lets a buffer the
+// caller has written regain its "zero outside the mask" status (retained-modes-only sweeps, fused stage kernel); reads the
+// masked-out entries only
+struct OutsideF {
+    static constexpr int NR = DDL_MAXC;
+    KGeom g;
+    const cplx* arr[DDL_MAXC];
+    int narr;
+    DDL_HD void operator()(long long i, double* acc) const {
+        int ia, ib, ic;
+        split3(i, g.dim, ia, ib, ic);
+        bool keep = g.keep[1][ib] && g.keep[2][ic];
+        if (g.keep[0]) keep = keep && g.keep[0][ia];
+        if (!keep) {
+            for (int f = 0; f < narr; ++f) {
+                const cplx v = arr[f][i];
+                if (v.x != 0.0 || v.y != 0.0) acc[f] += 1.0;          // NaN counts
+            }
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // Spectral invariants of one state (indices: include/ddl.h DDL_INV_*).  ND = 2 / 3; the state is
 // u (ND components) followed by NB components of a second group: 0 (hydro), 1 (T), ND (B).

@@ -17,7 +17,7 @@ EXPORTS = [
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
     "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count",
-    "ddl_reduce_invariants", "ddl_reduce_max_square", "ddl_rhs_capture_max", "ddl_set_shear", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_reduce_invariants", "ddl_reduce_outside_mask", "ddl_reduce_max_square", "ddl_rhs_capture_max", "ddl_set_shear", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
@@ -70,6 +70,7 @@ def bind_slab(lib):
     lib.ddl_reduce_invariants.argtypes = [vp, i32, vp, i32, vp, vp]
     lib.ddl_reduce_max_square.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, i32, vp, vp]
     lib.ddl_rhs_capture_max.argtypes = [vp, vp]
+    lib.ddl_reduce_outside_mask.argtypes = [vp, i32, vp, vp, vp]
     lib.ddl_dealias_array.argtypes = [i32, vp, vp, vp, vp, vp, i32, vp, vp]
     lib.ddl_step_array.argtypes = [i32, i32, C.c_longlong, vp, vp, vp, vp, vp, C.c_double, vp]
     lib.ddl_set_shear.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double]

@@ -262,21 +262,7 @@ class FourierRepresentation(Representation):
         its state) keep the full sweeps.  The verdict is cached until the next hand-out."""
         if self._clean or self._checked or self._curr_space != "kspace":
             return self._clean
-        pl = self._plan
-        dirty = torch.zeros((), dtype=torch.bool, device=self._k.device)
-        for name, keep in pl.keep_np.items():
-            axis = self.ktrans[name]
-            if axis == 0 and pl.nranks > 1:
-                keep = keep[pl.krows]
-            idx = np.nonzero(~keep)[0]
-            if len(idx):
-                sel = self._k.index_select(axis, torch.as_tensor(idx, device=self._k.device))
-                dirty |= (sel != 0).any()
-        # deliberately rank-local (no collective): ranks may disagree (one of them printed a mode, say) and
-        # then take different local tails (mask / full sweep vs fused sweep); the exchange sequence of the
-        # RHS pipeline is the same on every path, so that is safe - a collective here could deadlock
-        self._clean = not bool(dirty.item())
-        self._checked = True
+        verify_clean_many([self])
         return self._clean
 
     def zero_nyquist(self):
@@ -380,6 +366,27 @@ class FourierRepresentation(Representation):
         """Write the current data into an h5py-like dataset (representations.py:511-526)."""
         dataset[:] = self.data.cpu().numpy()
         dataset.attrs["space"] = self._curr_space
+
+
+def verify_clean_many(comps):
+    """verify_clean for several components of one plan with ONE device pass per eight of them and one host read
+    (include/ddl.h: ddl_reduce_outside_mask)."""
+    todo = [c for c in comps if not c._clean and not c._checked and c._curr_space == "kspace" and c._static_k]
+    for i in range(0, len(todo), 8):
+        group = todo[i:i + 8]
+        pl = group[0]._plan
+        out = torch.zeros(8, dtype=torch.float64, device=group[0]._k.device)
+        arr = (C.c_void_p * len(group))(*[c._k.data_ptr() for c in group])
+        check(lib.ddl_reduce_outside_mask(pl.handle, len(group), arr, out.data_ptr(), _plan.current_stream()))
+        # deliberately rank-local (no collective): ranks may disagree (one of them printed a mode, say) and then take
+        # different local tails (mask / full sweep vs fused sweep); the exchange sequence of the RHS pipeline is the same
+        # on every path, so that is safe - a collective here could deadlock
+        counts = out.cpu().tolist()
+        for c, n in zip(group, counts):
+            c._clean = not (n > 0 or n != n)
+            c._checked = True
+            if c._sphere is not None and c._clean:
+                c._clean = not bool((c._k[c._sphere] != 0).any().item())      # '2/3 spherical': the bounding cube is not enough
 
 
 class FourierShearRepresentation(FourierRepresentation):

@@ -76,11 +76,15 @@ def _settle(sd, R=None):
     object, their fields' 'solenoidal' verdict (Physics.verify_solenoidal): both decide which kernels run."""
     if R is not None and getattr(R, "_unfused", False):
         return                      # shearing box: no fused kernels to choose between
+    todo = None
     for c in sd._cached()[0]:
         if c._curr_space != "kspace":
             c.require_space("kspace")
         if not c._clean and not c._checked:
-            c.verify_clean()
+            todo = True
+    if todo:
+        from ..data_objects.representations import verify_clean_many
+        verify_clean_many(sd._cached()[0])          # one device pass and one host read for the whole state
     if R is not None and hasattr(R, "verify_solenoidal"):
         R.verify_solenoidal(sd)
 

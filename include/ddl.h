@@ -275,6 +275,12 @@ enum {
 };
 int ddl_reduce_invariants(ddl_plan* plan, int physics, void* const* state, int flags, double* out, void* stream);
 
+/* out[i] (device, 8 doubles) = number of non-zero entries of k-space array i (n <= 8) OUTSIDE the plan's dealias mask.  The
+ * reference never knows whether a spectrum is dealiased and masks on every transform (representations.py:344,353); here a buffer
+ * that IS zero out there takes the retained-modes-only sweeps and the fused stage kernel, and this one read-only pass over the
+ * masked-out entries re-establishes that knowledge for buffers the caller has written. */
+int ddl_reduce_outside_mask(ddl_plan* plan, int n, void* const* arrays, double* out, void* stream);
+
 /* CFL capture: the only place where u(x), B(x) exist is inside the x pass of the RHS, so the
  * maxima the time-step limit needs are reduced THERE.  While out2 (device, 2 doubles, zeroed by
  * the caller) is set, every x pass of ddl_rhs / ddl_rhs_stage / ddl_slab_xfused* on this plan does

@@ -288,3 +288,27 @@ def test_emulated_dealias_array_matches_reference_cython(lib, nd, branch):
     want = z[p + branch]
     assert np.array_equal(data, want)
     assert 0 < (want == 0).sum() < want.size
+
+
+@pytest.mark.parametrize("shape", [(16, 32), (8, 16, 16), (12, 20, 24)])
+def test_emulated_outside_mask_count(lib, shape):
+    """ddl_reduce_outside_mask: non-zero entries outside the dealias mask, per array (the check behind verify_clean)."""
+    import ctypes as C
+    g = orc.Grid(shape)
+    pl = emul.EmulPlan(lib, g)
+    rng = np.random.default_rng(2)
+    mask = g.dealias_mask()
+    clean = rng.standard_normal(g.kshape) + 1j * rng.standard_normal(g.kshape)
+    clean[mask] = 0.0
+    junk = clean.copy()
+    idx = np.argwhere(mask)[::7]
+    junk[tuple(idx.T)] = 1e-300                       # tiny, but not zero
+    nan = clean.copy()
+    nan[tuple(np.argwhere(mask)[0])] = np.nan
+    arrays = [np.ascontiguousarray(a) for a in (clean, junk, nan, clean * 2)]
+    out = np.full(8, -1.0)
+    lib.ddl_reduce_outside_mask.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+    assert lib.ddl_reduce_outside_mask(pl.plan, len(arrays), ptrs, out.ctypes.data_as(C.c_void_p), None) == 0, lib.ddl_last_error()
+    assert out[:4].tolist() == [0.0, float(len(idx)), 1.0, 0.0]
+    assert all(np.array_equal(a, b) for a, b in zip(arrays, (clean, junk, nan, clean * 2)) if not np.isnan(a).any())
