@@ -180,8 +180,14 @@ class Physics(object):
 
     @staticmethod
     def _finish_maxima(out):
-        from ..utils.parallelism import reduce_max
-        return (reduce_max(out[0], reduce_all=True), reduce_max(out[1], reduce_all=True))
+        """(max u^2, max B^2) over all ranks from the two device values: one all-reduce, one 16-byte host read."""
+        from ..utils.parallelism import com_sys
+        if com_sys.comm is not None:
+            import torch.distributed as dist
+            out = out.clone()
+            dist.all_reduce(out, op=dist.ReduceOp.MAX)
+        a, b = out.cpu().tolist()
+        return (a, b)
 
     def capture_begin(self, data):
         """Ask the x passes of the following RHS evaluations to maximise u_i(x)^2 / B_i(x)^2 into a
