@@ -1,0 +1,27 @@
+#!/bin/bash
+# First GPU call of round 2 (run under gpurun, ~10 minutes):  gpurun --timeout 1500 -- 'bash profiles/round2_first_call.sh'
+# Everything built after the last full GPU test run of round 1 gets its first device run here; outputs land in gpurun_out/.
+#   1. the native checker (3 s): device-only parts, one-to-one kernels, shearing-box transform, timing sweep incl. rhs_plane_chunk
+#   2. pytest -m gpu (ordered: what has passed on a B200 first), without -x so that one surprise does not hide the rest
+#   3. bench.py (headline line), then the widened-config timings and the 2-D eager / graph step times
+set -u
+mkdir -p gpurun_out
+export LD_LIBRARY_PATH=$(python - <<'PY'
+import os
+try:
+    import nvidia.cuda_runtime as m
+    print(os.path.join(list(m.__path__)[0], "lib"))
+except Exception:
+    print("/usr/local/cuda/lib64")
+PY
+):/usr/local/cuda/lib64:${LD_LIBRARY_PATH:-}
+tests/native/_build/devcheck 128 512 gpurun_out/devcheck_r2.txt reps=5 > gpurun_out/devcheck_r2.log 2>&1
+tail -25 gpurun_out/devcheck_r2.txt
+python -m pytest tests -q -m gpu -p no:cacheprovider --durations=15 > gpurun_out/pytest_gpu_r2.log 2>&1
+tail -30 gpurun_out/pytest_gpu_r2.log
+python bench.py > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.err
+tail -c 1500 gpurun_out/bench_r2.json
+python profiles/widened_configs.py > gpurun_out/widened_r2.jsonl 2>&1
+cat gpurun_out/widened_r2.jsonl
+python profiles/small_grids.py > gpurun_out/small_grids_r2.log 2>&1
+tail -8 gpurun_out/small_grids_r2.log
