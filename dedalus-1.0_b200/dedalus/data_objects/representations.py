@@ -486,3 +486,7 @@ class FourierShearRepresentation(FourierRepresentation):
 
     def _hermitian_project(self):
         raise NotImplementedError("FourierShearRepresentation: not on the fused path")
+
+
+class ChebyshevRepresentation(FourierRepresentation):
+    """Placeholder of the reference (representations.py:743-744: `class ChebyshevRepresentation(FourierRepresentation): pass`)."""
