@@ -96,3 +96,38 @@ def swap_indices(arr):
         raise NotImplementedError("swap_indices only implemented for numpy arrays and lists.")
     out[0], out[1] = out[1], out[0]
     return out
+
+
+def load_all(field, snap_dir):
+    """Concatenate every rank's part of one field component of a snapshot into a single array for analysis (reference:
+    parallelism.py:54-100): `field` like 'u/0' or '/fields/u/0'; returns (data, space) with the reference's conventions --
+    parts joined along axis 0, then axes 0 and 1 swapped (3-D).  Reads the HDF5 files when h5py is importable and they
+    exist, else the .npy + JSON fallback TimeStepBase.snapshot writes (block ky ownership)."""
+    import glob
+    import json
+    import os
+    name = field[len("/fields/"):] if field.startswith("/fields/") else field
+    h5 = sorted(glob.glob(os.path.join(snap_dir, "data.cpu*")))
+    parts, space = [], None
+    if h5:
+        import h5py
+        for fn in h5:
+            with h5py.File(fn, "r") as fi:
+                dset = fi["/fields/" + name]
+                space = dset.attrs["space"]
+                parts.append(np.asarray(dset[...]))
+        if isinstance(space, bytes):
+            space = space.decode()
+    else:
+        for fn in sorted(glob.glob(os.path.join(snap_dir, "fields.cpu*.json"))):
+            with open(fn) as f:
+                meta = json.load(f)
+            entry = meta["fields"][name]
+            space = entry["space"]
+            parts.append(np.load(os.path.join(snap_dir, entry["file"])))
+    if not parts:
+        raise IOError("no snapshot data in %s" % snap_dir)
+    data = np.concatenate(parts, axis=0)
+    if data.ndim == 3:
+        data = np.transpose(data, axes=[1, 0, 2])
+    return data, space

@@ -105,6 +105,21 @@ def test_snapshot_in_x_space_restores_the_space(tmp_path, monkeypatch):
     assert np.array_equal(d2["u"]["x"]["xspace"].cpu().numpy(), x)
 
 
+def test_load_all_reads_a_snapshot(tmp_path, monkeypatch):
+    """load_all (parallelism.py:54-100): one component of a snapshot as a single array, axes 0 and 1 swapped in 3-D."""
+    from dedalus.mods import IncompressibleMHD, FourierRepresentation, RK2mid
+    from dedalus.utils.api import load_all
+    monkeypatch.chdir(tmp_path)
+    P = IncompressibleMHD((8, 16, 16), FourierRepresentation)
+    data = noise_state(P, (8, 16, 16), 3)
+    RK2mid(P).snapshot(data)
+    arr, space = load_all("B/1", "snap_00000")
+    want = data["B"][1]["kspace"].cpu().numpy()
+    assert space == "kspace" and np.array_equal(arr, np.transpose(want, [1, 0, 2]))
+    arr2, _ = load_all("/fields/u/0", "snap_00000")
+    assert arr2.shape == (8, 16, 9)
+
+
 def test_restart_in_a_shearing_box(tmp_path, monkeypatch):
     """The drifting wavenumbers are rebuilt from the restored time (state_data.py:115-121 on load)."""
     import torch
