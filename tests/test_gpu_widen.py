@@ -486,3 +486,36 @@ def test_caller_written_states_reach_the_fused_stage_path(physics, shape):
     unfused = L.launch_count() - n0
     assert all(c._soln is True and c._clean for c in data.comp_list())
     assert per_step < unfused and per_step <= 4 * (6 if len(shape) == 3 else 4)
+
+
+@pytest.mark.parametrize("integ,nstages", [("RK2mid", 2), ("RK2trap", 2), ("RK4", 4), ("CrankNicholsonVisc", 1)])
+@pytest.mark.parametrize("shape", [(32, 32), (16, 16, 16)])
+@pytest.mark.parametrize("physics", ["IncompressibleHydro", "BoussinesqHydro", "IncompressibleMHD"])
+def test_steady_state_launch_counts(physics, shape, integ, nstages):
+    """Every physics class x dimension x integrator settles on the minimal launch sequence: per stage the passes of the
+    transform pipeline (z, y, x, y, z in 3-D; y, x, y in 2-D) and ONE fused assembly + stage-update kernel; a CFL-controlled
+    step (dt taken from its own first RHS evaluation) costs exactly one launch more."""
+    import torch
+    import dedalus._lib as L
+    import dedalus.time_stepping.api as tapi
+    P = dev_physics(physics, shape, None, dict(nu=1e-3))
+    data = P.create_fields(0.)
+    rng = np.random.default_rng(0)
+    for _, f in data:
+        for _, c in f:
+            c["xspace"] = torch.from_numpy(rng.standard_normal(shape))
+            c["kspace"]
+        if f.ncomp > 1:
+            f.div_free()
+    ti = getattr(tapi, integ)(P, CFL=0.3)
+    ti.save_cadence, ti.max_save_period, ti.iteration = 10 ** 9, 1e300, 1
+    for _ in range(2):
+        ti.do_advance(data, 1e-3)
+    n0 = L.launch_count()
+    ti.do_advance(data, 1e-3)
+    fixed = L.launch_count() - n0
+    n0 = L.launch_count()
+    ti.advance(data)
+    lazy = L.launch_count() - n0
+    assert fixed == (6 if len(shape) == 3 else 4) * nstages
+    assert lazy == fixed + 1
