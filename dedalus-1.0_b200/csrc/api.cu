@@ -1244,6 +1244,18 @@ extern "C" int ddl_stage(ddl_plan* pl, int kind, int ncomp, void* const* start, 
     return launch_items(f, count, (ddl_stream_t)stream, "stage");
 }
 
+// kind: DDL_EULER .. DDL_ETD2RK2, DDL_FUSE_RK4, DDL_FUSE_CN (the kinds of ddl_rhs_stage)
+extern "C" int ddl_stage_outside(ddl_plan* pl, int kind, int ncomp, void* const* start, void* const* out, const double* coeff,
+                                 int visc_order, double dt, void* stream) {
+    OutsideStageF f;
+    long long count;
+    DDL_TRY(fill_stage(pl, f.a, ncomp, coeff, visc_order, 0, count));
+    if (kind < DDL_EULER || kind > DDL_FUSE_CN) { set_error("bad stage kind %d", kind); return -1; }
+    f.a.kind = kind; f.a.dt = dt; f.a.wdiv = 1.0;
+    for (int c = 0; c < ncomp; ++c) { f.a.start[c] = (const cplx*)start[c]; f.a.out[c] = (cplx*)out[c]; }
+    return launch_items(f, count, (ddl_stream_t)stream, "stage_outside");
+}
+
 extern "C" int ddl_rk4_stage(ddl_plan* pl, int ncomp, void* const* y, void* const* k, void* const* total, void* const* out,
                              const double* coeff, int visc_order, double wdiv, double dt_step, int first, int last,
                              int flags, void* stream) {

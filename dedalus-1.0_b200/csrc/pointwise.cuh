@@ -212,6 +212,34 @@ struct DealiasArrayF {
     }
 };
 
+// The stage update at the modes OUTSIDE the dealias mask, where every derivative of the fused pipeline vanishes: what a state
+// that carries content there (hydro never dealiases its state, SURVEY F7: the Nyquist-row entries of the reference's 2-D
+// Taylor-Green field) still has to undergo -- the integrating factor alone.  Same arithmetic as StageF with d1 = d2 = 0, so
+// the result equals the full sweep's bit for bit; touches the masked-out entries only.
+struct OutsideStageF {
+    StageArgs a;
+    DDL_HD void operator()(long long i) const {
+        int ia, ib, ic;
+        split3(i, a.g.dim, ia, ib, ic);
+        bool keep = a.g.keep[1][ib] && a.g.keep[2][ic];
+        if (a.g.keep[0]) keep = keep && a.g.keep[0][ia];
+        if (keep) return;
+        const double pw = ipow(ksq(a.g, ia, ib, ic), a.vo);
+        const cplx zero = mk(0.0, 0.0);
+        for (int c = 0; c < a.ncomp; ++c) {
+            const double co = a.coeff[c];
+            double Z = 0.0, f0 = 1.0, f1 = 1.0, f2 = 0.5;
+            if (a.kind != SK_EULER) {
+                Z = -(co * pw) * a.dt;
+                if (Z != 0.0 && a.kind != SK_CN) phi_funcs(Z, a.g.twod, f0, f1, f2);
+            }
+            cplx tot = zero;
+            a.out[c][i] = stage_apply(a.kind, a.start[c][i], zero, zero, a.kind == SK_RK4 ? &tot : nullptr, 1, 1, a.wdiv, Z, f0, f1, f2,
+                                      a.dt, co * pw);
+        }
+    }
+};
+
 // zero the masked-out modes of up to DDL_MAXF arrays, touching only those entries
 struct MaskF {
     KGeom g;

@@ -21,7 +21,7 @@ _PHYSICS_OF = {("u",): _lib.HYDRO, ("u", "T"): _lib.BOUSSINESQ, ("u", "B"): _lib
 _shared = {"on": False, "key": None, "val": None}     # one sweep per VolumeAverageSet.run()
 
 
-def invariants(data):
+def invariants(data, retained_only=None):
     """(total, local): the DDL_INV_* vector of `data` summed over ranks, and this rank's own part
     (the reference's divergence_sum / mag_div_sum / vort_cenk are rank-local), as numpy arrays;
     None when `data` is not a standard u [+ T | B] state."""
@@ -31,7 +31,7 @@ def invariants(data):
     comps = [c for _, _, c in data.components()]
     if not comps[0]._static_k:
         return None             # shearing box: the sweep's wavenumber tables are static; tensor-level route
-    key = (id(data), data.time, tuple(c._k.data_ptr() for c in comps))
+    key = (id(data), data.time, tuple(c._k.data_ptr() for c in comps), retained_only)
     if _shared["on"] and _shared["key"] == key:
         return _shared["val"]
     state = []
@@ -40,7 +40,8 @@ def invariants(data):
         state.append(c._k)
     pl = comps[0]._plan
     out = torch.empty(_lib.NINV, dtype=torch.float64, device=pl.device)
-    flags = _lib.STAGE_RETAINED_ONLY if all(c._clean for c in comps) else 0
+    # retained_only=True: the sums over the modes inside the dealias mask whatever lies outside (what the fused pipeline sees)
+    flags = _lib.STAGE_RETAINED_ONLY if (retained_only or all(c._clean for c in comps)) else 0
     check(lib.ddl_reduce_invariants(pl.handle, pid, _lib.ptr_array(state), flags, out.data_ptr(), _plan.current_stream()))
     local = out.cpu().numpy()
     total = local

@@ -57,8 +57,12 @@ def _all_clean(*sds):
 
 
 def _mark(sd, clean):
+    """Record what a kernel of ours left in `sd`: zero outside the mask, or (computed from operands that were not) content
+    there -- a known status either way, so no device check is needed before the next step."""
     for c in sd._cached()[0]:
         c._clean = clean
+        if not clean:
+            c._checked = True
 
 
 def _inherit(out, start):
@@ -324,10 +328,13 @@ class TimeStepBase(object):
     # ---- stage update fused with the spectral assembly of the RHS --------------------------
     fuse_stages = True      # set False to force the unfused RHS + stage-kernel path (tests compare both)
 
-    def _can_fuse(self, *sds):
+    def _can_fuse(self, derivs, states):
         """ddl_rhs_stage applies: nothing else touches deriv (rotation, forcing, aux equations), the
-        integrating-factor coefficients are known (after the first unfused step), and every operand
-        vanishes outside the dealias mask (the fused sweep visits the retained modes only)."""
+        integrating-factor coefficients are known (after the first unfused step), the state is solenoidal (else the
+        advective-form RHS, which has no fused stage) and every operand vanishes outside the dealias mask (the fused sweep
+        visits the retained modes only).  The one exception to the last rule: `states` (the evolving state and the stage
+        states built from it) of a physics without linear terms out there may carry content outside the mask (hydro never
+        dealiases its state) -- _stage_fused then updates those entries with ddl_stage_outside."""
         R = self.RHS
         if not self.fuse_stages or getattr(self, "_coeff", None) is None or not hasattr(R, "_fused_rhs"):
             return False
@@ -335,11 +342,17 @@ class TimeStepBase(object):
             return False
         if R.aux_eqns or not R.can_fuse_stage():
             return False
-        for sd in sds:
-            if sd is not None:
-                for c in sd._cached()[0]:
-                    if not c._soln or not c._clean:
-                        return False    # compressive / unchecked state (advective-form RHS: no fused stage), or junk outside the mask
+        for sd in derivs:
+            for c in sd._cached()[0]:
+                if not c._soln or not c._clean:
+                    return False
+        junk_ok = getattr(R, "_junk_keeps_fused", False)
+        for sd in states:
+            for c in sd._cached()[0]:
+                if not c._soln:
+                    return False
+                if not c._clean and not (junk_ok and c._checked):
+                    return False
         return True
 
     def _stage_fused(self, kind, state_in, start, out, dt_step, deriv1=None, k_out=None, total=None, wdiv=1., first=0, last=0):
@@ -364,8 +377,17 @@ class TimeStepBase(object):
             if sd is not None:
                 _kspace_tensors(sd)                 # everything in k-space (no-ops in steady state)
         R._fused_rhs(state_in, None, R._rhs_flags(), fuse=fuse)
+        junk = not _all_clean(start)
+        if junk and not (kind == _lib.ETD2RK1 and out is start):
+            # content outside the mask (_can_fuse admitted it): the integrating factor alone acts there
+            coeff, order = self._coeff
+            check(lib.ddl_stage_outside(_plan_of(start).handle, int(kind), len(start._cached()[0]), _kspace_ptrs(start)[0],
+                                        _kspace_ptrs(out)[0], coeff, int(order), float(dt_step), _plan.current_stream()))
         for sd in marks:
             _mark(sd, True)
+        if junk:
+            for c in out._cached()[0]:
+                c._clean, c._checked = False, True
         _inherit(out, start)
         if k_out is not None:
             k_out.set_time(state_in.time)
@@ -424,7 +446,7 @@ class RK2mid(RKBase):
         _settle(data, self.RHS)
         data2, k1, k2 = self.data2, self.deriv1, self.deriv2
         lazy = dt is None
-        if not lazy and self._can_fuse(data, data2, k1):
+        if not lazy and self._can_fuse((k1,), (data, data2)):
             self._stage_fused(_lib.ETD1, data, data, data2, dt / 2., k_out=k1)              # k1 kept for the second stage
             data2.set_time(data.time + dt / 2.)
             self._stage_fused(_lib.ETD2RK2, data2, data, data, dt, deriv1=k1)               # k2 never stored
@@ -440,7 +462,7 @@ class RK2mid(RKBase):
             self._coeff = _if_coefficients(k1)
         self._stage(_lib.ETD1, data, data2, k1, None, k1, dt / 2.)        # a_n (euler where IF is None)
         data2.set_time(data.time + dt / 2.)
-        if lazy and self._can_fuse(data, data2, k1):
+        if lazy and self._can_fuse((k1,), (data, data2)):
             self._stage_fused(_lib.ETD2RK2, data2, data, data, dt, deriv1=k1)
         else:
             self.RHS.RHS(data2, k2)
@@ -462,7 +484,7 @@ class RK2trap(RKBase):
         _settle(data, self.RHS)
         k1, k2 = self.deriv1, self.deriv2
         lazy = dt is None
-        if not lazy and self._can_fuse(data, k1):
+        if not lazy and self._can_fuse((k1,), (data,)):
             self._stage_fused(_lib.ETD1, data, data, data, dt, k_out=k1)
             data.set_time(data.time + dt)
             self._stage_fused(_lib.ETD2RK1, data, data, data, dt, deriv1=k1)
@@ -477,7 +499,7 @@ class RK2trap(RKBase):
             self._coeff = _if_coefficients(k1)
         self._stage(_lib.ETD1, data, data, k1, None, k1, dt)
         data.set_time(data.time + dt)
-        if lazy and self._can_fuse(data, k1):
+        if lazy and self._can_fuse((k1,), (data,)):
             self._stage_fused(_lib.ETD2RK1, data, data, data, dt, deriv1=k1)
         else:
             self.RHS.RHS(data, k2)
@@ -502,10 +524,13 @@ class RK4(RKBase):
         ts, os_ = _kspace_ptrs(self.total_deriv)[0], _kspace_ptrs(out)[0]
         coeff, order = self._coeff
         clean = _all_clean(y, self.k_data, self.total_deriv, out)
+        # what the sweep leaves outside the mask: total = [total +] k / w is zero there when its operands are; out = S(y, .) when y is too
+        tot_clean = _all_clean(self.k_data) and (bool(first) or _all_clean(self.total_deriv))
+        out_clean = tot_clean and _all_clean(y)
         check(lib.ddl_rk4_stage(pl.handle, len(ys), ys, ks, ts, os_, coeff, order, float(wdiv), float(dt_step), int(first), int(last),
                                 _lib.STAGE_RETAINED_ONLY if clean else 0, _plan.current_stream()))
-        _mark(out, clean)
-        _mark(self.total_deriv, clean)
+        _mark(self.total_deriv, tot_clean)
+        _mark(out, out_clean)
         _inherit(out, y)
 
     def _rk4_fused(self, state_in, y, out, wdiv, dt_step, first, last):
@@ -568,7 +593,7 @@ class RK4(RKBase):
             return self._advance_dynamic_k(data, dt)
         _settle(data, self.RHS)
         lazy = dt is None
-        if not lazy and self._can_fuse(data, self.total_deriv, self.temp_data):
+        if not lazy and self._can_fuse((self.total_deriv,), (data, self.temp_data)):
             return self._advance_fused(data, dt)
         aux = list(R.aux_eqns.values())
         a_old = [a.value for a in aux]
@@ -583,7 +608,7 @@ class RK4(RKBase):
                 ct.integrating_factor = ck.integrating_factor
         self._rk4(data, tmp, 6., dt / 2., True, False)     # total = k1/6 ; tmp = S(y, k1, dt/2)
         tmp.set_time(data.time + dt / 2.)
-        if lazy and self._can_fuse(data, self.total_deriv, tmp):
+        if lazy and self._can_fuse((self.total_deriv,), (data, tmp)):
             self._rk4_fused(tmp, data, tmp, 3., dt / 2., False, False)      # k2
             self._rk4_fused(tmp, data, tmp, 3., dt, False, False)           # k3
             tmp.set_time(data.time + dt)
@@ -640,7 +665,7 @@ class CrankNicholsonVisc(TimeStepBase):
             return
         _settle(data, self.RHS)
         lazy = dt is None
-        if not lazy and self._can_fuse(data):
+        if not lazy and self._can_fuse((), (data,)):
             self._stage_fused(_lib.FUSE_CN, data, data, data, dt)
             data.set_time(data.time + dt)
             self.time += dt

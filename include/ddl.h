@@ -240,6 +240,14 @@ int ddl_rhs_stage(ddl_plan* plan, int physics, const ddl_phys_params* params, vo
 int ddl_slab_assemble_stage(ddl_plan* plan, int physics, const ddl_phys_params* params, void* const* e_in,
                             void* const* state, const ddl_stage_fuse* fuse, void* stream);
 
+/* Companion of ddl_rhs_stage for a state that carries content OUTSIDE the dealias mask (hydro-type physics never dealias their
+ * state; the reference's 2-D Taylor-Green field has such entries): there every derivative of the fused pipeline
+ * vanishes and the update is the integrating factor alone, out = S(start, 0).  Same arithmetic as ddl_stage / ddl_rk4_stage /
+ * ddl_cn_step with zero derivatives (bit-identical to their full sweeps), over the masked-out entries only.  kind as in
+ * ddl_stage_fuse.  With it such states keep the fused stage kernel for their retained modes. */
+int ddl_stage_outside(ddl_plan* plan, int kind, int ncomp, void* const* start, void* const* out, const double* coeff,
+                      int visc_order, double dt, void* stream);
+
 /* restated CrankNicholsonVisc (time_step.py:486-506): y = (top/bottom) y + k / bottom */
 int ddl_cn_step(ddl_plan* plan, int ncomp, void* const* y, void* const* k, const double* coeff,
                 int visc_order, double dt, int flags, void* stream);
