@@ -56,6 +56,32 @@ def main(out_path):
         results.append({"physics": physics, "shape": shape, "dealiasing": dl, "rel": float(torch.sqrt(num[0] / num[1])),
                         "dt": float(dt_dev), "dt_oracle": float(dt_orc), "unfused": bool(P._unfused)})
         decfg.set("FFT", "dealiasing", "2/3 cython")
+    # a hydro state with an entry outside the dealias mask: fused stage kernel + ddl_stage_outside, rank-local
+    Po = oracle_physics("IncompressibleHydro", (16, 16, 32), None, dict(nu=0.05))
+    do = orc.synthetic_ic(Po, 8)
+    y0 = do.kvector()
+    y0[:, 7, 3, 2] = 0.3 - 0.1j
+    for j, (_, _, c) in enumerate(do.components()):
+        c.kdata[...] = y0[j]
+    P = dev_physics("IncompressibleHydro", (16, 16, 32), None, dict(nu=0.05))
+    data = P.create_fields(0.)
+    comps = [c for _, _, c in data.components()]
+    rows = comps[0].local_rows["kspace"]
+    for j, c in enumerate(comps):
+        c["kspace"] = torch.from_numpy(np.ascontiguousarray(y0[j][rows]))
+    ti, to = tapi.RK4(P), orc.RK4(Po)
+    for _ in range(3):
+        ti.do_advance(data, 5e-3)
+        to.do_advance(do, 5e-3)
+    y1 = do.kvector()
+    loc = np.stack([c["kspace"].cpu().numpy() for c in comps])
+    num = torch.tensor([np.linalg.norm(loc - y1[:, rows]) ** 2, np.linalg.norm(y1[:, rows]) ** 2], dtype=torch.float64, device=dev)
+    dist.all_reduce(num)
+    junk_here = torch.tensor([float(abs(loc[0][list(rows).index(7), 3, 2])) if 7 in list(rows) else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(junk_here)
+    results.append({"physics": "IncompressibleHydro", "shape": (16, 16, 32), "dealiasing": "junk", "rel": float(torch.sqrt(num[0] / num[1])),
+                    "dt": 1.0, "dt_oracle": 1.0, "unfused": bool(P._unfused), "junk_left": float(junk_here[0]),
+                    "fused_cached": len(getattr(ti, "_fuse_cache", {}))})
     # shearing box, slab-decomposed, against the oracle's restatement (pinned to the reference goldens by tests/test_oracle_shear.py)
     import dedalus.physics.api as papi
     from dedalus.data_objects.api import FourierShearRepresentation

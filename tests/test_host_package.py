@@ -76,8 +76,9 @@ def test_slab_unfused_and_odd_grids_under_host_emulation_gloo(world, layout, tmp
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:]
     res = json.load(open(out))
-    assert len(res) == 6 and [c["unfused"] for c in res] == [True, True, False, True, True, True]
-    assert all(c["rel_init"] < 1e-13 for c in res[3:])
+    assert len(res) == 7 and [c["unfused"] for c in res] == [True, True, False, False, True, True, True]
+    assert all(c["rel_init"] < 1e-13 for c in res[4:])
+    assert res[3]["junk_left"] > 0.05 and res[3]["fused_cached"] > 0       # the out-of-mask entry survives; the fused path ran
     for case in res:
         assert case["rel"] < 1e-10, case
         assert abs(case["dt"] - case["dt_oracle"]) < 1e-11 * case["dt_oracle"], case
