@@ -218,8 +218,8 @@ int ddl_rk4_stage(ddl_plan* plan, int ncomp, void* const* y, void* const* k, voi
  * written only if k_out is given.  kind: DDL_EULER / DDL_ETD1 (the derivative of this RHS is THE
  * derivative), DDL_ETD2RK1 / DDL_ETD2RK2 (it is the SECOND one; deriv1 holds the first),
  * DDL_FUSE_RK4 (ddl_rk4_stage semantics with total / wdiv / first / last), DDL_FUSE_CN.
- * Only valid when state, y, total, deriv1 vanish outside the dealias mask (what
- * DDL_STAGE_RETAINED_ONLY asserts): the sweep visits the retained modes only.
+ * The sweep visits the retained modes only: total, deriv1 and k_out must vanish outside the dealias mask (what
+ * DDL_STAGE_RETAINED_ONLY asserts); state / y may carry content out there, which ddl_stage_outside then updates.
  * ddl_slab_assemble_stage is the same tail for the slab phases. */
 enum { DDL_FUSE_RK4 = 4, DDL_FUSE_CN = 5 };
 typedef struct ddl_stage_fuse {
