@@ -50,6 +50,10 @@ int DDL_CAT(run_xfused_, DDL_N)(int phys, const XFusedParams& p, int n_outer, in
             case 3: return launch_xfused<N, Hydro3C>(p, n_outer, variant, s);
             case 4: return launch_xfused<N, Bouss3C>(p, n_outer, variant, s);
             case 5: return launch_xfused<N, MHD3C>(p, n_outer, variant, s);
+            // advective-form policies (states that are not solenoidal, e.g. the reference's own 3-D turb_new fields): the two
+            // whose field counts fit the kernel's pointer tables; Boussinesq (13 products) stays on the generic tile kernel
+            case 9: return launch_xfused_basic<N, Hydro3A>(p, n_outer, s);
+            case 11: return launch_xfused_basic<N, MHD3A>(p, n_outer, s);
         }
     }
     return 1;

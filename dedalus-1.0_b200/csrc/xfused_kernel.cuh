@@ -539,4 +539,11 @@ int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t 
     return launch_xfused_v<N, PHYS, 0>(p, n_outer, stream);
 }
 
+// default CTA shape only (plus its CFL-capture twin): for the advective-form policies, which are off the measured path
+template <int N, class PHYS>
+int launch_xfused_basic(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
+    if (p.cfl) return launch_xfused_v<N, PHYS, 0, true>(p, n_outer, stream);
+    return launch_xfused_v<N, PHYS, 0>(p, n_outer, stream);
+}
+
 }  // namespace ddl

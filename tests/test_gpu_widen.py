@@ -318,7 +318,10 @@ def _compressive_state(Po, seed):
 
 NONSOL = [("IncompressibleHydro", (32, 64), dict(nu=1e-3)), ("BoussinesqHydro", (32, 32), dict(nu=1e-3, kappa=2e-3, g=1.5, beta=0.5)),
           ("IncompressibleMHD", (64, 32), dict(nu=1e-3, eta=2e-3, rho0=0.7)), ("IncompressibleHydro", (16, 32, 32), dict(nu=1e-2)),
-          ("BoussinesqHydro", (32, 16, 32), dict(nu=1e-2, kappa=1e-2, alpha_t=0.5)), ("IncompressibleMHD", (32, 32, 16), dict(nu=1e-2, eta=1e-2))]
+          ("BoussinesqHydro", (32, 16, 32), dict(nu=1e-2, kappa=1e-2, alpha_t=0.5)), ("IncompressibleMHD", (32, 32, 16), dict(nu=1e-2, eta=1e-2)),
+          # x length 128: the specialised fused x pass with the advective-form policies (hydro, MHD; Boussinesq stays generic)
+          ("IncompressibleHydro", (8, 16, 128), dict(nu=1e-2)), ("IncompressibleMHD", (8, 8, 128), dict(nu=1e-2, eta=1e-2)),
+          ("BoussinesqHydro", (8, 8, 128), dict(nu=1e-2, kappa=1e-2))]
 
 
 @pytest.mark.parametrize("physics,shape,params", NONSOL)
