@@ -13,10 +13,7 @@ import torch
 
 from .._lib import lib, check
 from ..config import decfg
-from ..utils.logger import mylog
-from ..utils.parallelism import com_sys
 from ..utils.timer import timer
-from ..utils.function_count import counts
 from . import plan as _plan
 
 

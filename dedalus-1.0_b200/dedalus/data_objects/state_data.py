@@ -2,8 +2,6 @@
 (reference: dedalus/data_objects/state_data.py:45-186)."""
 from collections import OrderedDict
 
-import numpy as np
-
 from ..utils.api import Timer
 from ..utils.logger import mylog
 from .fields import create_field_classes
