@@ -1,4 +1,5 @@
 // C ABI (include/ddl.h): plan, transforms, fused RHS pipelines, stage updates.
+#include <chrono>
 #include <cstdarg>
 #include <cmath>
 #include <string>
@@ -28,8 +29,13 @@ struct ProfEvent {
     const char* name;
 #if DDL_DEVICE_BUILD
     cudaEvent_t a, b;
+#else
+    double a, b;        // host emulation (tests only): wall-clock seconds, so that the report carries the labels of the path taken
 #endif
 };
+#if !DDL_DEVICE_BUILD
+static double prof_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#endif
 static long long g_launches = 0;
 static bool g_prof_on = false;
 static std::vector<ProfEvent> g_prof;
@@ -45,7 +51,13 @@ void prof_begin(const char* name, ddl_stream_t stream) {
     cudaEventRecord(e.a, stream);
     g_prof.push_back(e);
 #else
-    (void)name; (void)stream;
+    (void)stream;
+    if (!g_prof_on) return;
+    ProfEvent e;
+    e.name = name ? name : "?";
+    e.a = e.b = prof_now();
+    if (!g_prof.empty() && g_prof.back().b == g_prof.back().a) g_prof.back().b = e.a;   // emulated launchers without a prof_end
+    g_prof.push_back(e);
 #endif
 }
 void prof_end(ddl_stream_t stream) {
@@ -53,6 +65,7 @@ void prof_end(ddl_stream_t stream) {
     if (g_prof_on && !g_prof.empty()) cudaEventRecord(g_prof.back().b, stream);
 #else
     (void)stream;
+    if (g_prof_on && !g_prof.empty()) g_prof.back().b = prof_now();
 #endif
 }
 
@@ -1326,6 +1339,14 @@ extern "C" int ddl_profile_report(char* buf, size_t nbuf) {
         bool found = false;
         for (auto& a : agg) if (a.first == e.name) { a.second.first++; a.second.second += ms; found = true; break; }
         if (!found) agg.push_back({e.name, {1, (double)ms}});
+    }
+#else
+    if (!g_prof.empty() && g_prof.back().b == g_prof.back().a) g_prof.back().b = prof_now();
+    for (auto& e : g_prof) {
+        const double ms = (e.b - e.a) * 1e3;
+        bool found = false;
+        for (auto& a : agg) if (a.first == e.name) { a.second.first++; a.second.second += ms; found = true; break; }
+        if (!found) agg.push_back({e.name, {1, ms}});
     }
 #endif
     g_prof.clear();

@@ -41,3 +41,25 @@ def test_gpu_arm_emits_the_contract_keys():
                 '"cpu_baseline"', '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"traffic"', '"frac"', '"peak"', '"bound"'):
         assert key in src, key
     assert "/root/reference" not in src
+
+
+def test_gpu_arm_runs_against_the_package_under_host_emulation():
+    """bench.py's GPU arm, line for line, in the GPU-less container (tests/bench_emul_child.py: the conftest harness plus CPU
+    stand-ins for the torch.cuda calls the script makes itself).  Guards the script against drifting away from the package
+    between GPU runs: same launch labels, 24 launches per RK4 step of 3-D MHD, every contract key on the line."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env.pop("DEDALUS_DDL_LIB", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_emul_child.py"), "32"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["gpu_launches"] == 24 * line["steps"] and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert set(line["roofline"]["kernels"]) == {"z_inv", "y_inv", "x_fused", "y_fwd", "z_fwd", "assemble_stage"}
+    assert all(k["launches"] == 8 for k in line["roofline"]["kernels"].values())          # 2 instrumented steps x 4 RHS
+    nbytes = 6 * line["config"]["N_k"] * 16
+    assert line["e2e"]["h2d_bytes_per_step"] == nbytes and line["e2e"]["d2h_bytes_per_step"] == nbytes
+    assert line["roofline"]["kernel"] in line["roofline"]["kernels"] and line["roofline"]["frac"] > 0
+    assert 0 < line["invariants"]["ekin"] < 1 and 0 < line["invariants"]["emag"] < 1
