@@ -67,6 +67,13 @@ _main = _Stream()
 torch.cuda.current_stream = lambda *a: _main
 torch.cuda.stream = lambda s: contextlib.nullcontext()
 
+import torch.distributed as dist  # noqa: E402
+
+_init = dist.init_process_group
+dist.init_process_group = lambda backend=None, device_id=None, **kw: _init("gloo", **kw)     # torchrun children: gloo for nccl
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ["DEDALUS_SLAB_EXCHANGE"] = "collective"          # peer memory needs the device
+
 import bench  # noqa: E402
 
 if __name__ == "__main__":

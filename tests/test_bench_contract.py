@@ -63,3 +63,29 @@ def test_gpu_arm_runs_against_the_package_under_host_emulation():
     assert line["e2e"]["h2d_bytes_per_step"] == nbytes and line["e2e"]["d2h_bytes_per_step"] == nbytes
     assert line["roofline"]["kernel"] in line["roofline"]["kernels"] and line["roofline"]["frac"] > 0
     assert 0 < line["invariants"]["ekin"] < 1 and 0 < line["invariants"]["emag"] < 1
+
+
+def test_gpu_arm_under_torchrun_world_size_2_host_emulation():
+    """The same under torchrun with two ranks (gloo standing in for nccl, collective exchange): rank 0 alone prints the line,
+    the slab bookkeeping bench.py reads for its NVLink figures is still there, and the result is the same global field."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for k in ("DEDALUS_DDL_LIB", "DEDALUS_KY_LAYOUT", "DEDALUS_SLAB_EXCHANGE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "bench_emul_child.py"), "32"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and "cyclic" in line["config"]["parallelism"]
+    assert line["roofline"]["nvlink"]["bytes_out_per_gpu_per_step"] > 0 and line["roofline"]["nvlink"]["transposes_per_step"] == 60
+    assert line["e2e"]["h2d_bytes_per_step"] == 6 * line["config"]["N_k"] * 16
+    # the single-rank run of the same script gives these invariants for the same synthetic field (make_state draws the global noise)
+    assert abs(line["invariants"]["ekin"] - 0.4963064899312569) < 1e-9 and abs(line["invariants"]["emag"] - 0.5054009950719366) < 1e-9
+    assert "cpu_baseline" not in line
