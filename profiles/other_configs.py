@@ -15,11 +15,13 @@ import dedalus.time_stepping.api as tapi
 import dedalus.analysis.volume_average as va
 import dedalus._lib as L
 
+SHRINK = int(sys.argv[sys.argv.index("--shrink") + 1]) if "--shrink" in sys.argv else 1     # dry runs (tests/bench_emul_child.py)
 A_STAGE = {"IncompressibleHydro": 1104.0, "BoussinesqHydro": 1568.0, "IncompressibleMHD": 1920.0}
 for physics, n, integ, params in (("IncompressibleHydro", 256, "RK4", dict(nu=1e-3)),
                                   ("BoussinesqHydro", 512, "RK4", dict(nu=1e-3, kappa=1e-3)),
                                   ("BoussinesqHydro", 512, "RK2mid", dict(nu=1e-3, kappa=1e-3)),
                                   ("IncompressibleHydro", 512, "RK4", dict(nu=1e-3))):
+    n //= SHRINK
     P = dev_physics(physics, (n, n, n), None, params)
     data = P.create_fields(0.)
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -76,7 +76,12 @@ if int(os.environ.get("WORLD_SIZE", "1")) > 1:
 
 import bench  # noqa: E402
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].endswith(".py"):
+    # any other measurement script of the repo (profiles/*.py) under the same stand-ins:  bench_emul_child.py <script> [args]
+    import runpy
+    sys.argv = sys.argv[1:]
+    runpy.run_path(sys.argv[0], run_name="__main__")
+elif __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     bench.cpu_baseline = lambda args: {"value": None, "unit": bench.UNIT, "cores": 1, "kind": "reference", "sample": "skipped in the emulated run"}
     bench.run_ours(argparse.Namespace(n=n, steps=2, warmup=1, quick=False, cpu_n=16, cpu_steps=1, gpus=1, impl="ours"))
