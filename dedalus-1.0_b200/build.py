@@ -76,16 +76,22 @@ def NVCC_FLAGS_CMD(rest):
     return [NVCC] + NVCC_FLAGS + rest
 
 
-def build_emul(outdir):
-    """g++-only build of the same sources with DDL_HOST_EMUL (tests/host only; never shipped)."""
+def build_emul(outdir, sanitize=False):
+    """g++-only build of the same sources with DDL_HOST_EMUL (tests/host only; never shipped).
+    sanitize: AddressSanitizer + UBSan instrumentation (the process needs libasan preloaded; tests/test_host_sanitizer.py)."""
     os.makedirs(outdir, exist_ok=True)
     lib = os.path.join(outdir, "libddl_emul.so")
     stamp = os.path.join(outdir, ".digest")
-    dig = _digest("emul")
+    dig = _digest("emul-asan" if sanitize else "emul")
     if os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
         return lib
     cxx = os.environ.get("CXX", "g++")
     flags = ["-x", "c++", "-std=c++17", "-O2", "-fPIC", "-DDDL_HOST_EMUL", "-w"]
+    link = []
+    if sanitize:
+        flags = [f for f in flags if f != "-O2"] + ["-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=address",
+                                                     "-fsanitize=bounds,shift,integer-divide-by-zero,null", "-fno-sanitize-recover=all"]
+        link = ["-fsanitize=address", "-fsanitize=undefined", "-L/usr/lib/gcc/x86_64-linux-gnu/13"]
     jobs = []
     for n in SIZES:
         obj = os.path.join(outdir, "tile_inst_%d.o" % n)
@@ -95,7 +101,7 @@ def build_emul(outdir):
         jobs.append(([cxx] + flags + ["-c", os.path.join(CSRC, cu), "-o", obj], obj + ".log", obj))
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         list(ex.map(lambda j: _run(j[0], j[1]), jobs))
-    _run([cxx, "-shared", "-o", lib] + [j[2] for j in jobs], os.path.join(outdir, "link.log"))
+    _run([cxx, "-shared", "-o", lib] + link + [j[2] for j in jobs], os.path.join(outdir, "link.log"))
     with open(stamp, "w") as f:
         f.write(dig)
     return lib

@@ -28,7 +28,10 @@ HOST_EMUL_MAX_POINTS = int(os.environ.get("DDL_TEST_HOST_EMUL_MAX_POINTS", str(6
 def _enable_host_emulation():
     sys.path.insert(0, os.path.join(ROOT, "tests", "host"))
     import build as ddl_build                   # dedalus-1.0_b200/build.py
-    os.environ["DEDALUS_DDL_LIB"] = ddl_build.build_emul(os.path.join(ROOT, "tests", "host", "_build"))
+    if os.environ.get("DDL_TEST_HOST_EMUL_ASAN") == "1":      # tests/test_host_sanitizer.py: instrumented build, libasan preloaded
+        os.environ["DEDALUS_DDL_LIB"] = ddl_build.build_emul(os.path.join(ROOT, "tests", "host", "_build_asan"), sanitize=True)
+    else:
+        os.environ["DEDALUS_DDL_LIB"] = ddl_build.build_emul(os.path.join(ROOT, "tests", "host", "_build"))
     import torch
     import dedalus.data_objects.plan as plan_mod
     plan_mod.device = lambda: torch.device("cpu")

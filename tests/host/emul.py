@@ -24,7 +24,10 @@ class PhysParams(C.Structure):
 def load():
     sys.path.insert(0, os.path.join(ROOT, "dedalus-1.0_b200"))
     import build as ddl_build
-    lib = C.CDLL(ddl_build.build_emul(BUILD))
+    if os.environ.get("DDL_TEST_HOST_EMUL_ASAN") == "1":      # tests/test_host_sanitizer.py: instrumented build, libasan preloaded
+        lib = C.CDLL(ddl_build.build_emul(BUILD + "_asan", sanitize=True))
+    else:
+        lib = C.CDLL(ddl_build.build_emul(BUILD))
     lib.ddl_last_error.restype = C.c_char_p
     lib.ddl_version.restype = C.c_char_p
     lib.ddl_workspace_bytes.restype = C.c_size_t
