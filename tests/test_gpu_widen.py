@@ -592,3 +592,14 @@ def test_taylor_green_as_the_reference_writes_it_takes_the_fused_path():
     ti.do_advance(data, 1e-2)
     assert L.launch_count() - n0 == 2 * (4 + 1)                # per stage: y, x, y, fused assembly + update, out-of-mask update
     assert all(c._soln for c in data.comp_list()) and not any(c._clean for c in data.comp_list())
+
+
+@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (512, 8, 16)), ("IncompressibleMHD", (8, 512, 16)),
+                                           ("BoussinesqHydro", (256, 16, 32)), ("IncompressibleHydro", (16, 1024, 16)),
+                                           ("IncompressibleMHD", (128, 128, 16)), ("IncompressibleHydro", (2048, 8, 16)),
+                                           ("IncompressibleHydro", (8, 2048, 16))])
+def test_long_y_and_z_axes_on_small_grids(physics, shape):
+    """The strided pencil passes at the lengths of the headline grids (512, 1024, 2048 along y or z) on grids small enough for the
+    oracle and for the host-emulation / sanitizer harness: specialised and generic kernels agree and both match the oracle."""
+    from test_gpu_parity import test_generic_and_fast_kernels_agree
+    test_generic_and_fast_kernels_agree(physics, shape)
