@@ -73,8 +73,9 @@ def test_instrumented_build_reports_an_overrun():
 
 
 def test_kernel_bodies_under_asan():
-    """tests/test_host_emulation.py + the any-length transforms (C ABI through ctypes, numpy buffers)."""
-    _pytest(["test_host_emulation.py", "test_mixed_radix.py", "test_host_reductions.py"], marker="not gpu")
+    """tests/test_host_emulation.py + the any-length transforms (C ABI through ctypes, numpy buffers) + the reference's six
+    sample scripts (their children inherit the instrumented library and the preloaded runtime through the environment)."""
+    _pytest(["test_host_emulation.py", "test_mixed_radix.py", "test_host_reductions.py", "test_reference_samples.py"], marker="not gpu")
 
 
 def test_drop_in_package_under_asan():
