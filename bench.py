@@ -86,6 +86,26 @@ class ClockSampler(object):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(index):
+    """Multi-GPU runs: keep this rank's host thread (and, by first touch, its pinned staging buffers) on the CPUs NVML lists as
+    local to its GPU, so that the end-to-end leg's PCIe copies do not cross the socket interconnect.  Best effort: returns the
+    number of CPUs kept, or None when NVML, the affinity call or the container's cpuset do not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        near = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        keep = near & os.sched_getaffinity(0)
+        if len(keep) >= 2 and keep != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, keep)
+            return len(keep)
+    except Exception:
+        pass
+    return None
+
+
 def make_state(n, seed=5):
     """Synthetic random-phase MHD state on the device (SURVEY.md 8d recipe, torch generator):
     per component white noise -> forward -> k^(-5/6) amplitude -> solenoidal projection -> rms 1.
@@ -134,6 +154,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    near_cpus = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         # balanced ky ownership and the exchange fused into the passes (config.py [parallel]);
@@ -267,6 +288,8 @@ def run_ours(args):
     e2e = {"value": ksteps * 4 * nk / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
            "d2h_bytes_per_step": nbytes * world, "steps": ksteps, "ms_per_step": ms_e2e / ksteps,
            "note": "uploads / downloads on side streams; upload of component c waits for the download of component c of the previous step"}
+    if near_cpus:
+        e2e["host_cpus_near_gpu"] = near_cpus
 
     cpu = cpu_baseline(args) if (world == 1 and rank == 0) else None
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
