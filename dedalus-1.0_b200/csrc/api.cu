@@ -790,6 +790,43 @@ extern "C" int ddl_dealias_array(int ndim, const int64_t* kshape, void* data, co
     return launch_items(f, (long long)f.dim[0] * f.dim[1] * f.dim[2], (ddl_stream_t)stream, "dealias_array");
 }
 
+// Host <-> device copy of the listed boxes of a 3-D array (both sides in the same full layout): what a k-space component whose
+// modes outside the dealias mask are known to be zero needs to cross PCIe -- the retained box (two ky ranges x two kz ranges x
+// [0, kn) along kx) is 30 % of the array under the 2/3 rule.  One cudaMemcpy3DAsync per box; nothing is touched outside them.
+extern "C" int ddl_copy_boxes(void* dst, const void* src, const int64_t* shape, int nbox, const int64_t* boxes, int elem_bytes,
+                              int to_device, void* stream) {
+    if (!dst || !src || !shape || (nbox > 0 && !boxes) || elem_bytes <= 0) { set_error("ddl_copy_boxes: NULL argument"); return -1; }
+    for (int b = 0; b < nbox; ++b) {
+        const int64_t* q = boxes + 6 * b;
+        for (int d = 0; d < 3; ++d)
+            if (q[2 * d] < 0 || q[2 * d + 1] < q[2 * d] || q[2 * d + 1] > shape[d]) { set_error("ddl_copy_boxes: box %d outside the array", b); return -1; }
+    }
+    const size_t pitch = (size_t)shape[2] * elem_bytes;
+    for (int b = 0; b < nbox; ++b) {
+        const int64_t* q = boxes + 6 * b;
+        const size_t n0 = q[1] - q[0], n1 = q[3] - q[2], wb = (size_t)(q[5] - q[4]) * elem_bytes;
+        if (!n0 || !n1 || !wb) continue;
+#if DDL_DEVICE_BUILD
+        cudaMemcpy3DParms c;
+        memset(&c, 0, sizeof(c));
+        c.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), pitch, pitch, (size_t)shape[1]);
+        c.dstPtr = make_cudaPitchedPtr(dst, pitch, pitch, (size_t)shape[1]);
+        c.srcPos = c.dstPos = make_cudaPos((size_t)q[4] * elem_bytes, (size_t)q[2], (size_t)q[0]);
+        c.extent = make_cudaExtent(wb, n1, n0);
+        c.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        DDL_CUDA_CHECK(cudaMemcpy3DAsync(&c, (cudaStream_t)stream));
+#else
+        (void)to_device; (void)stream;
+        for (size_t i = 0; i < n0; ++i)
+            for (size_t j = 0; j < n1; ++j) {
+                const size_t off = ((size_t)(q[0] + i) * shape[1] + (q[2] + j)) * pitch + (size_t)q[4] * elem_bytes;
+                memcpy((char*)dst + off, (const char*)src + off, wb);
+            }
+#endif
+    }
+    return 0;
+}
+
 extern "C" int ddl_backward(ddl_plan* pl, void* k, double* x, void* work, size_t work_bytes, void* stream) {
     ddl_stream_t st = (ddl_stream_t)stream;
     DDL_TRY(need_one_rank(pl, "ddl_backward"));

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("DEDALUS_DDL_LIB") or os.path.join(_HERE, "libddl_b200
 
 EXPORTS = [
     "ddl_plan_create", "ddl_plan_create_slab", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
-    "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_dealias_array", "ddl_deriv", "ddl_rhs", "ddl_stage",
+    "ddl_forward", "ddl_backward", "ddl_dealias", "ddl_dealias_array", "ddl_copy_boxes", "ddl_deriv", "ddl_rhs", "ddl_stage",
     "ddl_rk4_stage", "ddl_cn_step", "ddl_step_array", "ddl_stage_outside", "ddl_rhs_stage", "ddl_slab_assemble_stage", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_theta", "ddl_slab_zinv", "ddl_slab_yinv",
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
@@ -73,6 +73,7 @@ def bind_slab(lib):
     lib.ddl_stage_outside.argtypes = [vp, i32, i32, vp, vp, vp, i32, C.c_double, vp]
     lib.ddl_reduce_outside_mask.argtypes = [vp, i32, vp, vp, vp]
     lib.ddl_dealias_array.argtypes = [i32, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.ddl_copy_boxes.argtypes = [vp, vp, vp, i32, vp, i32, i32, vp]
     lib.ddl_step_array.argtypes = [i32, i32, C.c_longlong, vp, vp, vp, vp, vp, C.c_double, vp]
     lib.ddl_set_shear.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double]
     if hasattr(lib, "ddl_p2p_create"):

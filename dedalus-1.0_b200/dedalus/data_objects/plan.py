@@ -133,6 +133,7 @@ class Plan(object):
             self.k[name] = torch.from_numpy(np.ascontiguousarray(kv)).to(self.device).reshape(shp_b)
         self._work = None
         self._pipe = None
+        self._boxes = None
         self.nmodes = int(np.prod(self.kshape))
 
     @property
@@ -155,6 +156,24 @@ class Plan(object):
             self._work = None
             self._work = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return self._work
+
+    def retained_boxes(self):
+        """(shape3, boxes) of the local k-space array for ddl_copy_boxes: the index boxes the plan's mask retains (runs of kept
+        indices along every axis; two per full axis, one along the half axis), int64 arrays.  2-D arrays get a leading axis of 1."""
+        if self._boxes is None:
+            runs = []
+            for axis in range(self.ndim):
+                name = [n for n, i in self.ktrans.items() if i == axis][0]
+                keep = np.asarray(self.keep_np[name]).astype(bool).ravel()
+                if axis == 0 and self.nranks > 1:
+                    keep = keep[self.krows]
+                edges = np.flatnonzero(np.diff(np.concatenate(([0], keep.astype(np.int8), [0]))))
+                runs.append(list(zip(edges[::2].tolist(), edges[1::2].tolist())))
+            runs = [[(0, 1)]] * (3 - self.ndim) + runs
+            boxes = [(a0, b0, a1, b1, a2, b2) for a0, b0 in runs[0] for a1, b1 in runs[1] for a2, b2 in runs[2]]
+            shape3 = np.array([1] * (3 - self.ndim) + [int(n) for n in self.kshape_local], dtype=np.int64)
+            self._boxes = (shape3, np.ascontiguousarray(np.array(boxes, dtype=np.int64).reshape(-1, 6)))
+        return self._boxes
 
     def transform_workspace(self):
         return self.workspace(lib.ddl_workspace_bytes(self.handle, 1, 1))

@@ -148,6 +148,55 @@ class FourierRepresentation(Representation):
         else:
             raise ValueError("space must be either xspace or kspace.")
 
+    # ------------------------------------------------------------------ host <-> device, retained modes only (extension)
+    def _host_spectrum(self, host):
+        if not (torch.is_tensor(host) and host.device.type == "cpu" and host.dtype == self._k.dtype and host.is_contiguous()
+                and tuple(host.shape) == tuple(self._k.shape)):
+            raise ValueError("host spectrum must be a contiguous CPU tensor of the local k-space shape and dtype.")
+        return host
+
+    def upload_retained(self, host):
+        """comp['kspace'] = host for a spectrum that is ZERO outside the dealias mask (the caller's promise, e.g. a state this
+        package handed out): only the retained box crosses PCIe (30 % of the array under the 2/3 rule; include/ddl.h
+        ddl_copy_boxes), the device buffer is zero elsewhere, and the component stays known-dealiased, so no check pass
+        follows.  Asynchronous on the current stream for pinned memory.  Not in the reference (its arrays never leave the host);
+        the assignment it replaces is representations.py:144-166."""
+        host = self._host_spectrum(host)
+        if self._sphere is not None or not self._static_k:
+            self["kspace"] = host                      # masks that are not a box: the full copy
+            return
+        pl = self._plan
+        if self._curr_space != "kspace" or not self._clean:
+            check(lib.ddl_dealias(pl.handle, self._k.data_ptr(), _plan.current_stream()))      # zero outside the mask, once
+        shape3, boxes = pl.retained_boxes()
+        check(lib.ddl_copy_boxes(self._k.data_ptr(), host.data_ptr(), shape3.ctypes.data, len(boxes), boxes.ctypes.data,
+                                 self._k.element_size(), 1, _plan.current_stream()))
+        self._curr_space = "kspace"
+        self._clean = True
+        self._checked = False
+        self._sym = False
+        self._soln = None
+
+    def download_retained(self, host):
+        """host <- comp['kspace'], retained box only; entries of `host` outside the mask are left as they are (zero them once).
+        Raises ValueError when the spectrum carries content outside the mask (hydro states may): use ['kspace']."""
+        host = self._host_spectrum(host)
+        self.require_space("kspace")
+        if self._sphere is not None or not self._static_k:
+            host.copy_(self._k, non_blocking=True)
+            return host
+        if not self.verify_clean():
+            raise ValueError("spectrum has content outside the dealias mask; download the full array (comp['kspace']).")
+        shape3, boxes = self._plan.retained_boxes()
+        check(lib.ddl_copy_boxes(host.data_ptr(), self._k.data_ptr(), shape3.ctypes.data, len(boxes), boxes.ctypes.data,
+                                 self._k.element_size(), 0, _plan.current_stream()))
+        return host
+
+    def retained_bytes(self):
+        """Bytes one upload_retained / download_retained moves."""
+        _, boxes = self._plan.retained_boxes()
+        return int(sum((b[1] - b[0]) * (b[3] - b[2]) * (b[5] - b[4]) for b in boxes)) * self._k.element_size()
+
     # ------------------------------------------------------------------ transforms
     @timer
     def forward(self):

@@ -105,6 +105,14 @@ int ddl_dealias(ddl_plan* plan, void* k, void* stream);
  * shearing box, whose ky drifts with kx and time).  Zero where any k >= 2/3 k_nyquist or k <= -2/3 k_nyquist. */
 int ddl_dealias_array(int ndim, const int64_t* kshape, void* data, const double* kx, const double* ky, const double* kz,
                       int ky_dense, const double* knyquist, void* stream);
+/* representations.py:144-166 __setitem__ copies the caller's array into the fixed buffer; here the caller's array is in HOST memory
+ * and the buffer on the device.  For a spectrum whose modes outside the dealias mask are known to be zero only the retained
+ * box has to cross PCIe: copy the nbox boxes (six int64 each: lo0, hi0, lo1, hi1, lo2, hi2, half-open, in elements) of a 3-D
+ * array of extents shape[3] (2-D spectra: shape[0] = 1) and elem_bytes per element between dst and src, both in the same full
+ * layout; to_device = 1 host -> device, 0 device -> host; asynchronous on `stream` (pinned host memory), nothing outside the
+ * boxes is read or written. */
+int ddl_copy_boxes(void* dst, const void* src, const int64_t* shape, int nbox, const int64_t* boxes, int elem_bytes,
+                   int to_device, void* stream);
 /* representations.py:419-425 deriv(): out = i * k_axis * in   (axis: 0=x, 1=y, 2=z) */
 int ddl_deriv(ddl_plan* plan, const void* k_in, void* k_out, int axis, void* stream);
 

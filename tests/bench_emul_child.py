@@ -84,4 +84,5 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].endswith(".py"):
 elif __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     bench.cpu_baseline = lambda args: {"value": None, "unit": bench.UNIT, "cores": 1, "kind": "reference", "sample": "skipped in the emulated run"}
-    bench.run_ours(argparse.Namespace(n=n, steps=2, warmup=1, quick=False, cpu_n=16, cpu_steps=1, gpus=1, impl="ours"))
+    bench.run_ours(argparse.Namespace(n=n, steps=2, warmup=1, quick=False, cpu_n=16, cpu_steps=1, gpus=1, impl="ours",
+                                     e2e_full="--e2e-full" in sys.argv))

@@ -603,3 +603,61 @@ def test_long_y_and_z_axes_on_small_grids(physics, shape):
     oracle and for the host-emulation / sanitizer harness: specialised and generic kernels agree and both match the oracle."""
     from test_gpu_parity import test_generic_and_fast_kernels_agree
     test_generic_and_fast_kernels_agree(physics, shape)
+
+
+@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (16, 16, 32)), ("IncompressibleHydro", (32, 16)), ("BoussinesqHydro", (12, 20, 24))])
+def test_retained_modes_only_host_transfers(physics, shape):
+    """upload_retained / download_retained (ddl_copy_boxes): a dealiased spectrum crosses PCIe as its retained box only -- same
+    host array as the full download bit for bit, same device array after the upload (zero elsewhere, still known-dealiased),
+    same step afterwards; a spectrum with content outside the mask refuses the short download."""
+    import torch
+    import dedalus.time_stepping.api as tapi
+    pin = torch.cuda.is_available()
+    P = dev_physics(physics, shape, None, dict(nu=1e-2))
+    Po = oracle_physics(physics, shape, None, dict(nu=1e-2))
+    import dedalus_oracle as orc
+    y0 = orc.synthetic_ic(Po, 3).kvector()
+    data = P.create_fields(0.)
+    set_state(data, y0)
+    comps = [c for _, _, c in data.components()]
+    for c in comps:
+        c.dealias()
+    want = [c["kspace"].cpu().clone() for c in comps]
+    host = [torch.zeros(tuple(w.shape), dtype=w.dtype, pin_memory=pin) for w in want]
+    for c, h, w in zip(comps, host, want):
+        assert c.download_retained(h) is h
+        if pin:
+            torch.cuda.synchronize()
+        assert torch.equal(h, w)
+        full = w.numel() * w.element_size()
+        assert 0 < c.retained_bytes() <= (0.36 if len(shape) == 3 else 0.5) * full
+    # the device buffers get junk everywhere, then the retained upload: bit-equal to the original, zero outside, known-dealiased
+    g = torch.Generator().manual_seed(1)
+    for c, h, w in zip(comps, host, want):
+        c["kspace"] = torch.view_as_complex(torch.randn(tuple(w.shape) + (2,), generator=g, dtype=torch.float64))
+        assert not c._clean
+        c.upload_retained(h)
+        assert c._clean and c._curr_space == "kspace"
+        assert torch.equal(c._k.cpu(), w)
+    # also from x-space (stale k buffer) and then a step: same as the step from the ordinary assignment
+    for c, h in zip(comps, host):
+        c["xspace"]
+        c.upload_retained(h)
+    ti = getattr(tapi, "RK4")(P)
+    ti.do_advance(data, 1e-2)
+    got = get_state(data)
+    P2 = dev_physics(physics, shape, None, dict(nu=1e-2))      # its own physics object: integrating factors are attached at the
+    data2 = P2.create_fields(0.)                                # first RHS call of a physics object only (physics.py:535-537)
+    set_state(data2, y0)
+    for _, _, c in data2.components():
+        c.dealias()
+    getattr(tapi, "RK4")(P2).do_advance(data2, 1e-2)
+    assert rel(got, get_state(data2)) < 1e-14
+    # content outside the mask: the short download refuses, the wrong host layout too
+    c = comps[0]
+    k = c["kspace"]
+    k[(0, 0, -1) if len(shape) == 3 else (-1, 0)] = 1.0        # a Nyquist-kx entry: k-space is (ky, kz, kx) in 3-D, (kx, ky) in 2-D
+    with pytest.raises(ValueError):
+        c.download_retained(host[0])
+    with pytest.raises(ValueError):
+        c.upload_retained(host[0][..., :-1])
