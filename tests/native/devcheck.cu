@@ -519,6 +519,68 @@ static void timing(int n, int reps) {
     dsync();
 }
 
+// ---------------------------------------------------------------- E: ddl_copy_boxes, the retained box of a spectrum across PCIe
+static void* hpinned(size_t bytes) {
+#ifndef DEVCHECK_EMUL
+    void* p; CK(cudaMallocHost(&p, bytes)); return p;
+#else
+    return malloc(bytes);
+#endif
+}
+static void hfree(void* p) {
+#ifndef DEVCHECK_EMUL
+    cudaFreeHost(p);
+#else
+    free(p);
+#endif
+}
+static void check_boxes(int n, bool time_it) {
+    say("E  ddl_copy_boxes: retained box of a (ky, kz, kx) spectrum between pinned host memory and the device (%d^3)\n", n);
+    Problem P(n, false);
+    const int nh = n / 2 + 1;
+    const long long nk = P.nk;
+    // runs of kept indices per axis, as the host layer derives them from the plan's masks
+    std::vector<std::pair<int, int>> ry, rx;
+    for (int i = 0; i < n;) { if (!P.keep[i]) { ++i; continue; } int j = i; while (j < n && P.keep[j]) ++j; ry.push_back({i, j}); i = j; }
+    for (int i = 0; i < nh;) { if (!P.keepx[i]) { ++i; continue; } int j = i; while (j < nh && P.keepx[j]) ++j; rx.push_back({i, j}); i = j; }
+    std::vector<int64_t> boxes;
+    long long kept = 0;
+    for (auto& a : ry) for (auto& b : ry) for (auto& c : rx) {
+        boxes.insert(boxes.end(), {a.first, a.second, b.first, b.second, c.first, c.second});
+        kept += (long long)(a.second - a.first) * (b.second - b.first) * (c.second - c.first);
+    }
+    const int nbox = (int)boxes.size() / 6;
+    int64_t shape[3] = {n, n, nh};
+    double* full = (double*)hpinned(nk * 16);
+    double* part = (double*)hpinned(nk * 16);
+    d2h(full, P.state[0], nk * 16);
+    memset(part, 0, nk * 16);
+    DDL(ddl_copy_boxes(part, P.state[0], shape, nbox, boxes.data(), 16, 0, nullptr));
+    dsync();
+    verdict("device -> host, boxes only: equals the full download (bytes differing)", memcmp(full, part, nk * 16) ? 1.0 : 0.0, 0.0);
+    void* dev = dmalloc(nk * 16);
+    dzero(dev, nk * 16);
+    DDL(ddl_copy_boxes(dev, full, shape, nbox, boxes.data(), 16, 1, nullptr));
+    dsync();
+    d2h(part, dev, nk * 16);
+    verdict("host -> device into a zeroed array: equals the spectrum", memcmp(full, part, nk * 16) ? 1.0 : 0.0, 0.0);
+    say("  %d boxes, %.1f %% of the array\n", nbox, 100.0 * kept / nk);
+    if (time_it) {
+        Timer t;
+        double best_d = 1e30, best_u = 1e30, best_f = 1e30;
+        for (int r = 0; r < 4; ++r) {
+            t.start(); DDL(ddl_copy_boxes(part, P.state[0], shape, nbox, boxes.data(), 16, 0, nullptr)); double ms = t.stop_ms(); if (ms < best_d) best_d = ms;
+            t.start(); DDL(ddl_copy_boxes(dev, full, shape, nbox, boxes.data(), 16, 1, nullptr)); ms = t.stop_ms(); if (ms < best_u) best_u = ms;
+#ifndef DEVCHECK_EMUL
+            t.start(); CK(cudaMemcpyAsync(part, P.state[0], nk * 16, cudaMemcpyDeviceToHost, 0)); ms = t.stop_ms(); if (ms < best_f) best_f = ms;
+#endif
+        }
+        say("  one component: boxes D2H %.3f ms (%.1f GB/s), boxes H2D %.3f ms (%.1f GB/s), full array D2H %.3f ms (%.1f GB/s)\n",
+            best_d, kept * 16 / best_d / 1e6, best_u, kept * 16 / best_u / 1e6, best_f, nk * 16 / best_f / 1e6);
+    }
+    dfree(dev); hfree(full); hfree(part);
+}
+
 int main(int argc, char** argv) {
     // devcheck [n_check=64] [n_time=0] [outfile] [option=value ...]      options: ddl_set_option names, reps=R
     int n_check = 64, n_time = 0, reps = 3, pos = 0;
@@ -533,8 +595,8 @@ int main(int argc, char** argv) {
         else if (pos == 1) { n_time = atoi(argv[i]); pos++; }
         else if (pos == 2) { g_out = fopen(argv[i], "w"); pos++; }
     }
-    if (n_check > 0) { check(n_check); check_seams(n_check < 64 ? n_check : 64); }
-    if (n_time > 0) timing(n_time, reps);
+    if (n_check > 0) { check(n_check); check_seams(n_check < 64 ? n_check : 64); check_boxes(n_check, false); }
+    if (n_time > 0) { timing(n_time, reps); check_boxes(n_time, true); }
     say("devcheck: %s (%d failure%s)\n", g_fail ? "FAILED" : "all ok", g_fail, g_fail == 1 ? "" : "s");
     if (g_out) fclose(g_out);
     return g_fail ? 1 : 0;
