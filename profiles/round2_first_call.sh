@@ -27,6 +27,17 @@ python -m pytest tests -q -m gpu -p no:cacheprovider --durations=15 > gpurun_out
 tail -30 gpurun_out/pytest_gpu_r2.log
 python bench.py > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.err
 tail -c 1500 gpurun_out/bench_r2.json
+# end-to-end leg with the full arrays, for comparison with the retained-box transfers the default run uses
+python bench.py --e2e-full --steps 4 --warmup 3 > gpurun_out/bench_r2_e2e_full.json 2> gpurun_out/bench_r2_e2e_full.err
+python - <<'PY'
+import json
+for f in ("gpurun_out/bench_r2.json", "gpurun_out/bench_r2_e2e_full.json"):
+    try:
+        e = json.loads(open(f).read().strip().splitlines()[-1])["e2e"]
+        print(f, "e2e ms/step %.1f" % e["ms_per_step"], e["transfer"][:40], e["h2d_bytes_per_step"])
+    except Exception as x:
+        print(f, "unreadable:", x)
+PY
 python profiles/widened_configs.py > gpurun_out/widened_r2.jsonl 2>&1
 cat gpurun_out/widened_r2.jsonl
 python profiles/small_grids.py > gpurun_out/small_grids_r2.log 2>&1
