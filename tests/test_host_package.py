@@ -7,9 +7,17 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _asan_run_covers_it():
+    import glob
+    return bool(glob.glob("/usr/lib/x86_64-linux-gnu/libasan.so.*") or glob.glob("/usr/lib/gcc/x86_64-linux-gnu/*/libasan.so"))
+
+
+@pytest.mark.skipif(_asan_run_covers_it(), reason="tests/test_host_sanitizer.py runs the same files, same assertions, with the instrumented build")
 def test_gpu_test_files_pass_under_host_emulation():
     env = dict(os.environ, DDL_TEST_HOST_EMUL="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
     env.pop("DEDALUS_DDL_LIB", None)
