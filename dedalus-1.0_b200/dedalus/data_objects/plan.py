@@ -163,7 +163,7 @@ class Plan(object):
         if self._boxes is None:
             runs = []
             for axis in range(self.ndim):
-                name = [n for n, i in self.ktrans.items() if i == axis][0]
+                name = [n for n, i in self.ktrans.items() if isinstance(n, str) and i == axis][0]
                 keep = np.asarray(self.keep_np[name]).astype(bool).ravel()
                 if axis == 0 and self.nranks > 1:
                     keep = keep[self.krows]

@@ -5,6 +5,8 @@ the copy lists.  Covers ranks that own no retained ky row (block slabs under 2/3
 import importlib.util
 import itertools
 import os
+import subprocess
+import sys
 
 import pytest
 
@@ -78,3 +80,43 @@ def test_peer_store_tables_address_the_copy_destinations(P, rows, nzl, cx, nz, n
                 # y pass: x-side position p = cy0[s] + j (rank s's j-th row) -> base + p*blk = block `me`, row j of s's k-side field
                 if rows[s]:
                     assert lay["yfwd_peer"][f][s] + cy0[s] * blk == fwd[s]
+
+
+def test_retained_boxes_cover_exactly_the_kept_modes():
+    """Plan.retained_boxes() (the index boxes comp.upload_retained / download_retained hand to ddl_copy_boxes): their union is
+    exactly the set of modes the plan's mask keeps, for every rank of block and cyclic ky ownership; no two boxes overlap.
+    One child process (host-emulation harness) for all cases."""
+    code = (
+        "import os, sys, numpy as np\n"
+        "os.environ['DDL_TEST_HOST_EMUL'] = '1'\n"
+        "sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "import conftest\n"
+        "from dedalus.data_objects.plan import Plan\n"
+        "done = 0\n"
+        "for shape, dealiasing in (((12, 16, 20), '2/3 cython'), ((16, 16, 32), '2/3 cython'), ((16, 24), '2/3 cython'), ((8, 16, 16), 'None')):\n"
+        "  for nranks, layout in ((1, 'block'), (2, 'block'), (4, 'block'), (2, 'cyclic'), (4, 'cyclic')):\n"
+        "    if len(shape) == 2 and nranks > 1:\n"
+        "        continue\n"
+        "    for rank in range(nranks):\n"
+        "        pl = Plan(shape, (2 * np.pi,) * len(shape), dealiasing, nranks, rank, layout)\n"
+        "        shape3, boxes = pl.retained_boxes()\n"
+        "        local = tuple(int(n) for n in pl.kshape_local)\n"
+        "        assert tuple(shape3) == (1,) * (3 - len(local)) + local\n"
+        "        hits = np.zeros(tuple(shape3), dtype=int)\n"
+        "        for b in boxes:\n"
+        "            hits[b[0]:b[1], b[2]:b[3], b[4]:b[5]] += 1\n"
+        "        keep = np.ones(local, dtype=bool)\n"
+        "        for name, axis in pl.ktrans.items():\n"
+        "            if not isinstance(name, str):\n"
+        "                continue\n"
+        "            kp = np.asarray(pl.keep_np[name]).astype(bool).ravel()\n"
+        "            if axis == 0 and nranks > 1:\n"
+        "                kp = kp[pl.krows]\n"
+        "            sh = [1] * len(local); sh[axis] = len(kp)\n"
+        "            keep = keep & kp.reshape(sh)\n"
+        "        assert hits.max() == 1 and np.array_equal(hits.reshape(local) == 1, keep), (shape, nranks, layout, rank)\n"
+        "        assert len(boxes) <= 4 and 0 < keep.sum() < keep.size\n"
+        "        done += 1\n"
+        "print('ok', done)\n") % (ROOT,)
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "ok 40" in r.stdout, r.stdout[-2000:]
