@@ -20,7 +20,7 @@ tail -25 gpurun_out/devcheck_r2.txt
 # device-side sanitizers on the native checker (the CPU suite runs the same kernel bodies under ASan/UBSan, tests/test_host_sanitizer.py;
 # shared-memory hazards of the warp-private x-pass stages and the shuffle epilogues exist only here)
 for tool in memcheck racecheck; do
-  timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 tests/native/_build/devcheck 128 > gpurun_out/sanitizer_${tool}_r2.log 2>&1
+  timeout 240 compute-sanitizer --tool $tool --error-exitcode 9 tests/native/_build/devcheck 64 > gpurun_out/sanitizer_${tool}_r2.log 2>&1
   echo "compute-sanitizer $tool: exit $?"; tail -4 gpurun_out/sanitizer_${tool}_r2.log
 done
 python -m pytest tests -q -m gpu -p no:cacheprovider --durations=15 > gpurun_out/pytest_gpu_r2.log 2>&1
