@@ -5,8 +5,14 @@
   value      whole-job throughput, state resident in HBM, CUDA-event timed (max over ranks)
   e2e        same metric through the public API with HOST buffers: every step copies the state
              from pinned host memory to the device, advances, and copies it back
-  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event duration (measured in
-             a separate instrumented pass of the same steps) vs the measured HBM peak
+  roofline   dominant kernel: bytes it MOVES per launch (computed from the plan's retained-mode counts,
+             checked against the committed ncu dram__bytes in tests/test_bench_contract.py) / CUDA-event
+             duration (a separate instrumented pass of the same steps) vs the measured HBM peak, and its
+             flops vs the FP64 peak measured live (ddl_measure_fp64); frac = max(bytes/BW, flops/peak)/time.
+             The SURVEY model's full-array bytes are kept beside it as frac_model.
+  parity     before anything is timed: 64^3 x 2 RK4 steps on THIS world size against the oracle and against
+             the reference's own code (oracle/ref_run.py child), and a layout-independent checksum of the
+             512^3 state after 2 steps, compared with the recorded single-GPU one (profiles/state_checksum.json)
   cpu_baseline  the reference's own CPU path (oracle/_ref) on this host, bounded sample
 
 `--impl reference` times only the reference CPU path and prints its own line.
@@ -106,6 +112,147 @@ def bind_near_gpu(index):
     return None
 
 
+
+def moved_bytes_per_rhs(n, kept, ni=6, no=9, ncomp=6):
+    """Bytes each kernel of the one-GPU 3-D RHS + fused RK4 stage MOVES per launch, from the plan's retained-mode
+    counts (kept = (cy, cz, kn): ky, kz, kx indices inside the 2/3 mask): every pass reads and writes whole 128-byte
+    lines of the retained kx range only (row pitch CX = kn rounded up to 8 complex), pruned ky / kz rows are neither read
+    nor written (DESIGN.md sections 2, 3).  Checked against the committed ncu dram__bytes (tests/test_bench_contract.py)."""
+    cy, cz, kn = kept
+    row = ((kn + 7) // 8) * 8 * 16
+    return {
+        "z_inv": ni * cy * (cz + n) * row,                 # state rows (retained) -> k-side pencils (all z)
+        "y_inv": ni * n * (cy + n) * row,                  # k-side pencils -> half-transformed lines (all y)
+        "x_fused": (ni + no) * n * n * row,                # state lines in, product lines out; real space never leaves the SM
+        "y_fwd": no * n * (n + cy) * row,
+        "z_fwd": no * cy * (n + cz) * row,
+        # 9 product spectra + per component: y_n read, stage state written, running total read + written (the first stage
+        # of a step does not read it, the last does not write it): 3.5 sweeps per component on average over the 4 stages
+        "assemble_stage": (no + 3.5 * ncomp) * cy * cz * row,
+        "assemble_stage_first": (no + 3 * ncomp) * cy * cz * row,      # the launch the committed ncu capture holds
+    }
+
+
+def flops_per_rhs(n, kept, ni=6, no=9):
+    """5 N log2 N per complex length-N transform actually computed (the conventional FFT count); the x pass transforms line
+    PAIRS (two real lines = one complex pencil)."""
+    import math
+    cy, cz, kn = kept
+    t = 5.0 * n * math.log2(n)
+    return {"z_inv": ni * cy * kn * t, "y_inv": ni * n * kn * t, "x_fused": (ni + no) * n * n / 2 * t,
+            "y_fwd": no * n * kn * t, "z_fwd": no * cy * kn * t, "assemble_stage": 0.0}
+
+
+def state_checksum(data, dist_mod, world):
+    """Layout-independent fingerprint of a spectral state: per component sum_k u(k) * exp(i (0.37 ky + 0.61 kz + 0.83 kx))
+    and sum_k |u(k)|^2 over ALL modes of the global array (each rank adds its own ky rows).  Two runs of the same global
+    problem on different rank counts agree to summation round-off (~1e-15 relative)."""
+    import torch
+    out = []
+    for _, _, c in data.components():
+        k = c._k                    # the spectral buffer itself: reading it through c['kspace'] would drop the "known dealiased" status
+        ph = 0.37 * c.k["y"] + 0.61 * c.k["z"] + 0.83 * c.k["x"]
+        w = torch.polar(torch.ones_like(ph), ph)
+        t = torch.stack([(k * w).sum(), (k.abs() ** 2).sum().to(k.dtype)])
+        t = torch.view_as_real(t).reshape(-1).clone()
+        if world > 1:
+            dist_mod.all_reduce(t)
+        out.append([float(v) for v in t.cpu()][:3])
+        del w, ph
+    return out
+
+
+def parity_block(world, rank, dist_mod, n=64, steps=2):
+    """64^3 x `steps` RK4 steps of the benchmark's physics on THIS world size (same slab pipeline, same kernels) against
+    (a) the numpy oracle, evaluated by every rank for its own ky rows, and (b) the reference's own RHS + Cython stage kernels
+    under the restated RK4 glue (oracle/ref_run.py child on rank 0).  The oracle / reference are the CHECKER here."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dedalus_oracle as orc
+    from dedalus.mods import IncompressibleMHD, FourierRepresentation, RK4
+    params, dt = dict(nu=1e-3, eta=1e-3), 2e-3
+    Po = orc.IncompressibleMHD((n, n, n))
+    Po.parameters.update(params)
+    do = orc.synthetic_ic(Po, 5)
+    y0 = do.kvector().copy()
+    child = None
+    if rank == 0 and os.path.exists(os.path.join(ROOT, "oracle", "_ref", ".built")):
+        import tempfile
+        tmp = tempfile.mkdtemp(prefix="ddl_parity_")
+        np.save(os.path.join(tmp, "y0.npy"), y0)
+        child = (subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "ref_run.py"), "--physics", "IncompressibleMHD",
+                                   "--shape", str(n), str(n), str(n), "--integ", "RK4", "--steps", str(steps), "--dt", repr(dt),
+                                   "--y0", os.path.join(tmp, "y0.npy"), "--out", os.path.join(tmp, "ref"), "--threads", "4",
+                                   "--param", "nu=1e-3", "--param", "eta=1e-3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE), tmp)
+    P = IncompressibleMHD((n, n, n), FourierRepresentation)
+    P.parameters.update(params)
+    data = P.create_fields(0.)
+    comps = [c for _, _, c in data.components()]
+    rows, dev = comps[0].local_rows["kspace"], comps[0]._k.device
+    for j, c in enumerate(comps):
+        c["kspace"] = torch.from_numpy(np.ascontiguousarray(y0[j][rows]))
+    ti, to = RK4(P), orc.RK4(Po)
+    for _ in range(steps):
+        ti.do_advance(data, dt)
+        to.do_advance(do, dt)
+    torch.cuda.synchronize()
+    loc = np.stack([c["kspace"].cpu().numpy() for c in comps])
+    y1 = do.kvector()
+    num = [np.linalg.norm(loc - y1[:, rows]) ** 2, np.linalg.norm(y1[:, rows]) ** 2, 0.0, 0.0]
+    ref_note = "oracle/_ref absent"
+    if child is not None:
+        so, se = child[0].communicate(timeout=600)
+        if child[0].returncode == 0:
+            ref = np.load(os.path.join(child[1], "ref", "y1.npy"))
+            ref_note = None
+        else:
+            ref_note = "reference child failed: " + se.decode()[-200:]
+    if world > 1:
+        # every rank compares its rows with the reference child's result too: rank 0 broadcasts it
+        flag = torch.tensor([1.0 if (rank == 0 and ref_note is None) else 0.0], dtype=torch.float64).to(dev)
+        dist_mod.broadcast(flag, 0)
+        if flag.item() > 0:
+            t = torch.from_numpy(np.ascontiguousarray(ref)).to(dev) if rank == 0 else torch.empty(y1.shape, dtype=torch.complex128).to(dev)
+            dist_mod.broadcast(torch.view_as_real(t), 0)
+            ref = t.cpu().numpy()
+            ref_note = None
+        elif rank != 0:
+            ref_note = "no reference result"
+    if ref_note is None:
+        num[2], num[3] = np.linalg.norm(loc - ref[:, rows]) ** 2, np.linalg.norm(ref[:, rows]) ** 2
+    t = torch.tensor(num, dtype=torch.float64).to(dev)
+    if world > 1:
+        dist_mod.all_reduce(t)
+    num = [float(v) for v in t.cpu()]
+    out = {"rel_l2": (num[0] / num[1]) ** 0.5, "n": n, "steps": steps, "integrator": "RK4", "world_size": world,
+           "against": "oracle/dedalus_oracle.py (numpy restatement, pinned to the reference's goldens)",
+           "rel_l2_reference_code": (num[2] / num[3]) ** 0.5 if num[3] > 0 else None,
+           "reference_code": "oracle/ref_run.py: the reference's physics.py RHS + representations.py (numpy FFT) + verbatim Cython "
+                             "euler/etd1 under the restated RK4 glue (time_step.py:426-483)" if num[3] > 0 else ref_note,
+           "tolerance": 1e-10}
+    out["ok"] = bool(out["rel_l2"] < 1e-10 and (out["rel_l2_reference_code"] is None or out["rel_l2_reference_code"] < 1e-10))
+    del data, ti, P, comps
+    torch.cuda.empty_cache()
+    return out
+
+
+def checksum_agreement(n, cs):
+    """Relative distance of this run's state checksum from the recorded single-GPU one (profiles/state_checksum.json)."""
+    path = os.path.join(ROOT, "profiles", "state_checksum.json")
+    try:
+        rec = json.load(open(path)).get(str(n))
+        if not rec:
+            return None, "no record for %d^3 in profiles/state_checksum.json" % n
+        import math
+        num = sum((a - b) ** 2 for x, y in zip(cs, rec["checksum"]) for a, b in zip(x[:2], y[:2]))
+        den = sum(b ** 2 for y in rec["checksum"] for b in y[:2])
+        en = max(abs(x[2] - y[2]) / abs(y[2]) for x, y in zip(cs, rec["checksum"]))
+        return {"phase_sum_rel": math.sqrt(num / den), "energy_rel_max": en, "recorded_on": rec.get("where")}, None
+    except Exception as e:
+        return None, "unreadable: %r" % (e,)
+
+
 def make_state(n, seed=5):
     """Synthetic random-phase MHD state on the device (SURVEY.md 8d recipe, torch generator):
     per component white noise -> forward -> k^(-5/6) amplitude -> solenoidal projection -> rms 1.
@@ -178,10 +325,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- parity first (nothing below is worth timing if this fails): small-grid RK4 against the oracle and the reference's
+    # own code on THIS world size, then a fingerprint of the full-size state after 2 steps
+    parity = None
+    if not args.quick:
+        parity = parity_block(world, rank, dist)
+        barrier()
     P, data, dt = make_state(n)
     ti = RK4(P)
     nk = n * n * (n // 2 + 1)
-    for _ in range(args.warmup):
+    n_cs = min(2, args.warmup)          # the fingerprint is taken inside the warm-up: the timed trajectory is what it always was
+    if parity is not None:
+        for _ in range(n_cs):
+            ti.do_advance(data, dt)
+        cs = state_checksum(data, dist, world)
+        agree, why_not = checksum_agreement(n, cs) if n_cs == 2 else (None, "needs --warmup >= 2")
+        parity["state_checksum"] = {"grid": n, "after_steps": n_cs, "per_component": cs,
+                                    "definition": "[Re, Im] of sum_k u(k) exp(i(0.37 ky + 0.61 kz + 0.83 kx)) and sum_k |u(k)|^2, all ranks summed",
+                                    "vs_recorded_1gpu": agree, "note": why_not}
+        if agree is not None:
+            parity["ok"] = bool(parity["ok"] and agree["phase_sum_rel"] < 1e-11 and agree["energy_rel_max"] < 1e-12)
+    for _ in range(args.warmup - (n_cs if parity is not None else 0)):
         ti.do_advance(data, dt)
     barrier()
     sampler = ClockSampler(local)
@@ -223,25 +387,47 @@ def run_ours(args):
     L.profile(False)
     peak, peak_src = measured_peak()
     tot_ms = sum(v["ms"] for v in prof.values())
-    # one RHS evaluation = one launch of each kernel on one GPU; under the slab pipeline the same
-    # work is split into per-field / per-chunk launches and each rank covers 1/world of the modes,
-    # so the algorithmic rate is taken per RHS evaluation
-    kern = {k: {"launches": v["n"], "ms_per_launch": v["ms"] / v["n"], "ms_per_rhs": v["ms"] / n_rhs, "share": v["ms"] / tot_ms,
-                "algo_gbs": ALGO_BYTES_PER_MODE.get(k, 0.0) * nk / world / (v["ms"] / n_rhs * 1e-3) / 1e9}
-            for k, v in prof.items()}
+    plan = next(data.components())[2]._plan
+    kept = tuple(int(plan.keep_np[a].sum()) for a in ("y", "z", "x"))
+    moved, flops = moved_bytes_per_rhs(n, kept), flops_per_rhs(n, kept)
+    try:
+        fp64_fma, fp64_add = L.measure_fp64()
+        fp64_src = "measured live: independent DFMA / DADD chains (ddl_measure_fp64)"
+    except Exception as e:
+        fp64_fma, fp64_add, fp64_src = 37.0, 18.5, "fallback 64 FMA/clk/SM (measurement failed: %r)" % (e,)
+    # one RHS evaluation = one launch of each kernel on one GPU; under the slab pipeline the same work is split into
+    # per-field / per-chunk launches and each rank covers 1/world of it, so rates are taken per RHS evaluation and per GPU
+    kern = {}
+    for k, v in prof.items():
+        ms_rhs = v["ms"] / n_rhs
+        mv, fl = moved.get(k, 0.0) / world, flops.get(k, 0.0) / world
+        t_b, t_f = mv / (peak * 1e9) * 1e3, fl / (fp64_fma * 1e12) * 1e3
+        kern[k] = {"launches": v["n"], "ms_per_launch": v["ms"] / v["n"], "ms_per_rhs": ms_rhs, "share": v["ms"] / tot_ms,
+                   "moved_bytes_per_rhs": mv, "moved_gbs": mv / (ms_rhs * 1e-3) / 1e9, "frac_hbm": t_b / ms_rhs,
+                   "gflop_per_rhs": fl / 1e9, "tflops": fl / (ms_rhs * 1e-3) / 1e12, "frac_fp64": t_f / ms_rhs,
+                   "frac": max(t_b, t_f) / ms_rhs, "bound": "hbm" if t_b >= t_f else "fp64",
+                   "model_gbs": ALGO_BYTES_PER_MODE.get(k, 0.0) * nk / world / (ms_rhs * 1e-3) / 1e9,
+                   "ncu_dram_bytes": TRAFFIC.get(k) if world == 1 and n == 512 else None}
     dom = max(prof, key=lambda k: prof[k]["ms"])
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["algo_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["algo_gbs"] / peak, "traffic": TRAFFIC.get(dom) if world == 1 and n == 512 else None,
+    d = kern[dom]
+    step_moved = sum(kk["moved_bytes_per_rhs"] for kk in kern.values())
+    roofline = {"bound": d["bound"], "kernel": dom, "achieved": d["moved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": d["frac"], "frac_hbm": d["frac_hbm"], "frac_fp64": d["frac_fp64"],
+                "traffic": TRAFFIC.get(dom) if world == 1 and n == 512 else None,
                 "traffic_source": TRAFFIC_SOURCE if world == 1 and n == 512 else None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_MODE.get(dom, 0.0) * nk / world * n_rhs / prof[dom]["n"],
-                # the SURVEY model counts full N_k arrays; the kernels only move the modes the 2/3 rule retains
-                # (DESIGN.md 3.3), so the same launch also as measured DRAM traffic / duration:
-                "achieved_dram_gbs": (TRAFFIC[dom] / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9) if (world == 1 and n == 512 and dom in TRAFFIC) else None,
-                "frac_dram": (TRAFFIC[dom] / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9 / peak) if (world == 1 and n == 512 and dom in TRAFFIC) else None,
-                "bound_note": "x_fused is limited by the FP64 pipe (53 %), issue slots (51 %) and the shared-memory pipe, not by HBM (profiles/ncu_r1.md)" if dom == "x_fused" else None,
-                "step": {"achieved": A_STAGE_MHD3D * value / 1e9 / world, "frac": A_STAGE_MHD3D * value / 1e9 / peak / world,
-                         "frac_of_8TBs": A_STAGE_MHD3D * value / 8e12 / world, "bytes_per_mode_stage": A_STAGE_MHD3D,
-                         "note": "per GPU"},
+                "bytes_per_launch": d["moved_bytes_per_rhs"] * n_rhs / prof[dom]["n"],
+                "bytes_definition": "bytes the kernel moves: whole 128-B lines of the modes the 2/3 rule retains, from the plan's "
+                                    "retained counts %r (DESIGN.md 3); within 3 %% of the committed ncu dram__bytes" % (kept,),
+                "fp64_peak_tflops": fp64_fma, "fp64_add_tflops": fp64_add, "fp64_peak_source": fp64_src,
+                "frac_definition": "max(moved bytes / measured HBM peak, 5 N log2 N flops / measured DFMA peak) / measured duration",
+                # SURVEY.md 8(d) counts FULL N_k arrays for every pass (15 x 32 B x N_k for the x pass); the kernels never touch the
+                # modes outside the mask, so this figure exceeds the hardware peak by construction: it is the model that is beaten
+                "frac_model": d["model_gbs"] / peak, "model_gbs": d["model_gbs"],
+                "model_bytes_per_launch": ALGO_BYTES_PER_MODE.get(dom, 0.0) * nk / world * n_rhs / prof[dom]["n"],
+                "step": {"moved_bytes_per_stage": step_moved, "moved_gbs": step_moved / (tot_ms / n_rhs * 1e-3) / 1e9,
+                         "frac": step_moved / (tot_ms / n_rhs * 1e-3) / 1e9 / peak,
+                         "model_bytes_per_mode_stage": A_STAGE_MHD3D, "frac_model": A_STAGE_MHD3D * value / 1e9 / peak / world,
+                         "frac_model_of_8TBs": A_STAGE_MHD3D * value / 8e12 / world, "note": "per GPU"},
                 "kernels": kern}
     if world > 1:
         pipe = next(data.components())[2]._plan.pipeline
@@ -333,7 +519,8 @@ def run_ours(args):
                       "parallelism": ("slab%d: x-space z-slabs, k-space %s ky ownership, exchange=%s" % (
                           world, os.environ.get("DEDALUS_KY_LAYOUT"), os.environ.get("DEDALUS_SLAB_EXCHANGE"))) if world > 1 else "single GPU",
                       "cache": "inputs larger than L2 (state %.1f GB per GPU)" % (6 * nk * 16 / world / 1e9)},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "invariants": {"ekin": ekin, "emag": emag}}
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "invariants": {"ekin": ekin, "emag": emag},
+           "parity": parity}
     if cpu is not None:
         out["cpu_baseline"] = cpu
     if rank == 0:
@@ -342,11 +529,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-# (profiles/), 512^3 single GPU; None where no capture exists for the current kernel version
-TRAFFIC = {"x_fused": 11.042e9, "y_inv": 7.275e9, "z_fwd": 7.303e9, "stage": 9.785e9, "assemble": 4.907e9,
-           "assemble_stage": 10.962e9}
-TRAFFIC_SOURCE = "profiles/ncu_r1.md (ncu --set full captures in profiles/r1/)"
+def _load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (one launch per kernel,
+    3-D MHD 512^3 on one B200): profiles/ncu_traffic.json, written by profiles/summarize_ncu.py from the reports' raw pages."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["512"]
+        return {k: v["dram_bytes"] for k, v in t.items()}, "profiles/ncu_traffic.json <- " + next(iter(t.values()))["source"].split(" ")[0]
+    except Exception:
+        return {}, None
+
+
+TRAFFIC, TRAFFIC_SOURCE = _load_traffic()
 
 
 def _ref_run(n, steps, threads):

@@ -18,7 +18,7 @@ SIZES = [0, 8, 16, 32, 64, 128, 256, 512, 1024, 2048]      # 0: the runtime-leng
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-EXTRA_CU = ["api.cu", "p2p.cu"]
+EXTRA_CU = ["api.cu", "p2p.cu", "microbench.cu"]
 
 
 def _sources():

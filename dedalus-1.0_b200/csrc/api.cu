@@ -1347,8 +1347,10 @@ extern "C" int ddl_set_shear(ddl_plan* pl, int enable, double shear_rate, double
     return 0;
 }
 
+namespace ddl { extern int g_p2p_timeout_s; }
 extern "C" int ddl_set_option(const char* name, int value) {
     if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
+    if (name && !strcmp(name, "p2p_timeout_s")) { ddl::g_p2p_timeout_s = value < 0 ? 0 : value; return 0; }
     if (name && !strcmp(name, "xfused_variant")) { g_xfused_variant = value; return 0; }
     if (name && !strcmp(name, "rhs_plane_chunk")) { g_plane_chunk = value < 0 ? 0 : value; return 0; }
     set_error("unknown option %s", name ? name : "(null)");

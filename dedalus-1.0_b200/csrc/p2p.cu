@@ -20,8 +20,21 @@
 #include "../../include/ddl.h"
 #include "ddl_common.cuh"
 
+namespace ddl {
+// ddl_set_option("p2p_timeout_s", s): how long a consumer pass waits for a peer's arrival flag before it traps;
+// 0 = wait for ever, like the blocking MPI all-to-all it replaces (_fftw.pyx:272-304).  A rank may legitimately be late by
+// minutes (rank-0-only analysis or I/O, a snapshot write between two RHS evaluations, a debugger, first-call lazy set-up).
+int g_p2p_timeout_s = 600;
+}
+
 #if DDL_DEVICE_BUILD
 namespace ddl {
+
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __global__ void p2p_signal_kernel(unsigned* const* flags, int n, int slot, unsigned value) {
     const int i = threadIdx.x;
@@ -34,14 +47,15 @@ __global__ void p2p_signal_kernel(unsigned* const* flags, int n, int slot, unsig
 }
 
 // spin until every watched flag has reached `value` (monotone sequence numbers; the
-// comparison is wrap-safe); trap after ~30 s so that a lost peer fails loudly instead of hanging
-__global__ void p2p_wait_kernel(const unsigned* flags, int n, int skip, unsigned value, long long timeout_cycles) {
+// comparison is wrap-safe); after timeout_ns of wall time (globaltimer: independent of the SM clock; 0 = never) trap, so that
+// a lost peer fails loudly instead of hanging
+__global__ void p2p_wait_kernel(const unsigned* flags, int n, int skip, unsigned value, unsigned long long timeout_ns) {
     const int i = threadIdx.x;
     if (i < n && i != skip) {
         const volatile unsigned* f = flags + i;
-        const long long t0 = clock64();
+        const unsigned long long t0 = p2p_now_ns();
         while ((int)(*f - value) < 0) {
-            if (clock64() - t0 > timeout_cycles) {
+            if (timeout_ns && p2p_now_ns() - t0 > timeout_ns) {
                 printf("ddl p2p: rank flag %d stuck at %u waiting for %u\n", i, *f, value);
                 __trap();
             }
@@ -162,7 +176,8 @@ extern "C" int ddl_p2p_wait(ddl_p2p* c, long long seq, void* stream) {
     const int slot = (unsigned)seq % DDL_P2P_RING;
     if (c->copied[slot]) DDL_CUDA_CHECK(cudaStreamWaitEvent(st, c->self[slot], 0));
     const unsigned* flags = (const unsigned*)c->base;
-    p2p_wait_kernel<<<1, 32, 0, st>>>(flags, c->nranks, c->rank, (unsigned)seq, 60000000000LL);   // ~30 s at 2 GHz
+    p2p_wait_kernel<<<1, 32, 0, st>>>(flags, c->nranks, c->rank, (unsigned)seq,
+                                      (unsigned long long)(ddl::g_p2p_timeout_s > 0 ? ddl::g_p2p_timeout_s : 0) * 1000000000ULL);
     DDL_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

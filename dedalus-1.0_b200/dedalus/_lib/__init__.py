@@ -8,7 +8,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("DEDALUS_DDL_LIB") or os.path.join(_HERE, "libddl_b200.so")   # override: kernel experiments only
+LIB_PATH = os.path.join(_HERE, "libddl_b200.so")
+# The one other library this module will bind is the g++ host-emulation build of the same sources, and only inside the test
+# harness (tests/conftest.py sets both variables in the test process): a stray DEDALUS_DDL_LIB in production is an error.
+if os.environ.get("DEDALUS_DDL_LIB"):
+    if os.environ.get("DDL_TEST_HOST_EMUL") != "1":
+        raise ImportError("DEDALUS_DDL_LIB is honoured only by the test harness (DDL_TEST_HOST_EMUL=1); unset it")
+    LIB_PATH = os.environ["DEDALUS_DDL_LIB"]
 
 EXPORTS = [
     "ddl_plan_create", "ddl_plan_create_slab", "ddl_plan_destroy", "ddl_workspace_bytes", "ddl_rhs_workspace_bytes",
@@ -17,7 +23,7 @@ EXPORTS = [
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
     "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count",
-    "ddl_reduce_invariants", "ddl_reduce_outside_mask", "ddl_reduce_max_square", "ddl_rhs_capture_max", "ddl_set_shear", "ddl_profile_enable", "ddl_profile_report", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
+    "ddl_reduce_invariants", "ddl_reduce_outside_mask", "ddl_reduce_max_square", "ddl_rhs_capture_max", "ddl_set_shear", "ddl_profile_enable", "ddl_profile_report", "ddl_measure_fp64", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
 HYDRO, BOUSSINESQ, MHD = 0, 1, 2
@@ -121,6 +127,7 @@ def _load():
     lib.ddl_profile_enable.argtypes = [i32]
     lib.ddl_profile_report.argtypes = [C.c_char_p, sz]
     lib.ddl_set_option.argtypes = [C.c_char_p, i32]
+    lib.ddl_measure_fp64.argtypes = [vp, vp]
     lib.ddl_sync.argtypes = [vp]
     lib.ddl_last_error.restype = C.c_char_p
     lib.ddl_version.restype = C.c_char_p
@@ -154,6 +161,13 @@ def profile_report():
     buf = C.create_string_buffer(1 << 16)
     check(lib.ddl_profile_report(buf, len(buf)))
     return json.loads(buf.value.decode())
+
+
+def measure_fp64(stream=None):
+    """(DFMA TFLOP/s, DADD TFLOP/s) of the current device, measured now (include/ddl.h ddl_measure_fp64)."""
+    out = (C.c_double * 2)()
+    check(lib.ddl_measure_fp64(out, stream))
+    return float(out[0]), float(out[1])
 
 
 def set_option(name, value):

@@ -98,11 +98,22 @@ class VolumeAverageSet(object):
         self.data = data
         self.filename = filename
         self.tasks = []
-        self.scratch = None
+        self._scratch = None
         if com_sys.myproc == 0:
             self.outfile = open(self.filename, "a")
             self.outfile.write("# Dedalus Volume Average\n")
             self.outfile.write("# Column 0: time\n")
+
+    @property
+    def scratch(self):
+        """data.clone() with a ScalarField 'scalar' and a VectorField 'vector' (volume_average.py:38-40): what every task
+        receives as its second argument.  Built on first use: the built-in tasks reduce on the device and never touch it
+        (4 full arrays in 3-D), user tasks registered with @VolumeAverageSet.register_task use it the reference's way."""
+        if self._scratch is None:
+            self._scratch = self.data.clone()
+            self._scratch.add_field("scalar", "ScalarField")
+            self._scratch.add_field("vector", "VectorField")
+        return self._scratch
 
     def add(self, name, fmt, options={}):
         self.tasks.append((self.known_analysis[name], fmt, options))
@@ -113,7 +124,7 @@ class VolumeAverageSet(object):
         line = ["%10.5f" % self.data.time]
         _shared.update(on=True, key=None, val=None)
         try:
-            vals = [f(self.data, self.scratch, **kwargs) for f, fmt, kwargs in self.tasks]
+            vals = [f(self.data, None if getattr(f, "_ddl_builtin", False) else self.scratch, **kwargs) for f, fmt, kwargs in self.tasks]
         finally:
             _shared.update(on=False, key=None, val=None)
         for (f, fmt, kwargs), val in zip(self.tasks, vals):
@@ -337,3 +348,10 @@ def current_squared(data):
     if inv is None or "B" not in data.fields:
         raise NotImplementedError("current_squared needs a (u, B) state")
     return _on_root(float(inv[0][INV["current2"]]))
+
+
+# The tasks above reduce on the device and ignore their `scratch` argument; VolumeAverageSet.run() therefore does not build
+# the scratch StateData for them.  Tasks a user registers later get it, as in the reference (volume_average.py:38-40,56-59).
+for _f in list(VolumeAverageSet.known_analysis.values()):
+    _f._ddl_builtin = True
+del _f

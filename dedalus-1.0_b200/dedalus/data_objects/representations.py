@@ -79,6 +79,13 @@ class FourierRepresentation(Representation):
         # fused RHS may then use the conservative products), False: known compressive (advective-form
         # policies), None: the caller has written the buffer since the last check (physics.verify_solenoidal)
         self._soln = True
+        # The hand-out of the k-space buffer drops all of the above -- once.  A caller who KEEPS the tensor (the reference's
+        # `uk = data['u']['x']['kspace']` is the live array) can write to it later; torch counts in-place writes to a tensor
+        # and to every view of it (`_version`), so a buffer that has ever escaped is re-examined before a step whenever
+        # that counter has moved since the last look (refresh_escaped; time_step._settle).  Writes torch cannot see
+        # (DLPack / __cuda_array_interface__ consumers, raw pointers) need an explicit comp.touch().
+        self._escaped = False
+        self._seen_version = 0
         self._curr_space = "kspace"
         self.integrating_factor = None
         self.fwd_count = 0
@@ -100,11 +107,27 @@ class FourierRepresentation(Representation):
     def kdata(self):
         """The k-space buffer.  Handing it out means the caller may modify it: the
         'zero outside the mask' knowledge is dropped (internal code uses _k)."""
+        self._drop_knowledge()
+        self._escaped = True
+        self._seen_version = self._k._version
+        return self._k
+
+    def _drop_knowledge(self):
         self._clean = False
         self._checked = False
         self._sym = False
         self._soln = None
-        return self._k
+
+    def touch(self):
+        """Tell the component that its k-space buffer has been modified behind torch's back (a write through a DLPack /
+        CUDA-array-interface alias or a raw pointer): everything known about it is re-established before the next step."""
+        self._drop_knowledge()
+
+    def refresh_escaped(self):
+        """A buffer that was handed out and has been written through torch since we last looked loses what we knew of it."""
+        if self._escaped and self._k._version != self._seen_version:
+            self._drop_knowledge()
+            self._seen_version = self._k._version
 
     @property
     def data(self):
@@ -136,6 +159,8 @@ class FourierRepresentation(Representation):
             if data.dim() == target.dim():
                 data = data[tuple(slice(int(n)) for n in target.shape)]
             target.copy_(data, non_blocking=True)
+        if space == "kspace":
+            self._seen_version = self._k._version      # this write is accounted for (refresh_escaped)
         self._curr_space = space
 
     def require_space(self, space):
@@ -259,6 +284,7 @@ class FourierRepresentation(Representation):
         check(lib.ddl_dealias(self._plan.handle, self._k.data_ptr(), _plan.current_stream()))
         if self._sphere is not None:
             self._k.masked_fill_(self._sphere, 0.0)
+            self._seen_version = self._k._version      # our own write: accounted for (refresh_escaped)
         self._clean = True
 
     dealias_23_spherical = dealias
@@ -280,6 +306,7 @@ class FourierRepresentation(Representation):
             row = d[0]
             d[0] = 0.5 * (row + row.flip(0).roll(1, 0).conj())
             self._sym = True
+            self._seen_version = d._version            # our own write: accounted for (refresh_escaped)
             return
         nranks = self._plan.nranks
         if nranks > 1:
@@ -298,6 +325,7 @@ class FourierRepresentation(Representation):
             plane = plane[torch.as_tensor(self.local_rows["kspace"], device=d.device)]
         d[:, :, 0] = plane
         self._sym = True
+        self._seen_version = d._version                # our own write: accounted for (refresh_escaped)
 
     def verify_clean(self):
         """Re-establish the 'zero outside the dealias mask' knowledge after the buffer was handed

@@ -152,6 +152,9 @@ class SlabPipeline(object):
         peer's own k-side size: [nmax x-side fields | nmax k-side fields]."""
         lib, P, me = self.lib, self.P, self.rank
         lay = arena_layout(P, me, self.rows, self.nzl, self.cx, self.nzl * P, nmax)
+        import os
+        if os.environ.get("DEDALUS_P2P_TIMEOUT"):       # seconds a pass waits for a late peer before it traps; 0 = for ever
+            self._check(lib.ddl_set_option(b"p2p_timeout_s", int(float(os.environ["DEDALUS_P2P_TIMEOUT"]))))
         ctx = C.c_void_p()
         handle = C.create_string_buffer(64)
         self._check(lib.ddl_p2p_create(C.byref(ctx), P, me, lay["bytes"], handle))

@@ -23,6 +23,7 @@ from ..config import decfg
 from ..data_objects.api import create_field_classes, AuxEquation, StateData
 from ..data_objects import plan as _plan
 from ..utils.logger import mylog
+from ..utils.parallelism import com_sys
 from ..utils.timer import timer
 
 
@@ -151,6 +152,7 @@ class Physics(object):
         from ..utils.parallelism import reduce_max
         if not self._is_finalized:
             self._finalize()
+        self.sync_knowledge(data)
         state = self._max_square_side_effects(data)
         pl = next(data.components())[2]._plan
         out = torch.zeros(2, dtype=torch.float64, device=pl.device)
@@ -194,6 +196,7 @@ class Physics(object):
         device buffer (include/ddl.h: ddl_rhs_capture_max): the time-step limit of the state an RHS
         is evaluated at then costs no transform at all.  Returns the token for capture_end()."""
         import torch
+        self.sync_knowledge(data)
         self._max_square_side_effects(data)
         pl = next(data.components())[2]._plan
         out = torch.zeros(2, dtype=torch.float64, device=pl.device)
@@ -265,6 +268,35 @@ class Physics(object):
     # ------------------------------------------------------------------ solenoidal or not
     SOLENOIDAL_TOL = 1e-12      # compressive fraction sqrt(sum |k.u|^2 / sum |k|^2 |u|^2) below which u counts as div-free
 
+    def sync_knowledge(self, data):
+        """Slab-decomposed runs: make what the ranks know about `data`'s buffers the same on every rank BEFORE anything
+        branches on it.  `_soln` / `_sym` are dropped on the rank that hands a buffer out only (kdata, comp['kspace']),
+        and callers do touch buffers asymmetrically (init_cond.taylor_green / alfven write on the ranks find_mode finds;
+        rank 0 prints a mode) -- while the checks those bits gate are device collectives: the invariants sweep
+        (all_reduce) and the Hermitian projection of the kx = 0 plane (all_gather).  One host-side OR per call (com_sys.host_or)
+        of [some vector component unverified, component i not known Hermitian]; every rank then adopts the union, so
+        all of them enter the same collectives.  Integrator-internal stage states (written by our kernels only) skip it."""
+        comps = data.comp_list()
+        if comps[0]._plan.nranks == 1 or data.__dict__.get("_internal"):
+            return
+        if self.__dict__.pop("_sync_done_for", None) == id(data):
+            return                         # _settle() of this very step has just done it for this state
+        bits = 0
+        for i, c in enumerate(comps):
+            if c._soln is None:
+                bits |= 1
+            if not c._sym:
+                bits |= 2 << i
+        union = com_sys.host_or(bits)
+        if union == 0:
+            return
+        vector = set(id(c) for n, f in data if n in ("u", "B") for _, c in f)
+        for i, c in enumerate(comps):
+            if (union & 1) and id(c) in vector:
+                c._soln = None             # some rank must re-measure: everyone takes part in the sweep
+            if union & (2 << i):
+                c._sym = False             # rows of the plane changed somewhere: every rank re-projects its rows
+
     def verify_solenoidal(self, data):
         """Make sure every vector component of `data` knows whether its field is solenoidal (`_soln`).
 
@@ -320,6 +352,10 @@ class Physics(object):
                 "The fused RHS uses conservative products, which equal the reference's advective form only under "
                 "2/3 dealiasing; FFT.dealiasing=%r is not supported." % decfg.get("FFT", "dealiasing"))
         comps = data.comp_list()
+        for c in comps:
+            if c._escaped:
+                c.refresh_escaped()        # written through a tensor the caller kept? (representations.py)
+        self.sync_knowledge(data)
         state_clean = deriv_clean = True
         for c in comps:
             if c._curr_space != "kspace":

@@ -80,6 +80,12 @@ def _settle(sd, R=None):
     object, their fields' 'solenoidal' verdict (Physics.verify_solenoidal): both decide which kernels run."""
     if R is not None and getattr(R, "_unfused", False):
         return                      # shearing box: no fused kernels to choose between
+    for c in sd._cached()[0]:
+        if c._escaped:
+            c.refresh_escaped()     # the caller kept the tensor and wrote to it since the last step?
+    if R is not None and hasattr(R, "sync_knowledge"):
+        R.sync_knowledge(sd)        # slab runs: ranks agree on which buffers need a collective check (no-op on one rank)
+        R._sync_done_for = id(sd)   # the RHS evaluation of this state that follows need not ask again
     todo = None
     for c in sd._cached()[0]:
         if c._curr_space != "kspace":
@@ -171,6 +177,7 @@ class TimeStepBase(object):
             return self.do_advance(data, dt)
         for c in comps:
             c.require_space("kspace")
+            c.refresh_escaped()
         key = (id(data), float(dt), tuple(c._clean for c in comps))
         g = getattr(self, "_graph", None)
         if g is None or g[0] != key:
@@ -210,7 +217,6 @@ class TimeStepBase(object):
         self.time += dt
         self.iteration += 1
 
-    @timer
     def __getstate__(self):
         """Pickled into every snapshot (time_step.py:133-138): the integrating-factor coefficients are a ctypes
         array at run time and travel as a plain list."""
@@ -229,6 +235,7 @@ class TimeStepBase(object):
             state["_coeff"] = ((C.c_double * len(co[1]))(*co[1]), co[2])
         self.__dict__.update(state)
 
+    @timer
     def snapshot(self, data):
         """Per-rank snapshot directory snap_%05i with the reference's contents (time_step.py:112-151): the source of
         the forcing functions (forcing_functions.py), the pickled physics / state-layout / integrator objects
@@ -439,6 +446,7 @@ class RK2mid(RKBase):
     def __init__(self, *arg, **kwargs):
         TimeStepBase.__init__(self, *arg, **kwargs)
         self.data2 = self.RHS.create_fields(0.)
+        self.data2._internal = True                     # written by our kernels only (Physics.sync_knowledge)
         self.deriv1 = self.RHS.create_fields(0.)
         self.deriv2 = self.RHS.create_fields(0.)
 
@@ -514,6 +522,7 @@ class RK4(RKBase):
     def __init__(self, *arg, **kwargs):
         TimeStepBase.__init__(self, *arg, **kwargs)
         self.temp_data = self.RHS.create_fields(0.)     # stage states
+        self.temp_data._internal = True                 # written by our kernels only (Physics.sync_knowledge)
         self.total_deriv = self.RHS.create_fields(0.)   # (k1 + 2 k2 + 2 k3 + k4) / 6
         self.k_data = self.RHS.create_fields(0.)        # current k_i
         self._coeff = None

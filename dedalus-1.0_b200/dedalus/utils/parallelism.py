@@ -32,6 +32,20 @@ class CommunicationSystem(object):
         return dist.get_world_size() if self.comm else 1
 
     MPI = None
+    _host_group = None
+
+    def host_or(self, bits):
+        """Bitwise OR of a small non-negative integer over all ranks, on the HOST (no device work, no stream
+        synchronisation): a gloo group beside the NCCL one, created at the first call -- which is collective, like
+        every later one.  Used where ranks must agree on what they know about caller-written buffers before any of
+        them enters a device collective (Physics.sync_knowledge)."""
+        if self.comm is None or self.nproc == 1:
+            return int(bits)
+        if self._host_group is None:
+            self._host_group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+        t = torch.tensor([int(bits)], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.BOR, group=self._host_group)
+        return int(t.item())
 
 
 com_sys = CommunicationSystem()

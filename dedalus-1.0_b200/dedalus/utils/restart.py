@@ -76,3 +76,17 @@ def load_all_data(data, location):
             if isinstance(space, bytes):
                 space = space.decode()
             c[space] = torch.from_numpy(np.asarray(dset[...]))
+
+
+def identify_version(snap_dir, cpu_file="data.cpu0000"):
+    """The version string of the code that wrote a snapshot (restart.py:101-110): attribute `hg_version` of the HDF5 field
+    file; for the .npy + JSON fallback TimeStepBase.snapshot writes without h5py, the same value from the JSON index."""
+    filename = os.path.join(snap_dir, cpu_file)
+    if os.path.exists(filename):
+        import h5py
+        with h5py.File(filename, mode="r") as fi:
+            version = fi.attrs["hg_version"]
+        return version.decode() if isinstance(version, bytes) else version
+    index = os.path.join(snap_dir, cpu_file.replace("data.", "fields.") + ".json")
+    with open(index) as f:
+        return json.load(f).get("hg_version")

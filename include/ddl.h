@@ -321,8 +321,15 @@ int ddl_profile_report(char* json_out, size_t nbytes);
 /* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both);
  * "xfused_variant" = 0/1/2/3 picks the variant of the fused x pass (csrc/xfused_kernel.cuh);
  * "rhs_plane_chunk" = n > 0 runs y_inv -> x -> y_fwd of the one-rank 3-D RHS over chunks of n z-planes with chunk-sized,
- *   reused half-transformed arrays (an L2-residency experiment, default 0 = off) */
+ *   reused half-transformed arrays (an L2-residency experiment, default 0 = off; measured slower on B200);
+ * "p2p_timeout_s" = seconds a consumer pass of the peer exchange waits for a peer's arrival flag before it traps the context
+ *   (default 600; 0 = wait for ever, like the blocking MPI all-to-all of _fftw.pyx:272-304 it replaces) */
 int ddl_set_option(const char* name, int value);
+
+/* Measured roofs of the FP64 vector pipe on the current device (bench.py roofline; nothing in the reference corresponds):
+ * out2[0] = TFLOP/s of independent DFMA chains (2 flops each), out2[1] = TFLOP/s of DADD chains (1 flop each: the
+ * instruction-issue roof an FFT butterfly, which is mostly additions, actually meets).  Host pointers; synchronises. */
+int ddl_measure_fp64(double* out2, void* stream);
 
 int ddl_sync(void* stream);
 const char* ddl_last_error(void);

@@ -100,3 +100,22 @@ def test_gpu_arm_under_torchrun_world_size_2_host_emulation():
     # the single-rank run of the same script gives these invariants for the same synthetic field (make_state draws the global noise)
     assert abs(line["invariants"]["ekin"] - 0.4963064899312569) < 1e-9 and abs(line["invariants"]["emag"] - 0.5054009950719366) < 1e-9
     assert "cpu_baseline" not in line
+
+
+def test_moved_bytes_model_matches_the_committed_ncu_traffic():
+    """bench.py's roofline uses bytes computed from the plan's retained-mode counts; they must be what the hardware counters
+    saw (profiles/ncu_traffic.json: dram__bytes_read + write of one launch per kernel, 512^3 MHD) to within 3 %."""
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["512"]
+    model = bench.moved_bytes_per_rhs(512, (341, 341, 171))
+    assert set(traffic) == {"z_inv", "y_inv", "x_fused", "y_fwd", "z_fwd", "assemble_stage"}
+    for k, v in traffic.items():
+        m = model["assemble_stage_first" if k == "assemble_stage" else k]       # the capture is the first stage of a step
+        assert abs(m - v["dram_bytes"]) < 0.03 * v["dram_bytes"], (k, m, v["dram_bytes"])
+        assert os.path.exists(os.path.join(ROOT, v["source"].split(" ")[0])), v["source"]
+    # no kernel can move more than the SURVEY model's full-array bytes, and the step sum is the ~52 GB DESIGN.md quotes
+    nk = 512 * 512 * 257
+    for k in ("z_inv", "y_inv", "x_fused", "y_fwd", "z_fwd"):
+        assert model[k] < bench.ALGO_BYTES_PER_MODE[k] * nk
+    assert 50e9 < sum(model[k] for k in traffic) < 54e9

@@ -146,3 +146,44 @@ def test_restart_in_a_shearing_box(tmp_path, monkeypatch):
         t2.do_advance(d2, 1e-2)
     assert np.array_equal(d2["u"][0].k["y"].cpu().numpy(), data["u"][0].k["y"].cpu().numpy())
     assert np.linalg.norm(kvec(d2) - kvec(data)) <= 1e-14 * np.linalg.norm(kvec(data))
+
+
+def test_hdf5_branch_of_snapshot_and_restart_with_an_h5py_stand_in(tmp_path, monkeypatch):
+    """This image has no h5py, so the HDF5 branch of snapshot() / restart() / load_all() / identify_version() -- the
+    reference's format (time_step.py:141-151, fields.py:118-125, restart.py:33-110, parallelism.py:54-100) -- is executed
+    against tests/h5shim.py, a stand-in for the h5py calls it makes: same layout (/time, hg_version, /fields/<name>/<comp>,
+    attribute 'space'), same continuation as the .npy fallback.  The HDF5 byte format itself stays unverified."""
+    import sys
+    import h5shim
+    import dedalus.time_stepping.api as tapi
+    from dedalus.utils.api import restart
+    from dedalus.utils.restart import identify_version
+    from dedalus.utils.parallelism import load_all
+    from devutil import dev_physics
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setitem(sys.modules, "h5py", h5shim)
+    shape = (16, 16, 16)
+    P = dev_physics("IncompressibleMHD", shape, None, dict(nu=0.01, eta=0.02))
+    data = noise_state(P, shape, 6)
+    ti = tapi.RK2mid(P)
+    for _ in range(2):
+        ti.do_advance(data, 5e-3)
+    data["B"]["y"]["xspace"]                      # one component is saved in x-space: its 'space' attribute must bring it back
+    ti.snapshot(data)
+    assert os.path.exists("snap_00000/data.cpu0000") and not os.path.exists("snap_00000/fields.cpu0000.json")
+    with h5shim.File("snap_00000/data.cpu0000", "r") as f:
+        assert abs(float(np.asarray(f["time"][...])) - ti.time) < 1e-15 and f.attrs["hg_version"]
+        assert f["/fields/u"].attrs["type"] == "VectorField" and f["/fields/u"].attrs["representation"] == "FourierRepresentation"
+        assert f["/fields/u/0"].attrs["space"] == "kspace" and f["/fields/B/1"].attrs["space"] == "xspace"
+        assert f["/fields/u/0"].shape == (16, 16, 9) and f["/fields/B/1"].shape == (16, 16, 16)
+    assert identify_version("snap_00000") == f.attrs["hg_version"]
+    arr, space = load_all("u/0", "snap_00000")
+    assert space == "kspace" and arr.shape == (16, 16, 9)
+    for _ in range(2):
+        ti.do_advance(data, 5e-3)
+    ref = kvec(data)
+    RHS2, data2, ti2 = restart("snap_00000")
+    assert data2["B"]["y"]._curr_space == "xspace"
+    for _ in range(2):
+        ti2.do_advance(data2, 5e-3)
+    assert np.abs(kvec(data2) - ref).max() < 1e-15 and ti2.iteration == ti.iteration
