@@ -1348,7 +1348,15 @@ extern "C" int ddl_set_shear(ddl_plan* pl, int enable, double shear_rate, double
 }
 
 namespace ddl { extern int g_p2p_timeout_s; }
+#if DDL_DEVICE_BUILD
+namespace ddl { int g_peer_pass_ctas = 0; }
+#endif
 extern "C" int ddl_set_option(const char* name, int value) {
+#if DDL_DEVICE_BUILD
+    if (name && !strcmp(name, "peer_pass_ctas")) { ddl::g_peer_pass_ctas = value < 0 ? 0 : value; return 0; }
+#else
+    if (name && !strcmp(name, "peer_pass_ctas")) return 0;
+#endif
     if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
     if (name && !strcmp(name, "p2p_timeout_s")) { ddl::g_p2p_timeout_s = value < 0 ? 0 : value; return 0; }
     if (name && !strcmp(name, "xfused_variant")) { g_xfused_variant = value; return 0; }

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "fft_core.cuh"
 
@@ -46,6 +47,24 @@ void set_error(const char* fmt, ...);
             return -2;                                                                     \
         }                                                                                  \
     } while (0)
+#endif
+
+#if DDL_DEVICE_BUILD
+// One-time, per-device set-up of a kernel instantiation (function attributes, occupancy queries): a function-local static
+// of this type replaces a plain `static bool done`, which is neither thread-safe nor valid for a second device.
+#define DDL_MAXDEV 64
+struct DeviceOnce {
+    std::mutex mu;
+    int val[DDL_MAXDEV] = {};
+    // value cached for the current device (> 0), else init() is run under the lock: it returns the value (> 0) or an error (< 0)
+    template <class F> int get(F&& init) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DDL_MAXDEV) { set_error("DeviceOnce: no current device"); return -2; }
+        std::lock_guard<std::mutex> guard(mu);
+        if (val[dev] <= 0) val[dev] = init();
+        return val[dev];
+    }
+};
 #endif
 
 // launch accounting + optional per-launch CUDA-event timing (ddl_profile_* in include/ddl.h)

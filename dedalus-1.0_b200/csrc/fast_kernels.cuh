@@ -46,7 +46,13 @@ struct FastParams {
     int inner_len;
     double scale;
     const cplx* tw;
+    int gx, gy, gz;           // EXT kernels walk the (inner chunk, outer, field) tiles themselves: tile t = (t % gx, t / gx % gy, t / (gx gy))
 };
+
+// Slab passes only (EXT): number of CTAs a peer-store pass may occupy, 0 = one CTA per tile (ddl_set_option("peer_pass_ctas", n)).
+// A pass whose stores cross NVLink is bound by the links, not by the SMs: a few resident CTAs per SM pair saturate them, and a
+// grid limited to that many CTAs leaves the rest of every SM to the HBM / FP64-bound pass running on the other stream.
+extern int g_peer_pass_ctas;
 
 // stored row of logical row r, or -1 if the row is pruned
 template <int N>
@@ -117,11 +123,18 @@ strided_fast(const __grid_constant__ FastParams p) {
     const cplx* __restrict__ tw = p.tw;
 
     const int c = threadIdx.x % CX, a = threadIdx.x / CX;
-    const int inner = blockIdx.x * CX + c;
+    // EXT: a (possibly limited) 1-D grid of CTAs walks the tiles; plain kernels: one CTA per tile of the 3-D grid
+    const int ntiles = EXT ? p.gx * p.gy * p.gz : 1;
+#pragma unroll 1
+    for (int t = EXT ? (int)blockIdx.x : 0; t < ntiles; t += EXT ? (int)gridDim.x : 1) {
+    const int bx = EXT ? t % p.gx : (int)blockIdx.x;
+    const int by = EXT ? (t / p.gx) % p.gy : (int)blockIdx.y;
+    const int bz = EXT ? t / (p.gx * p.gy) : (int)blockIdx.z;
+    if (EXT && t != (int)blockIdx.x) __syncthreads();        // the previous tile's last stage has read the shared tile
+    const int inner = bx * CX + c;
     const bool live = inner < p.inner_len;
-    const int by = blockIdx.y;
-    const cplx* __restrict__ in = p.in[blockIdx.z];
-    cplx* __restrict__ out = p.out[blockIdx.z];
+    const cplx* __restrict__ in = p.in[bz];
+    cplx* __restrict__ out = p.out[bz];
     const long long ib = (long long)(p.si.outer_tab ? p.si.outer_tab[by] : by) * p.si.s_outer + inner;
     const long long ob = (long long)(p.so.outer_tab ? p.so.outer_tab[by] : by) * p.so.s_outer + inner;
 
@@ -173,7 +186,7 @@ strided_fast(const __grid_constant__ FastParams p) {
                 if (live && row >= 0) {
                     if (p.so.peer_tab) {
                         const int blk = p.so.own_tab ? p.so.own_tab[row] : (row >> p.so.split_shift);
-                        cplx* __restrict__ dst = p.so.peer_tab[blockIdx.z * p.so.nblk + blk];
+                        cplx* __restrict__ dst = p.so.peer_tab[bz * p.so.nblk + blk];
                         dst[ob + p.so.peer_off + (long long)(row & p.so.split_mask) * p.so.s_n] = scal(v[r], sc);
                     } else {
                         out[ob + fast_row_off(p.so, row)] = scal(v[r], sc);
@@ -182,6 +195,7 @@ strided_fast(const __grid_constant__ FastParams p) {
             }
         }
     }
+    }   // tile loop
 }
 
 // pencils per tile for the strided pass of length N
@@ -209,12 +223,24 @@ int launch_strided_fast_v(const FastParams& p, int nf, int n_outer, const char* 
     constexpr int T = N / Fac<N>::radix(0);
     auto kern = strided_fast<N, DIR, CX, EXT>;
     const size_t smem = (size_t)N * CX * sizeof(cplx);
-    static bool attr_done = false;
-    if (!attr_done) {
-        DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    static DeviceOnce once;
+    if (once.get([&]() -> int {
+            DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            return 1;
+        }) < 0) return -2;
     dim3 grid((p.inner_len + CX - 1) / CX, n_outer, nf);
+    if constexpr (EXT) {
+        FastParams q = p;
+        q.gx = (int)grid.x; q.gy = (int)grid.y; q.gz = (int)grid.z;
+        const long long ntiles = (long long)q.gx * q.gy * q.gz;
+        const bool peer = p.so.peer_tab != nullptr;
+        const long long lim = (peer && g_peer_pass_ctas > 0 && g_peer_pass_ctas < ntiles) ? g_peer_pass_ctas : ntiles;
+        prof_begin(name, stream);
+        kern<<<(unsigned)lim, CX * T, smem, stream>>>(q);
+        prof_end(stream);
+        DDL_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     prof_begin(name, stream);
     kern<<<grid, CX * T, smem, stream>>>(p);
     prof_end(stream);

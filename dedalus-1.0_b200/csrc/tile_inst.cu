@@ -4,6 +4,7 @@
 #include "tile_kernel.cuh"
 #include "fast_kernels.cuh"
 #include "xfused_kernel.cuh"
+#include "xfused_persist.cuh"
 
 #ifndef DDL_N
 #error "compile with -DDDL_N=<transform length>"

@@ -505,12 +505,12 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     const int gx = (pairs + Cfg::G - 1) / Cfg::G;
 #if DDL_DEVICE_BUILD
     auto kern = xfused_kernel<N, PHYS, V, CFL, KNC>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_done = true;
-    }
+    static DeviceOnce once;
+    if (once.get([&]() -> int {
+            DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+            DDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            return 1;
+        }) < 0) return -2;
     dim3 grid(gx, n_outer, 1);
     prof_begin("x_fused", stream);
     kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(p);
@@ -526,8 +526,19 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     return 0;
 }
 
+#if DDL_DEVICE_BUILD
+template <int N, class PHYS, bool CFL> int launch_xfused_persist(const XFusedParams& p, int n_outer, ddl_stream_t stream);   // xfused_persist.cuh
+#endif
+
 template <int N, class PHYS>
 int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t stream) {
+#if DDL_DEVICE_BUILD
+    if (variant == 4) {
+        // persistent CTAs with the next pair's lines staged by the bulk-copy engine (xfused_persist.cuh); 1 = not applicable
+        const int rc = p.cfl ? launch_xfused_persist<N, PHYS, true>(p, n_outer, stream) : launch_xfused_persist<N, PHYS, false>(p, n_outer, stream);
+        if (rc != 1) return rc;
+    }
+#endif
     if (p.cfl) return launch_xfused_v<N, PHYS, 0, true>(p, n_outer, stream);     // capture: default CTA shape only
     if (variant == 3 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 0, false, N / 3 + 1>(p, n_outer, stream);
 #if DDL_DEVICE_BUILD

@@ -115,7 +115,15 @@ class SlabPipeline(object):
         self.exchanges = 0
         import os
         self.chunks = int(os.environ.get("DEDALUS_SLAB_CHUNKS", "4"))     # plane chunks of the forward x / y passes (peer exchange)
-        self.inverse_batched = os.environ.get("DEDALUS_SLAB_INVERSE", "batched") == "batched"
+        # inverse half: "batched" = one z pass and one y pass for all fields; "groups:G" = G field groups, the y pass of
+        # group g on the side stream while the (NVLink-bound) z pass of group g+1 pushes its rows; "fields" = one group per field
+        inv = os.environ.get("DEDALUS_SLAB_INVERSE", "batched")
+        self.inverse_batched = inv == "batched"
+        self.inverse_groups = int(inv.split(":")[1]) if inv.startswith("groups:") else 0
+        # CTAs the peer-store passes may occupy (include/ddl.h "peer_pass_ctas"; 0 = one per tile) and whether the stream
+        # they run on outranks the main stream, so that their few CTAs are placed as soon as an SM has room
+        self.peer_ctas = int(os.environ.get("DEDALUS_PEER_CTAS", "0"))
+        self.side_priority = os.environ.get("DEDALUS_SIDE_PRIORITY", "0") == "1"
         self.trace = None               # profiling only: list collecting (label, torch.cuda.Event) marks of rhs()
         self.skip_exchange = False      # profiling only (profiles/slab_breakdown.py): time the passes without the all-to-all
 
@@ -178,7 +186,9 @@ class SlabPipeline(object):
         yt = [[pb[s] + lay["yfwd_peer"][f][s] for s in range(P)] for f in range(nmax)]
         self._zinv_tab = torch.tensor(zt, dtype=torch.int64, device=self.device)
         self._yfwd_tab = torch.tensor(yt, dtype=torch.int64, device=self.device)
-        self._side = torch.cuda.Stream(device=self.device)
+        self._side = torch.cuda.Stream(device=self.device, priority=-1 if self.side_priority else 0)
+        if self.peer_ctas:
+            self._check(lib.ddl_set_option(b"peer_pass_ctas", self.peer_ctas))
         dist.barrier(group=self.group)
 
     def _signal(self):
@@ -210,20 +220,24 @@ class SlabPipeline(object):
             t.wait()
             self._check(lib.ddl_slab_yinv(h, ni, _ptrs(xs[:ni]), _ptrs(b["b"][:ni]), main.cuda_stream))
         else:
+            ng = min(self.inverse_groups, ni) if self.inverse_groups else ni
+            bounds = [(g * ni) // ng for g in range(ng + 1)]
             done = []
-            for f in range(ni):
-                self._check(lib.ddl_slab_zinv_peer(h, 1, _ptrs([state[f]]), zt + f * el, main.cuda_stream))
+            for g in range(ng):
+                f0, f1 = bounds[g], bounds[g + 1]
+                self._check(lib.ddl_slab_zinv_peer(h, f1 - f0, _ptrs(state[f0:f1]), zt + f0 * el, main.cuda_stream))
                 t = self._signal()
                 ev = torch.cuda.Event()
                 ev.record(main)
                 done.append((t, ev))
             self._mark("z_inv")
             with torch.cuda.stream(side):
-                for f in range(ni):
-                    t, ev = done[f]
+                for g in range(ng):
+                    f0, f1 = bounds[g], bounds[g + 1]
+                    t, ev = done[g]
                     side.wait_event(ev)             # my own block is written by my own pass
                     t.wait()                        # the peers' blocks: arrival flags
-                    self._check(lib.ddl_slab_yinv(h, 1, _ptrs([xs[f]]), _ptrs([b["b"][f]]), side.cuda_stream))
+                    self._check(lib.ddl_slab_yinv(h, f1 - f0, _ptrs(xs[f0:f1]), _ptrs(b["b"][f0:f1]), side.cuda_stream))
             main.wait_stream(side)
         self._mark("wait+y_inv")
         # forward, chunked over the local planes: the x pass of chunk c+1 (compute-bound) runs on

@@ -322,6 +322,9 @@ int ddl_profile_report(char* json_out, size_t nbytes);
  * "xfused_variant" = 0/1/2/3 picks the variant of the fused x pass (csrc/xfused_kernel.cuh);
  * "rhs_plane_chunk" = n > 0 runs y_inv -> x -> y_fwd of the one-rank 3-D RHS over chunks of n z-planes with chunk-sized,
  *   reused half-transformed arrays (an L2-residency experiment, default 0 = off; measured slower on B200);
+ * "peer_pass_ctas" = n > 0 limits the slab passes that store to the peers over NVLink (ddl_slab_zinv_peer / ddl_slab_yfwd_peer) to n
+ *   CTAs that walk the tiles themselves (NVLink-bound: a few CTAs per SM pair saturate the links and the rest of the SMs stays
+ *   free for the pass running on the other stream); 0 = one CTA per tile;
  * "p2p_timeout_s" = seconds a consumer pass of the peer exchange waits for a peer's arrival flag before it traps the context
  *   (default 600; 0 = wait for ever, like the blocking MPI all-to-all of _fftw.pyx:272-304 it replaces) */
 int ddl_set_option(const char* name, int value);

@@ -268,17 +268,17 @@ static void check(int n) {
     DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv2, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
     dsync();
     ddl_set_option("fast_kernels", 1);
-    for (int v = 0; v <= 3; ++v) {
+    for (int v = 0; v <= 4; ++v) {
         ddl_set_option("xfused_variant", v);
         for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
         dzero(P.dout, 16);
-        DDL(ddl_rhs_capture_max(P.plan, v == 0 ? P.dout : nullptr));     // variant 0 also with the capture on
+        DDL(ddl_rhs_capture_max(P.plan, (v == 0 || v == 4) ? P.dout : nullptr));     // variants 0 and 4 (persistent) also with the capture on
         DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
         DDL(ddl_rhs_capture_max(P.plan, nullptr));
         dsync();
         char label[96]; snprintf(label, sizeof label, "x-pass variant %d vs generic tile kernels (rel L2)", v);
         verdict(label, max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
-        if (v == 0) {
+        if (v == 0 || v == 4) {
             d2h(got, P.dout, sizeof got);
             verdict("maxima captured inside that RHS", std::fmax(rel(got[0], brute[0]), rel(got[1], brute[1])), 1e-12);
         }
@@ -450,7 +450,7 @@ static void timing(int n, int reps) {
     say("== timing: MHD %d^3 (CUDA events, ms per call, best of %d after 1 warm-up)\n", n, reps);
     Problem P(n, false);
     Timer t;
-    for (int v = 0; v <= 3; ++v) {
+    for (int v = 0; v <= 4; ++v) {
         ddl_set_option("xfused_variant", v);
         double best = 1e30;
         for (int r = 0; r <= reps; ++r) {
@@ -459,7 +459,13 @@ static void timing(int n, int reps) {
             const double ms = t.stop_ms();
             if (r > 0 && ms < best) best = ms;
         }
-        say("  ddl_rhs, x-pass variant %d: %.3f ms\n", v, best);
+        ddl_profile_enable(1);
+        DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
+        static char pbuf[1 << 14];
+        DDL(ddl_profile_report(pbuf, sizeof pbuf));
+        ddl_profile_enable(0);
+        const char* xf = strstr(pbuf, "\"x_fused\"");
+        say("  ddl_rhs, x-pass variant %d: %.3f ms   %.40s\n", v, best, xf ? xf : "");
     }
     ddl_set_option("xfused_variant", g_variant);
     // opt-in L2-residency experiment: y_inv -> x -> y_fwd over chunks of z-planes (include/ddl.h "rhs_plane_chunk")

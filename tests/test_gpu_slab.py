@@ -26,14 +26,20 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,layout,exchange", [(2, "block", "peer"), (2, "cyclic", "peer"), (2, "block", "collective"),
-                                                   (2, "cyclic", "p2p"), (4, "cyclic", "peer"), (8, "block", "peer"),
-                                                   (8, "cyclic", "peer")])
-def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, tmp_path):
+# schedule knobs of the peer exchange (dedalus/data_objects/slab.py): field groups of the inverse half, CTA limit of the
+# NVLink-bound passes (they then walk their tiles), priority of the stream they run on, plane chunks of the forward half
+TUNED = dict(DEDALUS_SLAB_INVERSE="groups:2", DEDALUS_PEER_CTAS="24", DEDALUS_SIDE_PRIORITY="1", DEDALUS_SLAB_CHUNKS="8")
+
+
+@pytest.mark.parametrize("world,layout,exchange,knobs", [
+    (2, "block", "peer", {}), (2, "cyclic", "peer", {}), (2, "block", "collective", {}), (2, "cyclic", "p2p", {}),
+    (2, "cyclic", "peer", TUNED), (2, "block", "peer", dict(TUNED, DEDALUS_SLAB_INVERSE="fields", DEDALUS_PEER_CTAS="7")),
+    (4, "cyclic", "peer", {}), (4, "cyclic", "peer", TUNED), (8, "block", "peer", {}), (8, "cyclic", "peer", {}), (8, "cyclic", "peer", TUNED)])
+def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, knobs, tmp_path):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     out = str(tmp_path / "res.json")
-    env = dict(os.environ, DEDALUS_KY_LAYOUT=layout, DEDALUS_SLAB_EXCHANGE=exchange)
+    env = dict(os.environ, DEDALUS_KY_LAYOUT=layout, DEDALUS_SLAB_EXCHANGE=exchange, **knobs)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "gpu_slab_worker.py"), out]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
