@@ -180,7 +180,14 @@ class FourierRepresentation(Representation):
             raise ValueError("host spectrum must be a contiguous CPU tensor of the local k-space shape and dtype.")
         return host
 
-    def upload_retained(self, host):
+    def retained_parts(self):
+        """Number of index boxes the retained modes of this component form (upload_retained / download_retained take a
+        `part` in range(retained_parts()) to move one of them: finer-grained pipelining of host transfers)."""
+        if self._sphere is not None or not self._static_k:
+            return 1
+        return len(self._plan.retained_boxes()[1])
+
+    def upload_retained(self, host, part=None):
         """comp['kspace'] = host for a spectrum that is ZERO outside the dealias mask (the caller's promise, e.g. a state this
         package handed out): only the retained box crosses PCIe (30 % of the array under the 2/3 rule; include/ddl.h
         ddl_copy_boxes), the device buffer is zero elsewhere, and the component stays known-dealiased, so no check pass
@@ -194,6 +201,8 @@ class FourierRepresentation(Representation):
         if self._curr_space != "kspace" or not self._clean:
             check(lib.ddl_dealias(pl.handle, self._k.data_ptr(), _plan.current_stream()))      # zero outside the mask, once
         shape3, boxes = pl.retained_boxes()
+        if part is not None:
+            boxes = boxes[int(part):int(part) + 1]          # one box of the set (the caller uploads every part)
         check(lib.ddl_copy_boxes(self._k.data_ptr(), host.data_ptr(), shape3.ctypes.data, len(boxes), boxes.ctypes.data,
                                  self._k.element_size(), 1, _plan.current_stream()))
         self._curr_space = "kspace"
@@ -202,7 +211,7 @@ class FourierRepresentation(Representation):
         self._sym = False
         self._soln = None
 
-    def download_retained(self, host):
+    def download_retained(self, host, part=None):
         """host <- comp['kspace'], retained box only; entries of `host` outside the mask are left as they are (zero them once).
         Raises ValueError when the spectrum carries content outside the mask (hydro states may): use ['kspace']."""
         host = self._host_spectrum(host)
@@ -213,6 +222,8 @@ class FourierRepresentation(Representation):
         if not self.verify_clean():
             raise ValueError("spectrum has content outside the dealias mask; download the full array (comp['kspace']).")
         shape3, boxes = self._plan.retained_boxes()
+        if part is not None:
+            boxes = boxes[int(part):int(part) + 1]
         check(lib.ddl_copy_boxes(host.data_ptr(), self._k.data_ptr(), shape3.ctypes.data, len(boxes), boxes.ctypes.data,
                                  self._k.element_size(), 0, _plan.current_stream()))
         return host

@@ -86,7 +86,7 @@ class StateData(object):
             f.report_counts()
 
     def __reduce__(self):
-        state = {k: v for k, v in self.__dict__.items() if k not in ("fields", "_field_classes", "_cache")}
+        state = {k: v for k, v in self.__dict__.items() if k not in ("fields", "_field_classes", "_cache", "_subs")}
         rep = next(iter(self._field_classes.values())).representation
         keys = [(n, f.__class__.__name__) for n, f in self.fields.items()]
         return (_rebuild_state, (self.__class__, state, rep, keys))

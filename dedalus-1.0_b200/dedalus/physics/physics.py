@@ -152,6 +152,7 @@ class Physics(object):
         from ..utils.parallelism import reduce_max
         if not self._is_finalized:
             self._finalize()
+        data = self._main(data)
         self.sync_knowledge(data)
         state = self._max_square_side_effects(data)
         pl = next(data.components())[2]._plan
@@ -196,6 +197,7 @@ class Physics(object):
         device buffer (include/ddl.h: ddl_rhs_capture_max): the time-step limit of the state an RHS
         is evaluated at then costs no transform at all.  Returns the token for capture_end()."""
         import torch
+        data = self._main(data)
         self.sync_knowledge(data)
         self._max_square_side_effects(data)
         pl = next(data.components())[2]._plan
@@ -223,7 +225,7 @@ class Physics(object):
     def _build_phys_params(self):
         p = self.parameters
         d = p.get("boussinesq_direction", "z")
-        if self._tracer:
+        if self._tracer and not self._tracer_extra:
             return _lib.PhysParams(float(p.get("rho0", 1.0)), 0.0, 0.0, 0.0, 0, 0)      # tracer in the T slot, no coupling
         return _lib.PhysParams(float(p.get("rho0", 1.0)), float(p.get("g", 1.0)), float(p.get("alpha_t", 1.0)),
                                float(p.get("beta", 1.0)), {"x": 0, "y": 1, "z": 2}[d], 0)
@@ -268,6 +270,53 @@ class Physics(object):
     # ------------------------------------------------------------------ solenoidal or not
     SOLENOIDAL_TOL = 1e-12      # compressive fraction sqrt(sum |k.u|^2 / sum |k|^2 |u|^2) below which u counts as div-free
 
+    # ------------------------------------------------------------------ passive tracer on BoussinesqHydro / IncompressibleMHD
+    @property
+    def _tracer_extra(self):
+        """True when this class carries the tracer next to fields of its own (T or B): the state then is (u, c, T | B)."""
+        return self._tracer and type(self).__name__ != "IncompressibleHydro"
+
+    def _substate(self, sd, names, replace=None):
+        """A StateData over the SAME field objects as `sd`, restricted to `names` (cached on sd): what the fused kernels of
+        this class (state without 'c') and the tracer pass (u, c) take.  `replace` swaps in other field objects by name."""
+        key = tuple(names) + (id(replace.get("u")) if replace else 0,)
+        subs = sd.__dict__.setdefault("_subs", {})      # not pickled (StateData.__reduce__)
+        sub = subs.get(key)
+        if sub is None:
+            sub = sd.clone()
+            for n in names:
+                sub.fields[n] = (replace or {}).get(n) or sd.fields[n]
+            sub._cache = None
+            sub.__dict__["_internal"] = sd.__dict__.get("_internal", False)
+            subs[key] = sub
+        sub.time = sd.time
+        return sub
+
+    def _main(self, sd):
+        """`sd` without the tracer field (everything this class's own kernels and reductions see)."""
+        if not self._tracer_extra or "c" not in sd.fields:
+            return sd
+        return self._substate(sd, [n for n in sd.fields if n != "c"])
+
+    def _tracer_pass(self, data, deriv):
+        """deriv['c'] = -u.grad c through a plain hydro-with-tracer object (the Boussinesq kernels with g = alpha_t = beta = 0
+        and c in the T slot, as IncompressibleHydro itself does); the velocity derivative it also produces goes to scratch."""
+        eng = self.__dict__.get("_tracer_engine")
+        if eng is None:
+            old = decfg.get("physics", "use_tracer")
+            decfg.set("physics", "use_tracer", "True")
+            try:
+                eng = IncompressibleHydro(self.shape, self._representation, self.length)
+            finally:
+                decfg.set("physics", "use_tracer", old)
+            eng._finalize()
+            self._tracer_engine = eng
+            self._tracer_scratch = deriv.clone()
+            self._tracer_scratch.add_field("u", "VectorField")
+        trc_d = self._substate(data, ["u", "c"])
+        trc_k = self._substate(deriv, ["u", "c"], replace={"u": self._tracer_scratch.fields["u"]})
+        eng._fused_rhs(trc_d, trc_k, _lib.RHS_ZERO_FILL)
+
     def sync_knowledge(self, data):
         """Slab-decomposed runs: make what the ranks know about `data`'s buffers the same on every rank BEFORE anything
         branches on it.  `_soln` / `_sym` are dropped on the rank that hands a buffer out only (kdata, comp['kspace']),
@@ -307,6 +356,7 @@ class Physics(object):
         compressive fraction of u and B.  Returns True when the whole state is solenoidal."""
         if self._unfused:
             return True                    # the unfused path evaluates the advective forms themselves
+        data = self._main(data)
         for c in data.comp_list():
             if c._soln is not True:
                 break
@@ -338,7 +388,7 @@ class Physics(object):
         integrator may ask for the spectral assembly fused with its stage update."""
         if not self._is_finalized:
             self._finalize()
-        if self._unfused:
+        if self._unfused or self._tracer_extra:
             return False
         return not getattr(self, "_rotation", False) and not self.forcing_functions
 
@@ -351,6 +401,11 @@ class Physics(object):
             raise NotImplementedError(
                 "The fused RHS uses conservative products, which equal the reference's advective form only under "
                 "2/3 dealiasing; FFT.dealiasing=%r is not supported." % decfg.get("FFT", "dealiasing"))
+        if self._tracer_extra and "c" in data.fields:
+            if fuse is not None:
+                raise RuntimeError("the fused stage update is not available with a tracer next to T / B (can_fuse_stage)")
+            self._tracer_pass(data, deriv)
+            data, deriv = self._main(data), self._main(deriv)
         comps = data.comp_list()
         for c in comps:
             if c._escaped:
@@ -540,11 +595,13 @@ class IncompressibleHydro(Physics):
             # passive scalar c advected by u (physics.py:468-470,516-522,580-582): d_t c = -u.grad c + c_diff lap c.
             # That is the Boussinesq temperature equation without buoyancy and stratification, so the plain
             # hydro class runs the Boussinesq kernels with g = alpha_t = beta = 0 and c in the T slot.
-            if type(self) is not IncompressibleHydro:
-                raise NotImplementedError("Passive tracer (physics.use_tracer) is implemented for IncompressibleHydro only.")
+            # BoussinesqHydro / IncompressibleMHD inherit the tracer (physics.py:467-470: field 'c' right after 'u'): their own
+            # kernels run on the state without 'c', and an internal plain-hydro-with-tracer object evaluates d_t c from
+            # (u, c) in a second pass (_tracer_pass; its velocity derivative goes to scratch).
             self._field_list.append(("c", "ScalarField"))
             self.parameters["c_diff"] = 0.
-            self._physics_id = _lib.BOUSSINESQ
+            if type(self) is IncompressibleHydro:
+                self._physics_id = _lib.BOUSSINESQ
         self._first_rhs = True
 
     def __reduce__(self):

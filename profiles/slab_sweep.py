@@ -40,9 +40,10 @@ pipe = next(data.components())[2]._plan.pipeline
 nk = a.n * a.n * (a.n // 2 + 1)
 
 # (chunks, inverse, peer_ctas, side_priority)
-CONFIGS = [(4, "batched", 0, 0), (8, "batched", 0, 0), (16, "batched", 0, 0), (4, "groups:2", 0, 0), (4, "groups:3", 0, 0),
-           (4, "batched", 0, 1), (4, "batched", 148, 1), (4, "batched", 296, 1), (8, "batched", 148, 1), (8, "groups:2", 148, 1),
-           (8, "groups:2", 296, 1), (8, "groups:3", 148, 1), (16, "groups:2", 148, 1), (4, "groups:2", 148, 0)]
+CONFIGS = [(4, "batched", 0, 0), (2, "batched", 0, 0), (8, "batched", 0, 0), (16, "batched", 0, 0), (4, "groups:2", 0, 0),
+           (4, "groups:3", 0, 0), (4, "fields", 0, 0), (8, "groups:2", 0, 0), (4, "batched", 0, 1), (8, "groups:2", 0, 1),
+           (4, "batched", 148, 1), (4, "batched", 296, 1), (4, "batched", 444, 1), (8, "batched", 296, 1), (8, "groups:2", 148, 1),
+           (8, "groups:2", 296, 1), (8, "groups:2", 444, 1), (8, "groups:3", 296, 1), (16, "groups:2", 296, 1), (8, "groups:2", 296, 0)]
 if a.configs:
     CONFIGS = [tuple(int(x) if x.lstrip("-").isdigit() else x for x in c.split(",")) for c in a.configs.split(";")]
 

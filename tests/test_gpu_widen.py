@@ -425,12 +425,50 @@ def test_rhs_options_match_reference_runs(tag):
         decfg.set("physics", "use_tracer", "False")
 
 
-def test_tracer_with_other_physics_is_refused_loudly():
+TRACER_CASES = {
+    "tracer_bouss3d": ("BoussinesqHydro", (16, 16, 16), dict(nu=1e-2, kappa=2e-2, c_diff=5e-3), "RK2mid"),
+    "tracer_mhd3d": ("IncompressibleMHD", (16, 16, 16), dict(nu=1e-2, eta=2e-2, c_diff=1e-2), "RK2trap"),
+    "tracer_mhd2d": ("IncompressibleMHD", (16, 32), dict(nu=1e-2, eta=1e-2, c_diff=0.), "RK2mid"),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(TRACER_CASES))
+def test_tracer_inherited_by_boussinesq_and_mhd_matches_reference_runs(tag):
+    """In the reference the passive tracer lives in IncompressibleHydro and BoussinesqHydro / IncompressibleMHD inherit it
+    (physics.py:467-470,515-522,578-583): state (u, c, T | B).  Goldens: runs of the reference itself
+    (tests/golden/make_tracer_goldens.py).  Also: CFL limit, RK4 / CN and the solenoidal check work on such a state."""
+    import dedalus.time_stepping.api as tapi
     from dedalus.config import decfg
+    z = np.load(os.path.join(SAMPLES, "options_tracer.npz"))
+    physics, shape, params, integ = TRACER_CASES[tag]
     decfg.set("physics", "use_tracer", "True")
     try:
-        with pytest.raises(NotImplementedError):
-            dev_physics("IncompressibleMHD", (16, 16, 16))
+        P = dev_physics(physics, shape, None, params)
+        data = P.create_fields(0.)
+        assert list(data.fields) == [str(n) for n in z[tag + "_fields"]] == ["u", "c", "T" if physics == "BoussinesqHydro" else "B"]
+        set_state(data, z[tag + "_y0"])
+        ti = getattr(tapi, integ)(P)
+        for _ in range(3):
+            ti.do_advance(data, 1e-2)
+        assert rel(get_state(data), z[tag + "_y1"]) < 1e-10
+        # the tracer is passive: the other fields evolve exactly as without it
+        decfg.set("physics", "use_tracer", "False")
+        Q = dev_physics(physics, shape, None, {k: v for k, v in params.items() if k != "c_diff"})
+        plain = Q.create_fields(0.)
+        keep = [j for j, (n, _, _) in enumerate(data.components()) if n != "c"]
+        set_state(plain, z[tag + "_y0"][keep])
+        tq = getattr(tapi, integ)(Q)
+        for _ in range(3):
+            tq.do_advance(plain, 1e-2)
+        assert rel(get_state(plain), z[tag + "_y1"][keep]) < 1e-10
+        decfg.set("physics", "use_tracer", "True")
+        dt = P.compute_dt(data)
+        assert abs(dt - Q.compute_dt(plain)) < 1e-12 * dt
+        for other in ("RK4", "CrankNicholsonVisc"):
+            t2 = getattr(tapi, other)(P)
+            for _ in range(2):
+                t2.do_advance(data, 2e-3)
+            assert np.isfinite(get_state(data)).all()
     finally:
         decfg.set("physics", "use_tracer", "False")
 
