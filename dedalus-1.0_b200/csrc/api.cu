@@ -1100,6 +1100,15 @@ extern "C" int ddl_slab_yfwd_peer(ddl_plan* pl, int nf, void* const* c_in, void*
     DDL_TRY(check_planes(pl, z0, nzc));
     return phase_yfwd_peer(pl, nf, (const void* const*)c_in, peer_tab, z0, nzc, (ddl_stream_t)stream);
 }
+extern "C" int ddl_slab_yfwd_planes(ddl_plan* pl, int nf, void* const* c_in, void* const* xs_out, int z0, int nzc, void* stream) {
+    DDL_TRY(need_3d(pl));
+    DDL_TRY(check_planes(pl, z0, nzc));
+    FastGuard fg(pl->ay.full);
+    const long long CX = kx_pitch(pl);
+    std::vector<const void*> cin(nf);
+    for (int f = 0; f < nf; ++f) cin[f] = (const cplx*)c_in[f] + (long long)z0 * pl->ay.n * CX;      // phase_yfwd_planes takes chunk-local inputs
+    return phase_yfwd_planes(pl, nf, cin.data(), xs_out, z0, nzc, (ddl_stream_t)stream);
+}
 extern "C" int ddl_slab_xfused_planes(ddl_plan* pl, int physics, const ddl_phys_params* prm, void* const* b_in, void* const* c_out,
                                       int z0, int nzc, void* stream) {
     int ni, no, code;
@@ -1349,13 +1358,15 @@ extern "C" int ddl_set_shear(ddl_plan* pl, int enable, double shear_rate, double
 
 namespace ddl { extern int g_p2p_timeout_s; }
 #if DDL_DEVICE_BUILD
-namespace ddl { int g_peer_pass_ctas = 0; }
+namespace ddl { int g_peer_pass_ctas = 0; int g_strided_staged = 0; extern int g_push_tma; }
 #endif
 extern "C" int ddl_set_option(const char* name, int value) {
 #if DDL_DEVICE_BUILD
     if (name && !strcmp(name, "peer_pass_ctas")) { ddl::g_peer_pass_ctas = value < 0 ? 0 : value; return 0; }
+    if (name && !strcmp(name, "strided_staged")) { ddl::g_strided_staged = value != 0; return 0; }
+    if (name && !strcmp(name, "push_tma")) { ddl::g_push_tma = value != 0; return 0; }
 #else
-    if (name && !strcmp(name, "peer_pass_ctas")) return 0;
+    if (name && (!strcmp(name, "peer_pass_ctas") || !strcmp(name, "strided_staged") || !strcmp(name, "push_tma"))) return 0;
 #endif
     if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
     if (name && !strcmp(name, "p2p_timeout_s")) { ddl::g_p2p_timeout_s = value < 0 ? 0 : value; return 0; }

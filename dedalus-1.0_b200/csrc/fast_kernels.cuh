@@ -47,6 +47,7 @@ struct FastParams {
     double scale;
     const cplx* tw;
     int gx, gy, gz;           // EXT kernels walk the (inner chunk, outer, field) tiles themselves: tile t = (t % gx, t / gx % gy, t / (gx gy))
+    unsigned mx, mxy;         // ceil(2^32 / gx), ceil(2^32 / (gx gy)): t / d == umulhi(t, m) for t < 2^32 / d (strided_staged)
 };
 
 // Slab passes only (EXT): number of CTAs a peer-store pass may occupy, 0 = one CTA per tile (ddl_set_option("peer_pass_ctas", n)).
@@ -127,9 +128,15 @@ strided_fast(const __grid_constant__ FastParams p) {
     const int ntiles = EXT ? p.gx * p.gy * p.gz : 1;
 #pragma unroll 1
     for (int t = EXT ? (int)blockIdx.x : 0; t < ntiles; t += EXT ? (int)gridDim.x : 1) {
-    const int bx = EXT ? t % p.gx : (int)blockIdx.x;
-    const int by = EXT ? (t / p.gx) % p.gy : (int)blockIdx.y;
-    const int bz = EXT ? t / (p.gx * p.gy) : (int)blockIdx.z;
+    // EXT: tile -> (inner chunk, outer, field) by multiply-high (p.mx, p.mxy: exact below 2^32 / divisor, checked by the launcher);
+    // three integer divisions per tile and thread would cost a measurable part of a butterfly stage
+    int bx = (int)blockIdx.x, by = (int)blockIdx.y, bz = (int)blockIdx.z;
+    if constexpr (EXT) {
+        bz = (int)__umulhi((unsigned)t, p.mxy);
+        const int rem = t - bz * (p.gx * p.gy);
+        by = (int)__umulhi((unsigned)rem, p.mx);
+        bx = rem - by * p.gx;
+    }
     if (EXT && t != (int)blockIdx.x) __syncthreads();        // the previous tile's last stage has read the shared tile
     const int inner = bx * CX + c;
     const bool live = inner < p.inner_len;
@@ -210,9 +217,17 @@ template <int N> struct FastCX {
 template <int N, int DIR, bool EXT>
 int launch_strided_fast_v(const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t stream);
 
+template <int N, int DIR> int launch_strided_staged(const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t stream);   // fast_staged.cuh
+extern int g_strided_staged;
+
 template <int N, int DIR>
 int launch_strided_fast(const FastParams& p, int nf, int n_outer, const char* name, ddl_stream_t stream) {
     const bool ext = p.si.row_tab || p.so.row_tab || p.so.peer_tab || p.si.split_shift != 31 || p.so.split_shift != 31;
+    if (!ext && g_strided_staged) {
+        // persistent CTAs with the next tile's first-stage inputs fetched by cp.async (fast_staged.cuh); 1 = not applicable
+        const int rc = launch_strided_staged<N, DIR>(p, nf, n_outer, name, stream);
+        if (rc != 1) return rc;
+    }
     return ext ? launch_strided_fast_v<N, DIR, true>(p, nf, n_outer, name, stream)
                : launch_strided_fast_v<N, DIR, false>(p, nf, n_outer, name, stream);
 }
@@ -233,6 +248,10 @@ int launch_strided_fast_v(const FastParams& p, int nf, int n_outer, const char* 
         FastParams q = p;
         q.gx = (int)grid.x; q.gy = (int)grid.y; q.gz = (int)grid.z;
         const long long ntiles = (long long)q.gx * q.gy * q.gz;
+        const long long gxy = (long long)q.gx * q.gy;
+        if (ntiles >= (1LL << 32) / gxy) { set_error("strided_fast: %lld tiles exceed the range of the tile decode", ntiles); return -1; }
+        q.mx = (unsigned)(((1ULL << 32) + q.gx - 1) / q.gx);
+        q.mxy = (unsigned)(((1ULL << 32) + gxy - 1) / gxy);
         const bool peer = p.so.peer_tab != nullptr;
         const long long lim = (peer && g_peer_pass_ctas > 0 && g_peer_pass_ctas < ntiles) ? g_peer_pass_ctas : ntiles;
         prof_begin(name, stream);

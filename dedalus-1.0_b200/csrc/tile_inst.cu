@@ -3,6 +3,7 @@
 // instantiation (mixed radix, fft_core.cuh RtFac) that serves every length without a unit of its own.
 #include "tile_kernel.cuh"
 #include "fast_kernels.cuh"
+#include "fast_staged.cuh"
 #include "xfused_kernel.cuh"
 #include "xfused_persist.cuh"
 

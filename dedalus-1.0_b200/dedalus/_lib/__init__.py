@@ -22,7 +22,7 @@ EXPORTS = [
     "ddl_rk4_stage", "ddl_cn_step", "ddl_step_array", "ddl_stage_outside", "ddl_rhs_stage", "ddl_slab_assemble_stage", "ddl_slab_info", "ddl_slab_rows", "ddl_slab_theta", "ddl_slab_zinv", "ddl_slab_yinv",
     "ddl_slab_xfused", "ddl_slab_xc2r", "ddl_slab_xr2c", "ddl_slab_yfwd", "ddl_slab_zfwd", "ddl_slab_assemble",
     "ddl_p2p_create", "ddl_p2p_connect", "ddl_p2p_base", "ddl_p2p_exchange", "ddl_p2p_wait", "ddl_p2p_destroy",
-    "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count",
+    "ddl_p2p_peer_base", "ddl_p2p_signal", "ddl_p2p_push", "ddl_slab_yfwd_planes", "ddl_slab_zinv_peer", "ddl_slab_yfwd_peer", "ddl_slab_xfused_planes", "ddl_launch_count",
     "ddl_reduce_invariants", "ddl_reduce_outside_mask", "ddl_reduce_max_square", "ddl_rhs_capture_max", "ddl_set_shear", "ddl_profile_enable", "ddl_profile_report", "ddl_measure_fp64", "ddl_set_option", "ddl_sync", "ddl_last_error", "ddl_version",
 ]
 
@@ -95,6 +95,9 @@ def bind_slab(lib):
         lib.ddl_p2p_peer_base.restype = vp
         lib.ddl_p2p_signal.argtypes = [vp, vp]
         lib.ddl_p2p_signal.restype = C.c_longlong
+        lib.ddl_p2p_push.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+        lib.ddl_p2p_push.restype = C.c_longlong
+        lib.ddl_slab_yfwd_planes.argtypes = [vp, i32, vp, vp, i32, i32, vp]
         lib.ddl_slab_zinv_peer.argtypes = [vp, i32, vp, vp, vp]
         lib.ddl_slab_yfwd_peer.argtypes = [vp, i32, vp, vp, i32, i32, vp]
         lib.ddl_slab_xfused_planes.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]

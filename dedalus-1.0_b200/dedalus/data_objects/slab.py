@@ -95,7 +95,9 @@ class SlabPipeline(object):
         "collective" = torch.distributed all_to_all_single (NCCL / gloo);
         "p2p"  = CUDA-IPC arenas + copy-engine pushes + arrival flags (csrc/p2p.cu);
         "peer" = the producing z / y pass stores straight into the peers' arenas over NVLink
-                 (no send buffer, no copy) + arrival flags; the default on the GPU box."""
+                 (no send buffer, no copy) + arrival flags;
+        "push" = the passes write locally and a small SM kernel on a second stream pushes the blocks to the peers
+                 (csrc/p2p.cu p2p_push_kernel) while the next passes run: the all-to-all overlapped with the 1-D transforms."""
         self.lib, self.h, self.device, self.group = lib, handle, device, group
         self.exchange_kind = exchange
         self._p2p = None
@@ -123,6 +125,7 @@ class SlabPipeline(object):
         # CTAs the peer-store passes may occupy (include/ddl.h "peer_pass_ctas"; 0 = one per tile) and whether the stream
         # they run on outranks the main stream, so that their few CTAs are placed as soon as an SM has room
         self.peer_ctas = int(os.environ.get("DEDALUS_PEER_CTAS", "0"))
+        self.push_ctas = int(os.environ.get("DEDALUS_PUSH_CTAS", "32"))       # CTAs of the push kernel ("push" exchange)
         self.side_priority = os.environ.get("DEDALUS_SIDE_PRIORITY", "0") == "1"
         self.trace = None               # profiling only: list collecting (label, torch.cuda.Event) marks of rhs()
         self.skip_exchange = False      # profiling only (profiles/slab_breakdown.py): time the passes without the all-to-all
@@ -171,6 +174,7 @@ class SlabPipeline(object):
         self._check(lib.ddl_p2p_connect(ctx, b"".join(gathered)))
         self._p2p = ctx
         self._p2p_nmax = nmax
+        self._p2p_layout = lay
         base = int(lib.ddl_p2p_base(ctx))
         self._p2p_xs = [_Raw(base + o) for o in lay["xs"]]
         self._p2p_ks = [_Raw(base + o) for o in lay["ks"]]
@@ -258,6 +262,95 @@ class SlabPipeline(object):
             t.wait()
             self._check(lib.ddl_slab_zfwd(h, no, _ptrs(ks[:no]), _ptrs(b["e"][:no]), 0, side.cuda_stream))
         main.wait_stream(side)
+        self._mark("y_fwd+z_fwd")
+        self._assemble(physics_id, pp, b["e"][:no], state, deriv, fuse, main.cuda_stream)
+        self._mark("assemble")
+
+    # ------------------------------------------------------------------ "push" exchange
+    def _push_table(self, key):
+        """ctypes argument block of ddl_p2p_push for ("inv", f0, f1) -- my k-side blocks of fields f0..f1 to the peers' x-side
+        rows -- or ("fwd", nf, z0, nzc) -- planes [z0, z0 + nzc) of the peers' rows of my x-side fields 0..nf to my block of
+        their k-side fields.  Offsets from arena_layout (tests/test_slab_layout.py); built once per key."""
+        tabs = self.__dict__.setdefault("_push_tabs", {})
+        t = tabs.get(key)
+        if t is None:
+            lay = self._p2p_layout
+            el, blk = 16, self.nzl * self.cx
+            ranks, src, dst, rb, nr, pitch = [], [], [], [], [], []
+            if key[0] == "inv":
+                for f in range(key[1], key[2]):
+                    order, so, do, nb = lay["inv"][f]
+                    for i, s in enumerate(order):
+                        ranks.append(s); src.append(so[i]); dst.append(do[i]); rb.append(nb[i]); nr.append(1); pitch.append(nb[i])
+            else:
+                _, nf, z0, nzc = key
+                for f in range(nf):
+                    order, so, do, nb = lay["fwd"][f]
+                    for i, s in enumerate(order):
+                        ranks.append(s); src.append(so[i] + z0 * self.cx * el); dst.append(do[i] + z0 * self.cx * el)
+                        rb.append(nzc * self.cx * el); nr.append(self.rows[s]); pitch.append(blk * el)
+            arr = lambda vals, t: (t * len(vals))(*vals)
+            t = tabs[key] = (len(ranks), arr(ranks, C.c_int), arr(src, C.c_int64), arr(dst, C.c_int64), arr(rb, C.c_int64),
+                             arr(nr, C.c_int64), arr(pitch, C.c_int64))
+        return t
+
+    def _push(self, key, publish, stream):
+        n, ranks, src, dst, rb, nr, pitch = self._push_table(key)
+        seq = self.lib.ddl_p2p_push(self._p2p, n, ranks, src, dst, rb, nr, pitch, self.push_ctas, 1 if publish else 0, stream.cuda_stream)
+        if seq < 0:
+            self._check(int(seq))
+        if publish:
+            self.exchanges += 1
+        return seq
+
+    def _rhs_push(self, physics_id, pp, state, deriv, ni, no, fuse=None):
+        """RHS with the all-to-all carried by a small SM kernel on a second (high-priority) stream: every pass reads and writes
+        local memory only (so it runs at its HBM / FP64 speed), the blocks it produced are pushed to the peers over NVLink
+        while the following passes run, and a pass waits for arrival flags only.  Inverse half: field groups (z pass of
+        group g+1 and y pass of group g-1 overlap the push of group g); forward half: plane chunks (the push of chunk c
+        overlaps the x and y passes of chunk c+1)."""
+        lib, h = self.lib, self.h
+        b = self._p2p_buffers(ni, no)
+        ks, xs = b["ks"], b["xs"]
+        main, side = torch.cuda.current_stream(), self._side
+        self._mark("start")
+        ng = min(self.inverse_groups, ni) if self.inverse_groups else (1 if self.inverse_batched else ni)
+        bounds = [(g * ni) // ng for g in range(ng + 1)]
+        sent = []
+        for g in range(ng):
+            f0, f1 = bounds[g], bounds[g + 1]
+            self._check(lib.ddl_slab_zinv(h, f1 - f0, _ptrs(state[f0:f1]), _ptrs(ks[f0:f1]), main.cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            seq = self._push(("inv", f0, f1), True, side)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            sent.append((seq, ev))
+        self._mark("z_inv")
+        for g in range(ng):
+            f0, f1 = bounds[g], bounds[g + 1]
+            seq, ev = sent[g]
+            main.wait_event(ev)                                          # my own block (a local copy inside the push)
+            self._check(lib.ddl_p2p_wait(self._p2p, seq, main.cuda_stream))   # the peers' blocks: arrival flags
+            self._check(lib.ddl_slab_yinv(h, f1 - f0, _ptrs(xs[f0:f1]), _ptrs(b["b"][f0:f1]), main.cuda_stream))
+        self._mark("wait+y_inv")
+        nch = self.chunks if self.nzl % self.chunks == 0 else 1
+        zc = self.nzl // nch
+        bin_, cout, xout = _ptrs(b["b"][:ni]), _ptrs(b["c"][:no]), _ptrs(xs[:no])
+        for c in range(nch):
+            self._check(lib.ddl_slab_xfused_planes(h, physics_id, pp, bin_, cout, c * zc, zc, main.cuda_stream))
+            self._check(lib.ddl_slab_yfwd_planes(h, no, cout, xout, c * zc, zc, main.cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            seq = self._push(("fwd", no, c * zc, zc), c == nch - 1, side)
+        self._mark("x_fused")
+        ev = torch.cuda.Event()
+        ev.record(side)
+        main.wait_event(ev)
+        self._check(lib.ddl_p2p_wait(self._p2p, seq, main.cuda_stream))
+        self._check(lib.ddl_slab_zfwd(h, no, _ptrs(ks[:no]), _ptrs(b["e"][:no]), 0, main.cuda_stream))
         self._mark("y_fwd+z_fwd")
         self._assemble(physics_id, pp, b["e"][:no], state, deriv, fuse, main.cuda_stream)
         self._mark("assemble")
@@ -361,6 +454,7 @@ class SlabPipeline(object):
         adv = physics_id >= 3
         p2p = self.exchange_kind == "p2p" and self.P > 1 and not self.skip_exchange and not adv
         peer = self.exchange_kind == "peer" and self.P > 1 and not self.skip_exchange and not adv
+        push = self.exchange_kind == "push" and self.P > 1 and not self.skip_exchange and not adv
         pp = C.byref(params)
         if dealias_state:
             for t in state[:ncomp]:
@@ -372,6 +466,8 @@ class SlabPipeline(object):
                 self._check(lib.ddl_dealias(h, t.data_ptr(), st))
         if peer:
             return self._rhs_peer(physics_id, pp, state, deriv, ni, no, fuse)
+        if push:
+            return self._rhs_push(physics_id, pp, state, deriv, ni, no, fuse)
         b = dict(self.buffers(ni, no)) if not p2p else dict(self._p2p_buffers(ni, no))
         ks, xs = b["ks"], b["xs"]
         self._mark("start")

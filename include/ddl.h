@@ -190,6 +190,17 @@ int ddl_p2p_wait(ddl_p2p* ctx, long long seq, void* stream);
  * built from ddl_p2p_peer_base.  ddl_p2p_signal then publishes the arrival flag behind the pass. */
 void* ddl_p2p_peer_base(ddl_p2p* ctx, int rank);
 long long ddl_p2p_signal(ddl_p2p* ctx, void* stream);
+/* The same blocks as ddl_p2p_exchange, moved by a small SM kernel on `stream` instead of the copy engines (which lose most of
+ * their rate while an HBM-bound pass runs): entry i = nrows[i] rows of row_bytes[i] bytes, pitch[i] bytes apart on both sides
+ * (all multiples of 16), from this arena + src_off[i] to rank dst_rank[i]'s arena + dst_off[i].  A few CTAs (`ctas`, 0 = 32)
+ * without shared memory saturate NVLink and share the SMs with the pass running on another stream -- the all-to-all FFTW-MPI
+ * performs inside every transform (_fftw.pyx:272-304), overlapped with the 1-D transforms.  publish = 1: raise this
+ * exchange's arrival flag in every peer behind the copies and return its sequence number; 0: return 0 (more chunks follow). */
+long long ddl_p2p_push(ddl_p2p* ctx, int n, const int* dst_rank, const int64_t* src_off, const int64_t* dst_off,
+                       const int64_t* row_bytes, const int64_t* nrows, const int64_t* pitch, int ctas, int publish, void* stream);
+/* forward y pass of local planes [z0, z0 + nzc) only, full-size arrays on both sides (chunked so that the push of chunk c
+ * overlaps the x pass of chunk c + 1): c_in[f] = C[nzl][y][CX]  ->  xs_out[f] = x-side pencils [cy][nzl][CX] */
+int ddl_slab_yfwd_planes(ddl_plan* plan, int nf, void* const* c_in, void* const* xs_out, int z0, int nzc, void* stream);
 int ddl_slab_zinv_peer(ddl_plan* plan, int nf, void* const* k_in, void* const* peer_tab, void* stream);
 /* yfwd_peer and xfused_planes work on local planes [z0, z0 + nzc) only, so that the forward y
  * pass of one chunk (NVLink-bound) overlaps the x pass of the next (compute-bound) */

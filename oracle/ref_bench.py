@@ -67,6 +67,28 @@ def restated_rk4(ts_mod, RHS):
     return RK4(RHS)
 
 
+def restated_cn(ts_mod, RHS):
+    """CrankNicholsonVisc.do_advance (time_step.py:486-506, which cannot run as shipped) restated around the
+    REFERENCE's RHS: per component y+ = ((1/dt - IF/2) y + N(y)) / (1/dt + IF/2), IF = 0 where the factor is None."""
+
+    class CN(ts_mod.TimeStepBase):
+        def __init__(self, RHS):
+            ts_mod.TimeStepBase.__init__(self, RHS)
+            self.deriv = RHS.create_fields(0.)
+
+        def do_advance(self, data, dt):
+            self.RHS.RHS(data, self.deriv)
+            for fn, f in data:
+                for i, c in f:
+                    IF = self.deriv[fn][i].integrating_factor
+                    IF = 0. if IF is None else IF
+                    c['kspace'] = ((1. / dt - IF / 2.) * c['kspace'] + self.deriv[fn][i]['kspace']) / (1. / dt + IF / 2.)
+            data.set_time(data.time + dt)
+            self.time += dt
+            self.iteration += 1
+    return CN(RHS)
+
+
 class _ThreadedFFT(object):
     """numpy.fft's interface on scipy.fft with `workers` threads: the one part of the reference's numpy route
     (representations.py:327-333) that can use more than one core without touching its code."""

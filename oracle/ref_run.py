@@ -8,6 +8,7 @@ What runs is the reference itself (oracle/_ref: its physics.py RHS, its represen
 the numpy FFT backend, its verbatim-compiled Cython stage kernels):
 
   * RK2mid / RK2trap: the reference's integrator classes, unmodified (time_step.py:275-392);
+  * CrankNicholsonVisc: likewise restated (time_step.py:486-506) around the reference's RHS (ref_bench.restated_cn);
   * RK4: the reference cannot run its own (time_step.py:209,214,449), so the
     data flow of time_step.py:426-483 is restated around the reference's RHS and its Cython
     euler / etd1 kernels (oracle/ref_bench.py restated_rk4).
@@ -52,7 +53,12 @@ def run(a):
     assert y0.shape[0] == len(comps), (y0.shape, len(comps))
     for j, c in enumerate(comps):
         c['kspace'] = np.array(y0[j])
-    ti = ref_bench.restated_rk4(ts, RHS) if a.integ == "RK4" else getattr(ts, a.integ)(RHS)
+    if a.integ == "RK4":
+        ti = ref_bench.restated_rk4(ts, RHS)
+    elif a.integ == "CrankNicholsonVisc":
+        ti = ref_bench.restated_cn(ts, RHS)
+    else:
+        ti = getattr(ts, a.integ)(RHS)
     t0 = time.perf_counter()
     for _ in range(a.steps):
         ti.do_advance(data, a.dt)

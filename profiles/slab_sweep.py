@@ -39,8 +39,12 @@ for _ in range(3):
 pipe = next(data.components())[2]._plan.pipeline
 nk = a.n * a.n * (a.n // 2 + 1)
 
-# (chunks, inverse, peer_ctas, side_priority)
-CONFIGS = [(4, "batched", 0, 0), (2, "batched", 0, 0), (8, "batched", 0, 0), (16, "batched", 0, 0), (4, "groups:2", 0, 0),
+# (chunks, inverse, peer_ctas [peer] / push_ctas [push], side_priority[, exchange kind = "peer"])
+CONFIGS = [(4, "batched", 0, 0), (2, "batched", 0, 0), (4, "batched", 64, 1), (4, "batched", 74, 1), (4, "batched", 96, 1), (4, "batched", 110, 1),
+           (8, "batched", 74, 1), (8, "batched", 96, 1), (8, "groups:2", 74, 1), (8, "groups:2", 96, 1), (8, "groups:3", 74, 1), (8, "groups:3", 96, 1),
+           (16, "groups:2", 96, 1), (4, "groups:2", 96, 1), (8, "groups:2", 96, 0), (8, "groups:2", 120, 1),
+           (4, "groups:3", 96, 1, "push"), (4, "groups:3", 128, 1, "push"), (8, "groups:3", 148, 1, "push")]
+_OLD = [(4, "batched", 0, 0), (2, "batched", 0, 0), (8, "batched", 0, 0), (16, "batched", 0, 0), (4, "groups:2", 0, 0),
            (4, "groups:3", 0, 0), (4, "fields", 0, 0), (8, "groups:2", 0, 0), (4, "batched", 0, 1), (8, "groups:2", 0, 1),
            (4, "batched", 148, 1), (4, "batched", 296, 1), (4, "batched", 444, 1), (8, "batched", 296, 1), (8, "groups:2", 148, 1),
            (8, "groups:2", 296, 1), (8, "groups:2", 444, 1), (8, "groups:3", 296, 1), (16, "groups:2", 296, 1), (8, "groups:2", 296, 0)]
@@ -49,7 +53,12 @@ if a.configs:
 
 
 def run(cfg):
-    chunks, inverse, ctas, prio = cfg
+    chunks, inverse, ctas, prio = cfg[:4]
+    kind = cfg[4] if len(cfg) > 4 else "peer"
+    pipe.exchange_kind = kind
+    if kind == "push":
+        pipe.push_ctas = ctas
+        ctas = 0
     pipe.chunks = chunks
     pipe.inverse_batched = inverse == "batched"
     pipe.inverse_groups = int(inverse.split(":")[1]) if inverse.startswith("groups:") else 0
@@ -75,9 +84,22 @@ for cfg in CONFIGS:
     ms = run(cfg)
     if rank == 0:
         rec = {"world": world, "n": a.n, "chunks": cfg[0], "inverse": cfg[1], "peer_pass_ctas": cfg[2], "side_priority": cfg[3],
-               "ms_per_step": round(ms, 3), "upd_per_s": 4 * nk / (ms * 1e-3)}
+               "exchange": cfg[4] if len(cfg) > 4 else "peer", "ms_per_step": round(ms, 3), "upd_per_s": 4 * nk / (ms * 1e-3)}
         out.append(rec)
         print(json.dumps(rec), flush=True)
+# per-kernel CUDA-event totals of one step for the first and the best configuration (launch labels of csrc/; "push" = the copy kernel)
+best = min(range(len(CONFIGS)), key=lambda i: out[i]["ms_per_step"]) if rank == 0 else 0
+bt = torch.tensor([best], device="cuda")
+dist.broadcast(bt, 0)
+for i in sorted({0, int(bt.item())}):
+    run(CONFIGS[i])
+    L.profile(True)
+    ti.do_advance(data, dt)
+    prof = L.profile_report()
+    L.profile(False)
+    if rank == 0:
+        print(json.dumps({"world": world, "config": list(CONFIGS[i]), "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
+                          "launches": {k: v["n"] for k, v in prof.items()}}), flush=True)
 ek = va.ekin(data, reduce_all=True)
 if rank == 0:
     print(json.dumps({"world": world, "ekin_after_all": ek, "best": min(out, key=lambda r: r["ms_per_step"])}))

@@ -13,7 +13,7 @@ BUILD = os.path.join(ROOT, "dedalus-1.0_b200", "build")
 
 # kernel family -> largest CTA its launcher asks for (csrc/api.cu round32, pointwise.cuh, reduce.cuh, p2p.cu)
 MAX_THREADS = {"ddl::tile_kernel": 768, "ddl::items_kernel": 256, "ddl::reduce_kernel": 256, "ddl::reduce_final_kernel": 256,
-               "ddl::p2p_wait_kernel": 32, "ddl::p2p_signal_kernel": 32, "ddl::fp64_rate_kernel": 256}
+               "ddl::p2p_wait_kernel": 32, "ddl::p2p_signal_kernel": 32, "ddl::fp64_rate_kernel": 256, "ddl::p2p_push_kernel": 1024}
 
 
 def _entries():
@@ -40,7 +40,7 @@ def test_every_kernel_fits_its_largest_launch():
             assert warps * per_warp <= 65536, (name, regs, MAX_THREADS[family])
         else:
             # xfused_kernel / strided_fast carry __maxnreg__ / __launch_bounds__ derived from their own CTA shape
-            assert family in ("ddl::xfused_kernel", "ddl::xfused_persist_kernel", "ddl::strided_fast"), name
+            assert family in ("ddl::xfused_kernel", "ddl::xfused_persist_kernel", "ddl::strided_fast", "ddl::strided_staged"), name
     for family in MAX_THREADS:
         assert seen[family] > 0, family
 

@@ -34,6 +34,9 @@ TUNED = dict(DEDALUS_SLAB_INVERSE="groups:2", DEDALUS_PEER_CTAS="24", DEDALUS_SI
 @pytest.mark.parametrize("world,layout,exchange,knobs", [
     (2, "block", "peer", {}), (2, "cyclic", "peer", {}), (2, "block", "collective", {}), (2, "cyclic", "p2p", {}),
     (2, "cyclic", "peer", TUNED), (2, "block", "peer", dict(TUNED, DEDALUS_SLAB_INVERSE="fields", DEDALUS_PEER_CTAS="7")),
+    (2, "cyclic", "push", {}), (2, "block", "push", dict(DEDALUS_SLAB_INVERSE="groups:3", DEDALUS_SLAB_CHUNKS="8", DEDALUS_PUSH_CTAS="5",
+                                                          DEDALUS_SIDE_PRIORITY="1")),
+    (4, "cyclic", "push", dict(DEDALUS_SLAB_INVERSE="groups:2")), (8, "cyclic", "push", dict(DEDALUS_SLAB_INVERSE="groups:3", DEDALUS_SLAB_CHUNKS="8")),
     (4, "cyclic", "peer", {}), (4, "cyclic", "peer", TUNED), (8, "block", "peer", {}), (8, "cyclic", "peer", {}), (8, "cyclic", "peer", TUNED)])
 def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, knobs, tmp_path):
     if _ngpu() < world:

@@ -51,3 +51,18 @@ def test_harness_reproduces_the_reference_rk2mid(tmp_path):
     for _ in range(3):
         ti.do_advance(do, dt)
     assert rel(do.kvector(), y1) < 1e-13
+
+
+@pytest.mark.parametrize("physics,shape,params,dt", [CASES[0], CASES[3], CASES[5], CASES[6]])
+def test_oracle_cn_equals_reference_code_under_restated_glue(tmp_path, physics, shape, params, dt):
+    """CrankNicholsonVisc (time_step.py:486-506, not runnable as shipped) restated around the reference's own RHS."""
+    Po = oracle_physics(physics, shape, None, params)
+    do = orc.synthetic_ic(Po, 6)
+    direction = ("y" if len(shape) == 2 else "z") if physics == "BoussinesqHydro" else None
+    y1, meta = run_reference(tmp_path, physics, shape, do.kvector().copy(), "CrankNicholsonVisc", 3, dt, params, threads=1,
+                             direction=direction)
+    ti = orc.CrankNicholsonVisc(Po)
+    for _ in range(3):
+        ti.do_advance(do, dt)
+    assert rel(do.kvector(), y1) < 1e-13
+    assert abs(do.time - meta["time"]) < 1e-14
