@@ -1014,7 +1014,7 @@ static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void*
         for (int f = 0; f < ni; ++f) { A[f] = r0 + f * s.ks; B[f] = r1 + f * s.b; }
         for (int f = 0; f < no; ++f) { C[f] = r2 + f * s.b; D[f] = r0 + f * s.ks; E[f] = r1 + f * s.e; }
         DDL_TRY(phase_zinv(pl, ni, (const void* const*)state, A.data(), st));
-        // Opt-in experiment (ddl_set_option("rhs_plane_chunk", n), default off, NOT YET TIMED): y_inv -> x -> y_fwd over chunks of n
+        // Opt-in experiment (ddl_set_option("rhs_plane_chunk", n), default off; measured in round 2: 12.2-18.9 ms per RHS against 10.6 ms, profiles/r2/devcheck_b200_r2_first.txt): y_inv -> x -> y_fwd over chunks of n
         // z-planes with chunk-sized b / c arrays that every chunk reuses, so that the half-transformed lines (22 of the 52 GB a
         // 512^3 MHD stage moves) can live in the 126 MB L2 instead of crossing HBM twice.  15 fields x 1.44 MB per plane: n <= 4.
         const long long cb = (long long)g_plane_chunk * Y.n * kx_pitch(pl);

@@ -472,8 +472,9 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
 // Launch variants (ddl_set_option("xfused_variant", v); the default is the measured best):
 //   0: 6 warps per CTA, 3 CTAs per SM   1: 9 warps per CTA, 2 CTAs per SM   2: 6 warps, 2 CTAs (more registers)
 //   3: shape 0 with the retained-mode count of the 2/3 rule (N/3 + 1) as a compile-time constant; falls back to 0 for
-//      any other mask.  NOT YET TIMED (added after the round's GPU budget was spent; cuobjdump: 2 296 -> 1 960 static
-//      instructions for <512, MHD3C>): round 2 measures it with profiles/kernel_times.py --opt xfused_variant=0,3
+//      any other mask.  Measured (profiles/r2/devcheck_b200_xfused_variants.txt): 4.30 ms against 4.12 ms for variant 0 although it has
+//      336 fewer static instructions (cuobjdump: 2 296 -> 1 960 for <512, MHD3C>): opt-in.
+//   4: persistent CTAs, next pair staged by cp.async.bulk + mbarrier (xfused_persist.cuh): 4.92 ms, opt-in
 template <int N, class PHYS, int V> struct XFusedCfg {
     static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
     static constexpr int G = (N >= 512) ? 1 : 512 / N;

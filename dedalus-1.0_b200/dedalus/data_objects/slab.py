@@ -116,7 +116,7 @@ class SlabPipeline(object):
         self._bufs = {}
         self.exchanges = 0
         import os
-        self.chunks = int(os.environ.get("DEDALUS_SLAB_CHUNKS", "4"))     # plane chunks of the forward x / y passes (peer exchange)
+        self.chunks = int(os.environ.get("DEDALUS_SLAB_CHUNKS", "2"))     # plane chunks of the forward x / y passes (peer exchange)
         # inverse half: "batched" = one z pass and one y pass for all fields; "groups:G" = G field groups, the y pass of
         # group g on the side stream while the (NVLink-bound) z pass of group g+1 pushes its rows; "fields" = one group per field
         inv = os.environ.get("DEDALUS_SLAB_INVERSE", "batched")

@@ -17,7 +17,7 @@ timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 tests/native/_
 echo "racecheck all kernels 128: exit $?"; tail -3 gpurun_out/sanitizer_racecheck_all128.log
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
   for ex in peer push; do
-    DEDALUS_KY_LAYOUT=cyclic DEDALUS_SLAB_EXCHANGE=$ex timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 \
+    DEDALUS_KY_LAYOUT=cyclic DEDALUS_SLAB_EXCHANGE=$ex timeout 420 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 \
       python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2957$((RANDOM % 10)) \
       tests/slab_asym_worker.py gpurun_out/sanitize_slab_$ex.json > gpurun_out/sanitizer_memcheck_slab2_$ex.log 2>&1
     echo "memcheck 2-GPU slab ($ex): exit $?"; grep -E "ERROR SUMMARY|rel" gpurun_out/sanitizer_memcheck_slab2_$ex.log | tail -4

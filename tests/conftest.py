@@ -94,7 +94,7 @@ def pytest_collection_modifyitems(config, items):
     needs_device = pytest.mark.skip(reason="host emulation: needs the CUDA device (graphs, peer memory, NCCL)")
     for item in items:
         if _points(item) > HOST_EMUL_MAX_POINTS or "full_size" in item.name or "512" in item.name or "256cubed" in item.name \
-                or "128cubed" in item.name:
+                or "128cubed" in item.name or "async_staging" in item.name:
             item.add_marker(big)
         if "cuda_graph" in item.name or "test_gpu_slab" in item.nodeid:
             item.add_marker(needs_device)

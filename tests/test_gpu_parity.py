@@ -483,3 +483,35 @@ def test_unfused_helpers_reproduce_the_fused_mhd_rhs():
     P.curlX(aux["mathvector"], deriv["B"])
     assert rel(get_state(deriv), get_state(fused)) < 1e-12
     assert rel(get_state(data), y0) < 1e-13          # the helpers leave the (dealiased) state intact
+
+
+@pytest.mark.parametrize("shape", [(16, 512, 512), (512, 16, 512)])
+def test_opt_in_async_staging_kernels_reproduce_the_default_ones(shape):
+    """The two async-copy variants built in round 2 and kept opt-in because they measured slower: the persistent
+    x pass with cp.async.bulk + mbarrier staging (xfused_variant = 4) and the persistent strided pass with cp.async staging
+    (strided_staged = 1).  Same butterflies in the same order: the staged strided pass is bit-identical, the x pass to round-off."""
+    import dedalus._lib as L
+    params = dict(nu=1e-3, eta=1e-3)
+    P = dev_physics("IncompressibleMHD", shape, None, params)
+    data, deriv = P.create_fields(0.), P.create_fields(0.)
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for _, f in data:
+        for _, c in f:
+            c["xspace"] = torch.randn(*shape, dtype=torch.float64, generator=g)
+            c["kspace"]
+        f.div_free()
+    out = {}
+    for tag, opts in (("default", {}), ("staged", {"strided_staged": 1}), ("persist", {"xfused_variant": 4})):
+        for k, v in opts.items():
+            L.set_option(k, v)
+        try:
+            P.RHS(data, deriv)
+            out[tag] = get_state(deriv)
+        finally:
+            for k in opts:
+                L.set_option(k, 0)
+    assert np.array_equal(out["staged"], out["default"])
+    assert rel(out["persist"], out["default"]) < 1e-14
+    assert np.isfinite(out["default"]).all() and np.abs(out["default"]).max() > 0
+
