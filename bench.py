@@ -441,6 +441,19 @@ def run_ours(args):
     # same host buffers.  Uploads and downloads run on their own streams: the upload of component c for
     # step n+1 starts as soon as the download of component c of step n has landed (PCIe is full duplex),
     # the step itself waits for all components.  Every byte crosses PCIe in both directions every step.
+    if args.skip_e2e:
+        # auxiliary runs only (config 5 at 1024^3: 52 GB of pinned host memory over 8 ranks); the headline run never skips it
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": {"workload": "3D incompressible MHD %d^3 RK4, 2/3 dealiasing, nu=eta=1e-3" % n, "N_k": nk,
+                                               "parallelism": "slab%d" % world if world > 1 else "single GPU"},
+               "clocks": clocks, "e2e": None, "gpu_launches": launches, "roofline": roofline, "invariants": {"ekin": ekin, "emag": emag},
+               "parity": parity, "note": "--skip-e2e: auxiliary run, no end-to-end leg"}
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     comps = [c for _, _, c in data.components()]
     host = [torch.empty(c._k.shape, dtype=c._k.dtype, pin_memory=True) for c in comps]
     for h, c in zip(host, comps):
@@ -603,6 +616,7 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--quick", action="store_true", help="timed region only (for runs under ncu)")
+    ap.add_argument("--skip-e2e", action="store_true", help="auxiliary runs only: no end-to-end leg (1024^3 would pin 52 GB of host memory)")
     ap.add_argument("--e2e-full", action="store_true", help="end-to-end leg: move the full arrays (default: the retained box only)")
     a = ap.parse_args()
     if a.impl == "reference":

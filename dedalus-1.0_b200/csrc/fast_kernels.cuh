@@ -35,6 +35,20 @@ struct FastSide {
     long long peer_off;       // added to every peer address (sub-range of outer planes)
 };
 
+// tile t -> (inner chunk bx, outer by, field bz) of a gx x gy x gz tile grid without integer division: t / d == umulhi(t, m) with
+// m = ceil(2^32 / d) for t < 2^32 / d (checked by the launchers); d == 1 has no such 32-bit m (2^32) and is the identity
+struct TileDecode {
+    int gx, gxy;
+    unsigned mx, mxy;
+};
+__device__ __forceinline__ void tile_decode(const TileDecode& d, int t, int& bx, int& by, int& bz) {
+    bz = d.gxy == 1 ? t : (int)__umulhi((unsigned)t, d.mxy);
+    const int rem = t - bz * d.gxy;
+    by = d.gx == 1 ? rem : (int)__umulhi((unsigned)rem, d.mx);
+    bx = rem - by * d.gx;
+}
+inline unsigned tile_magic(long long d) { return d <= 1 ? 0u : (unsigned)(((1ULL << 32) + d - 1) / d); }
+
 __device__ __forceinline__ long long fast_row_off(const FastSide& s, int r) {
     return (long long)(r >> s.split_shift) * s.s_blk + (long long)(r & s.split_mask) * s.s_n;
 }
@@ -131,12 +145,7 @@ strided_fast(const __grid_constant__ FastParams p) {
     // EXT: tile -> (inner chunk, outer, field) by multiply-high (p.mx, p.mxy: exact below 2^32 / divisor, checked by the launcher);
     // three integer divisions per tile and thread would cost a measurable part of a butterfly stage
     int bx = (int)blockIdx.x, by = (int)blockIdx.y, bz = (int)blockIdx.z;
-    if constexpr (EXT) {
-        bz = (int)__umulhi((unsigned)t, p.mxy);
-        const int rem = t - bz * (p.gx * p.gy);
-        by = (int)__umulhi((unsigned)rem, p.mx);
-        bx = rem - by * p.gx;
-    }
+    if constexpr (EXT) tile_decode(TileDecode{p.gx, p.gx * p.gy, p.mx, p.mxy}, t, bx, by, bz);
     if (EXT && t != (int)blockIdx.x) __syncthreads();        // the previous tile's last stage has read the shared tile
     const int inner = bx * CX + c;
     const bool live = inner < p.inner_len;
@@ -250,8 +259,8 @@ int launch_strided_fast_v(const FastParams& p, int nf, int n_outer, const char* 
         const long long ntiles = (long long)q.gx * q.gy * q.gz;
         const long long gxy = (long long)q.gx * q.gy;
         if (ntiles >= (1LL << 32) / gxy) { set_error("strided_fast: %lld tiles exceed the range of the tile decode", ntiles); return -1; }
-        q.mx = (unsigned)(((1ULL << 32) + q.gx - 1) / q.gx);
-        q.mxy = (unsigned)(((1ULL << 32) + gxy - 1) / gxy);
+        q.mx = tile_magic(q.gx);
+        q.mxy = tile_magic(gxy);
         const bool peer = p.so.peer_tab != nullptr;
         const long long lim = (peer && g_peer_pass_ctas > 0 && g_peer_pass_ctas < ntiles) ? g_peer_pass_ctas : ntiles;
         prof_begin(name, stream);

@@ -58,12 +58,7 @@ strided_staged(const __grid_constant__ FastParams p) {
         return -1;
     };
     // tile t -> (inner chunk, outer, field) without integer divisions (three per tile and thread would cost as much as a butterfly)
-    auto decode = [&](int t, int& bx, int& by, int& bz) {
-        bz = (int)__umulhi((unsigned)t, p.mxy);
-        const int rem = t - bz * (p.gx * p.gy);
-        by = (int)__umulhi((unsigned)rem, p.mx);
-        bx = rem - by * p.gx;
-    };
+    auto decode = [&](int t, int& bx, int& by, int& bz) { tile_decode(TileDecode{p.gx, p.gx * p.gy, p.mx, p.mxy}, t, bx, by, bz); };
     auto prefetch = [&](int t) {
         int bx, by, bz;
         decode(t, bx, by, bz);
@@ -171,8 +166,8 @@ int launch_strided_staged(const FastParams& p, int nf, int n_outer, const char* 
         if (ntiles < 1) return 0;
         const long long gxy = (long long)q.gx * q.gy;
         if (ntiles >= (1LL << 32) / gxy) return 1;             // the multiply-high decode is exact below 2^32 / divisor
-        q.mx = (unsigned)(((1ULL << 32) + q.gx - 1) / q.gx);
-        q.mxy = (unsigned)(((1ULL << 32) + gxy - 1) / gxy);
+        q.mx = tile_magic(q.gx);
+        q.mxy = tile_magic(gxy);
         const int grid = (int)(ntiles < ctas ? ntiles : ctas);
         prof_begin(name, stream);
         kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(q);

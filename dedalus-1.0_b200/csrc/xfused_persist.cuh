@@ -128,7 +128,11 @@ xfused_persist_kernel(const __grid_constant__ XFusedParams p, int n_outer, int p
                 }
                 v[j] = z;
             }
-            // the staged lines of this pencil are in registers: one arrival per inverse warp frees the buffer
+            // the staged lines of this pencil are in registers: one arrival per inverse warp frees the buffer.  The reads above went
+            // through the generic proxy, the refill will be written by the async proxy: fence.proxy.async orders the two (the
+            // mbarrier release / acquire pair orders the threads).  compute-sanitizer's racecheck does not follow this hand-over
+            // and reports the refill against these reads (profiles/r2/sanitizer_racecheck_xfused512.log).
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (a == 0) xp_mbar_arrive(empty);
             xdft<R0, +1>(v);

@@ -127,6 +127,11 @@ class SlabPipeline(object):
         self.peer_ctas = int(os.environ.get("DEDALUS_PEER_CTAS", "0"))
         self.push_ctas = int(os.environ.get("DEDALUS_PUSH_CTAS", "32"))       # CTAs of the push kernel ("push" exchange)
         self.side_priority = os.environ.get("DEDALUS_SIDE_PRIORITY", "0") == "1"
+        # tests only (tests/test_gpu_slab.py skew cases): delay this rank's GPU work by rank- and call-dependent amounts at the phase
+        # boundaries of the RHS, so that the ranks drift against each other by whole passes -- the arrival-flag protocol has no
+        # "buffer free" credits and must be correct under any such drift
+        self.test_skew = int(os.environ.get("DEDALUS_TEST_SKEW", "0"))
+        self._skew_calls = 0
         self.trace = None               # profiling only: list collecting (label, torch.cuda.Event) marks of rhs()
         self.skip_exchange = False      # profiling only (profiles/slab_breakdown.py): time the passes without the all-to-all
 
@@ -135,6 +140,12 @@ class SlabPipeline(object):
             raise RuntimeError(self.lib.ddl_last_error().decode())
 
     def _mark(self, label):
+        if self.test_skew:
+            # a different rank is the slow one at every mark, by up to test_skew milliseconds (torch.cuda._sleep: GPU-side spin)
+            self._skew_calls += 1
+            k = (self._skew_calls * 7 + self.rank * 3) % (self.P + 1)
+            if k:
+                torch.cuda._sleep(int(k * self.test_skew * 1.5e6 / self.P))
         if self.trace is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()

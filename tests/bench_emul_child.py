@@ -85,4 +85,4 @@ elif __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     bench.cpu_baseline = lambda args: {"value": None, "unit": bench.UNIT, "cores": 1, "kind": "reference", "sample": "skipped in the emulated run"}
     bench.run_ours(argparse.Namespace(n=n, steps=2, warmup=1, quick=False, cpu_n=16, cpu_steps=1, gpus=1, impl="ours",
-                                     e2e_full="--e2e-full" in sys.argv))
+                                     e2e_full="--e2e-full" in sys.argv, skip_e2e=False))

@@ -36,6 +36,9 @@ TUNED = dict(DEDALUS_SLAB_INVERSE="groups:2", DEDALUS_PEER_CTAS="24", DEDALUS_SI
     (2, "cyclic", "peer", TUNED), (2, "block", "peer", dict(TUNED, DEDALUS_SLAB_INVERSE="fields", DEDALUS_PEER_CTAS="7")),
     (2, "cyclic", "push", {}), (2, "block", "push", dict(DEDALUS_SLAB_INVERSE="groups:3", DEDALUS_SLAB_CHUNKS="8", DEDALUS_PUSH_CTAS="5",
                                                           DEDALUS_SIDE_PRIORITY="1")),
+    # the flag protocol under rank drift: every phase boundary delays a different rank by up to 3 ms of GPU time (slab.py test_skew)
+    (2, "cyclic", "peer", dict(DEDALUS_TEST_SKEW="3")), (2, "block", "push", dict(DEDALUS_TEST_SKEW="3", DEDALUS_SLAB_INVERSE="groups:3")),
+    (4, "cyclic", "peer", dict(DEDALUS_TEST_SKEW="3", DEDALUS_SLAB_CHUNKS="4")), (8, "cyclic", "peer", dict(DEDALUS_TEST_SKEW="2")),
     (4, "cyclic", "push", dict(DEDALUS_SLAB_INVERSE="groups:2")), (8, "cyclic", "push", dict(DEDALUS_SLAB_INVERSE="groups:3", DEDALUS_SLAB_CHUNKS="8")),
     (4, "cyclic", "peer", {}), (4, "cyclic", "peer", TUNED), (8, "block", "peer", {}), (8, "cyclic", "peer", {}), (8, "cyclic", "peer", TUNED)])
 def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, knobs, tmp_path):
