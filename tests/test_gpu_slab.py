@@ -61,3 +61,26 @@ def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, knobs, 
         assert case["solenoidal_verdict"] == (not case["compressive"]), case
         assert abs(case["emag"] - case["emag_oracle"]) < 1e-12, case
         assert case["exchanges"] > 0 and case["ky_layout"] == layout and case["exchange"] == exchange
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_full_size_state_agrees_with_the_single_gpu_run(world, tmp_path):
+    """1-GPU-vs-N-GPU agreement of the 512^3 state (<= 1e-13).  bench.py's parity block fingerprints the state after
+    two RK4 steps of the headline problem (layout-independent sums over all ranks) and compares it with the fingerprint recorded
+    from the single-GPU run (profiles/state_checksum.json); the same block advances 64^3 on these ranks against the oracle and
+    the reference's own code."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--gpus", str(world), "--steps", "2",
+           "--warmup", "2", "--skip-e2e"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
+    p = line["parity"]
+    assert p["ok"] and p["world_size"] == world and p["rel_l2"] < 1e-10
+    assert p["rel_l2_reference_code"] is None or p["rel_l2_reference_code"] < 1e-10
+    agree = p["state_checksum"]["vs_recorded_1gpu"]
+    assert agree is not None, p["state_checksum"]["note"]
+    assert agree["phase_sum_rel"] < 1e-13 and agree["energy_rel_max"] < 1e-13, agree
+    assert line["n_gpus"] == world and line["gpu_launches"] > 0
