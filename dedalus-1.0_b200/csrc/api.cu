@@ -1358,15 +1358,17 @@ extern "C" int ddl_set_shear(ddl_plan* pl, int enable, double shear_rate, double
 
 namespace ddl { extern int g_p2p_timeout_s; }
 #if DDL_DEVICE_BUILD
-namespace ddl { int g_peer_pass_ctas = 0; int g_strided_staged = 0; extern int g_push_tma; }
+namespace ddl { int g_peer_pass_ctas = 0; int g_strided_staged = 0; int g_persist_stagger_ns = 0; extern int g_push_tma; }
 #endif
 extern "C" int ddl_set_option(const char* name, int value) {
 #if DDL_DEVICE_BUILD
     if (name && !strcmp(name, "peer_pass_ctas")) { ddl::g_peer_pass_ctas = value < 0 ? 0 : value; return 0; }
     if (name && !strcmp(name, "strided_staged")) { ddl::g_strided_staged = value != 0; return 0; }
     if (name && !strcmp(name, "push_tma")) { ddl::g_push_tma = value != 0; return 0; }
+    if (name && !strcmp(name, "persist_stagger_ns")) { ddl::g_persist_stagger_ns = value < 0 ? 0 : value; return 0; }
 #else
-    if (name && (!strcmp(name, "peer_pass_ctas") || !strcmp(name, "strided_staged") || !strcmp(name, "push_tma"))) return 0;
+    if (name && (!strcmp(name, "peer_pass_ctas") || !strcmp(name, "strided_staged") || !strcmp(name, "push_tma") ||
+                 !strcmp(name, "persist_stagger_ns"))) return 0;
 #endif
     if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
     if (name && !strcmp(name, "p2p_timeout_s")) { ddl::g_p2p_timeout_s = value < 0 ? 0 : value; return 0; }

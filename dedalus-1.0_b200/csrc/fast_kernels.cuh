@@ -61,6 +61,7 @@ struct FastParams {
     double scale;
     const cplx* tw;
     int gx, gy, gz;           // EXT kernels walk the (inner chunk, outer, field) tiles themselves: tile t = (t % gx, t / gx % gy, t / (gx gy))
+    int stagger_ns, nsm;      // strided_staged: the k-th CTA of an SM starts k * stagger_ns late (see xfused_rot.cuh)
     unsigned mx, mxy;         // ceil(2^32 / gx), ceil(2^32 / (gx gy)): t / d == umulhi(t, m) for t < 2^32 / d (strided_staged)
 };
 
@@ -68,6 +69,7 @@ struct FastParams {
 // A pass whose stores cross NVLink is bound by the links, not by the SMs: a few resident CTAs per SM pair saturate them, and a
 // grid limited to that many CTAs leaves the rest of every SM to the HBM / FP64-bound pass running on the other stream.
 extern int g_peer_pass_ctas;
+extern int g_persist_stagger_ns;
 
 // stored row of logical row r, or -1 if the row is pruned
 template <int N>

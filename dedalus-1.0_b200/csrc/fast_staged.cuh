@@ -76,6 +76,9 @@ strided_staged(const __grid_constant__ FastParams p) {
         }
     };
 
+    if (p.stagger_ns > 0) {
+        for (int k = blockIdx.x / p.nsm; k > 0; --k) __nanosleep(p.stagger_ns);      // break the lock step of an SM's CTAs
+    }
     int t = blockIdx.x;
     if (t < ntiles) prefetch(t);
 #pragma unroll 1
@@ -168,6 +171,8 @@ int launch_strided_staged(const FastParams& p, int nf, int n_outer, const char* 
         if (ntiles >= (1LL << 32) / gxy) return 1;             // the multiply-high decode is exact below 2^32 / divisor
         q.mx = tile_magic(q.gx);
         q.mxy = tile_magic(gxy);
+        q.stagger_ns = g_persist_stagger_ns;
+        q.nsm = ctas >= 2 ? ctas / 2 : 1;
         const int grid = (int)(ntiles < ctas ? ntiles : ctas);
         prof_begin(name, stream);
         kern<<<grid, Cfg::NT, Cfg::SMEM, stream>>>(q);

@@ -6,6 +6,7 @@
 #include "fast_staged.cuh"
 #include "xfused_kernel.cuh"
 #include "xfused_persist.cuh"
+#include "xfused_rot.cuh"
 
 #ifndef DDL_N
 #error "compile with -DDDL_N=<transform length>"

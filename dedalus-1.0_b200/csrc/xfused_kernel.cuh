@@ -475,6 +475,7 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
 //      any other mask.  Measured (profiles/r2/devcheck_b200_xfused_variants.txt): 4.30 ms against 4.12 ms for variant 0 although it has
 //      336 fewer static instructions (cuobjdump: 2 296 -> 1 960 for <512, MHD3C>): opt-in.
 //   4: persistent CTAs, next pair staged by cp.async.bulk + mbarrier (xfused_persist.cuh): 4.92 ms, opt-in
+//   5: persistent CTAs of shape 0, no staging; warps without a second-round pencil start the next pair (xfused_rot.cuh)
 template <int N, class PHYS, int V> struct XFusedCfg {
     static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
     static constexpr int G = (N >= 512) ? 1 : 512 / N;
@@ -529,6 +530,7 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
 
 #if DDL_DEVICE_BUILD
 template <int N, class PHYS, bool CFL> int launch_xfused_persist(const XFusedParams& p, int n_outer, ddl_stream_t stream);   // xfused_persist.cuh
+template <int N, class PHYS, bool CFL> int launch_xfused_rot(const XFusedParams& p, int n_outer, ddl_stream_t stream);       // xfused_rot.cuh
 #endif
 
 template <int N, class PHYS>
@@ -537,6 +539,11 @@ int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t 
     if (variant == 4) {
         // persistent CTAs with the next pair's lines staged by the bulk-copy engine (xfused_persist.cuh); 1 = not applicable
         const int rc = p.cfl ? launch_xfused_persist<N, PHYS, true>(p, n_outer, stream) : launch_xfused_persist<N, PHYS, false>(p, n_outer, stream);
+        if (rc != 1) return rc;
+    }
+    if (variant == 5) {
+        // persistent CTAs of the default shape; the warps without a second-round pencil start the next pair (xfused_rot.cuh)
+        const int rc = p.cfl ? launch_xfused_rot<N, PHYS, true>(p, n_outer, stream) : launch_xfused_rot<N, PHYS, false>(p, n_outer, stream);
         if (rc != 1) return rc;
     }
 #endif

@@ -268,17 +268,17 @@ static void check(int n) {
     DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv2, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
     dsync();
     ddl_set_option("fast_kernels", 1);
-    for (int v = 0; v <= 4; ++v) {
+    for (int v = 0; v <= 5; ++v) {
         ddl_set_option("xfused_variant", v);
         for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
         dzero(P.dout, 16);
-        DDL(ddl_rhs_capture_max(P.plan, (v == 0 || v == 4) ? P.dout : nullptr));     // variants 0 and 4 (persistent) also with the capture on
+        DDL(ddl_rhs_capture_max(P.plan, (v == 0 || v >= 4) ? P.dout : nullptr));     // variants 0, 4 and 5 (persistent) also with the capture on
         DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
         DDL(ddl_rhs_capture_max(P.plan, nullptr));
         dsync();
         char label[96]; snprintf(label, sizeof label, "x-pass variant %d vs generic tile kernels (rel L2)", v);
         verdict(label, max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
-        if (v == 0 || v == 4) {
+        if (v == 0 || v >= 4) {
             d2h(got, P.dout, sizeof got);
             verdict("maxima captured inside that RHS", std::fmax(rel(got[0], brute[0]), rel(got[1], brute[1])), 1e-12);
         }
@@ -450,7 +450,7 @@ static void timing(int n, int reps) {
     say("== timing: MHD %d^3 (CUDA events, ms per call, best of %d after 1 warm-up)\n", n, reps);
     Problem P(n, false);
     Timer t;
-    for (int v = 0; v <= 4; ++v) {
+    for (int v = 0; v <= 5; ++v) {
         ddl_set_option("xfused_variant", v);
         double best = 1e30;
         for (int r = 0; r <= reps; ++r) {

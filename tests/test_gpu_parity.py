@@ -502,7 +502,7 @@ def test_opt_in_async_staging_kernels_reproduce_the_default_ones(shape):
             c["kspace"]
         f.div_free()
     out = {}
-    for tag, opts in (("default", {}), ("staged", {"strided_staged": 1}), ("persist", {"xfused_variant": 4})):
+    for tag, opts in (("default", {}), ("staged", {"strided_staged": 1}), ("persist", {"xfused_variant": 4}), ("rot", {"xfused_variant": 5})):
         for k, v in opts.items():
             L.set_option(k, v)
         try:
@@ -512,6 +512,6 @@ def test_opt_in_async_staging_kernels_reproduce_the_default_ones(shape):
             for k in opts:
                 L.set_option(k, 0)
     assert np.array_equal(out["staged"], out["default"])
-    assert rel(out["persist"], out["default"]) < 1e-14
+    assert rel(out["persist"], out["default"]) < 1e-14 and rel(out["rot"], out["default"]) < 1e-14
     assert np.isfinite(out["default"]).all() and np.abs(out["default"]).max() > 0
 
