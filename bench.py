@@ -560,9 +560,9 @@ def _load_traffic():
 TRAFFIC, TRAFFIC_SOURCE = _load_traffic()
 
 
-def _ref_run(n, steps, threads):
+def _ref_run(n, steps, threads, warmup=1):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--n", str(n), "--steps", str(steps),
-                        "--warmup", "1", "--threads", str(threads)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
+                        "--warmup", str(max(0, int(warmup))), "--threads", str(threads)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
@@ -573,10 +573,11 @@ def cpu_baseline(args):
     n, cores = args.cpu_n, os.cpu_count() or 1
     try:
         # the K timed steps go to the faster configuration; the other one gets a 2-step look (bounded CPU time)
-        one = _ref_run(n, min(args.cpu_steps, 2), 1)
-        many = _ref_run(n, args.cpu_steps, cores) if cores > 1 else one
+        warm = getattr(args, "cpu_warmup", 1)
+        one = _ref_run(n, min(args.cpu_steps, 2), 1, min(warm, 1))
+        many = _ref_run(n, args.cpu_steps, cores, warm) if cores > 1 else one
         if one["value"] >= many["value"] and one["steps"] != args.cpu_steps:
-            one = _ref_run(n, args.cpu_steps, 1)
+            one = _ref_run(n, args.cpu_steps, 1, warm)
         best = many if many["value"] > one["value"] else one
         return {"value": best["value"], "unit": UNIT, "cores": best["threads"], "host_cores": cores, "kind": "reference",
                 "sample": "reference Python path + reference Cython stage kernels, MHD %d^3, %s, %d steps after 1 warm-up; FFTs: %s "
@@ -584,7 +585,7 @@ def cpu_baseline(args):
                               n, best["integrator"], best["steps"],
                               "scipy.fft with %d workers behind the reference's numpy.fft calls" % best["threads"] if best["threads"] > 1
                               else "numpy pocketfft, single-threaded as shipped"),
-                "ms_per_step": best["ms_per_step"], "steps": best["steps"], "single_thread_value": one["value"], "threaded_fft_value": many["value"],
+                "ms_per_step": best["ms_per_step"], "steps": best["steps"], "warmup": best.get("warmup", 1), "single_thread_value": one["value"], "threaded_fft_value": many["value"],
                 "threaded_fft_workers": many["threads"]}
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "failed: %r" % (e,)}
@@ -595,10 +596,11 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.cpu_n
-    cb = cpu_baseline(argparse.Namespace(cpu_n=n, cpu_steps=max(1, args.steps)))
+    # the driver's --steps K --warmup W are honoured (warm-up capped at 5 steps: a 128^3 step takes seconds on the host)
+    cb = cpu_baseline(argparse.Namespace(cpu_n=n, cpu_steps=max(1, args.steps), cpu_warmup=min(max(0, args.warmup), 5)))
     nk = n * n * (n // 2 + 1)
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                      "steps": cb.get("steps", max(1, args.steps)), "warmup": 1, "ms_per_step": cb.get("ms_per_step"),
+                      "steps": cb.get("steps", max(1, args.steps)), "warmup": cb.get("warmup", 1), "ms_per_step": cb.get("ms_per_step"),
                       "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": "3D incompressible MHD RK4 (bounded CPU sample %d^3 of the 512^3 workload)" % n,
                                  "N_k": nk, "stages_per_step": 4},
