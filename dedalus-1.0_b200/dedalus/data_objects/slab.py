@@ -378,7 +378,7 @@ class SlabPipeline(object):
         """RHS buffer set whose exchange endpoints (k-side / x-side) live in the IPC arena."""
         nmax = max(ni, no)
         if self._p2p is None:
-            self._p2p_setup(9)
+            self._p2p_setup(13)      # the largest field count of any policy: 13 products of the advective-form Boussinesq RHS
         if nmax > self._p2p_nmax:
             raise RuntimeError("p2p arena holds %d fields, %d requested" % (self._p2p_nmax, nmax))
         key = ("p2p", ni, no)
@@ -458,13 +458,14 @@ class SlabPipeline(object):
     def rhs(self, physics_id, params, state, deriv, dealias_state, zero_fill, fuse=None, ncomp=None):
         """deriv = RHS(state) (physics.py:527-599 / 664-712 / 770-819), local slabs in and out.
         Advective-form policies (physics_id >= 3): `state` = the ncomp state slabs followed by the scratch
-        slabs for the divergence spectra; they take the collective exchange (the arenas of the peer-store
-        path are sized for the solenoidal policies)."""
+        slabs for the divergence spectra; with the "peer" exchange they go through the same fused peer-store
+        pipeline as the solenoidal policies (more fields), with "p2p" / "push" through the collective."""
         lib, h, st = self.lib, self.h, self._stream()
         ni, no = _COUNTS[physics_id]
         adv = physics_id >= 3
         p2p = self.exchange_kind == "p2p" and self.P > 1 and not self.skip_exchange and not adv
-        peer = self.exchange_kind == "peer" and self.P > 1 and not self.skip_exchange and not adv
+        # the advective-form policies (states that are not solenoidal) take the peer-store exchange too: the arenas hold 13 fields
+        peer = self.exchange_kind == "peer" and self.P > 1 and not self.skip_exchange
         push = self.exchange_kind == "push" and self.P > 1 and not self.skip_exchange and not adv
         pp = C.byref(params)
         if dealias_state:
@@ -475,6 +476,7 @@ class SlabPipeline(object):
         if zero_fill:
             for t in deriv:
                 self._check(lib.ddl_dealias(h, t.data_ptr(), st))
+        self.last_rhs_path = "peer" if peer else "push" if push else "p2p" if p2p else "collective"     # what carried the last exchange (tests)
         if peer:
             return self._rhs_peer(physics_id, pp, state, deriv, ni, no, fuse)
         if push:

@@ -105,6 +105,7 @@ def main(out_path):
                         "dt_taken": float(ti.dt_old), "emag": float(emag),
                         "emag_oracle": float(orc.energy(do, "B")) if physics == "IncompressibleMHD" else 0.0,
                         "exchanges": comps[0]._plan.pipeline.exchanges, "ky_layout": comps[0]._plan.ky_layout,
+                        "last_rhs_path": getattr(comps[0]._plan.pipeline, "last_rhs_path", None),
                         "exchange": comps[0]._plan.pipeline.exchange_kind})
     if rank == 0:
         with open(out_path, "w") as f:

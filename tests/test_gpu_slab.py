@@ -61,6 +61,9 @@ def test_slab_ranks_match_oracle_and_single_gpu(world, layout, exchange, knobs, 
         assert case["solenoidal_verdict"] == (not case["compressive"]), case
         assert abs(case["emag"] - case["emag_oracle"]) < 1e-12, case
         assert case["exchanges"] > 0 and case["ky_layout"] == layout and case["exchange"] == exchange
+        # the advective-form policies (compressive states) ride the fused peer-store pipeline too; push / p2p hand them to the collective
+        expect = exchange if (exchange == "peer" or not case["compressive"]) else "collective"
+        assert case["last_rhs_path"] == expect, case
 
 
 @pytest.mark.parametrize("world", [2, 8])
