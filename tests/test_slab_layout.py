@@ -120,3 +120,50 @@ def test_retained_boxes_cover_exactly_the_kept_modes():
         "print('ok', done)\n") % (ROOT,)
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "ok 40" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("P,rows,nzl,cx,nz,nmax", CASES)
+def test_push_tables_move_exactly_the_bytes_of_the_copy_lists(P, rows, nzl, cx, nz, nmax):
+    """The "push" exchange (SlabPipeline._push_table -> ddl_p2p_push) moves rows x pitch rectangles: per field group in the inverse
+    direction, per plane chunk in the forward one.  Over all groups / chunks they must cover, byte for byte and without overlap,
+    what the whole-field copy lists of arena_layout cover (which the tests above tie to the arenas)."""
+    for me in range(P):
+        lay = slab.arena_layout(P, me, rows, nzl, cx, nz, nmax)
+        pipe = type("P", (), {})()                           # the four attributes _push_table reads
+        pipe._p2p_layout, pipe.nzl, pipe.cx, pipe.rows = lay, nzl, cx, rows
+
+        def spans(key):
+            n, ranks, src, dst, rb, nr, pitch = slab.SlabPipeline._push_table(pipe, key)
+            out = []
+            for i in range(n):
+                for r in range(nr[i]):
+                    out.append((ranks[i], src[i] + r * pitch[i], dst[i] + r * pitch[i], rb[i]))
+            return out
+
+        def cover(sp):
+            """{(rank, dst byte)} and {src byte} sets, asserting no byte is written or read twice"""
+            d, s = set(), set()
+            for rank, so, do, nb in sp:
+                if nb == 0:
+                    continue
+                for b in range(0, nb, 16):
+                    assert (rank, do + b) not in d and (so + b) not in s
+                    d.add((rank, do + b))
+                    s.add(so + b)
+            return d, s
+
+        small = nzl * cx * sum(rows) * nmax <= 40000          # exhaustive byte sets only where they stay small
+        # inverse: groups [0, 2), [2, nmax) against the whole-field lists of the same fields
+        for f0, f1 in ((0, 2), (2, nmax)):
+            got = spans(("inv", f0, f1))
+            want = [(s, so, do, nb) for f in range(f0, f1) for s, so, do, nb in zip(*lay["inv"][f])]
+            assert sorted(got) == sorted(want)
+        # forward: chunks of the local planes
+        for nch in (1, 2, nzl):
+            zc = nzl // nch
+            got = [x for c in range(nch) for x in spans(("fwd", nmax, c * zc, zc))]
+            assert sum(nb for _, _, _, nb in got) == sum(nb for f in range(nmax) for nb in lay["fwd"][f][3])
+            if small:
+                gd, gs = cover(got)
+                wd, ws = cover([(s, so, do, nb) for f in range(nmax) for s, so, do, nb in zip(*lay["fwd"][f])])
+                assert gd == wd and gs == ws
