@@ -66,3 +66,19 @@ def test_oracle_cn_equals_reference_code_under_restated_glue(tmp_path, physics, 
         ti.do_advance(do, dt)
     assert rel(do.kvector(), y1) < 1e-13
     assert abs(do.time - meta["time"]) < 1e-14
+
+
+@pytest.mark.parametrize("physics,shape,integ,steps,dt,params", [
+    ("IncompressibleHydro", (128, 128), "RK2mid", 20, 5e-3, dict(nu=1e-2)),          # BASELINE config 1 (the reference's own RK2mid class)
+    ("IncompressibleMHD", (512, 512), "RK4", 5, 2e-3, dict(nu=1e-3, eta=1e-3)),      # BASELINE config 2 at full size
+])
+def test_oracle_equals_reference_code_on_the_2d_baseline_configs(tmp_path, physics, shape, integ, steps, dt, params):
+    Po = oracle_physics(physics, shape, None, params)
+    do = Po.create_fields(0.)
+    (orc.taylor_green if physics == "IncompressibleHydro" else orc.orszag_tang)(do)
+    y1, meta = run_reference(tmp_path, physics, shape, do.kvector().copy(), integ, steps, dt, params, threads=4)
+    ti = orc.INTEGRATORS[integ](Po)
+    for _ in range(steps):
+        ti.do_advance(do, dt)
+    assert rel(do.kvector(), y1) < 1e-13
+    assert abs(orc.energy(do, "u") - meta["ekin"]) < 1e-13
