@@ -70,7 +70,7 @@ def test_oracle_cn_equals_reference_code_under_restated_glue(tmp_path, physics, 
 
 @pytest.mark.parametrize("physics,shape,integ,steps,dt,params", [
     ("IncompressibleHydro", (128, 128), "RK2mid", 20, 5e-3, dict(nu=1e-2)),          # BASELINE config 1 (the reference's own RK2mid class)
-    ("IncompressibleMHD", (512, 512), "RK4", 5, 2e-3, dict(nu=1e-3, eta=1e-3)),      # BASELINE config 2 at full size
+    ("IncompressibleMHD", (512, 512), "RK4", 2, 2e-3, dict(nu=1e-3, eta=1e-3)),      # BASELINE config 2 at full size
 ])
 def test_oracle_equals_reference_code_on_the_2d_baseline_configs(tmp_path, physics, shape, integ, steps, dt, params):
     Po = oracle_physics(physics, shape, None, params)
