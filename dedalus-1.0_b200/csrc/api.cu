@@ -926,10 +926,15 @@ static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* cons
     return launch_items(f, count, st, "assemble");
 }
 
-template <class PHYS>
-static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_stage_fuse* fu,
-                        ddl_stream_t st) {
-    AssembleStageF<PHYS> f;
+// ddl_set_option("assemble_variant", v): 0 = loads where the arithmetic needs them, four CTAs per SM; 1 = every operand of a
+// mode loaded up front (AssembleStageF<PHYS, true>), four CTAs per SM; 2, 3 = the same with three / two CTAs per SM (85 / 128
+// registers per thread, so that all of a mode's loads can be in flight at once)
+static int g_assemble_variant = 0;
+
+template <class PHYS, bool HOIST>
+static int assemble_rk4_v(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_stage_fuse* fu,
+                          ddl_stream_t st, int minb) {
+    AssembleStageF<PHYS, HOIST> f;
     const long long count = fill_assemble<PHYS>(pl, f.a, E, state, nullptr, pc);
     for (int c = 0; c < PHYS::NC; ++c) {
         f.y[c] = (const cplx*)fu->y[c]; f.out[c] = (cplx*)fu->out[c];
@@ -941,7 +946,17 @@ static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const 
     f.kind = fu->kind; f.has_d1 = fu->deriv1 != nullptr; f.has_kout = fu->k_out != nullptr;
     f.vo = fu->visc_order; f.first = fu->first; f.last = fu->last; f.twod = pl->geom.twod;
     f.dt = fu->dt_step; f.wdiv = fu->wdiv;
+    if (minb == 3) return launch_items_b<AssembleStageF<PHYS, HOIST>, 3>(f, count, st, "assemble_stage");
+    if (minb == 2) return launch_items_b<AssembleStageF<PHYS, HOIST>, 2>(f, count, st, "assemble_stage");
     return launch_items(f, count, st, "assemble_stage");
+}
+
+template <class PHYS>
+static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_stage_fuse* fu,
+                        ddl_stream_t st) {
+    const int v = g_assemble_variant;
+    if (v <= 0) return assemble_rk4_v<PHYS, false>(pl, E, state, pc, fu, st, 4);
+    return assemble_rk4_v<PHYS, true>(pl, E, state, pc, fu, st, v == 2 ? 3 : (v == 3 ? 2 : 4));
 }
 
 static int assemble_rk4_any(ddl_plan* pl, int code, void* const* E, void* const* state, const PhysConst& pc,
@@ -1373,6 +1388,7 @@ extern "C" int ddl_set_option(const char* name, int value) {
     if (name && !strcmp(name, "fast_kernels")) { g_use_fast = value; return 0; }
     if (name && !strcmp(name, "p2p_timeout_s")) { ddl::g_p2p_timeout_s = value < 0 ? 0 : value; return 0; }
     if (name && !strcmp(name, "xfused_variant")) { g_xfused_variant = value; return 0; }
+    if (name && !strcmp(name, "assemble_variant")) { g_assemble_variant = value; return 0; }
     if (name && !strcmp(name, "rhs_plane_chunk")) { g_plane_chunk = value < 0 ? 0 : value; return 0; }
     set_error("unknown option %s", name ? name : "(null)");
     return -1;

@@ -336,7 +336,10 @@ struct AssembleF {
 // derivative; ETD2RK1/2: as the SECOND derivative, the first is read from deriv1), so it is not
 // written unless a later stage needs it (kout, RK2's k1).  Saves the 16 B write + 16 B read per mode
 // and component, and a launch.  Retained modes only: every operand must vanish outside the mask.
-template <class PHYS>
+// HOIST: every operand of the mode (product spectra, start values, running totals, first derivatives) is loaded before any
+// arithmetic; without it the per-component loads sit behind the branches and divisions of the previous component's update and
+// a mode pays one memory round trip per component (seven for 3-D MHD in the SASS) instead of one or two.
+template <class PHYS, bool HOIST = false>
 struct AssembleStageF {
     AssembleF<PHYS> a;
     const cplx* y[PHYS::NC];        // start
@@ -364,6 +367,16 @@ struct AssembleStageF {
         for (int f = 0; f < PHYS::NO; ++f) p[f] = a.P[f][ci];
 #pragma unroll
         for (int f = 0; f < PHYS::NS; ++f) s[f] = a.S[f][fi];
+        cplx yv[PHYS::NC], tv[PHYS::NC], dv[PHYS::NC];
+        if constexpr (HOIST) {
+            const bool rd_total = kind == SK_RK4 && !first;
+#pragma unroll
+            for (int c = 0; c < PHYS::NC; ++c) yv[c] = y[c][fi];
+#pragma unroll
+            for (int c = 0; c < PHYS::NC; ++c) tv[c] = rd_total ? total[c][fi] : mk(0.0, 0.0);
+#pragma unroll
+            for (int c = 0; c < PHYS::NC; ++c) dv[c] = has_d1 ? d1[c][fi] : mk(0.0, 0.0);
+        }
         PHYS::assemble(p, s, d, kk[0], kk[1], kk[2], a.pc);
         const double pw = ipow(k2, vo);
         double lastc = -1.0, Z = 0.0, f0 = 1.0, f1 = 1.0, f2 = 0.5;
@@ -377,9 +390,17 @@ struct AssembleStageF {
             }
             const cplx kc = d[c];
             if (has_kout) kout[c][fi] = kc;
-            const cplx first_d = has_d1 ? d1[c][fi] : kc;
-            out[c][fi] = stage_apply(kind, y[c][fi], first_d, kc, kind == SK_RK4 ? &total[c][fi] : nullptr, first, last, wdiv,
-                                     Z, f0, f1, f2, dt, co * pw);
+            if constexpr (HOIST) {
+                // same calls as below on the values loaded above; the running total goes back where stage_apply would have left it
+                const cplx first_d = has_d1 ? dv[c] : kc;
+                out[c][fi] = stage_apply(kind, yv[c], first_d, kc, kind == SK_RK4 ? &tv[c] : nullptr, first, last, wdiv,
+                                         Z, f0, f1, f2, dt, co * pw);
+                if (kind == SK_RK4 && !last) total[c][fi] = tv[c];
+            } else {
+                const cplx first_d = has_d1 ? d1[c][fi] : kc;
+                out[c][fi] = stage_apply(kind, y[c][fi], first_d, kc, kind == SK_RK4 ? &total[c][fi] : nullptr, first, last, wdiv,
+                                         Z, f0, f1, f2, dt, co * pw);
+            }
         }
     }
 };
@@ -391,6 +412,34 @@ __global__ void __launch_bounds__(256, 4) items_kernel(const __grid_constant__ F
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) f(i);
 }
 #endif
+
+#if DDL_DEVICE_BUILD
+// the same sweep with MINB resident CTAs per SM instead of four: 65536 / (256 MINB) registers per thread for loads in flight
+template <class F, int MINB>
+__global__ void __launch_bounds__(256, MINB) items_kernel_b(const __grid_constant__ F f, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) f(i);
+}
+#endif
+
+template <class F, int MINB>
+int launch_items_b(const F& f, long long count, ddl_stream_t stream, const char* name) {
+    if (count <= 0) return 0;
+#if DDL_DEVICE_BUILD
+    const int threads = 256;
+    long long blocks = (count + threads - 1) / threads;
+    const long long cap = 148LL * 4 * MINB;
+    if (blocks > cap) blocks = cap;
+    prof_begin(name, stream);
+    items_kernel_b<F, MINB><<<(unsigned)blocks, threads, 0, stream>>>(f, count);
+    prof_end(stream);
+    DDL_CUDA_CHECK(cudaGetLastError());
+#else
+    prof_begin(name, stream);
+    for (long long i = 0; i < count; ++i) f(i);
+#endif
+    return 0;
+}
 
 template <class F>
 int launch_items(const F& f, long long count, ddl_stream_t stream, const char* name = "pointwise") {

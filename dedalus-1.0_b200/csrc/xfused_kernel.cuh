@@ -236,6 +236,74 @@ DDL_BODY void xstage(cplx* T, int lane, const cplx* __restrict__ tw) {
     }
 }
 
+// complex load that returns 0 when `ok` is false, as ONE predicated instruction (no branch region: the loads of a pencil
+// stay independent of each other and of every predicate but their own)
+DDL_BODY cplx xldg_if(const cplx* __restrict__ ptr, bool ok) {
+#if DDL_DEVICE_BUILD
+    cplx r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+        "@q ld.global.nc.v2.f64 {%0, %1}, [%2];\n\t}"
+        : "=d"(r.x), "=d"(r.y) : "l"(ptr), "r"((int)ok));
+    return r;
+#else
+    return ok ? *ptr : mk(0.0, 0.0);
+#endif
+}
+
+// Hermitian-packed first-stage inputs of one pencil, v[j] = Z[a + j Q0] with Z = A + iB of the two lines at pa, pa + pitch
+// (pa already offset by a):  Z[e] = A[e] + i B[e] (e < kn),  Z[N-e] = conj(A[e]) + i conj(B[e]),  Z[0] = (Re A[0], Re B[0]),  else 0.
+// Input j is element e = a + j Q0: e < N/2 for j < R0/2 (read index e), e >= N/2 otherwise (mirror, read index N - e >= 1; e == N/2
+// reads nothing since kn <= N/2) - which of the two is known at compile time, so every input is one predicate and a constant offset
+// from one of four pointers.
+//   PACK 1: all loads from global memory into registers, predicated, none inside a branch region.
+//   PACK 2: only the direct half is loaded (each retained mode once instead of twice); the mirrored half comes from the partner
+//           lane through the pencil's own shared-memory slot T, which stage 0 overwrites afterwards.  Every thread of the
+//           pencil's group must call (kn = 0 for a group without work): two group barriers inside.
+template <int N, int R0, int PACK, int TP>
+DDL_BODY void xpack_inputs(cplx (&v)[R0], const cplx* __restrict__ pa, long long pitch, int a, int kn, cplx* T, int group) {
+    constexpr int Q0 = N / R0, H = R0 / 2;
+    const cplx* __restrict__ pb = pa + pitch;
+#if DDL_DEVICE_BUILD
+    if constexpr (PACK == 2) {
+        cplx za[H], zb[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const bool ok = a + j * Q0 < kn;
+            za[j] = xldg_if(pa + j * Q0, ok);
+            zb[j] = xldg_if(pb + j * Q0, ok);
+        }
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            if (a + j * Q0 < kn) { T[a + j * Q0] = za[j]; T[N / 2 + a + j * Q0] = zb[j]; }
+            if (j == 0 && a == 0) { za[j].y = -0.0; zb[j].y = 0.0; }      // exact: x - (+0) = x, (-0) + x = x
+            v[j] = mk(za[j].x - zb[j].y, za[j].y + zb[j].x);
+        }
+        xgroup_sync<TP>(group);
+#pragma unroll
+        for (int j = H; j < R0; ++j) {
+            const int idx = N - a - j * Q0;
+            cplx ma = mk(0.0, 0.0), mb = mk(0.0, 0.0);
+            if (idx < kn) { ma = T[idx]; mb = T[N / 2 + idx]; }
+            v[j] = mk(ma.x + mb.y, mb.x - ma.y);
+        }
+        xgroup_sync<TP>(group);
+        return;
+    }
+#endif
+    (void)T; (void)group;
+    const cplx* __restrict__ ma = pa + (N - 2 * a);
+    const cplx* __restrict__ mb = pb + (N - 2 * a);
+#pragma unroll
+    for (int j = 0; j < R0; ++j) {
+        const bool mir = j >= H;
+        const bool ok = (mir ? N - a - j * Q0 : a + j * Q0) < kn;
+        cplx za = xldg_if(mir ? ma - j * Q0 : pa + j * Q0, ok);
+        cplx zb = xldg_if(mir ? mb - j * Q0 : pb + j * Q0, ok);
+        if (j == 0 && a == 0) { za.y = -0.0; zb.y = 0.0; }
+        v[j] = mir ? mk(za.x + zb.y, zb.x - za.y) : mk(za.x - zb.y, za.y + zb.x);
+    }
+}
+
 // running maximum of non-negative values; NaN wins (numpy's max propagates it)
 DDL_HD double xmax_nn(double m, double a) { return (a > m || a != a) ? a : m; }
 
@@ -245,7 +313,10 @@ DDL_HD double xmax_nn(double m, double a) { return (a > m || a != a) ? a : m; }
 // no transform of its own.
 // KNC > 0: the retained-mode count is the compile-time constant KNC (the 2/3 rule: N/3 + 1) instead of p.kn, so the
 // zero tests of the Hermitian pack and the bounds of the unpack fold at compile time (launch variant 3, below).
-template <int N, class PHYS, int NT, int G, bool CFL = false, int KNC = 0>
+// PACK: how the first inverse stage gets its Hermitian-packed inputs.  0: one branch region per input (a memory round trip
+// each once the compiler has scheduled them: nine per pencil in the SASS of <512, MHD3C>); 1, 2: xpack_inputs above, with the
+// stage-0 twiddle fetched before the inputs instead of after the butterfly.
+template <int N, class PHYS, int NT, int G, bool CFL = false, int KNC = 0, int PACK = 0>
 DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
     constexpr int NI = PHYS::NI, NO = PHYS::NO;
     constexpr int NS = NI > NO ? NI : NO;     // pencil slots per line pair
@@ -260,13 +331,39 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
     const long long plane = (long long)by * p.s_outer;
     const int pair0 = bx * G;
 
+    // PACK != 0: the stage-0 twiddle of a thread, tw[a], is the same for every pencil it touches in either direction.  It is
+    // fetched once, together with the first inputs, and parked in TP entries behind the tile: every thread writes and later
+    // reads entry a itself (the other groups write the same value there), so no barrier is involved and the three uses cost
+    // a shared-memory load instead of a trip to L2 after each butterfly.
+    cplx* wtab = tile + (size_t)G * NS * N;
+    if constexpr (PACK != 0) {
+        DDL_XF_THREADS(t, NT) wtab[t % TP] = DDL_LDG(&tw[t % TP]);
+    }
+
     // ================= inverse: per pencil, stage 0 (global -> registers -> shared) then the
     //                   remaining outer stages, synchronised inside the pencil's own group
 #pragma unroll 1
     for (int pen0 = 0; pen0 < G * NI; pen0 += GPR) {
         DDL_XF_THREADS(t, NT) {
             const int pen = pen0 + t / TP, a = t % TP;
-            if (pen < G * NI) {
+            if constexpr (PACK != 0) {
+                // every thread of a pencil group goes through xpack_inputs (PACK 2 synchronises the group inside); a group
+                // without a pencil, or past the last line, loads nothing (kn = 0)
+                const bool act = pen < G * NI;
+                const int g = act ? pen / NI : 0, f = act ? pen % NI : 0;
+                const int l0 = 2 * (pair0 + g);
+                cplx* T = tile + (g * NS + f) * N;
+                cplx v[R0];
+                xpack_inputs<N, R0, PACK, TP>(v, p.in[f] + plane + (long long)l0 * p.pitch + a, p.pitch, a,
+                                              (act && l0 < p.n_lines) ? kn : 0, T, t / TP);
+                if (act) {
+                    xdft<R0, +1>(v);
+                    if (a != 0) xtwiddle<R0, true>(v, conj(wtab[a]));
+                    const int sb = xsw<N>(a);
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) T[sb ^ xsw<N>(r * Q0)] = v[xreg<R0>(r)];
+                }
+            } else if (pen < G * NI) {
                 const int g = pen / NI, f = pen % NI;
                 const int l0 = 2 * (pair0 + g);
                 cplx v[R0];
@@ -406,7 +503,7 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
             if (act) {
 #pragma unroll
                 for (int j = 0; j < R0; ++j) v[j] = T[sb ^ xsw<N>(j * Q0)];
-                if (a != 0) xtwiddle<R0, false>(v, DDL_LDG(&tw[a]));
+                if (a != 0) xtwiddle<R0, false>(v, PACK != 0 ? wtab[a] : DDL_LDG(&tw[a]));
                 xdft<R0, -1>(v);
             } else {
 #pragma unroll
@@ -480,9 +577,10 @@ template <int N, class PHYS, int V> struct XFusedCfg {
     static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
     static constexpr int G = (N >= 512) ? 1 : 512 / N;
     static constexpr int TP = N / XFac<N>::radix(0);
-    static constexpr int NT = TP > 32 ? 9 * TP : (V == 1 ? 288 : 192);
-    static constexpr size_t SMEM = (size_t)G * NS * N * sizeof(cplx);
-    static constexpr int WANT = (V == 0) ? 3 : 2;
+    static constexpr int NT = TP > 32 ? 9 * TP : ((V == 1 || V == 12) ? 288 : (V == 10 ? 96 : (V == 11 ? 128 : 192)));
+    static constexpr int PACK = (V == 6 || V == 7) ? 1 : (V >= 8 ? 2 : 0);
+    static constexpr size_t SMEM = ((size_t)G * NS * N + (PACK != 0 ? TP : 0)) * sizeof(cplx);      // PACK != 0: + the parked stage-0 twiddles
+    static constexpr int WANT = (V == 0 || (V >= 6 && V != 12)) ? 3 : 2;
     static constexpr int MINB = (SMEM * WANT <= 222 * 1024 && NT * WANT <= 1024) ? WANT : ((SMEM * 2 <= 222 * 1024 && NT * 2 <= 1024) ? 2 : 1);
     // register budget that still lets MINB CTAs share an SM: each of the four sub-partitions owns
     // 16 K registers and holds ceil(warps / 4) of the resident warps (allocation unit: 8 per thread)
@@ -495,7 +593,7 @@ template <int N, class PHYS, int V, bool CFL, int KNC = 0>
 __global__ void __maxnreg__((XFusedCfg<N, PHYS, V>::MAXREG))
 xfused_kernel(const __grid_constant__ XFusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    xfused_block<N, PHYS, XFusedCfg<N, PHYS, V>::NT, XFusedCfg<N, PHYS, V>::G, CFL, KNC>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
+    xfused_block<N, PHYS, XFusedCfg<N, PHYS, V>::NT, XFusedCfg<N, PHYS, V>::G, CFL, KNC, XFusedCfg<N, PHYS, V>::PACK>(p, reinterpret_cast<cplx*>(smem_raw), blockIdx.x, blockIdx.y);
 }
 #endif
 
@@ -522,7 +620,7 @@ int launch_xfused_v(const XFusedParams& p, int n_outer, ddl_stream_t stream) {
     prof_begin("x_fused", stream);
     cplx* tile = (cplx*)malloc(Cfg::SMEM);
     for (int by = 0; by < n_outer; ++by)
-        for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G, CFL, KNC>(p, tile, bx, by);
+        for (int bx = 0; bx < gx; ++bx) xfused_block<N, PHYS, Cfg::NT, Cfg::G, CFL, KNC, Cfg::PACK>(p, tile, bx, by);
     free(tile);
 #endif
     return 0;
@@ -549,6 +647,20 @@ int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t 
 #endif
     if (p.cfl) return launch_xfused_v<N, PHYS, 0, true>(p, n_outer, stream);     // capture: default CTA shape only
     if (variant == 3 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 0, false, N / 3 + 1>(p, n_outer, stream);
+    // 6 / 7: branch-free register pack (7: with the 2/3 rule's retained count at compile time when the mask is that rule);
+    // 8 / 9: direct half from global memory, mirrored half through the pencil's shared-memory slot
+    if (variant == 7 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 7, false, N / 3 + 1>(p, n_outer, stream);
+    if (variant == 6 || variant == 7) return launch_xfused_v<N, PHYS, 6>(p, n_outer, stream);
+    if (variant == 9 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 9, false, N / 3 + 1>(p, n_outer, stream);
+    if (variant == 8 || variant == 9) return launch_xfused_v<N, PHYS, 8>(p, n_outer, stream);
+#if DDL_DEVICE_BUILD
+    // pack 2 in other CTA shapes (pencil groups of one warp only): 10: 3 warps x 3 CTAs per SM, 11: 4 x 3, 12: 9 x 2
+    if (variant >= 10 && variant <= 12 && XFusedCfg<N, PHYS, 0>::TP <= 32) {
+        if (variant == 10) return launch_xfused_v<N, PHYS, 10>(p, n_outer, stream);
+        if (variant == 11) return launch_xfused_v<N, PHYS, 11>(p, n_outer, stream);
+        return launch_xfused_v<N, PHYS, 12>(p, n_outer, stream);
+    }
+#endif
 #if DDL_DEVICE_BUILD
     if (variant == 1) return launch_xfused_v<N, PHYS, 1>(p, n_outer, stream);
     if (variant == 2) return launch_xfused_v<N, PHYS, 2>(p, n_outer, stream);

@@ -30,6 +30,10 @@
 
 static FILE* g_out = nullptr;
 static int g_fail = 0;
+static int g_vmask = 0x3f;    // x-pass variants the sweeps of sections C and T visit (bit v = variant v; argument vmask=...)
+static int g_quick = 0;        // quick=1: section C (compared through 24 sums) and the variant / RK4-step timings only (kernel experiments on a
+                               // short GPU budget); quick=2: the same with the element-by-element comparison
+static int g_assemble_variant = 0;
 static int g_variant = 0;      // x-pass variant in force outside the variant sweeps (set by an xfused_variant=V argument)
 template <class... A> static void say(const char* fmt, A... a) {
     printf(fmt, a...); fflush(stdout);
@@ -171,11 +175,30 @@ static double max_rel_diff(Problem& P, void* const* a, void* const* b) {
     return (num == num && den > 0) ? std::sqrt(num / den) : NAN;
 }
 
+// quick mode: two sets of six spectra compared through the 24 sums of ddl_reduce_invariants (one sweep each on the device)
+// instead of element by element on the host (13 GB of downloads per comparison at 512^3)
+static double invariants_diff(Problem& P, void* const* a, void* const* b) {
+    double ia[DDL_NINV], ib[DDL_NINV];
+    void* a8[8] = {a[0], a[1], a[2], a[3], a[4], a[5], nullptr, nullptr};
+    void* b8[8] = {b[0], b[1], b[2], b[3], b[4], b[5], nullptr, nullptr};
+    DDL(ddl_reduce_invariants(P.plan, DDL_MHD, a8, 0, P.dout, nullptr)); dsync(); d2h(ia, P.dout, sizeof ia);
+    DDL(ddl_reduce_invariants(P.plan, DDL_MHD, b8, 0, P.dout, nullptr)); dsync(); d2h(ib, P.dout, sizeof ib);
+    double e = 0;
+    for (int j = 0; j < DDL_NINV; ++j) {
+        if (ia[j] != ia[j]) return NAN;
+        e = std::fmax(e, std::fabs(ia[j] - ib[j]) / (std::fabs(ib[j]) + std::fabs(ib[0])));
+    }
+    return e;
+}
+
 static void check(int n) {
     say("== devcheck: MHD %d^3, %s\n", n, ddl_version());
     Problem P(n, true);
     const long long nk = P.nk;
     const int nh = n / 2 + 1;
+    double brute[2] = {0, 0};
+    double got[2];
+    if (!g_quick) {
     // ---------------- A: invariants
     double inv_c[DDL_NINV], inv_f[DDL_NINV];
     DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, DDL_STAGE_RETAINED_ONLY, P.dout, nullptr));
@@ -234,7 +257,6 @@ static void check(int n) {
 
     // ---------------- B: max_square
     say("B  CFL maxima\n");
-    double brute[2] = {0, 0};
     {
         std::vector<double> hx(P.nx3);
         void* tmp = dmalloc(nk * 16);
@@ -251,7 +273,6 @@ static void check(int n) {
         }
         dfree(tmp);
     }
-    double got[2];
     for (int fast = 1; fast >= 0; --fast) {
         ddl_set_option("fast_kernels", fast);
         DDL(ddl_reduce_max_square(P.plan, DDL_MHD, &P.prm, P.state, P.work, P.work_bytes, 0, P.dout, nullptr));
@@ -261,6 +282,7 @@ static void check(int n) {
                 std::fmax(rel(got[0], brute[0]), rel(got[1], brute[1])), 1e-12);
     }
     ddl_set_option("fast_kernels", 1);
+    }   // !g_quick
 
     // ---------------- C: RHS variants
     say("C  ddl_rhs variants\n");
@@ -268,23 +290,25 @@ static void check(int n) {
     DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv2, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
     dsync();
     ddl_set_option("fast_kernels", 1);
-    for (int v = 0; v <= 5; ++v) {
+    for (int v = 0; v <= 15; ++v) {
+        if (!(g_vmask >> v & 1)) continue;
         ddl_set_option("xfused_variant", v);
         for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
         dzero(P.dout, 16);
-        DDL(ddl_rhs_capture_max(P.plan, (v == 0 || v >= 4) ? P.dout : nullptr));     // variants 0, 4 and 5 (persistent) also with the capture on
+        DDL(ddl_rhs_capture_max(P.plan, (v == 0 || v == 4 || v == 5) ? P.dout : nullptr));     // variants 0, 4 and 5 (persistent) also with the capture on
         DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
         DDL(ddl_rhs_capture_max(P.plan, nullptr));
         dsync();
-        char label[96]; snprintf(label, sizeof label, "x-pass variant %d vs generic tile kernels (rel L2)", v);
-        verdict(label, max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
-        if (v == 0 || v >= 4) {
+        char label[96]; snprintf(label, sizeof label, g_quick == 1 ? "x-pass variant %d vs generic tile kernels (24 sums)" : "x-pass variant %d vs generic tile kernels (rel L2)", v);
+        verdict(label, g_quick == 1 ? invariants_diff(P, P.deriv, P.deriv2) : max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
+        if (!g_quick && (v == 0 || v == 4 || v == 5)) {
             d2h(got, P.dout, sizeof got);
             verdict("maxima captured inside that RHS", std::fmax(rel(got[0], brute[0]), rel(got[1], brute[1])), 1e-12);
         }
     }
     ddl_set_option("xfused_variant", g_variant);
     for (int chunk : {1, 3}) {
+        if (g_quick) break;
         ddl_set_option("rhs_plane_chunk", chunk);
         for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
         DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
@@ -433,13 +457,13 @@ static void check_seams(int n) {
 
 // one RK4 step the way the Python integrator issues it once the state is dealiased (time_step.py RK4._advance_fused):
 // four ddl_rhs_stage calls, the spectral assembly fused with the stage update, y advanced in place
-static void rk4_fused_step(Problem& P, void* const* tmp, void* const* total, const double* coeff, double dt) {
+static void rk4_fused_step(Problem& P, void* const* tmp, void* const* total, const double* coeff, double dt, void* const* final_out = nullptr) {
     ddl_stage_fuse f;
     memset(&f, 0, sizeof f);
     f.total = total; f.coeff = coeff; f.visc_order = 1; f.kind = DDL_FUSE_RK4;
     const int flags = DDL_STAGE_RETAINED_ONLY * 0;      // ddl_rhs flags: state already dealiased, nothing to zero-fill
     struct { void* const* in; void* const* out; double wdiv, h; int first, last; } st[4] = {
-        {P.state, tmp, 6., dt / 2., 1, 0}, {tmp, tmp, 3., dt / 2., 0, 0}, {tmp, tmp, 3., dt, 0, 0}, {tmp, P.state, 6., dt, 0, 1}};
+        {P.state, tmp, 6., dt / 2., 1, 0}, {tmp, tmp, 3., dt / 2., 0, 0}, {tmp, tmp, 3., dt, 0, 0}, {tmp, final_out ? final_out : P.state, 6., dt, 0, 1}};
     for (int i = 0; i < 4; ++i) {
         f.y = P.state; f.out = st[i].out; f.wdiv = st[i].wdiv; f.dt_step = st[i].h; f.first = st[i].first; f.last = st[i].last;
         DDL(ddl_rhs_stage(P.plan, DDL_MHD, &P.prm, st[i].in, P.work, P.work_bytes, flags, &f, nullptr));
@@ -450,7 +474,8 @@ static void timing(int n, int reps) {
     say("== timing: MHD %d^3 (CUDA events, ms per call, best of %d after 1 warm-up)\n", n, reps);
     Problem P(n, false);
     Timer t;
-    for (int v = 0; v <= 5; ++v) {
+    for (int v = 0; v <= 15; ++v) {
+        if (!(g_vmask >> v & 1)) continue;
         ddl_set_option("xfused_variant", v);
         double best = 1e30;
         for (int r = 0; r <= reps; ++r) {
@@ -470,6 +495,7 @@ static void timing(int n, int reps) {
     ddl_set_option("xfused_variant", g_variant);
     // opt-in L2-residency experiment: y_inv -> x -> y_fwd over chunks of z-planes (include/ddl.h "rhs_plane_chunk")
     for (int chunk : {1, 2, 4, 8}) {
+        if (g_quick) break;
         ddl_set_option("rhs_plane_chunk", chunk);
         double best = 1e30;
         for (int r = 0; r <= reps; ++r) {
@@ -482,6 +508,7 @@ static void timing(int n, int reps) {
     }
     ddl_set_option("rhs_plane_chunk", 0);
     for (int mode = 0; mode < 3; ++mode) {
+        if (g_quick) break;
         double best = 1e30;
         for (int r = 0; r <= reps; ++r) {
             t.start();
@@ -501,6 +528,32 @@ static void timing(int n, int reps) {
         double inv[DDL_NINV];
         DDL(ddl_reduce_invariants(P.plan, DDL_MHD, P.state, 0, P.dout, nullptr)); dsync(); d2h(inv, P.dout, sizeof inv);
         const double dt = 0.2 * (2 * 3.14159265358979323846 / n) / std::sqrt(2.0 * inv[0] + 1e-300);      // ~ CFL 0.2 on the rms speed
+        // the fused assembly + stage kernel in its launch variants (ddl_set_option("assemble_variant", v)): same step from the same
+        // state into a side buffer, compared with variant 0, and timed
+        {
+            void* ref6[6]; void* out6[6];
+            for (int c = 0; c < 6; ++c) { ref6[c] = dmalloc(P.nk * 16); out6[c] = dmalloc(P.nk * 16); }
+            for (int av = 0; av <= 3; ++av) {
+                ddl_set_option("assemble_variant", av);
+                double b = 1e30;
+                for (int r = 0; r <= reps; ++r) {
+                    t.start();
+                    rk4_fused_step(P, tmp, total, coeff, dt, av == 0 ? ref6 : out6);
+                    const double ms = t.stop_ms();
+                    if (r > 0 && ms < b) b = ms;
+                }
+                ddl_profile_enable(1);
+                rk4_fused_step(P, tmp, total, coeff, dt, av == 0 ? ref6 : out6);
+                static char pb[1 << 16];
+                DDL(ddl_profile_report(pb, sizeof pb));
+                ddl_profile_enable(0);
+                const char* as = strstr(pb, "\"assemble_stage\"");
+                say("  RK4 step, assemble_variant %d: %.3f ms   %.48s\n", av, b, as ? as : "");
+                if (av > 0) { char label[96]; snprintf(label, sizeof label, "assemble_variant %d vs 0: state after the step (rel L2)", av); verdict(label, g_quick == 1 ? invariants_diff(P, out6, ref6) : max_rel_diff(P, out6, ref6), 1e-14); }
+            }
+            ddl_set_option("assemble_variant", g_assemble_variant);
+            for (int c = 0; c < 6; ++c) { dfree(ref6[c]); dfree(out6[c]); }
+        }
         double best = 1e30;
         for (int r = 0; r <= reps; ++r) {
             t.start();
@@ -594,15 +647,17 @@ int main(int argc, char** argv) {
         const char* eq = strchr(argv[i], '=');
         if (eq) {
             char name[64]; snprintf(name, sizeof name, "%.*s", (int)(eq - argv[i]), argv[i]);
-            const int val = atoi(eq + 1);
+            const int val = (int)strtol(eq + 1, nullptr, 0);
             if (!strcmp(name, "reps")) reps = val;
-            else { if (!strcmp(name, "xfused_variant")) g_variant = val; DDL(ddl_set_option(name, val)); }
+            else if (!strcmp(name, "vmask")) g_vmask = val;
+            else if (!strcmp(name, "quick")) g_quick = val;
+            else { if (!strcmp(name, "xfused_variant")) g_variant = val; if (!strcmp(name, "assemble_variant")) g_assemble_variant = val; DDL(ddl_set_option(name, val)); }
         } else if (pos == 0) { n_check = atoi(argv[i]); pos++; }
         else if (pos == 1) { n_time = atoi(argv[i]); pos++; }
         else if (pos == 2) { g_out = fopen(argv[i], "w"); pos++; }
     }
-    if (n_check > 0) { check(n_check); check_seams(n_check < 64 ? n_check : 64); check_boxes(n_check, false); }
-    if (n_time > 0) { timing(n_time, reps); check_boxes(n_time, true); }
+    if (n_check > 0) { check(n_check); if (!g_quick) { check_seams(n_check < 64 ? n_check : 64); check_boxes(n_check, false); } }
+    if (n_time > 0) { timing(n_time, reps); if (!g_quick) check_boxes(n_time, true); }
     say("devcheck: %s (%d failure%s)\n", g_fail ? "FAILED" : "all ok", g_fail, g_fail == 1 ? "" : "s");
     if (g_out) fclose(g_out);
     return g_fail ? 1 : 0;
