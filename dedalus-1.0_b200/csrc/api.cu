@@ -956,6 +956,7 @@ static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const 
                         ddl_stream_t st) {
     const int v = g_assemble_variant;
     if (v <= 0) return assemble_rk4_v<PHYS, false>(pl, E, state, pc, fu, st, 4);
+    if (v == 4) return assemble_rk4_v<PHYS, false>(pl, E, state, pc, fu, st, 2);
     return assemble_rk4_v<PHYS, true>(pl, E, state, pc, fu, st, v == 2 ? 3 : (v == 3 ? 2 : 4));
 }
 

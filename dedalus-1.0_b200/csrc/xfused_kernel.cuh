@@ -577,8 +577,8 @@ template <int N, class PHYS, int V> struct XFusedCfg {
     static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
     static constexpr int G = (N >= 512) ? 1 : 512 / N;
     static constexpr int TP = N / XFac<N>::radix(0);
-    static constexpr int NT = TP > 32 ? 9 * TP : ((V == 1 || V == 12) ? 288 : (V == 10 ? 96 : (V == 11 ? 128 : 192)));
-    static constexpr int PACK = (V == 6 || V == 7) ? 1 : (V >= 8 ? 2 : 0);
+    static constexpr int NT = TP > 32 ? 9 * TP : ((V == 1 || V == 12) ? 288 : ((V == 10 || V == 13) ? 96 : ((V == 11 || V == 14) ? 128 : 192)));
+    static constexpr int PACK = (V == 6 || V == 7) ? 1 : ((V >= 8 && V <= 12) ? 2 : 0);
     static constexpr size_t SMEM = ((size_t)G * NS * N + (PACK != 0 ? TP : 0)) * sizeof(cplx);      // PACK != 0: + the parked stage-0 twiddles
     static constexpr int WANT = (V == 0 || (V >= 6 && V != 12)) ? 3 : 2;
     static constexpr int MINB = (SMEM * WANT <= 222 * 1024 && NT * WANT <= 1024) ? WANT : ((SMEM * 2 <= 222 * 1024 && NT * 2 <= 1024) ? 2 : 1);
@@ -659,6 +659,12 @@ int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t 
         if (variant == 10) return launch_xfused_v<N, PHYS, 10>(p, n_outer, stream);
         if (variant == 11) return launch_xfused_v<N, PHYS, 11>(p, n_outer, stream);
         return launch_xfused_v<N, PHYS, 12>(p, n_outer, stream);
+    }
+    // the original pack in the small shapes: 13: 3 warps x 3 CTAs per SM (168 registers, every round of either direction full:
+    // 6 and 9 pencils on 3 warps), 14: 4 x 3
+    if ((variant == 13 || variant == 14) && XFusedCfg<N, PHYS, 0>::TP <= 32) {
+        if (variant == 13) return launch_xfused_v<N, PHYS, 13>(p, n_outer, stream);
+        return launch_xfused_v<N, PHYS, 14>(p, n_outer, stream);
     }
 #endif
 #if DDL_DEVICE_BUILD

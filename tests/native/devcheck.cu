@@ -533,7 +533,7 @@ static void timing(int n, int reps) {
         {
             void* ref6[6]; void* out6[6];
             for (int c = 0; c < 6; ++c) { ref6[c] = dmalloc(P.nk * 16); out6[c] = dmalloc(P.nk * 16); }
-            for (int av = 0; av <= 3; ++av) {
+            for (int av = 0; av <= 4; ++av) {
                 ddl_set_option("assemble_variant", av);
                 double b = 1e30;
                 for (int r = 0; r <= reps; ++r) {
