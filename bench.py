@@ -129,7 +129,8 @@ def moved_bytes_per_rhs(n, kept, ni=6, no=9, ncomp=6):
         # 9 product spectra + per component: y_n read, stage state written, running total read + written (the first stage
         # of a step does not read it, the last does not write it): 3.5 sweeps per component on average over the 4 stages
         "assemble_stage": (no + 3.5 * ncomp) * cy * cz * row,
-        "assemble_stage_first": (no + 3 * ncomp) * cy * cz * row,      # the launch the committed ncu capture holds
+        "assemble_stage_first": (no + 3 * ncomp) * cy * cz * row,      # first stage of a step (round-1 capture, profiles/r2/ncu_r2a.json)
+        "assemble_stage_middle": (no + 4 * ncomp) * cy * cz * row,     # the launch the committed ncu capture holds (prof_r2b)
     }
 
 

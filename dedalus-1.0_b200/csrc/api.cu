@@ -928,8 +928,12 @@ static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* cons
 
 // ddl_set_option("assemble_variant", v): 0 = loads where the arithmetic needs them, four CTAs per SM; 1 = every operand of a
 // mode loaded up front (AssembleStageF<PHYS, true>), four CTAs per SM; 2, 3 = the same with three / two CTAs per SM (85 / 128
-// registers per thread, so that all of a mode's loads can be in flight at once)
-static int g_assemble_variant = 0;
+// registers per thread, so that all of a mode's loads can be in flight at once); 4 = variant 0 with two CTAs per SM.
+// Measured at 512^3 MHD RK4 on a B200 (profiles/r2/devcheck_b200_xpass_pack.txt, ..._shapes.txt), ms per launch, same bits out:
+// 0: 2.04   1: 3.52 (64 registers: 704 B of spills)   2: 2.68   3: 1.77   4: 2.68.  In variant 0 a mode pays one memory round
+// trip for the nine product spectra and one more per component (start value, running total); variant 3 has all 21 loads of a
+// mode in flight at once: 10.9 GB in 1.87 ms under ncu = 5.8 TB/s, 0.90 of the measured copy bandwidth (variant 0: 0.80).
+static int g_assemble_variant = 3;
 
 template <class PHYS, bool HOIST>
 static int assemble_rk4_v(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_stage_fuse* fu,

@@ -330,7 +330,11 @@ int ddl_profile_enable(int on);
 int ddl_profile_report(char* json_out, size_t nbytes);
 
 /* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both);
- * "xfused_variant" = 0/1/2/3 picks the variant of the fused x pass (csrc/xfused_kernel.cuh);
+ * "xfused_variant" = 0..14 picks the variant of the fused x pass (csrc/xfused_kernel.cuh: CTA shapes, retained count at compile
+ *   time, persistent / staged kernels, branch-free input packs; 0 = the measured best);
+ * "assemble_variant" = 0..4 picks the launch variant of the spectral assembly fused with the stage update (ddl_rhs_stage): 3 (the
+ *   default) loads every operand of a mode before any arithmetic and runs two 256-thread CTAs per SM at 128 registers, 0 is the
+ *   round-1 kernel (loads between the per-component updates, four CTAs per SM); all variants are the same arithmetic, bit for bit;
  * "rhs_plane_chunk" = n > 0 runs y_inv -> x -> y_fwd of the one-rank 3-D RHS over chunks of n z-planes with chunk-sized,
  *   reused half-transformed arrays (an L2-residency experiment, default 0 = off; measured slower on B200);
  * "peer_pass_ctas" = n > 0 limits the slab passes that store to the peers over NVLink (ddl_slab_zinv_peer / ddl_slab_yfwd_peer) to n

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "dedalus-1.0_b200", "build")
 
 # kernel family -> largest CTA its launcher asks for (csrc/api.cu round32, pointwise.cuh, reduce.cuh, p2p.cu)
-MAX_THREADS = {"ddl::tile_kernel": 768, "ddl::items_kernel": 256, "ddl::reduce_kernel": 256, "ddl::reduce_final_kernel": 256,
+MAX_THREADS = {"ddl::tile_kernel": 768, "ddl::items_kernel": 256, "ddl::items_kernel_b": 256, "ddl::reduce_kernel": 256, "ddl::reduce_final_kernel": 256,
                "ddl::p2p_wait_kernel": 32, "ddl::p2p_signal_kernel": 32, "ddl::fp64_rate_kernel": 256, "ddl::p2p_push_kernel": 1024, "ddl::p2p_tma_push_kernel": 32}
 
 

@@ -501,6 +501,37 @@ def test_xfused_launch_variants_agree(physics, shape):
         assert rel(o, out[0]) < 1e-14
 
 
+@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (16, 16, 32)), ("BoussinesqHydro", (16, 32, 16)), ("IncompressibleHydro", (16, 16, 16)),
+                                           ("IncompressibleMHD", (32, 48)), ("BoussinesqHydro", (32, 32)), ("IncompressibleHydro", (48, 32))])
+@pytest.mark.parametrize("stepper", ["RK4", "RK2mid", "RK2trap", "CrankNicholsonVisc"])
+def test_assemble_stage_launch_variants_agree(physics, shape, stepper):
+    """ddl_set_option("assemble_variant", v): the spectral assembly fused with the stage update loads its operands where the
+    arithmetic needs them (0, 4) or all up front (1-3, the default 3), at four, three or two CTAs per SM -- one arithmetic:
+    three steps of every integrator (the first sets the fused path up, the others run it) end in the same bits."""
+    import dedalus._lib as L
+    import dedalus.time_stepping.api as tapi
+    import dedalus_oracle as orc
+    params = dict(nu=1e-3, eta=2e-3) if physics == "IncompressibleMHD" else (dict(nu=1e-3, kappa=2e-3) if physics == "BoussinesqHydro" else dict(nu=1e-3))
+    Po = oracle_physics(physics, shape, None, params)
+    y0 = orc.synthetic_ic(Po, 5).kvector()
+    out, launches = [], []
+    try:
+        for v in (0, 1, 2, 3, 4):
+            L.set_option("assemble_variant", v)
+            P = dev_physics(physics, shape, None, params)
+            data = P.create_fields(0.)
+            set_state(data, y0)
+            ti = getattr(tapi, stepper)(P)
+            for _ in range(3):
+                ti.do_advance(data, 2e-3)
+            out.append(get_state(data))
+    finally:
+        L.set_option("assemble_variant", 3)
+    assert np.isfinite(out[0]).all()
+    for o in out[1:]:
+        assert rel(o, out[0]) < 1e-15
+
+
 @pytest.mark.parametrize("physics,shape", [("BoussinesqHydro", (16, 16, 16)), ("IncompressibleMHD", (16, 16, 16)), ("IncompressibleHydro", (32, 32))])
 def test_caller_written_states_reach_the_fused_stage_path(physics, shape):
     """After the first (unfused) step every stage of a solenoidal, dealiased run is ONE ddl_rhs_stage call -- also for states
