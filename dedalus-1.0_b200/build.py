@@ -44,10 +44,34 @@ def _run(cmd, log):
     return r.stdout
 
 
+class _BuildLock:
+    """Exclusive lock on <dir>/.lock for the duration of a build: several processes asking for the same stale target (the ranks of a
+    gloo test, pytest-xdist workers) must not compile into the same object files at once; the late-comers find it fresh."""
+
+    def __init__(self, directory):
+        self.path = os.path.join(directory, ".lock")
+
+    def __enter__(self):
+        import fcntl
+        self.fh = open(self.path, "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
+
+
 def build_cuda(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    with _BuildLock(objdir):
+        return _build_cuda_locked(objdir, force, verbose)
+
+
+def _build_cuda_locked(objdir, force, verbose):
     stamp = os.path.join(LIBDIR, ".digest")
     dig = _digest("cuda")
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
@@ -80,6 +104,11 @@ def build_emul(outdir, sanitize=False):
     """g++-only build of the same sources with DDL_HOST_EMUL (tests/host only; never shipped).
     sanitize: AddressSanitizer + UBSan instrumentation (the process needs libasan preloaded; tests/test_host_sanitizer.py)."""
     os.makedirs(outdir, exist_ok=True)
+    with _BuildLock(outdir):
+        return _build_emul_locked(outdir, sanitize)
+
+
+def _build_emul_locked(outdir, sanitize):
     lib = os.path.join(outdir, "libddl_emul.so")
     stamp = os.path.join(outdir, ".digest")
     dig = _digest("emul-asan" if sanitize else "emul")
