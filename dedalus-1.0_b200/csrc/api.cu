@@ -11,6 +11,7 @@
 #include "reduce.cuh"
 #include "tile_kernel.cuh"
 #include "fast_kernels.cuh"
+#include "fast_two.cuh"
 #include "xfused_kernel.cuh"
 
 namespace ddl {
@@ -146,6 +147,21 @@ static int run_xfused(int N, int phys, const XFusedParams& p, int n_outer, ddl_s
 #define DDL_CASEX(N) case N: return run_xfused_##N(phys, p, n_outer, g_xfused_variant, s);
         DDL_CASEX(8) DDL_CASEX(16) DDL_CASEX(32) DDL_CASEX(64) DDL_CASEX(128) DDL_CASEX(256) DDL_CASEX(512)
         DDL_CASEX(1024) DDL_CASEX(2048)
+    }
+    return 1;
+}
+
+// two-stage strided pass (fast_two.cuh), both builds; ddl_set_option("strided_two", 1 | 2) routes the plain-row passes of the
+// lengths it covers through it (1: stage-0 twiddles generated in registers, 2: loaded from the table)
+#define DDL_DECLT(N) int run_two_strided_##N(int, int, const TwoParams&, int, int, const char*, ddl_stream_t);
+DDL_DECLT(8) DDL_DECLT(16) DDL_DECLT(32) DDL_DECLT(64) DDL_DECLT(128) DDL_DECLT(256) DDL_DECLT(512) DDL_DECLT(1024)
+DDL_DECLT(2048)
+static int g_strided_two = 0;
+static int run_two_strided(int N, int dir, const TwoParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
+    switch (N) {
+#define DDL_CASET(N) case N: return run_two_strided_##N(dir, g_strided_two, p, nf, n_outer, name, s);
+        DDL_CASET(8) DDL_CASET(16) DDL_CASET(32) DDL_CASET(64) DDL_CASET(128) DDL_CASET(256) DDL_CASET(512)
+        DDL_CASET(1024) DDL_CASET(2048)
     }
     return 1;
 }
@@ -500,6 +516,17 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
                     const TileSide& so, RowSpec ri, RowSpec ro, int inner_len, int n_outer, double scale, const cplx* tw,
                     ddl_stream_t st, const PeerOut* peer = nullptr) {
     if (n_outer <= 0 || nf <= 0 || inner_len <= 0) return 0;     // a rank may own no retained ky row
+    if (g_strided_two && g_use_fast && !peer && si.s_inner == 1 && so.s_inner == 1 && si.s_n != 1 && so.s_n != 1 && nf <= DDL_MAXF &&
+        !si.split && !so.split && ri.compact != 2 && ro.compact != 2) {
+        TwoParams t;
+        memset(&t, 0, sizeof(t));
+        for (int i = 0; i < nf; ++i) { t.in[i] = (const cplx*)in[i]; t.out[i] = (cplx*)out[i]; }
+        t.si.s_n = si.s_n; t.si.s_outer = si.s_outer; t.si.outer_tab = si.outer_tab; t.si.m = ri.m; t.si.compact = ri.compact;
+        t.so.s_n = so.s_n; t.so.s_outer = so.s_outer; t.so.outer_tab = so.outer_tab; t.so.m = ro.m; t.so.compact = ro.compact;
+        t.inner_len = inner_len; t.scale = scale; t.tw = tw;
+        const int rc = run_two_strided(N, dir, t, nf, n_outer, name, st);
+        if (rc <= 0) return rc;
+    }
 #if DDL_DEVICE_BUILD
     const bool pow2 = !(si.split & (si.split - 1)) && !(so.split & (so.split - 1));
     if (g_use_fast && si.s_inner == 1 && so.s_inner == 1 && si.s_n != 1 && so.s_n != 1 && nf <= DDL_MAXF && pow2) {
@@ -1394,6 +1421,7 @@ extern "C" int ddl_set_option(const char* name, int value) {
     if (name && !strcmp(name, "p2p_timeout_s")) { ddl::g_p2p_timeout_s = value < 0 ? 0 : value; return 0; }
     if (name && !strcmp(name, "xfused_variant")) { g_xfused_variant = value; return 0; }
     if (name && !strcmp(name, "assemble_variant")) { g_assemble_variant = value; return 0; }
+    if (name && !strcmp(name, "strided_two")) { g_strided_two = value; return 0; }
     if (name && !strcmp(name, "rhs_plane_chunk")) { g_plane_chunk = value < 0 ? 0 : value; return 0; }
     set_error("unknown option %s", name ? name : "(null)");
     return -1;

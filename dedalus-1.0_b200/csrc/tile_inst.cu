@@ -7,6 +7,7 @@
 #include "xfused_kernel.cuh"
 #include "xfused_persist.cuh"
 #include "xfused_rot.cuh"
+#include "fast_two.cuh"
 
 #ifndef DDL_N
 #error "compile with -DDDL_N=<transform length>"
@@ -60,6 +61,21 @@ int DDL_CAT(run_xfused_, DDL_N)(int phys, const XFusedParams& p, int n_outer, in
         }
     }
     return 1;
+}
+
+// two-stage strided pass for plain rows (fast_two.cuh); returns 1 if this length has none
+template <int N, bool OK = TwoFac<N>::ok> struct TwoStrided {
+    static int run(int, int, const TwoParams&, int, int, const char*, ddl_stream_t) { return 1; }
+};
+template <int N> struct TwoStrided<N, true> {
+    static int run(int dir, int variant, const TwoParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
+        if (variant == 2)      // twiddles from the table
+            return dir < 0 ? launch_strided_two<N, -1, true>(p, nf, n_outer, name, s) : launch_strided_two<N, +1, true>(p, nf, n_outer, name, s);
+        return dir < 0 ? launch_strided_two<N, -1, false>(p, nf, n_outer, name, s) : launch_strided_two<N, +1, false>(p, nf, n_outer, name, s);
+    }
+};
+int DDL_CAT(run_two_strided_, DDL_N)(int dir, int variant, const TwoParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
+    return TwoStrided<DDL_N>::run(dir, variant, p, nf, n_outer, name, s);
 }
 
 #if DDL_DEVICE_BUILD

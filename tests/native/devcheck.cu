@@ -33,7 +33,8 @@ static int g_fail = 0;
 static int g_vmask = 0x3f;    // x-pass variants the sweeps of sections C and T visit (bit v = variant v; argument vmask=...)
 static int g_quick = 0;        // quick=1: section C (compared through 24 sums) and the variant / RK4-step timings only (kernel experiments on a
                                // short GPU budget); quick=2: the same with the element-by-element comparison
-static int g_assemble_variant = 0;
+static int g_assemble_variant = 3;
+static int g_strided_two = 0;
 static int g_variant = 0;      // x-pass variant in force outside the variant sweeps (set by an xfused_variant=V argument)
 template <class... A> static void say(const char* fmt, A... a) {
     printf(fmt, a...); fflush(stdout);
@@ -307,6 +308,16 @@ static void check(int n) {
         }
     }
     ddl_set_option("xfused_variant", g_variant);
+    for (int tv = 1; tv <= 2; ++tv) {
+        // the y / z passes as two register butterflies around one trip through shared memory (csrc/fast_two.cuh)
+        ddl_set_option("strided_two", tv);
+        for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
+        DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
+        dsync();
+        char label[96]; snprintf(label, sizeof label, g_quick == 1 ? "strided_two %d vs generic tile kernels (24 sums)" : "strided_two %d vs generic tile kernels (rel L2)", tv);
+        verdict(label, g_quick == 1 ? invariants_diff(P, P.deriv, P.deriv2) : max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
+    }
+    ddl_set_option("strided_two", g_strided_two);
     for (int chunk : {1, 3}) {
         if (g_quick) break;
         ddl_set_option("rhs_plane_chunk", chunk);
@@ -493,6 +504,23 @@ static void timing(int n, int reps) {
         say("  ddl_rhs, x-pass variant %d: %.3f ms   %.40s\n", v, best, xf ? xf : "");
     }
     ddl_set_option("xfused_variant", g_variant);
+    for (int tv = 0; tv <= 2; ++tv) {
+        ddl_set_option("strided_two", tv);
+        double best = 1e30;
+        for (int r = 0; r <= reps; ++r) {
+            t.start();
+            DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
+            const double ms = t.stop_ms();
+            if (r > 0 && ms < best) best = ms;
+        }
+        ddl_profile_enable(1);
+        DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
+        static char pbuf2[1 << 14];
+        DDL(ddl_profile_report(pbuf2, sizeof pbuf2));
+        ddl_profile_enable(0);
+        say("  ddl_rhs, strided_two %d: %.3f ms   %s\n", tv, best, pbuf2);
+    }
+    ddl_set_option("strided_two", g_strided_two);
     // opt-in L2-residency experiment: y_inv -> x -> y_fwd over chunks of z-planes (include/ddl.h "rhs_plane_chunk")
     for (int chunk : {1, 2, 4, 8}) {
         if (g_quick) break;
@@ -651,7 +679,7 @@ int main(int argc, char** argv) {
             if (!strcmp(name, "reps")) reps = val;
             else if (!strcmp(name, "vmask")) g_vmask = val;
             else if (!strcmp(name, "quick")) g_quick = val;
-            else { if (!strcmp(name, "xfused_variant")) g_variant = val; if (!strcmp(name, "assemble_variant")) g_assemble_variant = val; DDL(ddl_set_option(name, val)); }
+            else { if (!strcmp(name, "xfused_variant")) g_variant = val; if (!strcmp(name, "assemble_variant")) g_assemble_variant = val; if (!strcmp(name, "strided_two")) g_strided_two = val; DDL(ddl_set_option(name, val)); }
         } else if (pos == 0) { n_check = atoi(argv[i]); pos++; }
         else if (pos == 1) { n_time = atoi(argv[i]); pos++; }
         else if (pos == 2) { g_out = fopen(argv[i], "w"); pos++; }

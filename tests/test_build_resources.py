@@ -40,7 +40,7 @@ def test_every_kernel_fits_its_largest_launch():
             assert warps * per_warp <= 65536, (name, regs, MAX_THREADS[family])
         else:
             # xfused_kernel / strided_fast carry __maxnreg__ / __launch_bounds__ derived from their own CTA shape
-            assert family in ("ddl::xfused_kernel", "ddl::xfused_persist_kernel", "ddl::xfused_rot_kernel", "ddl::strided_fast", "ddl::strided_staged"), name
+            assert family in ("ddl::xfused_kernel", "ddl::xfused_persist_kernel", "ddl::xfused_rot_kernel", "ddl::strided_fast", "ddl::strided_staged", "ddl::strided_two"), name
     for family in MAX_THREADS:
         assert seen[family] > 0, family
 

@@ -501,6 +501,44 @@ def test_xfused_launch_variants_agree(physics, shape):
         assert rel(o, out[0]) < 1e-14
 
 
+@pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (256, 16, 16)), ("IncompressibleHydro", (16, 256, 16)), ("BoussinesqHydro", (512, 8, 16)),
+                                           ("IncompressibleHydro", (8, 512, 16)), ("IncompressibleMHD", (256, 256, 16))])
+def test_two_stage_strided_pass_agrees(physics, shape):
+    """ddl_set_option("strided_two", 1): the y / z passes of lengths 256 and 512 as two register butterflies (16 x 16, 16 x 32)
+    around ONE trip through shared memory (csrc/fast_two.cuh) instead of three radix-8 stages: same RHS as the default kernels
+    to round-off and as the oracle to the usual tolerance; plain transforms (forward / backward of one component) included."""
+    import torch
+    import dedalus._lib as L
+    import dedalus_oracle as orc
+    params = dict(nu=1e-3, eta=1e-3) if physics == "IncompressibleMHD" else dict(nu=1e-3)
+    Po = oracle_physics(physics, shape, None, params)
+    do = orc.synthetic_ic(Po, 5)
+    y0 = do.kvector()
+    ko = Po.create_fields(0.)
+    Po.RHS(do, ko)
+    ref = ko.kvector()
+    out, back = [], []
+    try:
+        for v in (0, 1, 2):
+            L.set_option("strided_two", v)
+            P = dev_physics(physics, shape, None, params)
+            data, deriv = P.create_fields(0.), P.create_fields(0.)
+            set_state(data, y0)
+            P.RHS(data, deriv)
+            out.append(get_state(deriv))
+            c = data["u"]["x"]
+            x = c["xspace"].clone()
+            c["xspace"] = x
+            back.append((x.cpu().numpy().copy(), c["kspace"].clone().cpu().numpy()))
+    finally:
+        L.set_option("strided_two", 0)
+    for v in (1, 2):
+        assert np.isfinite(out[v]).all()
+        assert rel(out[v], out[0]) < 1e-13
+        assert rel(back[v][0], back[0][0]) < 1e-13 and rel(back[v][1], back[0][1]) < 1e-13
+        assert rel(out[v], ref) < 1e-12
+
+
 @pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (16, 16, 32)), ("BoussinesqHydro", (16, 32, 16)), ("IncompressibleHydro", (16, 16, 16)),
                                            ("IncompressibleMHD", (32, 48)), ("BoussinesqHydro", (32, 32)), ("IncompressibleHydro", (48, 32))])
 @pytest.mark.parametrize("stepper", ["RK4", "RK2mid", "RK2trap", "CrankNicholsonVisc"])
