@@ -152,11 +152,13 @@ static int run_xfused(int N, int phys, const XFusedParams& p, int n_outer, ddl_s
 }
 
 // two-stage strided pass (fast_two.cuh), both builds; ddl_set_option("strided_two", 1 | 2) routes the plain-row passes of the
-// lengths it covers through it (1: stage-0 twiddles generated in registers, 2: loaded from the table)
+// lengths it covers (256, 512) through it (1: stage-0 twiddles generated in registers, 2: loaded from the table), 0 = the
+// three-stage strided_fast.  Measured at 512^3 MHD on a B200 (profiles/r2/devcheck_b200_strided_two.txt), ms per launch 0 / 1 / 2:
+// z_inv 1.04 / 0.93 / 1.19, y_inv 1.50 / 1.28 / 1.63, y_fwd 2.13 / 1.93 / 2.49, z_fwd 1.31 / 1.24 / 1.57: 1 is the default.
 #define DDL_DECLT(N) int run_two_strided_##N(int, int, const TwoParams&, int, int, const char*, ddl_stream_t);
 DDL_DECLT(8) DDL_DECLT(16) DDL_DECLT(32) DDL_DECLT(64) DDL_DECLT(128) DDL_DECLT(256) DDL_DECLT(512) DDL_DECLT(1024)
 DDL_DECLT(2048)
-static int g_strided_two = 0;
+static int g_strided_two = 1;
 static int run_two_strided(int N, int dir, const TwoParams& p, int nf, int n_outer, const char* name, ddl_stream_t s) {
     switch (N) {
 #define DDL_CASET(N) case N: return run_two_strided_##N(dir, g_strided_two, p, nf, n_outer, name, s);
@@ -516,7 +518,12 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
                     const TileSide& so, RowSpec ri, RowSpec ro, int inner_len, int n_outer, double scale, const cplx* tw,
                     ddl_stream_t st, const PeerOut* peer = nullptr) {
     if (n_outer <= 0 || nf <= 0 || inner_len <= 0) return 0;     // a rank may own no retained ky row
-    if (g_strided_two && g_use_fast && !peer && si.s_inner == 1 && so.s_inner == 1 && si.s_n != 1 && so.s_n != 1 && nf <= DDL_MAXF &&
+#if DDL_DEVICE_BUILD
+    const bool staged_opt_in = ddl::g_strided_staged != 0;        // an explicit opt-in to the staged three-stage kernel wins
+#else
+    const bool staged_opt_in = false;
+#endif
+    if (g_strided_two && !staged_opt_in && g_use_fast && !peer && si.s_inner == 1 && so.s_inner == 1 && si.s_n != 1 && so.s_n != 1 && nf <= DDL_MAXF &&
         !si.split && !so.split && ri.compact != 2 && ro.compact != 2) {
         TwoParams t;
         memset(&t, 0, sizeof(t));

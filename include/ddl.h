@@ -332,6 +332,9 @@ int ddl_profile_report(char* json_out, size_t nbytes);
 /* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both);
  * "xfused_variant" = 0..14 picks the variant of the fused x pass (csrc/xfused_kernel.cuh: CTA shapes, retained count at compile
  *   time, persistent / staged kernels, branch-free input packs; 0 = the measured best);
+ * "strided_two" = 0/1/2: the y / z passes of lengths 256 and 512 on plain rows run as two register butterflies (16 x 16, 16 x 32)
+ *   around one trip through shared memory (csrc/fast_two.cuh; 1 = stage-0 twiddles generated in registers, the default; 2 = loaded
+ *   from the table) or as the three radix-8 stages of strided_fast (0); the slab-decomposed passes always take the latter;
  * "assemble_variant" = 0..4 picks the launch variant of the spectral assembly fused with the stage update (ddl_rhs_stage): 3 (the
  *   default) loads every operand of a mode before any arithmetic and runs two 256-thread CTAs per SM at 128 registers, 0 is the
  *   round-1 kernel (loads between the per-component updates, four CTAs per SM); all variants are the same arithmetic, bit for bit;

@@ -12,11 +12,11 @@ $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 # launch order inside one RHS: z_inv (strided +1), y_inv (strided +1), x_fused, y_fwd (strided -1), z_fwd (strided -1), assemble_stage
 for w in $WHAT; do
   case $w in
-    z_inv) K="regex:strided_fast.*Li1E"; S=0;;
-    y_inv) K="regex:strided_fast.*Li1E"; S=1;;
+    z_inv) K="regex:strided_(two|fast).*Li1E"; S=0;;
+    y_inv) K="regex:strided_(two|fast).*Li1E"; S=1;;
     x_fused) K="regex:xfused"; S=0;;
-    y_fwd) K="regex:strided_fast.*Lin1E"; S=0;;
-    z_fwd) K="regex:strided_fast.*Lin1E"; S=1;;
+    y_fwd) K="regex:strided_(two|fast).*Lin1E"; S=0;;
+    z_fwd) K="regex:strided_(two|fast).*Lin1E"; S=1;;
     assemble_stage) K="regex:AssembleStageF"; S=0;;
   esac
   $NCU --set full --import-source on --kernel-name-base mangled -k "$K" -s $S -c 1 -f -o gpurun_out/prof_${TAG}_$w \

@@ -34,7 +34,7 @@ static int g_vmask = 0x3f;    // x-pass variants the sweeps of sections C and T 
 static int g_quick = 0;        // quick=1: section C (compared through 24 sums) and the variant / RK4-step timings only (kernel experiments on a
                                // short GPU budget); quick=2: the same with the element-by-element comparison
 static int g_assemble_variant = 3;
-static int g_strided_two = 0;
+static int g_strided_two = 1;
 static int g_variant = 0;      // x-pass variant in force outside the variant sweeps (set by an xfused_variant=V argument)
 template <class... A> static void say(const char* fmt, A... a) {
     printf(fmt, a...); fflush(stdout);

@@ -531,7 +531,7 @@ def test_two_stage_strided_pass_agrees(physics, shape):
             c["xspace"] = x
             back.append((x.cpu().numpy().copy(), c["kspace"].clone().cpu().numpy()))
     finally:
-        L.set_option("strided_two", 0)
+        L.set_option("strided_two", 1)
     for v in (1, 2):
         assert np.isfinite(out[v]).all()
         assert rel(out[v], out[0]) < 1e-13
