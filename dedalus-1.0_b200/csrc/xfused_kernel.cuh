@@ -573,14 +573,17 @@ DDL_BODY void xfused_block(const XFusedParams& p, cplx* tile, int bx, int by) {
 //      336 fewer static instructions (cuobjdump: 2 296 -> 1 960 for <512, MHD3C>): opt-in.
 //   4: persistent CTAs, next pair staged by cp.async.bulk + mbarrier (xfused_persist.cuh): 4.92 ms, opt-in
 //   5: persistent CTAs of shape 0, no staging; warps without a second-round pencil start the next pair (xfused_rot.cuh)
+//   6, 8: shape 0 with the branch-free input packs of xpack_inputs (registers only / mirrored half through shared memory):
+//      one to three memory round trips per pencil instead of nine, 4.26 / 4.35 ms -- the pass is bound by the shared-memory /
+//      L1 data pipe (70 % busy), not by that latency: opt-in
 template <int N, class PHYS, int V> struct XFusedCfg {
     static constexpr int NS = PHYS::NI > PHYS::NO ? PHYS::NI : PHYS::NO;
     static constexpr int G = (N >= 512) ? 1 : 512 / N;
     static constexpr int TP = N / XFac<N>::radix(0);
-    static constexpr int NT = TP > 32 ? 9 * TP : ((V == 1 || V == 12) ? 288 : ((V == 10 || V == 13) ? 96 : ((V == 11 || V == 14) ? 128 : 192)));
-    static constexpr int PACK = (V == 6 || V == 7) ? 1 : ((V >= 8 && V <= 12) ? 2 : 0);
+    static constexpr int NT = TP > 32 ? 9 * TP : (V == 1 ? 288 : 192);
+    static constexpr int PACK = V == 6 ? 1 : (V == 8 ? 2 : 0);
     static constexpr size_t SMEM = ((size_t)G * NS * N + (PACK != 0 ? TP : 0)) * sizeof(cplx);      // PACK != 0: + the parked stage-0 twiddles
-    static constexpr int WANT = (V == 0 || (V >= 6 && V != 12)) ? 3 : 2;
+    static constexpr int WANT = (V == 0 || V >= 6) ? 3 : 2;
     static constexpr int MINB = (SMEM * WANT <= 222 * 1024 && NT * WANT <= 1024) ? WANT : ((SMEM * 2 <= 222 * 1024 && NT * 2 <= 1024) ? 2 : 1);
     // register budget that still lets MINB CTAs share an SM: each of the four sub-partitions owns
     // 16 K registers and holds ceil(warps / 4) of the resident warps (allocation unit: 8 per thread)
@@ -647,26 +650,12 @@ int launch_xfused(const XFusedParams& p, int n_outer, int variant, ddl_stream_t 
 #endif
     if (p.cfl) return launch_xfused_v<N, PHYS, 0, true>(p, n_outer, stream);     // capture: default CTA shape only
     if (variant == 3 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 0, false, N / 3 + 1>(p, n_outer, stream);
-    // 6 / 7: branch-free register pack (7: with the 2/3 rule's retained count at compile time when the mask is that rule);
-    // 8 / 9: direct half from global memory, mirrored half through the pencil's shared-memory slot
-    if (variant == 7 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 7, false, N / 3 + 1>(p, n_outer, stream);
-    if (variant == 6 || variant == 7) return launch_xfused_v<N, PHYS, 6>(p, n_outer, stream);
-    if (variant == 9 && p.kn == N / 3 + 1) return launch_xfused_v<N, PHYS, 9, false, N / 3 + 1>(p, n_outer, stream);
-    if (variant == 8 || variant == 9) return launch_xfused_v<N, PHYS, 8>(p, n_outer, stream);
-#if DDL_DEVICE_BUILD
-    // pack 2 in other CTA shapes (pencil groups of one warp only): 10: 3 warps x 3 CTAs per SM, 11: 4 x 3, 12: 9 x 2
-    if (variant >= 10 && variant <= 12 && XFusedCfg<N, PHYS, 0>::TP <= 32) {
-        if (variant == 10) return launch_xfused_v<N, PHYS, 10>(p, n_outer, stream);
-        if (variant == 11) return launch_xfused_v<N, PHYS, 11>(p, n_outer, stream);
-        return launch_xfused_v<N, PHYS, 12>(p, n_outer, stream);
-    }
-    // the original pack in the small shapes: 13: 3 warps x 3 CTAs per SM (168 registers, every round of either direction full:
-    // 6 and 9 pencils on 3 warps), 14: 4 x 3
-    if ((variant == 13 || variant == 14) && XFusedCfg<N, PHYS, 0>::TP <= 32) {
-        if (variant == 13) return launch_xfused_v<N, PHYS, 13>(p, n_outer, stream);
-        return launch_xfused_v<N, PHYS, 14>(p, n_outer, stream);
-    }
-#endif
+    // 6: branch-free register pack; 8: direct half from global memory, mirrored half through the pencil's shared-memory slot
+    // (xpack_inputs).  Both were also measured with the retained count at compile time (4.25 / 4.46 ms) and 8 in the CTA shapes
+    // 3 x 3, 4 x 3 and 9 x 2 warps (4.26 / 4.34 / 4.80 ms; the original pack in 3 x 3 and 4 x 3: 6.23 / 5.98 ms) -- those
+    // instantiations were removed after the measurement (profiles/r2/devcheck_b200_xpass_pack.txt, ..._shapes.txt)
+    if (variant == 6) return launch_xfused_v<N, PHYS, 6>(p, n_outer, stream);
+    if (variant == 8) return launch_xfused_v<N, PHYS, 8>(p, n_outer, stream);
 #if DDL_DEVICE_BUILD
     if (variant == 1) return launch_xfused_v<N, PHYS, 1>(p, n_outer, stream);
     if (variant == 2) return launch_xfused_v<N, PHYS, 2>(p, n_outer, stream);

@@ -330,8 +330,8 @@ int ddl_profile_enable(int on);
 int ddl_profile_report(char* json_out, size_t nbytes);
 
 /* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both);
- * "xfused_variant" = 0..14 picks the variant of the fused x pass (csrc/xfused_kernel.cuh: CTA shapes, retained count at compile
- *   time, persistent / staged kernels, branch-free input packs; 0 = the measured best);
+ * "xfused_variant" = 0..6, 8 picks the variant of the fused x pass (csrc/xfused_kernel.cuh: CTA shapes, retained count at compile
+ *   time, persistent / staged kernels, branch-free input packs; 0 = the measured best; unknown values run 0);
  * "strided_two" = 0/1/2: the y / z passes of lengths 256 and 512 on plain rows run as two register butterflies (16 x 16, 16 x 32)
  *   around one trip through shared memory (csrc/fast_two.cuh; 1 = stage-0 twiddles generated in registers, the default; 2 = loaded
  *   from the table) or as the three radix-8 stages of strided_fast (0); the slab-decomposed passes always take the latter;

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: kept as the record of how profiles/r2/devcheck_b200_xpass_*.txt were produced.  x-pass variants 7 and 9-14 were removed
+# from the library after this measurement (they run variant 0 now); 6 and 8 remain.
 # One short GPU call (native checker only, no Python): x-pass input-pack variants 6-12 and the fused assembly / stage launch
 # variants against the defaults at 512^3, then the RK4 step with the fastest of each.
 #   gpurun --timeout 240 -- 'bash profiles/r2/xpass_shot.sh'

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: kept as the record of how profiles/r2/devcheck_b200_xpass_*.txt were produced.  x-pass variants 7 and 9-14 were removed
+# from the library after this measurement (they run variant 0 now); 6 and 8 remain.
 # Second short GPU call: the original input pack in the 3- and 4-warp CTA shapes (variants 13, 14), the fused assembly / stage
 # launch variants 0-4, and one ncu --set full capture of the hoisted-load 2-CTA variant (a middle RK4 stage).
 #   gpurun --timeout 240 -- 'bash profiles/r2/xpass_shot2.sh'
