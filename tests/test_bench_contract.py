@@ -119,3 +119,15 @@ def test_moved_bytes_model_matches_the_committed_ncu_traffic():
     for k in ("z_inv", "y_inv", "x_fused", "y_fwd", "z_fwd"):
         assert model[k] < bench.ALGO_BYTES_PER_MODE[k] * nk
     assert 50e9 < sum(model[k] for k in traffic) < 54e9
+
+
+def test_smoke_body_runs_against_the_emulation_build():
+    """__graft_entry__.smoke() checks two small RK4 runs against the oracle on cuda:0; its body (everything after the GPU asserts)
+    is dry-run here so that the driver's GPU call is not spent on a Python error: 32^3 through the generic kernels, 16 x 256 x 128
+    through the two-stage strided pass, the fused x pass and the fused assembly / stage kernel."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_emul_child.py"), os.path.join(ROOT, "tests", "smoke_emul_script.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("smoke:")]
+    assert len(lines) == 2 and "16x256x128" in lines[1], r.stdout[-2000:]
+
