@@ -527,11 +527,12 @@ static int pass_c2c(const char* name, int N, int dir, int nf, const void* const*
         !si.split && !so.split && ri.compact != 2 && ro.compact != 2) {
         TwoParams t;
         memset(&t, 0, sizeof(t));
-        for (int i = 0; i < nf; ++i) { t.in[i] = (const cplx*)in[i]; t.out[i] = (cplx*)out[i]; }
+        bool distinct = true;       // the kernel reads through the non-coherent path: never for a pass that writes its own input
+        for (int i = 0; i < nf; ++i) { t.in[i] = (const cplx*)in[i]; t.out[i] = (cplx*)out[i]; distinct = distinct && in[i] != (const void*)out[i]; }
         t.si.s_n = si.s_n; t.si.s_outer = si.s_outer; t.si.outer_tab = si.outer_tab; t.si.m = ri.m; t.si.compact = ri.compact;
         t.so.s_n = so.s_n; t.so.s_outer = so.s_outer; t.so.outer_tab = so.outer_tab; t.so.m = ro.m; t.so.compact = ro.compact;
         t.inner_len = inner_len; t.scale = scale; t.tw = tw;
-        const int rc = run_two_strided(N, dir, t, nf, n_outer, name, st);
+        const int rc = distinct ? run_two_strided(N, dir, t, nf, n_outer, name, st) : 1;
         if (rc <= 0) return rc;
     }
 #if DDL_DEVICE_BUILD
