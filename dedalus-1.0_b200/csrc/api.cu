@@ -969,6 +969,8 @@ static int assemble(ddl_plan* pl, void* const* E, void* const* state, void* cons
 // trip for the nine product spectra and one more per component (start value, running total); variant 3 has all 21 loads of a
 // mode in flight at once: 10.9 GB in 1.87 ms under ncu = 5.8 TB/s, 0.90 of the measured copy bandwidth (variant 0: 0.80).
 static int g_assemble_variant = 3;
+// ddl_set_option("traceless_flux", 0 | 1): the one-rank 3-D RHS with 5 momentum products (T - delta T_zz) instead of 6
+static int g_traceless_flux = 1;
 
 template <class PHYS, bool HOIST>
 static int assemble_rk4_v(ddl_plan* pl, void* const* E, void* const* state, const PhysConst& pc, const ddl_stage_fuse* fu,
@@ -1001,8 +1003,11 @@ static int assemble_rk4(ddl_plan* pl, void* const* E, void* const* state, const 
 
 static int assemble_rk4_any(ddl_plan* pl, int code, void* const* E, void* const* state, const PhysConst& pc,
                             const ddl_stage_fuse* fu, ddl_stream_t st) {
-    if (code > 5) { set_error("the fused stage update exists for the solenoidal policies only (use ddl_rhs + ddl_stage)"); return -1; }
+    if (code > 5 && code < 12) { set_error("the fused stage update exists for the solenoidal policies only (use ddl_rhs + ddl_stage)"); return -1; }
     switch (code) {
+        case 12: return assemble_rk4<Hydro3T>(pl, E, state, pc, fu, st);
+        case 13: return assemble_rk4<Bouss3T>(pl, E, state, pc, fu, st);
+        case 14: return assemble_rk4<MHD3T>(pl, E, state, pc, fu, st);
         case 0: return assemble_rk4<Hydro2C>(pl, E, state, pc, fu, st);
         case 1: return assemble_rk4<Bouss2C>(pl, E, state, pc, fu, st);
         case 2: return assemble_rk4<MHD2C>(pl, E, state, pc, fu, st);
@@ -1026,6 +1031,9 @@ static int assemble_any(ddl_plan* pl, int code, void* const* E, void* const* sta
         case 8: return assemble<MHD2A>(pl, E, state, deriv, pc, st);
         case 9: return assemble<Hydro3A>(pl, E, state, deriv, pc, st);
         case 10: return assemble<Bouss3A>(pl, E, state, deriv, pc, st);
+        case 12: return assemble<Hydro3T>(pl, E, state, deriv, pc, st);
+        case 13: return assemble<Bouss3T>(pl, E, state, deriv, pc, st);
+        case 14: return assemble<MHD3T>(pl, E, state, deriv, pc, st);
         default: return assemble<MHD3A>(pl, E, state, deriv, pc, st);
     }
 }
@@ -1055,6 +1063,9 @@ static int rhs_impl(ddl_plan* pl, int physics, const ddl_phys_params* prm, void*
     DDL_TRY(check_physics(pl, physics, prm));
     phys_counts(pl->ndim, physics, ni, no, code, &ncomp);
     DDL_TRY(check_ws(pl, ni, no, work, work_bytes));
+    // one rank, 3-D, solenoidal policy: the traceless-flux twin (physics_ops.cuh) -- T_zz is never formed or transformed, one
+    // product field fewer through the x pass, the forward y and z passes and the assembly (the workspace was sized for `no`)
+    if (g_traceless_flux && pl->ndim == 3 && code >= 3 && code <= 5) { code += 9; no -= 1; }
     const PhysConst pc = phys_const(prm);
     if (flags & DDL_RHS_DEALIAS_STATE) DDL_TRY(mask_arrays(pl, ncomp, state, st));
     if ((flags & DDL_RHS_ZERO_FILL) && deriv) DDL_TRY(mask_arrays(pl, ncomp, deriv, st));
@@ -1430,6 +1441,7 @@ extern "C" int ddl_set_option(const char* name, int value) {
     if (name && !strcmp(name, "xfused_variant")) { g_xfused_variant = value; return 0; }
     if (name && !strcmp(name, "assemble_variant")) { g_assemble_variant = value; return 0; }
     if (name && !strcmp(name, "strided_two")) { g_strided_two = value; return 0; }
+    if (name && !strcmp(name, "traceless_flux")) { g_traceless_flux = value != 0; return 0; }
     if (name && !strcmp(name, "rhs_plane_chunk")) { g_plane_chunk = value < 0 ? 0 : value; return 0; }
     set_error("unknown option %s", name ? name : "(null)");
     return -1;

@@ -106,6 +106,73 @@ struct MHD3C {
     }
 };
 
+// ------------------------------------------------------------------ 3-D, traceless flux: one forward transform fewer
+// The momentum equation sees the flux only through P[-i k_j T_ij].  An isotropic part of T is a pressure: -i k_j (delta_ij s) = -i k_i s
+// is parallel to k and the projector removes it mode by mode, whatever s is.  With s = T_zz the tensor T' = T - delta T_zz has
+// T'_zz = 0 identically, so that component is never formed, transformed or read: 5 momentum products instead of 6 (the classic
+// saving of pseudospectral Navier-Stokes codes).  Same derivative as Hydro3C / Bouss3C / MHD3C up to the rounding of the
+// projection (measured: 1e-16 relative, tests/test_gpu_widen.py::test_traceless_flux_policies_agree); used by the one-rank
+// ddl_rhs / ddl_rhs_stage (ddl_set_option("traceless_flux", 0) restores the six-product policies, which the slab-decomposed
+// phases keep: their field counts are part of the exchange layout).
+//   products: 0: T_xx - T_zz   1: T_xy   2: T_xz   3: T_yy - T_zz   4: T_yz   then the policy's other products
+struct Hydro3T {
+    static constexpr int NI = 3, NO = 5, NS = 0, NC = 3, NDIM = 3, NG1 = 0;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst&) {
+        const double u = in[0], v = in[1], w = in[2];
+        const double tzz = w * w;
+        o[0] = u * u - tzz; o[1] = u * v; o[2] = u * w; o[3] = v * v - tzz; o[4] = v * w;
+    }
+    DDL_HD static void momentum(const cplx* P, cplx& nx, cplx& ny, cplx& nz, double kx, double ky, double kz) {
+        nx = mul_mi(lin3(kx, P[0], ky, P[1], kz, P[2]));
+        ny = mul_mi(lin3(kx, P[1], ky, P[3], kz, P[4]));
+        nz = mul_mi(lin2(kx, P[2], ky, P[4]));
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx*, cplx* D, double kx, double ky, double kz, const PhysConst&) {
+        cplx nx, ny, nz;
+        momentum(P, nx, ny, nz, kx, ky, kz);
+        project3(nx, ny, nz, kx, ky, kz, k2nz3(kx, ky, kz));
+        D[0] = nx; D[1] = ny; D[2] = nz;
+    }
+};
+
+struct Bouss3T {
+    static constexpr int NI = 4, NO = 8, NS = 4, NC = 4, NDIM = 3, NG1 = 1;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst& pc) {
+        Hydro3T::apply(in, o, pc);
+        const double T = in[3];
+        o[5] = in[0] * T; o[6] = in[1] * T; o[7] = in[2] * T;
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx* S, cplx* D, double kx, double ky, double kz, const PhysConst& pc) {
+        cplx n[3];
+        Hydro3T::momentum(P, n[0], n[1], n[2], kx, ky, kz);
+        n[pc.bdir] = n[pc.bdir] + scal(S[3], pc.g_alpha);
+        project3(n[0], n[1], n[2], kx, ky, kz, k2nz3(kx, ky, kz));
+        D[0] = n[0]; D[1] = n[1]; D[2] = n[2];
+        D[3] = mul_mi(lin3(kx, P[5], ky, P[6], kz, P[7])) - scal(S[pc.bdir], pc.beta);
+    }
+};
+
+struct MHD3T {
+    static constexpr int NI = 6, NO = 8, NS = 0, NC = 6, NDIM = 3, NG1 = 3;
+    DDL_HD static void apply(const double* in, double* o, const PhysConst& pc) {
+        const double u = in[0], v = in[1], w = in[2], a = in[3], b = in[4], c = in[5];
+        const double f = pc.inv_fpr;
+        const double tzz = w * w - f * (c * c);
+        o[0] = (u * u - f * (a * a)) - tzz; o[1] = u * v - f * (a * b); o[2] = u * w - f * (a * c);
+        o[3] = (v * v - f * (b * b)) - tzz; o[4] = v * w - f * (b * c);
+        o[5] = v * c - w * b; o[6] = w * a - u * c; o[7] = u * b - v * a;     // E = u x B
+    }
+    DDL_HD static void assemble(const cplx* P, const cplx*, cplx* D, double kx, double ky, double kz, const PhysConst&) {
+        cplx nx, ny, nz;
+        Hydro3T::momentum(P, nx, ny, nz, kx, ky, kz);
+        project3(nx, ny, nz, kx, ky, kz, k2nz3(kx, ky, kz));
+        D[0] = nx; D[1] = ny; D[2] = nz;
+        D[3] = mul_pi(lin2(ky, P[7], -kz, P[6]));
+        D[4] = mul_pi(lin2(kz, P[5], -kx, P[7]));
+        D[5] = mul_pi(lin2(kx, P[6], -ky, P[5]));
+    }
+};
+
 // ------------------------------------------------------------------ 2-D
 struct Hydro2C {
     static constexpr int NI = 2, NO = 3, NS = 0, NC = 2, NDIM = 2, NG1 = 0;

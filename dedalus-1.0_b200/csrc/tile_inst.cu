@@ -40,6 +40,10 @@ int DDL_CAT(run_tile_, DDL_N)(int mode, int dir, int phys, const TileParams& p, 
                 case 9: return launch_tile<N, TM_FUSED, 0, Hydro3A>(p, nthreads, s);
                 case 10: return launch_tile<N, TM_FUSED, 0, Bouss3A>(p, nthreads, s);
                 case 11: return launch_tile<N, TM_FUSED, 0, MHD3A>(p, nthreads, s);
+                // traceless-flux policies of the one-rank 3-D RHS (physics_ops.cuh)
+                case 12: return launch_tile<N, TM_FUSED, 0, Hydro3T>(p, nthreads, s);
+                case 13: return launch_tile<N, TM_FUSED, 0, Bouss3T>(p, nthreads, s);
+                case 14: return launch_tile<N, TM_FUSED, 0, MHD3T>(p, nthreads, s);
             }
     }
     set_error("run_tile: bad mode/physics %d/%d", mode, phys);
@@ -54,6 +58,12 @@ int DDL_CAT(run_xfused_, DDL_N)(int phys, const XFusedParams& p, int n_outer, in
             case 3: return launch_xfused<N, Hydro3C>(p, n_outer, variant, s);
             case 4: return launch_xfused<N, Bouss3C>(p, n_outer, variant, s);
             case 5: return launch_xfused<N, MHD3C>(p, n_outer, variant, s);
+            // traceless-flux policies (what the one-rank ddl_rhs runs by default): the default CTA shape and its CFL-capture twin
+            // only -- the opt-in launch variants were built and measured on the six-product policies and stay with them
+            // (ddl_set_option("traceless_flux", 0) + "xfused_variant")
+            case 12: return launch_xfused_basic<N, Hydro3T>(p, n_outer, s);
+            case 13: return launch_xfused_basic<N, Bouss3T>(p, n_outer, s);
+            case 14: return launch_xfused_basic<N, MHD3T>(p, n_outer, s);
             // advective-form policies (states that are not solenoidal, e.g. the reference's own 3-D turb_new fields): the two
             // whose field counts fit the kernel's pointer tables; Boussinesq (13 products) stays on the generic tile kernel
             case 9: return launch_xfused_basic<N, Hydro3A>(p, n_outer, s);

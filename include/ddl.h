@@ -332,6 +332,9 @@ int ddl_profile_report(char* json_out, size_t nbytes);
 /* "fast_kernels" = 0 routes every pass through the generic tile kernel (tests compare both);
  * "xfused_variant" = 0..6, 8 picks the variant of the fused x pass (csrc/xfused_kernel.cuh: CTA shapes, retained count at compile
  *   time, persistent / staged kernels, branch-free input packs; 0 = the measured best; unknown values run 0);
+ * "traceless_flux" = 0/1 (default 1): the one-rank 3-D ddl_rhs / ddl_rhs_stage form 5 momentum products (T_ij - delta_ij T_zz) instead
+ *   of 6 -- the difference is a pressure, removed by the solenoidal projection mode by mode -- i.e. one forward transform fewer per
+ *   evaluation; same derivative to the rounding of the projection (1e-16); the slab-decomposed phases always form 6;
  * "strided_two" = 0/1/2: the y / z passes of lengths 256 and 512 on plain rows run as two register butterflies (16 x 16, 16 x 32)
  *   around one trip through shared memory (csrc/fast_two.cuh; 1 = stage-0 twiddles generated in registers, the default; 2 = loaded
  *   from the table) or as the three radix-8 stages of strided_fast (0); the slab-decomposed passes always take the latter;

@@ -293,6 +293,7 @@ static void check(int n) {
     ddl_set_option("fast_kernels", 1);
     for (int v = 0; v <= 15; ++v) {
         if (!(g_vmask >> v & 1)) continue;
+        ddl_set_option("traceless_flux", v == 0);       // the launch variants exist for the six-product policies only
         ddl_set_option("xfused_variant", v);
         for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
         dzero(P.dout, 16);
@@ -308,6 +309,7 @@ static void check(int n) {
         }
     }
     ddl_set_option("xfused_variant", g_variant);
+    ddl_set_option("traceless_flux", 1);
     for (int tv = 1; tv <= 2; ++tv) {
         // the y / z passes as two register butterflies around one trip through shared memory (csrc/fast_two.cuh)
         ddl_set_option("strided_two", tv);
@@ -318,6 +320,16 @@ static void check(int n) {
         verdict(label, g_quick == 1 ? invariants_diff(P, P.deriv, P.deriv2) : max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
     }
     ddl_set_option("strided_two", g_strided_two);
+    {
+        // six momentum products instead of the default five (traceless flux, csrc/physics_ops.cuh): same derivative to round-off
+        ddl_set_option("traceless_flux", 0);
+        for (int c = 0; c < 6; ++c) dzero(P.deriv[c], nk * 16);
+        DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, DDL_RHS_ZERO_FILL, nullptr));
+        dsync();
+        verdict(g_quick == 1 ? "traceless_flux 0 vs generic tile kernels, traceless (24 sums)" : "traceless_flux 0 vs generic tile kernels, traceless (rel L2)",
+                g_quick == 1 ? invariants_diff(P, P.deriv, P.deriv2) : max_rel_diff(P, P.deriv, P.deriv2), 1e-12);
+        ddl_set_option("traceless_flux", 1);
+    }
     for (int chunk : {1, 3}) {
         if (g_quick) break;
         ddl_set_option("rhs_plane_chunk", chunk);
@@ -485,6 +497,7 @@ static void timing(int n, int reps) {
     say("== timing: MHD %d^3 (CUDA events, ms per call, best of %d after 1 warm-up)\n", n, reps);
     Problem P(n, false);
     Timer t;
+    ddl_set_option("traceless_flux", 0);       // the x-pass launch variants: six-product policies, like the earlier records of this sweep
     for (int v = 0; v <= 15; ++v) {
         if (!(g_vmask >> v & 1)) continue;
         ddl_set_option("xfused_variant", v);
@@ -504,6 +517,7 @@ static void timing(int n, int reps) {
         say("  ddl_rhs, x-pass variant %d: %.3f ms   %.40s\n", v, best, xf ? xf : "");
     }
     ddl_set_option("xfused_variant", g_variant);
+    ddl_set_option("traceless_flux", 1);
     for (int tv = 0; tv <= 2; ++tv) {
         ddl_set_option("strided_two", tv);
         double best = 1e30;
@@ -521,6 +535,23 @@ static void timing(int n, int reps) {
         say("  ddl_rhs, strided_two %d: %.3f ms   %s\n", tv, best, pbuf2);
     }
     ddl_set_option("strided_two", g_strided_two);
+    for (int tf = 0; tf <= 1; ++tf) {
+        ddl_set_option("traceless_flux", tf);
+        double best = 1e30;
+        for (int r = 0; r <= reps; ++r) {
+            t.start();
+            DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
+            const double ms = t.stop_ms();
+            if (r > 0 && ms < best) best = ms;
+        }
+        ddl_profile_enable(1);
+        DDL(ddl_rhs(P.plan, DDL_MHD, &P.prm, P.state, P.deriv, P.work, P.work_bytes, 0, nullptr));
+        static char pbuf3[1 << 14];
+        DDL(ddl_profile_report(pbuf3, sizeof pbuf3));
+        ddl_profile_enable(0);
+        say("  ddl_rhs, traceless_flux %d (%d product fields): %.3f ms   %s\n", tf, tf ? 8 : 9, best, pbuf3);
+    }
+    ddl_set_option("traceless_flux", 1);
     // opt-in L2-residency experiment: y_inv -> x -> y_fwd over chunks of z-planes (include/ddl.h "rhs_plane_chunk")
     for (int chunk : {1, 2, 4, 8}) {
         if (g_quick) break;

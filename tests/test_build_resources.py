@@ -47,4 +47,4 @@ def test_every_kernel_fits_its_largest_launch():
 
 def test_runtime_length_kernels_are_built():
     names = [n for n, _, _ in _entries() if n.startswith("ddl::tile_kernel<0,")]
-    assert len(names) == 16, names          # C2C fwd / inv, C2R, R2C and the twelve fused physics policies
+    assert len(names) == 19, names          # C2C fwd / inv, C2R, R2C and the fifteen fused physics policies (six solenoidal, six advective, three traceless-flux)

@@ -504,9 +504,10 @@ def test_opt_in_async_staging_kernels_reproduce_the_default_ones(shape):
             c["kspace"]
         f.div_free()
     out = {}
-    defaults = {"strided_two": 1}
+    defaults = {"strided_two": 1, "traceless_flux": 1}
+    six = {"traceless_flux": 0}        # the x-pass launch variants exist for the six-product policies (csrc/tile_inst.cu)
     for tag, opts in (("default", {}), ("three_stage", {"strided_two": 0}), ("staged", {"strided_staged": 1}),
-                      ("persist", {"xfused_variant": 4}), ("rot", {"xfused_variant": 5})):
+                      ("persist", dict(six, xfused_variant=4)), ("rot", dict(six, xfused_variant=5))):
         for k, v in opts.items():
             L.set_option(k, v)
         try:

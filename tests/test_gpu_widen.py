@@ -488,6 +488,7 @@ def test_xfused_launch_variants_agree(physics, shape):
     y0 = orc.synthetic_ic(Po, 5).kvector()
     out = []
     try:
+        L.set_option("traceless_flux", 0)          # the launch variants belong to the six-product policies
         for v in (0, 1, 2, 3, 6, 8):
             L.set_option("xfused_variant", v)
             P = dev_physics(physics, shape, None, params)
@@ -497,8 +498,49 @@ def test_xfused_launch_variants_agree(physics, shape):
             out.append(get_state(deriv))
     finally:
         L.set_option("xfused_variant", 0)
+        L.set_option("traceless_flux", 1)
     for o in out[1:]:
         assert rel(o, out[0]) < 1e-14
+
+
+@pytest.mark.parametrize("physics,shape,params", [("IncompressibleHydro", (16, 24, 32), dict(nu=1e-3)), ("BoussinesqHydro", (32, 16, 16), dict(nu=1e-3, kappa=2e-3)),
+                                                  ("IncompressibleMHD", (32, 32, 32), dict(nu=1e-3, eta=2e-3)), ("IncompressibleMHD", (16, 16, 128), dict(nu=1e-3, eta=2e-3)),
+                                                  ("BoussinesqHydro", (16, 256, 128), dict(nu=1e-3, kappa=2e-3)), ("IncompressibleHydro", (8, 16, 512), dict(nu=1e-3))])
+def test_traceless_flux_policies_agree(physics, shape, params):
+    """ddl_set_option("traceless_flux", 1) (the default): the one-rank 3-D RHS forms 5 momentum products, T_ij - delta_ij T_zz,
+    instead of 6 -- the part taken out is a pressure, which the solenoidal projection annihilates mode by mode
+    (csrc/physics_ops.cuh Hydro3T / Bouss3T / MHD3T): one forward transform fewer through the x pass, the forward y / z passes and
+    the assembly.  Same derivative as the six-product policies and as the oracle to the rounding of the projection, for the plain
+    RHS, for the RHS with the CFL capture, and through three RK4 steps (fused stages)."""
+    import dedalus._lib as L
+    import dedalus.time_stepping.api as tapi
+    import dedalus_oracle as orc
+    Po = oracle_physics(physics, shape, None, params)
+    do = orc.synthetic_ic(Po, 5)
+    y0 = do.kvector()
+    ko = Po.create_fields(0.)
+    Po.RHS(do, ko)
+    ref = ko.kvector()
+    rhs, stepped, dts = [], [], []
+    try:
+        for v in (0, 1):
+            L.set_option("traceless_flux", v)
+            P = dev_physics(physics, shape, None, params)
+            data, deriv = P.create_fields(0.), P.create_fields(0.)
+            set_state(data, y0)
+            P.RHS(data, deriv)
+            rhs.append(get_state(deriv))
+            dts.append(float(P.compute_dt(data)))
+            ti = tapi.RK4(P)
+            for _ in range(3):
+                ti.do_advance(data, 1e-3)
+            stepped.append(get_state(data))
+    finally:
+        L.set_option("traceless_flux", 1)
+    assert np.isfinite(rhs[1]).all() and np.isfinite(stepped[1]).all()
+    assert rel(rhs[1], rhs[0]) < 1e-14 and rel(rhs[1], ref) < 1e-13 and rel(rhs[0], ref) < 1e-13
+    assert rel(stepped[1], stepped[0]) < 1e-14
+    assert abs(dts[1] - dts[0]) <= 1e-14 * abs(dts[0])
 
 
 @pytest.mark.parametrize("physics,shape", [("IncompressibleMHD", (256, 16, 16)), ("IncompressibleHydro", (16, 256, 16)), ("BoussinesqHydro", (512, 8, 16)),
